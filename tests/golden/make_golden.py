@@ -1,0 +1,223 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by EXECUTING THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference package (`/root/reference/models`) and the shipped DTU
+checkpoint, runs reference functions / modules on seeded inputs and stores inputs + outputs:
+
+    dtu_weights.npz   the 'model' entry of checkpoints/dtu/model_000015.ckpt, fp32, keys without
+                      the DataParallel 'module.' prefix (data fixture; no reference source is copied)
+    stage_kats.npz    known-answer vectors for single operators (differentiable_warping at three
+                      resolution ratios incl. z<=0.01 pixels, ConvGRU, CorrNet, PixelViewWeight,
+                      convex upsample, Update.forward, F.interpolate resamplers)
+    e2e_d8.npz        config 1: 160x128, 2 src views, D=8 (patched as SURVEY 8c), 1 iteration
+    e2e_d32.npz       320x256, 4 src views, D=32 (checkpoint-compatible), 2 iterations
+                      both on the geometrically consistent plane scene, with every intermediate
+                      of IterMVS.forward captured through hooks.
+
+Nothing here is imported by the product package.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+warnings.filterwarnings("ignore")
+
+from models.net import Pipeline  # noqa: E402  (the reference)
+from models import module as ref_module  # noqa: E402
+from models import itermvs as ref_itermvs  # noqa: E402
+
+from itermvs_b200.synthetic import make_sample  # noqa: E402
+
+
+def np32(t):
+    return t.detach().cpu().numpy()
+
+
+def load_reference_model(iteration, num_sample=32, seed=0):
+    m = Pipeline(iteration=iteration, test=True)
+    sd = torch.load(os.path.join(REF, "checkpoints/dtu/model_000015.ckpt"), map_location="cpu")["model"]
+    sd = {k[7:]: v for k, v in sd.items()}
+    extra = {}
+    if num_sample != 32:          # SURVEY.md 8c recipe: D is hard-coded, patch it
+        m.iter_mvs.num_sample = num_sample
+        m.iter_mvs.depth_initialization.num_sample = num_sample
+        torch.manual_seed(seed)
+        m.iter_mvs.update.hidden_init_head[0] = nn.Conv2d(num_sample, 64, 3, stride=1, padding=1, bias=False)
+        key = "iter_mvs.update.hidden_init_head.0.weight"
+        sd = {k: v for k, v in sd.items() if k != key}
+        missing = m.load_state_dict(sd, strict=False)
+        assert missing.missing_keys == [key], missing
+        extra[key] = m.iter_mvs.update.hidden_init_head[0].weight.detach().clone()
+    else:
+        m.load_state_dict(sd, strict=True)
+    m.eval()
+    return m, extra
+
+
+def dump_weights():
+    sd = torch.load(os.path.join(REF, "checkpoints/dtu/model_000015.ckpt"), map_location="cpu")["model"]
+    out = {}
+    for k, v in sd.items():
+        k = k[7:] if k.startswith("module.") else k
+        if k.endswith("num_batches_tracked"):
+            continue
+        out[k] = v.float().numpy()
+    np.savez_compressed(os.path.join(HERE, "dtu_weights.npz"), **out)
+    print("dtu_weights.npz", sum(v.size for v in out.values()), "params")
+
+
+def stage_kats(model):
+    torch.manual_seed(1234)
+    g = {}
+    # ---- differentiable_warping at 3 resolution ratios (module.py:68) ----
+    sample = make_sample(160, 128, n_src=2, batch=1, seed=3, scene="noise")
+    for tag, (lvl_fea, lvl_depth) in {"same": (2, 2), "fea2x": (1, 2), "fea_half": (3, 2)}.items():
+        proj = sample["proj_matrices"][f"level_{lvl_fea}"].float()
+        hd, wd = 128 // 2 ** lvl_depth, 160 // 2 ** lvl_depth
+        hf, wf = 128 // 2 ** lvl_fea, 160 // 2 ** lvl_fea
+        c = {1: 16, 2: 32, 3: 48}[lvl_fea]
+        fea = torch.randn(1, c, hf, wf)
+        depth = 425 + (935 - 425) * torch.rand(1, 5, hd, wd)
+        depth[:, 0, :3] = -50.0          # behind the camera -> z <= 0.01 substitution branch
+        depth[:, 1, 5:7] = 1e-4
+        src_proj = proj[:, 2].clone()
+        ref_proj = proj[:, 0].clone()
+        out = ref_module.differentiable_warping(fea, src_proj, ref_proj, depth)
+        g[f"warp_{tag}_fea"] = np32(fea)
+        g[f"warp_{tag}_src_proj"] = np32(src_proj)
+        g[f"warp_{tag}_ref_proj"] = np32(ref_proj)
+        g[f"warp_{tag}_depth"] = np32(depth)
+        g[f"warp_{tag}_out"] = np32(out)
+    # batch == 2 branch (module.py:78-84)
+    fea = torch.randn(2, 16, 16, 20)
+    proj = sample["proj_matrices"]["level_3"].float().repeat(2, 1, 1, 1)
+    proj[1, 1, :3, 3] += torch.tensor([3.0, -2.0, 5.0])
+    depth = 425 + (935 - 425) * torch.rand(2, 3, 16, 20)
+    g["warp_b2_fea"], g["warp_b2_depth"] = np32(fea), np32(depth)
+    g["warp_b2_src_proj"], g["warp_b2_ref_proj"] = np32(proj[:, 1]), np32(proj[:, 0])
+    g["warp_b2_out"] = np32(ref_module.differentiable_warping(fea, proj[:, 1], proj[:, 0], depth))
+
+    upd = model.iter_mvs.update
+    ev = model.iter_mvs.evaluation
+    with torch.no_grad():
+        # ---- ConvGRU (module.py:59) ----
+        h = torch.tanh(torch.randn(1, 32, 12, 20))
+        x = torch.randn(1, 11, 12, 20) * 0.5
+        g["gru_h"], g["gru_x"], g["gru_out"] = np32(h), np32(x), np32(upd.gru(h, x))
+        # ---- CorrNet x3 (itermvs.py:367) ----
+        c = torch.randn(1, 8, 3, 32, 32) * 0.3
+        g["corrnet_in"] = np32(c)
+        for i in range(3):
+            g[f"corrnet{i}_out"] = np32(ev.corr_conv1[i](c))
+        # ---- PixelViewWeight (itermvs.py:341) ----
+        c = torch.randn(2, 8, 6, 8, 12) * 0.5
+        g["pvw_in"], g["pvw_out"] = np32(c), np32(ev.pixel_view_weight(c))
+        # ---- hidden_init / heads ----
+        c = torch.randn(1, 32, 8, 12)
+        g["hinit_in"], g["hinit_out"] = np32(c), np32(upd.hidden_init(c))
+        g["head_logits"] = np32(upd.depth_head(h))
+        g["conf_logit"] = np32(upd.confidence_head(h))
+        # ---- regression on a peaked distribution (well-posed arg-max) ----
+        logits = torch.randn(1, 256, 6, 10)
+        peak = torch.randint(0, 256, (1, 1, 6, 10))
+        peak[0, 0, 0, :4] = torch.tensor([0, 1, 254, 255])      # window clamping at both ends
+        logits.scatter_(1, peak, 12.0)
+        logits.scatter_add_(1, (peak + 1).clamp(max=255), torch.full_like(peak, 9.0, dtype=torch.float32))
+        prob = torch.softmax(logits, dim=1)
+        # replay itermvs.py:203-219 through the reference's own depth_init on a stub head
+        class _Stub(nn.Module):
+            def forward(self, _):
+                return logits
+        saved = upd.depth_head
+        upd.depth_head = _Stub()
+        nd, p = upd.depth_init(torch.zeros(1, 32, 6, 10))
+        upd.depth_head = saved
+        g["regress_logits"], g["regress_nd"], g["regress_prob"] = np32(logits), np32(nd), np32(p)
+        # ---- convex upsample (module.py:127) ----
+        x = torch.rand(1, 1, 6, 10)
+        w = torch.softmax(torch.randn(1, 1, 9, 4, 4, 6, 10), dim=2)
+        g["upsample_x"], g["upsample_w"], g["upsample_out"] = np32(x), np32(w), np32(ref_module.upsample(x, w))
+        # ---- F.interpolate semantics the estimator relies on ----
+        x = torch.randn(1, 3, 6, 10)
+        g["interp_in"] = np32(x)
+        g["interp_up2"] = np32(torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear"))
+        g["interp_up4"] = np32(torch.nn.functional.interpolate(x, scale_factor=4, mode="bilinear"))
+        g["interp_half"] = np32(torch.nn.functional.interpolate(x, scale_factor=0.5, mode="bilinear"))
+    np.savez_compressed(os.path.join(HERE, "stage_kats.npz"), **g)
+    print("stage_kats.npz", len(g), "arrays")
+
+
+def run_e2e(name, width, height, n_src, num_sample, iteration, seed):
+    model, extra = load_reference_model(iteration, num_sample)
+    sample = make_sample(width, height, n_src=n_src, batch=1, seed=seed, scene="plane")
+    rec = {"eval_out": [], "update_out": [], "hidden0": None, "nd0": None}
+    im = model.iter_mvs
+
+    h1 = im.evaluation.register_forward_hook(lambda m, i, o: rec["eval_out"].append(o))
+    h2 = im.update.register_forward_hook(lambda m, i, o: rec["update_out"].append(o))
+    orig_hidden_init, orig_depth_init = im.update.hidden_init, im.update.depth_init
+
+    def hidden_init(corr):
+        out = orig_hidden_init(corr)
+        rec["hidden0"] = out
+        return out
+
+    def depth_init(hidden):
+        out = orig_depth_init(hidden)
+        rec["nd0"] = out[0]
+        return out
+
+    im.update.hidden_init, im.update.depth_init = hidden_init, depth_init
+    feats = {}
+    h3 = model.feature_net.register_forward_hook(lambda m, i, o: feats.update(o))
+    with torch.no_grad():
+        out = model(sample["imgs"], sample["proj_matrices"], sample["depth_min"], sample["depth_max"])
+    for h in (h1, h2, h3):
+        h.remove()
+    g = {"width": width, "height": height, "n_src": n_src, "num_sample": num_sample, "iteration": iteration,
+         "seed": seed,
+         "depths_upsampled": np32(out["depths_upsampled"]),
+         "confidence_upsampled": np32(out["confidence_upsampled"]),
+         "hidden0": np32(rec["hidden0"]), "nd0": np32(rec["nd0"])}
+    vw, corr_init, depth_initial = rec["eval_out"][0]
+    g["view_weights"], g["corr_init"], g["depth_initial"] = np32(vw), np32(corr_init), np32(depth_initial)
+    for it in range(iteration):
+        g[f"corr_iter{it}"] = np32(rec["eval_out"][1 + it])
+        hidden, nd, prob, conf, conf0 = rec["update_out"][it]
+        g[f"hidden_iter{it}"] = np32(hidden)
+        g[f"nd_iter{it}"] = np32(nd)
+        if conf is not None:
+            g["confidence"] = np32(conf)
+    for lvl in ("level2", "level3"):
+        g[f"ref_{lvl}"] = np32(feats[lvl][0])
+    g["src0_level3"] = np32(feats["level3"][1])
+    for k, v in extra.items():
+        g["extra:" + k] = np32(v)
+    # images are regenerated from the seed in the tests; keep a checksum to detect generator drift
+    g["img_checksum"] = np.array([float(sample["imgs"]["level_0"].double().sum()),
+                                  float(sample["imgs"]["level_0"].double().abs().sum())])
+    np.savez_compressed(os.path.join(HERE, name), **g)
+    d = out["depths_upsampled"]
+    print(name, "depth range", float(d.min()), float(d.max()), "mean conf", float(out["confidence_upsampled"].mean()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    dump_weights()
+    model, _ = load_reference_model(iteration=1)
+    stage_kats(model)
+    run_e2e("e2e_d8.npz", 160, 128, n_src=2, num_sample=8, iteration=1, seed=0)
+    run_e2e("e2e_d32.npz", 320, 256, n_src=4, num_sample=32, iteration=2, seed=1)
