@@ -1,0 +1,206 @@
+/*
+ * itermvs_b200 -- C ABI of the B200 (sm_100a) implementation of the IterMVS hot path.
+ *
+ * The reference (FangjinhuaWang/IterMVS @ 453e9c7) is pure Python/PyTorch and has no FFI; its
+ * boundary is the Python call surface of models/module.py, models/itermvs.py and models/net.py.
+ * Each entry point below replaces one stock ATen/cuDNN call chain of that surface; the comment
+ * on every function names the reference lines it stands in for.  The Python binding a
+ * maintainer would add is shown in INTEGRATION.md (ctypes, exactly what itermvs_b200/_lib.py does).
+ *
+ * Conventions
+ *   - plain C: device pointers to dense fp32 buffers, int shapes, a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on error; imvs_last_error() gives the text
+ *     (thread-local).  Nothing synchronises, allocates or frees device memory: the caller owns all
+ *     buffers (outputs and scratch included), so every call is CUDA-graph capturable.
+ *   - the library uses the caller's CURRENT device; re-entrant across host threads.
+ *
+ * Layouts  ("P_l" = H_l*W_l, level 1 = 1/2 res C=16, level 2 = 1/4 res C=32, level 3 = 1/8 res C=48)
+ *   feature pyramids     [B][V][H_l][W_l][C_l]   channels-last, view 0 = reference view
+ *   projection matrices  [B][V][4][4]            row-major, as produced by the reference loaders
+ *   composed projections [B][S][12]              rot (3x3 row-major) then trans (3)
+ *   correlation volumes  [B][slice][P][8]        8 = group-wise correlation channels, innermost
+ *   maps / activations   [B][C][H][W]            planar (the reference's NCHW)
+ *   conv weights         [Cin][k*k][Cout]        (packed by itermvs_b200/_pack.py from state_dict)
+ */
+#ifndef ITERMVS_B200_H_
+#define ITERMVS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMVS_ABI_VERSION 1
+#define IMVS_GROUPS 8          /* reference models/itermvs.py:28 */
+#define IMVS_OUT_BINS 256      /* reference models/itermvs.py:134 */
+#define IMVS_RADIUS 4          /* reference models/itermvs.py:135 */
+#define IMVS_HIDDEN 32         /* reference models/net.py:72 */
+#define IMVS_ITER_SLICES 10    /* 4 + 4 + 2 refinement samples, models/itermvs.py:231-235 */
+#define IMVS_MAX_VIEWS 16      /* source views per reference view supported by the fused kernels */
+
+int imvs_abi_version(void);
+const char* imvs_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Weights of the estimator, already packed to [Cin][k*k][Cout] (transposed convs: [Cin][9][Cout]),
+ * biases dense.  Key names are the reference's state_dict keys.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */
+    const float* conv0;    /* conv0.conv.weight  8 -> 8            */
+    const float* conv1;    /* conv1.conv.weight  8 -> 16, stride 2 */
+    const float* conv2;    /* conv2.conv.weight 16 -> 32, stride 2 */
+    const float* conv3;    /* conv3.weight      32 -> 16, transposed stride 2 */
+    const float* conv4;    /* conv4.weight      16 -> 8,  transposed stride 2 */
+    const float* conv5;    /* conv5.weight       8 -> 1   */
+    const float* conv5_b;  /* conv5.bias [1]              */
+} imvs_corrnet_weights;
+
+typedef struct imvs_weights {
+    /* evaluation.pixel_view_weight (models/itermvs.py:333-350) */
+    const float* pvw_conv0;        /* conv.0.conv.weight 8 -> 16 */
+    const float* pvw_conv1;        /* conv.1.weight [16] */
+    const float* pvw_conv1_b;      /* conv.1.bias [1] */
+    /* evaluation.corr_conv1[0..2] (level 1, 2, 3) */
+    imvs_corrnet_weights corrnet[3];
+    /* update.gru (models/module.py:52-66): convz|convr stacked on Cout (64), convq (32) */
+    const float* gru_zr;           /* [43][9][64] */
+    const float* gru_zr_b;         /* [64] */
+    const float* gru_q;            /* [43][9][32] */
+    const float* gru_q_b;          /* [32] */
+    /* update.depth_head.0 | update.confidence_head.0 stacked on Cout (64) (itermvs.py:139-151) */
+    const float* head_conv0;       /* [32][9][64] : cout 0..31 depth head, 32..63 confidence head */
+    const float* head_fc1;         /* depth_head.2.weight  [32][64] */
+    const float* head_fc2;         /* depth_head.4.weight  [64][256] */
+    const float* head_fc2_b;       /* depth_head.4.bias    [256] */
+    const float* conf_fc;          /* confidence_head.2.weight [32] */
+    const float* conf_fc_b;        /* confidence_head.2.bias [1] */
+    /* update.hidden_init_head (itermvs.py:153-157) */
+    const float* hinit_conv0;      /* [D][9][64] */
+    const float* hinit_fc;         /* [64][32] */
+    const float* hinit_fc_b;       /* [32] */
+    /* iter_mvs.upsample (itermvs.py:246-250) */
+    const float* ups_conv0;        /* [32][9][64] */
+    const float* ups_fc;           /* [64][144] */
+} imvs_weights;
+
+/* ------------------------------------------------------------------------------------------
+ * Single operators (drop-in for the reference's module-level functions / modules)
+ * ---------------------------------------------------------------------------------------- */
+
+/* module.py:78-90 -- proj = src_proj @ inverse(ref_proj), rot/trans split, for every source view.
+ * proj: [B][V][4][4] (view 0 = reference).  out: [B][V-1][12].  nan_flag (device int, may be NULL)
+ * is set to 1 if a composed matrix contains NaN (the reference asserts, module.py:83,87). */
+int imvs_compose_projections(const float* proj, int B, int V, float* out, int* nan_flag, void* stream);
+
+/* module.py:68-125 -- differentiable_warping, the reference's own layouts:
+ * src_fea [B][C][H1][W1], src_proj/ref_proj [B][4][4], depth_samples [B][D][H][W] -> out [B][C][D][H][W].
+ * rt_scratch: B*12 floats (receives the composed rot|trans). */
+int imvs_differentiable_warping(const float* src_fea, const float* src_proj, const float* ref_proj,
+                                const float* depth_samples, float* out, int B, int C, int H1, int W1,
+                                int D, int H, int W, float* rt_scratch, int* nan_flag, void* stream);
+
+/* layout helpers: [N][C][H][W] <-> [N][H][W][C] */
+int imvs_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, void* stream);
+int imvs_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, void* stream);
+
+/* itermvs.py:11-19 + 45-51 -- fused plane sweep at level 3: generates the D inverse-depth
+ * hypotheses, warps + bilinearly samples every source view and writes the group-wise correlation
+ * per view.  fea3 [B][V][H3][W3][48], rt3 [B][S][12], out corr [B][S][D][P3][8].
+ * depth_samples: NULL (hypotheses generated in-kernel from depth_min/max [B], the estimator's path)
+ * or explicit [B][D][P3] hypotheses (Evaluation.forward's depth_sample argument, itermvs.py:33). */
+int imvs_warpcorr_init(const float* fea3, const float* rt3, const float* depth_min, const float* depth_max,
+                       const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream);
+
+/* itermvs.py:341-350 + 53-57 -- PixelViewWeight on every (view, hypothesis) slice, softmax over D,
+ * max over D, and the x2 bilinear upsampling.  corr [B][S][D][P3][8];
+ * logits scratch [B][S][D][P3]; vw3 [B][S][P3]; vw2 [B][S][4*P3]. */
+int imvs_pixel_view_weight(const imvs_weights* w, const float* corr, float* logits, float* vw3, float* vw2,
+                           int B, int S, int D, int H3, int W3, void* stream);
+
+/* itermvs.py:59-69 -- view-weighted aggregation of the init volume: agg [B][D][P3][8]. */
+int imvs_aggregate_init(const float* corr, const float* vw3, float* agg, int B, int S, int D, int P3, void* stream);
+
+/* itermvs.py:289-293 + 86-120 -- fused iteration kernel: hypotheses from the normalized depth,
+ * warp + sample of the three pyramids, group-wise correlation, pixel-wise view-weighted
+ * aggregation.  nd [B][nd_stride] (first P2 entries used), vw2 [B][S][P2]; agg [B][10][P2][8]
+ * (slices 0-3 level 1, 4-7 level 2, 8-9 level 3).  samples1/2/3: all NULL (hypotheses from nd) or all
+ * given as explicit depths [B][4][P2], [B][4][P2], [B][2][P2] (Evaluation.forward's dict argument). */
+int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
+                       const float* rt1, const float* rt2, const float* rt3,
+                       const float* nd, size_t nd_batch_stride, const float* vw2,
+                       const float* depth_min, const float* depth_max,
+                       const float* samples1, const float* samples2, const float* samples3, float* agg,
+                       int B, int V, int H2, int W2, void* stream);
+
+/* itermvs.py:367-381 -- CorrNet on N slices of a [N][P][8] volume.  Slice n uses weight set
+ * sets[(n % period) < split1 ? 0 : (n % period) < split2 ? 1 : 2].  out[(n / period) * out_batch_stride
+ * + (n % period) * H*W + p].  scratch: imvs_corrnet_scratch_floats(N,H,W) floats. */
+size_t imvs_corrnet_scratch_floats(int N, int H, int W);
+int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int split1, int split2, const float* vol,
+                 float* out, size_t out_batch_stride, float* scratch, int N, int H, int W, void* stream);
+
+/* itermvs.py:159-164 -- hidden_init: corr [B][D][H3][W3] -> hidden [B][32][2*H3][2*W3].
+ * scratch: B*(64+32)*H3*W3 floats. */
+int imvs_hidden_init(const imvs_weights* w, const float* corr, float* hidden, float* scratch,
+                     int B, int D, int H3, int W3, void* stream);
+
+/* module.py:59-66 -- ConvGRU.forward(h, x) with x = 11 channels (itermvs.py:193), in place on h.
+ * h [B][32][H][W], x [B][11][H][W]; scratch 2*B*32*H*W floats (z and r*h). */
+int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, float* scratch, int B, int H, int W, void* stream);
+
+/* itermvs.py:171-190 / 196-219 -- depth_head (+ confidence_head when conf != NULL), softmax over
+ * 256 bins, arg-max, clamped +-4 window regression.  hidden [B][32][H][W].
+ *   nd_out        [B][nd_batch_stride]  normalized depth (first H*W entries of each batch written)
+ *   probability   [B][256][H][W] or NULL (training needs it, itermvs.py:282,302)
+ *   conf / conf_logit [B][H][W] or NULL (sigmoid / raw)
+ *   depth_out     [B][H][W] or NULL: depth_unnormalization of nd_out (module.py:148-152)
+ * scratch: B*64*H*W floats. */
+int imvs_depth_head(const imvs_weights* w, const float* hidden, float* nd_out, size_t nd_batch_stride,
+                    float* probability, float* conf, float* conf_logit, float* depth_out,
+                    const float* depth_min, const float* depth_max, float* scratch,
+                    int B, int H, int W, void* stream);
+
+/* itermvs.py:262-264 + module.py:127-140 + itermvs.py:321-324 -- output stage: upsampling-weight
+ * net on the level-2 reference feature (planar [B][32][H2][W2]), softmax over the 9 taps, convex
+ * x4 upsampling of nd, depth_unnormalization; bilinear x4 of the confidence.
+ * depth_up / conf_up [B][4*H2][4*W2]; conf may be NULL (then conf_up is not written).
+ * scratch: B*64*H2*W2 floats. */
+int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea2_planar, const float* nd,
+                          size_t nd_batch_stride, const float* conf, const float* depth_min,
+                          const float* depth_max, float* depth_up, float* conf_up, float* scratch,
+                          int B, int H2, int W2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole estimator: IterMVS.forward in test mode (itermvs.py:253-329), one call = all launches.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct imvs_problem {
+    int B;            /* reference views in this call */
+    int V;            /* views per reference view (1 + source views) */
+    int H, W;         /* full-resolution image size, multiples of 32 */
+    int D;            /* initial hypotheses (32 in the reference, itermvs.py:237) */
+    int iterations;   /* GRU iterations (>= 1) */
+} imvs_problem;
+
+size_t imvs_forward_workspace_bytes(const imvs_problem* pb);
+
+/* fea1/2/3: channels-last pyramids [B][V][H_l][W_l][C_l]; ref_fea2_planar [B][32][H2][W2];
+ * proj1/2/3: [B][V][4][4] fp32.  Outputs (any may be NULL): depth [B][H2][W2] (pre-last-update value,
+ * itermvs.py:319), depth_up [B][H][W], conf [B][H2][W2], conf_up [B][H][W].
+ * nan_flag: device int, set to 1 on NaN projections (checked by the caller when it next syncs). */
+int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,
+                         const float* fea1, const float* fea2, const float* fea3, const float* ref_fea2_planar,
+                         const float* proj1, const float* proj2, const float* proj3,
+                         const float* depth_min, const float* depth_max,
+                         void* workspace, size_t workspace_bytes,
+                         float* depth, float* depth_up, float* conf, float* conf_up,
+                         int* nan_flag, void* stream);
+
+/* number of kernel launches one imvs_itermvs_forward issues for this problem (for bench.py's gpu_launches) */
+int imvs_forward_launch_count(const imvs_problem* pb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITERMVS_B200_H_ */

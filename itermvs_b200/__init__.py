@@ -1,0 +1,20 @@
+"""itermvs_b200 -- B200 (sm_100a) implementation of the IterMVS hot path behind the reference's
+own Python call surface (models/module.py, models/itermvs.py, models/net.py).
+
+    from itermvs_b200 import Pipeline
+    model = Pipeline(iteration=4, test=True).cuda().eval()
+    model.load_state_dict(torch.load(ckpt)["model"])          # reference checkpoints load as-is
+    out = model(imgs, proj_matrices, depth_min, depth_max)     # {"depths_upsampled", "confidence_upsampled"}
+
+All compute runs in hand-written CUDA kernels (itermvs_b200/csrc) bound through the C ABI declared
+in include/itermvs_b200.h.  There is no CPU fallback.
+"""
+from .ops import (differentiable_warping, depth_normalization, depth_unnormalization, upsample,  # noqa: F401
+                  compose_projections, nchw_to_nhwc, nhwc_to_nchw)
+from .estimator import (ConvGRU, CorrNet, DepthInitialization, Evaluation, IterMVS, PixelViewWeight,  # noqa: F401
+                        Update)
+from .pipeline import FeatureNet, Pipeline, full_loss  # noqa: F401
+
+__all__ = ["Pipeline", "FeatureNet", "IterMVS", "Evaluation", "Update", "ConvGRU", "CorrNet", "PixelViewWeight",
+           "DepthInitialization", "differentiable_warping", "depth_normalization", "depth_unnormalization", "upsample",
+           "compose_projections", "nchw_to_nhwc", "nhwc_to_nchw", "full_loss"]

@@ -1,0 +1,70 @@
+// Shared helpers for the sm_100a kernels of itermvs_b200 (host-side error plumbing + device utils).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+#include "../../include/itermvs_b200.h"
+
+namespace imvs {
+
+// ---- thread-local error text -------------------------------------------------------------
+char* err_buf();
+int fail(const char* fmt, ...);
+
+#define IMVS_REQUIRE(cond, ...)                                 \
+    do {                                                        \
+        if (!(cond)) return ::imvs::fail(__VA_ARGS__);          \
+    } while (0)
+
+#define IMVS_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return ::imvs::fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define IMVS_LAUNCH_CHECK(name)                                                               \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess)                                                               \
+            return ::imvs::fail("launch of %s failed: %s", name, cudaGetErrorString(e__));     \
+    } while (0)
+
+#define IMVS_TRY(expr)              \
+    do {                            \
+        int rc__ = (expr);          \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// launch counter (bench.py reports gpu_launches); bumped by every host-side launch helper
+void count_launch(int n = 1);
+long long launches_total();
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// F.interpolate(scale_factor=f, mode='bilinear', align_corners=False) source index (ATen
+// area_pixel_compute_source_index): src = (dst + 0.5) / f - 0.5, clamped below at 0.
+__device__ __forceinline__ void up_index(int dst, float inv_scale, int n, int& i0, int& i1, float& lam) {
+    float src = inv_scale * (dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    i1 = i0 + (i0 < n - 1 ? 1 : 0);
+    lam = src - (float)i0;
+}
+
+// inverse-depth parametrisation, module.py:148-152
+__device__ __forceinline__ float unnormalize_depth(float nd, float inv_min, float inv_max) {
+    return 1.0f / (inv_max + nd * (inv_min - inv_max));
+}
+
+}  // namespace imvs

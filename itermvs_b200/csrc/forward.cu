@@ -1,0 +1,133 @@
+// IterMVS.forward in test mode (reference models/itermvs.py:253-329) as one host call that
+// enqueues every kernel of the hot path on the caller's stream.  No allocation, no sync: the
+// caller provides the workspace, so the whole call is CUDA-graph capturable.
+#include "common.cuh"
+
+namespace imvs {
+
+struct Workspace {
+    float *rt1, *rt2, *rt3;
+    float *corr_init, *pvw_logits, *vw3, *vw2, *agg_init, *corrnet_scratch, *corr0;
+    float *hinit_scratch, *hidden, *xbuf, *agg_iter, *gru_scratch, *head_scratch, *ups_scratch, *conf_buf;
+    size_t total_floats;
+};
+
+static size_t take(size_t& cursor, size_t n) {
+    size_t at = cursor;
+    cursor += (n + 63) / 64 * 64;      // 256-byte granules keep every buffer float4-aligned
+    return at;
+}
+
+static Workspace carve(const imvs_problem& pb, float* base) {
+    const size_t B = pb.B, S = pb.V - 1, D = pb.D;
+    const size_t P2 = (size_t)(pb.H / 4) * (pb.W / 4), P3 = (size_t)(pb.H / 8) * (pb.W / 8);
+    size_t c = 0;
+    Workspace w;
+    auto at = [&](size_t n) { return base + take(c, n); };
+    w.rt1 = at(B * S * 12);
+    w.rt2 = at(B * S * 12);
+    w.rt3 = at(B * S * 12);
+    w.corr_init = at(B * S * D * P3 * 8);
+    w.pvw_logits = at(B * S * D * P3);
+    w.vw3 = at(B * S * P3);
+    w.vw2 = at(B * S * P2);
+    w.agg_init = at(B * D * P3 * 8);
+    size_t cn = B * D * P3 * 26, ci = B * IMVS_ITER_SLICES * P2 * 26;
+    w.corrnet_scratch = at(cn > ci ? cn : ci);
+    w.corr0 = at(B * D * P3);
+    w.hinit_scratch = at(B * 96 * P3);
+    w.hidden = at(B * 32 * P2);
+    w.xbuf = at(B * 11 * P2);
+    w.agg_iter = at(B * IMVS_ITER_SLICES * P2 * 8);
+    w.gru_scratch = at(B * 64 * P2);
+    w.head_scratch = at(B * 64 * P2);
+    w.ups_scratch = at(B * 64 * P2);
+    w.conf_buf = at(B * P2);
+    w.total_floats = c;
+    return w;
+}
+
+static int check_problem(const imvs_problem* pb) {
+    IMVS_REQUIRE(pb, "null problem");
+    IMVS_REQUIRE(pb->B >= 1, "B=%d", pb->B);
+    IMVS_REQUIRE(pb->V >= 2 && pb->V - 1 <= IMVS_MAX_VIEWS, "need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, pb->V);
+    IMVS_REQUIRE(pb->H >= 32 && pb->W >= 32 && pb->H % 32 == 0 && pb->W % 32 == 0,
+                 "H and W must be multiples of 32 (H=%d W=%d): CorrNet halves the 1/8-resolution map twice", pb->H, pb->W);
+    IMVS_REQUIRE(pb->D >= 2, "D=%d", pb->D);
+    IMVS_REQUIRE(pb->iterations >= 1, "iterations=%d", pb->iterations);
+    return 0;
+}
+
+}  // namespace imvs
+
+using namespace imvs;
+
+extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
+    if (check_problem(pb) != 0) return 0;
+    return carve(*pb, nullptr).total_floats * sizeof(float);
+}
+
+extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
+    if (check_problem(pb) != 0) return -1;
+    return 22 + 11 * pb->iterations;
+}
+
+extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,
+                                    const float* fea1, const float* fea2, const float* fea3, const float* ref_fea2_planar,
+                                    const float* proj1, const float* proj2, const float* proj3,
+                                    const float* depth_min, const float* depth_max,
+                                    void* workspace, size_t workspace_bytes,
+                                    float* depth, float* depth_up, float* conf, float* conf_up,
+                                    int* nan_flag, void* stream) {
+    IMVS_TRY(check_problem(pb));
+    IMVS_REQUIRE(w && fea1 && fea2 && fea3 && ref_fea2_planar && proj1 && proj2 && proj3 && depth_min && depth_max && workspace,
+                 "itermvs_forward: null pointer");
+    IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "itermvs_forward: workspace must be 256-byte aligned");
+    Workspace ws = carve(*pb, static_cast<float*>(workspace));
+    IMVS_REQUIRE(workspace_bytes >= ws.total_floats * sizeof(float), "itermvs_forward: workspace too small (%zu < %zu bytes)",
+                 workspace_bytes, ws.total_floats * sizeof(float));
+    const int B = pb->B, V = pb->V, S = V - 1, D = pb->D, I = pb->iterations;
+    const int H2 = pb->H / 4, W2 = pb->W / 4, H3 = pb->H / 8, W3 = pb->W / 8;
+    const int P2 = H2 * W2, P3 = H3 * W3;
+    const size_t xstride = (size_t)11 * P2;
+
+    // K1 (module.py:78-90), hoisted: once per level instead of once per warp call
+    IMVS_TRY(imvs_compose_projections(proj1, B, V, ws.rt1, nan_flag, stream));
+    IMVS_TRY(imvs_compose_projections(proj2, B, V, ws.rt2, nan_flag, stream));
+    IMVS_TRY(imvs_compose_projections(proj3, B, V, ws.rt3, nan_flag, stream));
+
+    // init evaluation (itermvs.py:270-271, 36-70)
+    IMVS_TRY(imvs_warpcorr_init(fea3, ws.rt3, depth_min, depth_max, nullptr, ws.corr_init, B, V, H3, W3, D, stream));
+    IMVS_TRY(imvs_pixel_view_weight(w, ws.corr_init, ws.pvw_logits, ws.vw3, ws.vw2, B, S, D, H3, W3, stream));
+    IMVS_TRY(imvs_aggregate_init(ws.corr_init, ws.vw3, ws.agg_init, B, S, D, P3, stream));
+    imvs_corrnet_weights init_sets[3] = {w->corrnet[2], w->corrnet[2], w->corrnet[2]};
+    IMVS_TRY(imvs_corrnet(init_sets, D, D, D, ws.agg_init, ws.corr0, (size_t)D * P3, ws.corrnet_scratch, B * D, H3, W3, stream));
+
+    // hidden state and first depth (itermvs.py:275-276)
+    IMVS_TRY(imvs_hidden_init(w, ws.corr0, ws.hidden, ws.hinit_scratch, B, D, H3, W3, stream));
+    IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xstride, nullptr, nullptr, nullptr, (I == 1) ? depth : nullptr,
+                             depth_min, depth_max, ws.head_scratch, B, H2, W2, stream));
+
+    float* conf_q = conf ? conf : ws.conf_buf;
+    for (int it = 0; it < I; ++it) {
+        const bool last = (it == I - 1);
+        // itermvs.py:288-295
+        IMVS_TRY(imvs_warpcorr_iter(fea1, fea2, fea3, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xstride, ws.vw2, depth_min, depth_max,
+                                    nullptr, nullptr, nullptr, ws.agg_iter, B, V, H2, W2, stream));
+        IMVS_TRY(imvs_corrnet(w->corrnet, IMVS_ITER_SLICES, 4, 8, ws.agg_iter, ws.xbuf + P2, xstride, ws.corrnet_scratch,
+                              B * IMVS_ITER_SLICES, H2, W2, stream));
+        // itermvs.py:316-320 -> Update.forward (192-220); x = [normalized_depth, corr] is xbuf itself
+        IMVS_TRY(imvs_conv_gru(w, ws.hidden, ws.xbuf, ws.gru_scratch, B, H2, W2, stream));
+        // `depth` returned in test mode is the value BEFORE the last update (itermvs.py:319)
+        float* depth_here = (!last && it == I - 2) ? depth : nullptr;
+        IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xstride, nullptr, last ? conf_q : nullptr, nullptr, depth_here,
+                                 depth_min, depth_max, ws.head_scratch, B, H2, W2, stream));
+    }
+    // itermvs.py:321-324
+    if (depth_up || conf_up) {
+        IMVS_REQUIRE(depth_up, "itermvs_forward: conf_up requested without depth_up");
+        IMVS_TRY(imvs_upsample_outputs(w, ref_fea2_planar, ws.xbuf, xstride, conf_up ? conf_q : nullptr, depth_min, depth_max,
+                                       depth_up, conf_up, ws.ups_scratch, B, H2, W2, stream));
+    }
+    return 0;
+}

@@ -1,0 +1,197 @@
+// Projection composition, the stand-alone differentiable_warping operator and layout helpers.
+// Reference: models/module.py:68-125 (FangjinhuaWang/IterMVS).
+#include "common.cuh"
+#include "sampling.cuh"
+
+namespace imvs {
+
+thread_local char g_err[512] = {0};
+char* err_buf() { return g_err; }
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launches_total() { return g_launches; }
+
+// ---------------------------------------------------------------------------------------------
+// K1: proj = src_proj @ inverse(ref_proj)  (module.py:78-90).  One thread per (b, source view).
+// Done in fp64 from the fp32 inputs (the reference uses an fp32 LU; both round to the same fp32
+// value up to ~1 ulp of the result) -- 4x4, so cost is irrelevant.
+// ---------------------------------------------------------------------------------------------
+__device__ bool invert4x4(const double* a, double* inv) {
+    double m[4][8];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            m[i][j] = a[i * 4 + j];
+            m[i][4 + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        double best = fabs(m[c][c]);
+        for (int r = c + 1; r < 4; ++r)
+            if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
+        if (piv != c)
+            for (int j = 0; j < 8; ++j) { double t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+        double d = 1.0 / m[c][c];          // singular -> inf/NaN, reported through nan_flag
+        for (int j = 0; j < 8; ++j) m[c][j] *= d;
+        for (int r = 0; r < 4; ++r) {
+            if (r == c) continue;
+            double f = m[r][c];
+            for (int j = 0; j < 8; ++j) m[r][j] -= f * m[c][j];
+        }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) inv[i * 4 + j] = m[i][4 + j];
+    return true;
+}
+
+__device__ void compose_one(const float* ref, const float* src, float* out12, int* nan_flag) {
+    double r[16], s[16], inv[16];
+    for (int i = 0; i < 16; ++i) { r[i] = (double)ref[i]; s[i] = (double)src[i]; }
+    invert4x4(r, inv);
+    bool bad = false;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += s[i * 4 + k] * inv[k * 4 + j];
+            float f = (float)acc;
+            bad |= isnan(f);
+            if (j < 3) out12[i * 3 + j] = f; else out12[9 + i] = f;
+        }
+    }
+    if (bad && nan_flag) atomicExch(nan_flag, 1);
+}
+
+__global__ void compose_kernel(const float* __restrict__ proj, int B, int V, float* __restrict__ out, int* nan_flag) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int S = V - 1;
+    if (t >= B * S) return;
+    int b = t / S, s = t % S;
+    compose_one(proj + (size_t)(b * V) * 16, proj + (size_t)(b * V + 1 + s) * 16, out + (size_t)t * 12, nan_flag);
+}
+
+__global__ void compose_pair_kernel(const float* __restrict__ src_proj, const float* __restrict__ ref_proj, int B,
+                                    float* __restrict__ out, int* nan_flag) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    compose_one(ref_proj + (size_t)b * 16, src_proj + (size_t)b * 16, out + (size_t)b * 12, nan_flag);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a1: differentiable_warping in the reference's own layouts (NCHW in, [B,C,D,H,W] out).
+// One thread per (b, d, y, x): sampling position once, then a loop over channels; stores are
+// coalesced along x.  This is the compatibility operator -- the estimator itself uses the fused
+// kernels of warpcorr.cu and never materialises this volume.
+// ---------------------------------------------------------------------------------------------
+__global__ void warp_nchw_kernel(const float* __restrict__ fea, const float* __restrict__ rt,
+                                 const float* __restrict__ depth, float* __restrict__ out,
+                                 int B, int C, int H1, int W1, int D, int H, int W) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    int bd = blockIdx.z;
+    if (x >= W) return;
+    int b = bd / D, d = bd % D;
+    const float* P = rt + (size_t)b * 12;
+    float dep = depth[((size_t)bd * H + y) * W + x];
+    float sx = (float)((double)W1 / (double)W), sy = (float)((double)H1 / (double)H);
+    Tap tp = project_tap(P, (float)x * sx, (float)y * sy, dep, (float)W, (float)H, W1, H1);
+    float w00 = (1.f - tp.fx) * (1.f - tp.fy), w01 = tp.fx * (1.f - tp.fy);
+    float w10 = (1.f - tp.fx) * tp.fy, w11 = tp.fx * tp.fy;
+    const size_t plane = (size_t)H1 * W1;
+    const float* base = fea + (size_t)b * C * plane;
+    size_t o = (((size_t)b * C) * D + d) * (size_t)H * W + (size_t)y * W + x;
+    const size_t ostride = (size_t)D * H * W;
+    int i00 = tp.y0 * W1 + tp.x0;
+    for (int c = 0; c < C; ++c) {
+        const float* p = base + (size_t)c * plane;
+        float acc = 0.f;
+        if (tp.mask & 1) acc = ldg(p + i00) * w00;
+        if (tp.mask & 2) acc = fmaf(ldg(p + i00 + 1), w01, acc);
+        if (tp.mask & 4) acc = fmaf(ldg(p + i00 + W1), w10, acc);
+        if (tp.mask & 8) acc = fmaf(ldg(p + i00 + W1 + 1), w11, acc);
+        out[o + (size_t)c * ostride] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers (tiled transpose through shared memory, 32x32 tiles over (C, H*W))
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_cp_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+    // in: [N][R][Cc] -> out: [N][Cc][R]
+    __shared__ float tile[32][33];
+    int n = blockIdx.z;
+    const float* src = in + (size_t)n * R * Cc;
+    float* dst = out + (size_t)n * R * Cc;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) tile[i][threadIdx.x] = src[(size_t)r * Cc + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) dst[(size_t)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+static int transpose_launch(const float* in, float* out, int N, int R, int Cc, cudaStream_t st) {
+    dim3 grid(cdiv(Cc, 32), cdiv(R, 32), N), block(32, 8);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: grid too large (R=%d N=%d)", R, N);
+    transpose_cp_kernel<<<grid, block, 0, st>>>(in, out, R, Cc);
+    count_launch();
+    IMVS_LAUNCH_CHECK("transpose_cp_kernel");
+    return 0;
+}
+
+}  // namespace imvs
+
+using namespace imvs;
+
+extern "C" int imvs_abi_version(void) { return IMVS_ABI_VERSION; }
+extern "C" const char* imvs_last_error(void) { return err_buf(); }
+extern "C" long long imvs_launches_total(void) { return launches_total(); }
+
+extern "C" int imvs_compose_projections(const float* proj, int B, int V, float* out, int* nan_flag, void* stream) {
+    IMVS_REQUIRE(proj && out, "compose_projections: null pointer");
+    IMVS_REQUIRE(B >= 1 && V >= 2, "compose_projections: need B>=1 and at least one source view (B=%d V=%d)", B, V);
+    int n = B * (V - 1);
+    compose_kernel<<<cdiv(n, 64), 64, 0, (cudaStream_t)stream>>>(proj, B, V, out, nan_flag);
+    count_launch();
+    IMVS_LAUNCH_CHECK("compose_kernel");
+    return 0;
+}
+
+extern "C" int imvs_differentiable_warping(const float* src_fea, const float* src_proj, const float* ref_proj,
+                                           const float* depth_samples, float* out, int B, int C, int H1, int W1,
+                                           int D, int H, int W, float* rt_scratch, int* nan_flag, void* stream) {
+    IMVS_REQUIRE(src_fea && src_proj && ref_proj && depth_samples && out && rt_scratch,
+                 "differentiable_warping: null pointer");
+    IMVS_REQUIRE(B >= 1 && C >= 1 && H1 >= 1 && W1 >= 1 && D >= 1 && H >= 1 && W >= 1,
+                 "differentiable_warping: bad shape");
+    IMVS_REQUIRE(H <= 65535 && (long long)B * D <= 65535, "differentiable_warping: H or B*D exceeds grid limits");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* rt = rt_scratch;
+    compose_pair_kernel<<<cdiv(B, 32), 32, 0, st>>>(src_proj, ref_proj, B, rt, nan_flag);
+    count_launch();
+    IMVS_LAUNCH_CHECK("compose_pair_kernel");
+    dim3 grid(cdiv(W, 128), H, B * D);
+    warp_nchw_kernel<<<grid, 128, 0, st>>>(src_fea, rt, depth_samples, out, B, C, H1, W1, D, H, W);
+    count_launch();
+    IMVS_LAUNCH_CHECK("warp_nchw_kernel");
+    return 0;
+}
+
+extern "C" int imvs_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, void* stream) {
+    IMVS_REQUIRE(in && out && N >= 1 && C >= 1 && H >= 1 && W >= 1, "nchw_to_nhwc: bad argument");
+    return transpose_launch(in, out, N, C, H * W, (cudaStream_t)stream);   // [C][P] -> [P][C]
+}
+
+extern "C" int imvs_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, void* stream) {
+    IMVS_REQUIRE(in && out && N >= 1 && C >= 1 && H >= 1 && W >= 1, "nhwc_to_nchw: bad argument");
+    return transpose_launch(in, out, N, H * W, C, (cudaStream_t)stream);   // [P][C] -> [C][P]
+}

@@ -1,0 +1,346 @@
+// Fused plane-sweep kernels: hypothesis generation + homography warp + bilinear sampling of the
+// source feature pyramids + group-wise correlation (+ pixel-wise view-weighted aggregation in the
+// iteration kernel).  The [C, D, H, W] warped volume of the reference (module.py:118-120) and the
+// same-size product tensor (itermvs.py:50, 103) are never materialised.
+//
+// Reference: models/module.py:68-125, models/itermvs.py:11-19, 45-69, 86-120, 289-293.
+//
+// Thread mapping (both kernels).  Features are channels-last, so one sampled tap is C contiguous
+// floats (64/128/192 B).  A warp is split into 4 "slots" of 8 lanes; lane g of a slot owns
+// correlation group g, i.e. channels [g*C/8, (g+1)*C/8) -- exactly one float2 / float4 / 3xfloat2
+// per tap, so a slot reads a tap as one fully used 64/128/192-byte segment and the group
+// reduction needs no shuffles.  The 4 slots are the 4 depth samples of ONE pixel (2 pixels x 2
+// samples at level 3): neighbouring hypotheses of a pixel land within ~a pixel of each other along
+// the epipolar line, so the four slots of a load instruction mostly hit the same 128-byte lines
+// (fewer L1 wavefronts than four different pixels would cost).  The sampling position of
+// (sample, view) is computed once -- by lane (slot, g = view) -- and broadcast with shuffles.
+#include "common.cuh"
+#include "sampling.cuh"
+
+namespace imvs {
+
+template <int CPG>
+__device__ __forceinline__ void load_group(const float* __restrict__ p, float (&v)[CPG]) {
+    if constexpr (CPG == 4) {
+        float4 t = ldg4(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < CPG / 2; ++i) {
+            float2 t = ldg2(p + 2 * i);
+            v[2 * i] = t.x; v[2 * i + 1] = t.y;
+        }
+    }
+}
+
+// bilinear sample of one tap position for this lane's channel group, then dot with the reference
+// feature group: returns mean_c( warped_c * ref_c )  (itermvs.py:50-51)
+template <int CPG>
+__device__ __forceinline__ float sample_dot(const float* __restrict__ fea_view_g, int C, int Wf, int i00,
+                                            float fx, float fy, unsigned mask, const float (&ref)[CPG]) {
+    float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+    float a[CPG];
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) a[i] = 0.f;
+    const float* p = fea_view_g + (ptrdiff_t)i00 * C;
+    float t[CPG];
+    if (mask & 1u) {
+        load_group<CPG>(p, t);
+#pragma unroll
+        for (int i = 0; i < CPG; ++i) a[i] = t[i] * w00;
+    }
+    if (mask & 2u) {
+        load_group<CPG>(p + C, t);
+#pragma unroll
+        for (int i = 0; i < CPG; ++i) a[i] = fmaf(t[i], w01, a[i]);
+    }
+    if (mask & 4u) {
+        load_group<CPG>(p + (ptrdiff_t)Wf * C, t);
+#pragma unroll
+        for (int i = 0; i < CPG; ++i) a[i] = fmaf(t[i], w10, a[i]);
+    }
+    if (mask & 8u) {
+        load_group<CPG>(p + (ptrdiff_t)(Wf + 1) * C, t);
+#pragma unroll
+        for (int i = 0; i < CPG; ++i) a[i] = fmaf(t[i], w11, a[i]);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) dot = fmaf(a[i], ref[i], dot);
+    return dot / (float)CPG;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: init plane sweep at level 3 (C = 48), per-view group correlation.
+//   grid (ceil(W3/TPX), ceil(H3/8), B*DSPLIT), block 256 (8 warps = 8 rows)
+// ---------------------------------------------------------------------------------------------
+constexpr int INIT_TPX = 4;
+
+__global__ void __launch_bounds__(256)
+warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ rt3,
+                     const float* __restrict__ depth_min, const float* __restrict__ depth_max,
+                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D,
+                     int dsplit) {
+    constexpr int CPG = 6, C = 48;
+    __shared__ float sP[IMVS_MAX_VIEWS * 12];
+    const int S = V - 1;
+    const int b = blockIdx.z / dsplit, dpart = blockIdx.z % dsplit;
+    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = rt3[(size_t)b * S * 12 + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = lane >> 3, g = lane & 7;
+    const int y = blockIdx.y * 8 + warp;
+    if (y >= H3) return;
+    const int P3 = H3 * W3;
+    const float inv_min = samples ? 0.f : 1.0f / depth_min[b], inv_max = samples ? 0.f : 1.0f / depth_max[b];
+    const int chunks = (D + 3) / 4;
+    const int c_begin = (chunks * dpart) / dsplit, c_end = (chunks * (dpart + 1)) / dsplit;
+    const int x_begin = blockIdx.x * INIT_TPX, x_end = min(x_begin + INIT_TPX, W3);
+    const float* ref_view = fea3 + (size_t)(b * V) * P3 * C;
+
+    for (int x = x_begin; x < x_end; ++x) {
+        const int p = y * W3 + x;
+        float ref[CPG];
+        load_group<CPG>(ref_view + (size_t)p * C + g * CPG, ref);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            const int d = ch * 4 + slot;
+            const bool dvalid = d < D;
+            // itermvs.py:13-17 (or the caller's explicit hypotheses, Evaluation.forward's depth_sample)
+            const float depth = samples ? ldg(samples + ((size_t)b * D + (dvalid ? d : 0)) * P3 + p)
+                                        : 1.0f / (inv_max + ((float)d / (float)(D - 1)) * (inv_min - inv_max));
+            for (int v0 = 0; v0 < S; v0 += 8) {
+                Tap tp;
+                tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
+                if (v0 + g < S && dvalid)
+                    tp = project_tap(sP + (v0 + g) * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
+                int i00 = tp.y0 * W3 + tp.x0;
+                const int nv = min(8, S - v0);
+                for (int j = 0; j < nv; ++j) {
+                    const int src = (lane & 24) | j;
+                    const int i00j = __shfl_sync(0xffffffffu, i00, src);
+                    const float fxj = __shfl_sync(0xffffffffu, tp.fx, src);
+                    const float fyj = __shfl_sync(0xffffffffu, tp.fy, src);
+                    const unsigned mj = __shfl_sync(0xffffffffu, tp.mask, src);
+                    const int v = v0 + j;
+                    const float* fv = fea3 + (size_t)(b * V + 1 + v) * P3 * C + g * CPG;
+                    const float c = sample_dot<CPG>(fv, C, W3, i00j, fxj, fyj, mj, ref);
+                    if (dvalid) corr[((((size_t)b * S + v) * D + d) * P3 + p) * 8 + g] = c;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: iteration kernel -- three pyramid levels, R = (4,4,2) samples per pixel around the current
+// normalized depth, all source views, view-weighted aggregation.  One launch covers the three
+// levels (blockIdx.z = b*3 + level).
+//   grid (ceil(W2/ITER_TPX), ceil(H2/8), B*3), block 256 (8 warps = 8 rows)
+// ---------------------------------------------------------------------------------------------
+constexpr int ITER_TPX = 16;
+
+struct IterParams {
+    const float* fea[3];   // level 1,2,3 pyramids  [B][V][Hf][Wf][C]
+    const float* rt[3];    // composed projections  [B][S][12]
+    const float* nd;       // [B][nd_stride]
+    size_t nd_stride;
+    const float* vw2;      // [B][S][P2]
+    const float* depth_min;
+    const float* depth_max;
+    const float* samples[3];   // optional explicit hypotheses [B][R_l][P2] per level (else from nd)
+    float* agg;            // [B][10][P2][8]
+    int B, V, H2, W2;
+};
+
+// MODE: how the reference-view feature of this level is brought to level-2 resolution
+// (itermvs.py:95-98): 0 same, 1 F.interpolate(x0.5) == 2x2 mean, 2 F.interpolate(x2) bilinear.
+template <int CPG, int R, int MODE>
+__device__ __forceinline__ void iter_level(const IterParams& prm, const float* sP, int b, int y, int x_begin,
+                                           int x_end, int slice_base, float o0, float o1, float o2, float o3) {
+    constexpr int C = CPG * 8;
+    constexpr int PPS = 4 / R;     // pixels per warp step
+    const int lane = threadIdx.x & 31;
+    const int slot = lane >> 3, g = lane & 7;
+    const int r = slot % R, pxo = slot / R;
+    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2, P2 = H2 * W2;
+    const int Hf = MODE == 1 ? H2 * 2 : (MODE == 2 ? H2 / 2 : H2);
+    const int Wf = MODE == 1 ? W2 * 2 : (MODE == 2 ? W2 / 2 : W2);
+    const float sx = (float)((double)Wf / (double)W2), sy = (float)((double)Hf / (double)H2);   // module.py:95-96
+    const float* fea = prm.fea[MODE == 1 ? 0 : (MODE == 0 ? 1 : 2)];
+    const float* ref_view = fea + (size_t)(b * V) * Hf * Wf * C + g * CPG;
+    const float* smp = prm.samples[MODE == 1 ? 0 : (MODE == 0 ? 1 : 2)];
+    const float inv_min = smp ? 0.f : 1.0f / prm.depth_min[b], inv_max = smp ? 0.f : 1.0f / prm.depth_max[b];
+    const float off = (r == 0 ? o0 : r == 1 ? o1 : r == 2 ? o2 : o3) * (1.0f / 256.0f);   // itermvs.py:229,290
+
+    for (int xs = x_begin; xs < x_end; xs += PPS) {
+        const int x = xs + pxo;
+        const bool pvalid = x < x_end;
+        const int xc = pvalid ? x : x_end - 1;
+        const int p = y * W2 + xc;
+        // hypotheses: itermvs.py:290-293
+        float depth;
+        if (smp) {
+            depth = ldg(smp + ((size_t)b * R + r) * P2 + p);
+        } else {
+            const float ndv = ldg(prm.nd + (size_t)b * prm.nd_stride + p);
+            const float s = fminf(fmaxf(ndv + off, 0.f), 1.f);
+            depth = unnormalize_depth(s, inv_min, inv_max);
+        }
+        // reference feature of this group at level-2 resolution
+        float ref[CPG];
+        if constexpr (MODE == 0) {
+            load_group<CPG>(ref_view + (size_t)p * C, ref);
+        } else if constexpr (MODE == 1) {
+            float a[CPG], bq[CPG], c[CPG], d[CPG];
+            const float* q = ref_view + ((size_t)(2 * y) * Wf + 2 * xc) * C;
+            load_group<CPG>(q, a);
+            load_group<CPG>(q + C, bq);
+            load_group<CPG>(q + (size_t)Wf * C, c);
+            load_group<CPG>(q + (size_t)(Wf + 1) * C, d);
+#pragma unroll
+            for (int i = 0; i < CPG; ++i) ref[i] = 0.5f * (0.5f * a[i] + 0.5f * bq[i]) + 0.5f * (0.5f * c[i] + 0.5f * d[i]);
+        } else {
+            int h0, h1, w0, w1;
+            float lh, lw;
+            up_index(y, 0.5f, Hf, h0, h1, lh);
+            up_index(xc, 0.5f, Wf, w0, w1, lw);
+            float a[CPG], bq[CPG], c[CPG], d[CPG];
+            load_group<CPG>(ref_view + ((size_t)h0 * Wf + w0) * C, a);
+            load_group<CPG>(ref_view + ((size_t)h0 * Wf + w1) * C, bq);
+            load_group<CPG>(ref_view + ((size_t)h1 * Wf + w0) * C, c);
+            load_group<CPG>(ref_view + ((size_t)h1 * Wf + w1) * C, d);
+#pragma unroll
+            for (int i = 0; i < CPG; ++i)
+                ref[i] = (1.f - lh) * ((1.f - lw) * a[i] + lw * bq[i]) + lh * ((1.f - lw) * c[i] + lw * d[i]);
+        }
+        float num = 0.f, wsum = 1e-5f;                          // itermvs.py:88-89
+        for (int v0 = 0; v0 < S; v0 += 8) {
+            Tap tp;
+            tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
+            float wv = 0.f;
+            if (v0 + g < S) {
+                tp = project_tap(sP + (v0 + g) * 12, (float)xc * sx, (float)y * sy, depth, (float)W2, (float)H2, Wf, Hf);
+                wv = ldg(prm.vw2 + ((size_t)b * S + v0 + g) * P2 + p);
+            }
+            const int i00 = tp.y0 * Wf + tp.x0;
+            const int nv = min(8, S - v0);
+#pragma unroll 4
+            for (int j = 0; j < nv; ++j) {
+                const int src = (lane & 24) | j;
+                const int i00j = __shfl_sync(0xffffffffu, i00, src);
+                const float fxj = __shfl_sync(0xffffffffu, tp.fx, src);
+                const float fyj = __shfl_sync(0xffffffffu, tp.fy, src);
+                const unsigned mj = __shfl_sync(0xffffffffu, tp.mask, src);
+                const float wj = __shfl_sync(0xffffffffu, wv, src);
+                const float* fv = fea + (size_t)(b * V + 1 + v0 + j) * Hf * Wf * C + g * CPG;
+                const float c = sample_dot<CPG>(fv, C, Wf, i00j, fxj, fyj, mj, ref);
+                num = fmaf(c, wj, num);                          // itermvs.py:114
+                wsum += wj;                                      // itermvs.py:115
+            }
+        }
+        if (pvalid) prm.agg[(((size_t)b * IMVS_ITER_SLICES + slice_base + r) * P2 + p) * 8 + g] = num / wsum;
+    }
+}
+
+__global__ void __launch_bounds__(256) warpcorr_iter_kernel(const IterParams prm) {
+    __shared__ float sP[IMVS_MAX_VIEWS * 12];
+    const int b = blockIdx.z / 3, lvl = blockIdx.z % 3;
+    const int S = prm.V - 1;
+    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = prm.rt[lvl][(size_t)b * S * 12 + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const int y = blockIdx.y * 8 + warp;
+    if (y >= prm.H2) return;
+    const int x_begin = blockIdx.x * ITER_TPX, x_end = min(x_begin + ITER_TPX, prm.W2);
+    if (x_begin >= x_end) return;
+    // itermvs.py:231-235
+    if (lvl == 0)      iter_level<2, 4, 1>(prm, sP, b, y, x_begin, x_end, 0, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
+    else if (lvl == 1) iter_level<4, 4, 0>(prm, sP, b, y, x_begin, x_end, 4, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
+    else               iter_level<6, 2, 2>(prm, sP, b, y, x_begin, x_end, 8, -32.f, 32.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// view-weighted aggregation of the init volume (itermvs.py:59-69): one thread per float4 of the
+// [B][D][P3][8] output.
+// ---------------------------------------------------------------------------------------------
+__global__ void aggregate_init_kernel(const float* __restrict__ corr, const float* __restrict__ vw3,
+                                      float* __restrict__ agg, int B, int S, int D, int P3) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)B * D * P3 * 2;
+    if (t >= total) return;
+    int half = (int)(t & 1);
+    size_t q = t >> 1;                 // (b*D + d)*P3 + p
+    int p = (int)(q % P3);
+    size_t bd = q / P3;
+    int d = (int)(bd % D), b = (int)(bd / D);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 1e-5f;                // itermvs.py:38
+    for (int v = 0; v < S; ++v) {
+        float w = ldg(vw3 + ((size_t)b * S + v) * P3 + p);
+        float4 c = ldg4(corr + ((((size_t)b * S + v) * D + d) * P3 + p) * 8 + half * 4);
+        acc.x = fmaf(c.x, w, acc.x); acc.y = fmaf(c.y, w, acc.y);
+        acc.z = fmaf(c.z, w, acc.z); acc.w = fmaf(c.w, w, acc.w);
+        wsum += w;
+    }
+    acc.x /= wsum; acc.y /= wsum; acc.z /= wsum; acc.w /= wsum;
+    reinterpret_cast<float4*>(agg)[t] = acc;
+}
+
+}  // namespace imvs
+
+using namespace imvs;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const float* depth_min, const float* depth_max,
+                                  const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream) {
+    IMVS_REQUIRE(fea3 && rt3 && corr && (depth_samples || (depth_min && depth_max)), "warpcorr_init: null pointer");
+    IMVS_REQUIRE(B >= 1 && V >= 2 && V - 1 <= IMVS_MAX_VIEWS, "warpcorr_init: need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, V);
+    IMVS_REQUIRE(H3 >= 1 && W3 >= 1 && D >= 2, "warpcorr_init: bad shape H3=%d W3=%d D=%d", H3, W3, D);
+    IMVS_REQUIRE(aligned16(fea3) && aligned16(corr), "warpcorr_init: feature/corr pointers must be 16-byte aligned");
+    const int dsplit = 2;
+    dim3 grid(cdiv(W3, INIT_TPX), cdiv(H3, 8), B * dsplit);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
+    warpcorr_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, dsplit);
+    count_launch();
+    IMVS_LAUNCH_CHECK("warpcorr_init_kernel");
+    return 0;
+}
+
+extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
+                                  const float* rt1, const float* rt2, const float* rt3,
+                                  const float* nd, size_t nd_batch_stride, const float* vw2,
+                                  const float* depth_min, const float* depth_max,
+                                  const float* samples1, const float* samples2, const float* samples3, float* agg,
+                                  int B, int V, int H2, int W2, void* stream) {
+    const bool explicit_samples = samples1 && samples2 && samples3;
+    IMVS_REQUIRE(fea1 && fea2 && fea3 && rt1 && rt2 && rt3 && vw2 && agg, "warpcorr_iter: null pointer");
+    IMVS_REQUIRE(explicit_samples || (!samples1 && !samples2 && !samples3 && nd && depth_min && depth_max),
+                 "warpcorr_iter: pass either all three sample tensors or nd + depth range");
+    IMVS_REQUIRE(B >= 1 && V >= 2 && V - 1 <= IMVS_MAX_VIEWS, "warpcorr_iter: need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, V);
+    IMVS_REQUIRE(H2 >= 2 && W2 >= 2 && H2 % 2 == 0 && W2 % 2 == 0, "warpcorr_iter: H2, W2 must be even (H2=%d W2=%d)", H2, W2);
+    IMVS_REQUIRE(aligned16(fea1) && aligned16(fea2) && aligned16(fea3) && aligned16(agg),
+                 "warpcorr_iter: feature/agg pointers must be 16-byte aligned");
+    IterParams prm;
+    prm.fea[0] = fea1; prm.fea[1] = fea2; prm.fea[2] = fea3;
+    prm.rt[0] = rt1; prm.rt[1] = rt2; prm.rt[2] = rt3;
+    prm.nd = nd; prm.nd_stride = nd_batch_stride; prm.vw2 = vw2;
+    prm.depth_min = depth_min; prm.depth_max = depth_max; prm.agg = agg;
+    prm.samples[0] = samples1; prm.samples[1] = samples2; prm.samples[2] = samples3;
+    prm.B = B; prm.V = V; prm.H2 = H2; prm.W2 = W2;
+    dim3 grid(cdiv(W2, ITER_TPX), cdiv(H2, 8), B * 3);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
+    warpcorr_iter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prm);
+    count_launch();
+    IMVS_LAUNCH_CHECK("warpcorr_iter_kernel");
+    return 0;
+}
+
+extern "C" int imvs_aggregate_init(const float* corr, const float* vw3, float* agg, int B, int S, int D, int P3, void* stream) {
+    IMVS_REQUIRE(corr && vw3 && agg && B >= 1 && S >= 1 && D >= 1 && P3 >= 1, "aggregate_init: bad argument");
+    size_t total = (size_t)B * D * P3 * 2;
+    aggregate_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(corr, vw3, agg, B, S, D, P3);
+    count_launch();
+    IMVS_LAUNCH_CHECK("aggregate_init_kernel");
+    return 0;
+}
