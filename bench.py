@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the IterMVS hot path on B200 (driver contract: one JSON line on stdout).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference --steps 3 --warmup 1        # CPU oracle port, all host threads
+
+Workload (BASELINE.json configs[1]): one reference view = 640x512 image + 4 source views, D=32
+initial hypotheses, 4 GRU iterations, batch 1 per GPU, synthetic consistent-plane scene, DTU
+checkpoint weights (tests/golden/dtu_weights.npz).  A step = one `Pipeline.forward` (FeatureNet +
+the whole estimator), test mode.  Metric = reference views per second.
+
+value : device-resident inputs, one CUDA-graph replay per step, per-step CUDA events, L2 flushed
+        between steps (outside the event windows), max over ranks.
+e2e   : same call from pinned HOST buffers: H2D of images/cameras + forward + D2H of the two
+        full-resolution outputs inside the per-step event window.
+roofline : fused warp+correlate iteration kernel, algorithmic bytes / its in-step
+        duration from the library's CUDA-event stage taps, against MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+W_IMG, H_IMG, N_SRC, D_HYP, ITERS = 640, 512, 4, 32, 4
+METRIC = "reference-views/sec at 640x512, 4 src, D=32, 4 iters"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def algorithmic_bytes(h, w, s, d):
+    p2, p3 = (h // 4) * (w // 4), (h // 8) * (w // 8)
+    init = 4 * p3 * (48 * (s + 1) + 8 * d)
+    it = 4 * p2 * (108 * (s + 1) + (s + 1) + 80)
+    return init, it
+
+
+def load_weights():
+    with np.load(os.path.join(ROOT, "tests", "golden", "dtu_weights.npz")) as z:
+        return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def pick_cpu_threads(run, budget_s=12.0):
+    """The CPU port is many small torch ops: using every hardware thread of a 128-core host is slower
+    than a moderate count.  Probe a few settings on one pass each (bounded) and keep the fastest."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, ncpu) if c <= ncpu})
+    best, best_t, spent = None, None, 0.0
+    torch.set_num_threads(cands[0])
+    run()                                         # warm-up (allocator, first-touch)
+    for c in cands:
+        if spent > budget_s:
+            break
+        torch.set_num_threads(c)
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+        spent += dt
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def run_reference(args, rank):
+    """Reference arm: the CPU port of the reference's algorithm (oracle/), all host threads."""
+    if rank != 0:
+        return
+    from oracle import itermvs_oracle as O
+    from itermvs_b200.synthetic import make_sample
+    weights = load_weights()
+    s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=0, scene="plane")
+    run = lambda: O.pipeline_forward(weights, s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"],
+                                     iteration=ITERS, num_sample=D_HYP)
+    pick_cpu_threads(run)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    cores = torch.get_num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "refs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 (BASELINE configs[1])",
+                   "note": "CPU port of the reference algorithm (oracle/itermvs_oracle.py, pinned to reference-generated "
+                           "golden vectors); the Python reference itself cannot travel to the GPU box"},
+        "cpu_baseline": {"value": v, "unit": "refs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full forward passes of the workload"},
+        "e2e": {"value": v, "unit": "refs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-stage timing table to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import itermvs_b200
+    from itermvs_b200 import _lib
+    from itermvs_b200.graph import GraphedPipeline, profile_stages
+    from itermvs_b200.synthetic import make_sample
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the CUDA path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True          # as eval.py:21
+    torch.backends.cudnn.allow_tf32 = False        # fp32 throughout (the metric's dtype)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    weights = load_weights()
+    model = itermvs_b200.Pipeline(iteration=ITERS, test=True)
+    model.load_state_dict(weights, strict=True)
+    model = model.to(dev).eval()
+    s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=rank, scene="plane")   # one reference view per GPU
+    host = {"imgs": {"level_0": s["imgs"]["level_0"].pin_memory()},
+            "proj": {k: s["proj_matrices"][k].float().pin_memory() for k in ("level_1", "level_2", "level_3")},
+            "dmin": s["depth_min"].pin_memory(), "dmax": s["depth_max"].pin_memory()}
+    d_imgs = {"level_0": host["imgs"]["level_0"].to(dev)}
+    d_proj = {k: v.to(dev) for k, v in host["proj"].items()}
+    d_dmin, d_dmax = host["dmin"].to(dev), host["dmax"].to(dev)
+
+    def eager():
+        with torch.no_grad():
+            return model(d_imgs, d_proj, d_dmin, d_dmax)
+
+    eager()
+    torch.cuda.synchronize()
+    l0 = _lib.launches_total()
+    eager()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launches_total() - l0
+    model._last_nan_flag.raise_if_set()
+
+    graphed = None if args.no_graph else GraphedPipeline(model, d_imgs, d_proj, d_dmin, d_dmax)
+    step = eager if graphed is None else graphed.replay
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- stage breakdown + in-step duration of the fused warp+correlate kernels (eager, taps on)
+    stage_ms = {}
+    for _ in range(3):
+        flush.zero_()
+        recs = profile_stages(eager)
+        acc = {}
+        for name, ms in recs:
+            acc.setdefault(name, []).append(ms)
+        for name, lst in acc.items():
+            stage_ms.setdefault(name, []).append(lst)
+    iter_ms = [m for rep in stage_ms.get("warpcorr_iter", []) for m in rep]
+    init_ms = [m for rep in stage_ms.get("warpcorr_init", []) for m in rep]
+
+    # ---- timed region: device-resident inputs
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end to end from pinned host buffers
+    out_host = {"d": torch.empty(1, 1, H_IMG, W_IMG).pin_memory(), "c": torch.empty(1, 1, H_IMG, W_IMG).pin_memory()}
+    h2d = host["imgs"]["level_0"].numel() * 4 + sum(v.numel() * 4 for v in host["proj"].values()) + 8
+    d2h = 2 * H_IMG * W_IMG * 4
+
+    def e2e_step():
+        if graphed is not None:
+            graphed.load_inputs(host["imgs"], host["proj"], host["dmin"], host["dmax"])
+            out = graphed.replay()
+        else:
+            with torch.no_grad():
+                out = model({"level_0": host["imgs"]["level_0"].to(dev, non_blocking=True)},
+                            {k: v.to(dev, non_blocking=True) for k, v in host["proj"].items()},
+                            host["dmin"].to(dev, non_blocking=True), host["dmax"].to(dev, non_blocking=True))
+        out_host["d"].copy_(out["depths_upsampled"], non_blocking=True)
+        out_host["c"].copy_(out["confidence_upsampled"], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        e2e_step()
+        b.record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clk = clocks.stop()
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * args.steps / (total_ms / 1000.0)
+    e2e_value = world * args.steps / (e2e_ms / 1000.0)
+
+    # ---- CPU baseline: oracle port on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import itermvs_oracle as O
+        s0 = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=0, scene="plane")
+        run = lambda: O.pipeline_forward(weights, s0["imgs"], s0["proj_matrices"], s0["depth_min"], s0["depth_max"],
+                                         iteration=ITERS, num_sample=D_HYP)
+        nthr = pick_cpu_threads(run)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+        cpu = {"value": 1.0 / statistics.median(ts), "unit": "refs/s", "cores": nthr, "kind": "port",
+               "host_cpus": os.cpu_count(),
+               "sample": "3 full forward passes of the workload (median) after a thread-count probe, "
+                         "oracle/itermvs_oracle.py on torch CPU fp32"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    init_b, iter_b = algorithmic_bytes(H_IMG, W_IMG, N_SRC, D_HYP)
+    peak, peak_src = hbm_peak()
+    mean_iter_ms = statistics.mean(iter_ms) if iter_ms else float("nan")
+    achieved = iter_b / (mean_iter_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("warpcorr_iter_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    breakdown = {k: round(statistics.mean(sum(rep) for rep in v), 4) for k, v in stage_ms.items()}
+    if args.breakdown:
+        print("stage breakdown (ms per forward, eager + event taps):", json.dumps(breakdown), file=sys.stderr)
+    fwd_launches = int(launches_per_step)
+    line = {
+        "metric": METRIC, "value": value, "unit": "refs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 per GPU (BASELINE configs[1])",
+                   "step": "Pipeline.forward test mode: FeatureNet (cuDNN fp32) + fused sm_100a estimator",
+                   "launch": "eager" if graphed is None else "cuda-graph replay",
+                   "l2": "256 MiB memset between steps, outside the per-step CUDA-event windows",
+                   "weights": "DTU checkpoint", "parallelism": f"replicas x{world} (one reference view per GPU, no collectives)"},
+        "e2e": {"value": e2e_value, "unit": "refs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": fwd_launches * args.steps,
+        "gpu_launches_per_step": fwd_launches,
+        "roofline": {"kernel": "warpcorr_iter_kernel (fused warp+sample+group-corr+view-weighted aggregation)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": iter_b,
+                     "avg_launch_ms": mean_iter_ms, "launches_timed": len(iter_ms),
+                     "init_kernel": {"algorithmic_bytes": init_b, "avg_launch_ms": statistics.mean(init_ms) if init_ms else None}},
+        "stage_ms": breakdown,
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
+        "wall_s_timed_region": t_wall,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

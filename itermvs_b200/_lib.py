@@ -44,6 +44,8 @@ _SIGNATURES = {
     "imvs_abi_version": (ci, []),
     "imvs_last_error": (C.c_char_p, []),
     "imvs_launches_total": (C.c_longlong, []),
+    "imvs_profile_begin": (ci, [ci]),
+    "imvs_profile_end": (ci, [vp, vp, ci]),
     "imvs_compose_projections": (ci, [vp, ci, ci, vp, vp, vp]),
     "imvs_differentiable_warping": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]),
     "imvs_nchw_to_nhwc": (ci, [vp, vp, ci, ci, ci, ci, vp]),

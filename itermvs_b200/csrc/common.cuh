@@ -45,6 +45,29 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 void count_launch(int n = 1);
 long long launches_total();
 
+// ---- optional per-stage CUDA-event timing (bench.py's roofline measurement; off by default) ----
+enum StageTag { ST_COMPOSE = 0, ST_WARPCORR_INIT, ST_PVW, ST_AGG_INIT, ST_CORRNET, ST_HIDDEN_INIT, ST_HEAD,
+                ST_WARPCORR_ITER, ST_GRU, ST_UPSAMPLE, ST_FEATURENET, ST_COUNT };
+bool profile_active();
+void profile_mark(int tag, cudaStream_t st, bool is_start);
+struct StageTimer {
+    int tag; cudaStream_t st; bool on;
+    StageTimer(int t, void* s) : tag(t), st((cudaStream_t)s), on(profile_active()) { if (on) profile_mark(tag, st, true); }
+    ~StageTimer() { if (on) profile_mark(tag, st, false); }
+};
+
+// opt in to > 48 KB dynamic shared memory once per (kernel, device); safe to call every launch
+template <class K>
+int ensure_dynamic_smem(K kern, size_t smem, int* done_mask) {
+    if (smem <= 48 * 1024) return 0;
+    int dev = 0;
+    IMVS_CUDA(cudaGetDevice(&dev));
+    if ((*done_mask >> (dev & 31)) & 1) return 0;
+    IMVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    *done_mask |= 1 << (dev & 31);
+    return 0;
+}
+
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

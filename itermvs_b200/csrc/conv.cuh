@@ -186,7 +186,8 @@ int launch_conv(const char* name, const In& in, const Epi& epi, const WeightSel&
     size_t smem = (size_t)Cin * KK * Cfg::CB * sizeof(float);
     IMVS_REQUIRE(smem <= 200 * 1024, "%s: weight slice of %zu bytes does not fit shared memory", name, smem);
     auto kern = conv_kernel<Cfg, In, Epi>;
-    if (smem > 48 * 1024) IMVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     dim3 grid(cdiv(Wout, 32), cdiv(Hout, Cfg::TILE_H), N * ncb);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
     kern<<<grid, Cfg::THREADS, smem, st>>>(in, epi, wsel, Cin, Hout, Wout, ncb);
@@ -279,7 +280,8 @@ int launch_tconv(const char* name, const float* in, const float* skip, float* ou
                  int Cin, int Hin, int Win, cudaStream_t st) {
     size_t smem = (size_t)Cin * 9 * CB * sizeof(float);
     auto kern = tconv_kernel<COUT, CB, CO, ROWS>;
-    if (smem > 48 * 1024) IMVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     dim3 grid(cdiv(Win, 32), cdiv(Hin, ROWS), N * (COUT / CB));
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
     kern<<<grid, 32 * ROWS * (CB / CO), smem, st>>>(in, skip, out, wsel, Cin, Hin, Win);

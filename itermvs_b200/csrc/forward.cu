@@ -92,42 +92,66 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
     const size_t xstride = (size_t)11 * P2;
 
     // K1 (module.py:78-90), hoisted: once per level instead of once per warp call
+    { StageTimer tm_(ST_COMPOSE, stream);
     IMVS_TRY(imvs_compose_projections(proj1, B, V, ws.rt1, nan_flag, stream));
     IMVS_TRY(imvs_compose_projections(proj2, B, V, ws.rt2, nan_flag, stream));
     IMVS_TRY(imvs_compose_projections(proj3, B, V, ws.rt3, nan_flag, stream));
+    }
 
     // init evaluation (itermvs.py:270-271, 36-70)
+    { StageTimer tm_(ST_WARPCORR_INIT, stream);
     IMVS_TRY(imvs_warpcorr_init(fea3, ws.rt3, depth_min, depth_max, nullptr, ws.corr_init, B, V, H3, W3, D, stream));
+    }
+    { StageTimer tm_(ST_PVW, stream);
     IMVS_TRY(imvs_pixel_view_weight(w, ws.corr_init, ws.pvw_logits, ws.vw3, ws.vw2, B, S, D, H3, W3, stream));
+    }
+    { StageTimer tm_(ST_AGG_INIT, stream);
     IMVS_TRY(imvs_aggregate_init(ws.corr_init, ws.vw3, ws.agg_init, B, S, D, P3, stream));
+    }
     imvs_corrnet_weights init_sets[3] = {w->corrnet[2], w->corrnet[2], w->corrnet[2]};
+    { StageTimer tm_(ST_CORRNET, stream);
     IMVS_TRY(imvs_corrnet(init_sets, D, D, D, ws.agg_init, ws.corr0, (size_t)D * P3, ws.corrnet_scratch, B * D, H3, W3, stream));
+    }
 
     // hidden state and first depth (itermvs.py:275-276)
+    { StageTimer tm_(ST_HIDDEN_INIT, stream);
     IMVS_TRY(imvs_hidden_init(w, ws.corr0, ws.hidden, ws.hinit_scratch, B, D, H3, W3, stream));
+    }
+    { StageTimer tm_(ST_HEAD, stream);
     IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xstride, nullptr, nullptr, nullptr, (I == 1) ? depth : nullptr,
                              depth_min, depth_max, ws.head_scratch, B, H2, W2, stream));
+    }
 
     float* conf_q = conf ? conf : ws.conf_buf;
     for (int it = 0; it < I; ++it) {
         const bool last = (it == I - 1);
         // itermvs.py:288-295
+        { StageTimer tm_(ST_WARPCORR_ITER, stream);
         IMVS_TRY(imvs_warpcorr_iter(fea1, fea2, fea3, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xstride, ws.vw2, depth_min, depth_max,
                                     nullptr, nullptr, nullptr, ws.agg_iter, B, V, H2, W2, stream));
+        }
+        { StageTimer tm_(ST_CORRNET, stream);
         IMVS_TRY(imvs_corrnet(w->corrnet, IMVS_ITER_SLICES, 4, 8, ws.agg_iter, ws.xbuf + P2, xstride, ws.corrnet_scratch,
                               B * IMVS_ITER_SLICES, H2, W2, stream));
+        }
         // itermvs.py:316-320 -> Update.forward (192-220); x = [normalized_depth, corr] is xbuf itself
+        { StageTimer tm_(ST_GRU, stream);
         IMVS_TRY(imvs_conv_gru(w, ws.hidden, ws.xbuf, ws.gru_scratch, B, H2, W2, stream));
+        }
         // `depth` returned in test mode is the value BEFORE the last update (itermvs.py:319)
         float* depth_here = (!last && it == I - 2) ? depth : nullptr;
+        { StageTimer tm_(ST_HEAD, stream);
         IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xstride, nullptr, last ? conf_q : nullptr, nullptr, depth_here,
                                  depth_min, depth_max, ws.head_scratch, B, H2, W2, stream));
+        }
     }
     // itermvs.py:321-324
     if (depth_up || conf_up) {
         IMVS_REQUIRE(depth_up, "itermvs_forward: conf_up requested without depth_up");
+        { StageTimer tm_(ST_UPSAMPLE, stream);
         IMVS_TRY(imvs_upsample_outputs(w, ref_fea2_planar, ws.xbuf, xstride, conf_up ? conf_q : nullptr, depth_min, depth_max,
                                        depth_up, conf_up, ws.ups_scratch, B, H2, W2, stream));
+        }
     }
     return 0;
 }

@@ -287,7 +287,8 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     prm.depth_min = depth_min; prm.depth_max = depth_max;
     prm.B = B; prm.P = P;
     const size_t smem = (size_t)(64 * 256 + 32 * 64 + 256 + 36 + (HEAD_THREADS / 32) * 2 * 64 * HEAD_PXW) * sizeof(float);
-    IMVS_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(head_kernel, smem, &smem_ok));
     int dev = 0, sms = 148;
     IMVS_CUDA(cudaGetDevice(&dev));
     IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

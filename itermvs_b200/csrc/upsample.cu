@@ -123,7 +123,8 @@ extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.depth_up = depth_up;
     prm.B = B; prm.H2 = H2; prm.W2 = W2;
     const size_t smem = (size_t)(64 * 144 + (UPS_THREADS / 32) * 64 * 8) * sizeof(float);
-    IMVS_CUDA(cudaFuncSetAttribute(convex_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(convex_upsample_kernel, smem, &smem_ok));
     int dev = 0, sms = 148;
     IMVS_CUDA(cudaGetDevice(&dev));
     IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -18,6 +18,28 @@ static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launches_total() { return g_launches; }
 
+// ---- stage timing taps -----------------------------------------------------------------------
+struct ProfileState {
+    bool active = false;
+    int cap = 0, n = 0;
+    cudaEvent_t* ev = nullptr;     // 2 per record: start, stop
+    int* tags = nullptr;
+};
+static ProfileState g_prof;
+bool profile_active() { return g_prof.active; }
+void profile_mark(int tag, cudaStream_t st, bool is_start) {
+    if (!g_prof.active) return;
+    if (is_start) {
+        if (g_prof.n >= g_prof.cap) return;
+        g_prof.tags[g_prof.n] = tag;
+        cudaEventRecord(g_prof.ev[2 * g_prof.n], st);
+    } else {
+        if (g_prof.n >= g_prof.cap) return;
+        cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], st);
+        g_prof.n++;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: proj = src_proj @ inverse(ref_proj)  (module.py:78-90).  One thread per (b, source view).
 // Done in fp64 from the fp32 inputs (the reference uses an fp32 LU; both round to the same fp32
@@ -155,6 +177,34 @@ using namespace imvs;
 extern "C" int imvs_abi_version(void) { return IMVS_ABI_VERSION; }
 extern "C" const char* imvs_last_error(void) { return err_buf(); }
 extern "C" long long imvs_launches_total(void) { return launches_total(); }
+
+// Profiling facility (NOT graph-capturable, synchronises in _end): records one CUDA-event pair
+// around every stage of imvs_itermvs_forward / imvs_featurenet_forward issued between begin and end.
+extern "C" int imvs_profile_begin(int capacity) {
+    IMVS_REQUIRE(!g_prof.active, "profile_begin: already active");
+    IMVS_REQUIRE(capacity > 0 && capacity <= 65536, "profile_begin: bad capacity");
+    g_prof.ev = new cudaEvent_t[2 * capacity];
+    g_prof.tags = new int[capacity];
+    for (int i = 0; i < 2 * capacity; ++i) IMVS_CUDA(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.cap = capacity; g_prof.n = 0; g_prof.active = true;
+    return 0;
+}
+extern "C" int imvs_profile_end(float* ms_out, int* tags_out, int capacity) {
+    IMVS_REQUIRE(g_prof.active, "profile_end: not active");
+    g_prof.active = false;
+    int n = g_prof.n < capacity ? g_prof.n : capacity;
+    if (g_prof.n > 0) IMVS_CUDA(cudaEventSynchronize(g_prof.ev[2 * g_prof.n - 1]));
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        IMVS_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+        ms_out[i] = ms; tags_out[i] = g_prof.tags[i];
+    }
+    for (int i = 0; i < 2 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
+    delete[] g_prof.ev; delete[] g_prof.tags;
+    g_prof.ev = nullptr; g_prof.tags = nullptr; g_prof.cap = 0;
+    int total = g_prof.n; g_prof.n = 0;
+    return -total;   // negative count = success with `total` records (0 -> none); positive = error
+}
 
 extern "C" int imvs_compose_projections(const float* proj, int B, int V, float* out, int* nan_flag, void* stream) {
     IMVS_REQUIRE(proj && out, "compose_projections: null pointer");

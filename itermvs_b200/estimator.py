@@ -12,6 +12,7 @@ path.  Parameters are re-packed to the kernel layout lazily whenever their versi
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -23,6 +24,18 @@ from ._pack import PackedWeights
 
 Tensor = torch.Tensor
 _LEVEL_DIM = {"level1": 16, "level2": 32, "level3": 48}
+
+# packed-weight caches live OUTSIDE the modules (ctypes structs must not be deep-copied / pickled
+# with a module): module -> {"key": versions, "val": packed}
+_PACK_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _cache_of(mod) -> dict:
+    c = _PACK_CACHE.get(mod)
+    if c is None:
+        c = {}
+        _PACK_CACHE[mod] = c
+    return c
 
 
 # ------------------------------------------------------------------------------ holders -------
@@ -62,7 +75,7 @@ class _WeightOwner:
         root = self._weight_root()
         params = dict(root.named_parameters())
         key = (str(device),) + tuple((k, p._version, p.data_ptr()) for k, p in params.items())
-        cache = root.__dict__.setdefault("_imvs_pack_cache", {})
+        cache = _cache_of(root)
         if cache.get("key") != key:
             cache["key"] = key
             cache["val"] = PackedWeights({k: p.detach() for k, p in params.items()}, device)
@@ -85,7 +98,7 @@ class DepthInitialization(nn.Module):
         return 1.0 / (inverse_depth_max + normalized * (inverse_depth_min - inverse_depth_max))
 
 
-class PixelViewWeight(nn.Module, _WeightOwner):
+class PixelViewWeight(nn.Module):
     """itermvs.py:333-350.  x [B,G,N,H,W] -> [B,1,H,W]."""
 
     def __init__(self, G):
@@ -136,7 +149,7 @@ class _StandaloneWeights:
     @staticmethod
     def _cached(mod, device, build):
         key = (str(device),) + tuple((k, p._version, p.data_ptr()) for k, p in mod.named_parameters())
-        cache = mod.__dict__.setdefault("_imvs_pack_cache", {})
+        cache = _cache_of(mod)
         if cache.get("key") != key:
             cache["key"], cache["val"] = key, build()
         return cache["val"]

@@ -1,0 +1,80 @@
+"""CUDA-graph replay of `Pipeline.forward` for a fixed input shape, and the stage profiler.
+
+The stock path issues ~1 500 kernel launches and 52 host synchronisations per reference view
+(SURVEY.md section 3.1); the CUDA path issues ~70 launches and never synchronises, so the whole forward
+(FeatureNet + estimator) can be captured once and replayed with a single launch.
+
+    g = GraphedPipeline(model, sample)        # sample: a representative batch (device tensors)
+    out = g(imgs, proj_matrices, depth_min, depth_max)   # same dict as Pipeline.forward
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import torch
+
+from . import _lib
+
+STAGE_NAMES = ["compose", "warpcorr_init", "pixel_view_weight", "aggregate_init", "corrnet", "hidden_init", "head",
+               "warpcorr_iter", "gru", "upsample", "featurenet"]
+
+
+class GraphedPipeline:
+    def __init__(self, model, imgs: Dict[str, torch.Tensor], proj_matrices: Dict[str, torch.Tensor],
+                 depth_min: torch.Tensor, depth_max: torch.Tensor, warmup: int = 3):
+        assert model.test and not model.training, "graph replay is for the inference pipeline (test=True, eval())"
+        self.model = model
+        dev = imgs["level_0"].device
+        # static inputs: only what Pipeline.forward reads (net.py:78-109): imgs['level_0'], proj level_1..3
+        self.s_img = imgs["level_0"].detach().clone().float().contiguous()
+        self.s_proj = {k: proj_matrices[k].detach().clone().float().contiguous() for k in ("level_1", "level_2", "level_3")}
+        self.s_dmin = depth_min.detach().clone().float().contiguous()
+        self.s_dmax = depth_max.detach().clone().float().contiguous()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.s_out = self._run()
+        self.nan_flag = model._last_nan_flag
+
+    def _run(self):
+        return self.model({"level_0": self.s_img}, self.s_proj, self.s_dmin, self.s_dmax)
+
+    def load_inputs(self, imgs, proj_matrices, depth_min, depth_max, non_blocking=True):
+        """Copies (H2D when the sources are pinned host tensors) into the graph's static inputs."""
+        self.s_img.copy_(imgs["level_0"], non_blocking=non_blocking)
+        for k in self.s_proj:
+            self.s_proj[k].copy_(proj_matrices[k], non_blocking=non_blocking)
+        self.s_dmin.copy_(depth_min, non_blocking=non_blocking)
+        self.s_dmax.copy_(depth_max, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.s_out
+
+    def __call__(self, imgs, proj_matrices, depth_min, depth_max):
+        self.load_inputs(imgs, proj_matrices, depth_min, depth_max)
+        return self.replay()
+
+
+def profile_stages(fn, capacity: int = 4096):
+    """Run fn() with the library's per-stage CUDA-event taps on; returns [(stage_name, ms), ...] in
+    issue order.  Synchronises; not capturable -- for bench.py's roofline / breakdown pass only."""
+    L = _lib.lib()
+    _lib.check(L.imvs_profile_begin(capacity), "profile_begin")
+    try:
+        fn()
+    finally:
+        ms = (C.c_float * capacity)()
+        tags = (C.c_int * capacity)()
+        rc = L.imvs_profile_end(ms, tags, capacity)
+    if rc > 0:
+        _lib.check(rc, "profile_end")
+    n = min(-rc, capacity)
+    return [(STAGE_NAMES[tags[i]], float(ms[i])) for i in range(n)]

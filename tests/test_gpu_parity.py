@@ -54,7 +54,8 @@ def test_differentiable_warping_golden(dev, stage_kats, tag):
     out = differentiable_warping(T(k[f"warp_{tag}_fea"]).to(dev), T(k[f"warp_{tag}_src_proj"]).to(dev),
                                  T(k[f"warp_{tag}_ref_proj"]).to(dev), T(k[f"warp_{tag}_depth"]).to(dev))
     assert out.shape == k[f"warp_{tag}_out"].shape
-    assert maxerr(out, T(k[f"warp_{tag}_out"])) < 5e-5
+    # white-noise features: |d fea / d px| ~ 3, fp32 position error ~2e-5 px  =>  ~1e-4 worst case
+    assert maxerr(out, T(k[f"warp_{tag}_out"])) < 2e-4
 
 
 def test_differentiable_warping_nan_assert(dev):
@@ -120,16 +121,17 @@ def test_window_regression_edges(dev, model):
     with torch.no_grad():
         for p in upd.parameters():
             p.zero_()
-        # hidden channel 0 carries t in [0,1]; conv0 centre tap copies it, fc1 copies, fc2: logit_c = -50*(c/255)^2 + 100*t*(c/255)
-        # => quadratic in c peaked at c* = 255*t
-        upd.depth_head[0].weight[0, 0, 1, 1] = 1.0
-        upd.depth_head[2].weight[0, 0, 0, 0] = 1.0
-        c = torch.arange(256, dtype=torch.float32) / 255
-        upd.depth_head[4].weight[:, 0, 0, 0] = 4000.0 * c
-        upd.depth_head[4].bias[:] = -2000.0 * c * c
-    targets = torch.tensor([0, 1, 2, 3, 4, 5, 100, 250, 251, 252, 253, 254, 255, 17, 64, 200], dtype=torch.float32)
+        # pixel j carries a one-hot hidden state on channel j; the centre taps of conv0 and fc1 copy it,
+        # fc2 turns it into logits 12 at bin target_j and 9 at bin target_j + 1 (small integers: exact)
+        targets = [0, 1, 2, 3, 4, 5, 100, 250, 251, 252, 253, 254, 255, 17, 64, 200]
+        for j, tj in enumerate(targets):
+            upd.depth_head[0].weight[j, j, 1, 1] = 1.0
+            upd.depth_head[2].weight[j, j, 0, 0] = 1.0
+            upd.depth_head[4].weight[tj, j, 0, 0] = 12.0
+            upd.depth_head[4].weight[min(tj + 1, 255), j, 0, 0] += 9.0
     h = torch.zeros(1, 32, 2, 8)
-    h[0, 0] = (targets / 255).view(2, 8)
+    for j in range(16):
+        h[0, j, j // 8, j % 8] = 1.0
     upd.return_probability = True
     nd, prob = upd.to(dev).depth_init(h.to(dev))
     w = {"iter_mvs.update." + k: v.detach().cpu() for k, v in upd.state_dict().items()}

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Run N eager forwards of the benchmark workload (for ncu captures; no timing, no CPU work)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import itermvs_b200  # noqa: E402
+from itermvs_b200.synthetic import make_sample  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+w, h, s_ = (int(x) for x in (sys.argv[2:5] if len(sys.argv) >= 5 else (640, 512, 4)))
+torch.backends.cudnn.allow_tf32 = False
+dev = torch.device("cuda:0")
+with np.load(os.path.join(ROOT, "tests", "golden", "dtu_weights.npz")) as z:
+    weights = {k: torch.from_numpy(z[k]) for k in z.files}
+model = itermvs_b200.Pipeline(iteration=4, test=True)
+model.load_state_dict(weights, strict=True)
+model = model.to(dev).eval()
+s = make_sample(w, h, n_src=s_, batch=1, seed=0, scene="plane")
+imgs = {"level_0": s["imgs"]["level_0"].to(dev)}
+proj = {k: v.float().to(dev) for k, v in s["proj_matrices"].items()}
+dmin, dmax = s["depth_min"].to(dev), s["depth_max"].to(dev)
+with torch.no_grad():
+    for i in range(n):
+        torch.cuda.nvtx.range_push(f"forward{i}")
+        out = model(imgs, proj, dmin, dmax)
+        torch.cuda.nvtx.range_pop()
+torch.cuda.synchronize()
+print("ok", float(out["depths_upsampled"].mean()))
