@@ -15,12 +15,15 @@
  *   - the library uses the caller's CURRENT device; re-entrant across host threads.
  *
  * Layouts  ("P_l" = H_l*W_l, level 1 = 1/2 res C=16, level 2 = 1/4 res C=32, level 3 = 1/8 res C=48)
- *   feature pyramids     [B][V][H_l][W_l][C_l]   channels-last, view 0 = reference view
- *   projection matrices  [B][V][4][4]            row-major, as produced by the reference loaders
- *   composed projections [B][S][12]              rot (3x3 row-major) then trans (3)
- *   correlation volumes  [B][slice][P][8]        8 = group-wise correlation channels, innermost
- *   maps / activations   [B][C][H][W]            planar (the reference's NCHW)
- *   conv weights         [Cin][k*k][Cout]        (packed by itermvs_b200/_pack.py from state_dict)
+ *   activations / features  [N][H][W][C]      channels-last ("NHWC"); pyramids are [B][V][H_l][W_l][C_l],
+ *                                             view 0 = reference view
+ *   projection matrices     [B][V][4][4]      row-major, as produced by the reference loaders
+ *   composed projections    [B][S][12]        rot (3x3 row-major) then trans (3)
+ *   correlation volumes     [B][slice][P][8]  8 = group-wise correlation channels, innermost
+ *   GRU input x             [B][H2][W2][16]   ch 0 = normalized depth, 1..10 = correlation, 11..15 = 0
+ *   conv weights            [tap][CinP][CoutP] CinP/CoutP = channels padded to a multiple of 8 with zeros,
+ *                                             values pre-rounded to TF32 ("hi"); "lo" = TF32(w - hi) for the
+ *                                             3-pass fp32-grade mode (packed by itermvs_b200/_pack.py)
  */
 #ifndef ITERMVS_B200_H_
 #define ITERMVS_B200_H_
@@ -32,57 +35,63 @@
 extern "C" {
 #endif
 
-#define IMVS_ABI_VERSION 1
+#define IMVS_ABI_VERSION 2
 #define IMVS_GROUPS 8          /* reference models/itermvs.py:28 */
 #define IMVS_OUT_BINS 256      /* reference models/itermvs.py:134 */
 #define IMVS_RADIUS 4          /* reference models/itermvs.py:135 */
 #define IMVS_HIDDEN 32         /* reference models/net.py:72 */
 #define IMVS_ITER_SLICES 10    /* 4 + 4 + 2 refinement samples, models/itermvs.py:231-235 */
+#define IMVS_XCH 16            /* stored channels of the GRU input x (11 used) */
 #define IMVS_MAX_VIEWS 16      /* source views per reference view supported by the fused kernels */
 
 int imvs_abi_version(void);
 const char* imvs_last_error(void);
+long long imvs_launches_total(void);
 
-/* ------------------------------------------------------------------------------------------
- * Weights of the estimator, already packed to [Cin][k*k][Cout] (transposed convs: [Cin][9][Cout]),
- * biases dense.  Key names are the reference's state_dict keys.
- * ---------------------------------------------------------------------------------------- */
+/* Tensor-core convolution precision: 1 = single-pass TF32 (what the reference's own cuDNN path uses on
+ * Ampere+ GPUs, torch.backends.cudnn.allow_tf32 = True by default), 3 = error-compensated 3-pass
+ * TF32 split (fp32-grade).  Process-wide; default 3. */
+int imvs_set_conv_passes(int passes);
+int imvs_get_conv_passes(void);
+
+typedef struct imvs_wpair { const float* hi; const float* lo; } imvs_wpair;   /* packed conv weight */
+
 typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */
-    const float* conv0;    /* conv0.conv.weight  8 -> 8            */
-    const float* conv1;    /* conv1.conv.weight  8 -> 16, stride 2 */
-    const float* conv2;    /* conv2.conv.weight 16 -> 32, stride 2 */
-    const float* conv3;    /* conv3.weight      32 -> 16, transposed stride 2 */
-    const float* conv4;    /* conv4.weight      16 -> 8,  transposed stride 2 */
-    const float* conv5;    /* conv5.weight       8 -> 1   */
-    const float* conv5_b;  /* conv5.bias [1]              */
+    imvs_wpair conv0;      /* conv0.conv.weight  8 -> 8            [9][8][8]   */
+    imvs_wpair conv1;      /* conv1.conv.weight  8 -> 16, stride 2 [9][8][16]  */
+    imvs_wpair conv2;      /* conv2.conv.weight 16 -> 32, stride 2 [9][16][32] */
+    imvs_wpair conv3;      /* conv3.weight      32 -> 16, transposed stride 2 [9][32][16] */
+    imvs_wpair conv4;      /* conv4.weight      16 -> 8,  transposed stride 2 [9][16][8]  */
+    imvs_wpair conv5;      /* conv5.weight       8 -> 1   [9][8][8] (cout padded) */
+    const float* conv5_b;  /* conv5.bias [1] */
 } imvs_corrnet_weights;
 
 typedef struct imvs_weights {
     /* evaluation.pixel_view_weight (models/itermvs.py:333-350) */
-    const float* pvw_conv0;        /* conv.0.conv.weight 8 -> 16 */
-    const float* pvw_conv1;        /* conv.1.weight [16] */
+    imvs_wpair pvw_conv0;          /* conv.0.conv.weight 8 -> 16  [9][8][16] */
+    const float* pvw_conv1;        /* conv.1.weight [16] (fp32) */
     const float* pvw_conv1_b;      /* conv.1.bias [1] */
     /* evaluation.corr_conv1[0..2] (level 1, 2, 3) */
     imvs_corrnet_weights corrnet[3];
-    /* update.gru (models/module.py:52-66): convz|convr stacked on Cout (64), convq (32) */
-    const float* gru_zr;           /* [43][9][64] */
+    /* update.gru (models/module.py:52-66): input channels = [h(32), x(16 stored, 11 used)] -> 48 */
+    imvs_wpair gru_zr;             /* convz|convr stacked on Cout: [9][48][64] */
     const float* gru_zr_b;         /* [64] */
-    const float* gru_q;            /* [43][9][32] */
+    imvs_wpair gru_q;              /* convq [9][48][32] */
     const float* gru_q_b;          /* [32] */
-    /* update.depth_head.0 | update.confidence_head.0 stacked on Cout (64) (itermvs.py:139-151) */
-    const float* head_conv0;       /* [32][9][64] : cout 0..31 depth head, 32..63 confidence head */
-    const float* head_fc1;         /* depth_head.2.weight  [32][64] */
+    /* update.depth_head.0 | update.confidence_head.0 stacked on Cout (itermvs.py:139-151) */
+    imvs_wpair head_conv0;         /* [9][32][64] : cout 0..31 depth head, 32..63 confidence head */
+    const float* head_fc1;         /* depth_head.2.weight  [32][64]  (fp32, FFMA epilogue kernel) */
     const float* head_fc2;         /* depth_head.4.weight  [64][256] */
     const float* head_fc2_b;       /* depth_head.4.bias    [256] */
     const float* conf_fc;          /* confidence_head.2.weight [32] */
     const float* conf_fc_b;        /* confidence_head.2.bias [1] */
     /* update.hidden_init_head (itermvs.py:153-157) */
-    const float* hinit_conv0;      /* [D][9][64] */
-    const float* hinit_fc;         /* [64][32] */
+    imvs_wpair hinit_conv0;        /* [9][D][64] */
+    imvs_wpair hinit_fc;           /* [1][64][32] */
     const float* hinit_fc_b;       /* [32] */
     /* iter_mvs.upsample (itermvs.py:246-250) */
-    const float* ups_conv0;        /* [32][9][64] */
-    const float* ups_fc;           /* [64][144] */
+    imvs_wpair ups_conv0;          /* [9][32][64] */
+    const float* ups_fc;           /* [64][144] (fp32) */
 } imvs_weights;
 
 /* ------------------------------------------------------------------------------------------
@@ -124,51 +133,54 @@ int imvs_aggregate_init(const float* corr, const float* vw3, float* agg, int B, 
 
 /* itermvs.py:289-293 + 86-120 -- fused iteration kernel: hypotheses from the normalized depth,
  * warp + sample of the three pyramids, group-wise correlation, pixel-wise view-weighted
- * aggregation.  nd [B][nd_stride] (first P2 entries used), vw2 [B][S][P2]; agg [B][10][P2][8]
- * (slices 0-3 level 1, 4-7 level 2, 8-9 level 3).  samples1/2/3: all NULL (hypotheses from nd) or all
- * given as explicit depths [B][4][P2], [B][4][P2], [B][2][P2] (Evaluation.forward's dict argument). */
+ * aggregation.  nd: normalized depth of pixel p of batch b at nd[b*nd_batch_stride + p*nd_pixel_stride];
+ * vw2 [B][S][P2]; agg [B][10][P2][8] (slices 0-3 level 1, 4-7 level 2, 8-9 level 3).
+ * samples1/2/3: all NULL (hypotheses from nd) or all given as explicit depths [B][4][P2], [B][4][P2],
+ * [B][2][P2] (Evaluation.forward's dict argument). */
 int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
                        const float* rt1, const float* rt2, const float* rt3,
-                       const float* nd, size_t nd_batch_stride, const float* vw2,
+                       const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
                        const float* depth_min, const float* depth_max,
                        const float* samples1, const float* samples2, const float* samples3, float* agg,
                        int B, int V, int H2, int W2, void* stream);
 
 /* itermvs.py:367-381 -- CorrNet on N slices of a [N][P][8] volume.  Slice n uses weight set
- * sets[(n % period) < split1 ? 0 : (n % period) < split2 ? 1 : 2].  out[(n / period) * out_batch_stride
- * + (n % period) * H*W + p].  scratch: imvs_corrnet_scratch_floats(N,H,W) floats. */
+ * sets[(n % period) < split1 ? 0 : (n % period) < split2 ? 1 : 2].  The scalar output of slice n, pixel p
+ * goes to out[(n / period) * out_batch_stride + p * out_pixel_stride + (n % period)].
+ * scratch: imvs_corrnet_scratch_floats(N,H,W) floats. */
 size_t imvs_corrnet_scratch_floats(int N, int H, int W);
 int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int split1, int split2, const float* vol,
-                 float* out, size_t out_batch_stride, float* scratch, int N, int H, int W, void* stream);
+                 float* out, size_t out_batch_stride, size_t out_pixel_stride, float* scratch,
+                 int N, int H, int W, void* stream);
 
-/* itermvs.py:159-164 -- hidden_init: corr [B][D][H3][W3] -> hidden [B][32][2*H3][2*W3].
- * scratch: B*(64+32)*H3*W3 floats. */
+/* itermvs.py:159-164 -- hidden_init: corr [B][H3][W3][D] -> hidden [B][2*H3][2*W3][32].
+ * scratch: B*(64+32)*H3*W3 floats.  D must be a multiple of 8. */
 int imvs_hidden_init(const imvs_weights* w, const float* corr, float* hidden, float* scratch,
                      int B, int D, int H3, int W3, void* stream);
 
-/* module.py:59-66 -- ConvGRU.forward(h, x) with x = 11 channels (itermvs.py:193), in place on h.
- * h [B][32][H][W], x [B][11][H][W]; scratch 2*B*32*H*W floats (z and r*h). */
+/* module.py:59-66 -- ConvGRU.forward(h, x), in place on h.
+ * h [B][H][W][32], x [B][H][W][16] (channels 11..15 must be zero); scratch 2*B*32*H*W floats. */
 int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, float* scratch, int B, int H, int W, void* stream);
 
-/* itermvs.py:171-190 / 196-219 -- depth_head (+ confidence_head when conf != NULL), softmax over
- * 256 bins, arg-max, clamped +-4 window regression.  hidden [B][32][H][W].
- *   nd_out        [B][nd_batch_stride]  normalized depth (first H*W entries of each batch written)
- *   probability   [B][256][H][W] or NULL (training needs it, itermvs.py:282,302)
+/* itermvs.py:171-190 / 196-219 -- depth_head (+ confidence_head when conf or conf_logit != NULL),
+ * softmax over 256 bins, arg-max, clamped +-4 window regression.  hidden [B][H][W][32].
+ *   nd_out        normalized depth of pixel p, batch b -> nd_out[b*nd_batch_stride + p*nd_pixel_stride]
+ *   probability   [B][256][H][W] (the reference's layout) or NULL (training needs it, itermvs.py:282,302)
  *   conf / conf_logit [B][H][W] or NULL (sigmoid / raw)
  *   depth_out     [B][H][W] or NULL: depth_unnormalization of nd_out (module.py:148-152)
  * scratch: B*64*H*W floats. */
 int imvs_depth_head(const imvs_weights* w, const float* hidden, float* nd_out, size_t nd_batch_stride,
-                    float* probability, float* conf, float* conf_logit, float* depth_out,
+                    size_t nd_pixel_stride, float* probability, float* conf, float* conf_logit, float* depth_out,
                     const float* depth_min, const float* depth_max, float* scratch,
                     int B, int H, int W, void* stream);
 
 /* itermvs.py:262-264 + module.py:127-140 + itermvs.py:321-324 -- output stage: upsampling-weight
- * net on the level-2 reference feature (planar [B][32][H2][W2]), softmax over the 9 taps, convex
- * x4 upsampling of nd, depth_unnormalization; bilinear x4 of the confidence.
+ * net on the level-2 reference feature (NHWC [H2][W2][32], image b at ref_fea2 + b*ref_batch_stride),
+ * softmax over the 9 taps, convex x4 upsampling of nd, depth_unnormalization; bilinear x4 of the confidence.
  * depth_up / conf_up [B][4*H2][4*W2]; conf may be NULL (then conf_up is not written).
  * scratch: B*64*H2*W2 floats. */
-int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea2_planar, const float* nd,
-                          size_t nd_batch_stride, const float* conf, const float* depth_min,
+int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea2, size_t ref_batch_stride, const float* nd,
+                          size_t nd_batch_stride, size_t nd_pixel_stride, const float* conf, const float* depth_min,
                           const float* depth_max, float* depth_up, float* conf_up, float* scratch,
                           int B, int H2, int W2, void* stream);
 
@@ -179,18 +191,18 @@ typedef struct imvs_problem {
     int B;            /* reference views in this call */
     int V;            /* views per reference view (1 + source views) */
     int H, W;         /* full-resolution image size, multiples of 32 */
-    int D;            /* initial hypotheses (32 in the reference, itermvs.py:237) */
+    int D;            /* initial hypotheses (32 in the reference, itermvs.py:237); multiple of 8 */
     int iterations;   /* GRU iterations (>= 1) */
 } imvs_problem;
 
 size_t imvs_forward_workspace_bytes(const imvs_problem* pb);
 
-/* fea1/2/3: channels-last pyramids [B][V][H_l][W_l][C_l]; ref_fea2_planar [B][32][H2][W2];
- * proj1/2/3: [B][V][4][4] fp32.  Outputs (any may be NULL): depth [B][H2][W2] (pre-last-update value,
- * itermvs.py:319), depth_up [B][H][W], conf [B][H2][W2], conf_up [B][H][W].
+/* fea1/2/3: channels-last pyramids [B][V][H_l][W_l][C_l]; proj1/2/3: [B][V][4][4] fp32.
+ * Outputs (any may be NULL): depth [B][H2][W2] (pre-last-update value, itermvs.py:319),
+ * depth_up [B][H][W], conf [B][H2][W2], conf_up [B][H][W].
  * nan_flag: device int, set to 1 on NaN projections (checked by the caller when it next syncs). */
 int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,
-                         const float* fea1, const float* fea2, const float* fea3, const float* ref_fea2_planar,
+                         const float* fea1, const float* fea2, const float* fea3,
                          const float* proj1, const float* proj2, const float* proj3,
                          const float* depth_min, const float* depth_max,
                          void* workspace, size_t workspace_bytes,
@@ -199,6 +211,25 @@ int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,
 
 /* number of kernel launches one imvs_itermvs_forward issues for this problem (for bench.py's gpu_launches) */
 int imvs_forward_launch_count(const imvs_problem* pb);
+
+/* ------------------------------------------------------------------------------------------
+ * FeatureNet (net.py:7-66), eval mode, BatchNorm folded into the convolutions by the packer.
+ * imgs [N][3][H][W] (N = B*V views) -> channels-last pyramids fea1 [N][H/2][W/2][16],
+ * fea2 [N][H/4][W/4][32], fea3 [N][H/8][W/8][48].
+ * ---------------------------------------------------------------------------------------- */
+#define IMVS_FNET_CONVS 22
+typedef struct imvs_featurenet_weights {
+    imvs_wpair w[IMVS_FNET_CONVS];      /* order documented in itermvs_b200/_pack.py:FNET_LAYERS */
+    const float* b[IMVS_FNET_CONVS];    /* per-layer bias (folded BN shift or conv bias) */
+} imvs_featurenet_weights;
+size_t imvs_featurenet_workspace_bytes(int N, int H, int W);
+int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs, float* fea1, float* fea2, float* fea3,
+                            void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream);
+int imvs_featurenet_launch_count(void);
+
+/* profiling taps (bench.py): CUDA-event pair around every stage of the two forward functions */
+int imvs_profile_begin(int capacity);
+int imvs_profile_end(float* ms_out, int* tags_out, int capacity);
 
 #ifdef __cplusplus
 }

@@ -18,18 +18,26 @@ _lib = None
 vp = C.c_void_p
 ci = C.c_int
 sz = C.c_size_t
+ABI_VERSION = 2
+FNET_CONVS = 22
+
+
+class WPair(C.Structure):
+    _fields_ = [("hi", vp), ("lo", vp)]
 
 
 class CorrNetWeights(C.Structure):
-    _fields_ = [(n, vp) for n in ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv5_b")]
+    _fields_ = [(n, WPair) for n in ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5")] + [("conv5_b", vp)]
 
 
 class Weights(C.Structure):
-    _fields_ = ([(n, vp) for n in ("pvw_conv0", "pvw_conv1", "pvw_conv1_b")]
-                + [("corrnet", CorrNetWeights * 3)]
-                + [(n, vp) for n in ("gru_zr", "gru_zr_b", "gru_q", "gru_q_b",
-                                     "head_conv0", "head_fc1", "head_fc2", "head_fc2_b", "conf_fc", "conf_fc_b",
-                                     "hinit_conv0", "hinit_fc", "hinit_fc_b", "ups_conv0", "ups_fc")])
+    _fields_ = [("pvw_conv0", WPair), ("pvw_conv1", vp), ("pvw_conv1_b", vp),
+                ("corrnet", CorrNetWeights * 3),
+                ("gru_zr", WPair), ("gru_zr_b", vp), ("gru_q", WPair), ("gru_q_b", vp),
+                ("head_conv0", WPair), ("head_fc1", vp), ("head_fc2", vp), ("head_fc2_b", vp),
+                ("conf_fc", vp), ("conf_fc_b", vp),
+                ("hinit_conv0", WPair), ("hinit_fc", WPair), ("hinit_fc_b", vp),
+                ("ups_conv0", WPair), ("ups_fc", vp)]
 
 
 class Problem(C.Structure):
@@ -37,13 +45,16 @@ class Problem(C.Structure):
 
 
 class FeatureNetWeights(C.Structure):
-    _fields_ = [("w", vp * 32), ("b", vp * 32)]
+    _fields_ = [("w", WPair * FNET_CONVS), ("b", vp * FNET_CONVS)]
 
 
+PW = C.POINTER(Weights)
 _SIGNATURES = {
     "imvs_abi_version": (ci, []),
     "imvs_last_error": (C.c_char_p, []),
     "imvs_launches_total": (C.c_longlong, []),
+    "imvs_set_conv_passes": (ci, [ci]),
+    "imvs_get_conv_passes": (ci, []),
     "imvs_profile_begin": (ci, [ci]),
     "imvs_profile_end": (ci, [vp, vp, ci]),
     "imvs_compose_projections": (ci, [vp, ci, ci, vp, vp, vp]),
@@ -51,24 +62,21 @@ _SIGNATURES = {
     "imvs_nchw_to_nhwc": (ci, [vp, vp, ci, ci, ci, ci, vp]),
     "imvs_nhwc_to_nchw": (ci, [vp, vp, ci, ci, ci, ci, vp]),
     "imvs_warpcorr_init": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
-    "imvs_pixel_view_weight": (ci, [C.POINTER(Weights), vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "imvs_pixel_view_weight": (ci, [PW, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "imvs_aggregate_init": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
-    "imvs_warpcorr_iter": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "imvs_warpcorr_iter": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_corrnet_scratch_floats": (sz, [ci, ci, ci]),
-    "imvs_corrnet": (ci, [C.POINTER(CorrNetWeights), ci, ci, ci, vp, vp, sz, vp, ci, ci, ci, vp]),
-    "imvs_hidden_init": (ci, [C.POINTER(Weights), vp, vp, vp, ci, ci, ci, ci, vp]),
-    "imvs_conv_gru": (ci, [C.POINTER(Weights), vp, vp, vp, ci, ci, ci, vp]),
-    "imvs_depth_head": (ci, [C.POINTER(Weights), vp, vp, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]),
-    "imvs_upsample_outputs": (ci, [C.POINTER(Weights), vp, vp, sz, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]),
+    "imvs_corrnet": (ci, [C.POINTER(CorrNetWeights), ci, ci, ci, vp, vp, sz, sz, vp, ci, ci, ci, vp]),
+    "imvs_hidden_init": (ci, [PW, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "imvs_conv_gru": (ci, [PW, vp, vp, vp, ci, ci, ci, vp]),
+    "imvs_depth_head": (ci, [PW, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]),
+    "imvs_upsample_outputs": (ci, [PW, vp, sz, vp, sz, sz, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]),
     "imvs_forward_workspace_bytes": (sz, [C.POINTER(Problem)]),
     "imvs_forward_launch_count": (ci, [C.POINTER(Problem)]),
-    "imvs_itermvs_forward": (ci, [C.POINTER(Problem), C.POINTER(Weights), vp, vp, vp, vp, vp, vp, vp, vp, vp,
+    "imvs_itermvs_forward": (ci, [C.POINTER(Problem), PW, vp, vp, vp, vp, vp, vp, vp, vp,
                                   vp, sz, vp, vp, vp, vp, vp, vp]),
-}
-# entry points that later revisions add; bound when present
-_OPTIONAL = {
     "imvs_featurenet_workspace_bytes": (sz, [ci, ci, ci]),
-    "imvs_featurenet_forward": (ci, [C.POINTER(FeatureNetWeights), vp, vp, vp, vp, vp, vp, sz, ci, ci, ci, vp]),
+    "imvs_featurenet_forward": (ci, [C.POINTER(FeatureNetWeights), vp, vp, vp, vp, vp, sz, ci, ci, ci, vp]),
     "imvs_featurenet_launch_count": (ci, []),
 }
 
@@ -100,12 +108,8 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        for name, (res, args) in _OPTIONAL.items():
-            if hasattr(handle, name):
-                fn = getattr(handle, name)
-                fn.restype, fn.argtypes = res, args
-        if handle.imvs_abi_version() != 1:
-            raise LibraryMissing(f"itermvs_b200: ABI version mismatch in {path}")
+        if handle.imvs_abi_version() != ABI_VERSION:
+            raise LibraryMissing(f"itermvs_b200: ABI version mismatch in {path} (rebuild with python -m itermvs_b200._build --force)")
         _lib = handle
         return _lib
 
@@ -122,3 +126,12 @@ def check(rc: int, what: str = "") -> None:
 
 def launches_total() -> int:
     return int(lib().imvs_launches_total())
+
+
+def set_conv_passes(passes: int) -> None:
+    """1 = single-pass TF32 tensor-core convolutions, 3 = 3xTF32 error-compensated (fp32-grade, default)."""
+    check(lib().imvs_set_conv_passes(int(passes)), "set_conv_passes")
+
+
+def get_conv_passes() -> int:
+    return int(lib().imvs_get_conv_passes())

@@ -1,14 +1,19 @@
-"""Pack the estimator's parameters (reference state_dict names) into the kernel layouts of
-include/itermvs_b200.h: conv weights [Cin][k*k][Cout], transposed convs [Cin][9][Cout].
+"""Pack parameters (reference state_dict names) into the kernel layouts of include/itermvs_b200.h.
 
-The packed tensors are plain device tensors owned by a `PackedWeights` object; `struct` is the
-`imvs_weights` C struct pointing at them.  Repack whenever parameters change (training) -- the
-modules in estimator.py key the cache on the parameters' `_version` counters.
+Tensor-core convolutions take weights as [tap][CinP][CoutP] (channels zero-padded to multiples of
+8), split into hi = TF32(w) and lo = TF32(w - hi) (round-to-nearest, ties away from zero -- the
+same rounding as `cvt.rna.tf32.f32`), so the kernels need no conversion on the weight operand and
+the 3-pass mode recovers fp32-grade products.  FeatureNet's BatchNorm (eval mode, running
+statistics, eps 1e-5) is folded into the preceding convolution.
+
+Packed tensors are plain device tensors owned by the Packed* objects; `.struct` is the C struct
+pointing at them.  Repack whenever parameters change -- the modules key their cache on the
+parameters' version counters.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict
+from typing import Dict, Tuple
 
 import torch
 
@@ -17,80 +22,163 @@ from . import _lib
 Tensor = torch.Tensor
 
 
-def pack_conv(w: Tensor) -> Tensor:
-    """nn.Conv2d weight [Cout,Cin,k,k] -> [Cin][k*k][Cout]."""
+def round_tf32(x: Tensor) -> Tensor:
+    """cvt.rna.tf32.f32: keep 10 mantissa bits, round to nearest, ties away from zero."""
+    bits = x.contiguous().view(torch.int32)
+    r = ((bits + 0x1000) & ~0x1FFF) if True else bits
+    # (two's-complement add on the sign-magnitude pattern raises the magnitude for both signs)
+    return r.view(torch.float32)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def split_tf32(w: Tensor) -> Tuple[Tensor, Tensor]:
+    hi = round_tf32(w)
+    lo = round_tf32(w - hi)
+    return hi.contiguous(), lo.contiguous()
+
+
+def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0) -> Tuple[Tensor, Tensor]:
+    """nn.Conv2d weight [Cout,Cin,kh,kw] -> (hi, lo) each [kh*kw][CinP][CoutP]."""
     co, cin, kh, kw = w.shape
-    return w.detach().float().permute(1, 2, 3, 0).reshape(cin, kh * kw, co).contiguous()
+    cinp, coutp = cinp or _pad8(cin), coutp or _pad8(co)
+    out = torch.zeros(kh * kw, cinp, coutp, device=w.device, dtype=torch.float32)
+    out[:, :cin, :co] = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, cin, co)
+    return split_tf32(out)
 
 
-def pack_tconv(w: Tensor) -> Tensor:
-    """nn.ConvTranspose2d weight [Cin,Cout,k,k] -> [Cin][k*k][Cout]."""
+def pack_mma_tconv(w: Tensor) -> Tuple[Tensor, Tensor]:
+    """nn.ConvTranspose2d weight [Cin,Cout,kh,kw] -> (hi, lo) each [kh*kw][CinP][CoutP]."""
     cin, co, kh, kw = w.shape
-    return w.detach().float().permute(0, 2, 3, 1).reshape(cin, kh * kw, co).contiguous()
+    out = torch.zeros(kh * kw, _pad8(cin), _pad8(co), device=w.device, dtype=torch.float32)
+    out[:, :cin, :co] = w.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cin, co)
+    return split_tf32(out)
+
+
+def pack_fc(w: Tensor) -> Tensor:
+    """1x1 conv weight [Cout,Cin,1,1] -> fp32 [Cin][Cout] (FFMA epilogue kernels)."""
+    return w.detach().float().reshape(w.shape[0], w.shape[1]).t().contiguous()
 
 
 def _vec(t: Tensor) -> Tensor:
     return t.detach().float().reshape(-1).contiguous()
 
 
-_CORR_FIELDS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv5_b")
+_CORR_CONVS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5")
 
 
-class PackedWeights:
+class _Holder:
+    def __init__(self):
+        self.keep = []
+
+    def pair(self, hl) -> _lib.WPair:
+        self.keep.extend(hl)
+        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr())
+
+    def ptr(self, t: Tensor) -> int:
+        self.keep.append(t)
+        return t.data_ptr()
+
+
+def fill_corrnet(h: _Holder, dst: _lib.CorrNetWeights, sd: Dict[str, Tensor], prefix: str, dev) -> None:
+    g = lambda k: sd[prefix + k].to(dev)
+    dst.conv0 = h.pair(pack_mma_conv(g("conv0.conv.weight")))
+    dst.conv1 = h.pair(pack_mma_conv(g("conv1.conv.weight")))
+    dst.conv2 = h.pair(pack_mma_conv(g("conv2.conv.weight")))
+    dst.conv3 = h.pair(pack_mma_tconv(g("conv3.weight")))
+    dst.conv4 = h.pair(pack_mma_tconv(g("conv4.weight")))
+    dst.conv5 = h.pair(pack_mma_conv(g("conv5.weight")))
+    dst.conv5_b = h.ptr(_vec(g("conv5.bias")))
+
+
+def fill_pvw(h: _Holder, s: _lib.Weights, sd, prefix, dev) -> None:
+    g = lambda k: sd[prefix + k].to(dev)
+    s.pvw_conv0 = h.pair(pack_mma_conv(g("conv.0.conv.weight")))
+    s.pvw_conv1 = h.ptr(_vec(g("conv.1.weight")))
+    s.pvw_conv1_b = h.ptr(_vec(g("conv.1.bias")))
+
+
+def fill_gru(h: _Holder, s: _lib.Weights, sd, prefix, dev) -> None:
+    g = lambda k: sd[prefix + k].to(dev)
+    # input channels [h(32), x(11)] -> stored [h(32), x(16)]: zero rows for the 5 padding channels
+    s.gru_zr = h.pair(pack_mma_conv(torch.cat([g("convz.weight"), g("convr.weight")], 0), cinp=48))
+    s.gru_zr_b = h.ptr(_vec(torch.cat([g("convz.bias"), g("convr.bias")], 0)))
+    s.gru_q = h.pair(pack_mma_conv(g("convq.weight"), cinp=48))
+    s.gru_q_b = h.ptr(_vec(g("convq.bias")))
+
+
+def fill_update(h: _Holder, s: _lib.Weights, sd, prefix, dev) -> None:
+    g = lambda k: sd[prefix + k].to(dev)
+    fill_gru(h, s, sd, prefix + "gru.", dev)
+    s.head_conv0 = h.pair(pack_mma_conv(torch.cat([g("depth_head.0.weight"), g("confidence_head.0.weight")], 0)))
+    s.head_fc1 = h.ptr(pack_fc(g("depth_head.2.weight")))
+    s.head_fc2 = h.ptr(pack_fc(g("depth_head.4.weight")))
+    s.head_fc2_b = h.ptr(_vec(g("depth_head.4.bias")))
+    s.conf_fc = h.ptr(_vec(g("confidence_head.2.weight")))
+    s.conf_fc_b = h.ptr(_vec(g("confidence_head.2.bias")))
+    s.hinit_conv0 = h.pair(pack_mma_conv(g("hidden_init_head.0.weight")))
+    s.hinit_fc = h.pair(pack_mma_conv(g("hidden_init_head.2.weight")))
+    s.hinit_fc_b = h.ptr(_vec(g("hidden_init_head.2.bias")))
+
+
+class PackedWeights(_Holder):
     """sd: {name: tensor} with names relative to the IterMVS module
     ('evaluation.pixel_view_weight.conv.0.conv.weight', 'update.gru.convz.weight', ...)."""
 
     def __init__(self, sd: Dict[str, Tensor], device: torch.device):
-        g = lambda k: sd[k].to(device)
-        keep = {}
-        ev, up = "evaluation.", "update."
-        keep["pvw_conv0"] = pack_conv(g(ev + "pixel_view_weight.conv.0.conv.weight"))
-        keep["pvw_conv1"] = _vec(g(ev + "pixel_view_weight.conv.1.weight"))
-        keep["pvw_conv1_b"] = _vec(g(ev + "pixel_view_weight.conv.1.bias"))
-        for i in range(3):
-            p = f"{ev}corr_conv1.{i}."
-            keep[f"c{i}.conv0"] = pack_conv(g(p + "conv0.conv.weight"))
-            keep[f"c{i}.conv1"] = pack_conv(g(p + "conv1.conv.weight"))
-            keep[f"c{i}.conv2"] = pack_conv(g(p + "conv2.conv.weight"))
-            keep[f"c{i}.conv3"] = pack_tconv(g(p + "conv3.weight"))
-            keep[f"c{i}.conv4"] = pack_tconv(g(p + "conv4.weight"))
-            keep[f"c{i}.conv5"] = pack_conv(g(p + "conv5.weight"))
-            keep[f"c{i}.conv5_b"] = _vec(g(p + "conv5.bias"))
-        keep["gru_zr"] = pack_conv(torch.cat([g(up + "gru.convz.weight"), g(up + "gru.convr.weight")], 0))
-        keep["gru_zr_b"] = _vec(torch.cat([g(up + "gru.convz.bias"), g(up + "gru.convr.bias")], 0))
-        keep["gru_q"] = pack_conv(g(up + "gru.convq.weight"))
-        keep["gru_q_b"] = _vec(g(up + "gru.convq.bias"))
-        keep["head_conv0"] = pack_conv(torch.cat([g(up + "depth_head.0.weight"), g(up + "confidence_head.0.weight")], 0))
-        keep["head_fc1"] = pack_conv(g(up + "depth_head.2.weight"))
-        keep["head_fc2"] = pack_conv(g(up + "depth_head.4.weight"))
-        keep["head_fc2_b"] = _vec(g(up + "depth_head.4.bias"))
-        keep["conf_fc"] = _vec(g(up + "confidence_head.2.weight"))
-        keep["conf_fc_b"] = _vec(g(up + "confidence_head.2.bias"))
-        keep["hinit_conv0"] = pack_conv(g(up + "hidden_init_head.0.weight"))
-        keep["hinit_fc"] = pack_conv(g(up + "hidden_init_head.2.weight"))
-        keep["hinit_fc_b"] = _vec(g(up + "hidden_init_head.2.bias"))
-        keep["ups_conv0"] = pack_conv(g("upsample.0.weight"))
-        keep["ups_fc"] = pack_conv(g("upsample.2.weight"))
-        self.tensors = keep
-        self.num_sample = int(sd[up + "hidden_init_head.0.weight"].shape[1])
+        super().__init__()
         s = _lib.Weights()
-        for name in ("pvw_conv0", "pvw_conv1", "pvw_conv1_b", "gru_zr", "gru_zr_b", "gru_q", "gru_q_b", "head_conv0",
-                     "head_fc1", "head_fc2", "head_fc2_b", "conf_fc", "conf_fc_b", "hinit_conv0", "hinit_fc",
-                     "hinit_fc_b", "ups_conv0", "ups_fc"):
-            setattr(s, name, keep[name].data_ptr())
+        fill_pvw(self, s, sd, "evaluation.pixel_view_weight.", device)
         for i in range(3):
-            for f in _CORR_FIELDS:
-                setattr(s.corrnet[i], f, keep[f"c{i}.{f}"].data_ptr())
+            fill_corrnet(self, s.corrnet[i], sd, f"evaluation.corr_conv1.{i}.", device)
+        fill_update(self, s, sd, "update.", device)
+        s.ups_conv0 = self.pair(pack_mma_conv(sd["upsample.0.weight"].to(device)))
+        s.ups_fc = self.ptr(pack_fc(sd["upsample.2.weight"].to(device)))
+        self.num_sample = int(sd["update.hidden_init_head.0.weight"].shape[1])
         self.struct = s
 
     @property
     def ref(self):
         return C.byref(self.struct)
 
-    def corrnet_sets(self, a: int, b: int, c: int):
-        """A C array of three CorrNet weight sets (indices into corr_conv1) for imvs_corrnet."""
-        arr = (_lib.CorrNetWeights * 3)()
-        for j, i in enumerate((a, b, c)):
-            for f in _CORR_FIELDS:
-                setattr(arr[j], f, getattr(self.struct.corrnet[i], f))
-        return arr
+
+# FeatureNet layer order of imvs_featurenet_weights (include/itermvs_b200.h):
+#   (state_dict prefix, has_bn)
+FNET_LAYERS = [("conv1.", True)]
+for _l in (1, 2, 3):
+    FNET_LAYERS += [(f"layer{_l}.0.conv1.", True), (f"layer{_l}.0.conv2.", True), (f"layer{_l}.0.downsample.", True),
+                    (f"layer{_l}.1.conv1.", True), (f"layer{_l}.1.conv2.", True)]
+FNET_LAYERS += [("output3.", False), ("inner2.", False), ("output2.", False), ("inner1.", False), ("output1.", False)]
+
+
+def fold_bn(sd: Dict[str, Tensor], prefix: str, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
+    """conv (no bias) + BatchNorm2d(eval) -> conv weight, bias  (module.py:6-29)."""
+    w = sd[prefix + "conv.weight"].float()
+    scale = sd[prefix + "bn.weight"].float() / torch.sqrt(sd[prefix + "bn.running_var"].float() + eps)
+    return w * scale.view(-1, 1, 1, 1), sd[prefix + "bn.bias"].float() - sd[prefix + "bn.running_mean"].float() * scale
+
+
+class PackedFeatureNet(_Holder):
+    """sd: FeatureNet state_dict (names relative to the module), eval-mode semantics."""
+
+    def __init__(self, sd: Dict[str, Tensor], device: torch.device):
+        super().__init__()
+        s = _lib.FeatureNetWeights()
+        sd = {k: v.to(device) for k, v in sd.items()}
+        for i, (prefix, has_bn) in enumerate(FNET_LAYERS):
+            if has_bn:
+                w, b = fold_bn(sd, prefix)
+            else:
+                w, b = sd[prefix + "weight"].float(), sd[prefix + "bias"].float()
+            s.w[i] = self.pair(pack_mma_conv(w))
+            s.b[i] = self.ptr(_vec(b))
+        # unused trailing slot: keep pointers valid
+        s.w[len(FNET_LAYERS)] = s.w[0]
+        s.b[len(FNET_LAYERS)] = s.b[0]
+        self.struct = s
+
+    @property
+    def ref(self):
+        return C.byref(self.struct)

@@ -1,59 +1,60 @@
 // The small convolutional nets of the evaluation stage and hidden-state initialisation:
 //   CorrNet (itermvs.py:352-381), PixelViewWeight (itermvs.py:333-350, 53-57), hidden_init
-//   (itermvs.py:153-164).  All built on the register-blocked direct convolution of conv.cuh.
+//   (itermvs.py:153-164) -- all on the tensor-core implicit-GEMM convolution of mmaconv.cuh,
+//   activations channels-last.
 #include "common.cuh"
-#include "conv.cuh"
+#include "mmaconv.cuh"
 
 namespace imvs {
 
 // ------------------------------------------------------------------------------- CorrNet ----
-struct EpiCorrOut {          // conv5: + bias, scatter slice n -> out[(n/period)*batch_stride + (n%period)*HW + p]
+struct EpiCorrOut {          // conv5 (1 valid cout): + bias, scatter to out[(n/period)*bstride + p*pstride + n%period]
     float* out;
     const float* bias[3];
     int period, split1, split2;
-    size_t batch_stride;
+    size_t bstride, pstride;
     int H, W;
-    template <int CO>
-    __device__ __forceinline__ void store(int n, int y, int x, int, const float (&a)[CO]) const {
-        int r = n % period;
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int, int t, const float (&v)[2 * NT]) const {
+        if (t != 0 || oy >= H || ox >= W) return;
+        const int r = n % period;
         const float* b = r < split1 ? bias[0] : (r < split2 ? bias[1] : bias[2]);
-        out[(size_t)(n / period) * batch_stride + (size_t)r * H * W + (size_t)y * W + x] = a[0] + ldg(b);
+        out[(size_t)(n / period) * bstride + ((size_t)oy * W + ox) * pstride + r] = v[0] + ldg(b);
     }
 };
 
-using CfgCorr0 = ConvCfg<8, 8, 8, 4, 4, 3, 1, 1, 8>;      // cl8 -> 8, relu
-using CfgCorr1 = ConvCfg<16, 16, 8, 4, 2, 3, 2, 1, 1>;    // 8 -> 16, stride 2, relu
-using CfgCorr2 = ConvCfg<32, 32, 8, 4, 2, 3, 2, 1, 1>;    // 16 -> 32, stride 2, relu
-using CfgCorr5 = ConvCfg<1, 1, 1, 4, 4, 3, 1, 1, 1>;      // 8 -> 1
-
-static WeightSel sel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
-    WeightSel s;
+static MmaWeightSel sel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
+    MmaWeightSel s;
     for (int i = 0; i < 3; ++i) {
         const imvs_corrnet_weights& c = sets[i];
-        const float* p = which == 0 ? c.conv0 : which == 1 ? c.conv1 : which == 2 ? c.conv2
-                       : which == 3 ? c.conv3 : which == 4 ? c.conv4 : c.conv5;
-        s.w[i] = p;
+        const imvs_wpair p = which == 0 ? c.conv0 : which == 1 ? c.conv1 : which == 2 ? c.conv2
+                           : which == 3 ? c.conv3 : which == 4 ? c.conv4 : c.conv5;
+        s.hi[i] = p.hi; s.lo[i] = p.lo;
     }
     s.period = period; s.split1 = split1; s.split2 = split2;
     return s;
 }
 
 // ------------------------------------------------------------------------ PixelViewWeight ----
-struct EpiPvw {              // relu(16) . w1 + b1 -> logits[n][y][x]
-    float* logits;
+struct EpiPvw {              // relu(16 channels) . w1 + b1 -> logits[n][y][x]; the 16 channels of a pixel
+    float* logits;           // are spread over the 4 lanes of a quad -> two xor-shuffles
     const float* w1;
     const float* b1;
     int H, W;
-    template <int CO>
-    __device__ __forceinline__ void store(int n, int y, int x, int, const float (&a)[CO]) const {
-        static_assert(CO == 16, "PixelViewWeight epilogue needs all 16 channels in one thread");
-        float s = ldg(b1);
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+        float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < CO; ++c) s = fmaf(fmaxf(a[c], 0.f), ldg(w1 + c), s);
-        logits[((size_t)n * H + y) * W + x] = s;
+        for (int j = 0; j < NT; ++j) {
+            const int co = co0 + 8 * j + 2 * t;
+            s = fmaf(fmaxf(v[2 * j], 0.f), ldg(w1 + co), s);
+            s = fmaf(fmaxf(v[2 * j + 1], 0.f), ldg(w1 + co + 1), s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (t == 0 && oy < H && ox < W) logits[((size_t)n * H + oy) * W + ox] = s + ldg(b1);
     }
 };
-using CfgPvw = ConvCfg<16, 16, 16, 4, 4, 3, 1, 1, 8>;
 
 // softmax over D then max over D == 1 / sum_d exp(l_d - max_d l)   (itermvs.py:347-348)
 __global__ void pvw_reduce_kernel(const float* __restrict__ logits, float* __restrict__ vw3, int BS, int D, int P3) {
@@ -68,26 +69,40 @@ __global__ void pvw_reduce_kernel(const float* __restrict__ logits, float* __res
     vw3[t] = 1.0f / s;
 }
 
-// F.interpolate(scale_factor=2, mode='bilinear')  (itermvs.py:56-57), maps [N][H][W] -> [N][2H][2W]
-__global__ void upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, bool apply_tanh) {
+// F.interpolate(scale_factor=2, mode='bilinear') of channels-last maps [N][H][W][C] -> [N][2H][2W][C]
+// (C = 1: itermvs.py:56-57; C = 32 with tanh: itermvs.py:161-163)
+__global__ void upsample2x_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C,
+                                       bool apply_tanh) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int Ho = 2 * H, Wo = 2 * W;
-    if (t >= (size_t)N * Ho * Wo) return;
-    int ox = (int)(t % Wo), oy = (int)((t / Wo) % Ho);
-    size_t n = t / ((size_t)Wo * Ho);
+    const int Ho = 2 * H, Wo = 2 * W;
+    if (t >= (size_t)N * Ho * Wo * C) return;
+    const int c = (int)(t % C);
+    size_t q = t / C;
+    const int ox = (int)(q % Wo), oy = (int)((q / Wo) % Ho);
+    const size_t n = q / ((size_t)Wo * Ho);
     int h0, h1, w0, w1;
     float lh, lw;
     up_index(oy, 0.5f, H, h0, h1, lh);
     up_index(ox, 0.5f, W, w0, w1, lw);
-    const float* q = in + n * H * W;
-    float v = (1.f - lh) * ((1.f - lw) * ldg(q + h0 * W + w0) + lw * ldg(q + h0 * W + w1)) +
-              lh * ((1.f - lw) * ldg(q + h1 * W + w0) + lw * ldg(q + h1 * W + w1));
+    const float* b = in + n * H * W * C + c;
+    float v = (1.f - lh) * ((1.f - lw) * ldg(b + ((size_t)h0 * W + w0) * C) + lw * ldg(b + ((size_t)h0 * W + w1) * C)) +
+              lh * ((1.f - lw) * ldg(b + ((size_t)h1 * W + w0) * C) + lw * ldg(b + ((size_t)h1 * W + w1) * C));
     out[t] = apply_tanh ? tanhf(v) : v;
 }
 
-// ----------------------------------------------------------------------------- hidden_init ----
-using CfgHinit0 = ConvCfg<64, 32, 8, 4, 2, 3, 1, 1, 1>;   // D -> 64, relu
-using CfgHinit1 = ConvCfg<32, 32, 8, 4, 2, 1, 1, 1, 1>;   // 1x1 64 -> 32, + bias
+int launch_upsample2x_nhwc(const float* in, float* out, int N, int H, int W, int C, bool apply_tanh, cudaStream_t st) {
+    size_t total = (size_t)N * H * W * C * 4;
+    upsample2x_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, N, H, W, C, apply_tanh);
+    count_launch();
+    IMVS_LAUNCH_CHECK("upsample2x_nhwc_kernel");
+    return 0;
+}
+
+template <int D>
+static int hinit_conv0(const imvs_weights* w, const float* corr, float* t, int B, int H3, int W3, cudaStream_t st) {
+    return mma_conv<D, 64, 2, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), EpiNHWC{t, nullptr, nullptr, H3, W3, 64, 64, 1},
+                                           MmaWeightSel::single(w->hinit_conv0), make_taps_conv(3, 1, 1, 8), B, 64, H3, W3, 1, st);
+}
 
 }  // namespace imvs
 
@@ -96,32 +111,42 @@ using namespace imvs;
 extern "C" size_t imvs_corrnet_scratch_floats(int N, int H, int W) { return (size_t)N * 26 * H * W; }
 
 extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int split1, int split2, const float* vol,
-                            float* out, size_t out_batch_stride, float* scratch, int N, int H, int W, void* stream) {
+                            float* out, size_t out_batch_stride, size_t out_pixel_stride, float* scratch,
+                            int N, int H, int W, void* stream) {
     IMVS_REQUIRE(sets && vol && out && scratch, "corrnet: null pointer");
     IMVS_REQUIRE(N >= 1 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "corrnet: H, W must be multiples of 4 (H=%d W=%d)", H, W);
     IMVS_REQUIRE(period >= 1 && N % period == 0, "corrnet: N=%d not a multiple of period=%d", N, period);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t HW = (size_t)H * W;
-    float* c0 = scratch;                    // [N][8][H][W]
-    float* c1 = c0 + (size_t)N * 8 * HW;    // [N][16][H/2][W/2]
-    float* c2 = c1 + (size_t)N * 4 * HW;    // [N][32][H/4][W/4]
-    float* x3 = c2 + (size_t)N * 2 * HW;    // [N][16][H/2][W/2]
-    float* x4 = x3 + (size_t)N * 4 * HW;    // [N][8][H][W]
+    float* c0 = scratch;                    // [N][H][W][8]
+    float* c1 = c0 + (size_t)N * 8 * HW;    // [N][H/2][W/2][16]
+    float* c2 = c1 + (size_t)N * 4 * HW;    // [N][H/4][W/4][32]
+    float* x3 = c2 + (size_t)N * 2 * HW;    // [N][H/2][W/2][16]
+    float* x4 = x3 + (size_t)N * 4 * HW;    // [N][H][W][8]
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
-    IMVS_TRY((launch_conv<CfgCorr0>("corrnet.conv0", InChannelsLast8{vol, H, W}, EpiPlanar{c0, nullptr, 8, H, W, true},
-                                    sel_of(sets, period, split1, split2, 0), N, 8, H, W, st)));
-    IMVS_TRY((launch_conv<CfgCorr1>("corrnet.conv1", InPlanar{c0, 8, H, W}, EpiPlanar{c1, nullptr, 16, H1, W1, true},
-                                    sel_of(sets, period, split1, split2, 1), N, 8, H1, W1, st)));
-    IMVS_TRY((launch_conv<CfgCorr2>("corrnet.conv2", InPlanar{c1, 16, H1, W1}, EpiPlanar{c2, nullptr, 32, H2, W2, true},
-                                    sel_of(sets, period, split1, split2, 2), N, 16, H2, W2, st)));
-    IMVS_TRY((launch_tconv<16, 16, 8, 4>("corrnet.conv3", c2, c1, x3, sel_of(sets, period, split1, split2, 3), N, 32, H2, W2, st)));
-    IMVS_TRY((launch_tconv<8, 8, 8, 4>("corrnet.conv4", x3, c0, x4, sel_of(sets, period, split1, split2, 4), N, 16, H1, W1, st)));
+    auto sel = [&](int which) { return sel_of(sets, period, split1, split2, which); };
+    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), EpiNHWC{c0, nullptr, nullptr, H, W, 8, 8, 1},
+                                            sel(0), make_taps_conv(3, 1, 1, 8), N, 8, H, W, 1, st)));
+    IMVS_TRY((mma_conv<8, 16, 2, 4, 2, true>("corrnet.conv1", in_nhwc(c0, H, W, 8), EpiNHWC{c1, nullptr, nullptr, H1, W1, 16, 16, 1},
+                                             sel(1), make_taps_conv(3, 2, 1, 8), N, 16, H1, W1, 1, st)));
+    IMVS_TRY((mma_conv<16, 32, 2, 4, 2, true>("corrnet.conv2", in_nhwc(c1, H1, W1, 16), EpiNHWC{c2, nullptr, nullptr, H2, W2, 32, 32, 1},
+                                              sel(2), make_taps_conv(3, 2, 1, 8), N, 32, H2, W2, 1, st)));
+    for (int ab = 0; ab < 4; ++ab) {        // conv3: transposed 32 -> 16 on the H/4 grid, + c1  (itermvs.py:374)
+        const int a = ab >> 1, b = ab & 1;
+        IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("corrnet.conv3", in_nhwc(c2, H2, W2, 32), EpiTconvNHWC{x3, c1, H2, W2, 16, a, b},
+                                                  sel(3), make_taps_tconv(a, b, 8), N, 16, H2, W2, 1, st)));
+    }
+    for (int ab = 0; ab < 4; ++ab) {        // conv4: transposed 16 -> 8 on the H/2 grid, + c0   (itermvs.py:376)
+        const int a = ab >> 1, b = ab & 1;
+        IMVS_TRY((mma_conv<16, 8, 2, 4, 1, true>("corrnet.conv4", in_nhwc(x3, H1, W1, 16), EpiTconvNHWC{x4, c0, H1, W1, 8, a, b},
+                                                 sel(4), make_taps_tconv(a, b, 8), N, 8, H1, W1, 1, st)));
+    }
     EpiCorrOut e5;
     e5.out = out;
     for (int i = 0; i < 3; ++i) e5.bias[i] = sets[i].conv5_b;
     e5.period = period; e5.split1 = split1; e5.split2 = split2;
-    e5.batch_stride = out_batch_stride; e5.H = H; e5.W = W;
-    IMVS_TRY((launch_conv<CfgCorr5>("corrnet.conv5", InPlanar{x4, 8, H, W}, e5, sel_of(sets, period, split1, split2, 5), N, 8, H, W, st)));
+    e5.bstride = out_batch_stride; e5.pstride = out_pixel_stride; e5.H = H; e5.W = W;
+    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), make_taps_conv(3, 1, 1, 8), N, 8, H, W, 1, st)));
     return 0;
 }
 
@@ -131,33 +156,31 @@ extern "C" int imvs_pixel_view_weight(const imvs_weights* w, const float* corr, 
     IMVS_REQUIRE(B >= 1 && S >= 1 && D >= 1 && H3 >= 1 && W3 >= 1, "pixel_view_weight: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = B * S * D, P3 = H3 * W3;
-    IMVS_TRY((launch_conv<CfgPvw>("pvw.conv", InChannelsLast8{corr, H3, W3}, EpiPvw{logits, w->pvw_conv1, w->pvw_conv1_b, H3, W3},
-                                  WeightSel::single(w->pvw_conv0), N, 8, H3, W3, st)));
+    IMVS_TRY((mma_conv<8, 16, 2, 4, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), EpiPvw{logits, w->pvw_conv1, w->pvw_conv1_b, H3, W3},
+                                             MmaWeightSel::single(w->pvw_conv0), make_taps_conv(3, 1, 1, 8), N, 16, H3, W3, 1, st)));
     pvw_reduce_kernel<<<cdiv(B * S * P3, 128), 128, 0, st>>>(logits, vw3, B * S, D, P3);
     count_launch();
     IMVS_LAUNCH_CHECK("pvw_reduce_kernel");
-    size_t total = (size_t)B * S * P3 * 4;
-    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(vw3, vw2, B * S, H3, W3, false);
-    count_launch();
-    IMVS_LAUNCH_CHECK("upsample2x_kernel");
-    return 0;
+    return launch_upsample2x_nhwc(vw3, vw2, B * S, H3, W3, 1, false, st);
 }
 
 extern "C" int imvs_hidden_init(const imvs_weights* w, const float* corr, float* hidden, float* scratch,
                                 int B, int D, int H3, int W3, void* stream) {
     IMVS_REQUIRE(w && corr && hidden && scratch, "hidden_init: null pointer");
-    IMVS_REQUIRE(B >= 1 && D >= 1 && H3 >= 1 && W3 >= 1, "hidden_init: bad shape");
+    IMVS_REQUIRE(B >= 1 && H3 >= 1 && W3 >= 1, "hidden_init: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t P3 = (size_t)H3 * W3;
-    float* t = scratch;                       // [B][64][P3]
-    float* u = scratch + (size_t)B * 64 * P3; // [B][32][P3]
-    IMVS_TRY((launch_conv<CfgHinit0>("hidden_init.conv0", InPlanar{corr, D, H3, W3}, EpiPlanar{t, nullptr, 64, H3, W3, true},
-                                     WeightSel::single(w->hinit_conv0), B, D, H3, W3, st)));
-    IMVS_TRY((launch_conv<CfgHinit1>("hidden_init.fc", InPlanar{t, 64, H3, W3}, EpiPlanar{u, w->hinit_fc_b, 32, H3, W3, false},
-                                     WeightSel::single(w->hinit_fc), B, 64, H3, W3, st)));
-    size_t total = (size_t)B * 32 * P3 * 4;
-    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(u, hidden, B * 32, H3, W3, true);
-    count_launch();
-    IMVS_LAUNCH_CHECK("upsample2x_kernel(tanh)");
-    return 0;
+    float* t = scratch;                       // [B][P3][64]
+    float* u = scratch + (size_t)B * 64 * P3; // [B][P3][32]
+    switch (D) {
+        case 8: IMVS_TRY(hinit_conv0<8>(w, corr, t, B, H3, W3, st)); break;
+        case 16: IMVS_TRY(hinit_conv0<16>(w, corr, t, B, H3, W3, st)); break;
+        case 32: IMVS_TRY(hinit_conv0<32>(w, corr, t, B, H3, W3, st)); break;
+        case 48: IMVS_TRY(hinit_conv0<48>(w, corr, t, B, H3, W3, st)); break;
+        case 64: IMVS_TRY(hinit_conv0<64>(w, corr, t, B, H3, W3, st)); break;
+        default: return fail("hidden_init: D=%d not supported (8, 16, 32, 48 or 64 hypotheses)", D);
+    }
+    IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("hidden_init.fc", in_nhwc(t, H3, W3, 64), EpiNHWC{u, w->hinit_fc_b, nullptr, H3, W3, 32, 32, 0},
+                                              MmaWeightSel::single(w->hinit_fc), make_taps_conv(1, 1, 1, 8), B, 32, H3, W3, 1, st)));
+    return launch_upsample2x_nhwc(u, hidden, B, H3, W3, 32, true, st);
 }

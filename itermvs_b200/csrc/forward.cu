@@ -37,7 +37,7 @@ static Workspace carve(const imvs_problem& pb, float* base) {
     w.corr0 = at(B * D * P3);
     w.hinit_scratch = at(B * 96 * P3);
     w.hidden = at(B * 32 * P2);
-    w.xbuf = at(B * 11 * P2);
+    w.xbuf = at(B * IMVS_XCH * P2);
     w.agg_iter = at(B * IMVS_ITER_SLICES * P2 * 8);
     w.gru_scratch = at(B * 64 * P2);
     w.head_scratch = at(B * 64 * P2);
@@ -53,7 +53,7 @@ static int check_problem(const imvs_problem* pb) {
     IMVS_REQUIRE(pb->V >= 2 && pb->V - 1 <= IMVS_MAX_VIEWS, "need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, pb->V);
     IMVS_REQUIRE(pb->H >= 32 && pb->W >= 32 && pb->H % 32 == 0 && pb->W % 32 == 0,
                  "H and W must be multiples of 32 (H=%d W=%d): CorrNet halves the 1/8-resolution map twice", pb->H, pb->W);
-    IMVS_REQUIRE(pb->D >= 2, "D=%d", pb->D);
+    IMVS_REQUIRE(pb->D >= 8 && pb->D % 8 == 0, "D=%d must be a multiple of 8", pb->D);
     IMVS_REQUIRE(pb->iterations >= 1, "iterations=%d", pb->iterations);
     return 0;
 }
@@ -69,18 +69,18 @@ extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
 
 extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     if (check_problem(pb) != 0) return -1;
-    return 22 + 11 * pb->iterations;
+    return 28 + 17 * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,
-                                    const float* fea1, const float* fea2, const float* fea3, const float* ref_fea2_planar,
+                                    const float* fea1, const float* fea2, const float* fea3,
                                     const float* proj1, const float* proj2, const float* proj3,
                                     const float* depth_min, const float* depth_max,
                                     void* workspace, size_t workspace_bytes,
                                     float* depth, float* depth_up, float* conf, float* conf_up,
                                     int* nan_flag, void* stream) {
     IMVS_TRY(check_problem(pb));
-    IMVS_REQUIRE(w && fea1 && fea2 && fea3 && ref_fea2_planar && proj1 && proj2 && proj3 && depth_min && depth_max && workspace,
+    IMVS_REQUIRE(w && fea1 && fea2 && fea3 && proj1 && proj2 && proj3 && depth_min && depth_max && workspace,
                  "itermvs_forward: null pointer");
     IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "itermvs_forward: workspace must be 256-byte aligned");
     Workspace ws = carve(*pb, static_cast<float*>(workspace));
@@ -89,7 +89,10 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
     const int B = pb->B, V = pb->V, S = V - 1, D = pb->D, I = pb->iterations;
     const int H2 = pb->H / 4, W2 = pb->W / 4, H3 = pb->H / 8, W3 = pb->W / 8;
     const int P2 = H2 * W2, P3 = H3 * W3;
-    const size_t xstride = (size_t)11 * P2;
+    const size_t xb = (size_t)IMVS_XCH * P2, xp = IMVS_XCH;      // x: [B][P2][16], ch 0 = normalized depth
+
+    // x channels 11..15 are zero padding of the GRU's 43 -> 48 input channels
+    IMVS_CUDA(cudaMemsetAsync(ws.xbuf, 0, sizeof(float) * (size_t)B * xb, (cudaStream_t)stream));
 
     // K1 (module.py:78-90), hoisted: once per level instead of once per warp call
     { StageTimer tm_(ST_COMPOSE, stream);
@@ -109,8 +112,8 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
     IMVS_TRY(imvs_aggregate_init(ws.corr_init, ws.vw3, ws.agg_init, B, S, D, P3, stream));
     }
     imvs_corrnet_weights init_sets[3] = {w->corrnet[2], w->corrnet[2], w->corrnet[2]};
-    { StageTimer tm_(ST_CORRNET, stream);
-    IMVS_TRY(imvs_corrnet(init_sets, D, D, D, ws.agg_init, ws.corr0, (size_t)D * P3, ws.corrnet_scratch, B * D, H3, W3, stream));
+    { StageTimer tm_(ST_CORRNET, stream);       // -> corr0 [B][P3][D] channels-last
+    IMVS_TRY(imvs_corrnet(init_sets, D, D, D, ws.agg_init, ws.corr0, (size_t)D * P3, (size_t)D, ws.corrnet_scratch, B * D, H3, W3, stream));
     }
 
     // hidden state and first depth (itermvs.py:275-276)
@@ -118,7 +121,7 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
     IMVS_TRY(imvs_hidden_init(w, ws.corr0, ws.hidden, ws.hinit_scratch, B, D, H3, W3, stream));
     }
     { StageTimer tm_(ST_HEAD, stream);
-    IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xstride, nullptr, nullptr, nullptr, (I == 1) ? depth : nullptr,
+    IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xb, xp, nullptr, nullptr, nullptr, (I == 1) ? depth : nullptr,
                              depth_min, depth_max, ws.head_scratch, B, H2, W2, stream));
     }
 
@@ -127,11 +130,11 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
         const bool last = (it == I - 1);
         // itermvs.py:288-295
         { StageTimer tm_(ST_WARPCORR_ITER, stream);
-        IMVS_TRY(imvs_warpcorr_iter(fea1, fea2, fea3, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xstride, ws.vw2, depth_min, depth_max,
+        IMVS_TRY(imvs_warpcorr_iter(fea1, fea2, fea3, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xb, xp, ws.vw2, depth_min, depth_max,
                                     nullptr, nullptr, nullptr, ws.agg_iter, B, V, H2, W2, stream));
         }
-        { StageTimer tm_(ST_CORRNET, stream);
-        IMVS_TRY(imvs_corrnet(w->corrnet, IMVS_ITER_SLICES, 4, 8, ws.agg_iter, ws.xbuf + P2, xstride, ws.corrnet_scratch,
+        { StageTimer tm_(ST_CORRNET, stream);   // -> x channels 1..10
+        IMVS_TRY(imvs_corrnet(w->corrnet, IMVS_ITER_SLICES, 4, 8, ws.agg_iter, ws.xbuf + 1, xb, xp, ws.corrnet_scratch,
                               B * IMVS_ITER_SLICES, H2, W2, stream));
         }
         // itermvs.py:316-320 -> Update.forward (192-220); x = [normalized_depth, corr] is xbuf itself
@@ -141,17 +144,16 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
         // `depth` returned in test mode is the value BEFORE the last update (itermvs.py:319)
         float* depth_here = (!last && it == I - 2) ? depth : nullptr;
         { StageTimer tm_(ST_HEAD, stream);
-        IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xstride, nullptr, last ? conf_q : nullptr, nullptr, depth_here,
+        IMVS_TRY(imvs_depth_head(w, ws.hidden, ws.xbuf, xb, xp, nullptr, last ? conf_q : nullptr, nullptr, depth_here,
                                  depth_min, depth_max, ws.head_scratch, B, H2, W2, stream));
         }
     }
     // itermvs.py:321-324
     if (depth_up || conf_up) {
         IMVS_REQUIRE(depth_up, "itermvs_forward: conf_up requested without depth_up");
-        { StageTimer tm_(ST_UPSAMPLE, stream);
-        IMVS_TRY(imvs_upsample_outputs(w, ref_fea2_planar, ws.xbuf, xstride, conf_up ? conf_q : nullptr, depth_min, depth_max,
+        StageTimer tm_(ST_UPSAMPLE, stream);
+        IMVS_TRY(imvs_upsample_outputs(w, fea2, (size_t)V * P2 * 32, ws.xbuf, xb, xp, conf_up ? conf_q : nullptr, depth_min, depth_max,
                                        depth_up, conf_up, ws.ups_scratch, B, H2, W2, stream));
-        }
     }
     return 0;
 }

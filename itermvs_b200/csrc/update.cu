@@ -1,34 +1,35 @@
 // Update stage: ConvGRU (module.py:52-66) and depth / confidence heads with softmax, arg-max and
-// clamped-window regression (itermvs.py:139-151, 171-190, 192-220).
+// clamped-window regression (itermvs.py:139-151, 171-190, 192-220).  Activations channels-last.
 #include <algorithm>
 
 #include "common.cuh"
-#include "conv.cuh"
+#include "mmaconv.cuh"
 
 namespace imvs {
 
 // --------------------------------------------------------------------------------- ConvGRU ----
-// z|r as ONE 43 -> 64 dilated convolution (convz and convr share their input hx = [h, x]); the
-// epilogue applies the sigmoids and writes z and r*h.  q = tanh(convq([r*h, x])) is a second
-// convolution whose epilogue performs the gate  h <- (1-z) h + z q  in place (h is only read
-// point-wise there).
+// z|r as ONE 48 -> 64 dilated implicit GEMM (convz and convr share their input hx = [h, x]); the
+// epilogue applies the sigmoids and writes z and r*h.  q = tanh(convq([r*h, x])) is a second GEMM
+// whose epilogue performs the gate  h <- (1-z) h + z q  in place (h is only read point-wise there).
 struct EpiGruZR {
     const float* bias;   // [64]
-    const float* h;      // [N][32][H][W]
-    float* z;            // [N][32][H][W]
-    float* rh;           // [N][32][H][W]
+    const float* h;      // [N][H][W][32]
+    float* z;            // [N][H][W][32]
+    float* rh;           // [N][H][W][32]
     int H, W;
-    template <int CO>
-    __device__ __forceinline__ void store(int n, int y, int x, int co0, const float (&a)[CO]) const {
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+        if (oy >= H || ox >= W) return;
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
 #pragma unroll
-        for (int c = 0; c < CO; ++c) {
-            const int co = co0 + c;
-            const float s = sigmoidf_(a[c] + ldg(bias + co));
+        for (int j = 0; j < NT; ++j) {
+            const int co = co0 + 8 * j + 2 * t;
+            const float s0 = sigmoidf_(v[2 * j] + ldg(bias + co)), s1 = sigmoidf_(v[2 * j + 1] + ldg(bias + co + 1));
             if (co < 32) {
-                z[(((size_t)n * 32 + co) * H + y) * W + x] = s;
+                *reinterpret_cast<float2*>(z + base + co) = make_float2(s0, s1);
             } else {
-                const size_t o = (((size_t)n * 32 + (co - 32)) * H + y) * W + x;
-                rh[o] = s * ldg(h + o);
+                const float2 hh = ldg2(h + base + co - 32);
+                *reinterpret_cast<float2*>(rh + base + co - 32) = make_float2(s0 * hh.x, s1 * hh.y);
             }
         }
     }
@@ -39,22 +40,22 @@ struct EpiGruQ {
     const float* z;
     float* h;            // updated in place
     int H, W;
-    template <int CO>
-    __device__ __forceinline__ void store(int n, int y, int x, int co0, const float (&a)[CO]) const {
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+        if (oy >= H || ox >= W) return;
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
 #pragma unroll
-        for (int c = 0; c < CO; ++c) {
-            const int co = co0 + c;
-            const size_t o = (((size_t)n * 32 + co) * H + y) * W + x;
-            const float q = tanhf(a[c] + ldg(bias + co));
-            const float zz = ldg(z + o);
-            h[o] = (1.f - zz) * h[o] + zz * q;
+        for (int j = 0; j < NT; ++j) {
+            const int co = co0 + 8 * j + 2 * t;
+            const float q0 = tanhf(v[2 * j] + ldg(bias + co)), q1 = tanhf(v[2 * j + 1] + ldg(bias + co + 1));
+            const float2 zz = ldg2(z + base + co);
+            float2 hh = *reinterpret_cast<const float2*>(h + base + co);
+            hh.x = (1.f - zz.x) * hh.x + zz.x * q0;
+            hh.y = (1.f - zz.y) * hh.y + zz.y * q1;
+            *reinterpret_cast<float2*>(h + base + co) = hh;
         }
     }
 };
-
-using CfgGruZR = ConvCfg<64, 32, 8, 4, 2, 3, 1, 2, 1>;   // 43 -> 64, dilation 2
-using CfgGruQ = ConvCfg<32, 16, 8, 2, 4, 3, 1, 2, 1>;    // 43 -> 32, dilation 2
-using CfgHead64 = ConvCfg<64, 32, 8, 4, 2, 3, 1, 2, 1>;  // depth_head.0 | confidence_head.0
 
 // ------------------------------------------------------------------------------------ heads ----
 // Per pixel:  t[32] (relu'd 3x3 output) -> fc1 32->64 relu -> fc2 64->256 + b -> softmax -> arg-max
@@ -67,15 +68,14 @@ constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_PXW = 8;            // pixels per warp step
 
 struct HeadParams {
-    const float* t;          // [B][CT][P]  CT = 64 (with confidence) or 32
-    int CT;
+    const float* t;          // [B][P][64] channels-last: 0..31 depth head, 32..63 confidence head
     const float* fc1;        // [32][64]
     const float* fc2;        // [64][256]
     const float* fc2_b;      // [256]
     const float* conf_w;     // [32]
     const float* conf_b;     // [1]
-    float* nd_out;           // [B][nd_stride]
-    size_t nd_stride;
+    float* nd_out;
+    size_t nd_bstride, nd_pstride;
     float* prob;             // [B][256][P] or null
     float* conf;             // [B][P] or null
     float* conf_logit;       // [B][P] or null
@@ -110,11 +110,17 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadParams prm
     for (int item = blockIdx.x * (HEAD_THREADS / 32) + warp; item < items; item += nwarps) {
         const int gp = item * HEAD_PXW;          // flat pixel over [B][P]
         const int b = gp / P, p0 = gp % P;
-        // ---- stage A: activations t[k][8 px] -> smem
+        // ---- stage A: activations of 8 pixels (8 x 64 contiguous floats) -> smem, transposed to [k][px]
         {
-            const int px = lane & 7, kq = lane >> 3;
-            const float* tb = prm.t + (size_t)b * prm.CT * P + p0 + px;
-            for (int k = kq; k < rows; k += 4) st[k * HEAD_PXW + px] = ldg(tb + (size_t)k * P);
+            const float* tb = prm.t + ((size_t)b * P + p0) * 64;
+            for (int i = lane; i < HEAD_PXW * rows / 4; i += 32) {
+                const int px = i / (rows / 4), k4 = i % (rows / 4);
+                const float4 v = ldg4(tb + (size_t)px * 64 + 4 * k4);
+                st[(4 * k4 + 0) * HEAD_PXW + px] = v.x;
+                st[(4 * k4 + 1) * HEAD_PXW + px] = v.y;
+                st[(4 * k4 + 2) * HEAD_PXW + px] = v.z;
+                st[(4 * k4 + 3) * HEAD_PXW + px] = v.w;
+            }
         }
         __syncwarp();
         // ---- stage B: fc1 + relu: lane owns hidden channels 2*lane, 2*lane+1
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadParams prm
             }
         }
         if (lane < HEAD_PXW) {
-            prm.nd_out[(size_t)b * prm.nd_stride + p0 + lane] = nd_mine;
+            prm.nd_out[(size_t)b * prm.nd_bstride + (size_t)(p0 + lane) * prm.nd_pstride] = nd_mine;
             if (prm.depth_out) {
                 const float inv_min = 1.0f / prm.depth_min[b], inv_max = 1.0f / prm.depth_max[b];
                 prm.depth_out[(size_t)b * P + p0 + lane] = unnormalize_depth(nd_mine, inv_min, inv_max);
@@ -256,33 +262,36 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
     const size_t n = (size_t)B * 32 * H * W;
     float* z = scratch;
     float* rh = scratch + n;
-    IMVS_TRY((launch_conv<CfgGruZR>("gru.zr", InConcat2{h, x, 32, 11, H, W}, EpiGruZR{w->gru_zr_b, h, z, rh, H, W},
-                                    WeightSel::single(w->gru_zr), B, 43, H, W, st)));
-    IMVS_TRY((launch_conv<CfgGruQ>("gru.q", InConcat2{rh, x, 32, 11, H, W}, EpiGruQ{w->gru_q_b, z, h, H, W},
-                                   WeightSel::single(w->gru_q), B, 43, H, W, st)));
+    const TapTable taps = make_taps_conv(3, 1, 2, 8);
+    IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.zr", InNHWC2{h, x, H, W, 32, IMVS_XCH}, EpiGruZR{w->gru_zr_b, h, z, rh, H, W},
+                                               MmaWeightSel::single(w->gru_zr), taps, B, 64, H, W, 2, st)));
+    IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.q", InNHWC2{rh, x, H, W, 32, IMVS_XCH}, EpiGruQ{w->gru_q_b, z, h, H, W},
+                                               MmaWeightSel::single(w->gru_q), taps, B, 32, H, W, 1, st)));
     return 0;
 }
 
 extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float* nd_out, size_t nd_batch_stride,
-                               float* probability, float* conf, float* conf_logit, float* depth_out,
+                               size_t nd_pixel_stride, float* probability, float* conf, float* conf_logit, float* depth_out,
                                const float* depth_min, const float* depth_max, float* scratch,
                                int B, int H, int W, void* stream) {
     IMVS_REQUIRE(w && hidden && nd_out && scratch, "depth_head: null pointer");
     IMVS_REQUIRE(B >= 1 && H >= 1 && W >= 1 && (H * W) % HEAD_PXW == 0, "depth_head: H*W must be a multiple of %d", HEAD_PXW);
     IMVS_REQUIRE(!depth_out || (depth_min && depth_max), "depth_head: depth_out needs depth_min/depth_max");
+    IMVS_REQUIRE(nd_pixel_stride >= 1, "depth_head: nd_pixel_stride must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     const bool want_conf = conf || conf_logit;
     const int P = H * W;
-    float* t = scratch;
-    // stacked weight [32][9][64]: channel block 0 = depth_head.0, block 1 = confidence_head.0; the
+    float* t = scratch;                     // [B][P][64]
+    // stacked weight [9][32][64]: channel block 0 = depth_head.0, block 1 = confidence_head.0; the
     // confidence block only runs when a confidence output is requested (itermvs.py:196-199)
-    IMVS_TRY((launch_conv<CfgHead64>("head.conv0", InPlanar{hidden, 32, H, W}, EpiPlanar{t, nullptr, 64, H, W, true},
-                                     WeightSel::single(w->head_conv0), B, 32, H, W, st, want_conf ? 2 : 1)));
+    IMVS_TRY((mma_conv<32, 32, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), EpiNHWC{t, nullptr, nullptr, H, W, 64, 64, 1},
+                                               MmaWeightSel::single(w->head_conv0), make_taps_conv(3, 1, 2, 8), B, 64, H, W,
+                                               want_conf ? 2 : 1, st)));
     HeadParams prm;
-    prm.t = t; prm.CT = 64;
+    prm.t = t;
     prm.fc1 = w->head_fc1; prm.fc2 = w->head_fc2; prm.fc2_b = w->head_fc2_b;
     prm.conf_w = w->conf_fc; prm.conf_b = w->conf_fc_b;
-    prm.nd_out = nd_out; prm.nd_stride = nd_batch_stride;
+    prm.nd_out = nd_out; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
     prm.prob = probability; prm.conf = conf; prm.conf_logit = conf_logit; prm.depth_out = depth_out;
     prm.depth_min = depth_min; prm.depth_max = depth_max;
     prm.B = B; prm.P = P;

@@ -5,19 +5,17 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "conv.cuh"
+#include "mmaconv.cuh"
 
 namespace imvs {
-
-using CfgUps0 = ConvCfg<64, 32, 8, 4, 2, 3, 1, 1, 1>;    // iter_mvs.upsample.0 : 32 -> 64, relu
 
 constexpr int UPS_THREADS = 256;
 
 struct UpsParams {
-    const float* t;        // [B][64][P2] relu'd conv output
+    const float* t;        // [B][P2][64] relu'd conv output, channels-last
     const float* fc;       // [64][144]
-    const float* nd;       // [B][nd_stride]
-    size_t nd_stride;
+    const float* nd;
+    size_t nd_bstride, nd_pstride;
     const float* depth_min;
     const float* depth_max;
     float* depth_up;       // [B][4H2][4W2]
@@ -42,9 +40,15 @@ __global__ void __launch_bounds__(UPS_THREADS) convex_upsample_kernel(const UpsP
         const int gp = item * 8;
         const int b = gp / P, p0 = gp % P;
         {
-            const int px = lane & 7, kq = lane >> 3;
-            const float* tb = prm.t + (size_t)b * 64 * P + p0 + px;
-            for (int k = kq; k < 64; k += 4) st[k * 8 + px] = ldg(tb + (size_t)k * P);
+            const float* tb = prm.t + ((size_t)b * P + p0) * 64;
+            for (int i = lane; i < 8 * 16; i += 32) {
+                const int px = i / 16, k4 = i % 16;
+                const float4 v = ldg4(tb + (size_t)px * 64 + 4 * k4);
+                st[(4 * k4 + 0) * 8 + px] = v.x;
+                st[(4 * k4 + 1) * 8 + px] = v.y;
+                st[(4 * k4 + 2) * 8 + px] = v.z;
+                st[(4 * k4 + 3) * 8 + px] = v.w;
+            }
         }
         __syncwarp();
         float acc[4][9];
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(UPS_THREADS) convex_upsample_kernel(const UpsP
             }
         }
         const float inv_min = 1.0f / prm.depth_min[b], inv_max = 1.0f / prm.depth_max[b];
-        const float* ndb = prm.nd + (size_t)b * prm.nd_stride;
+        const float* ndb = prm.nd + (size_t)b * prm.nd_bstride;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int p = p0 + pp * 4 + i;
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(UPS_THREADS) convex_upsample_kernel(const UpsP
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const int yy = min(max(y + k / 3 - 1, 0), H2 - 1), xx = min(max(x + k % 3 - 1, 0), W2 - 1);   // ReplicationPad2d(1)
-                up = fmaf(ldg(ndb + yy * W2 + xx), e[k] / sum, up);
+                up = fmaf(ldg(ndb + (size_t)(yy * W2 + xx) * prm.nd_pstride), e[k] / sum, up);
             }
             const int oy = 4 * y + (s >> 2), ox = 4 * x + (s & 3);
             prm.depth_up[((size_t)b * 4 * H2 + oy) * (4 * W2) + ox] = unnormalize_depth(up, inv_min, inv_max);
@@ -108,18 +112,20 @@ __global__ void upsample4x_kernel(const float* __restrict__ in, float* __restric
 
 using namespace imvs;
 
-extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea2_planar, const float* nd,
-                                     size_t nd_batch_stride, const float* conf, const float* depth_min,
+extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea2, size_t ref_batch_stride, const float* nd,
+                                     size_t nd_batch_stride, size_t nd_pixel_stride, const float* conf, const float* depth_min,
                                      const float* depth_max, float* depth_up, float* conf_up, float* scratch,
                                      int B, int H2, int W2, void* stream) {
-    IMVS_REQUIRE(w && ref_fea2_planar && nd && depth_min && depth_max && depth_up && scratch, "upsample_outputs: null pointer");
+    IMVS_REQUIRE(w && ref_fea2 && nd && depth_min && depth_max && depth_up && scratch, "upsample_outputs: null pointer");
     IMVS_REQUIRE(B >= 1 && H2 >= 1 && W2 >= 1 && (H2 * W2) % 8 == 0, "upsample_outputs: H2*W2 must be a multiple of 8");
     IMVS_REQUIRE(!conf || conf_up, "upsample_outputs: conf given without conf_up");
+    IMVS_REQUIRE(nd_pixel_stride >= 1, "upsample_outputs: nd_pixel_stride must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
-    IMVS_TRY((launch_conv<CfgUps0>("upsample.conv0", InPlanar{ref_fea2_planar, 32, H2, W2}, EpiPlanar{scratch, nullptr, 64, H2, W2, true},
-                                   WeightSel::single(w->ups_conv0), B, 32, H2, W2, st)));
+    IMVS_TRY((mma_conv<32, 64, 2, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride),
+                                               EpiNHWC{scratch, nullptr, nullptr, H2, W2, 64, 64, 1}, MmaWeightSel::single(w->ups_conv0),
+                                               make_taps_conv(3, 1, 1, 8), B, 64, H2, W2, 1, st)));
     UpsParams prm;
-    prm.t = scratch; prm.fc = w->ups_fc; prm.nd = nd; prm.nd_stride = nd_batch_stride;
+    prm.t = scratch; prm.fc = w->ups_fc; prm.nd = nd; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.depth_up = depth_up;
     prm.B = B; prm.H2 = H2; prm.W2 = W2;
     const size_t smem = (size_t)(64 * 144 + (UPS_THREADS / 32) * 64 * 8) * sizeof(float);

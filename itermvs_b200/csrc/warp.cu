@@ -17,6 +17,8 @@ int fail(const char* fmt, ...) {
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launches_total() { return g_launches; }
+static int g_conv_passes = 3;
+int conv_passes() { return g_conv_passes; }
 
 // ---- stage timing taps -----------------------------------------------------------------------
 struct ProfileState {
@@ -177,6 +179,12 @@ using namespace imvs;
 extern "C" int imvs_abi_version(void) { return IMVS_ABI_VERSION; }
 extern "C" const char* imvs_last_error(void) { return err_buf(); }
 extern "C" long long imvs_launches_total(void) { return launches_total(); }
+extern "C" int imvs_set_conv_passes(int passes) {
+    IMVS_REQUIRE(passes == 1 || passes == 3, "set_conv_passes: passes must be 1 (TF32) or 3 (3xTF32, fp32-grade), got %d", passes);
+    g_conv_passes = passes;
+    return 0;
+}
+extern "C" int imvs_get_conv_passes(void) { return g_conv_passes; }
 
 // Profiling facility (NOT graph-capturable, synchronises in _end): records one CUDA-event pair
 // around every stage of imvs_itermvs_forward / imvs_featurenet_forward issued between begin and end.

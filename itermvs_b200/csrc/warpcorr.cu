@@ -143,7 +143,7 @@ struct IterParams {
     const float* fea[3];   // level 1,2,3 pyramids  [B][V][Hf][Wf][C]
     const float* rt[3];    // composed projections  [B][S][12]
     const float* nd;       // [B][nd_stride]
-    size_t nd_stride;
+    size_t nd_stride, nd_pstride;
     const float* vw2;      // [B][S][P2]
     const float* depth_min;
     const float* depth_max;
@@ -182,7 +182,7 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
         if (smp) {
             depth = ldg(smp + ((size_t)b * R + r) * P2 + p);
         } else {
-            const float ndv = ldg(prm.nd + (size_t)b * prm.nd_stride + p);
+            const float ndv = ldg(prm.nd + (size_t)b * prm.nd_stride + (size_t)p * prm.nd_pstride);
             const float s = fminf(fmaxf(ndv + off, 0.f), 1.f);
             depth = unnormalize_depth(s, inv_min, inv_max);
         }
@@ -309,7 +309,7 @@ extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const flo
 
 extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
                                   const float* rt1, const float* rt2, const float* rt3,
-                                  const float* nd, size_t nd_batch_stride, const float* vw2,
+                                  const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
                                   const float* depth_min, const float* depth_max,
                                   const float* samples1, const float* samples2, const float* samples3, float* agg,
                                   int B, int V, int H2, int W2, void* stream) {
@@ -324,7 +324,7 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     IterParams prm;
     prm.fea[0] = fea1; prm.fea[1] = fea2; prm.fea[2] = fea3;
     prm.rt[0] = rt1; prm.rt[1] = rt2; prm.rt[2] = rt3;
-    prm.nd = nd; prm.nd_stride = nd_batch_stride; prm.vw2 = vw2;
+    prm.nd = nd; prm.nd_stride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride; prm.vw2 = vw2;
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.agg = agg;
     prm.samples[0] = samples1; prm.samples[1] = samples2; prm.samples[2] = samples3;
     prm.B = B; prm.V = V; prm.H2 = H2; prm.W2 = W2;

@@ -7,53 +7,44 @@ Pipeline.forward(imgs, proj_matrices, depth_min, depth_max)            reference
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
+from . import _lib
+from . import _pack
 from . import ops
-from .estimator import IterMVS
+from .estimator import IterMVS, _cached_pack
 
 Tensor = torch.Tensor
 
 
 class _ConvBN(nn.Module):
-    """conv(no bias) + BatchNorm (+ReLU): key layout `<name>.conv.weight`, `<name>.bn.*` (module.py:6-29)."""
-
-    def __init__(self, cin, cout, stride=1, relu=True):
-        super().__init__()
-        self.conv = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
-        self.bn = nn.BatchNorm2d(cout)
-        self._relu = relu
-
-    def forward(self, x):
-        y = self.bn(self.conv(x))
-        return F.relu(y, inplace=True) if self._relu else y
-
-
-class _ResBlock(nn.Module):
-    """module.py:32-50."""
+    """conv(no bias) + BatchNorm: key layout `<name>.conv.weight`, `<name>.bn.*` (module.py:6-29).
+    Parameter / buffer holder; the kernels consume the BN-folded weights."""
 
     def __init__(self, cin, cout, stride=1):
         super().__init__()
-        self.conv1 = _ConvBN(cin, cout, stride=stride, relu=True)
-        self.conv2 = _ConvBN(cout, cout, relu=False)
-        self.downsample = None if stride == 1 else _ConvBN(cin, cout, stride=stride, relu=False)
+        self.conv = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
 
-    def forward(self, x):
-        y = self.conv2(self.conv1(x))
-        if self.downsample is not None:
-            x = self.downsample(x)
-        return F.relu(x + y, inplace=True)
+
+class _ResBlock(nn.Module):
+    """module.py:32-50 (holder)."""
+
+    def __init__(self, cin, cout, stride=1):
+        super().__init__()
+        self.conv1 = _ConvBN(cin, cout, stride=stride)
+        self.conv2 = _ConvBN(cout, cout)
+        self.downsample = None if stride == 1 else _ConvBN(cin, cout, stride=stride)
 
 
 class FeatureNet(nn.Module):
-    """net.py:7-66 -- FPN feature extractor.  Outside the hot path named by the north star (SURVEY
-    section 8 row f-1): convolutions run on the stock cuDNN path; what this class adds is batching
-    all views of all reference views into one pass in eval mode (the reference loops over views,
-    net.py:56-65) and emitting the channels-last pyramids the fused kernels consume."""
+    """net.py:7-66 -- FPN feature extractor, eval-mode semantics (BatchNorm running statistics),
+    on the tensor-core convolution kernels: all views of all reference views in one pass, BN / ReLU /
+    residual / FPN adds fused into the convolutions, pyramids emitted channels-last."""
 
     def __init__(self, test=False):
         super().__init__()
@@ -68,31 +59,48 @@ class FeatureNet(nn.Module):
         self.inner1 = nn.Conv2d(16, 48, 1, stride=1, padding=0, bias=True)
         self.inner2 = nn.Conv2d(32, 48, 1, stride=1, padding=0, bias=True)
         self.inner3 = nn.Conv2d(48, 48, 1, stride=1, padding=0, bias=True)   # unused in forward, as in net.py:25
+        self._ws = {}
 
-    def _pyramid(self, x: Tensor) -> Dict[str, Tensor]:
-        f1 = self.layer1(self.conv1(x))
-        f2 = self.layer2(f1)
-        f3 = self.layer3(f2)
-        out3 = self.output3(f3)
-        intra = F.interpolate(f3, scale_factor=2, mode="bilinear") + self.inner2(f2)
-        out2 = self.output2(intra)
-        intra = F.interpolate(intra, scale_factor=2, mode="bilinear") + self.inner1(f1)
-        return {"level3": out3, "level2": out2, "level1": self.output1(intra)}
+    def _packed(self, device) -> _pack.PackedFeatureNet:
+        def build():
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            return _pack.PackedFeatureNet(sd, device)
+        # BN running statistics are buffers: include their versions in the cache key through a cheap proxy
+        return _cached_pack(self, device, build)
 
-    def forward_batched(self, x: Tensor) -> Dict[str, Tensor]:
-        """x [B,V,3,H,W] -> NCHW pyramids [B*V,C_l,H_l,W_l] (all views in one pass)."""
-        b, v, _, h, w = x.shape
-        if self.training and self.test:
-            # BatchNorm in training mode uses per-call batch statistics: keep the reference's per-view calls
-            per = [self._pyramid(x[:, i]) for i in range(v)]
-            return {k: torch.stack([p[k] for p in per], dim=1).flatten(0, 1) for k in per[0]}
-        return self._pyramid(x.reshape(b * v, 3, h, w))
+    def forward_nhwc(self, x: Tensor):
+        """x [B,V,3,H,W] -> channels-last pyramids (fea1 [B,V,H/2,W/2,16], fea2 [...,32], fea3 [...,48])."""
+        if self.training:
+            raise NotImplementedError("itermvs_b200.FeatureNet: BatchNorm in training mode (batch statistics) is not "
+                                      "built; call .eval() (the inference path of eval.py:126 does)")
+        x = ops._chk(x.float(), "imgs")
+        b, v, c, h, w = x.shape
+        assert c == 3
+        dev = x.device
+        n = b * v
+        key = (n, h, w, str(dev))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = _lib.lib().imvs_featurenet_workspace_bytes(n, h, w)
+            if nbytes == 0:
+                raise ValueError(f"FeatureNet: unsupported shape {tuple(x.shape)}")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws = {key: ws}
+        f1 = torch.empty(b, v, h // 2, w // 2, 16, device=dev)
+        f2 = torch.empty(b, v, h // 4, w // 4, 32, device=dev)
+        f3 = torch.empty(b, v, h // 8, w // 8, 48, device=dev)
+        _lib.check(_lib.lib().imvs_featurenet_forward(self._packed(dev).ref, x.data_ptr(), f1.data_ptr(), f2.data_ptr(),
+                                                      f3.data_ptr(), ws.data_ptr(), ws.numel(), n, h, w, ops._stream()),
+                   "featurenet_forward")
+        return f1, f2, f3
 
     def forward(self, x: Tensor):
-        """Reference return format (net.py:35-66): dict level -> sequence of per-view [B,C,H,W]."""
-        b, v = x.shape[:2]
-        pyr = self.forward_batched(x)
-        return {k: list(torch.unbind(t.view(b, v, *t.shape[1:]), dim=1)) for k, t in pyr.items()}
+        """Reference return format (net.py:35-66): dict level -> list of per-view NCHW [B,C,H,W]."""
+        f1, f2, f3 = self.forward_nhwc(x)
+        out = {}
+        for name, f in (("level1", f1), ("level2", f2), ("level3", f3)):
+            out[name] = [f[:, i].permute(0, 3, 1, 2).contiguous() for i in range(f.shape[1])]
+        return out
 
 
 class Pipeline(nn.Module):
@@ -105,6 +113,7 @@ class Pipeline(nn.Module):
         self.test = test
         self.feature_net = FeatureNet(test=test)
         self.iter_mvs = IterMVS(iteration, self.feature_dim[2], self.hidden_dim, test)
+        self._last_nan_flag = None
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts checkpoints with the DataParallel 'module.' prefix (train.py:153-157) too."""
@@ -119,17 +128,11 @@ class Pipeline(nn.Module):
         x = imgs["level_0"]
         if not x.is_cuda:
             raise RuntimeError("itermvs_b200.Pipeline: inputs must be CUDA tensors (there is no CPU path)")
-        b, v = x.shape[:2]
-        pyr = self.feature_net.forward_batched(x.float())
-        fea = {}
-        for k, t in pyr.items():
-            n, c, h, w = t.shape
-            fea[k] = ops.nchw_to_nhwc(t).view(b, v, h, w, c)
-        ref2 = pyr["level2"].view(b, v, *pyr["level2"].shape[1:])[:, 0].contiguous()
+        f1, f2, f3 = self.feature_net.forward_nhwc(x)
         projs = [ops._chk(proj_matrices[f"level_{l}"].float(), "proj_matrices") for l in (1, 2, 3)]   # net.py:96-98
         flag = ops.NanFlag(x.device)
         depth, depth_up, conf, conf_up = self.iter_mvs.forward_packed(
-            fea["level1"], fea["level2"], fea["level3"], ref2, projs[0], projs[1], projs[2],
+            f1, f2, f3, projs[0], projs[1], projs[2],
             ops._chk(depth_min.float(), "depth_min"), ops._chk(depth_max.float(), "depth_max"), nan_flag=flag)
         self._last_nan_flag = flag            # checked lazily by callers that synchronise (tests, eval loop)
         return {"depths_upsampled": depth_up, "confidence_upsampled": conf_up}

@@ -1,0 +1,112 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/itermvs_b200.h declares
+(no compute calls without a GPU), host-side logic (weight packing, TF32 split, BN folding, synthetic
+generator), and the product package never touches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    from itermvs_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "itermvs_b200.h")).read()
+    declared = set(re.findall(r"\b(imvs_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"imvs_wpair", "imvs_weights", "imvs_problem", "imvs_corrnet_weights", "imvs_featurenet_weights"}
+    handle = _lib.lib()
+    missing = [s for s in sorted(declared) if not hasattr(handle, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTED_SYMBOLS) <= declared | {"imvs_launches_total"}
+    assert handle.imvs_abi_version() == _lib.ABI_VERSION
+
+
+def test_host_side_validation_without_gpu():
+    from itermvs_b200 import _lib
+    L = _lib.lib()
+    pb = _lib.Problem(1, 5, 512, 640, 32, 4)
+    nbytes = L.imvs_forward_workspace_bytes(C.byref(pb))
+    assert 50e6 < nbytes < 200e6
+    assert L.imvs_forward_launch_count(C.byref(pb)) == 28 + 17 * 4
+    for bad in (_lib.Problem(1, 1, 512, 640, 32, 4), _lib.Problem(1, 5, 512, 650, 32, 4), _lib.Problem(1, 5, 512, 640, 30, 4),
+                _lib.Problem(0, 5, 512, 640, 32, 4), _lib.Problem(1, 40, 512, 640, 32, 4)):
+        assert L.imvs_forward_workspace_bytes(C.byref(bad)) == 0
+        assert len(L.imvs_last_error()) > 0
+    assert L.imvs_featurenet_workspace_bytes(5, 512, 640) > 0
+    assert L.imvs_get_conv_passes() == 3
+
+
+def test_tf32_split_and_packing(dtu_weights):
+    from itermvs_b200 import _pack
+    w = torch.randn(10000) * torch.logspace(-6, 3, 10000)
+    hi, lo = _pack.split_tf32(w)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # 10-bit mantissa
+    assert float(((w - hi).abs() / w.abs()).max()) <= 2 ** -11 + 1e-9       # round to nearest
+    assert float(((w - hi - lo).abs() / w.abs()).max()) < 2 ** -21
+    # round-half-away on an exact tie
+    t = torch.tensor([1.0 + 2 ** -11, -(1.0 + 2 ** -11)])
+    assert torch.equal(_pack.round_tf32(t), torch.tensor([1.0 + 2 ** -10, -(1.0 + 2 ** -10)]))
+    # conv packing: [Cout,Cin,3,3] -> [9][CinP][CoutP]
+    w = dtu_weights["iter_mvs.update.gru.convq.weight"]
+    hi, lo = _pack.pack_mma_conv(w, cinp=48)
+    assert hi.shape == (9, 48, 32)
+    rec = (hi + lo)[:, :43, :].reshape(3, 3, 43, 32).permute(3, 2, 0, 1)
+    assert float((rec - w).abs().max()) < 1e-7 * float(w.abs().max()) + 1e-12
+    assert float(hi[:, 43:, :].abs().max()) == 0.0
+    wt = dtu_weights["iter_mvs.evaluation.corr_conv1.0.conv3.weight"]          # ConvTranspose [Cin,Cout,3,3]
+    hi, lo = _pack.pack_mma_tconv(wt)
+    assert hi.shape == (9, 32, 16)
+    assert float(((hi + lo)[4] - wt[:, :, 1, 1]).abs().max()) < 1e-7
+
+
+def test_bn_folding_matches_batchnorm(dtu_weights):
+    import torch.nn.functional as F
+    from itermvs_b200 import _pack
+    sd = {k[len("feature_net."):]: v for k, v in dtu_weights.items() if k.startswith("feature_net.")}
+    x = torch.randn(2, 8, 12, 14)
+    p = "layer1.0.conv1."
+    w, b = _pack.fold_bn(sd, p)
+    got = F.conv2d(x, w, b, stride=2, padding=1)
+    ref = F.batch_norm(F.conv2d(x, sd[p + "conv.weight"], stride=2, padding=1), sd[p + "bn.running_mean"], sd[p + "bn.running_var"],
+                       sd[p + "bn.weight"], sd[p + "bn.bias"], training=False, eps=1e-5)
+    assert float((got - ref).abs().max()) < 1e-5
+    assert len(_pack.FNET_LAYERS) == 21
+
+
+def test_state_dict_is_reference_compatible(dtu_weights):
+    import itermvs_b200
+    m = itermvs_b200.Pipeline(iteration=4, test=True)
+    res = m.load_state_dict({"module." + k: v for k, v in dtu_weights.items()}, strict=True)   # DataParallel prefix accepted
+    assert not res.missing_keys and not res.unexpected_keys
+    ours = {k for k in m.state_dict() if not k.endswith("num_batches_tracked")}
+    assert ours == set(dtu_weights)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "itermvs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_cpu_inputs_fail_loudly(dtu_weights):
+    import itermvs_b200
+    with pytest.raises(RuntimeError, match="CUDA"):
+        itermvs_b200.differentiable_warping(torch.zeros(1, 8, 4, 4), torch.eye(4)[None], torch.eye(4)[None], torch.ones(1, 2, 4, 4))
+
+
+def test_synthetic_generator_is_deterministic():
+    from itermvs_b200.synthetic import make_sample, plane_depth_map
+    a = make_sample(160, 128, n_src=2, seed=3)
+    b = make_sample(160, 128, n_src=2, seed=3)
+    assert torch.equal(a["imgs"]["level_0"], b["imgs"]["level_0"])
+    assert a["imgs"]["level_0"].shape == (1, 3, 3, 128, 160) and a["proj_matrices"]["level_2"].shape == (1, 3, 4, 4)
+    K3 = a["proj_matrices"]["level_3"][0, 0, :3, :3].numpy()
+    K0 = a["proj_matrices"]["level_0"][0, 0, :3, :3].numpy()
+    np.testing.assert_allclose(K3[:2] * 8, K0[:2], rtol=1e-12)
+    gt = plane_depth_map(160, 128)
+    assert 600 < gt.min() < gt.max() < 700

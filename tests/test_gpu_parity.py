@@ -198,10 +198,10 @@ def test_upsample_outputs(dev, model, dtu_weights):
     c_up = torch.empty_like(d_up)
     scratch = torch.empty(b * 64 * h2 * w2, device=dev)
     gd = lambda t: t.to(dev).contiguous()
-    ref2g, ndg, confg, dming, dmaxg = gd(ref2), gd(nd), gd(conf), gd(dmin), gd(dmax)
-    _lib.check(_lib.lib().imvs_upsample_outputs(wts.ref, ref2g.data_ptr(), ndg.data_ptr(), h2 * w2, confg.data_ptr(),
-                                                dming.data_ptr(), dmaxg.data_ptr(), d_up.data_ptr(), c_up.data_ptr(),
-                                                scratch.data_ptr(), b, h2, w2, ops._stream()))
+    ref2g, ndg, confg, dming, dmaxg = gd(ref2.permute(0, 2, 3, 1)), gd(nd), gd(conf), gd(dmin), gd(dmax)   # feature channels-last
+    _lib.check(_lib.lib().imvs_upsample_outputs(wts.ref, ref2g.data_ptr(), h2 * w2 * 32, ndg.data_ptr(), h2 * w2, 1,
+                                                confg.data_ptr(), dming.data_ptr(), dmaxg.data_ptr(), d_up.data_ptr(),
+                                                c_up.data_ptr(), scratch.data_ptr(), b, h2, w2, ops._stream()))
     assert maxerr(d_up, want_d) / 500.0 < 2e-6
     assert maxerr(c_up, want_c) < 1e-6
 
@@ -283,3 +283,51 @@ def test_size_independent_properties(dev, model):
     assert torch.isfinite(d).all() and float(d.min()) >= 425.0 - 1e-2 and float(d.max()) <= 935.0 + 1e-2
     c = both["confidence_upsampled"]
     assert torch.isfinite(c).all() and float(c.min()) >= 0 and float(c.max()) <= 1
+
+
+def test_featurenet_vs_oracle(dev, model, dtu_weights):
+    """FeatureNet on the tensor-core conv kernels (BN folded, 3xTF32 split) against the fp32 CPU oracle."""
+    s = make_sample(320, 256, n_src=2, batch=1, seed=6, scene="plane")
+    x = s["imgs"]["level_0"]
+    got = model.feature_net(x.to(dev))                     # reference return format: level -> list of NCHW views
+    for v in range(3):
+        want = O.feature_net(dtu_weights, x[:, v])
+        for lvl in ("level1", "level2", "level3"):
+            err = maxerr(got[lvl][v], want[lvl])
+            scale = float(want[lvl].abs().max())
+            assert err < 2e-5 * max(scale, 1.0), (lvl, v, err, scale)
+
+
+def test_single_pass_tf32_mode(dev, model, dtu_weights):
+    """conv_passes=1 (plain TF32 tensor-core convolutions, the precision of the reference's own cuDNN
+    path on Ampere+): depth must still meet the 1e-3 relative tolerance on the consistent scene."""
+    from itermvs_b200 import _lib
+    s = make_sample(640, 512, n_src=4, batch=1, seed=0, scene="plane")
+    want = O.pipeline_forward(dtu_weights, s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"], iteration=4)
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    _lib.set_conv_passes(1)
+    try:
+        with torch.no_grad():
+            out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_conv_passes(3)
+    d, dref = out["depths_upsampled"].cpu(), want["depths_upsampled"]
+    rel = ((d - dref).abs() / dref).numpy()
+    print(f"TF32 single pass: depth rel err mean {rel.mean():.2e} median {np.median(rel):.2e} max {rel.max():.2e}, "
+          f"px>1e-3: {100 * (rel > 1e-3).mean():.3f}%")
+    assert np.median(rel) < 2e-4
+    assert (rel > 1e-3).mean() < 0.05
+
+
+def test_error_behaviour(dev, model):
+    """Bad arguments surface as Python exceptions carrying the library's message (no crash, no sync)."""
+    from itermvs_b200 import _lib
+    import ctypes as C
+    pb = _lib.Problem(1, 5, 500, 640, 32, 4)                 # H not a multiple of 32
+    assert _lib.lib().imvs_forward_workspace_bytes(C.byref(pb)) == 0
+    assert b"multiples of 32" in _lib.lib().imvs_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.set_conv_passes(2)
+    with pytest.raises(RuntimeError):                        # CPU tensors are rejected: there is no CPU path
+        model({"level_0": torch.zeros(1, 3, 3, 64, 64)}, {}, torch.ones(1), torch.ones(1))
