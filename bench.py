@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--passes", type=int, default=3, choices=[1, 3],
+                    help="tensor-core conv precision: 3 = 3xTF32 split (fp32-grade, default), 1 = single-pass TF32")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage timing table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -188,9 +190,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cudnn.benchmark = True          # as eval.py:21
-    torch.backends.cudnn.allow_tf32 = False        # fp32 throughout (the metric's dtype)
-    torch.backends.cuda.matmul.allow_tf32 = False
+    _lib.set_conv_passes(args.passes)
 
     weights = load_weights()
     model = itermvs_b200.Pipeline(iteration=ITERS, test=True)
@@ -334,9 +334,9 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "refs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32 (3xTF32 tensor-core convolutions, fp32 accumulate; sampling/softmax/regression fp32)" if args.passes == 3 else "tf32 (single-pass TF32 tensor-core convolutions, fp32 accumulate; rest fp32)", "data": "synthetic",
         "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 per GPU (BASELINE configs[1])",
-                   "step": "Pipeline.forward test mode: FeatureNet (cuDNN fp32) + fused sm_100a estimator",
+                   "step": "Pipeline.forward test mode: FeatureNet + estimator, all in hand-written sm_100a kernels (no cuDNN/cuBLAS)",
                    "launch": "eager" if graphed is None else "cuda-graph replay",
                    "l2": "256 MiB memset between steps, outside the per-step CUDA-event windows",
                    "weights": "DTU checkpoint", "parallelism": f"replicas x{world} (one reference view per GPU, no collectives)"},
