@@ -21,9 +21,9 @@
  *   composed projections    [B][S][12]        rot (3x3 row-major) then trans (3)
  *   correlation volumes     [B][slice][P][8]  8 = group-wise correlation channels, innermost
  *   GRU input x             [B][H2][W2][16]   ch 0 = normalized depth, 1..10 = correlation, 11..15 = 0
- *   conv weights            [tap][CinP][CoutP] CinP/CoutP = channels padded to a multiple of 8 with zeros,
- *                                             values pre-rounded to TF32 ("hi"); "lo" = TF32(w - hi) for the
- *                                             3-pass fp32-grade mode (packed by itermvs_b200/_pack.py)
+ *   conv weights            [tap][CinP][CoutP] CinP/CoutP = channels padded to a multiple of 8 with zeros; each
+ *                                             weight is given twice: TF32-rounded (1-pass mode) and plain
+ *                                             fp32 (3-pass fp32-grade mode) (packed by itermvs_b200/_pack.py)
  */
 #ifndef ITERMVS_B200_H_
 #define ITERMVS_B200_H_
@@ -54,7 +54,10 @@ long long imvs_launches_total(void);
 int imvs_set_conv_passes(int passes);
 int imvs_get_conv_passes(void);
 
-typedef struct imvs_wpair { const float* hi; const float* lo; } imvs_wpair;   /* packed conv weight */
+typedef struct imvs_wpair {      /* packed conv weight [tap][CinP][CoutP] */
+    const float* tf32;           /* values rounded to TF32 (round-to-nearest): operand of the 1-pass mode */
+    const float* fp32;           /* plain fp32: the 3-pass mode splits hi/lo in registers */
+} imvs_wpair;
 
 typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */
     imvs_wpair conv0;      /* conv0.conv.weight  8 -> 8            [9][8][8]   */

@@ -23,7 +23,7 @@ FNET_CONVS = 22
 
 
 class WPair(C.Structure):
-    _fields_ = [("hi", vp), ("lo", vp)]
+    _fields_ = [("tf32", vp), ("fp32", vp)]
 
 
 class CorrNetWeights(C.Structure):

@@ -25,7 +25,7 @@ Tensor = torch.Tensor
 def round_tf32(x: Tensor) -> Tensor:
     """cvt.rna.tf32.f32: keep 10 mantissa bits, round to nearest, ties away from zero."""
     bits = x.contiguous().view(torch.int32)
-    r = ((bits + 0x1000) & ~0x1FFF) if True else bits
+    r = (bits + 0x1000) & ~0x1FFF
     # (two's-complement add on the sign-magnitude pattern raises the magnitude for both signs)
     return r.view(torch.float32)
 
@@ -35,9 +35,8 @@ def _pad8(n: int) -> int:
 
 
 def split_tf32(w: Tensor) -> Tuple[Tensor, Tensor]:
-    hi = round_tf32(w)
-    lo = round_tf32(w - hi)
-    return hi.contiguous(), lo.contiguous()
+    """(TF32-rounded copy for the 1-pass mode, plain fp32 for the 3-pass mode)."""
+    return round_tf32(w).contiguous(), w.contiguous().clone()
 
 
 def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0) -> Tuple[Tensor, Tensor]:

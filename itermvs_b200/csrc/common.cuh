@@ -63,7 +63,7 @@ int ensure_dynamic_smem(K kern, size_t smem, int* done_mask) {
     int dev = 0;
     IMVS_CUDA(cudaGetDevice(&dev));
     if ((*done_mask >> (dev & 31)) & 1) return 0;
-    IMVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    IMVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     *done_mask |= 1 << (dev & 31);
     return 0;
 }

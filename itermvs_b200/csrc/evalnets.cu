@@ -15,7 +15,7 @@ struct EpiCorrOut {          // conv5 (1 valid cout): + bias, scatter to out[(n/
     size_t bstride, pstride;
     int H, W;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int, int t, const float (&v)[2 * NT], int) const {
         if (t != 0 || oy >= H || ox >= W) return;
         const int r = n % period;
         const float* b = r < split1 ? bias[0] : (r < split2 ? bias[1] : bias[2]);
@@ -23,13 +23,12 @@ struct EpiCorrOut {          // conv5 (1 valid cout): + bias, scatter to out[(n/
     }
 };
 
-static MmaWeightSel sel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
-    MmaWeightSel s;
+static WSets sel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
+    WSets s;
     for (int i = 0; i < 3; ++i) {
         const imvs_corrnet_weights& c = sets[i];
-        const imvs_wpair p = which == 0 ? c.conv0 : which == 1 ? c.conv1 : which == 2 ? c.conv2
-                           : which == 3 ? c.conv3 : which == 4 ? c.conv4 : c.conv5;
-        s.hi[i] = p.hi; s.lo[i] = p.lo;
+        s.w[i] = which == 0 ? c.conv0 : which == 1 ? c.conv1 : which == 2 ? c.conv2
+               : which == 3 ? c.conv3 : which == 4 ? c.conv4 : c.conv5;
     }
     s.period = period; s.split1 = split1; s.split2 = split2;
     return s;
@@ -42,7 +41,7 @@ struct EpiPvw {              // relu(16 channels) . w1 + b1 -> logits[n][y][x]; 
     const float* b1;
     int H, W;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -101,7 +100,7 @@ int launch_upsample2x_nhwc(const float* in, float* out, int N, int H, int W, int
 template <int D>
 static int hinit_conv0(const imvs_weights* w, const float* corr, float* t, int B, int H3, int W3, cudaStream_t st) {
     return mma_conv<D, 64, 2, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), EpiNHWC{t, nullptr, nullptr, H3, W3, 64, 64, 1},
-                                           MmaWeightSel::single(w->hinit_conv0), make_taps_conv(3, 1, 1, 8), B, 64, H3, W3, 1, st);
+                                           WSets::single(w->hinit_conv0), conv_tables(3, 1, 1, 8), B, 64, H3, W3, 1, st);
 }
 
 }  // namespace imvs
@@ -126,27 +125,23 @@ extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int sp
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
     auto sel = [&](int which) { return sel_of(sets, period, split1, split2, which); };
     IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), EpiNHWC{c0, nullptr, nullptr, H, W, 8, 8, 1},
-                                            sel(0), make_taps_conv(3, 1, 1, 8), N, 8, H, W, 1, st)));
+                                            sel(0), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));
     IMVS_TRY((mma_conv<8, 16, 2, 4, 2, true>("corrnet.conv1", in_nhwc(c0, H, W, 8), EpiNHWC{c1, nullptr, nullptr, H1, W1, 16, 16, 1},
-                                             sel(1), make_taps_conv(3, 2, 1, 8), N, 16, H1, W1, 1, st)));
+                                             sel(1), conv_tables(3, 2, 1, 8), N, 16, H1, W1, 1, st)));
     IMVS_TRY((mma_conv<16, 32, 2, 4, 2, true>("corrnet.conv2", in_nhwc(c1, H1, W1, 16), EpiNHWC{c2, nullptr, nullptr, H2, W2, 32, 32, 1},
-                                              sel(2), make_taps_conv(3, 2, 1, 8), N, 32, H2, W2, 1, st)));
-    for (int ab = 0; ab < 4; ++ab) {        // conv3: transposed 32 -> 16 on the H/4 grid, + c1  (itermvs.py:374)
-        const int a = ab >> 1, b = ab & 1;
-        IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("corrnet.conv3", in_nhwc(c2, H2, W2, 32), EpiTconvNHWC{x3, c1, H2, W2, 16, a, b},
-                                                  sel(3), make_taps_tconv(a, b, 8), N, 16, H2, W2, 1, st)));
-    }
-    for (int ab = 0; ab < 4; ++ab) {        // conv4: transposed 16 -> 8 on the H/2 grid, + c0   (itermvs.py:376)
-        const int a = ab >> 1, b = ab & 1;
-        IMVS_TRY((mma_conv<16, 8, 2, 4, 1, true>("corrnet.conv4", in_nhwc(x3, H1, W1, 16), EpiTconvNHWC{x4, c0, H1, W1, 8, a, b},
-                                                 sel(4), make_taps_tconv(a, b, 8), N, 8, H1, W1, 1, st)));
-    }
+                                              sel(2), conv_tables(3, 2, 1, 8), N, 32, H2, W2, 1, st)));
+    // conv3 / conv4: transposed convolutions, the four output parities as variants of one launch,
+    // + U-Net skips c1 / c0 (itermvs.py:374-377)
+    IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("corrnet.conv3", in_nhwc(c2, H2, W2, 32), EpiTconvNHWC{x3, c1, H2, W2, 16},
+                                              sel(3), tconv_tables(8), N, 16, H2, W2, 1, st)));
+    IMVS_TRY((mma_conv<16, 8, 2, 4, 1, true>("corrnet.conv4", in_nhwc(x3, H1, W1, 16), EpiTconvNHWC{x4, c0, H1, W1, 8},
+                                             sel(4), tconv_tables(8), N, 8, H1, W1, 1, st)));
     EpiCorrOut e5;
     e5.out = out;
     for (int i = 0; i < 3; ++i) e5.bias[i] = sets[i].conv5_b;
     e5.period = period; e5.split1 = split1; e5.split2 = split2;
     e5.bstride = out_batch_stride; e5.pstride = out_pixel_stride; e5.H = H; e5.W = W;
-    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), make_taps_conv(3, 1, 1, 8), N, 8, H, W, 1, st)));
+    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));
     return 0;
 }
 
@@ -157,7 +152,7 @@ extern "C" int imvs_pixel_view_weight(const imvs_weights* w, const float* corr, 
     cudaStream_t st = (cudaStream_t)stream;
     const int N = B * S * D, P3 = H3 * W3;
     IMVS_TRY((mma_conv<8, 16, 2, 4, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), EpiPvw{logits, w->pvw_conv1, w->pvw_conv1_b, H3, W3},
-                                             MmaWeightSel::single(w->pvw_conv0), make_taps_conv(3, 1, 1, 8), N, 16, H3, W3, 1, st)));
+                                             WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 8), N, 16, H3, W3, 1, st)));
     pvw_reduce_kernel<<<cdiv(B * S * P3, 128), 128, 0, st>>>(logits, vw3, B * S, D, P3);
     count_launch();
     IMVS_LAUNCH_CHECK("pvw_reduce_kernel");
@@ -181,6 +176,6 @@ extern "C" int imvs_hidden_init(const imvs_weights* w, const float* corr, float*
         default: return fail("hidden_init: D=%d not supported (8, 16, 32, 48 or 64 hypotheses)", D);
     }
     IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("hidden_init.fc", in_nhwc(t, H3, W3, 64), EpiNHWC{u, w->hinit_fc_b, nullptr, H3, W3, 32, 32, 0},
-                                              MmaWeightSel::single(w->hinit_fc), make_taps_conv(1, 1, 1, 8), B, 32, H3, W3, 1, st)));
+                                              WSets::single(w->hinit_fc), conv_tables(1, 1, 1, 8), B, 32, H3, W3, 1, st)));
     return launch_upsample2x_nhwc(u, hidden, B, H3, W3, 32, true, st);
 }

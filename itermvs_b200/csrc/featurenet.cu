@@ -15,7 +15,7 @@ struct EpiAddUp2 {
     const float* coarse;     // [N][H/2][W/2][C]
     int H, W, C;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
         if (oy >= H || ox >= W) return;
         const int Hc = H / 2, Wc = W / 2;
         int h0, h1, w0, w1;
@@ -63,19 +63,19 @@ template <int CI, int CO, bool WALL_A, bool WALL_B>
 static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, float* const buf[4], int N, int Hin, int Win,
                      cudaStream_t st) {
     const int H = Hin / 2, W = Win / 2;
-    const TapTable s2 = make_taps_conv(3, 2, 1, 8), s1 = make_taps_conv(3, 1, 1, 8);
+    const TapTables s2 = conv_tables(3, 2, 1, 8), s1 = conv_tables(3, 1, 1, 8);
     // block 0: conv1 (stride 2, relu), downsample (stride 2), conv2 + downsample -> relu
     IMVS_TRY((mma_conv<CI, CO, 2, 4, 2, WALL_A>("fnet.block0.conv1", in_nhwc(x, Hin, Win, CI), EpiNHWC{buf[0], w->b[L], nullptr, H, W, CO, CO, 1},
-                                                MmaWeightSel::single(w->w[L]), s2, N, CO, H, W, 1, st)));
+                                                WSets::single(w->w[L]), s2, N, CO, H, W, 1, st)));
     IMVS_TRY((mma_conv<CI, CO, 2, 4, 2, WALL_A>("fnet.block0.downsample", in_nhwc(x, Hin, Win, CI), EpiNHWC{buf[1], w->b[L + 2], nullptr, H, W, CO, CO, 0},
-                                                MmaWeightSel::single(w->w[L + 2]), s2, N, CO, H, W, 1, st)));
+                                                WSets::single(w->w[L + 2]), s2, N, CO, H, W, 1, st)));
     IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
-                                                MmaWeightSel::single(w->w[L + 1]), s1, N, CO, H, W, 1, st)));
+                                                WSets::single(w->w[L + 1]), s1, N, CO, H, W, 1, st)));
     // block 1: conv1 relu, conv2 + x -> relu
     IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
-                                                MmaWeightSel::single(w->w[L + 3]), s1, N, CO, H, W, 1, st)));
+                                                WSets::single(w->w[L + 3]), s1, N, CO, H, W, 1, st)));
     IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
-                                                MmaWeightSel::single(w->w[L + 4]), s1, N, CO, H, W, 1, st)));
+                                                WSets::single(w->w[L + 4]), s1, N, CO, H, W, 1, st)));
     return 0;
 }
 
@@ -101,25 +101,25 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm_(ST_FEATURENET, stream);
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8;
-    const TapTable s1 = make_taps_conv(3, 1, 1, 8), k1 = make_taps_conv(1, 1, 1, 8);
+    const TapTables s1 = conv_tables(3, 1, 1, 8), k1 = conv_tables(1, 1, 1, 8);
     // conv1: 3 -> 8, BN, ReLU on the planar image (net.py:13)
     IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
-                                            MmaWeightSel::single(w->w[0]), s1, N, 8, H, W, 1, st)));
+                                            WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
     IMVS_TRY((res_stage<16, 32, true, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));   // layer2 -> l2[3]  [H/4][W/4][32]
     IMVS_TRY((res_stage<32, 48, false, false>(w, 11, b.l2[3], b.l3, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48]
     // output3 (net.py:59)
     IMVS_TRY((mma_conv<48, 48, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), EpiNHWC{fea3, w->b[16], nullptr, H3, W3, 48, 48, 0},
-                                               MmaWeightSel::single(w->w[16]), s1, N, 48, H3, W3, 1, st)));
+                                               WSets::single(w->w[16]), s1, N, 48, H3, W3, 1, st)));
     // intra2 = up2(f3) + inner2(f2); output2 (net.py:60-62)
     IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2{b.intra2, w->b[17], b.l3[3], H2, W2, 48},
-                                              MmaWeightSel::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
+                                              WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
     IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), EpiNHWC{fea2, w->b[18], nullptr, H2, W2, 32, 32, 0},
-                                               MmaWeightSel::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
+                                               WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
     // intra1 = up2(intra2) + inner1(f1); output1 (net.py:63-64)
     IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2{b.intra1, w->b[19], b.intra2, H1, W1, 48},
-                                              MmaWeightSel::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
+                                              WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
     IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), EpiNHWC{fea1, w->b[20], nullptr, H1, W1, 16, 16, 0},
-                                               MmaWeightSel::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
+                                               WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
     return 0;
 }

@@ -69,7 +69,7 @@ extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
 
 extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     if (check_problem(pb) != 0) return -1;
-    return 28 + 17 * pb->iterations;
+    return 22 + 11 * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,

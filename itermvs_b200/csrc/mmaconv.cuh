@@ -4,19 +4,24 @@
 //
 // * activations are channels-last (NHWC, channel count padded to a multiple of 8);
 // * a CTA owns a TH x 16 output tile (TH = WARPS*MT rows, one m16 MMA row-tile = 16 consecutive x)
-//   and NB output channels; it stages the input tile WITH HALO once in shared memory (rounded to
-//   TF32, round-to-nearest), so every tap of the 3x3 / dilated / strided / transposed stencil is the
-//   same smem tile read at a shifted address -- no im2col copy, each input element is fetched from
-//   L2 once per CTA instead of once per tap;
-// * weights stream through a double-buffered smem ring, one tap ([Cin][NB]) per stage, cp.async;
-// * math: mma.sync.m16n8k8 TF32 with fp32 accumulation.  PASSES = 3 adds the error-compensated
-//   split (a = a_hi + a_lo, w = w_hi + w_lo; hi*hi + hi*lo + lo*hi) for fp32-grade results.
-//   The stock PyTorch/cuDNN GPU path of the reference runs its convolutions in TF32 as well
-//   (torch.backends.cudnn.allow_tf32 defaults to True), so PASSES = 1 is the reference's own
-//   GPU precision; the parity tests state which mode they ran.
-// * the stencil is a runtime tap table, so regular, dilated, strided and (per output parity)
-//   transposed convolutions share one kernel.
+//   and NB output channels; it copies the input tile WITH HALO once into shared memory with
+//   cp.async (zero-filled outside the image), so every tap of the 3x3 / dilated / strided /
+//   transposed stencil is the same smem tile read at a shifted address -- no im2col copy, each
+//   input element is fetched from L2 once per CTA instead of once per tap;
+// * weights stream through a 3-stage cp.async ring, one tap ([Cin][NB]) per stage, loaded two taps
+//   ahead (small layers keep all taps resident: WALL);
+// * math: mma.sync.m16n8k8 TF32 with fp32 accumulation.
+//     PASSES = 1: A rounded to TF32 (round-to-nearest) at fragment load, weights pre-rounded on
+//                 the host -- the precision of the reference's own cuDNN path on Ampere+
+//                 (torch.backends.cudnn.allow_tf32 defaults to True);
+//     PASSES = 3: error-compensated split computed in registers from the fp32 operands
+//                 (x_hi = x & ~0x1fff, x_lo = x - x_hi):  lo*hi + hi*lo + hi*hi  -> fp32-grade
+//                 (relative error ~2^-21), no extra shared memory.
+// * the stencil is a runtime tap table (up to 4 variants per launch), so regular, dilated, strided
+//   and the four output parities of a transposed convolution share one kernel / one launch.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace imvs {
@@ -27,6 +32,11 @@ struct TapTable {
     int widx[9];            // weight slice of each tap in the packed [slice][CINP][COUT] array
     int dy_min, dx_min;     // tile origin offset
     int IH, IW;             // smem input tile extent for a TH x 16 output tile
+};
+
+struct TapTables {          // launch variants (blockIdx.z % count)
+    TapTable t[4];
+    int count;
 };
 
 inline TapTable make_taps_conv(int ks, int stride, int dil, int TH) {
@@ -44,22 +54,35 @@ inline TapTable make_taps_conv(int ks, int stride, int dil, int TH) {
     return t;
 }
 
-// ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1), output parity (a, b): the outputs
-// (2*iy + a, 2*ix + b) as a stride-1 "convolution" over the INPUT grid (y = 2*iy - 1 + ky):
-//   a = 0: ky = 1 (dy 0)          a = 1: ky = 0 (dy +1), ky = 2 (dy 0)        likewise in x
-inline TapTable make_taps_tconv(int a, int b, int TH) {
-    TapTable t{};
-    int kys[2], dys[2], nky, kxs[2], dxs[2], nkx;
-    if (a == 0) { nky = 1; kys[0] = 1; dys[0] = 0; } else { nky = 2; kys[0] = 0; dys[0] = 1; kys[1] = 2; dys[1] = 0; }
-    if (b == 0) { nkx = 1; kxs[0] = 1; dxs[0] = 0; } else { nkx = 2; kxs[0] = 0; dxs[0] = 1; kxs[1] = 2; dxs[1] = 0; }
-    t.n = 0;
-    for (int i = 0; i < nky; ++i)
-        for (int j = 0; j < nkx; ++j) {
-            t.dy[t.n] = dys[i]; t.dx[t.n] = dxs[j]; t.widx[t.n] = kys[i] * 3 + kxs[j]; t.n++;
-        }
-    t.dy_min = 0; t.dx_min = 0;
-    t.IH = TH + 1; t.IW = 17;
-    return t;
+inline TapTables conv_tables(int ks, int stride, int dil, int TH) {
+    TapTables tt{};
+    tt.t[0] = make_taps_conv(ks, stride, dil, TH);
+    tt.count = 1;
+    return tt;
+}
+
+// ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1): the outputs (2*iy + a, 2*ix + b) of
+// parity (a, b) as a stride-1 "convolution" over the INPUT grid (y = 2*iy - 1 + ky):
+//   a = 0: ky = 1 (dy 0)          a = 1: ky = 0 (dy +1), ky = 2 (dy 0)        likewise in x.
+// Variant v = 2*a + b.
+inline TapTables tconv_tables(int TH) {
+    TapTables tt{};
+    for (int v = 0; v < 4; ++v) {
+        const int a = v >> 1, b = v & 1;
+        TapTable& t = tt.t[v];
+        int kys[2], dys[2], nky, kxs[2], dxs[2], nkx;
+        if (a == 0) { nky = 1; kys[0] = 1; dys[0] = 0; } else { nky = 2; kys[0] = 0; dys[0] = 1; kys[1] = 2; dys[1] = 0; }
+        if (b == 0) { nkx = 1; kxs[0] = 1; dxs[0] = 0; } else { nkx = 2; kxs[0] = 0; dxs[0] = 1; kxs[1] = 2; dxs[1] = 0; }
+        t.n = 0;
+        for (int i = 0; i < nky; ++i)
+            for (int j = 0; j < nkx; ++j) {
+                t.dy[t.n] = dys[i]; t.dx[t.n] = dxs[j]; t.widx[t.n] = kys[i] * 3 + kxs[j]; t.n++;
+            }
+        t.dy_min = 0; t.dx_min = 0;
+        t.IH = TH + 1; t.IW = 17;
+    }
+    tt.count = 4;
+    return tt;
 }
 
 __device__ __forceinline__ uint32_t f2tf32(float x) {
@@ -75,15 +98,23 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+// x = hi + lo with hi = upper 19 bits (TF32 by truncation), lo = TF32-truncated remainder
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;            // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // WALL_ = true: all taps' weights are staged up front (small layers: no per-tap barrier);
-// false: one tap per stage through a double-buffered ring (large layers).
+// false: one tap per stage through a 3-deep ring (large layers).
 template <int CINP_, int NB_, int MT_, int WARPS_, int STRIDE_, int PASSES_, bool WALL_ = false>
 struct MmaCfg {
     static constexpr int CINP = CINP_, NB = NB_, MT = MT_, WARPS = WARPS_, STRIDE = STRIDE_, PASSES = PASSES_;
@@ -95,23 +126,29 @@ struct MmaCfg {
     static constexpr int NP = NB + 8 + (NB == 8 ? 8 : 0);   // smem cout pitch: = 8 or 24 mod 32 -> conflict-free B loads
     static constexpr int KSTEPS = CINP / 8;
     static constexpr int WBUF = CINP * NP;                  // floats per weight stage
+    static constexpr int RING = 3;
     static_assert(CINP % 8 == 0 && NB % 8 == 0, "channel padding");
     static_assert(PASSES == 1 || PASSES == 3, "PASSES");
-    static size_t smem_bytes(const TapTable& t) {
-        size_t tile = (size_t)t.IH * t.IW * CP;
-        const size_t stages = WALL ? (size_t)t.n : 2;
-        return sizeof(float) * ((PASSES == 3 ? 2 : 1) * (tile + stages * (size_t)WBUF));
+    static size_t smem_bytes(const TapTables& tt) {
+        size_t tile = 0, taps = 0;
+        for (int v = 0; v < tt.count; ++v) {
+            tile = std::max(tile, (size_t)tt.t[v].IH * tt.t[v].IW * CP);
+            taps = std::max(taps, (size_t)tt.t[v].n);
+        }
+        return sizeof(float) * (tile + (WALL ? taps : (size_t)RING) * WBUF);
     }
 };
 
-// ---- input functors: float4 of channels [4*c4, 4*c4+4) at (n, iy, ix); zeros outside the image
+// ---- input functors ----------------------------------------------------------------------------
+// async functors give the address of channels [4*c4, 4*c4+4) at (n, iy, ix) (valid=false outside)
 struct InNHWC {
+    static constexpr bool kAsync = true;
     const float* p;
     int H, W, C;            // C = stored channel count (>= CINP used by the kernel)
     size_t nstride;         // floats between consecutive images n (H*W*C when dense)
-    __device__ __forceinline__ float4 load4(int n, int iy, int ix, int c4) const {
-        if (iy < 0 || iy >= H || ix < 0 || ix >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return ldg4(p + (size_t)n * nstride + ((size_t)iy * W + ix) * C + 4 * c4);
+    __device__ __forceinline__ const float* ptr4(int n, int iy, int ix, int c4, bool& valid) const {
+        valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        return valid ? p + (size_t)n * nstride + ((size_t)iy * W + ix) * C + 4 * c4 : p;
     }
 };
 inline InNHWC in_nhwc(const float* p, int H, int W, int C, size_t nstride = 0) {
@@ -119,18 +156,21 @@ inline InNHWC in_nhwc(const float* p, int H, int W, int C, size_t nstride = 0) {
 }
 
 struct InNHWC2 {            // channels [0,CA) from a, then [CA, CA+CB) from b (both NHWC, multiples of 4)
+    static constexpr bool kAsync = true;
     const float* a;
     const float* b;
     int H, W, CA, CBc;
-    __device__ __forceinline__ float4 load4(int n, int iy, int ix, int c4) const {
-        if (iy < 0 || iy >= H || ix < 0 || ix >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+    __device__ __forceinline__ const float* ptr4(int n, int iy, int ix, int c4, bool& valid) const {
+        valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        if (!valid) return a;
         const size_t pix = ((size_t)n * H + iy) * W + ix;
         const int c = 4 * c4;
-        return c < CA ? ldg4(a + pix * CA + c) : ldg4(b + pix * CBc + (c - CA));
+        return c < CA ? a + pix * CA + c : b + pix * CBc + (c - CA);
     }
 };
 
-struct InNCHW3 {            // 3-channel planar image [N][3][H][W] -> channels (r,g,b,0,0,0,0,0)
+struct InNCHW3 {            // 3-channel planar image [N][3][H][W] -> channels (r,g,b,0,0,0,0,0); synchronous staging
+    static constexpr bool kAsync = false;
     const float* p;
     int H, W;
     __device__ __forceinline__ float4 load4(int n, int iy, int ix, int c4) const {
@@ -140,91 +180,76 @@ struct InNCHW3 {            // 3-channel planar image [N][3][H][W] -> channels (
     }
 };
 
-// grid: (ceil(Wout/16), ceil(Hout/TH), N * ncb); block: THREADS; dyn smem: Cfg::smem_bytes(taps)
-// weights: w_hi (and w_lo when PASSES == 3): [slice][CINP][cout_total], values already rounded to TF32.
-// Epi::row(n, oy, ox, co0, v): v[2*j], v[2*j+1] = couts co0 + 8*j + 2*t, +1 of pixel (oy, ox) for this
-// thread's quad position t = lane & 3; called for every (row-tile, half) with FULL-WARP uniformity
-// (pixels outside the image included: the functor masks its stores), so it may shuffle within quads.
 struct MmaWeightSel {       // image n of a batched launch picks one of up to three weight sets
-    const float* hi[3];
-    const float* lo[3];
+    const float* w[3];      // [slice][CINP][cout_total]: TF32-rounded (PASSES 1) or plain fp32 (PASSES 3)
     int period, split1, split2;
-    __device__ __forceinline__ int pick(int n) const {
+    __device__ __forceinline__ const float* pick(int n) const {
         const int r = n % period;
-        return r < split1 ? 0 : (r < split2 ? 1 : 2);
-    }
-    static MmaWeightSel single(imvs_wpair w) {
-        MmaWeightSel s;
-        for (int i = 0; i < 3; ++i) { s.hi[i] = w.hi; s.lo[i] = w.lo; }
-        s.period = 1; s.split1 = 1; s.split2 = 1;
-        return s;
+        return r < split1 ? w[0] : (r < split2 ? w[1] : w[2]);
     }
 };
 
+// grid: (ceil(Wout/16), ceil(Hout/TH), N * ncb * variants); block: THREADS; dyn smem: Cfg::smem_bytes
+// Epi::row<NT>(n, oy, ox, co0, t, v, variant): v[2*j], v[2*j+1] = couts co0 + 8*j + 2*t, +1 of pixel
+// (oy, ox) for this thread's quad position t = lane & 3; called for every (row-tile, half) with
+// FULL-WARP uniformity (pixels outside the image included: the functor masks its stores), so it may
+// shuffle within quads.
 template <class Cfg, class In, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS)
-mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel,
-                const TapTable taps, int cout_total, int Hout, int Wout, int ncb) {
+mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTables tabs, int cout_total, int Hout, int Wout, int ncb) {
     constexpr int CP = Cfg::CP, NP = Cfg::NP, CINP = Cfg::CINP, NB = Cfg::NB, MT = Cfg::MT, NT = Cfg::NT;
     extern __shared__ __align__(16) float smem[];
-    const int tile_floats = taps.IH * taps.IW * CP;
+    const int variant = blockIdx.z % tabs.count;
+    const int ncbz = blockIdx.z / tabs.count;
+    const int n = ncbz / ncb, cb = ncbz % ncb;
+    const TapTable& taps = tabs.t[variant];
+    int tile_floats = 0;
+    for (int v = 0; v < tabs.count; ++v) tile_floats = max(tile_floats, tabs.t[v].IH * tabs.t[v].IW * CP);
     float* sA = smem;
-    float* sAlo = smem + tile_floats;                                        // PASSES == 3 only
-    const int wstages = Cfg::WALL ? taps.n : 2;
-    float* sW = smem + (Cfg::PASSES == 3 ? 2 : 1) * tile_floats;             // [stages][WBUF] (hi) then the same (lo)
-    float* sWlo = sW + wstages * Cfg::WBUF;
-
-    const int n = blockIdx.z / ncb, cb = blockIdx.z % ncb;
+    float* sW = smem + tile_floats;
     const int oy0 = blockIdx.y * Cfg::TH, ox0 = blockIdx.x * 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wset = wsel.pick(n);
-    const float* __restrict__ w_hi = wsel.hi[wset];
-    const float* __restrict__ w_lo = wsel.lo[wset];
+    const float* __restrict__ wg = wsel.pick(n);
+    const int ntaps = taps.n;
 
-    auto load_weights = [&](int tap, int buf) {
-        const float* src = w_hi + ((size_t)taps.widx[tap] * CINP) * cout_total + cb * NB;
+    auto issue_weights = [&](int tap, int buf) {
+        const float* src = wg + ((size_t)taps.widx[tap] * CINP) * cout_total + cb * NB;
         float* dst = sW + buf * Cfg::WBUF;
         constexpr int Q = NB / 4;
         for (int i = tid; i < CINP * Q; i += Cfg::THREADS) {
             const int k = i / Q, q = i % Q;
-            cp_async16(dst + k * NP + 4 * q, src + (size_t)k * cout_total + 4 * q);
+            cp_async16(dst + k * NP + 4 * q, src + (size_t)k * cout_total + 4 * q, true);
         }
-        if constexpr (Cfg::PASSES == 3) {
-            const float* srcl = w_lo + ((size_t)taps.widx[tap] * CINP) * cout_total + cb * NB;
-            float* dstl = sWlo + buf * Cfg::WBUF;
-            for (int i = tid; i < CINP * Q; i += Cfg::THREADS) {
-                const int k = i / Q, q = i % Q;
-                cp_async16(dstl + k * NP + 4 * q, srcl + (size_t)k * cout_total + 4 * q);
-            }
-        }
-        cp_async_commit();
     };
 
-    if constexpr (Cfg::WALL) {
-        for (int tp = 0; tp < taps.n; ++tp) load_weights(tp, tp);
-    } else {
-        load_weights(0, 0);
-    }
-    {   // stage the input tile (with halo), rounded to TF32
+    {   // input tile (with halo)
         const int iy0 = oy0 * Cfg::STRIDE + taps.dy_min, ix0 = ox0 * Cfg::STRIDE + taps.dx_min;
         constexpr int C4 = CINP / 4;
         const int total = taps.IH * taps.IW * C4;
         for (int i = tid; i < total; i += Cfg::THREADS) {
             const int slot = i / C4, c4 = i % C4;
             const int iy = iy0 + slot / taps.IW, ix = ix0 + slot % taps.IW;
-            const float4 v = in.load4(n, iy, ix, c4);
-            uint4 hi = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
-            *reinterpret_cast<uint4*>(sA + (size_t)slot * CP + 4 * c4) = hi;
-            if constexpr (Cfg::PASSES == 3) {
-                uint4 lo = make_uint4(f2tf32(v.x - __uint_as_float(hi.x)), f2tf32(v.y - __uint_as_float(hi.y)),
-                                      f2tf32(v.z - __uint_as_float(hi.z)), f2tf32(v.w - __uint_as_float(hi.w)));
-                *reinterpret_cast<uint4*>(sAlo + (size_t)slot * CP + 4 * c4) = lo;
+            if constexpr (In::kAsync) {
+                bool valid;
+                const float* src = in.ptr4(n, iy, ix, c4, valid);
+                cp_async16(sA + (size_t)slot * CP + 4 * c4, src, valid);
+            } else {
+                *reinterpret_cast<float4*>(sA + (size_t)slot * CP + 4 * c4) = in.load4(n, iy, ix, c4);
             }
         }
     }
-    cp_async_wait_all();
-    __syncthreads();
+    if constexpr (Cfg::WALL) {
+        for (int tp = 0; tp < ntaps; ++tp) issue_weights(tp, tp);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    } else {
+        issue_weights(0, 0);
+        cp_async_commit();
+        if (ntaps > 1) issue_weights(1, 1);
+        cp_async_commit();
+    }
 
     float acc[MT][NT][4];
 #pragma unroll
@@ -234,13 +259,16 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel,
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[r][j][q] = 0.f;
 
-    for (int tap = 0; tap < taps.n; ++tap) {
+    for (int tap = 0; tap < ntaps; ++tap) {
+        int wsel_buf = tap;
         if constexpr (!Cfg::WALL) {
-            if (tap + 1 < taps.n) load_weights(tap + 1, (tap + 1) & 1);
+            cp_async_wait<1>();            // everything but the newest group has landed: tile + this tap's weights
+            __syncthreads();               // ... for all threads; also: everyone is done with tap-1's buffer
+            if (tap + 2 < ntaps) issue_weights(tap + 2, (tap + 2) % Cfg::RING);
+            cp_async_commit();
+            wsel_buf = tap % Cfg::RING;
         }
-        const int wsel = Cfg::WALL ? tap : (tap & 1);
-        const float* wb = sW + wsel * Cfg::WBUF;
-        const float* wbl = sWlo + wsel * Cfg::WBUF;
+        const float* wb = sW + wsel_buf * Cfg::WBUF;
         const int ry = taps.dy[tap] - taps.dy_min, rx = taps.dx[tap] - taps.dx_min;
         int slot0[MT], slot1[MT];
 #pragma unroll
@@ -255,37 +283,34 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel,
             uint32_t a[MT][4], al[MT][4];
 #pragma unroll
             for (int r = 0; r < MT; ++r) {
-                a[r][0] = __float_as_uint(sA[slot0[r] + k0 + t]);
-                a[r][1] = __float_as_uint(sA[slot1[r] + k0 + t]);
-                a[r][2] = __float_as_uint(sA[slot0[r] + k0 + t + 4]);
-                a[r][3] = __float_as_uint(sA[slot1[r] + k0 + t + 4]);
+                const float f0 = sA[slot0[r] + k0 + t], f1 = sA[slot1[r] + k0 + t];
+                const float f2 = sA[slot0[r] + k0 + t + 4], f3 = sA[slot1[r] + k0 + t + 4];
                 if constexpr (Cfg::PASSES == 3) {
-                    al[r][0] = __float_as_uint(sAlo[slot0[r] + k0 + t]);
-                    al[r][1] = __float_as_uint(sAlo[slot1[r] + k0 + t]);
-                    al[r][2] = __float_as_uint(sAlo[slot0[r] + k0 + t + 4]);
-                    al[r][3] = __float_as_uint(sAlo[slot1[r] + k0 + t + 4]);
+                    split_tf32(f0, a[r][0], al[r][0]); split_tf32(f1, a[r][1], al[r][1]);
+                    split_tf32(f2, a[r][2], al[r][2]); split_tf32(f3, a[r][3], al[r][3]);
+                } else {
+                    a[r][0] = f2tf32(f0); a[r][1] = f2tf32(f1); a[r][2] = f2tf32(f2); a[r][3] = f2tf32(f3);
                 }
             }
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const uint32_t b0 = __float_as_uint(wb[(k0 + t) * NP + 8 * j + g]);
-                const uint32_t b1 = __float_as_uint(wb[(k0 + t + 4) * NP + 8 * j + g]);
-#pragma unroll
-                for (int r = 0; r < MT; ++r) mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
+                const float w0 = wb[(k0 + t) * NP + 8 * j + g], w1 = wb[(k0 + t + 4) * NP + 8 * j + g];
                 if constexpr (Cfg::PASSES == 3) {
-                    const uint32_t bl0 = __float_as_uint(wbl[(k0 + t) * NP + 8 * j + g]);
-                    const uint32_t bl1 = __float_as_uint(wbl[(k0 + t + 4) * NP + 8 * j + g]);
+                    uint32_t b0, b1, bl0, bl1;
+                    split_tf32(w0, b0, bl0);
+                    split_tf32(w1, b1, bl1);
 #pragma unroll
                     for (int r = 0; r < MT; ++r) {
-                        mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], bl0, bl1);
                         mma_tf32(acc[r][j], al[r][0], al[r][1], al[r][2], al[r][3], b0, b1);
+                        mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], bl0, bl1);
+                        mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
                     }
+                } else {
+                    const uint32_t b0 = __float_as_uint(w0), b1 = __float_as_uint(w1);     // pre-rounded on the host
+#pragma unroll
+                    for (int r = 0; r < MT; ++r) mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
                 }
             }
-        }
-        if constexpr (!Cfg::WALL) {
-            cp_async_wait_all();
-            __syncthreads();
         }
     }
 
@@ -298,26 +323,25 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel,
             float v[2 * NT];
 #pragma unroll
             for (int j = 0; j < NT; ++j) { v[2 * j] = acc[r][j][2 * h]; v[2 * j + 1] = acc[r][j][2 * h + 1]; }
-            epi.template row<NT>(n, oy, ox0 + g + 8 * h, cb * NB, t, v);
+            epi.template row<NT>(n, oy, ox0 + g + 8 * h, cb * NB, t, v, variant);
         }
     }
 }
 
 template <class Cfg, class In, class Epi>
 int launch_mma_conv(const char* name, const In& in, const Epi& epi, const MmaWeightSel& wsel,
-                    const TapTable& taps, int N, int cout_total, int Hout, int Wout, int ncb, cudaStream_t st) {
-    for (int i = 0; i < 3; ++i)
-        IMVS_REQUIRE(wsel.hi[i] && (Cfg::PASSES == 1 || wsel.lo[i]), "%s: null weights", name);
+                    const TapTables& tabs, int N, int cout_total, int Hout, int Wout, int ncb, cudaStream_t st) {
+    for (int i = 0; i < 3; ++i) IMVS_REQUIRE(wsel.w[i], "%s: null weights", name);
     IMVS_REQUIRE(cout_total % 4 == 0 && ncb * Cfg::NB <= cout_total, "%s: cout_total=%d must be a multiple of 4 and >= %d", name,
                  cout_total, ncb * Cfg::NB);
-    const size_t smem = Cfg::smem_bytes(taps);
-    IMVS_REQUIRE(smem <= 200 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
+    const size_t smem = Cfg::smem_bytes(tabs);
+    IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
     auto kern = mma_conv_kernel<Cfg, In, Epi>;
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
-    dim3 grid(cdiv(Wout, 16), cdiv(Hout, Cfg::TH), N * ncb);
+    dim3 grid(cdiv(Wout, 16), cdiv(Hout, Cfg::TH), N * ncb * tabs.count);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
-    kern<<<grid, Cfg::THREADS, smem, st>>>(in, epi, wsel, taps, cout_total, Hout, Wout, ncb);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(in, epi, wsel, tabs, cout_total, Hout, Wout, ncb);
     count_launch();
     IMVS_LAUNCH_CHECK(name);
     return 0;
@@ -325,13 +349,24 @@ int launch_mma_conv(const char* name, const In& in, const Epi& epi, const MmaWei
 
 int conv_passes();       // process-wide precision switch (imvs_set_conv_passes), defined in warp.cu
 
+struct WSets {           // host-side: up to three packed weights + the slice -> set mapping
+    imvs_wpair w[3];
+    int period, split1, split2;
+    static WSets single(imvs_wpair p) { return WSets{{p, p, p}, 1, 1, 1}; }
+};
+
 // precision dispatch: one call site, both instantiations
 template <int CINP, int NB, int MT, int WARPS, int STRIDE, bool WALL, class In, class Epi>
-int mma_conv(const char* name, const In& in, const Epi& epi, const MmaWeightSel& wsel, const TapTable& taps, int N,
+int mma_conv(const char* name, const In& in, const Epi& epi, const WSets& ws, const TapTables& tabs, int N,
              int cout_total, int Hout, int Wout, int ncb, cudaStream_t st) {
-    if (conv_passes() == 3)
-        return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 3, WALL>>(name, in, epi, wsel, taps, N, cout_total, Hout, Wout, ncb, st);
-    return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 1, WALL>>(name, in, epi, wsel, taps, N, cout_total, Hout, Wout, ncb, st);
+    MmaWeightSel sel;
+    sel.period = ws.period; sel.split1 = ws.split1; sel.split2 = ws.split2;
+    if (conv_passes() == 3) {
+        for (int i = 0; i < 3; ++i) sel.w[i] = ws.w[i].fp32;
+        return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 3, WALL>>(name, in, epi, sel, tabs, N, cout_total, Hout, Wout, ncb, st);
+    }
+    for (int i = 0; i < 3; ++i) sel.w[i] = ws.w[i].tf32;
+    return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 1, WALL>>(name, in, epi, sel, tabs, N, cout_total, Hout, Wout, ncb, st);
 }
 
 // ---- common epilogues (NHWC outputs) --------------------------------------------------------------
@@ -344,7 +379,7 @@ struct EpiNHWC {
     int Cvalid;              // couts actually produced (<= C)
     int relu;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
         if (oy >= H || ox >= W) return;
         const size_t base = (((size_t)n * H + oy) * W + ox) * C;
 #pragma unroll
@@ -361,15 +396,16 @@ struct EpiNHWC {
     }
 };
 
-// transposed-conv parity pass (see make_taps_tconv): grid position (oy, ox) -> output (2*oy + a, 2*ox + b),
-// plus the U-Net skip connection (itermvs.py:374-377)
+// transposed-conv parity variant v = 2a + b (see tconv_tables): grid position (oy, ox) -> output
+// (2*oy + a, 2*ox + b), plus the U-Net skip connection (itermvs.py:374-377)
 struct EpiTconvNHWC {
     float* out;
     const float* skip;
-    int Hin, Win, C, a, b;
+    int Hin, Win, C;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int variant) const {
         if (oy >= Hin || ox >= Win) return;
+        const int a = variant >> 1, b = variant & 1;
         const size_t base = (((size_t)n * 2 * Hin + 2 * oy + a) * (2 * Win) + 2 * ox + b) * C;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {

@@ -18,7 +18,7 @@ struct EpiGruZR {
     float* rh;           // [N][H][W][32]
     int H, W;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
         if (oy >= H || ox >= W) return;
         const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
 #pragma unroll
@@ -41,7 +41,7 @@ struct EpiGruQ {
     float* h;            // updated in place
     int H, W;
     template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT]) const {
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
         if (oy >= H || ox >= W) return;
         const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
 #pragma unroll
@@ -262,11 +262,11 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
     const size_t n = (size_t)B * 32 * H * W;
     float* z = scratch;
     float* rh = scratch + n;
-    const TapTable taps = make_taps_conv(3, 1, 2, 8);
+    const TapTables taps = conv_tables(3, 1, 2, 8);
     IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.zr", InNHWC2{h, x, H, W, 32, IMVS_XCH}, EpiGruZR{w->gru_zr_b, h, z, rh, H, W},
-                                               MmaWeightSel::single(w->gru_zr), taps, B, 64, H, W, 2, st)));
+                                               WSets::single(w->gru_zr), taps, B, 64, H, W, 2, st)));
     IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.q", InNHWC2{rh, x, H, W, 32, IMVS_XCH}, EpiGruQ{w->gru_q_b, z, h, H, W},
-                                               MmaWeightSel::single(w->gru_q), taps, B, 32, H, W, 1, st)));
+                                               WSets::single(w->gru_q), taps, B, 32, H, W, 1, st)));
     return 0;
 }
 
@@ -285,7 +285,7 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     // stacked weight [9][32][64]: channel block 0 = depth_head.0, block 1 = confidence_head.0; the
     // confidence block only runs when a confidence output is requested (itermvs.py:196-199)
     IMVS_TRY((mma_conv<32, 32, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), EpiNHWC{t, nullptr, nullptr, H, W, 64, 64, 1},
-                                               MmaWeightSel::single(w->head_conv0), make_taps_conv(3, 1, 2, 8), B, 64, H, W,
+                                               WSets::single(w->head_conv0), conv_tables(3, 1, 2, 8), B, 64, H, W,
                                                want_conf ? 2 : 1, st)));
     HeadParams prm;
     prm.t = t;

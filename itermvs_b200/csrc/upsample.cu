@@ -122,8 +122,8 @@ extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea
     IMVS_REQUIRE(nd_pixel_stride >= 1, "upsample_outputs: nd_pixel_stride must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
     IMVS_TRY((mma_conv<32, 64, 2, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride),
-                                               EpiNHWC{scratch, nullptr, nullptr, H2, W2, 64, 64, 1}, MmaWeightSel::single(w->ups_conv0),
-                                               make_taps_conv(3, 1, 1, 8), B, 64, H2, W2, 1, st)));
+                                               EpiNHWC{scratch, nullptr, nullptr, H2, W2, 64, 64, 1}, WSets::single(w->ups_conv0),
+                                               conv_tables(3, 1, 1, 8), B, 64, H2, W2, 1, st)));
     UpsParams prm;
     prm.t = scratch; prm.fc = w->ups_fc; prm.nd = nd; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.depth_up = depth_up;
