@@ -83,8 +83,8 @@ typedef struct imvs_weights {
     const float* gru_q_b;          /* [32] */
     /* update.depth_head.0 | update.confidence_head.0 stacked on Cout (itermvs.py:139-151) */
     imvs_wpair head_conv0;         /* [9][32][64] : cout 0..31 depth head, 32..63 confidence head */
-    const float* head_fc1;         /* depth_head.2.weight  [32][64]  (fp32, FFMA epilogue kernel) */
-    const float* head_fc2;         /* depth_head.4.weight  [64][256] */
+    imvs_wpair head_fc1;           /* depth_head.2.weight  [1][32][64]  */
+    imvs_wpair head_fc2;           /* depth_head.4.weight  [1][64][256] */
     const float* head_fc2_b;       /* depth_head.4.bias    [256] */
     const float* conf_fc;          /* confidence_head.2.weight [32] */
     const float* conf_fc_b;        /* confidence_head.2.bias [1] */
@@ -171,7 +171,7 @@ int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, float* scratc
  *   probability   [B][256][H][W] (the reference's layout) or NULL (training needs it, itermvs.py:282,302)
  *   conf / conf_logit [B][H][W] or NULL (sigmoid / raw)
  *   depth_out     [B][H][W] or NULL: depth_unnormalization of nd_out (module.py:148-152)
- * scratch: B*64*H*W floats. */
+ * scratch: B*384*H*W floats (conv output 64 + hidden 64 + logits 256 per pixel). */
 int imvs_depth_head(const imvs_weights* w, const float* hidden, float* nd_out, size_t nd_batch_stride,
                     size_t nd_pixel_stride, float* probability, float* conf, float* conf_logit, float* depth_out,
                     const float* depth_min, const float* depth_max, float* scratch,

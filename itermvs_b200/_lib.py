@@ -34,7 +34,7 @@ class Weights(C.Structure):
     _fields_ = [("pvw_conv0", WPair), ("pvw_conv1", vp), ("pvw_conv1_b", vp),
                 ("corrnet", CorrNetWeights * 3),
                 ("gru_zr", WPair), ("gru_zr_b", vp), ("gru_q", WPair), ("gru_q_b", vp),
-                ("head_conv0", WPair), ("head_fc1", vp), ("head_fc2", vp), ("head_fc2_b", vp),
+                ("head_conv0", WPair), ("head_fc1", WPair), ("head_fc2", WPair), ("head_fc2_b", vp),
                 ("conf_fc", vp), ("conf_fc_b", vp),
                 ("hinit_conv0", WPair), ("hinit_fc", WPair), ("hinit_fc_b", vp),
                 ("ups_conv0", WPair), ("ups_fc", vp)]

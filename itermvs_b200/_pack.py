@@ -112,8 +112,8 @@ def fill_update(h: _Holder, s: _lib.Weights, sd, prefix, dev) -> None:
     g = lambda k: sd[prefix + k].to(dev)
     fill_gru(h, s, sd, prefix + "gru.", dev)
     s.head_conv0 = h.pair(pack_mma_conv(torch.cat([g("depth_head.0.weight"), g("confidence_head.0.weight")], 0)))
-    s.head_fc1 = h.ptr(pack_fc(g("depth_head.2.weight")))
-    s.head_fc2 = h.ptr(pack_fc(g("depth_head.4.weight")))
+    s.head_fc1 = h.pair(pack_mma_conv(g("depth_head.2.weight")))
+    s.head_fc2 = h.pair(pack_mma_conv(g("depth_head.4.weight")))
     s.head_fc2_b = h.ptr(_vec(g("depth_head.4.bias")))
     s.conf_fc = h.ptr(_vec(g("confidence_head.2.weight")))
     s.conf_fc_b = h.ptr(_vec(g("confidence_head.2.bias")))

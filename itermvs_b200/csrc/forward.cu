@@ -40,7 +40,7 @@ static Workspace carve(const imvs_problem& pb, float* base) {
     w.xbuf = at(B * IMVS_XCH * P2);
     w.agg_iter = at(B * IMVS_ITER_SLICES * P2 * 8);
     w.gru_scratch = at(B * 64 * P2);
-    w.head_scratch = at(B * 64 * P2);
+    w.head_scratch = at(B * 384 * P2);
     w.ups_scratch = at(B * 64 * P2);
     w.conf_buf = at(B * P2);
     w.total_floats = c;
@@ -69,7 +69,7 @@ extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
 
 extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     if (check_problem(pb) != 0) return -1;
-    return 22 + 11 * pb->iterations;
+    return 24 + 13 * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,

@@ -33,40 +33,67 @@ __device__ __forceinline__ void load_group(const float* __restrict__ p, float (&
     }
 }
 
-// bilinear sample of one tap position for this lane's channel group, then dot with the reference
-// feature group: returns mean_c( warped_c * ref_c )  (itermvs.py:50-51)
+// Sampling parameters of one (pixel, hypothesis, view), computed by the owner lane and broadcast:
+// clamped top-left tap offset, +1 steps (0 when clamped at the border) and the four bilinear weights
+// with the zero-padding of grid_sample folded in (weight 0 for taps outside the map), so that all
+// taps can be loaded unconditionally from in-bounds addresses -- no branches, loads issue back to back.
+struct TapSet {
+    int o00;        // (y0c * Wf + x0c)
+    int flags;      // bit0: x step (0/1), bit1: y step (0/1)
+    float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ TapSet make_tapset(const Tap& tp, int Wf, int Hf) {
+    TapSet ts;
+    const int x0c = min(max(tp.x0, 0), Wf - 1), x1c = min(max(tp.x0 + 1, 0), Wf - 1);
+    const int y0c = min(max(tp.y0, 0), Hf - 1), y1c = min(max(tp.y0 + 1, 0), Hf - 1);
+    ts.o00 = y0c * Wf + x0c;
+    ts.flags = (x1c - x0c) | ((y1c - y0c) << 1);
+    const float gx = 1.f - tp.fx, gy = 1.f - tp.fy;
+    ts.w00 = (tp.mask & 1u) ? gx * gy : 0.f;
+    ts.w01 = (tp.mask & 2u) ? tp.fx * gy : 0.f;
+    ts.w10 = (tp.mask & 4u) ? gx * tp.fy : 0.f;
+    ts.w11 = (tp.mask & 8u) ? tp.fx * tp.fy : 0.f;
+    return ts;
+}
+
+__device__ __forceinline__ TapSet shfl_tapset(const TapSet& ts, int src) {
+    TapSet r;
+    r.o00 = __shfl_sync(0xffffffffu, ts.o00, src);
+    r.flags = __shfl_sync(0xffffffffu, ts.flags, src);
+    r.w00 = __shfl_sync(0xffffffffu, ts.w00, src);
+    r.w01 = __shfl_sync(0xffffffffu, ts.w01, src);
+    r.w10 = __shfl_sync(0xffffffffu, ts.w10, src);
+    r.w11 = __shfl_sync(0xffffffffu, ts.w11, src);
+    return r;
+}
+
+// the four taps of this lane's channel group (issued back to back), then interpolate and dot with
+// the reference feature group: mean_c( warped_c * ref_c )  (itermvs.py:50-51)
 template <int CPG>
-__device__ __forceinline__ float sample_dot(const float* __restrict__ fea_view_g, int C, int Wf, int i00,
-                                            float fx, float fy, unsigned mask, const float (&ref)[CPG]) {
-    float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-    float a[CPG];
-#pragma unroll
-    for (int i = 0; i < CPG; ++i) a[i] = 0.f;
-    const float* p = fea_view_g + (ptrdiff_t)i00 * C;
-    float t[CPG];
-    if (mask & 1u) {
-        load_group<CPG>(p, t);
-#pragma unroll
-        for (int i = 0; i < CPG; ++i) a[i] = t[i] * w00;
-    }
-    if (mask & 2u) {
-        load_group<CPG>(p + C, t);
-#pragma unroll
-        for (int i = 0; i < CPG; ++i) a[i] = fmaf(t[i], w01, a[i]);
-    }
-    if (mask & 4u) {
-        load_group<CPG>(p + (ptrdiff_t)Wf * C, t);
-#pragma unroll
-        for (int i = 0; i < CPG; ++i) a[i] = fmaf(t[i], w10, a[i]);
-    }
-    if (mask & 8u) {
-        load_group<CPG>(p + (ptrdiff_t)(Wf + 1) * C, t);
-#pragma unroll
-        for (int i = 0; i < CPG; ++i) a[i] = fmaf(t[i], w11, a[i]);
-    }
+struct TapLoads { float t00[CPG], t01[CPG], t10[CPG], t11[CPG]; };
+
+template <int CPG>
+__device__ __forceinline__ void issue_taps(TapLoads<CPG>& L, const float* __restrict__ fea_view_g, int C, int Wf, const TapSet& ts) {
+    const float* p00 = fea_view_g + (ptrdiff_t)ts.o00 * C;
+    const int dx = (ts.flags & 1) * C, dy = ((ts.flags >> 1) & 1) * Wf * C;
+    load_group<CPG>(p00, L.t00);
+    load_group<CPG>(p00 + dx, L.t01);
+    load_group<CPG>(p00 + dy, L.t10);
+    load_group<CPG>(p00 + dy + dx, L.t11);
+}
+
+template <int CPG>
+__device__ __forceinline__ float finish_taps(const TapLoads<CPG>& L, const TapSet& ts, const float (&ref)[CPG]) {
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < CPG; ++i) dot = fmaf(a[i], ref[i], dot);
+    for (int i = 0; i < CPG; ++i) {
+        float a = L.t00[i] * ts.w00;
+        a = fmaf(L.t01[i], ts.w01, a);
+        a = fmaf(L.t10[i], ts.w10, a);
+        a = fmaf(L.t11[i], ts.w11, a);
+        dot = fmaf(a, ref[i], dot);
+    }
     return dot / (float)CPG;
 }
 
@@ -113,18 +140,23 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
                 tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
                 if (v0 + g < S && dvalid)
                     tp = project_tap(sP + (v0 + g) * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
-                int i00 = tp.y0 * W3 + tp.x0;
+                const TapSet mine = make_tapset(tp, W3, H3);
                 const int nv = min(8, S - v0);
-                for (int j = 0; j < nv; ++j) {
-                    const int src = (lane & 24) | j;
-                    const int i00j = __shfl_sync(0xffffffffu, i00, src);
-                    const float fxj = __shfl_sync(0xffffffffu, tp.fx, src);
-                    const float fyj = __shfl_sync(0xffffffffu, tp.fy, src);
-                    const unsigned mj = __shfl_sync(0xffffffffu, tp.mask, src);
-                    const int v = v0 + j;
-                    const float* fv = fea3 + (size_t)(b * V + 1 + v) * P3 * C + g * CPG;
-                    const float c = sample_dot<CPG>(fv, C, W3, i00j, fxj, fyj, mj, ref);
-                    if (dvalid) corr[((((size_t)b * S + v) * D + d) * P3 + p) * 8 + g] = c;
+                for (int j0 = 0; j0 < nv; j0 += 2) {          // two views per batch: 8 x 3 float2 loads in flight
+                    TapSet ts[2];
+                    TapLoads<CPG> L[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        ts[u] = shfl_tapset(mine, (lane & 24) | min(j0 + u, 7));
+                        const int v = min(v0 + j0 + u, S - 1);
+                        issue_taps<CPG>(L[u], fea3 + (size_t)(b * V + 1 + v) * P3 * C + g * CPG, C, W3, ts[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int v = v0 + j0 + u;
+                        const float c = finish_taps<CPG>(L[u], ts[u], ref);
+                        if (dvalid && v < S) corr[((((size_t)b * S + v) * D + d) * P3 + p) * 8 + g] = c;
+                    }
                 }
             }
         }
@@ -214,6 +246,7 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
                 ref[i] = (1.f - lh) * ((1.f - lw) * a[i] + lw * bq[i]) + lh * ((1.f - lw) * c[i] + lw * d[i]);
         }
         float num = 0.f, wsum = 1e-5f;                          // itermvs.py:88-89
+        constexpr int VG = CPG == 2 ? 4 : 2;                    // views per load batch (bounded by registers)
         for (int v0 = 0; v0 < S; v0 += 8) {
             Tap tp;
             tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
@@ -222,27 +255,35 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
                 tp = project_tap(sP + (v0 + g) * 12, (float)xc * sx, (float)y * sy, depth, (float)W2, (float)H2, Wf, Hf);
                 wv = ldg(prm.vw2 + ((size_t)b * S + v0 + g) * P2 + p);
             }
-            const int i00 = tp.y0 * Wf + tp.x0;
+            const TapSet mine = make_tapset(tp, Wf, Hf);
             const int nv = min(8, S - v0);
-#pragma unroll 4
-            for (int j = 0; j < nv; ++j) {
-                const int src = (lane & 24) | j;
-                const int i00j = __shfl_sync(0xffffffffu, i00, src);
-                const float fxj = __shfl_sync(0xffffffffu, tp.fx, src);
-                const float fyj = __shfl_sync(0xffffffffu, tp.fy, src);
-                const unsigned mj = __shfl_sync(0xffffffffu, tp.mask, src);
-                const float wj = __shfl_sync(0xffffffffu, wv, src);
-                const float* fv = fea + (size_t)(b * V + 1 + v0 + j) * Hf * Wf * C + g * CPG;
-                const float c = sample_dot<CPG>(fv, C, Wf, i00j, fxj, fyj, mj, ref);
-                num = fmaf(c, wj, num);                          // itermvs.py:114
-                wsum += wj;                                      // itermvs.py:115
+            for (int j0 = 0; j0 < nv; j0 += VG) {
+                TapSet ts[VG];
+                TapLoads<CPG> L[VG];
+                float wj[VG];
+#pragma unroll
+                for (int u = 0; u < VG; ++u) {
+                    const int src = (lane & 24) | min(j0 + u, 7);
+                    ts[u] = shfl_tapset(mine, src);
+                    wj[u] = __shfl_sync(0xffffffffu, wv, src);          // 0 for views >= S
+                    const int v = min(v0 + j0 + u, S - 1);
+                    issue_taps<CPG>(L[u], fea + (size_t)(b * V + 1 + v) * Hf * Wf * C + g * CPG, C, Wf, ts[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < VG; ++u) {
+                    const float c = finish_taps<CPG>(L[u], ts[u], ref);
+                    if (v0 + j0 + u < S) {
+                        num = fmaf(c, wj[u], num);                       // itermvs.py:114
+                        wsum += wj[u];                                   // itermvs.py:115
+                    }
+                }
             }
         }
         if (pvalid) prm.agg[(((size_t)b * IMVS_ITER_SLICES + slice_base + r) * P2 + p) * 8 + g] = num / wsum;
     }
 }
 
-__global__ void __launch_bounds__(256) warpcorr_iter_kernel(const IterParams prm) {
+__global__ void __launch_bounds__(256, 3) warpcorr_iter_kernel(const IterParams prm) {
     __shared__ float sP[IMVS_MAX_VIEWS * 12];
     const int b = blockIdx.z / 3, lvl = blockIdx.z % 3;
     const int S = prm.V - 1;

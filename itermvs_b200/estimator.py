@@ -329,7 +329,7 @@ class Update(nn.Module):
         prob = torch.empty(b, self.out_num_samples, h, w, device=dev) if self._want_prob() else None
         conf = torch.empty(b, 1, h, w, device=dev) if want_conf else None
         conf0 = torch.empty(b, 1, h, w, device=dev) if want_conf else None
-        scratch = torch.empty(b * 64 * h * w, device=dev)
+        scratch = torch.empty(b * 384 * h * w, device=dev)
         _lib.check(_lib.lib().imvs_depth_head(self._packed(dev).ref, hidden.data_ptr(), nd.data_ptr(), h * w, 1, ops._p(prob),
                                               ops._p(conf), ops._p(conf0), None, None, None, scratch.data_ptr(), b, h, w,
                                               ops._stream()), "depth_head")
