@@ -286,12 +286,11 @@ def main():
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
     clk = clocks.stop()
 
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
-    value = world * args.steps / (total_ms / 1000.0)
-    e2e_value = world * args.steps / (e2e_ms / 1000.0)
+    # replicas: every rank processed `steps` reference views; whole-job rate = all units / slowest rank
+    from itermvs_b200 import replicas
+    value = replicas.aggregate_throughput(args.steps, total_ms, device=dev)
+    e2e_value = replicas.aggregate_throughput(args.steps, e2e_ms, device=dev)
+    total_ms = replicas.max_over_ranks([total_ms], device=dev)[0]
 
     # ---- CPU baseline: oracle port on this box's host cores (rank 0, N=1 only)
     cpu = None
