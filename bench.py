@@ -310,6 +310,27 @@ def main():
                "sample": "3 full forward passes of the workload (median) after a thread-count probe, "
                          "oracle/itermvs_oracle.py on torch CPU fp32"}
 
+    # ---- the same port on THIS GPU through stock ATen/cuDNN ops (proxy for the reference's stock GPU path,
+    #      which cannot travel to the box): eager, cudnn.benchmark as eval.py:21, TF32 convs as torch defaults
+    gpu_stock = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import itermvs_oracle as O
+        torch.backends.cudnn.benchmark = True
+        wd = {k: v.to(dev) for k, v in weights.items()}
+        di = {k: v.to(dev) for k, v in s["imgs"].items()}
+        dp = {k: v.to(dev) for k, v in s["proj_matrices"].items()}
+        run_g = lambda: O.pipeline_forward(wd, di, dp, d_dmin, d_dmax, iteration=ITERS, num_sample=D_HYP)
+        for _ in range(3):
+            run_g()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            run_g()
+        torch.cuda.synchronize()
+        gpu_stock = {"value": 10 / (time.perf_counter() - t0), "unit": "refs/s",
+                     "what": "oracle port executed on this GPU with stock ATen/cuDNN ops (eager, cudnn.benchmark, default TF32): "
+                             "proxy for the reference's stock PyTorch path, wall clock over 10 forwards"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -353,6 +374,8 @@ def main():
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if gpu_stock is not None:
+        line["gpu_stock_port"] = gpu_stock
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

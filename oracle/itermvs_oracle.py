@@ -51,7 +51,7 @@ def _lin_up_axis(x: Tensor, dim: int, factor: int) -> Tensor:
     """1-D linear upsampling by an integer factor, align_corners=False:
     src = (dst + 0.5) / factor - 0.5, clamped below at 0; i1 = min(i0 + 1, n - 1)."""
     n = x.shape[dim]
-    dst = torch.arange(n * factor, dtype=torch.float32)
+    dst = torch.arange(n * factor, dtype=torch.float32, device=x.device)
     src = ((dst + 0.5) / factor - 0.5).clamp_(min=0.0)
     i0 = src.floor().to(torch.long)
     i1 = (i0 + 1).clamp_(max=n - 1)
@@ -93,13 +93,13 @@ def depth_normalization(depth: Tensor, inv_min: Tensor, inv_max: Tensor) -> Tens
 def initial_depth_samples(inv_min: Tensor, inv_max: Tensor, num: int, h: int, w: int) -> Tensor:
     """itermvs.py:11-19. inv_* are [B,1,1,1]; returns [B,num,h,w]."""
     b = inv_min.shape[0]
-    idx = torch.arange(num, dtype=torch.float32).view(1, num, 1, 1).repeat(b, 1, h, w) / (num - 1)
+    idx = torch.arange(num, dtype=torch.float32, device=inv_min.device).view(1, num, 1, 1).repeat(b, 1, h, w) / (num - 1)
     return 1.0 / (inv_max + idx * (inv_min - inv_max))
 
 
 def iteration_depth_samples(nd: Tensor, level: int, inv_min: Tensor, inv_max: Tensor) -> Tensor:
     """itermvs.py:289-293."""
-    off = torch.tensor(CORR_INTERVAL[level], dtype=torch.float32).view(1, -1, 1, 1)
+    off = torch.tensor(CORR_INTERVAL[level], dtype=torch.float32, device=nd.device).view(1, -1, 1, 1)
     s = (nd + off * INTERVAL_SCALE).clamp(min=0, max=1)
     return depth_unnormalization(s, inv_min, inv_max)
 
@@ -117,7 +117,8 @@ def warp_sample_positions(proj: Tensor, depth_samples: Tensor, h1: int, w1: int)
     b, d, h, w = depth_samples.shape
     rot = proj[:, :3, :3]
     trans = proj[:, :3, 3:4]
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
+    dev = depth_samples.device
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev), torch.arange(w, dtype=torch.float32, device=dev),
                             indexing="ij")
     xs = xs.reshape(-1) * (w1 / w)                      # module.py:95-96 (no half-pixel offset)
     ys = ys.reshape(-1) * (h1 / h)
@@ -151,7 +152,7 @@ def differentiable_warping(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, 
     fx = ix - x0
     fy = iy - y0
     flat = src_fea.reshape(b, c, h1 * w1)
-    out = torch.zeros(b, c, d * h * w, dtype=src_fea.dtype)
+    out = torch.zeros(b, c, d * h * w, dtype=src_fea.dtype, device=src_fea.device)
     for dy, dx, wgt in ((0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)),
                         (1, 0, (1 - fx) * fy), (1, 1, fx * fy)):
         xx = x0 + dx
@@ -219,7 +220,7 @@ def evaluation_init(wts: Weights, ref_fea3: Tensor, src_feas3: Sequence[Tensor],
     corr = corr_net(wts, agg, ev + "corr_conv1.2.")
     d = depth_sample.shape[1]
     prob = torch.softmax(corr, dim=1)
-    idx = (torch.arange(d, dtype=torch.float32).view(1, d, 1, 1) * prob).sum(dim=1, keepdim=True)
+    idx = (torch.arange(d, dtype=torch.float32, device=corr.device).view(1, d, 1, 1) * prob).sum(dim=1, keepdim=True)
     depth = bilinear_up(depth_unnormalization(idx / (d - 1.0), inv_min, inv_max), 2)
     return {"view_weights": torch.cat(vws, dim=1), "corr": corr, "depth": depth, "aggregated": agg,
             "per_view_corr": per_corr, "per_view_weight": per_vw}
