@@ -189,6 +189,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_conv_passes(args.passes)
 
