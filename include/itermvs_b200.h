@@ -220,9 +220,10 @@ int imvs_forward_launch_count(const imvs_problem* pb);
  * imgs [N][3][H][W] (N = B*V views) -> channels-last pyramids fea1 [N][H/2][W/2][16],
  * fea2 [N][H/4][W/4][32], fea3 [N][H/8][W/8][48].
  * ---------------------------------------------------------------------------------------- */
-#define IMVS_FNET_CONVS 22
+#define IMVS_FNET_CONVS 24
 typedef struct imvs_featurenet_weights {
-    imvs_wpair w[IMVS_FNET_CONVS];      /* order documented in itermvs_b200/_pack.py:FNET_LAYERS */
+    imvs_wpair w[IMVS_FNET_CONVS];      /* order documented in itermvs_b200/_pack.py:FNET_LAYERS; slots 21..23 =
+                                           [layerK.0.conv1 | layerK.0.downsample] stacked on Cout, K = 1..3 */
     const float* b[IMVS_FNET_CONVS];    /* per-layer bias (folded BN shift or conv bias) */
 } imvs_featurenet_weights;
 size_t imvs_featurenet_workspace_bytes(int N, int H, int W);

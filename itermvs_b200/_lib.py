@@ -19,7 +19,7 @@ vp = C.c_void_p
 ci = C.c_int
 sz = C.c_size_t
 ABI_VERSION = 2
-FNET_CONVS = 22
+FNET_CONVS = 24
 
 
 class WPair(C.Structure):

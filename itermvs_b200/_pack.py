@@ -173,9 +173,12 @@ class PackedFeatureNet(_Holder):
                 w, b = sd[prefix + "weight"].float(), sd[prefix + "bias"].float()
             s.w[i] = self.pair(pack_mma_conv(w))
             s.b[i] = self.ptr(_vec(b))
-        # unused trailing slot: keep pointers valid
-        s.w[len(FNET_LAYERS)] = s.w[0]
-        s.b[len(FNET_LAYERS)] = s.b[0]
+        # slots 21..23: [layerK.0.conv1 | layerK.0.downsample] stacked on Cout (one GEMM over the shared input)
+        for k in (1, 2, 3):
+            w1, b1 = fold_bn(sd, f"layer{k}.0.conv1.")
+            w2, b2 = fold_bn(sd, f"layer{k}.0.downsample.")
+            s.w[20 + k] = self.pair(pack_mma_conv(torch.cat([w1, w2], 0)))
+            s.b[20 + k] = self.ptr(_vec(torch.cat([b1, b2], 0)))
         self.struct = s
 
     @property

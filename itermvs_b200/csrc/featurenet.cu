@@ -38,6 +38,27 @@ struct EpiAddUp2 {
     }
 };
 
+// block-0 of a residual stage: conv1 (ReLU) and downsample (no ReLU) read the same input with the same
+// stride-2 stencil -> one implicit GEMM over the stacked output channels [conv1 | downsample]
+struct EpiSplit2 {
+    float* out_relu;         // couts [0, CO)      -> relu(v + bias)
+    float* out_lin;          // couts [CO, 2*CO)   -> v + bias
+    const float* bias;       // [2*CO]
+    int H, W, CO;
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
+        if (oy >= H || ox >= W) return;
+        const size_t base = (((size_t)n * H + oy) * W + ox) * CO;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int co = co0 + 8 * j + 2 * t;
+            const float a = v[2 * j] + ldg(bias + co), b = v[2 * j + 1] + ldg(bias + co + 1);
+            if (co < CO) *reinterpret_cast<float2*>(out_relu + base + co) = make_float2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+            else *reinterpret_cast<float2*>(out_lin + base + co - CO) = make_float2(a, b);
+        }
+    }
+};
+
 struct FnetBuffers {
     float *a0, *l1[4], *l2[4], *l3[4], *intra2, *intra1;
     size_t total;
@@ -64,11 +85,11 @@ static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, fl
                      cudaStream_t st) {
     const int H = Hin / 2, W = Win / 2;
     const TapTables s2 = conv_tables(3, 2, 1, 8), s1 = conv_tables(3, 1, 1, 8);
-    // block 0: conv1 (stride 2, relu), downsample (stride 2), conv2 + downsample -> relu
-    IMVS_TRY((mma_conv<CI, CO, 2, 4, 2, WALL_A>("fnet.block0.conv1", in_nhwc(x, Hin, Win, CI), EpiNHWC{buf[0], w->b[L], nullptr, H, W, CO, CO, 1},
-                                                WSets::single(w->w[L]), s2, N, CO, H, W, 1, st)));
-    IMVS_TRY((mma_conv<CI, CO, 2, 4, 2, WALL_A>("fnet.block0.downsample", in_nhwc(x, Hin, Win, CI), EpiNHWC{buf[1], w->b[L + 2], nullptr, H, W, CO, CO, 0},
-                                                WSets::single(w->w[L + 2]), s2, N, CO, H, W, 1, st)));
+    // block 0: [conv1 (stride 2, relu) | downsample (stride 2)] as one GEMM, then conv2 + downsample -> relu
+    const int LS = 21 + (L - 1) / 5;           // stacked [conv1 | downsample] weights of this stage
+    IMVS_TRY((mma_conv<CI, 2 * CO, 2, 4, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
+                                                    EpiSplit2{buf[0], buf[1], w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO,
+                                                    H, W, 1, st)));
     IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
                                                 WSets::single(w->w[L + 1]), s1, N, CO, H, W, 1, st)));
     // block 1: conv1 relu, conv2 + x -> relu
@@ -88,7 +109,7 @@ extern "C" size_t imvs_featurenet_workspace_bytes(int N, int H, int W) {
     return fnet_carve(nullptr, N, H, W).total * sizeof(float);
 }
 
-extern "C" int imvs_featurenet_launch_count(void) { return 21; }
+extern "C" int imvs_featurenet_launch_count(void) { return 18; }
 
 extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs, float* fea1, float* fea2, float* fea3,
                                        void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
@@ -106,7 +127,7 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                             WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
-    IMVS_TRY((res_stage<16, 32, true, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));   // layer2 -> l2[3]  [H/4][W/4][32]
+    IMVS_TRY((res_stage<16, 32, false, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));   // layer2 -> l2[3]  [H/4][W/4][32]
     IMVS_TRY((res_stage<32, 48, false, false>(w, 11, b.l2[3], b.l3, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48]
     // output3 (net.py:59)
     IMVS_TRY((mma_conv<48, 48, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), EpiNHWC{fea3, w->b[16], nullptr, H3, W3, 48, 48, 0},
