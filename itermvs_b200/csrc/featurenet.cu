@@ -127,7 +127,7 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                             WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
-    IMVS_TRY((res_stage<16, 32, false, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));   // layer2 -> l2[3]  [H/4][W/4][32]
+    IMVS_TRY((res_stage<16, 32, true, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));   // layer2 -> l2[3]  [H/4][W/4][32]
     IMVS_TRY((res_stage<32, 48, false, false>(w, 11, b.l2[3], b.l3, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48]
     // output3 (net.py:59)
     IMVS_TRY((mma_conv<48, 48, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), EpiNHWC{fea3, w->b[16], nullptr, H3, W3, 48, 48, 0},

@@ -328,208 +328,26 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
     }
 }
 
-// ---- persistent variant for small layers (all weight slices resident) ------------------------------
-// grid = a few CTAs per SM; each CTA walks tile tasks (task -> image n, cout block, variant, tile) with a
-// grid stride, keeps the layer's weights in shared memory and double-buffers the input tile: the
-// cp.async of tile k+1 overlaps the MMAs + epilogue of tile k, one barrier per tile.  (One-shot CTAs
-// spent most of their life waiting for a 10-15 KB tile and re-fetching the same weights 3 000 times.)
-template <class Cfg, class In, class Epi>
-__global__ void __launch_bounds__(Cfg::THREADS)
-mma_conv_persistent_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTables tabs, int cout_total,
-                           int Hout, int Wout, int ncb, int N, int nslices) {
-    constexpr int CP = Cfg::CP, NP = Cfg::NP, CINP = Cfg::CINP, NB = Cfg::NB, MT = Cfg::MT, NT = Cfg::NT;
-    extern __shared__ __align__(16) float smem[];
-    int tile_floats = 0;
-    for (int v = 0; v < tabs.count; ++v) tile_floats = max(tile_floats, tabs.t[v].IH * tabs.t[v].IW * CP);
-    float* sTile[2] = {smem, smem + tile_floats};
-    float* sW = smem + 2 * tile_floats;                 // [nslices][CINP][NP]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int tiles_x = (Wout + 15) / 16, tiles_y = (Hout + Cfg::TH - 1) / Cfg::TH;
-    const int per_image = tiles_x * tiles_y;
-    const int total = N * ncb * tabs.count * per_image;
-
-    struct Task { int n, cb, variant, oy0, ox0; const float* w; };
-    auto decode = [&](int task) {
-        Task k;
-        const int tile = task % per_image, z = task / per_image;
-        k.variant = z % tabs.count;
-        const int ncbz = z / tabs.count;
-        k.n = ncbz / ncb; k.cb = ncbz % ncb;
-        k.oy0 = (tile / tiles_x) * Cfg::TH; k.ox0 = (tile % tiles_x) * 16;
-        k.w = wsel.pick(k.n);
-        return k;
-    };
-    auto issue_weights = [&](const Task& k) {
-        constexpr int Q = NB / 4;
-        const float* src = k.w + k.cb * NB;
-        for (int i = tid; i < nslices * CINP * Q; i += Cfg::THREADS) {
-            const int row = i / Q, q = i % Q;           // row = slice*CINP + cin
-            cp_async16(sW + row * NP + 4 * q, src + (size_t)row * cout_total + 4 * q, true);
-        }
-    };
-    auto issue_tile = [&](const Task& k, float* dstTile) {
-        const TapTable& taps = tabs.t[k.variant];
-        const int iy0 = k.oy0 * Cfg::STRIDE + taps.dy_min, ix0 = k.ox0 * Cfg::STRIDE + taps.dx_min;
-        constexpr int C4 = CINP / 4;
-        const int tot = taps.IH * taps.IW * C4;
-        for (int i = tid; i < tot; i += Cfg::THREADS) {
-            const int slot = i / C4, c4 = i % C4;
-            const int iy = iy0 + slot / taps.IW, ix = ix0 + slot % taps.IW;
-            if constexpr (In::kAsync) {
-                bool valid;
-                const float* src = in.ptr4(k.n, iy, ix, c4, valid);
-                cp_async16(dstTile + (size_t)slot * CP + 4 * c4, src, valid);
-            } else {
-                *reinterpret_cast<float4*>(dstTile + (size_t)slot * CP + 4 * c4) = in.load4(k.n, iy, ix, c4);
-            }
-        }
-    };
-
-    int task = blockIdx.x;
-    if (task >= total) return;
-    Task cur = decode(task);
-    issue_weights(cur);
-    issue_tile(cur, sTile[0]);
-    cp_async_commit();
-    int buf = 0;
-    for (;;) {
-        cp_async_wait<0>();
-        __syncthreads();                       // tile `cur` + weights landed; previous tile's readers are done
-        const int next = task + gridDim.x;
-        const bool have_next = next < total;
-        Task nxt = cur;
-        bool same_w = false;
-        if (have_next) {
-            nxt = decode(next);
-            same_w = (nxt.w == cur.w) && (nxt.cb == cur.cb);
-            if (same_w) { issue_tile(nxt, sTile[buf ^ 1]); cp_async_commit(); }
-        }
-        {   // ---- MMAs on the current tile
-            const TapTable& taps = tabs.t[cur.variant];
-            const float* sA = sTile[buf];
-            float acc[MT][NT][4];
-#pragma unroll
-            for (int r = 0; r < MT; ++r)
-#pragma unroll
-                for (int j = 0; j < NT; ++j)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[r][j][q] = 0.f;
-            for (int tap = 0; tap < taps.n; ++tap) {
-                const float* wb = sW + taps.widx[tap] * Cfg::WBUF;
-                const int ry = taps.dy[tap] - taps.dy_min, rx = taps.dx[tap] - taps.dx_min;
-                int slot0[MT], slot1[MT];
-#pragma unroll
-                for (int r = 0; r < MT; ++r) {
-                    const int row = (warp * MT + r) * Cfg::STRIDE + ry;
-                    slot0[r] = (row * taps.IW + g * Cfg::STRIDE + rx) * CP;
-                    slot1[r] = (row * taps.IW + (g + 8) * Cfg::STRIDE + rx) * CP;
-                }
-#pragma unroll
-                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-                    const int k0 = ks * 8;
-                    uint32_t a[MT][4], al[MT][4];
-#pragma unroll
-                    for (int r = 0; r < MT; ++r) {
-                        const float f0 = sA[slot0[r] + k0 + t], f1 = sA[slot1[r] + k0 + t];
-                        const float f2 = sA[slot0[r] + k0 + t + 4], f3 = sA[slot1[r] + k0 + t + 4];
-                        if constexpr (Cfg::PASSES == 3) {
-                            split_tf32(f0, a[r][0], al[r][0]); split_tf32(f1, a[r][1], al[r][1]);
-                            split_tf32(f2, a[r][2], al[r][2]); split_tf32(f3, a[r][3], al[r][3]);
-                        } else {
-                            a[r][0] = f2tf32(f0); a[r][1] = f2tf32(f1); a[r][2] = f2tf32(f2); a[r][3] = f2tf32(f3);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        const float w0 = wb[(k0 + t) * NP + 8 * j + g], w1 = wb[(k0 + t + 4) * NP + 8 * j + g];
-                        if constexpr (Cfg::PASSES == 3) {
-                            uint32_t b0, b1, bl0, bl1;
-                            split_tf32(w0, b0, bl0);
-                            split_tf32(w1, b1, bl1);
-#pragma unroll
-                            for (int r = 0; r < MT; ++r) {
-                                mma_tf32(acc[r][j], al[r][0], al[r][1], al[r][2], al[r][3], b0, b1);
-                                mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], bl0, bl1);
-                                mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
-                            }
-                        } else {
-                            const uint32_t b0 = __float_as_uint(w0), b1 = __float_as_uint(w1);
-#pragma unroll
-                            for (int r = 0; r < MT; ++r) mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < MT; ++r) {
-                const int oy = cur.oy0 + warp * MT + r;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[2 * NT];
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) { v[2 * j] = acc[r][j][2 * h]; v[2 * j + 1] = acc[r][j][2 * h + 1]; }
-                    epi.template row<NT>(cur.n, oy, cur.ox0 + g + 8 * h, cur.cb * NB, t, v, cur.variant);
-                }
-            }
-        }
-        if (!have_next) break;
-        if (!same_w) {                          // new weight set: drain, then load weights + tile without overlap
-            __syncthreads();
-            issue_weights(nxt);
-            issue_tile(nxt, sTile[buf ^ 1]);
-            cp_async_commit();
-        }
-        cur = nxt; task = next; buf ^= 1;
-    }
-}
-
 template <class Cfg, class In, class Epi>
 int launch_mma_conv(const char* name, const In& in, const Epi& epi, const MmaWeightSel& wsel,
                     const TapTables& tabs, int N, int cout_total, int Hout, int Wout, int ncb, cudaStream_t st) {
     for (int i = 0; i < 3; ++i) IMVS_REQUIRE(wsel.w[i], "%s: null weights", name);
     IMVS_REQUIRE(cout_total % 4 == 0 && ncb * Cfg::NB <= cout_total, "%s: cout_total=%d must be a multiple of 4 and >= %d", name,
                  cout_total, ncb * Cfg::NB);
-    if constexpr (Cfg::WALL) {
-        int nslices = 0;
-        size_t tile = 0;
-        for (int v = 0; v < tabs.count; ++v) {
-            tile = std::max(tile, (size_t)tabs.t[v].IH * tabs.t[v].IW * Cfg::CP);
-            for (int k = 0; k < tabs.t[v].n; ++k) nslices = std::max(nslices, tabs.t[v].widx[k] + 1);
-        }
-        const size_t smem = sizeof(float) * (2 * tile + (size_t)nslices * Cfg::WBUF);
-        IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
-        auto kern = mma_conv_persistent_kernel<Cfg, In, Epi>;
-        static int smem_ok = 0;
-        IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            IMVS_CUDA(cudaGetDevice(&dev));
-            IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        }
-        const long long total = (long long)N * ncb * tabs.count * cdiv(Wout, 16) * cdiv(Hout, Cfg::TH);
-        IMVS_REQUIRE(total < (1ll << 31), "%s: too many tiles", name);
-        int per_sm = (int)std::min<size_t>(6, (200 * 1024) / smem);
-        per_sm = std::max(1, std::min(per_sm, 1536 / Cfg::THREADS));
-        const int ctas = (int)std::min<long long>(total, (long long)sms * per_sm);
-        kern<<<ctas, Cfg::THREADS, smem, st>>>(in, epi, wsel, tabs, cout_total, Hout, Wout, ncb, N, nslices);
-        count_launch();
-        IMVS_LAUNCH_CHECK(name);
-        return 0;
-    } else {
-        const size_t smem = Cfg::smem_bytes(tabs);
-        IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
-        auto kern = mma_conv_kernel<Cfg, In, Epi>;
-        static int smem_ok = 0;
-        IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
-        dim3 grid(cdiv(Wout, 16), cdiv(Hout, Cfg::TH), N * ncb * tabs.count);
-        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
-        kern<<<grid, Cfg::THREADS, smem, st>>>(in, epi, wsel, tabs, cout_total, Hout, Wout, ncb);
-        count_launch();
-        IMVS_LAUNCH_CHECK(name);
-        return 0;
-    }
+    // (a persistent, tile-double-buffered variant of this kernel for the small layers was measured in round 1
+    //  and was 5% SLOWER end to end: the doubled tile buffer halves the resident warps and these layers are
+    //  issue/latency bound, not load bound -- see profiles/README.md)
+    const size_t smem = Cfg::smem_bytes(tabs);
+    IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
+    auto kern = mma_conv_kernel<Cfg, In, Epi>;
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
+    dim3 grid(cdiv(Wout, 16), cdiv(Hout, Cfg::TH), N * ncb * tabs.count);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(in, epi, wsel, tabs, cout_total, Hout, Wout, ncb);
+    count_launch();
+    IMVS_LAUNCH_CHECK(name);
+    return 0;
 }
 
 int conv_passes();       // process-wide precision switch (imvs_set_conv_passes), defined in warp.cu

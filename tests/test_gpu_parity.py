@@ -362,4 +362,5 @@ def test_config5_stress_shape(dev, dtu_weights):
           f"px>1e-3: {100 * (rel > 1e-3).mean():.4f}%")
     # hidden_init_head.0 is random for D != 32 (no checkpoint exists): flat distributions, isolated arg-max
     # flips as in e2e_d8 -> median-tight, a few percent of pixels may move by a bin
-    assert np.median(rel) < 1e-5 and (rel > 1e-3).mean() < 0.03
+    assert np.median(rel) < 1e-5, (np.median(rel), rel.mean())
+    assert (rel > 1e-3).mean() < 0.03, (rel > 1e-3).mean()
