@@ -53,10 +53,17 @@ long long imvs_launches_total(void);
  * TF32 split (fp32-grade).  Process-wide; default 3. */
 int imvs_set_conv_passes(int passes);
 int imvs_get_conv_passes(void);
+/* tcgen05/TMEM kernels for the 32..64-channel stride-1 convolutions in the 1-pass TF32 mode (default on).
+ * imvs_tcgen05_status() synchronises the device and returns 0, or 1 if a tcgen05 kernel timed out on its
+ * mbarrier (never expected; guards against a hung GPU). */
+int imvs_set_tcgen05(int enabled);
+int imvs_tcgen05_status(void);
 
 typedef struct imvs_wpair {      /* packed conv weight [tap][CinP][CoutP] */
     const float* tf32;           /* values rounded to TF32 (round-to-nearest): operand of the 1-pass mode */
     const float* fp32;           /* plain fp32: the 3-pass mode splits hi/lo in registers */
+    const float* umma;           /* TF32-rounded, tcgen05 K-major canonical order [cout block][tap][CinP/4][NB][4]
+                                    with NB = min(CoutP, 64); may be NULL (then the mma.sync kernels run) */
 } imvs_wpair;
 
 typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */

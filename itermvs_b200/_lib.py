@@ -23,7 +23,7 @@ FNET_CONVS = 24
 
 
 class WPair(C.Structure):
-    _fields_ = [("tf32", vp), ("fp32", vp)]
+    _fields_ = [("tf32", vp), ("fp32", vp), ("umma", vp)]
 
 
 class CorrNetWeights(C.Structure):
@@ -55,6 +55,8 @@ _SIGNATURES = {
     "imvs_launches_total": (C.c_longlong, []),
     "imvs_set_conv_passes": (ci, [ci]),
     "imvs_get_conv_passes": (ci, []),
+    "imvs_set_tcgen05": (ci, [ci]),
+    "imvs_tcgen05_status": (ci, []),
     "imvs_profile_begin": (ci, [ci]),
     "imvs_profile_end": (ci, [vp, vp, ci]),
     "imvs_compose_projections": (ci, [vp, ci, ci, vp, vp, vp]),

@@ -39,13 +39,24 @@ def split_tf32(w: Tensor) -> Tuple[Tensor, Tensor]:
     return round_tf32(w).contiguous(), w.contiguous().clone()
 
 
-def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0) -> Tuple[Tensor, Tensor]:
-    """nn.Conv2d weight [Cout,Cin,kh,kw] -> (hi, lo) each [kh*kw][CinP][CoutP]."""
+def pack_umma(w_tf32: Tensor) -> Tensor:
+    """[tap][CinP][CoutP] (TF32) -> tcgen05 K-major canonical order [cout block][tap][CinP/4][NB][4],
+    NB = min(CoutP, 64): element (n, k) of a tap at (k/4)*NB*16 B + n*16 B + (k%4)*4 B."""
+    taps, cinp, coutp = w_tf32.shape
+    nb = min(coutp, 64)
+    assert coutp % nb == 0 and cinp % 4 == 0
+    x = w_tf32.reshape(taps, cinp // 4, 4, coutp // nb, nb)          # [tap][kc][k4][cb][n]
+    return x.permute(3, 0, 1, 4, 2).contiguous()                     # [cb][tap][kc][n][k4]
+
+
+def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0):
+    """nn.Conv2d weight [Cout,Cin,kh,kw] -> (tf32, fp32, umma): [kh*kw][CinP][CoutP] twice + the tcgen05 order."""
     co, cin, kh, kw = w.shape
     cinp, coutp = cinp or _pad8(cin), coutp or _pad8(co)
     out = torch.zeros(kh * kw, cinp, coutp, device=w.device, dtype=torch.float32)
     out[:, :cin, :co] = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, cin, co)
-    return split_tf32(out)
+    t, f = split_tf32(out)
+    return t, f, pack_umma(t)
 
 
 def pack_mma_tconv(w: Tensor) -> Tuple[Tensor, Tensor]:
@@ -53,7 +64,8 @@ def pack_mma_tconv(w: Tensor) -> Tuple[Tensor, Tensor]:
     cin, co, kh, kw = w.shape
     out = torch.zeros(kh * kw, _pad8(cin), _pad8(co), device=w.device, dtype=torch.float32)
     out[:, :cin, :co] = w.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cin, co)
-    return split_tf32(out)
+    t, f = split_tf32(out)
+    return t, f, pack_umma(t)
 
 
 def pack_fc(w: Tensor) -> Tensor:
@@ -74,7 +86,7 @@ class _Holder:
 
     def pair(self, hl) -> _lib.WPair:
         self.keep.extend(hl)
-        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr())
+        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if len(hl) > 2 else None)
 
     def ptr(self, t: Tensor) -> int:
         self.keep.append(t)

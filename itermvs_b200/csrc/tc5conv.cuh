@@ -1,0 +1,288 @@
+// tcgen05 (5th-generation tensor core, TMEM accumulator) implicit-GEMM convolution, TF32.
+//
+// Used for the stride-1 32..64-channel convolutions when conv_passes == 1 (single-pass TF32).
+//
+//   * a CTA computes ONE UMMA M-block: 128 consecutive "slots" of a haloed tile that is WT slots wide
+//     (slot = tile_row * WT + tile_col), for NB output channels: D[128 x NB] fp32 lives in TMEM.
+//   * the input tile (TH_o + 2*pad rows, rounded to TF32) sits in shared memory in the UMMA
+//     K-major / no-swizzle canonical layout with the 8-row core matrices laid out CONTIGUOUSLY:
+//         element (slot, k)  at  (k / 4) * LBO + slot * 16 B + (k % 4) * 4 B ,  SBO = 128 B.
+//     Because consecutive slots are 16 bytes apart for every K chunk, a stencil tap (dy, dx) is the
+//     SAME shared-memory tile addressed (dy*WT + dx) * 16 bytes further: the A operand of each tap
+//     is just a shared-memory descriptor with a shifted start address.  No im2col, the tile is
+//     fetched from L2 once.  Output columns >= WT - 2*pad of every tile row are wrap-around garbage
+//     and are discarded by the epilogue.
+//   * weights are pre-packed on the host in the same canonical layout ([tap][k/4][n][4], TF32) so the
+//     CTA stages them with plain 16-byte cp.async copies.
+//   * one elected thread issues KS*KS*CINP/8 tcgen05.mma (kind::tf32, M=128, N=NB, K=8) back to back
+//     and commits to an mbarrier; four warps then pull their 32 TMEM lanes with tcgen05.ld and run the
+//     fused epilogue (one thread = one pixel = NB contiguous output channels).
+#pragma once
+#include "common.cuh"
+#include "mmaconv.cuh"
+
+namespace imvs {
+namespace tc5 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+//   [0,14) start >> 4, [16,30) leading byte offset >> 4 (between the two 16-byte K chunks of one MMA),
+//   [32,46) stride byte offset >> 4 (between 8-row core matrices), [46,48) version = 1, [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct Geometry {      // host-computed tile geometry
+    int WT;            // slots per tile row (power of two: 32 or 64); valid output columns = WT - 2*pad
+    int THo;           // output rows per CTA = 128 / WT
+    int pad;           // dil * (ks - 1) / 2
+    int dil, ks;
+    int nslot;         // slots staged = (THo + 2*pad) * WT + 2*pad (rounded up to 8)
+};
+
+inline Geometry make_geometry(int ks, int dil, int Wout) {
+    Geometry g;
+    g.ks = ks; g.dil = dil; g.pad = dil * (ks - 1) / 2;
+    // narrower tiles waste fewer halo columns on narrow images, wider ones fewer halo rows
+    g.WT = (Wout + 2 * g.pad <= 32 || (Wout % (64 - 2 * g.pad) != 0 && Wout % (32 - 2 * g.pad) == 0)) ? 32 : 64;
+    g.THo = 128 / g.WT;
+    g.nslot = ((g.THo + 2 * g.pad) * g.WT + 2 * g.pad + 7) / 8 * 8;
+    return g;
+}
+
+// error flag (device int): 1 = an mbarrier wait timed out (should never happen; keeps a broken build from hanging the GPU)
+// Epi::pixel<NB>(n, oy, ox, v): the NB output channels of pixel (oy, ox), in range, one thread.
+template <int CINP, int NB, class In, class Epi>
+__global__ void __launch_bounds__(128)
+tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, const Geometry geo, int Hout, int Wout, int* err_flag) {
+    static_assert(CINP % 8 == 0 && NB % 16 == 0 && NB <= 256, "UMMA shape");
+    constexpr int KC = CINP / 4;                                 // 16-byte K chunks
+    constexpr int TMEM_COLS = NB <= 32 ? 32 : (NB <= 64 ? 64 : (NB <= 128 ? 128 : 256));
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nslot = geo.nslot, WT = geo.WT, pad = geo.pad, dil = geo.dil, ks = geo.ks;
+    const int ntaps = ks * ks;
+    float* sA = reinterpret_cast<float*>(smem_raw);              // [KC][nslot][4]
+    float* sB = sA + (size_t)KC * nslot * 4;                     // [ntaps][KC][NB][4]
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + (size_t)ntaps * KC * NB * 4);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.z;
+    const int wvalid = WT - 2 * pad;
+    const int oy0 = blockIdx.y * geo.THo, ox0 = blockIdx.x * wvalid;
+
+    if (warp == 0) tmem_alloc(smem_u32(sTmem), TMEM_COLS);
+    if (tid == 32) { mbar_init(smem_u32(sBar), 1); fence_mbar_init(); }
+
+    // ---- stage weights (already TF32 + canonical layout): plain copy
+    {
+        const float* src = w_umma;
+        const int chunks = ntaps * KC * NB;
+        for (int i = tid; i < chunks; i += 128) cp_async16(sB + 4 * (size_t)i, src + 4 * (size_t)i, true);
+    }
+    // ---- stage the haloed input tile: slot s -> pixel (oy0 - pad + s / WT, ox0 - pad + s % WT)
+    const int total = nslot * KC;
+    for (int i = tid; i < total; i += 128) {
+        const int s = i / KC, kc = i % KC;
+        const int iy = oy0 - pad + s / WT, ix = ox0 - pad + s % WT;
+        bool valid;
+        const float* src = in.ptr4(n, iy, ix, kc, valid);
+        cp_async16(sA + ((size_t)kc * nslot + s) * 4, src, valid);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    // round this thread's own chunks to TF32 (round-to-nearest; the tensor core would truncate)
+    for (int i = tid; i < total; i += 128) {
+        const int s = i / KC, kc = i % KC;
+        float4* p = reinterpret_cast<float4*>(sA + ((size_t)kc * nslot + s) * 4);
+        float4 v = *p;
+        v.x = __uint_as_float(f2tf32(v.x)); v.y = __uint_as_float(f2tf32(v.y));
+        v.z = __uint_as_float(f2tf32(v.z)); v.w = __uint_as_float(f2tf32(v.w));
+        *p = v;
+    }
+    fence_async_shared();                 // generic-proxy writes -> visible to the tensor core's async proxy
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = *sTmem;
+
+    // ---- MMAs: one thread issues everything, then commits to the mbarrier
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32(NB);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        const uint32_t lbo_a = (uint32_t)nslot * 16u, lbo_b = (uint32_t)NB * 16u;
+        uint32_t acc = 0;
+        for (int tap = 0; tap < ntaps; ++tap) {
+            const int shift = (tap / ks) * dil * WT + (tap % ks) * dil;          // slots
+            for (int k8 = 0; k8 < CINP / 8; ++k8) {
+                const uint64_t da = make_desc(a_base + (uint32_t)shift * 16u + (uint32_t)(2 * k8) * lbo_a, lbo_a, 128u);
+                const uint64_t db = make_desc(b_base + (uint32_t)((tap * KC + 2 * k8) * NB) * 16u, lbo_b, 128u);
+                umma_tf32(tmem_d, da, db, idesc, acc);
+                acc = 1;
+            }
+        }
+        umma_commit(smem_u32(sBar));
+    }
+    // ---- wait for the accumulator (bounded spin: a wrong descriptor must not hang the GPU)
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 22) && !done; ++it) done = mbar_try_wait(smem_u32(sBar), 0);
+    fence_after_sync();
+    if (!done) {
+        if (tid == 0 && err_flag) atomicExch(err_flag, 1);
+    } else {
+        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = slots; thread = one output pixel
+        const int m = warp * 32 + lane;
+        const int oy = oy0 + m / WT, oxl = m % WT, ox = ox0 + oxl;
+        const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
+        float v[NB];
+#pragma unroll
+        for (int c = 0; c < NB; c += 16) {
+            float t16[16];
+            tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, t16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[c + i] = t16[i];
+        }
+        if (ok) epi.template pixel<NB>(n, oy, ox, v);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <int CINP, int NB>
+inline size_t smem_bytes(const Geometry& g) {
+    return sizeof(float) * ((size_t)(CINP / 4) * g.nslot * 4 + (size_t)g.ks * g.ks * (CINP / 4) * NB * 4) + 64;
+}
+
+template <int CINP, int NB, class In, class Epi>
+int launch(const char* name, const In& in, const Epi& epi, const float* w_umma, int ks, int dil, int N, int Hout, int Wout,
+           int* err_flag, cudaStream_t st) {
+    IMVS_REQUIRE(w_umma, "%s: null tcgen05 weights", name);
+    const Geometry g = make_geometry(ks, dil, Wout);
+    const size_t smem = smem_bytes<CINP, NB>(g);
+    IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
+    auto kern = tc5_conv_kernel<CINP, NB, In, Epi>;
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
+    dim3 grid(cdiv(Wout, g.WT - 2 * g.pad), cdiv(Hout, g.THo), N);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
+    kern<<<grid, 128, smem, st>>>(in, epi, w_umma, g, Hout, Wout, err_flag);
+    count_launch();
+    IMVS_LAUNCH_CHECK(name);
+    return 0;
+}
+
+// ---- epilogues (one thread = one pixel, NB contiguous channels) -----------------------------------
+struct PixNHWC {          // out[n][oy][ox][0..NB) = (v + bias) (+ residual) (relu)
+    float* out;
+    const float* bias;
+    const float* residual;
+    int H, W, C, relu;
+    template <int NB>
+    __device__ __forceinline__ void pixel(int n, int oy, int ox, const float (&v)[NB]) const {
+        const size_t base = (((size_t)n * H + oy) * W + ox) * C;
+#pragma unroll
+        for (int c = 0; c < NB; c += 4) {
+            float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            if (bias) { const float4 b = ldg4(bias + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (residual) { const float4 r = ldg4(residual + base + c); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(out + base + c) = o;
+        }
+    }
+};
+
+struct PixGruZR {         // NB = 64: channels 0..31 -> z = sigmoid, 32..63 -> r = sigmoid, store r*h   (module.py:61-62)
+    const float* bias;
+    const float* h;
+    float* z;
+    float* rh;
+    int H, W;
+    template <int NB>
+    __device__ __forceinline__ void pixel(int n, int oy, int ox, const float (&v)[NB]) const {
+        static_assert(NB == 64, "z|r stacked");
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            const float4 bz = ldg4(bias + c), br = ldg4(bias + 32 + c), hh = ldg4(h + base + c);
+            *reinterpret_cast<float4*>(z + base + c) = make_float4(sigmoidf_(v[c] + bz.x), sigmoidf_(v[c + 1] + bz.y),
+                                                                    sigmoidf_(v[c + 2] + bz.z), sigmoidf_(v[c + 3] + bz.w));
+            *reinterpret_cast<float4*>(rh + base + c) = make_float4(sigmoidf_(v[32 + c] + br.x) * hh.x, sigmoidf_(v[33 + c] + br.y) * hh.y,
+                                                                     sigmoidf_(v[34 + c] + br.z) * hh.z, sigmoidf_(v[35 + c] + br.w) * hh.w);
+        }
+    }
+};
+
+struct PixGruQ {          // NB = 32: q = tanh, h <- (1-z) h + z q in place   (module.py:63-64)
+    const float* bias;
+    const float* z;
+    float* h;
+    int H, W;
+    template <int NB>
+    __device__ __forceinline__ void pixel(int n, int oy, int ox, const float (&v)[NB]) const {
+        static_assert(NB == 32, "q");
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            const float4 b = ldg4(bias + c), zz = ldg4(z + base + c);
+            float4 hh = *reinterpret_cast<const float4*>(h + base + c);
+            hh.x = (1.f - zz.x) * hh.x + zz.x * tanhf(v[c] + b.x);
+            hh.y = (1.f - zz.y) * hh.y + zz.y * tanhf(v[c + 1] + b.y);
+            hh.z = (1.f - zz.z) * hh.z + zz.z * tanhf(v[c + 2] + b.z);
+            hh.w = (1.f - zz.w) * hh.w + zz.w * tanhf(v[c + 3] + b.w);
+            *reinterpret_cast<float4*>(h + base + c) = hh;
+        }
+    }
+};
+
+}  // namespace tc5
+
+int tc5_enabled();        // imvs_set_tcgen05(): use the tcgen05 kernels when conv_passes == 1 (default on)
+int* tc5_error_flag();    // process-wide device int (lazily allocated outside graph capture), or nullptr
+
+}  // namespace imvs

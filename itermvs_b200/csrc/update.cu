@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "mmaconv.cuh"
+#include "tc5conv.cuh"
 
 namespace imvs {
 
@@ -169,6 +170,14 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
     const size_t n = (size_t)B * 32 * H * W;
     float* z = scratch;
     float* rh = scratch + n;
+    if (conv_passes() == 1 && tc5_enabled() && w->gru_zr.umma && w->gru_q.umma) {
+        // tcgen05 path: z|r as one M=128 x N=64 x K=432 UMMA chain per tile, q as N=32
+        IMVS_TRY((tc5::launch<48, 64>("gru.zr(tcgen05)", InNHWC2{h, x, H, W, 32, IMVS_XCH}, tc5::PixGruZR{w->gru_zr_b, h, z, rh, H, W},
+                                      w->gru_zr.umma, 3, 2, B, H, W, tc5_error_flag(), st)));
+        IMVS_TRY((tc5::launch<48, 32>("gru.q(tcgen05)", InNHWC2{rh, x, H, W, 32, IMVS_XCH}, tc5::PixGruQ{w->gru_q_b, z, h, H, W},
+                                      w->gru_q.umma, 3, 2, B, H, W, tc5_error_flag(), st)));
+        return 0;
+    }
     const TapTables taps = conv_tables(3, 1, 2, 8);
     IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.zr", InNHWC2{h, x, H, W, 32, IMVS_XCH}, EpiGruZR{w->gru_zr_b, h, z, rh, H, W},
                                                WSets::single(w->gru_zr), taps, B, 64, H, W, 2, st)));
@@ -193,8 +202,13 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     float* logits = h1 + (size_t)B * P * 64;     // [B][P][256]
     // stacked weight [9][32][64]: channel block 0 = depth_head.0, block 1 = confidence_head.0; the
     // confidence block only runs when a confidence output is requested (itermvs.py:196-199)
-    IMVS_TRY((mma_conv<32, 32, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), EpiNHWC{t, nullptr, nullptr, H, W, 64, 64, 1},
-                                               WSets::single(w->head_conv0), conv_tables(3, 1, 2, 8), B, 64, H, W, want_conf ? 2 : 1, st)));
+    if (conv_passes() == 1 && tc5_enabled() && w->head_conv0.umma) {
+        IMVS_TRY((tc5::launch<32, 64>("head.conv0(tcgen05)", in_nhwc(hidden, H, W, 32), tc5::PixNHWC{t, nullptr, nullptr, H, W, 64, 1},
+                                      w->head_conv0.umma, 3, 2, B, H, W, tc5_error_flag(), st)));
+    } else {
+        IMVS_TRY((mma_conv<32, 32, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), EpiNHWC{t, nullptr, nullptr, H, W, 64, 64, 1},
+                                                   WSets::single(w->head_conv0), conv_tables(3, 1, 2, 8), B, 64, H, W, want_conf ? 2 : 1, st)));
+    }
     IMVS_TRY((mma_conv<32, 64, 2, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), EpiNHWC{h1, nullptr, nullptr, H, W, 64, 64, 1},
                                               WSets::single(w->head_fc1), conv_tables(1, 1, 1, 8), B, 64, H, W, 1, st)));
     IMVS_TRY((mma_conv<64, 64, 2, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), EpiNHWC{logits, w->head_fc2_b, nullptr, H, W, 256, 256, 0},

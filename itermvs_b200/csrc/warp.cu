@@ -19,6 +19,17 @@ void count_launch(int n) { g_launches += n; }
 long long launches_total() { return g_launches; }
 static int g_conv_passes = 3;
 int conv_passes() { return g_conv_passes; }
+static int g_tc5 = 1;
+int tc5_enabled() { return g_tc5; }
+__device__ int g_tc5_err = 0;
+int* tc5_error_flag() {
+    static int* p = nullptr;
+    if (!p) {
+        void* q = nullptr;
+        if (cudaGetSymbolAddress(&q, g_tc5_err) == cudaSuccess) p = static_cast<int*>(q);
+    }
+    return p;
+}
 
 // ---- stage timing taps -----------------------------------------------------------------------
 struct ProfileState {
@@ -185,6 +196,13 @@ extern "C" int imvs_set_conv_passes(int passes) {
     return 0;
 }
 extern "C" int imvs_get_conv_passes(void) { return g_conv_passes; }
+extern "C" int imvs_set_tcgen05(int enabled) { g_tc5 = enabled ? 1 : 0; return 0; }
+extern "C" int imvs_tcgen05_status(void) {
+    int v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+    if (cudaMemcpyFromSymbol(&v, g_tc5_err, sizeof(int)) != cudaSuccess) return 2;
+    return v;
+}
 
 // Profiling facility (NOT graph-capturable, synchronises in _end): records one CUDA-event pair
 // around every stage of imvs_itermvs_forward / imvs_featurenet_forward issued between begin and end.

@@ -51,13 +51,14 @@ def test_tf32_split_and_packing(dtu_weights):
     assert torch.equal(_pack.round_tf32(t), torch.tensor([1.0 + 2 ** -10, -(1.0 + 2 ** -10)]))
     # conv packing: [Cout,Cin,3,3] -> [9][CinP][CoutP]
     w = dtu_weights["iter_mvs.update.gru.convq.weight"]
-    hi, full = _pack.pack_mma_conv(w, cinp=48)
+    hi, full, um = _pack.pack_mma_conv(w, cinp=48)
+    assert um.shape == (1, 9, 12, 32, 4) and torch.equal(um[0, 4, 3, 7], hi[4, 12:16, 7])
     assert hi.shape == (9, 48, 32)
     rec = full[:, :43, :].reshape(3, 3, 43, 32).permute(3, 2, 0, 1)
     assert torch.equal(rec, w)
     assert float(hi[:, 43:, :].abs().max()) == 0.0
     wt = dtu_weights["iter_mvs.evaluation.corr_conv1.0.conv3.weight"]          # ConvTranspose [Cin,Cout,3,3]
-    hi, full = _pack.pack_mma_tconv(wt)
+    hi, full, _ = _pack.pack_mma_tconv(wt)
     assert hi.shape == (9, 32, 16)
     assert torch.equal(full[4], wt[:, :, 1, 1])
 

@@ -375,3 +375,39 @@ def test_config5_stress_shape(dev, dtu_weights):
     # median-tight, a bounded fraction of pixels may move by a bin
     assert np.median(rel) < 1e-5, (np.median(rel), rel.mean())
     assert (rel > 1e-3).mean() < 0.2, (rel > 1e-3).mean()
+
+
+def test_tcgen05_path_matches_mma_sync(dev, stage_kats, model):
+    """TF32 1-pass mode: the tcgen05/TMEM convolution (GRU, head conv0) against the mma.sync kernels on the
+    same TF32-rounded operands -- they differ only by fp32 accumulation order."""
+    from itermvs_b200 import _lib
+    L = _lib.lib()
+    upd = model.iter_mvs.update
+    g = torch.Generator().manual_seed(5)
+    h = torch.tanh(torch.randn(2, 32, 40, 72, generator=g)).to(dev)        # W = 72: two 60-wide tiles, ragged
+    x = (torch.randn(2, 11, 40, 72, generator=g) * 0.5).to(dev)
+    _lib.set_conv_passes(1)
+    try:
+        L.imvs_set_tcgen05(0)
+        ref_h = upd.gru(h, x)
+        upd.return_probability = True
+        ref_nd, ref_p = upd.depth_init(h)
+        L.imvs_set_tcgen05(1)
+        got_h = upd.gru(h, x)
+        got_nd, got_p = upd.depth_init(h)
+        assert L.imvs_tcgen05_status() == 0, "a tcgen05 kernel timed out on its mbarrier"
+    finally:
+        upd.return_probability = None
+        L.imvs_set_tcgen05(1)
+        _lib.set_conv_passes(3)
+    print("tcgen05 vs mma.sync: gru max diff", maxerr(got_h, ref_h), "prob max diff", maxerr(got_p, ref_p))
+    assert maxerr(got_h, ref_h) < 2e-5
+    assert maxerr(got_p, ref_p) < 2e-5
+    # and against the fp32 golden GRU within TF32 accuracy
+    k = stage_kats
+    _lib.set_conv_passes(1)
+    try:
+        out = upd.gru(T(k["gru_h"]).to(dev), T(k["gru_x"]).to(dev))
+    finally:
+        _lib.set_conv_passes(3)
+    assert maxerr(out, T(k["gru_out"])) < 5e-3
