@@ -44,7 +44,8 @@ def pack_umma(w_tf32: Tensor) -> Tensor:
     NB = min(CoutP, 64): element (n, k) of a tap at (k/4)*NB*16 B + n*16 B + (k%4)*4 B."""
     taps, cinp, coutp = w_tf32.shape
     nb = min(coutp, 64)
-    assert coutp % nb == 0 and cinp % 4 == 0
+    if coutp % nb != 0 or nb % 16 != 0 or cinp % 8 != 0:
+        return None                                  # shape not served by the tcgen05 kernels
     x = w_tf32.reshape(taps, cinp // 4, 4, coutp // nb, nb)          # [tap][kc][k4][cb][n]
     return x.permute(3, 0, 1, 4, 2).contiguous()                     # [cb][tap][kc][n][k4]
 
@@ -86,7 +87,7 @@ class _Holder:
 
     def pair(self, hl) -> _lib.WPair:
         self.keep.extend(hl)
-        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if len(hl) > 2 else None)
+        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if len(hl) > 2 and hl[2] is not None else None)
 
     def ptr(self, t: Tensor) -> int:
         self.keep.append(t)
