@@ -13,7 +13,7 @@
 //     fetched from L2 once.  Output columns >= WT - 2*pad of every tile row are wrap-around garbage
 //     and are discarded by the epilogue.
 //   * weights are pre-packed on the host in the same canonical layout ([tap][k/4][n][4], TF32) so the
-//     CTA stages them with plain 16-byte cp.async copies.
+//     CTA stages them with one 1-D bulk copy per tap through the TMA engine (cp.async.bulk + mbarrier).
 //   * one elected thread issues KS*KS*CINP/8 tcgen05.mma (kind::tf32, M=128, N=NB, K=8) back to back
 //     and commits to an mbarrier; four warps then pull their 32 TMEM lanes with tcgen05.ld and run the
 //     fused epilogue (one thread = one pixel = NB contiguous output channels).
@@ -36,6 +36,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the async proxy (TMA engine, no tensor map), completes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -97,8 +105,16 @@ inline Geometry make_geometry(int ks, int dil, int Wout) {
 
 // error flag (device int): 1 = an mbarrier wait timed out (should never happen; keeps a broken build from hanging the GPU)
 // Epi::pixel<NB>(n, oy, ox, v): the NB output channels of pixel (oy, ox), in range, one thread.
+constexpr int TC5_THREADS = 256;      // 8 warps stage the tile; warps 0-3 run the epilogue (TMEM lanes 32w..32w+31)
+
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 22) && !done; ++it) done = mbar_try_wait(bar, parity);
+    return done != 0;
+}
+
 template <int CINP, int NB, class In, class Epi>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TC5_THREADS)
 tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, const Geometry geo, int Hout, int Wout, int* err_flag) {
     static_assert(CINP % 8 == 0 && NB % 16 == 0 && NB <= 256, "UMMA shape");
     constexpr int KC = CINP / 4;                                 // 16-byte K chunks
@@ -108,28 +124,31 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
     const int ntaps = ks * ks;
     float* sA = reinterpret_cast<float*>(smem_raw);              // [KC][nslot][4]
     float* sB = sA + (size_t)KC * nslot * 4;                     // [ntaps][KC][NB][4]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + (size_t)ntaps * KC * NB * 4);
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + (size_t)ntaps * KC * NB * 4);   // [0] weights landed, [1] MMAs done
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = blockIdx.z;
     const int wvalid = WT - 2 * pad;
     const int oy0 = blockIdx.y * geo.THo, ox0 = blockIdx.x * wvalid;
+    const uint32_t bar_w = smem_u32(sBar), bar_d = smem_u32(sBar + 1);
 
     if (warp == 0) tmem_alloc(smem_u32(sTmem), TMEM_COLS);
-    if (tid == 32) { mbar_init(smem_u32(sBar), 1); fence_mbar_init(); }
-
-    // ---- stage weights (already TF32 + canonical layout): plain copy
-    {
-        const float* src = w_umma;
-        const int chunks = ntaps * KC * NB;
-        for (int i = tid; i < chunks; i += 128) cp_async16(sB + 4 * (size_t)i, src + 4 * (size_t)i, true);
+    if (tid == 32) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_d, 1);
+        fence_mbar_init();
+        // weights (already TF32, canonical order): one bulk copy per tap through the TMA engine
+        constexpr uint32_t tap_bytes = KC * NB * 16;
+        mbar_expect_tx(bar_w, tap_bytes * (uint32_t)ntaps);
+        for (int tap = 0; tap < ntaps; ++tap)
+            bulk_g2s(smem_u32(sB) + tap * tap_bytes, w_umma + (size_t)tap * (tap_bytes / 4), tap_bytes, bar_w);
     }
     // ---- stage the haloed input tile: slot s -> pixel (oy0 - pad + s / WT, ox0 - pad + s % WT)
     const int total = nslot * KC;
-    for (int i = tid; i < total; i += 128) {
-        const int s = i / KC, kc = i % KC;
-        const int iy = oy0 - pad + s / WT, ix = ox0 - pad + s % WT;
+    for (int i = tid; i < total; i += TC5_THREADS) {
+        const int s = i / KC, kc = i - s * KC;
+        const int iy = oy0 - pad + s / WT, ix = ox0 - pad + (s & (WT - 1));
         bool valid;
         const float* src = in.ptr4(n, iy, ix, kc, valid);
         cp_async16(sA + ((size_t)kc * nslot + s) * 4, src, valid);
@@ -137,8 +156,8 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
     cp_async_commit();
     cp_async_wait<0>();
     // round this thread's own chunks to TF32 (round-to-nearest; the tensor core would truncate)
-    for (int i = tid; i < total; i += 128) {
-        const int s = i / KC, kc = i % KC;
+    for (int i = tid; i < total; i += TC5_THREADS) {
+        const int s = i / KC, kc = i - s * KC;
         float4* p = reinterpret_cast<float4*>(sA + ((size_t)kc * nslot + s) * 4);
         float4 v = *p;
         v.x = __uint_as_float(f2tf32(v.x)); v.y = __uint_as_float(f2tf32(v.y));
@@ -152,43 +171,49 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
     const uint32_t tmem_d = *sTmem;
 
     // ---- MMAs: one thread issues everything, then commits to the mbarrier
+    bool ok_w = true;
     if (tid == 0) {
+        ok_w = mbar_wait_bounded(bar_w, 0);                       // weights landed (async proxy)
         constexpr uint32_t idesc = make_idesc_tf32(NB);
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         const uint32_t lbo_a = (uint32_t)nslot * 16u, lbo_b = (uint32_t)NB * 16u;
         uint32_t acc = 0;
-        for (int tap = 0; tap < ntaps; ++tap) {
-            const int shift = (tap / ks) * dil * WT + (tap % ks) * dil;          // slots
-            for (int k8 = 0; k8 < CINP / 8; ++k8) {
-                const uint64_t da = make_desc(a_base + (uint32_t)shift * 16u + (uint32_t)(2 * k8) * lbo_a, lbo_a, 128u);
-                const uint64_t db = make_desc(b_base + (uint32_t)((tap * KC + 2 * k8) * NB) * 16u, lbo_b, 128u);
-                umma_tf32(tmem_d, da, db, idesc, acc);
-                acc = 1;
+        if (ok_w) {
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const int shift = (tap / ks) * dil * WT + (tap % ks) * dil;          // slots
+#pragma unroll
+                for (int k8 = 0; k8 < CINP / 8; ++k8) {
+                    const uint64_t da = make_desc(a_base + (uint32_t)shift * 16u + (uint32_t)(2 * k8) * lbo_a, lbo_a, 128u);
+                    const uint64_t db = make_desc(b_base + (uint32_t)((tap * KC + 2 * k8) * NB) * 16u, lbo_b, 128u);
+                    umma_tf32(tmem_d, da, db, idesc, acc);
+                    acc = 1;
+                }
             }
         }
-        umma_commit(smem_u32(sBar));
+        umma_commit(bar_d);
     }
-    // ---- wait for the accumulator (bounded spin: a wrong descriptor must not hang the GPU)
-    uint32_t done = 0;
-    for (int it = 0; it < (1 << 22) && !done; ++it) done = mbar_try_wait(smem_u32(sBar), 0);
-    fence_after_sync();
-    if (!done) {
-        if (tid == 0 && err_flag) atomicExch(err_flag, 1);
-    } else {
-        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = slots; thread = one output pixel
-        const int m = warp * 32 + lane;
-        const int oy = oy0 + m / WT, oxl = m % WT, ox = ox0 + oxl;
-        const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
-        float v[NB];
+    // ---- epilogue: warp w (< 4) owns TMEM lanes 32w..32w+31 = slots; thread = one output pixel
+    if (warp < 4) {
+        const bool done = mbar_wait_bounded(bar_d, 0);
+        fence_after_sync();
+        if (!done) {
+            if (lane == 0 && err_flag) atomicExch(err_flag, 1);
+        } else {
+            const int m = warp * 32 + lane;
+            const int oy = oy0 + m / WT, oxl = m & (WT - 1), ox = ox0 + oxl;
+            const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
+            float v[NB];
 #pragma unroll
-        for (int c = 0; c < NB; c += 16) {
-            float t16[16];
-            tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, t16);
+            for (int c = 0; c < NB; c += 16) {
+                float t16[16];
+                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, t16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[c + i] = t16[i];
+                for (int i = 0; i < 16; ++i) v[c + i] = t16[i];
+            }
+            if (ok) epi.template pixel<NB>(n, oy, ox, v);
         }
-        if (ok) epi.template pixel<NB>(n, oy, ox, v);
     }
+    if (tid == 0 && !ok_w && err_flag) atomicExch(err_flag, 1);
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
@@ -211,7 +236,7 @@ int launch(const char* name, const In& in, const Epi& epi, const float* w_umma, 
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     dim3 grid(cdiv(Wout, g.WT - 2 * g.pad), cdiv(Hout, g.THo), N);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
-    kern<<<grid, 128, smem, st>>>(in, epi, w_umma, g, Hout, Wout, err_flag);
+    kern<<<grid, TC5_THREADS, smem, st>>>(in, epi, w_umma, g, Hout, Wout, err_flag);
     count_launch();
     IMVS_LAUNCH_CHECK(name);
     return 0;
