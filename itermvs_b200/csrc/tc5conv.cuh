@@ -22,6 +22,7 @@
 #include "mmaconv.cuh"
 
 namespace imvs {
+long long* tc5_clock_buffer();
 namespace tc5 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +91,7 @@ struct Geometry {      // host-computed tile geometry
     int THo;           // output rows per CTA = 128 / WT
     int pad;           // dil * (ks - 1) / 2
     int dil, ks;
-    int nslot;         // slots staged = (THo + 2*pad) * WT + 2*pad (rounded up to 8)
+    int nslot;         // slots staged >= (THo + 2*pad) * WT + 2*pad, = 2 (mod 8)
 };
 
 inline Geometry make_geometry(int ks, int dil, int Wout) {
@@ -99,13 +100,13 @@ inline Geometry make_geometry(int ks, int dil, int Wout) {
     // narrower tiles waste fewer halo columns on narrow images, wider ones fewer halo rows
     g.WT = (Wout + 2 * g.pad <= 32 || (Wout % (64 - 2 * g.pad) != 0 && Wout % (32 - 2 * g.pad) == 0)) ? 32 : 64;
     g.THo = 128 / g.WT;
-    g.nslot = ((g.THo + 2 * g.pad) * g.WT + 2 * g.pad + 7) / 8 * 8;
+    g.nslot = ((g.THo + 2 * g.pad) * g.WT + 2 * g.pad + 7) / 8 * 8 + 2;      // = 2 (mod 8): conflict-free staging stores
     return g;
 }
 
 // error flag (device int): 1 = an mbarrier wait timed out (should never happen; keeps a broken build from hanging the GPU)
-// Epi::pixel<NB>(n, oy, ox, v): the NB output channels of pixel (oy, ox), in range, one thread.
-constexpr int TC5_THREADS = 256;      // 8 warps stage the tile; warps 0-3 run the epilogue (TMEM lanes 32w..32w+31)
+// Epi::part<NC>(n, oy, ox, c0, v): output channels [c0, c0+NC) of pixel (oy, ox), in range, one thread.
+constexpr int TC5_THREADS = 256;      // 8 warps: all stage the tile; warp w reads TMEM lanes 32*(w&3).. and columns half (w>>2)
 
 __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -115,11 +116,16 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
 
 template <int CINP, int NB, class In, class Epi>
 __global__ void __launch_bounds__(TC5_THREADS)
-tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, const Geometry geo, int Hout, int Wout, int* err_flag) {
-    static_assert(CINP % 8 == 0 && NB % 16 == 0 && NB <= 256, "UMMA shape");
+tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, const Geometry geo, int Hout, int Wout, int* err_flag,
+                long long* clk) {
+    static_assert(CINP % 16 == 0 && NB % 32 == 0 && NB <= 256, "UMMA shape / staging pattern");
     constexpr int KC = CINP / 4;                                 // 16-byte K chunks
+    constexpr int KG = KC / 4;                                   // chunk groups of 4 (one per lane & 3)
     constexpr int TMEM_COLS = NB <= 32 ? 32 : (NB <= 64 ? 64 : (NB <= 128 ? 128 : 256));
+    constexpr int NC = NB / 2;                                   // epilogue columns per thread
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const bool stamp = clk != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    if (stamp) clk[0] = clock64();
     const int nslot = geo.nslot, WT = geo.WT, pad = geo.pad, dil = geo.dil, ks = geo.ks;
     const int ntaps = ks * ks;
     float* sA = reinterpret_cast<float*>(smem_raw);              // [KC][nslot][4]
@@ -144,78 +150,92 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
         for (int tap = 0; tap < ntaps; ++tap)
             bulk_g2s(smem_u32(sB) + tap * tap_bytes, w_umma + (size_t)tap * (tap_bytes / 4), tap_bytes, bar_w);
     }
-    // ---- stage the haloed input tile: slot s -> pixel (oy0 - pad + s / WT, ox0 - pad + s % WT)
-    const int total = nslot * KC;
-    for (int i = tid; i < total; i += TC5_THREADS) {
-        const int s = i / KC, kc = i - s * KC;
-        const int iy = oy0 - pad + s / WT, ix = ox0 - pad + (s & (WT - 1));
-        bool valid;
-        const float* src = in.ptr4(n, iy, ix, kc, valid);
-        cp_async16(sA + ((size_t)kc * nslot + s) * 4, src, valid);
+    // ---- stage the haloed input tile, rounding to TF32 (round-to-nearest) on the way:
+    //      slot s -> pixel (oy0 - pad + s / WT, ox0 - pad + s % WT).  A quarter-warp covers 2 slots x 4 chunks;
+    //      nslot = 2 (mod 8) makes the 16-byte stores of a quarter-warp hit 8 distinct bank groups.
+    {
+        const int kcl = lane & 3, sl = lane >> 2;
+        for (int s0 = warp * 8; s0 < nslot; s0 += (TC5_THREADS / 32) * 8) {
+            const int s = s0 + sl;
+            const bool in_tile = s < nslot;
+            const int iy = oy0 - pad + s / WT, ix = ox0 - pad + (s & (WT - 1));
+            float4 v[KG];
+#pragma unroll
+            for (int kg = 0; kg < KG; ++kg) {
+                bool valid;
+                const float* src = in.ptr4(n, iy, ix, kg * 4 + kcl, valid);
+                v[kg] = (valid && in_tile) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (in_tile) {
+#pragma unroll
+                for (int kg = 0; kg < KG; ++kg) {
+                    uint4 r = make_uint4(f2tf32(v[kg].x), f2tf32(v[kg].y), f2tf32(v[kg].z), f2tf32(v[kg].w));
+                    *reinterpret_cast<uint4*>(sA + ((size_t)(kg * 4 + kcl) * nslot + s) * 4) = r;
+                }
+            }
+        }
     }
-    cp_async_commit();
-    cp_async_wait<0>();
-    // round this thread's own chunks to TF32 (round-to-nearest; the tensor core would truncate)
-    for (int i = tid; i < total; i += TC5_THREADS) {
-        const int s = i / KC, kc = i - s * KC;
-        float4* p = reinterpret_cast<float4*>(sA + ((size_t)kc * nslot + s) * 4);
-        float4 v = *p;
-        v.x = __uint_as_float(f2tf32(v.x)); v.y = __uint_as_float(f2tf32(v.y));
-        v.z = __uint_as_float(f2tf32(v.z)); v.w = __uint_as_float(f2tf32(v.w));
-        *p = v;
-    }
+    if (stamp) clk[1] = clock64();
     fence_async_shared();                 // generic-proxy writes -> visible to the tensor core's async proxy
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_d = *sTmem;
+    if (stamp) clk[3] = clock64();
 
     // ---- MMAs: one thread issues everything, then commits to the mbarrier
     bool ok_w = true;
     if (tid == 0) {
         ok_w = mbar_wait_bounded(bar_w, 0);                       // weights landed (async proxy)
+        if (stamp) clk[4] = clock64();
         constexpr uint32_t idesc = make_idesc_tf32(NB);
-        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         const uint32_t lbo_a = (uint32_t)nslot * 16u, lbo_b = (uint32_t)NB * 16u;
+        const uint64_t da0 = make_desc(smem_u32(sA), lbo_a, 128u), db0 = make_desc(smem_u32(sB), lbo_b, 128u);
+        const uint32_t ka = (2u * lbo_a) >> 4, kb = (2u * lbo_b) >> 4;            // per K-step (8 elements) advance, in 16 B units
         uint32_t acc = 0;
         if (ok_w) {
             for (int tap = 0; tap < ntaps; ++tap) {
-                const int shift = (tap / ks) * dil * WT + (tap % ks) * dil;          // slots
+                const uint32_t shift = (uint32_t)((tap / ks) * dil * WT + (tap % ks) * dil);       // slots == 16 B units
+                uint64_t da = da0 + shift, db = db0 + (uint32_t)(tap * KC * NB);
 #pragma unroll
                 for (int k8 = 0; k8 < CINP / 8; ++k8) {
-                    const uint64_t da = make_desc(a_base + (uint32_t)shift * 16u + (uint32_t)(2 * k8) * lbo_a, lbo_a, 128u);
-                    const uint64_t db = make_desc(b_base + (uint32_t)((tap * KC + 2 * k8) * NB) * 16u, lbo_b, 128u);
                     umma_tf32(tmem_d, da, db, idesc, acc);
                     acc = 1;
+                    da += ka; db += kb;
                 }
             }
         }
         umma_commit(bar_d);
+        if (stamp) clk[5] = clock64();
     }
-    // ---- epilogue: warp w (< 4) owns TMEM lanes 32w..32w+31 = slots; thread = one output pixel
-    if (warp < 4) {
+    // ---- epilogue: warp w owns TMEM lanes 32*(w&3).. (= slots) and the column half (w>>2); thread = one pixel
+    {
         const bool done = mbar_wait_bounded(bar_d, 0);
         fence_after_sync();
+        if (stamp) clk[6] = clock64();
         if (!done) {
             if (lane == 0 && err_flag) atomicExch(err_flag, 1);
         } else {
-            const int m = warp * 32 + lane;
+            const int lg = warp & 3, half = warp >> 2;
+            const int m = lg * 32 + lane;
             const int oy = oy0 + m / WT, oxl = m & (WT - 1), ox = ox0 + oxl;
             const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
-            float v[NB];
+            float v[NC];
 #pragma unroll
-            for (int c = 0; c < NB; c += 16) {
+            for (int c = 0; c < NC; c += 16) {
                 float t16[16];
-                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, t16);
+                tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NC + c), t16);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[c + i] = t16[i];
             }
-            if (ok) epi.template pixel<NB>(n, oy, ox, v);
+            if (ok) epi.template part<NC>(n, oy, ox, half * NC, v);
         }
     }
+    if (stamp) clk[7] = clock64();
     if (tid == 0 && !ok_w && err_flag) atomicExch(err_flag, 1);
     fence_before_sync();
     __syncthreads();
+    if (stamp) clk[8] = clock64();
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
@@ -236,25 +256,29 @@ int launch(const char* name, const In& in, const Epi& epi, const float* w_umma, 
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     dim3 grid(cdiv(Wout, g.WT - 2 * g.pad), cdiv(Hout, g.THo), N);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
-    kern<<<grid, TC5_THREADS, smem, st>>>(in, epi, w_umma, g, Hout, Wout, err_flag);
+    kern<<<grid, TC5_THREADS, smem, st>>>(in, epi, w_umma, g, Hout, Wout, err_flag, tc5_clock_buffer());
     count_launch();
     IMVS_LAUNCH_CHECK(name);
     return 0;
 }
 
-// ---- epilogues (one thread = one pixel, NB contiguous channels) -----------------------------------
-struct PixNHWC {          // out[n][oy][ox][0..NB) = (v + bias) (+ residual) (relu)
+// ---- epilogues (one thread = one pixel, NC contiguous channels starting at c0) ---------------------
+// TF32 mode: gates use the fast exponential (ex2.approx; relative error ~1e-6, far below TF32's 5e-4)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+struct PixNHWC {          // out[n][oy][ox][c0..c0+NC) = (v + bias) (+ residual) (relu)
     float* out;
     const float* bias;
     const float* residual;
     int H, W, C, relu;
-    template <int NB>
-    __device__ __forceinline__ void pixel(int n, int oy, int ox, const float (&v)[NB]) const {
-        const size_t base = (((size_t)n * H + oy) * W + ox) * C;
+    template <int NC>
+    __device__ __forceinline__ void part(int n, int oy, int ox, int c0, const float (&v)[NC]) const {
+        const size_t base = (((size_t)n * H + oy) * W + ox) * C + c0;
 #pragma unroll
-        for (int c = 0; c < NB; c += 4) {
+        for (int c = 0; c < NC; c += 4) {
             float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-            if (bias) { const float4 b = ldg4(bias + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (bias) { const float4 b = ldg4(bias + c0 + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
             if (residual) { const float4 r = ldg4(residual + base + c); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(out + base + c) = o;
@@ -262,44 +286,50 @@ struct PixNHWC {          // out[n][oy][ox][0..NB) = (v + bias) (+ residual) (re
     }
 };
 
-struct PixGruZR {         // NB = 64: channels 0..31 -> z = sigmoid, 32..63 -> r = sigmoid, store r*h   (module.py:61-62)
+struct PixGruZR {         // 64 stacked channels: c0 = 0 -> z = sigmoid (32), c0 = 32 -> r = sigmoid, store r*h   (module.py:61-62)
     const float* bias;
     const float* h;
     float* z;
     float* rh;
     int H, W;
-    template <int NB>
-    __device__ __forceinline__ void pixel(int n, int oy, int ox, const float (&v)[NB]) const {
-        static_assert(NB == 64, "z|r stacked");
+    template <int NC>
+    __device__ __forceinline__ void part(int n, int oy, int ox, int c0, const float (&v)[NC]) const {
+        static_assert(NC == 32, "z | r halves");
         const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
+        if (c0 == 0) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            const float4 bz = ldg4(bias + c), br = ldg4(bias + 32 + c), hh = ldg4(h + base + c);
-            *reinterpret_cast<float4*>(z + base + c) = make_float4(sigmoidf_(v[c] + bz.x), sigmoidf_(v[c + 1] + bz.y),
-                                                                    sigmoidf_(v[c + 2] + bz.z), sigmoidf_(v[c + 3] + bz.w));
-            *reinterpret_cast<float4*>(rh + base + c) = make_float4(sigmoidf_(v[32 + c] + br.x) * hh.x, sigmoidf_(v[33 + c] + br.y) * hh.y,
-                                                                     sigmoidf_(v[34 + c] + br.z) * hh.z, sigmoidf_(v[35 + c] + br.w) * hh.w);
+            for (int c = 0; c < 32; c += 4) {
+                const float4 b = ldg4(bias + c);
+                *reinterpret_cast<float4*>(z + base + c) = make_float4(fast_sigmoid(v[c] + b.x), fast_sigmoid(v[c + 1] + b.y),
+                                                                        fast_sigmoid(v[c + 2] + b.z), fast_sigmoid(v[c + 3] + b.w));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 b = ldg4(bias + 32 + c), hh = ldg4(h + base + c);
+                *reinterpret_cast<float4*>(rh + base + c) = make_float4(fast_sigmoid(v[c] + b.x) * hh.x, fast_sigmoid(v[c + 1] + b.y) * hh.y,
+                                                                         fast_sigmoid(v[c + 2] + b.z) * hh.z, fast_sigmoid(v[c + 3] + b.w) * hh.w);
+            }
         }
     }
 };
 
-struct PixGruQ {          // NB = 32: q = tanh, h <- (1-z) h + z q in place   (module.py:63-64)
+struct PixGruQ {          // 32 channels in two halves: q = tanh, h <- (1-z) h + z q in place   (module.py:63-64)
     const float* bias;
     const float* z;
     float* h;
     int H, W;
-    template <int NB>
-    __device__ __forceinline__ void pixel(int n, int oy, int ox, const float (&v)[NB]) const {
-        static_assert(NB == 32, "q");
-        const size_t base = (((size_t)n * H + oy) * W + ox) * 32;
+    template <int NC>
+    __device__ __forceinline__ void part(int n, int oy, int ox, int c0, const float (&v)[NC]) const {
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32 + c0;
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            const float4 b = ldg4(bias + c), zz = ldg4(z + base + c);
+        for (int c = 0; c < NC; c += 4) {
+            const float4 b = ldg4(bias + c0 + c), zz = ldg4(z + base + c);
             float4 hh = *reinterpret_cast<const float4*>(h + base + c);
-            hh.x = (1.f - zz.x) * hh.x + zz.x * tanhf(v[c] + b.x);
-            hh.y = (1.f - zz.y) * hh.y + zz.y * tanhf(v[c + 1] + b.y);
-            hh.z = (1.f - zz.z) * hh.z + zz.z * tanhf(v[c + 2] + b.z);
-            hh.w = (1.f - zz.w) * hh.w + zz.w * tanhf(v[c + 3] + b.w);
+            hh.x = (1.f - zz.x) * hh.x + zz.x * fast_tanh(v[c] + b.x);
+            hh.y = (1.f - zz.y) * hh.y + zz.y * fast_tanh(v[c + 1] + b.y);
+            hh.z = (1.f - zz.z) * hh.z + zz.z * fast_tanh(v[c + 2] + b.z);
+            hh.w = (1.f - zz.w) * hh.w + zz.w * fast_tanh(v[c + 3] + b.w);
             *reinterpret_cast<float4*>(h + base + c) = hh;
         }
     }
@@ -308,6 +338,7 @@ struct PixGruQ {          // NB = 32: q = tanh, h <- (1-z) h + z q in place   (m
 }  // namespace tc5
 
 int tc5_enabled();        // imvs_set_tcgen05(): use the tcgen05 kernels when conv_passes == 1 (default on)
+long long* tc5_clock_buffer();   // non-null only while imvs_tc5_debug_clocks(1): CTA 0 stamps its phases
 int* tc5_error_flag();    // process-wide device int (lazily allocated outside graph capture), or nullptr
 
 }  // namespace imvs

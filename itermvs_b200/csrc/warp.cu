@@ -22,6 +22,17 @@ int conv_passes() { return g_conv_passes; }
 static int g_tc5 = 1;
 int tc5_enabled() { return g_tc5; }
 __device__ int g_tc5_err = 0;
+__device__ long long g_tc5_clk[16];
+static int g_tc5_clk_on = 0;
+long long* tc5_clock_buffer() {
+    if (!g_tc5_clk_on) return nullptr;
+    static long long* p = nullptr;
+    if (!p) {
+        void* q = nullptr;
+        if (cudaGetSymbolAddress(&q, g_tc5_clk) == cudaSuccess) p = static_cast<long long*>(q);
+    }
+    return p;
+}
 int* tc5_error_flag() {
     static int* p = nullptr;
     if (!p) {
@@ -197,6 +208,14 @@ extern "C" int imvs_set_conv_passes(int passes) {
 }
 extern "C" int imvs_get_conv_passes(void) { return g_conv_passes; }
 extern "C" int imvs_set_tcgen05(int enabled) { g_tc5 = enabled ? 1 : 0; return 0; }
+extern "C" int imvs_tc5_debug_clocks(int on, long long* out16) {   // debug: phase stamps of CTA 0 of the last tcgen05 launch
+    g_tc5_clk_on = on;
+    if (out16) {
+        if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+        if (cudaMemcpyFromSymbol(out16, g_tc5_clk, sizeof(long long) * 16) != cudaSuccess) return 2;
+    }
+    return 0;
+}
 extern "C" int imvs_tcgen05_status(void) {
     int v = 0;
     if (cudaDeviceSynchronize() != cudaSuccess) return 2;
