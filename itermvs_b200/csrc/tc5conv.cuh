@@ -154,22 +154,28 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
     //      slot s -> pixel (oy0 - pad + s / WT, ox0 - pad + s % WT).  A quarter-warp covers 2 slots x 4 chunks;
     //      nslot = 2 (mod 8) makes the 16-byte stores of a quarter-warp hit 8 distinct bank groups.
     {
+        // all global loads of a thread are issued before the first conversion / store (<= 7 x KG float4 in flight)
+        constexpr int MAXIT = 7;                                  // ceil(nslot_max / 64), nslot_max = 394 + padding
         const int kcl = lane & 3, sl = lane >> 2;
-        for (int s0 = warp * 8; s0 < nslot; s0 += (TC5_THREADS / 32) * 8) {
-            const int s = s0 + sl;
-            const bool in_tile = s < nslot;
+        float4 v[MAXIT][KG];
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int s = (it * (TC5_THREADS / 32) + warp) * 8 + sl;
             const int iy = oy0 - pad + s / WT, ix = ox0 - pad + (s & (WT - 1));
-            float4 v[KG];
 #pragma unroll
             for (int kg = 0; kg < KG; ++kg) {
                 bool valid;
                 const float* src = in.ptr4(n, iy, ix, kg * 4 + kcl, valid);
-                v[kg] = (valid && in_tile) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[it][kg] = (valid && s < nslot) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (in_tile) {
+        }
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int s = (it * (TC5_THREADS / 32) + warp) * 8 + sl;
+            if (s < nslot) {
 #pragma unroll
                 for (int kg = 0; kg < KG; ++kg) {
-                    uint4 r = make_uint4(f2tf32(v[kg].x), f2tf32(v[kg].y), f2tf32(v[kg].z), f2tf32(v[kg].w));
+                    uint4 r = make_uint4(f2tf32(v[it][kg].x), f2tf32(v[it][kg].y), f2tf32(v[it][kg].z), f2tf32(v[it][kg].w));
                     *reinterpret_cast<uint4*>(sA + ((size_t)(kg * 4 + kcl) * nslot + s) * 4) = r;
                 }
             }
@@ -251,6 +257,7 @@ int launch(const char* name, const In& in, const Epi& epi, const float* w_umma, 
     const Geometry g = make_geometry(ks, dil, Wout);
     const size_t smem = smem_bytes<CINP, NB>(g);
     IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
+    IMVS_REQUIRE(g.nslot <= 7 * 64, "%s: tile of %d slots exceeds the staging pattern", name, g.nslot);
     auto kern = tc5_conv_kernel<CINP, NB, In, Epi>;
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
