@@ -38,17 +38,16 @@ __device__ __forceinline__ void load_group(const float* __restrict__ p, float (&
 // with the zero-padding of grid_sample folded in (weight 0 for taps outside the map), so that all
 // taps can be loaded unconditionally from in-bounds addresses -- no branches, loads issue back to back.
 struct TapSet {
-    int o00;        // (y0c * Wf + x0c)
-    int flags;      // bit0: x step (0/1), bit1: y step (0/1)
-    float w00, w01, w10, w11;
+    int o00, o01, o10, o11;     // element offsets of the 4 (clamped) taps inside one view: (y*Wf + x) * C
+    float w00, w01, w10, w11;   // bilinear weights, 0 for taps outside the map
 };
 
-__device__ __forceinline__ TapSet make_tapset(const Tap& tp, int Wf, int Hf) {
+__device__ __forceinline__ TapSet make_tapset(const Tap& tp, int Wf, int Hf, int C) {
     TapSet ts;
     const int x0c = min(max(tp.x0, 0), Wf - 1), x1c = min(max(tp.x0 + 1, 0), Wf - 1);
     const int y0c = min(max(tp.y0, 0), Hf - 1), y1c = min(max(tp.y0 + 1, 0), Hf - 1);
-    ts.o00 = y0c * Wf + x0c;
-    ts.flags = (x1c - x0c) | ((y1c - y0c) << 1);
+    ts.o00 = (y0c * Wf + x0c) * C; ts.o01 = (y0c * Wf + x1c) * C;
+    ts.o10 = (y1c * Wf + x0c) * C; ts.o11 = (y1c * Wf + x1c) * C;
     const float gx = 1.f - tp.fx, gy = 1.f - tp.fy;
     ts.w00 = (tp.mask & 1u) ? gx * gy : 0.f;
     ts.w01 = (tp.mask & 2u) ? tp.fx * gy : 0.f;
@@ -57,15 +56,23 @@ __device__ __forceinline__ TapSet make_tapset(const Tap& tp, int Wf, int Hf) {
     return ts;
 }
 
-__device__ __forceinline__ TapSet shfl_tapset(const TapSet& ts, int src) {
-    TapSet r;
-    r.o00 = __shfl_sync(0xffffffffu, ts.o00, src);
-    r.flags = __shfl_sync(0xffffffffu, ts.flags, src);
-    r.w00 = __shfl_sync(0xffffffffu, ts.w00, src);
-    r.w01 = __shfl_sync(0xffffffffu, ts.w01, src);
-    r.w10 = __shfl_sync(0xffffffffu, ts.w10, src);
-    r.w11 = __shfl_sync(0xffffffffu, ts.w11, src);
-    return r;
+// Owner lanes publish their tap set (+ view weight) in shared memory; every lane of the slot then reads
+// it back as three broadcast 16-byte loads (cheaper than seven shuffles, and no per-lane offset math).
+struct __align__(16) TapRecord { int4 off; float4 w; float4 extra; };     // extra.x = view weight
+
+__device__ __forceinline__ void publish_tapset(TapRecord* rec, const TapSet& ts, float wv) {
+    rec->off = make_int4(ts.o00, ts.o01, ts.o10, ts.o11);
+    rec->w = make_float4(ts.w00, ts.w01, ts.w10, ts.w11);
+    rec->extra = make_float4(wv, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ TapSet read_tapset(const TapRecord* rec, float& wv) {
+    const int4 o = rec->off;
+    const float4 w = rec->w;
+    wv = rec->extra.x;
+    TapSet ts;
+    ts.o00 = o.x; ts.o01 = o.y; ts.o10 = o.z; ts.o11 = o.w;
+    ts.w00 = w.x; ts.w01 = w.y; ts.w10 = w.z; ts.w11 = w.w;
+    return ts;
 }
 
 // the four taps of this lane's channel group (issued back to back), then interpolate and dot with
@@ -74,13 +81,11 @@ template <int CPG>
 struct TapLoads { float t00[CPG], t01[CPG], t10[CPG], t11[CPG]; };
 
 template <int CPG>
-__device__ __forceinline__ void issue_taps(TapLoads<CPG>& L, const float* __restrict__ fea_view_g, int C, int Wf, const TapSet& ts) {
-    const float* p00 = fea_view_g + (ptrdiff_t)ts.o00 * C;
-    const int dx = (ts.flags & 1) * C, dy = ((ts.flags >> 1) & 1) * Wf * C;
-    load_group<CPG>(p00, L.t00);
-    load_group<CPG>(p00 + dx, L.t01);
-    load_group<CPG>(p00 + dy, L.t10);
-    load_group<CPG>(p00 + dy + dx, L.t11);
+__device__ __forceinline__ void issue_taps(TapLoads<CPG>& L, const float* __restrict__ fea_view_g, const TapSet& ts) {
+    load_group<CPG>(fea_view_g + ts.o00, L.t00);
+    load_group<CPG>(fea_view_g + ts.o01, L.t01);
+    load_group<CPG>(fea_view_g + ts.o10, L.t10);
+    load_group<CPG>(fea_view_g + ts.o11, L.t11);
 }
 
 template <int CPG>
@@ -94,7 +99,7 @@ __device__ __forceinline__ float finish_taps(const TapLoads<CPG>& L, const TapSe
         a = fmaf(L.t11[i], ts.w11, a);
         dot = fmaf(a, ref[i], dot);
     }
-    return dot / (float)CPG;
+    return dot * (1.0f / (float)CPG);     // exact for 2 and 4 channels per group, <= 1 ulp for 6
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -110,6 +115,7 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
                      int dsplit) {
     constexpr int CPG = 6, C = 48;
     __shared__ float sP[IMVS_MAX_VIEWS * 12];
+    __shared__ TapRecord sTap[8][4][8];          // [warp][slot][view of the current chunk]
     const int S = V - 1;
     const int b = blockIdx.z / dsplit, dpart = blockIdx.z % dsplit;
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = rt3[(size_t)b * S * 12 + i];
@@ -124,6 +130,8 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
     const int c_begin = (chunks * dpart) / dsplit, c_end = (chunks * (dpart + 1)) / dsplit;
     const int x_begin = blockIdx.x * INIT_TPX, x_end = min(x_begin + INIT_TPX, W3);
     const float* ref_view = fea3 + (size_t)(b * V) * P3 * C;
+    const size_t view_stride = (size_t)P3 * C;
+    const float* src_base = fea3 + (size_t)(b * V + 1) * view_stride + g * CPG;      // source view 0, this lane's group
 
     for (int x = x_begin; x < x_end; ++x) {
         const int p = y * W3 + x;
@@ -140,16 +148,19 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
                 tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
                 if (v0 + g < S && dvalid)
                     tp = project_tap(sP + (v0 + g) * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
-                const TapSet mine = make_tapset(tp, W3, H3);
+                __syncwarp();
+                publish_tapset(&sTap[warp][slot][g], make_tapset(tp, W3, H3, C), 0.f);
+                __syncwarp();
                 const int nv = min(8, S - v0);
                 for (int j0 = 0; j0 < nv; j0 += 2) {          // two views per batch: 8 x 3 float2 loads in flight
                     TapSet ts[2];
                     TapLoads<CPG> L[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        ts[u] = shfl_tapset(mine, (lane & 24) | min(j0 + u, 7));
+                        float unused;
+                        ts[u] = read_tapset(&sTap[warp][slot][min(j0 + u, 7)], unused);
                         const int v = min(v0 + j0 + u, S - 1);
-                        issue_taps<CPG>(L[u], fea3 + (size_t)(b * V + 1 + v) * P3 * C + g * CPG, C, W3, ts[u]);
+                        issue_taps<CPG>(L[u], src_base + (size_t)v * view_stride, ts[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -187,7 +198,7 @@ struct IterParams {
 // MODE: how the reference-view feature of this level is brought to level-2 resolution
 // (itermvs.py:95-98): 0 same, 1 F.interpolate(x0.5) == 2x2 mean, 2 F.interpolate(x2) bilinear.
 template <int CPG, int R, int MODE>
-__device__ __forceinline__ void iter_level(const IterParams& prm, const float* sP, int b, int y, int x_begin,
+__device__ __forceinline__ void iter_level(const IterParams& prm, const float* sP, TapRecord (*sTap)[8], int b, int y, int x_begin,
                                            int x_end, int slice_base, float o0, float o1, float o2, float o3) {
     constexpr int C = CPG * 8;
     constexpr int PPS = 4 / R;     // pixels per warp step
@@ -199,7 +210,9 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
     const int Wf = MODE == 1 ? W2 * 2 : (MODE == 2 ? W2 / 2 : W2);
     const float sx = (float)((double)Wf / (double)W2), sy = (float)((double)Hf / (double)H2);   // module.py:95-96
     const float* fea = prm.fea[MODE == 1 ? 0 : (MODE == 0 ? 1 : 2)];
-    const float* ref_view = fea + (size_t)(b * V) * Hf * Wf * C + g * CPG;
+    const size_t view_stride = (size_t)Hf * Wf * C;
+    const float* ref_view = fea + (size_t)(b * V) * view_stride + g * CPG;
+    const float* src_base = ref_view + view_stride;                                   // source view 0, this lane's group
     const float* smp = prm.samples[MODE == 1 ? 0 : (MODE == 0 ? 1 : 2)];
     const float inv_min = smp ? 0.f : 1.0f / prm.depth_min[b], inv_max = smp ? 0.f : 1.0f / prm.depth_max[b];
     const float off = (r == 0 ? o0 : r == 1 ? o1 : r == 2 ? o2 : o3) * (1.0f / 256.0f);   // itermvs.py:229,290
@@ -255,7 +268,9 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
                 tp = project_tap(sP + (v0 + g) * 12, (float)xc * sx, (float)y * sy, depth, (float)W2, (float)H2, Wf, Hf);
                 wv = ldg(prm.vw2 + ((size_t)b * S + v0 + g) * P2 + p);
             }
-            const TapSet mine = make_tapset(tp, Wf, Hf);
+            __syncwarp();
+            publish_tapset(&sTap[slot][g], make_tapset(tp, Wf, Hf, C), wv);
+            __syncwarp();
             const int nv = min(8, S - v0);
             for (int j0 = 0; j0 < nv; j0 += VG) {
                 TapSet ts[VG];
@@ -263,11 +278,9 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
                 float wj[VG];
 #pragma unroll
                 for (int u = 0; u < VG; ++u) {
-                    const int src = (lane & 24) | min(j0 + u, 7);
-                    ts[u] = shfl_tapset(mine, src);
-                    wj[u] = __shfl_sync(0xffffffffu, wv, src);          // 0 for views >= S
+                    ts[u] = read_tapset(&sTap[slot][min(j0 + u, 7)], wj[u]);          // weight 0 for views >= S
                     const int v = min(v0 + j0 + u, S - 1);
-                    issue_taps<CPG>(L[u], fea + (size_t)(b * V + 1 + v) * Hf * Wf * C + g * CPG, C, Wf, ts[u]);
+                    issue_taps<CPG>(L[u], src_base + (size_t)v * view_stride, ts[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < VG; ++u) {
@@ -285,6 +298,7 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
 
 __global__ void __launch_bounds__(256, 3) warpcorr_iter_kernel(const IterParams prm) {
     __shared__ float sP[IMVS_MAX_VIEWS * 12];
+    __shared__ TapRecord sTapAll[8][4][8];       // [warp][slot][view of the current chunk]
     const int b = blockIdx.z / 3, lvl = blockIdx.z % 3;
     const int S = prm.V - 1;
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = prm.rt[lvl][(size_t)b * S * 12 + i];
@@ -295,9 +309,10 @@ __global__ void __launch_bounds__(256, 3) warpcorr_iter_kernel(const IterParams 
     const int x_begin = blockIdx.x * ITER_TPX, x_end = min(x_begin + ITER_TPX, prm.W2);
     if (x_begin >= x_end) return;
     // itermvs.py:231-235
-    if (lvl == 0)      iter_level<2, 4, 1>(prm, sP, b, y, x_begin, x_end, 0, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
-    else if (lvl == 1) iter_level<4, 4, 0>(prm, sP, b, y, x_begin, x_end, 4, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
-    else               iter_level<6, 2, 2>(prm, sP, b, y, x_begin, x_end, 8, -32.f, 32.f, 0.f, 0.f);
+    TapRecord (*sTap)[8] = sTapAll[warp];
+    if (lvl == 0)      iter_level<2, 4, 1>(prm, sP, sTap, b, y, x_begin, x_end, 0, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
+    else if (lvl == 1) iter_level<4, 4, 0>(prm, sP, sTap, b, y, x_begin, x_end, 4, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
+    else               iter_level<6, 2, 2>(prm, sP, sTap, b, y, x_begin, x_end, 8, -32.f, 32.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
