@@ -296,7 +296,7 @@ __device__ __forceinline__ void iter_level(const IterParams& prm, const float* s
     }
 }
 
-__global__ void __launch_bounds__(256, 3) warpcorr_iter_kernel(const IterParams prm) {
+__global__ void __launch_bounds__(256, 4) warpcorr_iter_kernel(const IterParams prm) {
     __shared__ float sP[IMVS_MAX_VIEWS * 12];
     __shared__ TapRecord sTapAll[8][4][8];       // [warp][slot][view of the current chunk]
     const int b = blockIdx.z / 3, lvl = blockIdx.z % 3;

@@ -78,3 +78,51 @@ def profile_stages(fn, capacity: int = 4096):
         _lib.check(rc, "profile_end")
     n = min(-rc, capacity)
     return [(STAGE_NAMES[tags[i]], float(ms[i])) for i in range(n)]
+
+
+class StreamingPipeline:
+    """Serving loop from pinned HOST buffers with two graph slots: the H2D copy of sample k+1 (copy
+    engine 1) and the D2H copy of result k-1 (copy engine 2) overlap the graph replay of sample k.
+
+        sp = StreamingPipeline(model, imgs, proj, dmin, dmax)        # device sample, shapes only
+        sp.submit(host_imgs, host_proj, host_dmin, host_dmax, out_depth_pinned, out_conf_pinned)   # per sample
+        sp.drain()                                                   # all results are in their host buffers
+    """
+
+    def __init__(self, model, imgs, proj_matrices, depth_min, depth_max):
+        dev = imgs["level_0"].device
+        self.dev = dev
+        self.slots = [GraphedPipeline(model, imgs, proj_matrices, depth_min, depth_max) for _ in range(2)]
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        main = torch.cuda.current_stream(dev)
+        for e in self.ev_done + self.ev_out:
+            e.record(main)
+
+    def submit(self, imgs, proj_matrices, depth_min, depth_max, out_depth, out_conf):
+        s = self.k & 1
+        slot = self.slots[s]
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(self.ev_done[s])          # slot's previous replay has consumed its inputs
+            slot.load_inputs(imgs, proj_matrices, depth_min, depth_max)
+            self.ev_in[s].record(self.h2d)
+        main.wait_event(self.ev_in[s])
+        main.wait_event(self.ev_out[s])                    # slot's previous outputs have left the device
+        out = slot.replay()
+        self.ev_done[s].record(main)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.ev_done[s])
+            out_depth.copy_(out["depths_upsampled"], non_blocking=True)
+            out_conf.copy_(out["confidence_upsampled"], non_blocking=True)
+            self.ev_out[s].record(self.d2h)
+        self.k += 1
+
+    def drain(self):
+        main = torch.cuda.current_stream(self.dev)
+        for e in self.ev_out:
+            main.wait_event(e)
