@@ -48,9 +48,11 @@ int imvs_abi_version(void);
 const char* imvs_last_error(void);
 long long imvs_launches_total(void);
 
-/* Tensor-core convolution precision: 1 = single-pass TF32 (what the reference's own cuDNN path uses on
- * Ampere+ GPUs, torch.backends.cudnn.allow_tf32 = True by default), 3 = error-compensated 3-pass
- * TF32 split (fp32-grade).  Process-wide; default 3. */
+/* Tensor-core convolution precision ("mode"): 1 = single-pass TF32 (what the reference's own cuDNN path
+ * uses on Ampere+ GPUs, torch.backends.cudnn.allow_tf32 = True by default), 3 = error-compensated
+ * 3-product TF32 split (fp32-grade, relative 2^-21), 4 = the same 3-product compensation on the FP16
+ * tensor-core path (x = fp16 hi + fp16 lo: 22 bits for |x| < 65504, absolute floor 2^-25; twice the
+ * TF32 MMA rate).  Process-wide; default 4. */
 int imvs_set_conv_passes(int passes);
 int imvs_get_conv_passes(void);
 /* tcgen05/TMEM kernels for the 32..64-channel stride-1 convolutions in the 1-pass TF32 mode (default on).
@@ -64,6 +66,8 @@ typedef struct imvs_wpair {      /* packed conv weight [tap][CinP][CoutP] */
     const float* fp32;           /* plain fp32: the 3-pass mode splits hi/lo in registers */
     const float* umma;           /* TF32-rounded, tcgen05 K-major canonical order [cout block][tap][CinP/4][NB][4]
                                     with NB = min(CoutP, 64); may be NULL (then the mma.sync kernels run) */
+    const void* f16x3;           /* fp16 hi/lo split for mode 4: [tap][CinK/2][CoutP] of 8-byte entries
+                                    {half2 hi(k, k+1), half2 lo(k, k+1)}, CinK = CinP rounded up to 16 (zeros) */
 } imvs_wpair;
 
 typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */

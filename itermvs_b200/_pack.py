@@ -50,14 +50,36 @@ def pack_umma(w_tf32: Tensor) -> Tensor:
     return x.permute(3, 0, 1, 4, 2).contiguous()                     # [cb][tap][kc][n][k4]
 
 
+def pack_f16x3(w: Tensor) -> Tensor:
+    """[tap][CinP][CoutP] fp32 -> [tap][CinK/2][CoutP][2] int32: per channel pair (k, k+1) and cout the
+    half2 of the fp16 roundings (k in the low 16 bits) and the half2 of the fp16-rounded remainders.
+    CinK = CinP rounded up to 16 (zero rows).  Values beyond +-65504 saturate like the kernel's split."""
+    taps, cinp, coutp = w.shape
+    cink = (cinp + 15) // 16 * 16
+    x = torch.zeros(taps, cink, coutp, device=w.device, dtype=torch.float32)
+    x[:, :cinp] = w
+    hi = x.clamp(-65504.0, 65504.0).half()
+    lo = (x - hi.float()).clamp(-65504.0, 65504.0).half()
+
+    def pairs(h):   # [tap][CinK][CoutP] fp16 -> [tap][CinK/2][CoutP] int32 (k even in the low half)
+        return h.reshape(taps, cink // 2, 2, coutp).permute(0, 1, 3, 2).contiguous().view(torch.int32).squeeze(-1)
+
+    return torch.stack([pairs(hi), pairs(lo)], dim=-1).contiguous()
+
+
+def _packs(out: Tensor):
+    t, f = split_tf32(out)
+    return t, f, pack_umma(t), pack_f16x3(f)
+
+
 def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0):
-    """nn.Conv2d weight [Cout,Cin,kh,kw] -> (tf32, fp32, umma): [kh*kw][CinP][CoutP] twice + the tcgen05 order."""
+    """nn.Conv2d weight [Cout,Cin,kh,kw] -> (tf32, fp32, umma, f16x3): [kh*kw][CinP][CoutP] twice, the
+    tcgen05 order and the fp16 hi/lo split."""
     co, cin, kh, kw = w.shape
     cinp, coutp = cinp or _pad8(cin), coutp or _pad8(co)
     out = torch.zeros(kh * kw, cinp, coutp, device=w.device, dtype=torch.float32)
     out[:, :cin, :co] = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, cin, co)
-    t, f = split_tf32(out)
-    return t, f, pack_umma(t)
+    return _packs(out)
 
 
 def pack_mma_tconv(w: Tensor) -> Tuple[Tensor, Tensor]:
@@ -65,8 +87,7 @@ def pack_mma_tconv(w: Tensor) -> Tuple[Tensor, Tensor]:
     cin, co, kh, kw = w.shape
     out = torch.zeros(kh * kw, _pad8(cin), _pad8(co), device=w.device, dtype=torch.float32)
     out[:, :cin, :co] = w.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cin, co)
-    t, f = split_tf32(out)
-    return t, f, pack_umma(t)
+    return _packs(out)
 
 
 def pack_fc(w: Tensor) -> Tensor:
@@ -87,7 +108,7 @@ class _Holder:
 
     def pair(self, hl) -> _lib.WPair:
         self.keep.extend(hl)
-        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if len(hl) > 2 and hl[2] is not None else None)
+        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if hl[2] is not None else None, hl[3].data_ptr())
 
     def ptr(self, t: Tensor) -> int:
         self.keep.append(t)

@@ -17,9 +17,17 @@
 //     PASSES = 3: error-compensated split computed in registers from the fp32 operands
 //                 (x_hi = x & ~0x1fff, x_lo = x - x_hi):  lo*hi + hi*lo + hi*hi  -> fp32-grade
 //                 (relative error ~2^-21), no extra shared memory.
+//     PASSES = 4: the same 3-product compensation on the FP16 tensor-core path (mma.sync.m16n8k16,
+//                 twice the TF32 rate): x_hi = fp16(x), x_lo = fp16(x - x_hi) -> 22 significant bits
+//                 for |x| < 65504 (saturating conversion above), absolute floor 2^-25 below 2^-14.
+//                 Activations are split in registers from the fp32 tile (splitting the tile once in
+//                 shared memory was measured slower: the extra pass costs more than the ALU it saves);
+//                 weights come pre-split from the host ([slice][CinK/2][Cout] uint2).
 // * the stencil is a runtime tap table (up to 4 variants per launch), so regular, dilated, strided
 //   and the four output parities of a transposed convolution share one kernel / one launch.
 #pragma once
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -104,6 +112,20 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                        uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// (v.x, v.y) = channels (k, k+1) -> hi = half2(fp16(v.x), fp16(v.y)) [k in the low half], lo = the remainder
+__device__ __forceinline__ void split_f16(float2 v, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y - hf.y), "f"(v.x - hf.x));
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     const int bytes = valid ? 16 : 0;            // src-size 0 -> the 16 destination bytes are zero-filled
@@ -122,13 +144,18 @@ struct MmaCfg {
     static constexpr int TH = WARPS * MT;
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int NT = NB / 8;                       // n-tiles per CTA
-    static constexpr int CP = CINP + 4;                     // smem channel pitch (floats): CP/4 odd -> conflict-free A loads
-    static constexpr int NP = NB + 8 + (NB == 8 ? 8 : 0);   // smem cout pitch: = 8 or 24 mod 32 -> conflict-free B loads
-    static constexpr int KSTEPS = CINP / 8;
-    static constexpr int WBUF = CINP * NP;                  // floats per weight stage
+    static constexpr bool F16 = PASSES == 4;
+    static constexpr int CINK = F16 ? (CINP + 15) / 16 * 16 : CINP;   // K extent staged in smem (zero-filled beyond CINP)
+    // smem channel pitch (floats): TF32: CP/4 odd -> conflict-free LDS.32 A loads; FP16: CP = 8 or 24 mod 32
+    // -> conflict-free LDS.64 A loads
+    static constexpr int CP = F16 ? CINK + 8 : CINP + 4;
+    // smem cout pitch: TF32: floats, = 8 or 24 mod 32; FP16: uint2 (hi, lo) units, 2*NP = 8 or 24 mod 32
+    static constexpr int NP = F16 ? NB + 4 : NB + 8 + (NB == 8 ? 8 : 0);
+    static constexpr int KSTEPS = F16 ? CINK / 16 : CINP / 8;
+    static constexpr int WBUF = CINK * NP;                  // floats per weight stage (FP16: CINK/2 rows of NP uint2)
     static constexpr int RING = 3;
     static_assert(CINP % 8 == 0 && NB % 8 == 0, "channel padding");
-    static_assert(PASSES == 1 || PASSES == 3, "PASSES");
+    static_assert(PASSES == 1 || PASSES == 3 || PASSES == 4, "PASSES");
     static size_t smem_bytes(const TapTables& tt) {
         size_t tile = 0, taps = 0;
         for (int v = 0; v < tt.count; ++v) {
@@ -181,7 +208,8 @@ struct InNCHW3 {            // 3-channel planar image [N][3][H][W] -> channels (
 };
 
 struct MmaWeightSel {       // image n of a batched launch picks one of up to three weight sets
-    const float* w[3];      // [slice][CINP][cout_total]: TF32-rounded (PASSES 1) or plain fp32 (PASSES 3)
+    const float* w[3];      // [slice][CINP][cout_total]: TF32-rounded (PASSES 1) or plain fp32 (PASSES 3);
+                            // PASSES 4: [slice][CINK/2][cout_total] uint2 = (hi half2, lo half2) of a channel pair
     int period, split1, split2;
     __device__ __forceinline__ const float* pick(int n) const {
         const int r = n % period;
@@ -214,26 +242,35 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
     const int ntaps = taps.n;
 
     auto issue_weights = [&](int tap, int buf) {
-        const float* src = wg + ((size_t)taps.widx[tap] * CINP) * cout_total + cb * NB;
         float* dst = sW + buf * Cfg::WBUF;
-        constexpr int Q = NB / 4;
-        for (int i = tid; i < CINP * Q; i += Cfg::THREADS) {
-            const int k = i / Q, q = i % Q;
-            cp_async16(dst + k * NP + 4 * q, src + (size_t)k * cout_total + 4 * q, true);
+        if constexpr (Cfg::F16) {      // rows = channel pairs, NB (hi, lo) uint2 per row
+            const float* src = wg + 2 * (((size_t)taps.widx[tap] * (Cfg::CINK / 2)) * cout_total + cb * NB);
+            constexpr int Q = NB / 2;
+            for (int i = tid; i < (Cfg::CINK / 2) * Q; i += Cfg::THREADS) {
+                const int k = i / Q, q = i % Q;
+                cp_async16(dst + 2 * (k * NP) + 4 * q, src + 2 * ((size_t)k * cout_total) + 4 * q, true);
+            }
+        } else {
+            const float* src = wg + ((size_t)taps.widx[tap] * CINP) * cout_total + cb * NB;
+            constexpr int Q = NB / 4;
+            for (int i = tid; i < CINP * Q; i += Cfg::THREADS) {
+                const int k = i / Q, q = i % Q;
+                cp_async16(dst + k * NP + 4 * q, src + (size_t)k * cout_total + 4 * q, true);
+            }
         }
     };
 
     {   // input tile (with halo)
         const int iy0 = oy0 * Cfg::STRIDE + taps.dy_min, ix0 = ox0 * Cfg::STRIDE + taps.dx_min;
-        constexpr int C4 = CINP / 4;
+        constexpr int C4 = Cfg::CINK / 4;
         const int total = taps.IH * taps.IW * C4;
         for (int i = tid; i < total; i += Cfg::THREADS) {
             const int slot = i / C4, c4 = i % C4;
             const int iy = iy0 + slot / taps.IW, ix = ix0 + slot % taps.IW;
             if constexpr (In::kAsync) {
                 bool valid;
-                const float* src = in.ptr4(n, iy, ix, c4, valid);
-                cp_async16(sA + (size_t)slot * CP + 4 * c4, src, valid);
+                const float* src = in.ptr4(n, iy, ix, c4 < CINP / 4 ? c4 : 0, valid);
+                cp_async16(sA + (size_t)slot * CP + 4 * c4, src, valid && c4 < CINP / 4);
             } else {
                 *reinterpret_cast<float4*>(sA + (size_t)slot * CP + 4 * c4) = in.load4(n, iy, ix, c4);
             }
@@ -277,6 +314,31 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
             slot0[r] = (row * taps.IW + g * Cfg::STRIDE + rx) * CP;
             slot1[r] = (row * taps.IW + (g + 8) * Cfg::STRIDE + rx) * CP;
         }
+        if constexpr (Cfg::F16) {
+            const uint2* wb2 = reinterpret_cast<const uint2*>(wb);
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                const int k0 = ks * 16 + 2 * t;
+                uint32_t a[MT][4], al[MT][4];
+#pragma unroll
+                for (int r = 0; r < MT; ++r) {
+                    split_f16(*reinterpret_cast<const float2*>(sA + slot0[r] + k0), a[r][0], al[r][0]);
+                    split_f16(*reinterpret_cast<const float2*>(sA + slot1[r] + k0), a[r][1], al[r][1]);
+                    split_f16(*reinterpret_cast<const float2*>(sA + slot0[r] + k0 + 8), a[r][2], al[r][2]);
+                    split_f16(*reinterpret_cast<const float2*>(sA + slot1[r] + k0 + 8), a[r][3], al[r][3]);
+                }
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const uint2 w0 = wb2[(ks * 8 + t) * NP + 8 * j + g], w1 = wb2[(ks * 8 + t + 4) * NP + 8 * j + g];
+#pragma unroll
+                    for (int r = 0; r < MT; ++r) {
+                        mma_f16(acc[r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0.x, w1.x);
+                        mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0.y, w1.y);
+                        mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0.x, w1.x);
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
             const int k0 = ks * 8;
@@ -311,6 +373,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
                     for (int r = 0; r < MT; ++r) mma_tf32(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], b0, b1);
                 }
             }
+        }
         }
     }
 
@@ -364,6 +427,10 @@ int mma_conv(const char* name, const In& in, const Epi& epi, const WSets& ws, co
              int cout_total, int Hout, int Wout, int ncb, cudaStream_t st) {
     MmaWeightSel sel;
     sel.period = ws.period; sel.split1 = ws.split1; sel.split2 = ws.split2;
+    if (conv_passes() == 4) {
+        for (int i = 0; i < 3; ++i) sel.w[i] = static_cast<const float*>(ws.w[i].f16x3);
+        return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 4, WALL>>(name, in, epi, sel, tabs, N, cout_total, Hout, Wout, ncb, st);
+    }
     if (conv_passes() == 3) {
         for (int i = 0; i < 3; ++i) sel.w[i] = ws.w[i].fp32;
         return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 3, WALL>>(name, in, epi, sel, tabs, N, cout_total, Hout, Wout, ncb, st);

@@ -17,7 +17,7 @@ int fail(const char* fmt, ...) {
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launches_total() { return g_launches; }
-static int g_conv_passes = 3;
+static int g_conv_passes = 4;
 int conv_passes() { return g_conv_passes; }
 static int g_tc5 = 1;
 int tc5_enabled() { return g_tc5; }
@@ -202,7 +202,8 @@ extern "C" int imvs_abi_version(void) { return IMVS_ABI_VERSION; }
 extern "C" const char* imvs_last_error(void) { return err_buf(); }
 extern "C" long long imvs_launches_total(void) { return launches_total(); }
 extern "C" int imvs_set_conv_passes(int passes) {
-    IMVS_REQUIRE(passes == 1 || passes == 3, "set_conv_passes: passes must be 1 (TF32) or 3 (3xTF32, fp32-grade), got %d", passes);
+    IMVS_REQUIRE(passes == 1 || passes == 3 || passes == 4,
+                 "set_conv_passes: mode must be 1 (TF32), 3 (3xTF32, fp32-grade) or 4 (3xFP16 split, fp32-grade), got %d", passes);
     g_conv_passes = passes;
     return 0;
 }

@@ -36,7 +36,7 @@ def test_host_side_validation_without_gpu():
         assert L.imvs_forward_workspace_bytes(C.byref(bad)) == 0
         assert len(L.imvs_last_error()) > 0
     assert L.imvs_featurenet_workspace_bytes(5, 512, 640) > 0
-    assert L.imvs_get_conv_passes() == 3
+    assert L.imvs_get_conv_passes() == 4
 
 
 def test_tf32_split_and_packing(dtu_weights):
@@ -51,16 +51,60 @@ def test_tf32_split_and_packing(dtu_weights):
     assert torch.equal(_pack.round_tf32(t), torch.tensor([1.0 + 2 ** -10, -(1.0 + 2 ** -10)]))
     # conv packing: [Cout,Cin,3,3] -> [9][CinP][CoutP]
     w = dtu_weights["iter_mvs.update.gru.convq.weight"]
-    hi, full, um = _pack.pack_mma_conv(w, cinp=48)
+    hi, full, um, f16 = _pack.pack_mma_conv(w, cinp=48)
     assert um.shape == (1, 9, 12, 32, 4) and torch.equal(um[0, 4, 3, 7], hi[4, 12:16, 7])
     assert hi.shape == (9, 48, 32)
     rec = full[:, :43, :].reshape(3, 3, 43, 32).permute(3, 2, 0, 1)
     assert torch.equal(rec, w)
     assert float(hi[:, 43:, :].abs().max()) == 0.0
     wt = dtu_weights["iter_mvs.evaluation.corr_conv1.0.conv3.weight"]          # ConvTranspose [Cin,Cout,3,3]
-    hi, full, _ = _pack.pack_mma_tconv(wt)
+    hi, full, _, _ = _pack.pack_mma_tconv(wt)
     assert hi.shape == (9, 32, 16)
     assert torch.equal(full[4], wt[:, :, 1, 1])
+
+
+def test_fp16_split_packing(dtu_weights):
+    """mode 4 weights: [tap][CinK/2][CoutP][{hi,lo}] int32, each a half2 of channels (k, k+1), k in the low half;
+    hi + lo reproduces the fp32 weight to 2^-22 relative (2^-25 absolute floor), saturating beyond fp16 range."""
+    from itermvs_b200 import _pack
+    w = torch.randn(9, 24, 16) * torch.logspace(-5, 2, 16)
+    w[0, 0, 0] = 1e6
+    p = _pack.pack_f16x3(w)
+    assert p.shape == (9, 16, 16, 2) and p.dtype == torch.int32            # CinK = 32
+    halves = p.view(torch.float16).reshape(9, 16, 16, 2, 2)                # [...][hi|lo][k even|k odd]
+    rec = (halves[..., 0, :].float() + halves[..., 1, :].float()).permute(0, 1, 3, 2).reshape(9, 32, 16)
+    assert float(rec[:, 24:].abs().max()) == 0.0
+    assert float(rec[0, 0, 0]) == 65504.0 + 65504.0                        # saturated, finite
+    ww, rr = w.clone(), rec[:, :24].clone()
+    ww[0, 0, 0] = rr[0, 0, 0] = 0.0
+    err = (rr - ww).abs()
+    assert bool((err <= ww.abs() * 2.0 ** -21 + 2.0 ** -24).all())
+    # a real layer: the packed pair order matches the fp32 packing
+    _, full, _, f16 = _pack.pack_mma_conv(dtu_weights["iter_mvs.update.gru.convq.weight"], cinp=48)
+    h = f16.view(torch.float16).reshape(9, 24, 32, 2, 2)
+    assert torch.equal(h[4, 5, 7, 0, 1], full[4, 11, 7].half()) and torch.equal(h[4, 5, 7, 0, 0], full[4, 10, 7].half())
+
+
+def test_fp16_split_product_accuracy():
+    """The arithmetic behind mode 4, emulated in torch: sum_k (a_hi b_hi + a_hi b_lo + a_lo b_hi) with fp16
+    hi/lo parts (exact products, wide accumulation) against the exact dot product, over activation
+    scales from fp16-subnormal remainders to near the top of the fp16 range."""
+    g = torch.Generator().manual_seed(3)
+    K = 432
+    b = torch.randn(K, 64, generator=g) * 0.1
+    bh = b.half(); bl = (b - bh.float()).half()
+    for scale in (2.0 ** -16, 2.0 ** -12, 2.0 ** -6, 1.0, 2.0 ** 10, 2.0 ** 13):
+        a = torch.randn(256, K, generator=g) * scale
+        ah = a.clamp(-65504, 65504).half(); al = (a - ah.float()).half()     # cvt.rn.satfinite
+        d = lambda x: x.double()
+        got = d(ah) @ d(bh) + d(ah) @ d(bl) + d(al) @ d(bh)
+        ref = d(a) @ d(b)
+        denom = (d(a).abs() @ d(b).abs())               # forward-error scale of an fp32 dot product
+        rel = float(((got - ref).abs() / denom).max())
+        floor = 2.0 ** -25 * float(b.abs().sum(0).max()) / float(denom.min())   # absolute floor of the subnormal remainders
+        assert rel < 2.0 ** -20 + 2 * floor, (scale, rel, floor)
+        if scale >= 2.0 ** -6:
+            assert rel < 2.0 ** -20, (scale, rel)
 
 
 def test_bn_folding_matches_batchnorm(dtu_weights):

@@ -312,13 +312,37 @@ def test_single_pass_tf32_mode(dev, model, dtu_weights):
             out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
         torch.cuda.synchronize()
     finally:
-        _lib.set_conv_passes(3)
+        _lib.set_conv_passes(4)
     d, dref = out["depths_upsampled"].cpu(), want["depths_upsampled"]
     rel = ((d - dref).abs() / dref).numpy()
     print(f"TF32 single pass: depth rel err mean {rel.mean():.2e} median {np.median(rel):.2e} max {rel.max():.2e}, "
           f"px>1e-3: {100 * (rel > 1e-3).mean():.3f}%")
     assert np.median(rel) < 2e-4
     assert (rel > 1e-3).mean() < 0.05
+
+
+def test_3xtf32_mode_matches_default(dev, model, dtu_weights):
+    """mode 3 (3-product TF32 split) and the default mode 4 (3-product FP16 split) are both fp32-grade:
+    each within 1e-3 of the oracle everywhere, and within 1e-4 of each other."""
+    from itermvs_b200 import _lib
+    s = make_sample(640, 512, n_src=4, batch=1, seed=0, scene="plane")
+    want = O.pipeline_forward(dtu_weights, s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"], iteration=4)
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    outs = {}
+    assert _lib.get_conv_passes() == 4
+    try:
+        for mode in (4, 3):
+            _lib.set_conv_passes(mode)
+            with torch.no_grad():
+                outs[mode] = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))["depths_upsampled"].cpu()
+    finally:
+        _lib.set_conv_passes(4)
+    dref = want["depths_upsampled"]
+    for mode, d in outs.items():
+        rel = ((d - dref).abs() / dref).numpy()
+        print(f"mode {mode}: depth rel err mean {rel.mean():.2e} max {rel.max():.2e}")
+        assert rel.max() < 1e-3 and rel.mean() < 2e-6
+    assert float(((outs[3] - outs[4]).abs() / dref).max()) < 1e-4
 
 
 def test_error_behaviour(dev, model):
@@ -399,7 +423,7 @@ def test_tcgen05_path_matches_mma_sync(dev, stage_kats, model):
     finally:
         upd.return_probability = None
         L.imvs_set_tcgen05(1)
-        _lib.set_conv_passes(3)
+        _lib.set_conv_passes(4)
     print("tcgen05 vs mma.sync: gru max diff", maxerr(got_h, ref_h), "prob max diff", maxerr(got_p, ref_p))
     # identical TF32 products and accumulation order; the tcgen05 epilogue uses ex2.approx-based gates
     # (|err| ~1e-6 relative on the exponential), far below the TF32 operand rounding (5e-4)
@@ -411,5 +435,5 @@ def test_tcgen05_path_matches_mma_sync(dev, stage_kats, model):
     try:
         out = upd.gru(T(k["gru_h"]).to(dev), T(k["gru_x"]).to(dev))
     finally:
-        _lib.set_conv_passes(3)
+        _lib.set_conv_passes(4)
     assert maxerr(out, T(k["gru_out"])) < 5e-3

@@ -14,7 +14,7 @@ from itermvs_b200.synthetic import make_sample  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 w, h, s_ = (int(x) for x in (sys.argv[2:5] if len(sys.argv) >= 5 else (640, 512, 4)))
 from itermvs_b200 import _lib  # noqa: E402
-_lib.set_conv_passes(int(os.environ.get('IMVS_PASSES', '3')))
+_lib.set_conv_passes(int(os.environ.get('IMVS_PASSES', '4')))
 dev = torch.device("cuda:0")
 with np.load(os.path.join(ROOT, "tests", "golden", "dtu_weights.npz")) as z:
     weights = {k: torch.from_numpy(z[k]) for k in z.files}
