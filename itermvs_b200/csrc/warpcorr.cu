@@ -5,314 +5,422 @@
 //
 // Reference: models/module.py:68-125, models/itermvs.py:11-19, 45-69, 86-120, 289-293.
 //
-// Thread mapping (both kernels).  Features are channels-last, so one sampled tap is C contiguous
-// floats (64/128/192 B).  A warp is split into 4 "slots" of 8 lanes; lane g of a slot owns
-// correlation group g, i.e. channels [g*C/8, (g+1)*C/8) -- exactly one float2 / float4 / 3xfloat2
-// per tap, so a slot reads a tap as one fully used 64/128/192-byte segment and the group
-// reduction needs no shuffles.  The 4 slots are the 4 depth samples of ONE pixel (2 pixels x 2
-// samples at level 3): neighbouring hypotheses of a pixel land within ~a pixel of each other along
-// the epipolar line, so the four slots of a load instruction mostly hit the same 128-byte lines
-// (fewer L1 wavefronts than four different pixels would cost).  The sampling position of
-// (sample, view) is computed once -- by lane (slot, g = view) -- and broadcast with shuffles.
+// Structure (round-1 "v4").  The kernels are bound by the L1 data pipe (one 128-byte wavefront per
+// cycle per SM) and by instruction issue, not by HBM: every sample is a 4-tap gather of C contiguous
+// floats.  Both are attacked the same way:
+//   * two phases per warp.  Phase A: the 32 lanes compute 32 DIFFERENT (pixel, hypothesis, view)
+//     sampling positions (projection, 4 IEEE divisions, clamping, bilinear weights) and leave a 24-byte
+//     record per sample in shared memory.  Phase B: groups of 4/8 lanes walk the records and do
+//     nothing but loads and FMAs.  (v3 computed each position on a quarter of the lanes and re-derived
+//     four 64-bit addresses per tap.)
+//   * the taps of a record sit at FIXED offsets from one base (top-left tap clamped to
+//     [0, W-2] x [0, H-2]; the bilinear weights are permuted / zeroed to match, which also folds in
+//     grid_sample's zero padding), so a sample costs one address computation.
+//   * every load instruction reads 64 or 128 CONTIGUOUS bytes per sample.  At level 3 (48 channels,
+//     6 per correlation group) a lane therefore holds channel pairs {g, 8+g, 16+g} instead of "its"
+//     group; the per-pair partial sums are accumulated over the views (the aggregation is linear) and
+//     regrouped once per (pixel, hypothesis) with three shuffles.  v3 read 8-byte pieces at a 24-byte
+//     stride: 2 lines per instruction per sample, 3x the wavefronts.
+//   * one warp = 4 pixels x 3 levels, one block = 4 rows: 1 280 equal blocks at 640x512 instead of
+//     480 unequal ones (1.08 waves), 32 resident warps per SM.
 #include "common.cuh"
 #include "sampling.cuh"
+#include "warpcorr_v3.cuh"
+
+#include <cstdlib>
 
 namespace imvs {
 
-template <int CPG>
-__device__ __forceinline__ void load_group(const float* __restrict__ p, float (&v)[CPG]) {
-    if constexpr (CPG == 4) {
-        float4 t = ldg4(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < CPG / 2; ++i) {
-            float2 t = ldg2(p + 2 * i);
-            v[2 * i] = t.x; v[2 * i + 1] = t.y;
-        }
-    }
-}
+constexpr int WC_WARPS = 4;     // warps per block = rows of the pixel tile
+constexpr int WC_NPX = 4;       // consecutive pixels of a row handled by one warp
 
-// Sampling parameters of one (pixel, hypothesis, view), computed by the owner lane and broadcast:
-// clamped top-left tap offset, +1 steps (0 when clamped at the border) and the four bilinear weights
-// with the zero-padding of grid_sample folded in (weight 0 for taps outside the map), so that all
-// taps can be loaded unconditionally from in-bounds addresses -- no branches, loads issue back to back.
-struct TapSet {
-    int o00, o01, o10, o11;     // element offsets of the 4 (clamped) taps inside one view: (y*Wf + x) * C
-    float w00, w01, w10, w11;   // bilinear weights, 0 for taps outside the map
-};
-
-__device__ __forceinline__ TapSet make_tapset(const Tap& tp, int Wf, int Hf, int C) {
-    TapSet ts;
-    const int x0c = min(max(tp.x0, 0), Wf - 1), x1c = min(max(tp.x0 + 1, 0), Wf - 1);
-    const int y0c = min(max(tp.y0, 0), Hf - 1), y1c = min(max(tp.y0 + 1, 0), Hf - 1);
-    ts.o00 = (y0c * Wf + x0c) * C; ts.o01 = (y0c * Wf + x1c) * C;
-    ts.o10 = (y1c * Wf + x0c) * C; ts.o11 = (y1c * Wf + x1c) * C;
+// Phase-A result for one (pixel, hypothesis, view).  Taps are read at element offsets
+// off, off + C, off + pitch, off + pitch + C (pitch = Wf * C) with weights w.x .. w.w.
+__device__ __forceinline__ void make_record(const Tap& tp, int Wf, int Hf, int C, int view, float4& w, int& off) {
+    const int xb = min(max(tp.x0, 0), Wf - 2), yb = min(max(tp.y0, 0), Hf - 2);
     const float gx = 1.f - tp.fx, gy = 1.f - tp.fy;
-    ts.w00 = (tp.mask & 1u) ? gx * gy : 0.f;
-    ts.w01 = (tp.mask & 2u) ? tp.fx * gy : 0.f;
-    ts.w10 = (tp.mask & 4u) ? gx * tp.fy : 0.f;
-    ts.w11 = (tp.mask & 8u) ? tp.fx * tp.fy : 0.f;
-    return ts;
+    // weight of the loaded column xb / xb+1: column x0 carries gx, column x0+1 carries fx, columns outside
+    // the map carry nothing (grid_sample padding_mode='zeros').  Same for the rows.
+    const float wxa = tp.x0 == xb ? gx : (tp.x0 + 1 == xb ? tp.fx : 0.f);
+    const float wxb = tp.x0 == xb ? tp.fx : (tp.x0 == xb + 1 ? gx : 0.f);
+    const float wya = tp.y0 == yb ? gy : (tp.y0 + 1 == yb ? tp.fy : 0.f);
+    const float wyb = tp.y0 == yb ? tp.fy : (tp.y0 == yb + 1 ? gy : 0.f);
+    w = make_float4(wxa * wya, wxb * wya, wxa * wyb, wxb * wyb);
+    off = ((view * Hf + yb) * Wf + xb) * C;
 }
 
-// Owner lanes publish their tap set (+ view weight) in shared memory; every lane of the slot then reads
-// it back as three broadcast 16-byte loads (cheaper than seven shuffles, and no per-lane offset math).
-struct __align__(16) TapRecord { int4 off; float4 w; float4 extra; };     // extra.x = view weight
-
-__device__ __forceinline__ void publish_tapset(TapRecord* rec, const TapSet& ts, float wv) {
-    rec->off = make_int4(ts.o00, ts.o01, ts.o10, ts.o11);
-    rec->w = make_float4(ts.w00, ts.w01, ts.w10, ts.w11);
-    rec->extra = make_float4(wv, 0.f, 0.f, 0.f);
-}
-__device__ __forceinline__ TapSet read_tapset(const TapRecord* rec, float& wv) {
-    const int4 o = rec->off;
-    const float4 w = rec->w;
-    wv = rec->extra.x;
-    TapSet ts;
-    ts.o00 = o.x; ts.o01 = o.y; ts.o10 = o.z; ts.o11 = o.w;
-    ts.w00 = w.x; ts.w01 = w.y; ts.w10 = w.z; ts.w11 = w.w;
-    return ts;
+__device__ __forceinline__ float bilerp(float t00, float t01, float t10, float t11, const float4& w) {
+    float a = t00 * w.x;
+    a = fmaf(t01, w.y, a);
+    a = fmaf(t10, w.z, a);
+    return fmaf(t11, w.w, a);
 }
 
-// the four taps of this lane's channel group (issued back to back), then interpolate and dot with
-// the reference feature group: mean_c( warped_c * ref_c )  (itermvs.py:50-51)
-template <int CPG>
-struct TapLoads { float t00[CPG], t01[CPG], t10[CPG], t11[CPG]; };
-
-template <int CPG>
-__device__ __forceinline__ void issue_taps(TapLoads<CPG>& L, const float* __restrict__ fea_view_g, const TapSet& ts) {
-    load_group<CPG>(fea_view_g + ts.o00, L.t00);
-    load_group<CPG>(fea_view_g + ts.o01, L.t01);
-    load_group<CPG>(fea_view_g + ts.o10, L.t10);
-    load_group<CPG>(fea_view_g + ts.o11, L.t11);
-}
-
-template <int CPG>
-__device__ __forceinline__ float finish_taps(const TapLoads<CPG>& L, const TapSet& ts, const float (&ref)[CPG]) {
-    float dot = 0.f;
+// Level-3 regrouping: lane g of an 8-lane slot holds the partial sums of channel pairs g, 8+g, 16+g
+// (acc[k] <-> pair 8k+g); correlation group G is pairs 3G, 3G+1, 3G+2.  Three shuffles, each lane
+// supplying the register its reader needs.
+__device__ __forceinline__ float regroup48(const float (&acc)[3], int lane) {
+    const int g = lane & 7, slot_base = lane & ~7;
+    float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < CPG; ++i) {
-        float a = L.t00[i] * ts.w00;
-        a = fmaf(L.t01[i], ts.w01, a);
-        a = fmaf(L.t10[i], ts.w10, a);
-        a = fmaf(L.t11[i], ts.w11, a);
-        dot = fmaf(a, ref[i], dot);
+    for (int m = 0; m < 3; ++m) {
+        const int Gd = (3 * (g - m + 8)) & 7;          // the group whose pair 3*Gd+m lives in this lane
+        const int ks = (3 * Gd + m) >> 3;
+        const float mine = ks == 0 ? acc[0] : (ks == 1 ? acc[1] : acc[2]);
+        sum += __shfl_sync(0xffffffffu, mine, slot_base | ((3 * g + m) & 7));
     }
-    return dot * (1.0f / (float)CPG);     // exact for 2 and 4 channels per group, <= 1 ulp for 6
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2: init plane sweep at level 3 (C = 48), per-view group correlation.
-//   grid (ceil(W3/TPX), ceil(H3/8), B*DSPLIT), block 256 (8 warps = 8 rows)
-// ---------------------------------------------------------------------------------------------
-constexpr int INIT_TPX = 4;
-
-__global__ void __launch_bounds__(256)
-warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ rt3,
-                     const float* __restrict__ depth_min, const float* __restrict__ depth_max,
-                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D,
-                     int dsplit) {
-    constexpr int CPG = 6, C = 48;
-    __shared__ float sP[IMVS_MAX_VIEWS * 12];
-    __shared__ TapRecord sTap[8][4][8];          // [warp][slot][view of the current chunk]
-    const int S = V - 1;
-    const int b = blockIdx.z / dsplit, dpart = blockIdx.z % dsplit;
-    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = rt3[(size_t)b * S * 12 + i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = lane >> 3, g = lane & 7;
-    const int y = blockIdx.y * 8 + warp;
-    if (y >= H3) return;
-    const int P3 = H3 * W3;
-    const float inv_min = samples ? 0.f : 1.0f / depth_min[b], inv_max = samples ? 0.f : 1.0f / depth_max[b];
-    const int chunks = (D + 3) / 4;
-    const int c_begin = (chunks * dpart) / dsplit, c_end = (chunks * (dpart + 1)) / dsplit;
-    const int x_begin = blockIdx.x * INIT_TPX, x_end = min(x_begin + INIT_TPX, W3);
-    const float* ref_view = fea3 + (size_t)(b * V) * P3 * C;
-    const size_t view_stride = (size_t)P3 * C;
-    const float* src_base = fea3 + (size_t)(b * V + 1) * view_stride + g * CPG;      // source view 0, this lane's group
-
-    for (int x = x_begin; x < x_end; ++x) {
-        const int p = y * W3 + x;
-        float ref[CPG];
-        load_group<CPG>(ref_view + (size_t)p * C + g * CPG, ref);
-        for (int ch = c_begin; ch < c_end; ++ch) {
-            const int d = ch * 4 + slot;
-            const bool dvalid = d < D;
-            // itermvs.py:13-17 (or the caller's explicit hypotheses, Evaluation.forward's depth_sample)
-            const float depth = samples ? ldg(samples + ((size_t)b * D + (dvalid ? d : 0)) * P3 + p)
-                                        : 1.0f / (inv_max + ((float)d / (float)(D - 1)) * (inv_min - inv_max));
-            for (int v0 = 0; v0 < S; v0 += 8) {
-                Tap tp;
-                tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
-                if (v0 + g < S && dvalid)
-                    tp = project_tap(sP + (v0 + g) * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
-                __syncwarp();
-                publish_tapset(&sTap[warp][slot][g], make_tapset(tp, W3, H3, C), 0.f);
-                __syncwarp();
-                const int nv = min(8, S - v0);
-                for (int j0 = 0; j0 < nv; j0 += 2) {          // two views per batch: 8 x 3 float2 loads in flight
-                    TapSet ts[2];
-                    TapLoads<CPG> L[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        float unused;
-                        ts[u] = read_tapset(&sTap[warp][slot][min(j0 + u, 7)], unused);
-                        const int v = min(v0 + j0 + u, S - 1);
-                        issue_taps<CPG>(L[u], src_base + (size_t)v * view_stride, ts[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int v = v0 + j0 + u;
-                        const float c = finish_taps<CPG>(L[u], ts[u], ref);
-                        if (dvalid && v < S) corr[((((size_t)b * S + v) * D + d) * P3 + p) * 8 + g] = c;
-                    }
-                }
-            }
-        }
-    }
+    return sum;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3: iteration kernel -- three pyramid levels, R = (4,4,2) samples per pixel around the current
-// normalized depth, all source views, view-weighted aggregation.  One launch covers the three
-// levels (blockIdx.z = b*3 + level).
-//   grid (ceil(W2/ITER_TPX), ceil(H2/8), B*3), block 256 (8 warps = 8 rows)
+// normalized depth, all source views, view-weighted aggregation.
+//   grid (ceil(W2/4), ceil(H2/4), B), block 128 (4 warps = 4 rows, 4 pixels each)
 // ---------------------------------------------------------------------------------------------
-constexpr int ITER_TPX = 16;
-
-struct IterParams {
-    const float* fea[3];   // level 1,2,3 pyramids  [B][V][Hf][Wf][C]
-    const float* rt[3];    // composed projections  [B][S][12]
-    const float* nd;       // [B][nd_stride]
-    size_t nd_stride, nd_pstride;
-    const float* vw2;      // [B][S][P2]
-    const float* depth_min;
-    const float* depth_max;
-    const float* samples[3];   // optional explicit hypotheses [B][R_l][P2] per level (else from nd)
-    float* agg;            // [B][10][P2][8]
-    int B, V, H2, W2;
+struct IterSmem {
+    float4* recW;      // [16*S] bilinear weights of the warp's samples of the current level
+    int2* recO;        // [16*S] {element offset inside this batch item's pyramid, view weight bits}
+    const float* sP;   // [3][S][12] composed projections of this batch item
+    float* nd;         // [4] normalized depth of the warp's pixels
+    float* vw;         // [S][4] view weights of the warp's pixels
 };
 
-// MODE: how the reference-view feature of this level is brought to level-2 resolution
-// (itermvs.py:95-98): 0 same, 1 F.interpolate(x0.5) == 2x2 mean, 2 F.interpolate(x2) bilinear.
-template <int CPG, int R, int MODE>
-__device__ __forceinline__ void iter_level(const IterParams& prm, const float* sP, TapRecord (*sTap)[8], int b, int y, int x_begin,
-                                           int x_end, int slice_base, float o0, float o1, float o2, float o3) {
-    constexpr int C = CPG * 8;
-    constexpr int PPS = 4 / R;     // pixels per warp step
+// LVL 0: level 1 (C=16, feature map 2x the depth map), 1: level 2 (C=32), 2: level 3 (C=48, half size)
+template <int LVL>
+__device__ __forceinline__ void iter_build(const IterParams& prm, const IterSmem& sm, int b, int y, int x0,
+                                           float inv_min, float inv_max, float o0, float o1, float o2, float o3) {
+    constexpr int C = LVL == 0 ? 16 : (LVL == 1 ? 32 : 48);
+    constexpr int R = LVL == 2 ? 2 : 4;
+    constexpr int NPR = WC_NPX * R;
+    constexpr float SC = LVL == 0 ? 2.f : (LVL == 1 ? 1.f : 0.5f);       // module.py:95-96 (Wf / W2, exact)
     const int lane = threadIdx.x & 31;
-    const int slot = lane >> 3, g = lane & 7;
-    const int r = slot % R, pxo = slot / R;
-    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2, P2 = H2 * W2;
-    const int Hf = MODE == 1 ? H2 * 2 : (MODE == 2 ? H2 / 2 : H2);
-    const int Wf = MODE == 1 ? W2 * 2 : (MODE == 2 ? W2 / 2 : W2);
-    const float sx = (float)((double)Wf / (double)W2), sy = (float)((double)Hf / (double)H2);   // module.py:95-96
-    const float* fea = prm.fea[MODE == 1 ? 0 : (MODE == 0 ? 1 : 2)];
-    const size_t view_stride = (size_t)Hf * Wf * C;
-    const float* ref_view = fea + (size_t)(b * V) * view_stride + g * CPG;
-    const float* src_base = ref_view + view_stride;                                   // source view 0, this lane's group
-    const float* smp = prm.samples[MODE == 1 ? 0 : (MODE == 0 ? 1 : 2)];
-    const float inv_min = smp ? 0.f : 1.0f / prm.depth_min[b], inv_max = smp ? 0.f : 1.0f / prm.depth_max[b];
-    const float off = (r == 0 ? o0 : r == 1 ? o1 : r == 2 ? o2 : o3) * (1.0f / 256.0f);   // itermvs.py:229,290
-
-    for (int xs = x_begin; xs < x_end; xs += PPS) {
-        const int x = xs + pxo;
-        const bool pvalid = x < x_end;
-        const int xc = pvalid ? x : x_end - 1;
-        const int p = y * W2 + xc;
-        // hypotheses: itermvs.py:290-293
+    const int S = prm.V - 1, H2 = prm.H2, W2 = prm.W2;
+    const int Hf = LVL == 0 ? H2 * 2 : (LVL == 2 ? H2 / 2 : H2);
+    const int Wf = LVL == 0 ? W2 * 2 : (LVL == 2 ? W2 / 2 : W2);
+    const float* smp = prm.samples[LVL];
+    const float* sP = sm.sP + LVL * S * 12;
+    const int total = NPR * S;
+    for (int t = lane; t < total; t += 32) {
+        const int v = t / NPR, pr = t % NPR, px = pr / R, r = pr % R;
+        const int x = min(x0 + px, W2 - 1);
         float depth;
         if (smp) {
-            depth = ldg(smp + ((size_t)b * R + r) * P2 + p);
-        } else {
-            const float ndv = ldg(prm.nd + (size_t)b * prm.nd_stride + (size_t)p * prm.nd_pstride);
-            const float s = fminf(fmaxf(ndv + off, 0.f), 1.f);
+            depth = ldg(smp + ((size_t)b * R + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x);
+        } else {                                                         // itermvs.py:229, 290-293
+            const float off = (r == 0 ? o0 : r == 1 ? o1 : r == 2 ? o2 : o3) * (1.0f / 256.0f);
+            const float s = fminf(fmaxf(sm.nd[px] + off, 0.f), 1.f);
             depth = unnormalize_depth(s, inv_min, inv_max);
         }
-        // reference feature of this group at level-2 resolution
-        float ref[CPG];
-        if constexpr (MODE == 0) {
-            load_group<CPG>(ref_view + (size_t)p * C, ref);
-        } else if constexpr (MODE == 1) {
-            float a[CPG], bq[CPG], c[CPG], d[CPG];
-            const float* q = ref_view + ((size_t)(2 * y) * Wf + 2 * xc) * C;
-            load_group<CPG>(q, a);
-            load_group<CPG>(q + C, bq);
-            load_group<CPG>(q + (size_t)Wf * C, c);
-            load_group<CPG>(q + (size_t)(Wf + 1) * C, d);
-#pragma unroll
-            for (int i = 0; i < CPG; ++i) ref[i] = 0.5f * (0.5f * a[i] + 0.5f * bq[i]) + 0.5f * (0.5f * c[i] + 0.5f * d[i]);
-        } else {
-            int h0, h1, w0, w1;
-            float lh, lw;
-            up_index(y, 0.5f, Hf, h0, h1, lh);
-            up_index(xc, 0.5f, Wf, w0, w1, lw);
-            float a[CPG], bq[CPG], c[CPG], d[CPG];
-            load_group<CPG>(ref_view + ((size_t)h0 * Wf + w0) * C, a);
-            load_group<CPG>(ref_view + ((size_t)h0 * Wf + w1) * C, bq);
-            load_group<CPG>(ref_view + ((size_t)h1 * Wf + w0) * C, c);
-            load_group<CPG>(ref_view + ((size_t)h1 * Wf + w1) * C, d);
-#pragma unroll
-            for (int i = 0; i < CPG; ++i)
-                ref[i] = (1.f - lh) * ((1.f - lw) * a[i] + lw * bq[i]) + lh * ((1.f - lw) * c[i] + lw * d[i]);
-        }
-        float num = 0.f, wsum = 1e-5f;                          // itermvs.py:88-89
-        constexpr int VG = CPG == 2 ? 4 : 2;                    // views per load batch (bounded by registers)
-        for (int v0 = 0; v0 < S; v0 += 8) {
-            Tap tp;
-            tp.x0 = tp.y0 = 0; tp.fx = tp.fy = 0.f; tp.mask = 0u;
-            float wv = 0.f;
-            if (v0 + g < S) {
-                tp = project_tap(sP + (v0 + g) * 12, (float)xc * sx, (float)y * sy, depth, (float)W2, (float)H2, Wf, Hf);
-                wv = ldg(prm.vw2 + ((size_t)b * S + v0 + g) * P2 + p);
-            }
-            __syncwarp();
-            publish_tapset(&sTap[slot][g], make_tapset(tp, Wf, Hf, C), wv);
-            __syncwarp();
-            const int nv = min(8, S - v0);
-            for (int j0 = 0; j0 < nv; j0 += VG) {
-                TapSet ts[VG];
-                TapLoads<CPG> L[VG];
-                float wj[VG];
-#pragma unroll
-                for (int u = 0; u < VG; ++u) {
-                    ts[u] = read_tapset(&sTap[slot][min(j0 + u, 7)], wj[u]);          // weight 0 for views >= S
-                    const int v = min(v0 + j0 + u, S - 1);
-                    issue_taps<CPG>(L[u], src_base + (size_t)v * view_stride, ts[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < VG; ++u) {
-                    const float c = finish_taps<CPG>(L[u], ts[u], ref);
-                    if (v0 + j0 + u < S) {
-                        num = fmaf(c, wj[u], num);                       // itermvs.py:114
-                        wsum += wj[u];                                   // itermvs.py:115
-                    }
-                }
-            }
-        }
-        if (pvalid) prm.agg[(((size_t)b * IMVS_ITER_SLICES + slice_base + r) * P2 + p) * 8 + g] = num / wsum;
+        const Tap tp = project_tap(sP + v * 12, (float)x * SC, (float)y * SC, depth, (float)W2, (float)H2, Wf, Hf);
+        float4 w;
+        int off;
+        make_record(tp, Wf, Hf, C, v + 1, w, off);
+        sm.recW[t] = w;
+        sm.recO[t] = make_int2(off, __float_as_int(sm.vw[v * WC_NPX + px]));
     }
 }
 
-__global__ void __launch_bounds__(256, 4) warpcorr_iter_kernel(const IterParams prm) {
-    __shared__ float sP[IMVS_MAX_VIEWS * 12];
-    __shared__ TapRecord sTapAll[8][4][8];       // [warp][slot][view of the current chunk]
-    const int b = blockIdx.z / 3, lvl = blockIdx.z % 3;
+// level 1: 4 lanes per sample (float4 = correlation groups 2j, 2j+1), 8 samples per instruction =
+// 4 hypotheses x 2 pixels.  Reference feature: F.interpolate(x0.5) == 2x2 mean (itermvs.py:95-96).
+__device__ __forceinline__ void iter_gather_l1(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
+    constexpr int NPR = WC_NPX * 4;
+    const int lane = threadIdx.x & 31, j = lane & 3, q = lane >> 2, r = q & 3, pxpar = q >> 2;
+    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2, Wf = 2 * W2, Hf = 2 * H2;
+    const float* base = prm.fea[0] + (size_t)b * V * Hf * Wf * 16 + 4 * j;
+    const int pitch = Wf * 16;
+#pragma unroll 1
+    for (int h = 0; h < WC_NPX / 2; ++h) {
+        const int px = 2 * h + pxpar, pr = px * 4 + r;
+        const int x = x0 + px;
+        const bool pvalid = x < W2;
+        const int xc = pvalid ? x : W2 - 1;
+        const float* qr = base + ((size_t)(2 * y) * Wf + 2 * xc) * 16;
+        const float4 ra = ldg4(qr), rb = ldg4(qr + 16), rc = ldg4(qr + pitch), rd = ldg4(qr + pitch + 16);
+        float4 ref;
+        ref.x = 0.5f * (0.5f * ra.x + 0.5f * rb.x) + 0.5f * (0.5f * rc.x + 0.5f * rd.x);
+        ref.y = 0.5f * (0.5f * ra.y + 0.5f * rb.y) + 0.5f * (0.5f * rc.y + 0.5f * rd.y);
+        ref.z = 0.5f * (0.5f * ra.z + 0.5f * rb.z) + 0.5f * (0.5f * rc.z + 0.5f * rd.z);
+        ref.w = 0.5f * (0.5f * ra.w + 0.5f * rb.w) + 0.5f * (0.5f * rc.w + 0.5f * rd.w);
+        float n0 = 0.f, n1 = 0.f, wsum = 1e-5f;                           // itermvs.py:88-89
+#pragma unroll 1
+        for (int v = 0; v < S; v += 2) {
+            const bool two = v + 1 < S;
+            const int t0 = v * NPR + pr, t1 = t0 + (two ? NPR : 0);
+            const float4 w0 = sm.recW[t0], w1 = sm.recW[t1];
+            const int2 o0 = sm.recO[t0], o1 = sm.recO[t1];
+            const float* p0 = base + o0.x;
+            const float* p1 = base + o1.x;
+            const float4 a0 = ldg4(p0), b0 = ldg4(p0 + 16), c0 = ldg4(p0 + pitch), d0 = ldg4(p0 + pitch + 16);
+            const float4 a1 = ldg4(p1), b1 = ldg4(p1 + 16), c1 = ldg4(p1 + pitch), d1 = ldg4(p1 + pitch + 16);
+            {
+                const float lo = fmaf(bilerp(a0.y, b0.y, c0.y, d0.y, w0), ref.y, bilerp(a0.x, b0.x, c0.x, d0.x, w0) * ref.x) * 0.5f;
+                const float hi = fmaf(bilerp(a0.w, b0.w, c0.w, d0.w, w0), ref.w, bilerp(a0.z, b0.z, c0.z, d0.z, w0) * ref.z) * 0.5f;
+                const float wv = __int_as_float(o0.y);
+                n0 = fmaf(lo, wv, n0);                                    // itermvs.py:114
+                n1 = fmaf(hi, wv, n1);
+                wsum += wv;                                               // itermvs.py:115
+            }
+            if (two) {
+                const float lo = fmaf(bilerp(a1.y, b1.y, c1.y, d1.y, w1), ref.y, bilerp(a1.x, b1.x, c1.x, d1.x, w1) * ref.x) * 0.5f;
+                const float hi = fmaf(bilerp(a1.w, b1.w, c1.w, d1.w, w1), ref.w, bilerp(a1.z, b1.z, c1.z, d1.z, w1) * ref.z) * 0.5f;
+                const float wv = __int_as_float(o1.y);
+                n0 = fmaf(lo, wv, n0);
+                n1 = fmaf(hi, wv, n1);
+                wsum += wv;
+            }
+        }
+        if (pvalid) {
+            float* out = prm.agg + (((size_t)b * IMVS_ITER_SLICES + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + 2 * j;
+            *reinterpret_cast<float2*>(out) = make_float2(n0 / wsum, n1 / wsum);
+        }
+    }
+}
+
+// level 2: 8 lanes per sample (float4 = one correlation group), 4 samples per instruction = the 4 hypotheses
+// of one pixel; one tap is exactly one 128-byte line.
+__device__ __forceinline__ void iter_gather_l2(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
+    constexpr int NPR = WC_NPX * 4;
+    const int lane = threadIdx.x & 31, g = lane & 7, r = lane >> 3;
+    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2;
+    const float* base = prm.fea[1] + (size_t)b * V * H2 * W2 * 32 + 4 * g;
+    const int pitch = W2 * 32;
+#pragma unroll 1
+    for (int px = 0; px < WC_NPX; ++px) {
+        const int pr = px * 4 + r;
+        const int x = x0 + px;
+        const bool pvalid = x < W2;
+        const int xc = pvalid ? x : W2 - 1;
+        const float4 ref = ldg4(base + ((size_t)y * W2 + xc) * 32);
+        float num = 0.f, wsum = 1e-5f;
+#pragma unroll 1
+        for (int v = 0; v < S; v += 2) {
+            const bool two = v + 1 < S;
+            const int t0 = v * NPR + pr, t1 = t0 + (two ? NPR : 0);
+            const float4 w0 = sm.recW[t0], w1 = sm.recW[t1];
+            const int2 o0 = sm.recO[t0], o1 = sm.recO[t1];
+            const float* p0 = base + o0.x;
+            const float* p1 = base + o1.x;
+            const float4 a0 = ldg4(p0), b0 = ldg4(p0 + 32), c0 = ldg4(p0 + pitch), d0 = ldg4(p0 + pitch + 32);
+            const float4 a1 = ldg4(p1), b1 = ldg4(p1 + 32), c1 = ldg4(p1 + pitch), d1 = ldg4(p1 + pitch + 32);
+            {
+                float dot = bilerp(a0.x, b0.x, c0.x, d0.x, w0) * ref.x;
+                dot = fmaf(bilerp(a0.y, b0.y, c0.y, d0.y, w0), ref.y, dot);
+                dot = fmaf(bilerp(a0.z, b0.z, c0.z, d0.z, w0), ref.z, dot);
+                dot = fmaf(bilerp(a0.w, b0.w, c0.w, d0.w, w0), ref.w, dot);
+                const float wv = __int_as_float(o0.y);
+                num = fmaf(dot * 0.25f, wv, num);
+                wsum += wv;
+            }
+            if (two) {
+                float dot = bilerp(a1.x, b1.x, c1.x, d1.x, w1) * ref.x;
+                dot = fmaf(bilerp(a1.y, b1.y, c1.y, d1.y, w1), ref.y, dot);
+                dot = fmaf(bilerp(a1.z, b1.z, c1.z, d1.z, w1), ref.z, dot);
+                dot = fmaf(bilerp(a1.w, b1.w, c1.w, d1.w, w1), ref.w, dot);
+                const float wv = __int_as_float(o1.y);
+                num = fmaf(dot * 0.25f, wv, num);
+                wsum += wv;
+            }
+        }
+        if (pvalid)
+            prm.agg[(((size_t)b * IMVS_ITER_SLICES + 4 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
+    }
+}
+
+// 12 contiguous-per-instruction float2 loads of one level-3 sample (4 taps x 3 chunks of 64 bytes) and the
+// partial correlation of this lane's three channel pairs with the reference feature
+struct Taps48 { float2 t[4][3]; };
+__device__ __forceinline__ void load48(Taps48& T, const float* __restrict__ p, int pitch) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T.t[0][k] = ldg2(p + 16 * k);
+        T.t[1][k] = ldg2(p + 48 + 16 * k);
+        T.t[2][k] = ldg2(p + pitch + 16 * k);
+        T.t[3][k] = ldg2(p + pitch + 48 + 16 * k);
+    }
+}
+__device__ __forceinline__ float pair_dot(const Taps48& T, int k, const float4& w, const float2& ref) {
+    const float ax = bilerp(T.t[0][k].x, T.t[1][k].x, T.t[2][k].x, T.t[3][k].x, w);
+    const float ay = bilerp(T.t[0][k].y, T.t[1][k].y, T.t[2][k].y, T.t[3][k].y, w);
+    return fmaf(ay, ref.y, ax * ref.x);
+}
+
+// level 3: 8 lanes per sample, 4 samples per instruction = 2 hypotheses x 2 pixels.  Reference feature:
+// F.interpolate(x2, bilinear, align_corners=False) of the level-3 map (itermvs.py:97-98).
+__device__ __forceinline__ void iter_gather_l3(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
+    constexpr int NPR = WC_NPX * 2;
+    const int lane = threadIdx.x & 31, g = lane & 7, slot = lane >> 3, r = slot & 1, pxpar = slot >> 1;
+    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2, Wf = W2 / 2, Hf = H2 / 2;
+    const float* base = prm.fea[2] + (size_t)b * V * Hf * Wf * 48 + 2 * g;
+    const int pitch = Wf * 48;
+    int h0, h1;
+    float lh;
+    up_index(y, 0.5f, Hf, h0, h1, lh);
+#pragma unroll 1
+    for (int h = 0; h < WC_NPX / 2; ++h) {
+        const int px = 2 * h + pxpar, pr = px * 2 + r;
+        const int x = x0 + px;
+        const bool pvalid = x < W2;
+        const int xc = pvalid ? x : W2 - 1;
+        int w0i, w1i;
+        float lw;
+        up_index(xc, 0.5f, Wf, w0i, w1i, lw);
+        float2 ref[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float2 a = ldg2(base + ((size_t)h0 * Wf + w0i) * 48 + 16 * k), bq = ldg2(base + ((size_t)h0 * Wf + w1i) * 48 + 16 * k);
+            const float2 c = ldg2(base + ((size_t)h1 * Wf + w0i) * 48 + 16 * k), d = ldg2(base + ((size_t)h1 * Wf + w1i) * 48 + 16 * k);
+            ref[k].x = (1.f - lh) * ((1.f - lw) * a.x + lw * bq.x) + lh * ((1.f - lw) * c.x + lw * d.x);
+            ref[k].y = (1.f - lh) * ((1.f - lw) * a.y + lw * bq.y) + lh * ((1.f - lw) * c.y + lw * d.y);
+        }
+        float acc[3] = {0.f, 0.f, 0.f};
+        float wsum = 1e-5f;
+#pragma unroll 1
+        for (int v = 0; v < S; ++v) {
+            const int t = v * NPR + pr;
+            const float4 w = sm.recW[t];
+            const int2 o = sm.recO[t];
+            Taps48 T;
+            load48(T, base + o.x, pitch);
+            const float wv = __int_as_float(o.y);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[k] = fmaf(pair_dot(T, k, w, ref[k]), wv, acc[k]);
+            wsum += wv;
+        }
+        const float num = regroup48(acc, lane) * (1.0f / 6.0f);
+        if (pvalid)
+            prm.agg[(((size_t)b * IMVS_ITER_SLICES + 8 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
+    }
+}
+
+__global__ void __launch_bounds__(WC_WARPS * 32, 8) warpcorr_iter_kernel(const IterParams prm) {
+    extern __shared__ float4 smem4[];
     const int S = prm.V - 1;
-    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = prm.rt[lvl][(size_t)b * S * 12 + i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z;
+    // carve: [warps][16S] float4 | [warps][16S] int2 | [3][S][12] float | [warps][4] float | [warps][S][4] float
+    float4* recW_all = smem4;
+    int2* recO_all = reinterpret_cast<int2*>(recW_all + WC_WARPS * 16 * S);
+    float* sP = reinterpret_cast<float*>(recO_all + WC_WARPS * 16 * S);
+    float* nd_all = sP + 36 * S;
+    float* vw_all = nd_all + WC_WARPS * WC_NPX;
+    for (int i = threadIdx.x; i < 36 * S; i += blockDim.x) {
+        const int lvl = i / (12 * S), k = i - lvl * 12 * S;
+        sP[i] = prm.rt[lvl][(size_t)b * S * 12 + k];
+    }
+    IterSmem sm;
+    sm.recW = recW_all + warp * 16 * S;
+    sm.recO = recO_all + warp * 16 * S;
+    sm.sP = sP;
+    sm.nd = nd_all + warp * WC_NPX;
+    sm.vw = vw_all + warp * WC_NPX * S;
+    const int y = blockIdx.y * WC_WARPS + warp, x0 = blockIdx.x * WC_NPX;
+    const int H2 = prm.H2, W2 = prm.W2;
+    const bool row_ok = y < H2;
+    const bool explicit_samples = prm.samples[0] != nullptr;
+    if (row_ok) {
+        const size_t P2 = (size_t)H2 * W2;
+        if (lane < WC_NPX)
+            sm.nd[lane] = explicit_samples ? 0.f
+                                           : ldg(prm.nd + (size_t)b * prm.nd_stride + ((size_t)y * W2 + min(x0 + lane, W2 - 1)) * prm.nd_pstride);
+        for (int i = lane; i < WC_NPX * S; i += 32) {
+            const int v = i / WC_NPX, px = i % WC_NPX;
+            sm.vw[i] = ldg(prm.vw2 + ((size_t)b * S + v) * P2 + (size_t)y * W2 + min(x0 + px, W2 - 1));
+        }
+    }
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    const int y = blockIdx.y * 8 + warp;
-    if (y >= prm.H2) return;
-    const int x_begin = blockIdx.x * ITER_TPX, x_end = min(x_begin + ITER_TPX, prm.W2);
-    if (x_begin >= x_end) return;
+    if (!row_ok) return;
+    const float inv_min = explicit_samples ? 0.f : 1.0f / prm.depth_min[b];
+    const float inv_max = explicit_samples ? 0.f : 1.0f / prm.depth_max[b];
     // itermvs.py:231-235
-    TapRecord (*sTap)[8] = sTapAll[warp];
-    if (lvl == 0)      iter_level<2, 4, 1>(prm, sP, sTap, b, y, x_begin, x_end, 0, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
-    else if (lvl == 1) iter_level<4, 4, 0>(prm, sP, sTap, b, y, x_begin, x_end, 4, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
-    else               iter_level<6, 2, 2>(prm, sP, sTap, b, y, x_begin, x_end, 8, -32.f, 32.f, 0.f, 0.f);
+    iter_build<2>(prm, sm, b, y, x0, inv_min, inv_max, -32.f, 32.f, 0.f, 0.f);
+    __syncwarp();
+    iter_gather_l3(prm, sm, b, y, x0);
+    __syncwarp();
+    iter_build<1>(prm, sm, b, y, x0, inv_min, inv_max, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
+    __syncwarp();
+    iter_gather_l2(prm, sm, b, y, x0);
+    __syncwarp();
+    iter_build<0>(prm, sm, b, y, x0, inv_min, inv_max, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
+    __syncwarp();
+    iter_gather_l1(prm, sm, b, y, x0);
+}
+
+static size_t iter_smem_bytes(int S) {
+    return (size_t)WC_WARPS * 16 * S * (sizeof(float4) + sizeof(int2)) + sizeof(float) * (36 * S + WC_WARPS * WC_NPX + WC_WARPS * WC_NPX * S);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: init plane sweep at level 3 (C = 48), per-view group correlation.  One warp = one pixel; its D
+// hypotheses in chunks of 32 (phase A: lane = hypothesis, one view per pass), then 4 consecutive
+// hypotheses per load instruction (they lie within a few pixels of each other on the epipolar line and
+// share cache lines).
+//   grid (ceil(W3/2), ceil(H3/2), B), block 128 (4 warps = 2 x 2 pixels)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WC_WARPS * 32, 8)
+warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ rt3,
+                     const float* __restrict__ depth_min, const float* __restrict__ depth_max,
+                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D) {
+    extern __shared__ float4 smem4[];
+    const int S = V - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z;
+    float4* recW = smem4 + warp * 32 * S;
+    int* recO = reinterpret_cast<int*>(smem4 + WC_WARPS * 32 * S) + warp * 32 * S;
+    float* sP = reinterpret_cast<float*>(reinterpret_cast<int*>(smem4 + WC_WARPS * 32 * S) + WC_WARPS * 32 * S);
+    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = rt3[(size_t)b * S * 12 + i];
+    __syncthreads();
+    const int x = blockIdx.x * 2 + (warp & 1), y = blockIdx.y * 2 + (warp >> 1);
+    if (x >= W3 || y >= H3) return;
+    const int g = lane & 7, slot = lane >> 3;
+    const int P3 = H3 * W3, p = y * W3 + x;
+    const float inv_min = samples ? 0.f : 1.0f / depth_min[b], inv_max = samples ? 0.f : 1.0f / depth_max[b];
+    const float* base = fea3 + (size_t)b * V * P3 * 48 + 2 * g;
+    const int pitch = W3 * 48;
+    float2 ref[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ref[k] = ldg2(base + (size_t)p * 48 + 16 * k);
+
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        // phase A: lane <-> hypothesis d0 + lane, one source view per pass
+        {
+            const int d = min(d0 + lane, D - 1);
+            // itermvs.py:13-17 (or the caller's explicit hypotheses, Evaluation.forward's depth_sample)
+            const float depth = samples ? ldg(samples + ((size_t)b * D + d) * P3 + p)
+                                        : 1.0f / (inv_max + ((float)d / (float)(D - 1)) * (inv_min - inv_max));
+            for (int v = 0; v < S; ++v) {
+                const Tap tp = project_tap(sP + v * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
+                float4 w;
+                int off;
+                make_record(tp, W3, H3, 48, v + 1, w, off);
+                recW[v * 32 + lane] = w;
+                recO[v * 32 + lane] = off;
+            }
+        }
+        __syncwarp();
+        const int nd = min(32, D - d0);
+#pragma unroll 1
+        for (int dd = 0; dd < nd; dd += 4) {
+            const int d = d0 + dd + slot;
+            const bool dvalid = d < D;
+#pragma unroll 1
+            for (int v = 0; v < S; ++v) {
+                const int t = v * 32 + dd + slot;
+                const float4 w = recW[t];
+                Taps48 T;
+                load48(T, base + recO[t], pitch);
+                float acc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[k] = pair_dot(T, k, w, ref[k]);
+                const float c = regroup48(acc, lane) * (1.0f / 6.0f);
+                if (dvalid) corr[((((size_t)b * S + v) * D + d) * P3 + p) * 8 + g] = c;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static size_t init_smem_bytes(int S) {
+    return (size_t)WC_WARPS * 32 * S * (sizeof(float4) + sizeof(int)) + sizeof(float) * 12 * S;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -342,6 +450,15 @@ __global__ void aggregate_init_kernel(const float* __restrict__ corr, const floa
     reinterpret_cast<float4*>(agg)[t] = acc;
 }
 
+// A/B switch for profiling: IMVS_WARPCORR_V3=1 in the environment selects the round-1 "v3" kernels.
+static bool use_v3() {
+    static const bool v3 = [] {
+        const char* e = std::getenv("IMVS_WARPCORR_V3");
+        return e && e[0] == '1';
+    }();
+    return v3;
+}
+
 }  // namespace imvs
 
 using namespace imvs;
@@ -352,12 +469,20 @@ extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const flo
                                   const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream) {
     IMVS_REQUIRE(fea3 && rt3 && corr && (depth_samples || (depth_min && depth_max)), "warpcorr_init: null pointer");
     IMVS_REQUIRE(B >= 1 && V >= 2 && V - 1 <= IMVS_MAX_VIEWS, "warpcorr_init: need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, V);
-    IMVS_REQUIRE(H3 >= 1 && W3 >= 1 && D >= 2, "warpcorr_init: bad shape H3=%d W3=%d D=%d", H3, W3, D);
+    IMVS_REQUIRE(H3 >= 2 && W3 >= 2 && D >= 2, "warpcorr_init: bad shape H3=%d W3=%d D=%d", H3, W3, D);
+    IMVS_REQUIRE((double)V * H3 * W3 * 48 < 2147483647.0, "warpcorr_init: one batch item's pyramid exceeds 2^31 elements");
     IMVS_REQUIRE(aligned16(fea3) && aligned16(corr), "warpcorr_init: feature/corr pointers must be 16-byte aligned");
-    const int dsplit = 2;
-    dim3 grid(cdiv(W3, INIT_TPX), cdiv(H3, 8), B * dsplit);
-    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
-    warpcorr_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, dsplit);
+    if (use_v3()) {
+        const int dsplit = 2;
+        dim3 grid(cdiv(W3, INIT_TPX), cdiv(H3, 8), B * dsplit);
+        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
+        warpcorr_init_v3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, dsplit);
+    } else {
+        dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B);
+        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
+        warpcorr_init_kernel<<<grid, WC_WARPS * 32, init_smem_bytes(V - 1), (cudaStream_t)stream>>>(
+            fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D);
+    }
     count_launch();
     IMVS_LAUNCH_CHECK("warpcorr_init_kernel");
     return 0;
@@ -374,7 +499,8 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     IMVS_REQUIRE(explicit_samples || (!samples1 && !samples2 && !samples3 && nd && depth_min && depth_max),
                  "warpcorr_iter: pass either all three sample tensors or nd + depth range");
     IMVS_REQUIRE(B >= 1 && V >= 2 && V - 1 <= IMVS_MAX_VIEWS, "warpcorr_iter: need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, V);
-    IMVS_REQUIRE(H2 >= 2 && W2 >= 2 && H2 % 2 == 0 && W2 % 2 == 0, "warpcorr_iter: H2, W2 must be even (H2=%d W2=%d)", H2, W2);
+    IMVS_REQUIRE(H2 >= 4 && W2 >= 4 && H2 % 2 == 0 && W2 % 2 == 0, "warpcorr_iter: H2, W2 must be even and >= 4 (H2=%d W2=%d)", H2, W2);
+    IMVS_REQUIRE((double)V * H2 * W2 * 64 < 2147483647.0, "warpcorr_iter: one batch item's level-1 pyramid exceeds 2^31 elements");
     IMVS_REQUIRE(aligned16(fea1) && aligned16(fea2) && aligned16(fea3) && aligned16(agg),
                  "warpcorr_iter: feature/agg pointers must be 16-byte aligned");
     IterParams prm;
@@ -384,9 +510,15 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.agg = agg;
     prm.samples[0] = samples1; prm.samples[1] = samples2; prm.samples[2] = samples3;
     prm.B = B; prm.V = V; prm.H2 = H2; prm.W2 = W2;
-    dim3 grid(cdiv(W2, ITER_TPX), cdiv(H2, 8), B * 3);
-    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
-    warpcorr_iter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prm);
+    if (use_v3()) {
+        dim3 grid(cdiv(W2, ITER_TPX), cdiv(H2, 8), B * 3);
+        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
+        warpcorr_iter_v3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prm);
+    } else {
+        dim3 grid(cdiv(W2, WC_NPX), cdiv(H2, WC_WARPS), B);
+        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
+        warpcorr_iter_kernel<<<grid, WC_WARPS * 32, iter_smem_bytes(V - 1), (cudaStream_t)stream>>>(prm);
+    }
     count_launch();
     IMVS_LAUNCH_CHECK("warpcorr_iter_kernel");
     return 0;
