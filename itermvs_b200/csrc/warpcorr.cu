@@ -27,6 +27,8 @@
 #include "sampling.cuh"
 #include "warpcorr_v3.cuh"
 
+#include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 namespace imvs {
@@ -75,18 +77,37 @@ __device__ __forceinline__ float regroup48(const float (&acc)[3], int lane) {
 // ---------------------------------------------------------------------------------------------
 // K3: iteration kernel -- three pyramid levels, R = (4,4,2) samples per pixel around the current
 // normalized depth, all source views, view-weighted aggregation.
-//   grid (ceil(W2/4), ceil(H2/4), B), block 128 (4 warps = 4 rows, 4 pixels each)
+//
+// Work item = (4 consecutive pixels of a row, one pyramid level); items are ordered level 3, 2, 1
+// (heaviest first).  The grid is persistent (one wave of 128-thread blocks); every warp starts on the
+// item with its own global warp index and then draws further items from a self-resetting atomic
+// counter, so the tail is one light level-1 item instead of a partial second wave of blocks.
+// Inside an item the gather loop is software-pipelined by hand: the taps of step i+1 are in flight
+// while step i is multiplied out (the v4 kernel spent issue time and L1 time strictly one after the
+// other: 43 % + 49 % busy).
+//   grid (min(items/4, resident blocks)), block 128
 // ---------------------------------------------------------------------------------------------
+constexpr int WC_CTR_SLOTS = 64;
+__device__ unsigned int g_iter_counter[WC_CTR_SLOTS];
+
+struct IterParams5 {
+    IterParams p;
+    unsigned int* counter;      // self-resetting: atomicInc wraps to 0 after `grabs` draws
+    unsigned int n_items, n_static, grabs_minus_1;
+    int tiles_x, tiles_y;       // 4x4-pixel tiles of the level-2 map
+};
+
 struct IterSmem {
-    float4* recW;      // [16*S] bilinear weights of the warp's samples of the current level
+    float4* recW;      // [16*S] bilinear weights of the warp's samples of the current item
     int2* recO;        // [16*S] {element offset inside this batch item's pyramid, view weight bits}
-    const float* sP;   // [3][S][12] composed projections of this batch item
-    float* nd;         // [4] normalized depth of the warp's pixels
-    float* vw;         // [S][4] view weights of the warp's pixels
+    float* sP;         // [S][12] composed projections of this item's batch element / level
+    float* nd;         // [4] normalized depth of the item's pixels
+    float* vw;         // [S][4] view weights of the item's pixels
+    float* park;       // [32][6] level 3: reference feature of the second pixel pair
 };
 
 // LVL 0: level 1 (C=16, feature map 2x the depth map), 1: level 2 (C=32), 2: level 3 (C=48, half size)
-template <int LVL>
+template <int LVL, int ST>
 __device__ __forceinline__ void iter_build(const IterParams& prm, const IterSmem& sm, int b, int y, int x0,
                                            float inv_min, float inv_max, float o0, float o1, float o2, float o3) {
     constexpr int C = LVL == 0 ? 16 : (LVL == 1 ? 32 : 48);
@@ -94,12 +115,12 @@ __device__ __forceinline__ void iter_build(const IterParams& prm, const IterSmem
     constexpr int NPR = WC_NPX * R;
     constexpr float SC = LVL == 0 ? 2.f : (LVL == 1 ? 1.f : 0.5f);       // module.py:95-96 (Wf / W2, exact)
     const int lane = threadIdx.x & 31;
-    const int S = prm.V - 1, H2 = prm.H2, W2 = prm.W2;
+    const int S = ST ? ST : prm.V - 1, H2 = prm.H2, W2 = prm.W2;
     const int Hf = LVL == 0 ? H2 * 2 : (LVL == 2 ? H2 / 2 : H2);
     const int Wf = LVL == 0 ? W2 * 2 : (LVL == 2 ? W2 / 2 : W2);
     const float* smp = prm.samples[LVL];
-    const float* sP = sm.sP + LVL * S * 12;
     const int total = NPR * S;
+#pragma unroll (ST ? 4 : 1)
     for (int t = lane; t < total; t += 32) {
         const int v = t / NPR, pr = t % NPR, px = pr / R, r = pr % R;
         const int x = min(x0 + px, W2 - 1);
@@ -111,7 +132,7 @@ __device__ __forceinline__ void iter_build(const IterParams& prm, const IterSmem
             const float s = fminf(fmaxf(sm.nd[px] + off, 0.f), 1.f);
             depth = unnormalize_depth(s, inv_min, inv_max);
         }
-        const Tap tp = project_tap(sP + v * 12, (float)x * SC, (float)y * SC, depth, (float)W2, (float)H2, Wf, Hf);
+        const Tap tp = project_tap(sm.sP + v * 12, (float)x * SC, (float)y * SC, depth, (float)W2, (float)H2, Wf, Hf);
         float4 w;
         int off;
         make_record(tp, Wf, Hf, C, v + 1, w, off);
@@ -120,111 +141,269 @@ __device__ __forceinline__ void iter_build(const IterParams& prm, const IterSmem
     }
 }
 
+struct Buf4 { float4 a, b, c, d, w; float wv; };      // the four taps of one sample (one float4 per lane) + its record
+
+template <int C>
+__device__ __forceinline__ void fetch4(Buf4& B, const IterSmem& sm, const float* __restrict__ base, int pitch, int t) {
+    B.w = sm.recW[t];
+    const int2 o = sm.recO[t];
+    B.wv = __int_as_float(o.y);
+    const float* p = base + o.x;
+    B.a = ldg4(p); B.b = ldg4(p + C); B.c = ldg4(p + pitch); B.d = ldg4(p + pitch + C);
+}
+
 // level 1: 4 lanes per sample (float4 = correlation groups 2j, 2j+1), 8 samples per instruction =
 // 4 hypotheses x 2 pixels.  Reference feature: F.interpolate(x0.5) == 2x2 mean (itermvs.py:95-96).
+template <int ST>
 __device__ __forceinline__ void iter_gather_l1(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
     constexpr int NPR = WC_NPX * 4;
     const int lane = threadIdx.x & 31, j = lane & 3, q = lane >> 2, r = q & 3, pxpar = q >> 2;
-    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2, Wf = 2 * W2, Hf = 2 * H2;
+    const int V = prm.V, S = ST ? ST : V - 1, H2 = prm.H2, W2 = prm.W2, Wf = 2 * W2, Hf = 2 * H2;
     const float* base = prm.fea[0] + (size_t)b * V * Hf * Wf * 16 + 4 * j;
     const int pitch = Wf * 16;
-#pragma unroll 1
-    for (int h = 0; h < WC_NPX / 2; ++h) {
-        const int px = 2 * h + pxpar, pr = px * 4 + r;
-        const int x = x0 + px;
-        const bool pvalid = x < W2;
-        const int xc = pvalid ? x : W2 - 1;
+    float4 refs[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int xc = min(x0 + 2 * h + pxpar, W2 - 1);
         const float* qr = base + ((size_t)(2 * y) * Wf + 2 * xc) * 16;
         const float4 ra = ldg4(qr), rb = ldg4(qr + 16), rc = ldg4(qr + pitch), rd = ldg4(qr + pitch + 16);
-        float4 ref;
-        ref.x = 0.5f * (0.5f * ra.x + 0.5f * rb.x) + 0.5f * (0.5f * rc.x + 0.5f * rd.x);
-        ref.y = 0.5f * (0.5f * ra.y + 0.5f * rb.y) + 0.5f * (0.5f * rc.y + 0.5f * rd.y);
-        ref.z = 0.5f * (0.5f * ra.z + 0.5f * rb.z) + 0.5f * (0.5f * rc.z + 0.5f * rd.z);
-        ref.w = 0.5f * (0.5f * ra.w + 0.5f * rb.w) + 0.5f * (0.5f * rc.w + 0.5f * rd.w);
-        float n0 = 0.f, n1 = 0.f, wsum = 1e-5f;                           // itermvs.py:88-89
-#pragma unroll 1
-        for (int v = 0; v < S; v += 2) {
-            const bool two = v + 1 < S;
-            const int t0 = v * NPR + pr, t1 = t0 + (two ? NPR : 0);
-            const float4 w0 = sm.recW[t0], w1 = sm.recW[t1];
-            const int2 o0 = sm.recO[t0], o1 = sm.recO[t1];
-            const float* p0 = base + o0.x;
-            const float* p1 = base + o1.x;
-            const float4 a0 = ldg4(p0), b0 = ldg4(p0 + 16), c0 = ldg4(p0 + pitch), d0 = ldg4(p0 + pitch + 16);
-            const float4 a1 = ldg4(p1), b1 = ldg4(p1 + 16), c1 = ldg4(p1 + pitch), d1 = ldg4(p1 + pitch + 16);
-            {
-                const float lo = fmaf(bilerp(a0.y, b0.y, c0.y, d0.y, w0), ref.y, bilerp(a0.x, b0.x, c0.x, d0.x, w0) * ref.x) * 0.5f;
-                const float hi = fmaf(bilerp(a0.w, b0.w, c0.w, d0.w, w0), ref.w, bilerp(a0.z, b0.z, c0.z, d0.z, w0) * ref.z) * 0.5f;
-                const float wv = __int_as_float(o0.y);
-                n0 = fmaf(lo, wv, n0);                                    // itermvs.py:114
-                n1 = fmaf(hi, wv, n1);
-                wsum += wv;                                               // itermvs.py:115
-            }
-            if (two) {
-                const float lo = fmaf(bilerp(a1.y, b1.y, c1.y, d1.y, w1), ref.y, bilerp(a1.x, b1.x, c1.x, d1.x, w1) * ref.x) * 0.5f;
-                const float hi = fmaf(bilerp(a1.w, b1.w, c1.w, d1.w, w1), ref.w, bilerp(a1.z, b1.z, c1.z, d1.z, w1) * ref.z) * 0.5f;
-                const float wv = __int_as_float(o1.y);
-                n0 = fmaf(lo, wv, n0);
-                n1 = fmaf(hi, wv, n1);
-                wsum += wv;
+        refs[h].x = 0.5f * (0.5f * ra.x + 0.5f * rb.x) + 0.5f * (0.5f * rc.x + 0.5f * rd.x);
+        refs[h].y = 0.5f * (0.5f * ra.y + 0.5f * rb.y) + 0.5f * (0.5f * rc.y + 0.5f * rd.y);
+        refs[h].z = 0.5f * (0.5f * ra.z + 0.5f * rb.z) + 0.5f * (0.5f * rc.z + 0.5f * rd.z);
+        refs[h].w = 0.5f * (0.5f * ra.w + 0.5f * rb.w) + 0.5f * (0.5f * rc.w + 0.5f * rd.w);
+    }
+    float4 ref = refs[0];
+    float n0 = 0.f, n1 = 0.f, wsum = 1e-5f;                               // itermvs.py:88-89
+    auto tix = [&](int h, int v) { return v * NPR + (2 * h + pxpar) * 4 + r; };
+    auto consume = [&](const Buf4& B, int h, int v) {
+        if (v == 0) { ref = h == 0 ? refs[0] : refs[1]; n0 = 0.f; n1 = 0.f; wsum = 1e-5f; }
+        const float lo = fmaf(bilerp(B.a.y, B.b.y, B.c.y, B.d.y, B.w), ref.y, bilerp(B.a.x, B.b.x, B.c.x, B.d.x, B.w) * ref.x) * 0.5f;
+        const float hi = fmaf(bilerp(B.a.w, B.b.w, B.c.w, B.d.w, B.w), ref.w, bilerp(B.a.z, B.b.z, B.c.z, B.d.z, B.w) * ref.z) * 0.5f;
+        n0 = fmaf(lo, B.wv, n0);                                          // itermvs.py:114
+        n1 = fmaf(hi, B.wv, n1);
+        wsum += B.wv;                                                     // itermvs.py:115
+        if (v == S - 1) {
+            const int x = x0 + 2 * h + pxpar;
+            if (x < W2) {
+                float* out = prm.agg + (((size_t)b * IMVS_ITER_SLICES + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + 2 * j;
+                *reinterpret_cast<float2*>(out) = make_float2(n0 / wsum, n1 / wsum);
             }
         }
-        if (pvalid) {
-            float* out = prm.agg + (((size_t)b * IMVS_ITER_SLICES + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + 2 * j;
-            *reinterpret_cast<float2*>(out) = make_float2(n0 / wsum, n1 / wsum);
-        }
+    };
+    Buf4 A, Bb;
+    int h = 0, v = 0;
+    fetch4<16>(A, sm, base, pitch, tix(0, 0));
+    const int n = 2 * S;
+#pragma unroll (ST ? 64 : 1)
+    for (int i = 0; i < n; i += 2) {
+        int vb = v + 1, hb = h;
+        if (vb == S) { vb = 0; hb = h + 1; }
+        fetch4<16>(Bb, sm, base, pitch, tix(hb, vb));
+        consume(A, h, v);
+        v = vb + 1; h = hb;
+        if (v == S) { v = 0; h = hb + 1; }
+        if (i + 2 < n) fetch4<16>(A, sm, base, pitch, tix(h, v));
+        consume(Bb, hb, vb);
     }
 }
 
 // level 2: 8 lanes per sample (float4 = one correlation group), 4 samples per instruction = the 4 hypotheses
 // of one pixel; one tap is exactly one 128-byte line.
+template <int ST>
 __device__ __forceinline__ void iter_gather_l2(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
     constexpr int NPR = WC_NPX * 4;
     const int lane = threadIdx.x & 31, g = lane & 7, r = lane >> 3;
-    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2;
+    const int V = prm.V, S = ST ? ST : V - 1, H2 = prm.H2, W2 = prm.W2;
     const float* base = prm.fea[1] + (size_t)b * V * H2 * W2 * 32 + 4 * g;
     const int pitch = W2 * 32;
-#pragma unroll 1
-    for (int px = 0; px < WC_NPX; ++px) {
-        const int pr = px * 4 + r;
-        const int x = x0 + px;
-        const bool pvalid = x < W2;
-        const int xc = pvalid ? x : W2 - 1;
-        const float4 ref = ldg4(base + ((size_t)y * W2 + xc) * 32);
-        float num = 0.f, wsum = 1e-5f;
-#pragma unroll 1
-        for (int v = 0; v < S; v += 2) {
-            const bool two = v + 1 < S;
-            const int t0 = v * NPR + pr, t1 = t0 + (two ? NPR : 0);
-            const float4 w0 = sm.recW[t0], w1 = sm.recW[t1];
-            const int2 o0 = sm.recO[t0], o1 = sm.recO[t1];
-            const float* p0 = base + o0.x;
-            const float* p1 = base + o1.x;
-            const float4 a0 = ldg4(p0), b0 = ldg4(p0 + 32), c0 = ldg4(p0 + pitch), d0 = ldg4(p0 + pitch + 32);
-            const float4 a1 = ldg4(p1), b1 = ldg4(p1 + 32), c1 = ldg4(p1 + pitch), d1 = ldg4(p1 + pitch + 32);
-            {
-                float dot = bilerp(a0.x, b0.x, c0.x, d0.x, w0) * ref.x;
-                dot = fmaf(bilerp(a0.y, b0.y, c0.y, d0.y, w0), ref.y, dot);
-                dot = fmaf(bilerp(a0.z, b0.z, c0.z, d0.z, w0), ref.z, dot);
-                dot = fmaf(bilerp(a0.w, b0.w, c0.w, d0.w, w0), ref.w, dot);
-                const float wv = __int_as_float(o0.y);
-                num = fmaf(dot * 0.25f, wv, num);
-                wsum += wv;
-            }
-            if (two) {
-                float dot = bilerp(a1.x, b1.x, c1.x, d1.x, w1) * ref.x;
-                dot = fmaf(bilerp(a1.y, b1.y, c1.y, d1.y, w1), ref.y, dot);
-                dot = fmaf(bilerp(a1.z, b1.z, c1.z, d1.z, w1), ref.z, dot);
-                dot = fmaf(bilerp(a1.w, b1.w, c1.w, d1.w, w1), ref.w, dot);
-                const float wv = __int_as_float(o1.y);
-                num = fmaf(dot * 0.25f, wv, num);
-                wsum += wv;
-            }
+    const float* refrow = base + (size_t)y * W2 * 32;
+    float4 ref, refn = ldg4(refrow + (size_t)min(x0, W2 - 1) * 32);
+    float num = 0.f, wsum = 1e-5f;
+    auto tix = [&](int px, int v) { return v * NPR + px * 4 + r; };
+    auto consume = [&](const Buf4& B, int px, int v) {
+        if (v == 0) {
+            ref = refn; num = 0.f; wsum = 1e-5f;
+            if (px + 1 < WC_NPX) refn = ldg4(refrow + (size_t)min(x0 + px + 1, W2 - 1) * 32);
         }
-        if (pvalid)
-            prm.agg[(((size_t)b * IMVS_ITER_SLICES + 4 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
+        float dot = bilerp(B.a.x, B.b.x, B.c.x, B.d.x, B.w) * ref.x;
+        dot = fmaf(bilerp(B.a.y, B.b.y, B.c.y, B.d.y, B.w), ref.y, dot);
+        dot = fmaf(bilerp(B.a.z, B.b.z, B.c.z, B.d.z, B.w), ref.z, dot);
+        dot = fmaf(bilerp(B.a.w, B.b.w, B.c.w, B.d.w, B.w), ref.w, dot);
+        num = fmaf(dot * 0.25f, B.wv, num);
+        wsum += B.wv;
+        if (v == S - 1) {
+            const int x = x0 + px;
+            if (x < W2) prm.agg[(((size_t)b * IMVS_ITER_SLICES + 4 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
+        }
+    };
+    Buf4 A, Bb;
+    int px = 0, v = 0;
+    fetch4<32>(A, sm, base, pitch, tix(0, 0));
+    const int n = WC_NPX * S;
+#pragma unroll (ST ? 64 : 1)
+    for (int i = 0; i < n; i += 2) {
+        int vb = v + 1, pxb = px;
+        if (vb == S) { vb = 0; pxb = px + 1; }
+        fetch4<32>(Bb, sm, base, pitch, tix(pxb, vb));
+        consume(A, px, v);
+        v = vb + 1; px = pxb;
+        if (v == S) { v = 0; px = pxb + 1; }
+        if (i + 2 < n) fetch4<32>(A, sm, base, pitch, tix(px, v));
+        consume(Bb, pxb, vb);
     }
 }
+
+// one row (two horizontally adjacent taps) of a level-3 sample: 6 float2 loads, each instruction reading 64
+// contiguous bytes per sample (lane g: channel pairs g, 8+g, 16+g)
+struct Row48 { float2 l[3], r[3]; float wl, wr, wv; };
+__device__ __forceinline__ void fetch_row48(Row48& R, const IterSmem& sm, const float* __restrict__ base, int pitch, int t, int row) {
+    const float4 w = sm.recW[t];
+    const int2 o = sm.recO[t];
+    R.wl = row ? w.z : w.x; R.wr = row ? w.w : w.y; R.wv = __int_as_float(o.y);
+    const float* p = base + o.x + (row ? pitch : 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { R.l[k] = ldg2(p + 16 * k); R.r[k] = ldg2(p + 48 + 16 * k); }
+}
+
+// level 3: 8 lanes per sample, 4 samples per instruction = 2 hypotheses x 2 pixels.  Reference feature:
+// F.interpolate(x2, bilinear, align_corners=False) of the level-3 map (itermvs.py:97-98).
+template <int ST>
+__device__ __forceinline__ void iter_gather_l3(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
+    constexpr int NPR = WC_NPX * 2;
+    const int lane = threadIdx.x & 31, g = lane & 7, slot = lane >> 3, r = slot & 1, pxpar = slot >> 1;
+    const int V = prm.V, S = ST ? ST : V - 1, H2 = prm.H2, W2 = prm.W2, Wf = W2 / 2, Hf = H2 / 2;
+    const float* base = prm.fea[2] + (size_t)b * V * Hf * Wf * 48 + 2 * g;
+    const int pitch = Wf * 48;
+    int h0, h1;
+    float lh;
+    up_index(y, 0.5f, Hf, h0, h1, lh);
+    float2 ref[3];
+#pragma unroll
+    for (int h = 1; h >= 0; --h) {          // second pixel pair first: parked in shared memory
+        const int xc = min(x0 + 2 * h + pxpar, W2 - 1);
+        int w0i, w1i;
+        float lw;
+        up_index(xc, 0.5f, Wf, w0i, w1i, lw);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float2 a = ldg2(base + ((size_t)h0 * Wf + w0i) * 48 + 16 * k), bq = ldg2(base + ((size_t)h0 * Wf + w1i) * 48 + 16 * k);
+            const float2 c = ldg2(base + ((size_t)h1 * Wf + w0i) * 48 + 16 * k), d = ldg2(base + ((size_t)h1 * Wf + w1i) * 48 + 16 * k);
+            ref[k].x = (1.f - lh) * ((1.f - lw) * a.x + lw * bq.x) + lh * ((1.f - lw) * c.x + lw * d.x);
+            ref[k].y = (1.f - lh) * ((1.f - lw) * a.y + lw * bq.y) + lh * ((1.f - lw) * c.y + lw * d.y);
+        }
+        if (h == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) *reinterpret_cast<float2*>(sm.park + (k * 32 + lane) * 2) = ref[k];
+        }
+    }
+    float acc[3] = {0.f, 0.f, 0.f};
+    float ax[3], ay[3];
+    float wsum = 1e-5f;
+    auto tix = [&](int h, int v) { return v * NPR + (2 * h + pxpar) * 2 + r; };
+    Row48 A, Bb;
+    int h = 0, v = 0;
+    fetch_row48(A, sm, base, pitch, tix(0, 0), 0);
+    const int n = 2 * S;
+#pragma unroll (ST ? 64 : 1)
+    for (int i = 0; i < n; ++i) {
+        fetch_row48(Bb, sm, base, pitch, tix(h, v), 1);
+        if (v == 0) {
+            acc[0] = acc[1] = acc[2] = 0.f; wsum = 1e-5f;
+            if (h == 1) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ref[k] = *reinterpret_cast<const float2*>(sm.park + (k * 32 + lane) * 2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ax[k] = fmaf(A.r[k].x, A.wr, A.l[k].x * A.wl);
+            ay[k] = fmaf(A.r[k].y, A.wr, A.l[k].y * A.wl);
+        }
+        const int hc = h, vc = v;
+        if (++v == S) { v = 0; ++h; }
+        if (i + 1 < n) fetch_row48(A, sm, base, pitch, tix(h, v), 0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ax[k] = fmaf(Bb.r[k].x, Bb.wr, fmaf(Bb.l[k].x, Bb.wl, ax[k]));
+            ay[k] = fmaf(Bb.r[k].y, Bb.wr, fmaf(Bb.l[k].y, Bb.wl, ay[k]));
+            acc[k] = fmaf(fmaf(ay[k], ref[k].y, ax[k] * ref[k].x), Bb.wv, acc[k]);
+        }
+        wsum += Bb.wv;
+        if (vc == S - 1) {
+            const float num = regroup48(acc, lane) * (1.0f / 6.0f);
+            const int x = x0 + 2 * hc + pxpar;
+            if (x < W2)
+                prm.agg[(((size_t)b * IMVS_ITER_SLICES + 8 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
+        }
+    }
+}
+
+// ST = number of source views when it is 1..8 (gather loops fully unrolled: the software pipeline becomes
+// straight-line code with statically renamed buffers), 0 = any number (rolled loops)
+template <int ST>
+__global__ void __launch_bounds__(WC_WARPS * 32, 6) warpcorr_iter_kernel(const IterParams5 q) {
+    extern __shared__ float4 smem4[];
+    const IterParams& prm = q.p;
+    const int S = ST ? ST : prm.V - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp carve: [16S] float4 | [16S] int2 | [32][6] float | [S][12] float | [S][4] float | [4] float
+    const int per_warp4 = 16 * S + 8 * S + 48 + 3 * S + S + 1;      // in float4 units
+    float4* mine = smem4 + warp * per_warp4;
+    IterSmem sm;
+    sm.recW = mine;
+    sm.recO = reinterpret_cast<int2*>(mine + 16 * S);
+    sm.park = reinterpret_cast<float*>(mine + 24 * S);
+    sm.sP = sm.park + 192;
+    sm.vw = sm.sP + 12 * S;
+    sm.nd = sm.vw + 4 * S;
+    const int H2 = prm.H2, W2 = prm.W2;
+    const size_t P2 = (size_t)H2 * W2;
+    const bool explicit_samples = prm.samples[0] != nullptr;
+    const unsigned per_level = q.n_items / 3;
+    unsigned item = blockIdx.x * WC_WARPS + warp;
+    while (item < q.n_items) {
+        const unsigned li = item / per_level, rem = item - li * per_level;      // li 0: level 3, 1: level 2, 2: level 1
+        const int row = rem & 3;
+        const unsigned tile = rem >> 2;
+        const int tx = tile % q.tiles_x, ty = (tile / q.tiles_x) % q.tiles_y, b = tile / (q.tiles_x * q.tiles_y);
+        const int y = ty * 4 + row, x0 = tx * WC_NPX;
+        if (y < H2) {
+            const int lvl = 2 - (int)li;
+            const float* rt = prm.rt[lvl] + (size_t)b * S * 12;
+            for (int i = lane; i < 12 * S; i += 32) sm.sP[i] = ldg(rt + i);
+            if (lane < WC_NPX)
+                sm.nd[lane] = explicit_samples ? 0.f
+                                               : ldg(prm.nd + (size_t)b * prm.nd_stride + ((size_t)y * W2 + min(x0 + lane, W2 - 1)) * prm.nd_pstride);
+            for (int i = lane; i < WC_NPX * S; i += 32) {
+                const int v = i / WC_NPX, px = i % WC_NPX;
+                sm.vw[i] = ldg(prm.vw2 + ((size_t)b * S + v) * P2 + (size_t)y * W2 + min(x0 + px, W2 - 1));
+            }
+            const float inv_min = explicit_samples ? 0.f : 1.0f / prm.depth_min[b];
+            const float inv_max = explicit_samples ? 0.f : 1.0f / prm.depth_max[b];
+            __syncwarp();
+            // itermvs.py:231-235
+            if (lvl == 2) {
+                iter_build<2, ST>(prm, sm, b, y, x0, inv_min, inv_max, -32.f, 32.f, 0.f, 0.f);
+                __syncwarp();
+                iter_gather_l3<ST>(prm, sm, b, y, x0);
+            } else if (lvl == 1) {
+                iter_build<1, ST>(prm, sm, b, y, x0, inv_min, inv_max, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
+                __syncwarp();
+                iter_gather_l2<ST>(prm, sm, b, y, x0);
+            } else {
+                iter_build<0, ST>(prm, sm, b, y, x0, inv_min, inv_max, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
+                __syncwarp();
+                iter_gather_l1<ST>(prm, sm, b, y, x0);
+            }
+            __syncwarp();
+        }
+        unsigned nxt = 0;
+        if (lane == 0) nxt = q.n_static + atomicInc(q.counter, q.grabs_minus_1);
+        item = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+}
+
+static size_t iter_smem_bytes(int S) { return (size_t)WC_WARPS * (16 * S + 8 * S + 48 + 3 * S + S + 1) * sizeof(float4); }
 
 // 12 contiguous-per-instruction float2 loads of one level-3 sample (4 taps x 3 chunks of 64 bytes) and the
 // partial correlation of this lane's three channel pairs with the reference feature
@@ -242,111 +421,6 @@ __device__ __forceinline__ float pair_dot(const Taps48& T, int k, const float4& 
     const float ax = bilerp(T.t[0][k].x, T.t[1][k].x, T.t[2][k].x, T.t[3][k].x, w);
     const float ay = bilerp(T.t[0][k].y, T.t[1][k].y, T.t[2][k].y, T.t[3][k].y, w);
     return fmaf(ay, ref.y, ax * ref.x);
-}
-
-// level 3: 8 lanes per sample, 4 samples per instruction = 2 hypotheses x 2 pixels.  Reference feature:
-// F.interpolate(x2, bilinear, align_corners=False) of the level-3 map (itermvs.py:97-98).
-__device__ __forceinline__ void iter_gather_l3(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
-    constexpr int NPR = WC_NPX * 2;
-    const int lane = threadIdx.x & 31, g = lane & 7, slot = lane >> 3, r = slot & 1, pxpar = slot >> 1;
-    const int V = prm.V, S = V - 1, H2 = prm.H2, W2 = prm.W2, Wf = W2 / 2, Hf = H2 / 2;
-    const float* base = prm.fea[2] + (size_t)b * V * Hf * Wf * 48 + 2 * g;
-    const int pitch = Wf * 48;
-    int h0, h1;
-    float lh;
-    up_index(y, 0.5f, Hf, h0, h1, lh);
-#pragma unroll 1
-    for (int h = 0; h < WC_NPX / 2; ++h) {
-        const int px = 2 * h + pxpar, pr = px * 2 + r;
-        const int x = x0 + px;
-        const bool pvalid = x < W2;
-        const int xc = pvalid ? x : W2 - 1;
-        int w0i, w1i;
-        float lw;
-        up_index(xc, 0.5f, Wf, w0i, w1i, lw);
-        float2 ref[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float2 a = ldg2(base + ((size_t)h0 * Wf + w0i) * 48 + 16 * k), bq = ldg2(base + ((size_t)h0 * Wf + w1i) * 48 + 16 * k);
-            const float2 c = ldg2(base + ((size_t)h1 * Wf + w0i) * 48 + 16 * k), d = ldg2(base + ((size_t)h1 * Wf + w1i) * 48 + 16 * k);
-            ref[k].x = (1.f - lh) * ((1.f - lw) * a.x + lw * bq.x) + lh * ((1.f - lw) * c.x + lw * d.x);
-            ref[k].y = (1.f - lh) * ((1.f - lw) * a.y + lw * bq.y) + lh * ((1.f - lw) * c.y + lw * d.y);
-        }
-        float acc[3] = {0.f, 0.f, 0.f};
-        float wsum = 1e-5f;
-#pragma unroll 1
-        for (int v = 0; v < S; ++v) {
-            const int t = v * NPR + pr;
-            const float4 w = sm.recW[t];
-            const int2 o = sm.recO[t];
-            Taps48 T;
-            load48(T, base + o.x, pitch);
-            const float wv = __int_as_float(o.y);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) acc[k] = fmaf(pair_dot(T, k, w, ref[k]), wv, acc[k]);
-            wsum += wv;
-        }
-        const float num = regroup48(acc, lane) * (1.0f / 6.0f);
-        if (pvalid)
-            prm.agg[(((size_t)b * IMVS_ITER_SLICES + 8 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
-    }
-}
-
-__global__ void __launch_bounds__(WC_WARPS * 32, 8) warpcorr_iter_kernel(const IterParams prm) {
-    extern __shared__ float4 smem4[];
-    const int S = prm.V - 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z;
-    // carve: [warps][16S] float4 | [warps][16S] int2 | [3][S][12] float | [warps][4] float | [warps][S][4] float
-    float4* recW_all = smem4;
-    int2* recO_all = reinterpret_cast<int2*>(recW_all + WC_WARPS * 16 * S);
-    float* sP = reinterpret_cast<float*>(recO_all + WC_WARPS * 16 * S);
-    float* nd_all = sP + 36 * S;
-    float* vw_all = nd_all + WC_WARPS * WC_NPX;
-    for (int i = threadIdx.x; i < 36 * S; i += blockDim.x) {
-        const int lvl = i / (12 * S), k = i - lvl * 12 * S;
-        sP[i] = prm.rt[lvl][(size_t)b * S * 12 + k];
-    }
-    IterSmem sm;
-    sm.recW = recW_all + warp * 16 * S;
-    sm.recO = recO_all + warp * 16 * S;
-    sm.sP = sP;
-    sm.nd = nd_all + warp * WC_NPX;
-    sm.vw = vw_all + warp * WC_NPX * S;
-    const int y = blockIdx.y * WC_WARPS + warp, x0 = blockIdx.x * WC_NPX;
-    const int H2 = prm.H2, W2 = prm.W2;
-    const bool row_ok = y < H2;
-    const bool explicit_samples = prm.samples[0] != nullptr;
-    if (row_ok) {
-        const size_t P2 = (size_t)H2 * W2;
-        if (lane < WC_NPX)
-            sm.nd[lane] = explicit_samples ? 0.f
-                                           : ldg(prm.nd + (size_t)b * prm.nd_stride + ((size_t)y * W2 + min(x0 + lane, W2 - 1)) * prm.nd_pstride);
-        for (int i = lane; i < WC_NPX * S; i += 32) {
-            const int v = i / WC_NPX, px = i % WC_NPX;
-            sm.vw[i] = ldg(prm.vw2 + ((size_t)b * S + v) * P2 + (size_t)y * W2 + min(x0 + px, W2 - 1));
-        }
-    }
-    __syncthreads();
-    if (!row_ok) return;
-    const float inv_min = explicit_samples ? 0.f : 1.0f / prm.depth_min[b];
-    const float inv_max = explicit_samples ? 0.f : 1.0f / prm.depth_max[b];
-    // itermvs.py:231-235
-    iter_build<2>(prm, sm, b, y, x0, inv_min, inv_max, -32.f, 32.f, 0.f, 0.f);
-    __syncwarp();
-    iter_gather_l3(prm, sm, b, y, x0);
-    __syncwarp();
-    iter_build<1>(prm, sm, b, y, x0, inv_min, inv_max, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
-    __syncwarp();
-    iter_gather_l2(prm, sm, b, y, x0);
-    __syncwarp();
-    iter_build<0>(prm, sm, b, y, x0, inv_min, inv_max, -2.f, -2.0f / 3, 2.0f / 3, 2.f);
-    __syncwarp();
-    iter_gather_l1(prm, sm, b, y, x0);
-}
-
-static size_t iter_smem_bytes(int S) {
-    return (size_t)WC_WARPS * 16 * S * (sizeof(float4) + sizeof(int2)) + sizeof(float) * (36 * S + WC_WARPS * WC_NPX + WC_WARPS * WC_NPX * S);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -459,6 +533,15 @@ static bool use_v3() {
     return v3;
 }
 
+// test hook: IMVS_WC_GENERIC=1 forces the rolled-loop instantiation that serves more than 8 source views
+static bool iter_generic() {
+    static const bool v = [] {
+        const char* e = std::getenv("IMVS_WC_GENERIC");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 }  // namespace imvs
 
 using namespace imvs;
@@ -515,9 +598,41 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
         IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
         warpcorr_iter_v3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prm);
     } else {
-        dim3 grid(cdiv(W2, WC_NPX), cdiv(H2, WC_WARPS), B);
-        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
-        warpcorr_iter_kernel<<<grid, WC_WARPS * 32, iter_smem_bytes(V - 1), (cudaStream_t)stream>>>(prm);
+        // persistent grid: one wave of blocks; warps draw (4-pixel row, level) items
+        static std::atomic<unsigned> launch_serial{0};
+        void (*kern)(const IterParams5) = warpcorr_iter_kernel<0>;
+        switch (iter_generic() ? 0 : V - 1) {
+            case 1: kern = warpcorr_iter_kernel<1>; break;
+            case 2: kern = warpcorr_iter_kernel<2>; break;
+            case 3: kern = warpcorr_iter_kernel<3>; break;
+            case 4: kern = warpcorr_iter_kernel<4>; break;
+            case 5: kern = warpcorr_iter_kernel<5>; break;
+            case 6: kern = warpcorr_iter_kernel<6>; break;
+            case 7: kern = warpcorr_iter_kernel<7>; break;
+            case 8: kern = warpcorr_iter_kernel<8>; break;
+            default: break;
+        }
+        const size_t smem = iter_smem_bytes(V - 1);
+        int dev = 0, sms = 0, per_sm = 0;
+        IMVS_CUDA(cudaGetDevice(&dev));
+        IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        IMVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WC_WARPS * 32, smem));
+        IMVS_REQUIRE(per_sm >= 1, "warpcorr_iter: kernel does not fit on an SM (S=%d)", V - 1);
+        IterParams5 q;
+        q.p = prm;
+        q.tiles_x = cdiv(W2, WC_NPX); q.tiles_y = cdiv(H2, 4);
+        const long long items = 3LL * B * q.tiles_x * q.tiles_y * 4;
+        IMVS_REQUIRE(items < (1LL << 31), "warpcorr_iter: too many work items");
+        const int blocks = (int)std::min<long long>((items + WC_WARPS - 1) / WC_WARPS, (long long)sms * per_sm);
+        q.n_items = (unsigned)items;
+        q.n_static = (unsigned)blocks * WC_WARPS;
+        // every warp draws until it gets an out-of-range item: (items - static) successful + one failed draw per warp
+        const long long grabs = std::max<long long>(items - q.n_static, 0) + q.n_static;
+        q.grabs_minus_1 = (unsigned)(grabs - 1);
+        unsigned int* ctr = nullptr;
+        IMVS_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_iter_counter));
+        q.counter = ctr + (launch_serial.fetch_add(1) % WC_CTR_SLOTS);
+        kern<<<blocks, WC_WARPS * 32, smem, (cudaStream_t)stream>>>(q);
     }
     count_launch();
     IMVS_LAUNCH_CHECK("warpcorr_iter_kernel");
