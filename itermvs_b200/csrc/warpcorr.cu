@@ -5,36 +5,35 @@
 //
 // Reference: models/module.py:68-125, models/itermvs.py:11-19, 45-69, 86-120, 289-293.
 //
-// Structure (round-1 "v4").  The kernels are bound by the L1 data pipe (one 128-byte wavefront per
-// cycle per SM) and by instruction issue, not by HBM: every sample is a 4-tap gather of C contiguous
-// floats.  Both are attacked the same way:
+// Structure.  These kernels are bound by the L1 data pipe (one 128-byte wavefront per cycle per SM)
+// and by instruction issue, not by HBM: every sample is a 4-tap gather of C contiguous floats whose
+// lines are reused ~8x out of L1.  The design attacks both:
 //   * two phases per warp.  Phase A: the 32 lanes compute 32 DIFFERENT (pixel, hypothesis, view)
 //     sampling positions (projection, 4 IEEE divisions, clamping, bilinear weights) and leave a 24-byte
 //     record per sample in shared memory.  Phase B: groups of 4/8 lanes walk the records and do
-//     nothing but loads and FMAs.  (v3 computed each position on a quarter of the lanes and re-derived
-//     four 64-bit addresses per tap.)
+//     nothing but loads and FMAs.
 //   * the taps of a record sit at FIXED offsets from one base (top-left tap clamped to
 //     [0, W-2] x [0, H-2]; the bilinear weights are permuted / zeroed to match, which also folds in
 //     grid_sample's zero padding), so a sample costs one address computation.
 //   * every load instruction reads 64 or 128 CONTIGUOUS bytes per sample.  At level 3 (48 channels,
 //     6 per correlation group) a lane therefore holds channel pairs {g, 8+g, 16+g} instead of "its"
 //     group; the per-pair partial sums are accumulated over the views (the aggregation is linear) and
-//     regrouped once per (pixel, hypothesis) with three shuffles.  v3 read 8-byte pieces at a 24-byte
-//     stride: 2 lines per instruction per sample, 3x the wavefronts.
-//   * one warp = 4 pixels x 3 levels, one block = 4 rows: 1 280 equal blocks at 640x512 instead of
-//     480 unequal ones (1.08 waves), 32 resident warps per SM.
+//     regrouped once per (pixel, hypothesis) with three shuffles.  (Loading a lane's own 6 channels
+//     means 8-byte pieces at a 24-byte stride: 2 lines per instruction per sample, 3x the wavefronts.)
+//   * iteration kernel: one persistent 768-thread block per SM owns a compact pixel region (L1 hit
+//     rate 79 %), its warps draw (4-pixel row, level) items from a shared-memory counter, and the
+//     gather loops are software-pipelined and fully unrolled per source-view count.
+// Measured history at 640x512 / 4 views: profiles/README.md.
 #include "common.cuh"
 #include "sampling.cuh"
-#include "warpcorr_v3.cuh"
 
 #include <algorithm>
-#include <atomic>
-#include <cstdlib>
 
 namespace imvs {
 
 constexpr int WC_WARPS = 4;     // warps per block = rows of the pixel tile
 constexpr int WC_NPX = 4;       // consecutive pixels of a row handled by one warp
+constexpr int WC_ITER_WARPS = 24;   // iteration kernel: one 768-thread block per SM (<= 85 registers)
 
 // Phase-A result for one (pixel, hypothesis, view).  Taps are read at element offsets
 // off, off + C, off + pitch, off + pitch + C (pitch = Wf * C) with weights w.x .. w.w.
@@ -78,23 +77,32 @@ __device__ __forceinline__ float regroup48(const float (&acc)[3], int lane) {
 // K3: iteration kernel -- three pyramid levels, R = (4,4,2) samples per pixel around the current
 // normalized depth, all source views, view-weighted aggregation.
 //
-// Work item = (4 consecutive pixels of a row, one pyramid level); items are ordered level 3, 2, 1
-// (heaviest first).  The grid is persistent (one wave of 128-thread blocks); every warp starts on the
-// item with its own global warp index and then draws further items from a self-resetting atomic
-// counter, so the tail is one light level-1 item instead of a partial second wave of blocks.
-// Inside an item the gather loop is software-pipelined by hand: the taps of step i+1 are in flight
-// while step i is multiplied out (the v4 kernel spent issue time and L1 time strictly one after the
-// other: 43 % + 49 % busy).
-//   grid (min(items/4, resident blocks)), block 128
+// Work item = (4 consecutive pixels of a row, one pyramid level).  ONE persistent block per SM owns a
+// contiguous, spatially compact range of 4x4-pixel tiles (all three levels), so that the halo of every tap
+// stays in that SM's L1; its warps draw items from a shared-memory counter, level 3 first (heaviest), so the
+// tail is one light level-1 item.  Inside an item the gather loop is software-pipelined by hand: the taps of
+// step i+1 are in flight while step i is multiplied out (the v4 kernel spent issue time and L1 time
+// strictly one after the other: 43 % + 49 % busy).
+//   grid (#SMs), block 768 or 1024
 // ---------------------------------------------------------------------------------------------
-constexpr int WC_CTR_SLOTS = 64;
-__device__ unsigned int g_iter_counter[WC_CTR_SLOTS];
+struct IterParams {
+    const float* fea[3];   // level 1,2,3 pyramids  [B][V][Hf][Wf][C]
+    const float* rt[3];    // composed projections  [B][S][12]
+    const float* nd;       // [B][nd_stride]
+    size_t nd_stride, nd_pstride;
+    const float* vw2;      // [B][S][P2]
+    const float* depth_min;
+    const float* depth_max;
+    const float* samples[3];   // optional explicit hypotheses [B][R_l][P2] per level (else from nd)
+    float* agg;            // [B][10][P2][8]
+    int B, V, H2, W2;
+};
 
 struct IterParams5 {
     IterParams p;
-    unsigned int* counter;      // self-resetting: atomicInc wraps to 0 after `grabs` draws
-    unsigned int n_items, n_static, grabs_minus_1;
-    int tiles_x, tiles_y;       // 4x4-pixel tiles of the level-2 map
+    unsigned int n_tiles;       // 4x4-pixel tiles of the level-2 maps of all batch items
+    int tiles_x, tiles_y;
+    unsigned long long strip_magic;     // fastdiv constant for 2 * tiles_x
 };
 
 struct IterSmem {
@@ -338,11 +346,63 @@ __device__ __forceinline__ void iter_gather_l3(const IterParams& prm, const Iter
     }
 }
 
-// ST = number of source views when it is 1..8 (gather loops fully unrolled: the software pipeline becomes
-// straight-line code with statically renamed buffers), 0 = any number (rolled loops)
+// Item header: everything a warp needs before phase A of an item, fetched into registers one item ahead
+// (the loads fly while the current item is processed) and parked in shared memory when the item starts.
 template <int ST>
-__global__ void __launch_bounds__(WC_WARPS * 32, 6) warpcorr_iter_kernel(const IterParams5 q) {
+struct ItemHeader {
+    static constexpr int NRT = ST ? (12 * ST + 31) / 32 : (12 * IMVS_MAX_VIEWS + 31) / 32;      // rot|trans floats per lane
+    static constexpr int NVW = ST ? (WC_NPX * ST + 31) / 32 : (WC_NPX * IMVS_MAX_VIEWS + 31) / 32;
+    int b, y, x0, lvl;          // lvl 0..2 = pyramid level 1..3, -1 = no item
+    float rt[NRT], vw[NVW], misc;       // misc: lanes 0..3 normalized depth, lane 4 / 5 depth_min / depth_max
+};
+
+// n / d for n < 2^28, d <= 4096, m = ceil(2^40 / d)
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned long long m) { return (unsigned)(((unsigned long long)n * m) >> 40); }
+
+template <int ST>
+__device__ __forceinline__ void fetch_header(ItemHeader<ST>& h, const IterParams5& q, unsigned item, unsigned n_items,
+                                             unsigned r0, unsigned per_level, int S, int lane) {
+    const IterParams& prm = q.p;
+    if (item >= n_items) { h.lvl = -1; return; }
+    // items of a block: level 3 rows first (heaviest), then level 2, then level 1
+    const unsigned li = (item >= per_level) + (item >= 2 * per_level);
+    const unsigned row_item = r0 + (item - li * per_level);
+    const unsigned tile = row_item >> 2;
+    // tile order: batch item, then strips of two tile rows, column by column inside a strip -- consecutive
+    // tiles (what one SM works on) form a compact region, 8 rows high
+    const unsigned per_b = (unsigned)(q.tiles_x * q.tiles_y);
+    const unsigned b = q.p.B == 1 ? 0u : tile / per_b;
+    const unsigned k = tile - b * per_b;
+    const unsigned strip = fastdiv(k, q.strip_magic), within = k - strip * 2 * q.tiles_x;
+    const bool two = (int)(2 * strip + 1) < q.tiles_y;
+    const int tx = two ? within >> 1 : within, ty = 2 * strip + (two ? (within & 1) : 0);
+    h.b = b; h.lvl = 2 - (int)li;
+    h.y = ty * 4 + (row_item & 3); h.x0 = tx * WC_NPX;
+    const int H2 = prm.H2, W2 = prm.W2;
+    if (h.y >= H2) { h.lvl = -1; return; }          // ragged last tile row: nothing to do
+    const float* rt = prm.rt[h.lvl] + (size_t)b * S * 12;
+#pragma unroll
+    for (int i = 0; i < ItemHeader<ST>::NRT; ++i) h.rt[i] = (lane + 32 * i < 12 * S) ? ldg(rt + lane + 32 * i) : 0.f;
+#pragma unroll
+    for (int i = 0; i < ItemHeader<ST>::NVW; ++i) {
+        const int e = lane + 32 * i, v = e / WC_NPX, px = e % WC_NPX;
+        h.vw[i] = e < WC_NPX * S ? ldg(prm.vw2 + ((size_t)b * S + v) * ((size_t)H2 * W2) + (size_t)h.y * W2 + min(h.x0 + px, W2 - 1)) : 0.f;
+    }
+    h.misc = 0.f;
+    if (prm.samples[0] == nullptr) {
+        if (lane < WC_NPX) h.misc = ldg(prm.nd + (size_t)b * prm.nd_stride + ((size_t)h.y * W2 + min(h.x0 + lane, W2 - 1)) * prm.nd_pstride);
+        else if (lane == 4) h.misc = ldg(prm.depth_min + b);
+        else if (lane == 5) h.misc = ldg(prm.depth_max + b);
+    }
+}
+
+// ST = number of source views when it is 1..8 (gather loops fully unrolled: the software pipeline becomes
+// straight-line code with statically renamed buffers), 0 = any number (rolled loops).
+// NW = warps of the (single) block an SM runs.
+template <int ST, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) warpcorr_iter_kernel(const IterParams5 q) {
     extern __shared__ float4 smem4[];
+    __shared__ unsigned int next_item;
     const IterParams& prm = q.p;
     const int S = ST ? ST : prm.V - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,37 +416,38 @@ __global__ void __launch_bounds__(WC_WARPS * 32, 6) warpcorr_iter_kernel(const I
     sm.sP = sm.park + 192;
     sm.vw = sm.sP + 12 * S;
     sm.nd = sm.vw + 4 * S;
-    const int H2 = prm.H2, W2 = prm.W2;
-    const size_t P2 = (size_t)H2 * W2;
-    const bool explicit_samples = prm.samples[0] != nullptr;
-    const unsigned per_level = q.n_items / 3;
-    unsigned item = blockIdx.x * WC_WARPS + warp;
-    while (item < q.n_items) {
-        const unsigned li = item / per_level, rem = item - li * per_level;      // li 0: level 3, 1: level 2, 2: level 1
-        const int row = rem & 3;
-        const unsigned tile = rem >> 2;
-        const int tx = tile % q.tiles_x, ty = (tile / q.tiles_x) % q.tiles_y, b = tile / (q.tiles_x * q.tiles_y);
-        const int y = ty * 4 + row, x0 = tx * WC_NPX;
-        if (y < H2) {
-            const int lvl = 2 - (int)li;
-            const float* rt = prm.rt[lvl] + (size_t)b * S * 12;
-            for (int i = lane; i < 12 * S; i += 32) sm.sP[i] = ldg(rt + i);
-            if (lane < WC_NPX)
-                sm.nd[lane] = explicit_samples ? 0.f
-                                               : ldg(prm.nd + (size_t)b * prm.nd_stride + ((size_t)y * W2 + min(x0 + lane, W2 - 1)) * prm.nd_pstride);
-            for (int i = lane; i < WC_NPX * S; i += 32) {
-                const int v = i / WC_NPX, px = i % WC_NPX;
-                sm.vw[i] = ldg(prm.vw2 + ((size_t)b * S + v) * P2 + (size_t)y * W2 + min(x0 + px, W2 - 1));
-            }
-            const float inv_min = explicit_samples ? 0.f : 1.0f / prm.depth_min[b];
-            const float inv_max = explicit_samples ? 0.f : 1.0f / prm.depth_max[b];
+    // this block's contiguous range of 4-pixel rows (4 per tile) and its item queue
+    const unsigned r0 = (unsigned)(((unsigned long long)q.n_tiles * 4 * blockIdx.x) / gridDim.x);
+    const unsigned r1 = (unsigned)(((unsigned long long)q.n_tiles * 4 * (blockIdx.x + 1)) / gridDim.x);
+    const unsigned per_level = r1 - r0, n_items = per_level * 3;
+    if (threadIdx.x == 0) next_item = 2 * NW;
+    __syncthreads();
+    ItemHeader<ST> cur, nxt;
+    fetch_header<ST>(cur, q, warp, n_items, r0, per_level, S, lane);
+    unsigned nxt_item = NW + warp;
+    while (cur.lvl >= 0 || nxt_item < n_items) {
+        // the next item's header loads fly while this item is processed
+        fetch_header<ST>(nxt, q, nxt_item, n_items, r0, per_level, S, lane);
+        if (cur.lvl >= 0) {
+#pragma unroll
+            for (int i = 0; i < ItemHeader<ST>::NRT; ++i)
+                if (lane + 32 * i < 12 * S) sm.sP[lane + 32 * i] = cur.rt[i];
+#pragma unroll
+            for (int i = 0; i < ItemHeader<ST>::NVW; ++i)
+                if (lane + 32 * i < WC_NPX * S) sm.vw[lane + 32 * i] = cur.vw[i];
+            if (lane < WC_NPX) sm.nd[lane] = cur.misc;
+            const float dmin = __shfl_sync(0xffffffffu, cur.misc, 4), dmax = __shfl_sync(0xffffffffu, cur.misc, 5);
+            const bool explicit_samples = prm.samples[0] != nullptr;
+            const float inv_min = explicit_samples ? 0.f : 1.0f / dmin;
+            const float inv_max = explicit_samples ? 0.f : 1.0f / dmax;
             __syncwarp();
+            const int b = cur.b, y = cur.y, x0 = cur.x0;
             // itermvs.py:231-235
-            if (lvl == 2) {
+            if (cur.lvl == 2) {
                 iter_build<2, ST>(prm, sm, b, y, x0, inv_min, inv_max, -32.f, 32.f, 0.f, 0.f);
                 __syncwarp();
                 iter_gather_l3<ST>(prm, sm, b, y, x0);
-            } else if (lvl == 1) {
+            } else if (cur.lvl == 1) {
                 iter_build<1, ST>(prm, sm, b, y, x0, inv_min, inv_max, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
                 __syncwarp();
                 iter_gather_l2<ST>(prm, sm, b, y, x0);
@@ -397,13 +458,29 @@ __global__ void __launch_bounds__(WC_WARPS * 32, 6) warpcorr_iter_kernel(const I
             }
             __syncwarp();
         }
-        unsigned nxt = 0;
-        if (lane == 0) nxt = q.n_static + atomicInc(q.counter, q.grabs_minus_1);
-        item = __shfl_sync(0xffffffffu, nxt, 0);
+        cur = nxt;
+        unsigned drawn = 0;
+        if (lane == 0 && nxt_item < n_items) drawn = atomicAdd(&next_item, 1u);
+        nxt_item = nxt_item < n_items ? __shfl_sync(0xffffffffu, drawn, 0) : n_items;
     }
 }
 
-static size_t iter_smem_bytes(int S) { return (size_t)WC_WARPS * (16 * S + 8 * S + 48 + 3 * S + S + 1) * sizeof(float4); }
+static size_t iter_smem_bytes(int S, int nw) { return (size_t)nw * (16 * S + 8 * S + 48 + 3 * S + S + 1) * sizeof(float4); }
+
+template <int NW>
+static void (*iter_kernel_for(int S))(const IterParams5) {
+    switch (S) {
+        case 1: return warpcorr_iter_kernel<1, NW>;
+        case 2: return warpcorr_iter_kernel<2, NW>;
+        case 3: return warpcorr_iter_kernel<3, NW>;
+        case 4: return warpcorr_iter_kernel<4, NW>;
+        case 5: return warpcorr_iter_kernel<5, NW>;
+        case 6: return warpcorr_iter_kernel<6, NW>;
+        case 7: return warpcorr_iter_kernel<7, NW>;
+        case 8: return warpcorr_iter_kernel<8, NW>;
+        default: return warpcorr_iter_kernel<0, NW>;
+    }
+}
 
 // 12 contiguous-per-instruction float2 loads of one level-3 sample (4 taps x 3 chunks of 64 bytes) and the
 // partial correlation of this lane's three channel pairs with the reference feature
@@ -524,24 +601,6 @@ __global__ void aggregate_init_kernel(const float* __restrict__ corr, const floa
     reinterpret_cast<float4*>(agg)[t] = acc;
 }
 
-// A/B switch for profiling: IMVS_WARPCORR_V3=1 in the environment selects the round-1 "v3" kernels.
-static bool use_v3() {
-    static const bool v3 = [] {
-        const char* e = std::getenv("IMVS_WARPCORR_V3");
-        return e && e[0] == '1';
-    }();
-    return v3;
-}
-
-// test hook: IMVS_WC_GENERIC=1 forces the rolled-loop instantiation that serves more than 8 source views
-static bool iter_generic() {
-    static const bool v = [] {
-        const char* e = std::getenv("IMVS_WC_GENERIC");
-        return e && e[0] == '1';
-    }();
-    return v;
-}
-
 }  // namespace imvs
 
 using namespace imvs;
@@ -555,17 +614,10 @@ extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const flo
     IMVS_REQUIRE(H3 >= 2 && W3 >= 2 && D >= 2, "warpcorr_init: bad shape H3=%d W3=%d D=%d", H3, W3, D);
     IMVS_REQUIRE((double)V * H3 * W3 * 48 < 2147483647.0, "warpcorr_init: one batch item's pyramid exceeds 2^31 elements");
     IMVS_REQUIRE(aligned16(fea3) && aligned16(corr), "warpcorr_init: feature/corr pointers must be 16-byte aligned");
-    if (use_v3()) {
-        const int dsplit = 2;
-        dim3 grid(cdiv(W3, INIT_TPX), cdiv(H3, 8), B * dsplit);
-        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
-        warpcorr_init_v3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, dsplit);
-    } else {
-        dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B);
-        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
-        warpcorr_init_kernel<<<grid, WC_WARPS * 32, init_smem_bytes(V - 1), (cudaStream_t)stream>>>(
-            fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D);
-    }
+    dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
+    const size_t smem = init_smem_bytes(V - 1);
+    warpcorr_init_kernel<<<grid, WC_WARPS * 32, smem, (cudaStream_t)stream>>>(fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D);
     count_launch();
     IMVS_LAUNCH_CHECK("warpcorr_init_kernel");
     return 0;
@@ -593,47 +645,24 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.agg = agg;
     prm.samples[0] = samples1; prm.samples[1] = samples2; prm.samples[2] = samples3;
     prm.B = B; prm.V = V; prm.H2 = H2; prm.W2 = W2;
-    if (use_v3()) {
-        dim3 grid(cdiv(W2, ITER_TPX), cdiv(H2, 8), B * 3);
-        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_iter: grid too large");
-        warpcorr_iter_v3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prm);
-    } else {
-        // persistent grid: one wave of blocks; warps draw (4-pixel row, level) items
-        static std::atomic<unsigned> launch_serial{0};
-        void (*kern)(const IterParams5) = warpcorr_iter_kernel<0>;
-        switch (iter_generic() ? 0 : V - 1) {
-            case 1: kern = warpcorr_iter_kernel<1>; break;
-            case 2: kern = warpcorr_iter_kernel<2>; break;
-            case 3: kern = warpcorr_iter_kernel<3>; break;
-            case 4: kern = warpcorr_iter_kernel<4>; break;
-            case 5: kern = warpcorr_iter_kernel<5>; break;
-            case 6: kern = warpcorr_iter_kernel<6>; break;
-            case 7: kern = warpcorr_iter_kernel<7>; break;
-            case 8: kern = warpcorr_iter_kernel<8>; break;
-            default: break;
-        }
-        const size_t smem = iter_smem_bytes(V - 1);
-        int dev = 0, sms = 0, per_sm = 0;
-        IMVS_CUDA(cudaGetDevice(&dev));
-        IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        IMVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WC_WARPS * 32, smem));
-        IMVS_REQUIRE(per_sm >= 1, "warpcorr_iter: kernel does not fit on an SM (S=%d)", V - 1);
-        IterParams5 q;
-        q.p = prm;
-        q.tiles_x = cdiv(W2, WC_NPX); q.tiles_y = cdiv(H2, 4);
-        const long long items = 3LL * B * q.tiles_x * q.tiles_y * 4;
-        IMVS_REQUIRE(items < (1LL << 31), "warpcorr_iter: too many work items");
-        const int blocks = (int)std::min<long long>((items + WC_WARPS - 1) / WC_WARPS, (long long)sms * per_sm);
-        q.n_items = (unsigned)items;
-        q.n_static = (unsigned)blocks * WC_WARPS;
-        // every warp draws until it gets an out-of-range item: (items - static) successful + one failed draw per warp
-        const long long grabs = std::max<long long>(items - q.n_static, 0) + q.n_static;
-        q.grabs_minus_1 = (unsigned)(grabs - 1);
-        unsigned int* ctr = nullptr;
-        IMVS_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_iter_counter));
-        q.counter = ctr + (launch_serial.fetch_add(1) % WC_CTR_SLOTS);
-        kern<<<blocks, WC_WARPS * 32, smem, (cudaStream_t)stream>>>(q);
-    }
+    // one persistent block per SM, each owning a contiguous, compact range of 4-pixel rows
+    const int S = V - 1;
+    auto kern = iter_kernel_for<WC_ITER_WARPS>(S);
+    const size_t smem = iter_smem_bytes(S, WC_ITER_WARPS);
+    int dev = 0, sms = 0;
+    IMVS_CUDA(cudaGetDevice(&dev));
+    IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > 48 * 1024) IMVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IterParams5 q;
+    q.p = prm;
+    q.tiles_x = cdiv(W2, WC_NPX); q.tiles_y = cdiv(H2, 4);
+    const long long tiles = (long long)B * q.tiles_x * q.tiles_y;
+    IMVS_REQUIRE(tiles < (1LL << 26), "warpcorr_iter: too many tiles");
+    IMVS_REQUIRE(2 * q.tiles_x <= 4096, "warpcorr_iter: W2=%d too wide", W2);
+    q.n_tiles = (unsigned)tiles;
+    q.strip_magic = ((1ULL << 40) + 2 * q.tiles_x - 1) / (2 * q.tiles_x);
+    const int blocks = (int)std::min<long long>(tiles, sms);
+    kern<<<blocks, WC_ITER_WARPS * 32, smem, (cudaStream_t)stream>>>(q);
     count_launch();
     IMVS_LAUNCH_CHECK("warpcorr_iter_kernel");
     return 0;

@@ -153,7 +153,7 @@ def _feature_inputs(dev, width, height, n_src, batch, seed):
     return (ref, srcs, rp, sp, s), (to(ref), to(srcs), to(rp), to(sp))
 
 
-@pytest.mark.parametrize("batch,n_src", [(1, 2), (2, 3)])
+@pytest.mark.parametrize("batch,n_src", [(1, 2), (2, 3), (1, 1)])
 def test_evaluation_init_branch(dev, model, dtu_weights, batch, n_src):
     (ref, srcs, rp, sp, s), (gref, gsrcs, grp, gsp) = _feature_inputs(dev, 160, 128, n_src, batch, seed=11)
     inv_min = (1.0 / s["depth_min"]).view(batch, 1, 1, 1)
@@ -167,7 +167,8 @@ def test_evaluation_init_branch(dev, model, dtu_weights, batch, n_src):
     assert maxerr(depth, want["depth"]) / 600.0 < 1e-4
 
 
-@pytest.mark.parametrize("batch,n_src", [(1, 4), (2, 3)])
+# n_src 1..8 run the kernels unrolled per view count, 9 the rolled-loop instantiation (up to 16 views)
+@pytest.mark.parametrize("batch,n_src", [(1, 4), (2, 3), (1, 1), (1, 7), (2, 9)])
 def test_evaluation_iter_branch(dev, model, dtu_weights, batch, n_src):
     (ref, srcs, rp, sp, s), (gref, gsrcs, grp, gsp) = _feature_inputs(dev, 160, 128, n_src, batch, seed=12)
     g = torch.Generator().manual_seed(3)
