@@ -45,6 +45,38 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 void count_launch(int n = 1);
 long long launches_total();
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// A forward pass is ~95 short kernels (20 us on average) in one stream / one CUDA graph.  Every kernel
+// starts with pdl_trigger() (lets the NEXT kernel's CTAs become resident as soon as this grid's last CTAs
+// have started) and executes pdl_wait() before its first access to memory another kernel produces (blocks
+// until the PREVIOUS grid has completed and flushed), so launch latency, CTA ramp-up and the
+// producer-independent prologue (weight staging, index arithmetic) overlap the predecessor's tail.
+// Host side: launch_k() adds cudaLaunchAttributeProgrammaticStreamSerialization except for the first
+// launch of an outermost C-ABI call (its predecessor in the stream may be a memcpy / memset / foreign
+// kernel).  IMVS_PDL=0 in the environment (read once) disables the attribute; the device-side
+// instructions are then no-ops.
+bool pdl_enabled();
+bool* pdl_armed();                 // thread-local: a kernel of this API call has already been launched
+int* api_depth();                  // thread-local nesting depth of extern "C" entry points
+struct ApiScope {
+    ApiScope() { if ((*api_depth())++ == 0) *pdl_armed() = false; }
+    ~ApiScope() { --*api_depth(); }
+};
+
+template <class... KArgs, class... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (*pdl_armed() && pdl_enabled()) ? 1 : 0;
+    *pdl_armed() = true;
+    count_launch();
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(static_cast<Args&&>(args))...);
+}
+
 // ---- optional per-stage CUDA-event timing (bench.py's roofline measurement; off by default) ----
 enum StageTag { ST_COMPOSE = 0, ST_WARPCORR_INIT, ST_PVW, ST_AGG_INIT, ST_CORRNET, ST_HIDDEN_INIT, ST_HEAD,
                 ST_WARPCORR_ITER, ST_GRU, ST_UPSAMPLE, ST_FEATURENET, ST_COUNT };
@@ -69,6 +101,8 @@ int ensure_dynamic_smem(K kern, size_t smem, int* done_mask) {
 }
 
 // ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }

@@ -57,6 +57,8 @@ struct EpiPvw {              // relu(16 channels) . w1 + b1 -> logits[n][y][x]; 
 
 // softmax over D then max over D == 1 / sum_d exp(l_d - max_d l)   (itermvs.py:347-348)
 __global__ void pvw_reduce_kernel(const float* __restrict__ logits, float* __restrict__ vw3, int BS, int D, int P3) {
+    pdl_trigger();
+    pdl_wait();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= BS * P3) return;
     int bs = t / P3, p = t % P3;
@@ -72,6 +74,8 @@ __global__ void pvw_reduce_kernel(const float* __restrict__ logits, float* __res
 // (C = 1: itermvs.py:56-57; C = 32 with tanh: itermvs.py:161-163)
 __global__ void upsample2x_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C,
                                        bool apply_tanh) {
+    pdl_trigger();
+    pdl_wait();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int Ho = 2 * H, Wo = 2 * W;
     if (t >= (size_t)N * Ho * Wo * C) return;
@@ -91,9 +95,7 @@ __global__ void upsample2x_nhwc_kernel(const float* __restrict__ in, float* __re
 
 int launch_upsample2x_nhwc(const float* in, float* out, int N, int H, int W, int C, bool apply_tanh, cudaStream_t st) {
     size_t total = (size_t)N * H * W * C * 4;
-    upsample2x_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, N, H, W, C, apply_tanh);
-    count_launch();
-    IMVS_LAUNCH_CHECK("upsample2x_nhwc_kernel");
+    IMVS_CUDA(launch_k(upsample2x_nhwc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, out, N, H, W, C, apply_tanh));
     return 0;
 }
 
@@ -115,6 +117,7 @@ extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int sp
     IMVS_REQUIRE(sets && vol && out && scratch, "corrnet: null pointer");
     IMVS_REQUIRE(N >= 1 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0, "corrnet: H, W must be multiples of 4 (H=%d W=%d)", H, W);
     IMVS_REQUIRE(period >= 1 && N % period == 0, "corrnet: N=%d not a multiple of period=%d", N, period);
+    ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t HW = (size_t)H * W;
     float* c0 = scratch;                    // [N][H][W][8]
@@ -149,13 +152,12 @@ extern "C" int imvs_pixel_view_weight(const imvs_weights* w, const float* corr, 
                                       int B, int S, int D, int H3, int W3, void* stream) {
     IMVS_REQUIRE(w && corr && logits && vw3 && vw2, "pixel_view_weight: null pointer");
     IMVS_REQUIRE(B >= 1 && S >= 1 && D >= 1 && H3 >= 1 && W3 >= 1, "pixel_view_weight: bad shape");
+    ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     const int N = B * S * D, P3 = H3 * W3;
     IMVS_TRY((mma_conv<8, 16, 2, 4, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), EpiPvw{logits, w->pvw_conv1, w->pvw_conv1_b, H3, W3},
                                              WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 8), N, 16, H3, W3, 1, st)));
-    pvw_reduce_kernel<<<cdiv(B * S * P3, 128), 128, 0, st>>>(logits, vw3, B * S, D, P3);
-    count_launch();
-    IMVS_LAUNCH_CHECK("pvw_reduce_kernel");
+    IMVS_CUDA(launch_k(pvw_reduce_kernel, dim3(cdiv(B * S * P3, 128)), dim3(128), 0, st, (const float*)logits, vw3, B * S, D, P3));
     return launch_upsample2x_nhwc(vw3, vw2, B * S, H3, W3, 1, false, st);
 }
 
@@ -163,6 +165,7 @@ extern "C" int imvs_hidden_init(const imvs_weights* w, const float* corr, float*
                                 int B, int D, int H3, int W3, void* stream) {
     IMVS_REQUIRE(w && corr && hidden && scratch, "hidden_init: null pointer");
     IMVS_REQUIRE(B >= 1 && H3 >= 1 && W3 >= 1, "hidden_init: bad shape");
+    ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t P3 = (size_t)H3 * W3;
     float* t = scratch;                       // [B][P3][64]

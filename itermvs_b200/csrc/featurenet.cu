@@ -80,23 +80,25 @@ static FnetBuffers fnet_carve(float* base, size_t N, size_t H, size_t W) {
 }
 
 // one residual stage (two ResidualBlocks, module.py:32-50):  x [Hin][Win][CI] -> buf[3] [Hin/2][Win/2][CO]
-template <int CI, int CO, bool WALL_A, bool WALL_B>
+// NBA / NBB: cout block of the stride-2 [conv1 | downsample] GEMM / of the CO -> CO convolutions; MT: row-tiles per warp
+template <int CI, int CO, bool WALL_A, bool WALL_B, int NBA = 2 * CO, int NBB = CO, int MT = 2>
 static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, float* const buf[4], int N, int Hin, int Win,
                      cudaStream_t st) {
     const int H = Hin / 2, W = Win / 2;
-    const TapTables s2 = conv_tables(3, 2, 1, 8), s1 = conv_tables(3, 1, 1, 8);
+    const TapTables s2 = conv_tables(3, 2, 1, 4 * MT), s1 = conv_tables(3, 1, 1, 4 * MT);
+    constexpr int NCA = 2 * CO / NBA, NCB = CO / NBB;
     // block 0: [conv1 (stride 2, relu) | downsample (stride 2)] as one GEMM, then conv2 + downsample -> relu
     const int LS = 21 + (L - 1) / 5;           // stacked [conv1 | downsample] weights of this stage
-    IMVS_TRY((mma_conv<CI, 2 * CO, 2, 4, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
-                                                    EpiSplit2{buf[0], buf[1], w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO,
-                                                    H, W, 1, st)));
-    IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
-                                                WSets::single(w->w[L + 1]), s1, N, CO, H, W, 1, st)));
+    IMVS_TRY((mma_conv<CI, NBA, MT, 4, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
+                                                  EpiSplit2{buf[0], buf[1], w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO,
+                                                  H, W, NCA, st)));
+    IMVS_TRY((mma_conv<CO, NBB, MT, 4, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
+                                                  WSets::single(w->w[L + 1]), s1, N, CO, H, W, NCB, st)));
     // block 1: conv1 relu, conv2 + x -> relu
-    IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
-                                                WSets::single(w->w[L + 3]), s1, N, CO, H, W, 1, st)));
-    IMVS_TRY((mma_conv<CO, CO, 2, 4, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
-                                                WSets::single(w->w[L + 4]), s1, N, CO, H, W, 1, st)));
+    IMVS_TRY((mma_conv<CO, NBB, MT, 4, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
+                                                  WSets::single(w->w[L + 3]), s1, N, CO, H, W, NCB, st)));
+    IMVS_TRY((mma_conv<CO, NBB, MT, 4, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
+                                                  WSets::single(w->w[L + 4]), s1, N, CO, H, W, NCB, st)));
     return 0;
 }
 
@@ -120,6 +122,7 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     IMVS_REQUIRE(workspace_bytes >= b.total * sizeof(float), "featurenet_forward: workspace too small (%zu < %zu bytes)", workspace_bytes,
                  b.total * sizeof(float));
     cudaStream_t st = (cudaStream_t)stream;
+    ApiScope api_;
     StageTimer tm_(ST_FEATURENET, stream);
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8;
     const TapTables s1 = conv_tables(3, 1, 1, 8), k1 = conv_tables(1, 1, 1, 8);
@@ -127,11 +130,30 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                             WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
-    IMVS_TRY((res_stage<16, 32, true, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));   // layer2 -> l2[3]  [H/4][W/4][32]
-    IMVS_TRY((res_stage<32, 48, false, false>(w, 11, b.l2[3], b.l3, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48]
-    // output3 (net.py:59)
-    IMVS_TRY((mma_conv<48, 48, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), EpiNHWC{fea3, w->b[16], nullptr, H3, W3, 48, 48, 0},
-                                               WSets::single(w->w[16]), s1, N, 48, H3, W3, 1, st)));
+    switch (tune("FNET2", 0)) {                                                          // layer2 -> l2[3]  [H/4][W/4][32]
+        case 1: IMVS_TRY((res_stage<16, 32, true, false, 32, 16, 2>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
+        case 2: IMVS_TRY((res_stage<16, 32, true, false, 64, 32, 1>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
+        default: IMVS_TRY((res_stage<16, 32, true, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));
+    }
+    const int t3 = tune("FNET3", 0);
+    const EpiNHWC eo3{fea3, w->b[16], nullptr, H3, W3, 48, 48, 0};
+    switch (t3) {                                                                         // layer3 -> l3[3]  [H/8][W/8][48]; output3 (net.py:59)
+        case 1:
+            IMVS_TRY((res_stage<32, 48, false, false, 32, 16, 2>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
+            IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), s1, N, 48, H3, W3, 3, st)));
+            break;
+        case 2:
+            IMVS_TRY((res_stage<32, 48, false, false, 96, 48, 1>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
+            IMVS_TRY((mma_conv<48, 48, 1, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), conv_tables(3, 1, 1, 4), N, 48, H3, W3, 1, st)));
+            break;
+        case 3:
+            IMVS_TRY((res_stage<32, 48, false, false, 32, 16, 1>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
+            IMVS_TRY((mma_conv<48, 16, 1, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), conv_tables(3, 1, 1, 4), N, 48, H3, W3, 3, st)));
+            break;
+        default:
+            IMVS_TRY((res_stage<32, 48, false, false>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
+            IMVS_TRY((mma_conv<48, 48, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), s1, N, 48, H3, W3, 1, st)));
+    }
     // intra2 = up2(f3) + inner2(f2); output2 (net.py:60-62)
     IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2{b.intra2, w->b[17], b.l3[3], H2, W2, 48},
                                               WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));

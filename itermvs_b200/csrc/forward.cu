@@ -83,6 +83,7 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
     IMVS_REQUIRE(w && fea1 && fea2 && fea3 && proj1 && proj2 && proj3 && depth_min && depth_max && workspace,
                  "itermvs_forward: null pointer");
     IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "itermvs_forward: workspace must be 256-byte aligned");
+    ApiScope api_;
     Workspace ws = carve(*pb, static_cast<float*>(workspace));
     IMVS_REQUIRE(workspace_bytes >= ws.total_floats * sizeof(float), "itermvs_forward: workspace too small (%zu < %zu bytes)",
                  workspace_bytes, ws.total_floats * sizeof(float));

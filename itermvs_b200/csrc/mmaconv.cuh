@@ -260,6 +260,15 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         }
     };
 
+    // weights are constants of the forward pass: their first stages are requested BEFORE the grid-dependency
+    // wait, so they arrive while the producer of the input is still draining (programmatic dependent launch)
+    pdl_trigger();
+    if constexpr (Cfg::WALL) {
+        for (int tp = 0; tp < ntaps; ++tp) issue_weights(tp, tp);
+    } else {
+        issue_weights(0, 0);
+    }
+    pdl_wait();
     {   // input tile (with halo)
         const int iy0 = oy0 * Cfg::STRIDE + taps.dy_min, ix0 = ox0 * Cfg::STRIDE + taps.dx_min;
         constexpr int C4 = Cfg::CINK / 4;
@@ -277,15 +286,13 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         }
     }
     if constexpr (Cfg::WALL) {
-        for (int tp = 0; tp < ntaps; ++tp) issue_weights(tp, tp);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
     } else {
-        issue_weights(0, 0);
-        cp_async_commit();
+        cp_async_commit();              // group 0: tap-0 weights + tile
         if (ntaps > 1) issue_weights(1, 1);
-        cp_async_commit();
+        cp_async_commit();              // group 1: tap-1 weights
     }
 
     float acc[MT][NT][4];
@@ -327,16 +334,26 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
                     split_f16(*reinterpret_cast<const float2*>(sA + slot0[r] + k0 + 8), a[r][2], al[r][2]);
                     split_f16(*reinterpret_cast<const float2*>(sA + slot1[r] + k0 + 8), a[r][3], al[r][3]);
                 }
+                // the three products of one accumulator tile are issued MT*NT MMAs apart: back-to-back they
+                // serialise on the accumulator (HMMA latency), which left the tensor pipe 26 % busy
+                uint2 w0[NT], w1[NT];
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const uint2 w0 = wb2[(ks * 8 + t) * NP + 8 * j + g], w1 = wb2[(ks * 8 + t + 4) * NP + 8 * j + g];
-#pragma unroll
-                    for (int r = 0; r < MT; ++r) {
-                        mma_f16(acc[r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0.x, w1.x);
-                        mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0.y, w1.y);
-                        mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0.x, w1.x);
-                    }
+                    w0[j] = wb2[(ks * 8 + t) * NP + 8 * j + g];
+                    w1[j] = wb2[(ks * 8 + t + 4) * NP + 8 * j + g];
                 }
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int r = 0; r < MT; ++r) mma_f16(acc[r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0[j].x, w1[j].x);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int r = 0; r < MT; ++r) mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].y, w1[j].y);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int r = 0; r < MT; ++r) mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].x, w1[j].x);
             }
         } else {
 #pragma unroll
@@ -407,12 +424,12 @@ int launch_mma_conv(const char* name, const In& in, const Epi& epi, const MmaWei
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     dim3 grid(cdiv(Wout, 16), cdiv(Hout, Cfg::TH), N * ncb * tabs.count);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
-    kern<<<grid, Cfg::THREADS, smem, st>>>(in, epi, wsel, tabs, cout_total, Hout, Wout, ncb);
-    count_launch();
-    IMVS_LAUNCH_CHECK(name);
+    if (launch_k(kern, grid, dim3(Cfg::THREADS), smem, st, in, epi, wsel, tabs, cout_total, Hout, Wout, ncb) != cudaSuccess)
+        return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
 
+int tune(const char* name, int def);   // IMVS_TUNE_<NAME> experiment switch, defined in warp.cu
 int conv_passes();       // process-wide precision switch (imvs_set_conv_passes), defined in warp.cu
 
 struct WSets {           // host-side: up to three packed weights + the slice -> set mapping

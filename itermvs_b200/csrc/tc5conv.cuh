@@ -150,6 +150,8 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
         for (int tap = 0; tap < ntaps; ++tap)
             bulk_g2s(smem_u32(sB) + tap * tap_bytes, w_umma + (size_t)tap * (tap_bytes / 4), tap_bytes, bar_w);
     }
+    pdl_trigger();
+    pdl_wait();         // TMEM allocation and the weight copies above overlap the predecessor's tail
     // ---- stage the haloed input tile, rounding to TF32 (round-to-nearest) on the way:
     //      slot s -> pixel (oy0 - pad + s / WT, ox0 - pad + s % WT).  A quarter-warp covers 2 slots x 4 chunks;
     //      nslot = 2 (mod 8) makes the 16-byte stores of a quarter-warp hit 8 distinct bank groups.
@@ -263,9 +265,8 @@ int launch(const char* name, const In& in, const Epi& epi, const float* w_umma, 
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     dim3 grid(cdiv(Wout, g.WT - 2 * g.pad), cdiv(Hout, g.THo), N);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
-    kern<<<grid, TC5_THREADS, smem, st>>>(in, epi, w_umma, g, Hout, Wout, err_flag, tc5_clock_buffer());
-    count_launch();
-    IMVS_LAUNCH_CHECK(name);
+    if (launch_k(kern, grid, dim3(TC5_THREADS), smem, st, in, epi, w_umma, g, Hout, Wout, err_flag, tc5_clock_buffer()) != cudaSuccess)
+        return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
 

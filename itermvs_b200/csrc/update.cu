@@ -82,6 +82,8 @@ struct RegressParams {
 };
 
 __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParams prm) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= prm.B * prm.P) return;
@@ -166,6 +168,7 @@ using namespace imvs;
 extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, float* scratch, int B, int H, int W, void* stream) {
     IMVS_REQUIRE(w && h && x && scratch, "conv_gru: null pointer");
     IMVS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "conv_gru: bad shape");
+    ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)B * 32 * H * W;
     float* z = scratch;
@@ -178,11 +181,27 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
                                       w->gru_q.umma, 3, 2, B, H, W, tc5_error_flag(), st)));
         return 0;
     }
-    const TapTables taps = conv_tables(3, 1, 2, 8);
-    IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.zr", InNHWC2{h, x, H, W, 32, IMVS_XCH}, EpiGruZR{w->gru_zr_b, h, z, rh, H, W},
-                                               WSets::single(w->gru_zr), taps, B, 64, H, W, 2, st)));
-    IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.q", InNHWC2{rh, x, H, W, 32, IMVS_XCH}, EpiGruQ{w->gru_q_b, z, h, H, W},
-                                               WSets::single(w->gru_q), taps, B, 32, H, W, 1, st)));
+    const InNHWC2 in_zr{h, x, H, W, 32, IMVS_XCH}, in_q{rh, x, H, W, 32, IMVS_XCH};
+    const EpiGruZR ezr{w->gru_zr_b, h, z, rh, H, W};
+    const EpiGruQ eq{w->gru_q_b, z, h, H, W};
+    const WSets wzr = WSets::single(w->gru_zr), wq = WSets::single(w->gru_q);
+    switch (tune("GRU", 0)) {
+        case 1:      // 16-cout blocks: 4x / 2x the CTAs
+            IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("gru.zr", in_zr, ezr, wzr, conv_tables(3, 1, 2, 8), B, 64, H, W, 4, st)));
+            IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("gru.q", in_q, eq, wq, conv_tables(3, 1, 2, 8), B, 32, H, W, 2, st)));
+            break;
+        case 2:      // 4-row tiles
+            IMVS_TRY((mma_conv<48, 32, 1, 4, 1, false>("gru.zr", in_zr, ezr, wzr, conv_tables(3, 1, 2, 4), B, 64, H, W, 2, st)));
+            IMVS_TRY((mma_conv<48, 32, 1, 4, 1, false>("gru.q", in_q, eq, wq, conv_tables(3, 1, 2, 4), B, 32, H, W, 1, st)));
+            break;
+        case 3:      // both
+            IMVS_TRY((mma_conv<48, 16, 1, 4, 1, false>("gru.zr", in_zr, ezr, wzr, conv_tables(3, 1, 2, 4), B, 64, H, W, 4, st)));
+            IMVS_TRY((mma_conv<48, 16, 1, 4, 1, false>("gru.q", in_q, eq, wq, conv_tables(3, 1, 2, 4), B, 32, H, W, 2, st)));
+            break;
+        default:
+            IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.zr", in_zr, ezr, wzr, conv_tables(3, 1, 2, 8), B, 64, H, W, 2, st)));
+            IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("gru.q", in_q, eq, wq, conv_tables(3, 1, 2, 8), B, 32, H, W, 1, st)));
+    }
     return 0;
 }
 
@@ -194,6 +213,7 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     IMVS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "depth_head: bad shape");
     IMVS_REQUIRE(!depth_out || (depth_min && depth_max), "depth_head: depth_out needs depth_min/depth_max");
     IMVS_REQUIRE(nd_pixel_stride >= 1, "depth_head: nd_pixel_stride must be >= 1");
+    ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     const bool want_conf = conf || conf_logit;
     const size_t P = (size_t)H * W;
@@ -206,13 +226,43 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
         IMVS_TRY((tc5::launch<32, 64>("head.conv0(tcgen05)", in_nhwc(hidden, H, W, 32), tc5::PixNHWC{t, nullptr, nullptr, H, W, 64, 1},
                                       w->head_conv0.umma, 3, 2, B, H, W, tc5_error_flag(), st)));
     } else {
-        IMVS_TRY((mma_conv<32, 32, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), EpiNHWC{t, nullptr, nullptr, H, W, 64, 64, 1},
-                                                   WSets::single(w->head_conv0), conv_tables(3, 1, 2, 8), B, 64, H, W, want_conf ? 2 : 1, st)));
+        const EpiNHWC e0{t, nullptr, nullptr, H, W, 64, 64, 1};
+        const int nc = want_conf ? 2 : 1;
+        switch (tune("HEAD", 0)) {
+            case 1:
+                IMVS_TRY((mma_conv<32, 16, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), e0, WSets::single(w->head_conv0),
+                                                           conv_tables(3, 1, 2, 8), B, 64, H, W, 2 * nc, st)));
+                break;
+            case 2:
+                IMVS_TRY((mma_conv<32, 32, 1, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), e0, WSets::single(w->head_conv0),
+                                                           conv_tables(3, 1, 2, 4), B, 64, H, W, nc, st)));
+                break;
+            case 3:
+                IMVS_TRY((mma_conv<32, 16, 1, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), e0, WSets::single(w->head_conv0),
+                                                           conv_tables(3, 1, 2, 4), B, 64, H, W, 2 * nc, st)));
+                break;
+            default:
+                IMVS_TRY((mma_conv<32, 32, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), e0, WSets::single(w->head_conv0),
+                                                           conv_tables(3, 1, 2, 8), B, 64, H, W, nc, st)));
+        }
     }
-    IMVS_TRY((mma_conv<32, 64, 2, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), EpiNHWC{h1, nullptr, nullptr, H, W, 64, 64, 1},
-                                              WSets::single(w->head_fc1), conv_tables(1, 1, 1, 8), B, 64, H, W, 1, st)));
-    IMVS_TRY((mma_conv<64, 64, 2, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), EpiNHWC{logits, w->head_fc2_b, nullptr, H, W, 256, 256, 0},
-                                              WSets::single(w->head_fc2), conv_tables(1, 1, 1, 8), B, 256, H, W, 4, st)));
+    {
+        const EpiNHWC e1{h1, nullptr, nullptr, H, W, 64, 64, 1};
+        const EpiNHWC e2{logits, w->head_fc2_b, nullptr, H, W, 256, 256, 0};
+        switch (tune("FC", 0)) {
+            case 1:      // fc1 in 16-cout blocks, fc2 in 32-cout blocks
+                IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), e1, WSets::single(w->head_fc1), conv_tables(1, 1, 1, 8), B, 64, H, W, 4, st)));
+                IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), e2, WSets::single(w->head_fc2), conv_tables(1, 1, 1, 8), B, 256, H, W, 8, st)));
+                break;
+            case 2:      // 4-row tiles
+                IMVS_TRY((mma_conv<32, 64, 1, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), e1, WSets::single(w->head_fc1), conv_tables(1, 1, 1, 4), B, 64, H, W, 1, st)));
+                IMVS_TRY((mma_conv<64, 64, 1, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), e2, WSets::single(w->head_fc2), conv_tables(1, 1, 1, 4), B, 256, H, W, 4, st)));
+                break;
+            default:
+                IMVS_TRY((mma_conv<32, 64, 2, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), e1, WSets::single(w->head_fc1), conv_tables(1, 1, 1, 8), B, 64, H, W, 1, st)));
+                IMVS_TRY((mma_conv<64, 64, 2, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), e2, WSets::single(w->head_fc2), conv_tables(1, 1, 1, 8), B, 256, H, W, 4, st)));
+        }
+    }
     RegressParams prm;
     prm.logits = logits; prm.t = t; prm.conf_w = w->conf_fc; prm.conf_b = w->conf_fc_b;
     prm.nd_out = nd_out; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
@@ -220,8 +270,6 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     prm.depth_min = depth_min; prm.depth_max = depth_max;
     prm.B = B; prm.P = (int)P;
     const size_t warps = (size_t)B * P;
-    softmax_regress_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(prm);
-    count_launch();
-    IMVS_LAUNCH_CHECK("softmax_regress_kernel");
+    IMVS_CUDA(launch_k(softmax_regress_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, prm));
     return 0;
 }

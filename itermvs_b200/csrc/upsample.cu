@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(UPS_THREADS) convex_upsample_kernel(const UpsP
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;                       // [64][144]
     float* sWarp = sW + 64 * 144;           // per warp [64][8]
+    pdl_trigger();                          // the 1x1 weights are constants: staged while the predecessor drains
     for (int i = threadIdx.x; i < 64 * 144 / 4; i += UPS_THREADS) reinterpret_cast<float4*>(sW)[i] = ldg4(prm.fc + 4 * i);
+    pdl_wait();
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* st = sWarp + warp * 64 * 8;
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(UPS_THREADS) convex_upsample_kernel(const UpsP
 
 // F.interpolate(scale_factor=4, mode='bilinear') of a [N][H][W] map (itermvs.py:323-324)
 __global__ void upsample4x_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int Ho = 4 * H, Wo = 4 * W;
     if (t >= (size_t)N * Ho * Wo) return;
@@ -120,6 +124,7 @@ extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea
     IMVS_REQUIRE(B >= 1 && H2 >= 1 && W2 >= 1 && (H2 * W2) % 8 == 0, "upsample_outputs: H2*W2 must be a multiple of 8");
     IMVS_REQUIRE(!conf || conf_up, "upsample_outputs: conf given without conf_up");
     IMVS_REQUIRE(nd_pixel_stride >= 1, "upsample_outputs: nd_pixel_stride must be >= 1");
+    ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     IMVS_TRY((mma_conv<32, 64, 2, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride),
                                                EpiNHWC{scratch, nullptr, nullptr, H2, W2, 64, 64, 1}, WSets::single(w->ups_conv0),
@@ -136,14 +141,10 @@ extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea
     IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int items = (B * H2 * W2) / 8;
     const int blocks = std::min(cdiv(items, UPS_THREADS / 32), 3 * sms);
-    convex_upsample_kernel<<<blocks, UPS_THREADS, smem, st>>>(prm);
-    count_launch();
-    IMVS_LAUNCH_CHECK("convex_upsample_kernel");
+    IMVS_CUDA(launch_k(convex_upsample_kernel, dim3(blocks), dim3(UPS_THREADS), smem, st, prm));
     if (conf) {
         size_t total = (size_t)B * H2 * W2 * 16;
-        upsample4x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(conf, conf_up, B, H2, W2);
-        count_launch();
-        IMVS_LAUNCH_CHECK("upsample4x_kernel");
+        IMVS_CUDA(launch_k(upsample4x_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, conf, conf_up, B, H2, W2));
     }
     return 0;
 }

@@ -1,5 +1,6 @@
 // Projection composition, the stand-alone differentiable_warping operator and layout helpers.
 // Reference: models/module.py:68-125 (FangjinhuaWang/IterMVS).
+#include <cstdlib>
 #include "common.cuh"
 #include "sampling.cuh"
 
@@ -19,6 +20,21 @@ void count_launch(int n) { g_launches += n; }
 long long launches_total() { return g_launches; }
 static int g_conv_passes = 4;
 int conv_passes() { return g_conv_passes; }
+// experiment switch for tile-shape A/B runs: IMVS_TUNE_<NAME>=<int> in the environment (read on every call; cheap)
+int tune(const char* name, int def) {
+    char key[64];
+    snprintf(key, sizeof key, "IMVS_TUNE_%s", name);
+    const char* e = getenv(key);
+    return e ? atoi(e) : def;
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("IMVS_PDL"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+static thread_local bool g_pdl_armed = false;
+static thread_local int g_api_depth = 0;
+bool* pdl_armed() { return &g_pdl_armed; }
+int* api_depth() { return &g_api_depth; }
 static int g_tc5 = 1;
 int tc5_enabled() { return g_tc5; }
 __device__ int g_tc5_err = 0;
@@ -114,6 +130,8 @@ __device__ void compose_one(const float* ref, const float* src, float* out12, in
 }
 
 __global__ void compose_kernel(const float* __restrict__ proj, int B, int V, float* __restrict__ out, int* nan_flag) {
+    pdl_trigger();
+    pdl_wait();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int S = V - 1;
     if (t >= B * S) return;
@@ -123,6 +141,8 @@ __global__ void compose_kernel(const float* __restrict__ proj, int B, int V, flo
 
 __global__ void compose_pair_kernel(const float* __restrict__ src_proj, const float* __restrict__ ref_proj, int B,
                                     float* __restrict__ out, int* nan_flag) {
+    pdl_trigger();
+    pdl_wait();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     compose_one(ref_proj + (size_t)b * 16, src_proj + (size_t)b * 16, out + (size_t)b * 12, nan_flag);
@@ -137,6 +157,8 @@ __global__ void compose_pair_kernel(const float* __restrict__ src_proj, const fl
 __global__ void warp_nchw_kernel(const float* __restrict__ fea, const float* __restrict__ rt,
                                  const float* __restrict__ depth, float* __restrict__ out,
                                  int B, int C, int H1, int W1, int D, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     int bd = blockIdx.z;
@@ -170,6 +192,8 @@ __global__ void warp_nchw_kernel(const float* __restrict__ fea, const float* __r
 __global__ void transpose_cp_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
     // in: [N][R][Cc] -> out: [N][Cc][R]
     __shared__ float tile[32][33];
+    pdl_trigger();
+    pdl_wait();
     int n = blockIdx.z;
     const float* src = in + (size_t)n * R * Cc;
     float* dst = out + (size_t)n * R * Cc;
@@ -188,9 +212,7 @@ __global__ void transpose_cp_kernel(const float* __restrict__ in, float* __restr
 static int transpose_launch(const float* in, float* out, int N, int R, int Cc, cudaStream_t st) {
     dim3 grid(cdiv(Cc, 32), cdiv(R, 32), N), block(32, 8);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: grid too large (R=%d N=%d)", R, N);
-    transpose_cp_kernel<<<grid, block, 0, st>>>(in, out, R, Cc);
-    count_launch();
-    IMVS_LAUNCH_CHECK("transpose_cp_kernel");
+    IMVS_CUDA(launch_k(transpose_cp_kernel, grid, block, 0, st, in, out, R, Cc));
     return 0;
 }
 
@@ -256,9 +278,8 @@ extern "C" int imvs_compose_projections(const float* proj, int B, int V, float* 
     IMVS_REQUIRE(proj && out, "compose_projections: null pointer");
     IMVS_REQUIRE(B >= 1 && V >= 2, "compose_projections: need B>=1 and at least one source view (B=%d V=%d)", B, V);
     int n = B * (V - 1);
-    compose_kernel<<<cdiv(n, 64), 64, 0, (cudaStream_t)stream>>>(proj, B, V, out, nan_flag);
-    count_launch();
-    IMVS_LAUNCH_CHECK("compose_kernel");
+    ApiScope api_;
+    IMVS_CUDA(launch_k(compose_kernel, dim3(cdiv(n, 64)), dim3(64), 0, (cudaStream_t)stream, proj, B, V, out, nan_flag));
     return 0;
 }
 
@@ -272,22 +293,21 @@ extern "C" int imvs_differentiable_warping(const float* src_fea, const float* sr
     IMVS_REQUIRE(H <= 65535 && (long long)B * D <= 65535, "differentiable_warping: H or B*D exceeds grid limits");
     cudaStream_t st = (cudaStream_t)stream;
     float* rt = rt_scratch;
-    compose_pair_kernel<<<cdiv(B, 32), 32, 0, st>>>(src_proj, ref_proj, B, rt, nan_flag);
-    count_launch();
-    IMVS_LAUNCH_CHECK("compose_pair_kernel");
+    ApiScope api_;
+    IMVS_CUDA(launch_k(compose_pair_kernel, dim3(cdiv(B, 32)), dim3(32), 0, st, src_proj, ref_proj, B, rt, nan_flag));
     dim3 grid(cdiv(W, 128), H, B * D);
-    warp_nchw_kernel<<<grid, 128, 0, st>>>(src_fea, rt, depth_samples, out, B, C, H1, W1, D, H, W);
-    count_launch();
-    IMVS_LAUNCH_CHECK("warp_nchw_kernel");
+    IMVS_CUDA(launch_k(warp_nchw_kernel, grid, dim3(128), 0, st, src_fea, (const float*)rt, depth_samples, out, B, C, H1, W1, D, H, W));
     return 0;
 }
 
 extern "C" int imvs_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, void* stream) {
     IMVS_REQUIRE(in && out && N >= 1 && C >= 1 && H >= 1 && W >= 1, "nchw_to_nhwc: bad argument");
+    ApiScope api_;
     return transpose_launch(in, out, N, C, H * W, (cudaStream_t)stream);   // [C][P] -> [P][C]
 }
 
 extern "C" int imvs_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, void* stream) {
     IMVS_REQUIRE(in && out && N >= 1 && C >= 1 && H >= 1 && W >= 1, "nhwc_to_nchw: bad argument");
+    ApiScope api_;
     return transpose_launch(in, out, N, H * W, C, (cudaStream_t)stream);   // [P][C] -> [C][P]
 }

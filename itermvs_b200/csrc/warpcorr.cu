@@ -403,6 +403,7 @@ template <int ST, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) warpcorr_iter_kernel(const IterParams5 q) {
     extern __shared__ float4 smem4[];
     __shared__ unsigned int next_item;
+    pdl_trigger();
     const IterParams& prm = q.p;
     const int S = ST ? ST : prm.V - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -422,6 +423,7 @@ __global__ void __launch_bounds__(NW * 32, 1) warpcorr_iter_kernel(const IterPar
     const unsigned per_level = r1 - r0, n_items = per_level * 3;
     if (threadIdx.x == 0) next_item = 2 * NW;
     __syncthreads();
+    pdl_wait();                     // nd / view weights / pyramids come from the preceding kernels
     ItemHeader<ST> cur, nxt;
     fetch_header<ST>(cur, q, warp, n_items, r0, per_level, S, lane);
     unsigned nxt_item = NW + warp;
@@ -518,6 +520,8 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
     float4* recW = smem4 + warp * 32 * S;
     int* recO = reinterpret_cast<int*>(smem4 + WC_WARPS * 32 * S) + warp * 32 * S;
     float* sP = reinterpret_cast<float*>(reinterpret_cast<int*>(smem4 + WC_WARPS * 32 * S) + WC_WARPS * 32 * S);
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = rt3[(size_t)b * S * 12 + i];
     __syncthreads();
     const int x = blockIdx.x * 2 + (warp & 1), y = blockIdx.y * 2 + (warp >> 1);
@@ -580,6 +584,8 @@ static size_t init_smem_bytes(int S) {
 // ---------------------------------------------------------------------------------------------
 __global__ void aggregate_init_kernel(const float* __restrict__ corr, const float* __restrict__ vw3,
                                       float* __restrict__ agg, int B, int S, int D, int P3) {
+    pdl_trigger();
+    pdl_wait();
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * D * P3 * 2;
     if (t >= total) return;
@@ -617,9 +623,9 @@ extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const flo
     dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
     const size_t smem = init_smem_bytes(V - 1);
-    warpcorr_init_kernel<<<grid, WC_WARPS * 32, smem, (cudaStream_t)stream>>>(fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D);
-    count_launch();
-    IMVS_LAUNCH_CHECK("warpcorr_init_kernel");
+    ApiScope api_;
+    IMVS_CUDA(launch_k(warpcorr_init_kernel, grid, dim3(WC_WARPS * 32), smem, (cudaStream_t)stream, fea3, rt3, depth_min, depth_max,
+                       depth_samples, corr, B, V, H3, W3, D));
     return 0;
 }
 
@@ -662,17 +668,15 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     q.n_tiles = (unsigned)tiles;
     q.strip_magic = ((1ULL << 40) + 2 * q.tiles_x - 1) / (2 * q.tiles_x);
     const int blocks = (int)std::min<long long>(tiles, sms);
-    kern<<<blocks, WC_ITER_WARPS * 32, smem, (cudaStream_t)stream>>>(q);
-    count_launch();
-    IMVS_LAUNCH_CHECK("warpcorr_iter_kernel");
+    ApiScope api_;
+    IMVS_CUDA(launch_k(kern, dim3(blocks), dim3(WC_ITER_WARPS * 32), smem, (cudaStream_t)stream, q));
     return 0;
 }
 
 extern "C" int imvs_aggregate_init(const float* corr, const float* vw3, float* agg, int B, int S, int D, int P3, void* stream) {
     IMVS_REQUIRE(corr && vw3 && agg && B >= 1 && S >= 1 && D >= 1 && P3 >= 1, "aggregate_init: bad argument");
     size_t total = (size_t)B * D * P3 * 2;
-    aggregate_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(corr, vw3, agg, B, S, D, P3);
-    count_launch();
-    IMVS_LAUNCH_CHECK("aggregate_init_kernel");
+    ApiScope api_;
+    IMVS_CUDA(launch_k(aggregate_init_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, corr, vw3, agg, B, S, D, P3));
     return 0;
 }
