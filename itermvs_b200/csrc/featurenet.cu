@@ -59,6 +59,74 @@ struct EpiSplit2 {
     }
 };
 
+// conv1 of FeatureNet (net.py:13): 3 -> 8 channels, 3x3, pad 1, folded BN + ReLU; planar image in, NHWC-8 out.
+// K = 27: the tensor-core engine pads this layer to K = 144 (one 16-channel k-step x 9 taps) and spends its
+// time staging zeros (112 us at 5 x 640 x 512).  Here it is exact fp32 FFMA: a 32 x 8-pixel tile per
+// 128-thread block, the three image planes with halo in shared memory, each thread two vertically adjacent
+// pixels x 8 output channels (432 FFMA per 12 image + 54 broadcast weight LDS).
+constexpr int C0_TW = 32, C0_TH = 8, C0_PITCH = C0_TW + 2;
+__global__ void __launch_bounds__(128)
+fnet_conv0_kernel(const float* __restrict__ img, const float* __restrict__ wgt, const float* __restrict__ bias,
+                  float* __restrict__ out, int H, int W) {
+    __shared__ float sI[3][C0_TH + 2][C0_PITCH];
+    __shared__ __align__(16) float sW[27][8];       // [(ky*3 + kx)*3 + cin][cout]
+    __shared__ __align__(16) float sB[8];
+    const int tid = threadIdx.x, n = blockIdx.z;
+    const int x0 = blockIdx.x * C0_TW, y0 = blockIdx.y * C0_TH;
+    pdl_trigger();
+    for (int i = tid; i < 27 * 8; i += 128) {       // packed weight: [tap][8 cin (3 used)][8 cout]
+        const int row = i >> 3, co = i & 7, tap = row / 3, c = row % 3;
+        sW[row][co] = ldg(wgt + (tap * 8 + c) * 8 + co);
+    }
+    if (tid < 8) sB[tid] = ldg(bias + tid);
+    pdl_wait();
+    const size_t plane = (size_t)H * W;
+    const float* src = img + (size_t)n * 3 * plane;
+    for (int i = tid; i < 3 * (C0_TH + 2) * C0_PITCH; i += 128) {
+        const int c = i / ((C0_TH + 2) * C0_PITCH), rem = i % ((C0_TH + 2) * C0_PITCH);
+        const int r = rem / C0_PITCH, col = rem % C0_PITCH;
+        const int y = y0 - 1 + r, x = x0 - 1 + col;
+        sI[c][r][col] = (y >= 0 && y < H && x >= 0 && x < W) ? ldg(src + c * plane + (size_t)y * W + x) : 0.f;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    float a0[8], a1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a0[k] = a1[k] = sB[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[r][k] = sI[c][2 * ty + r][tx + k];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 wa = *reinterpret_cast<const float4*>(&sW[(ky * 3 + kx) * 3 + c][0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&sW[(ky * 3 + kx) * 3 + c][4]);
+                const float p = v[ky][kx], q = v[ky + 1][kx];
+                a0[0] = fmaf(p, wa.x, a0[0]); a0[1] = fmaf(p, wa.y, a0[1]); a0[2] = fmaf(p, wa.z, a0[2]); a0[3] = fmaf(p, wa.w, a0[3]);
+                a0[4] = fmaf(p, wb.x, a0[4]); a0[5] = fmaf(p, wb.y, a0[5]); a0[6] = fmaf(p, wb.z, a0[6]); a0[7] = fmaf(p, wb.w, a0[7]);
+                a1[0] = fmaf(q, wa.x, a1[0]); a1[1] = fmaf(q, wa.y, a1[1]); a1[2] = fmaf(q, wa.z, a1[2]); a1[3] = fmaf(q, wa.w, a1[3]);
+                a1[4] = fmaf(q, wb.x, a1[4]); a1[5] = fmaf(q, wb.y, a1[5]); a1[6] = fmaf(q, wb.z, a1[6]); a1[7] = fmaf(q, wb.w, a1[7]);
+            }
+    }
+    const int x = x0 + tx, y = y0 + 2 * ty;
+    if (x >= W) return;
+    if (y < H) {
+        float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H + y) * W + x) * 8);
+        o[0] = make_float4(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f), fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f));
+        o[1] = make_float4(fmaxf(a0[4], 0.f), fmaxf(a0[5], 0.f), fmaxf(a0[6], 0.f), fmaxf(a0[7], 0.f));
+    }
+    if (y + 1 < H) {
+        float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H + y + 1) * W + x) * 8);
+        o[0] = make_float4(fmaxf(a1[0], 0.f), fmaxf(a1[1], 0.f), fmaxf(a1[2], 0.f), fmaxf(a1[3], 0.f));
+        o[1] = make_float4(fmaxf(a1[4], 0.f), fmaxf(a1[5], 0.f), fmaxf(a1[6], 0.f), fmaxf(a1[7], 0.f));
+    }
+}
+
 struct FnetBuffers {
     float *a0, *l1[4], *l2[4], *l3[4], *intra2, *intra1;
     size_t total;
@@ -127,15 +195,22 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8;
     const TapTables s1 = conv_tables(3, 1, 1, 8), k1 = conv_tables(1, 1, 1, 8);
     // conv1: 3 -> 8, BN, ReLU on the planar image (net.py:13)
-    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
-                                            WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
+    if (tune("CONV0", 1)) {
+        IMVS_REQUIRE(w->w[0].fp32 && w->b[0], "featurenet_forward: conv1 weights missing");
+        dim3 grid(cdiv(W, C0_TW), cdiv(H, C0_TH), N);
+        IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "fnet.conv1: grid too large");
+        IMVS_CUDA(launch_k(fnet_conv0_kernel, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+    } else {
+        IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
+                                                WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
+    }
     IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
     switch (tune("FNET2", 0)) {                                                          // layer2 -> l2[3]  [H/4][W/4][32]
         case 1: IMVS_TRY((res_stage<16, 32, true, false, 32, 16, 2>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
         case 2: IMVS_TRY((res_stage<16, 32, true, false, 64, 32, 1>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
         default: IMVS_TRY((res_stage<16, 32, true, false>(w, 6, b.l1[3], b.l2, N, H1, W1, st)));
     }
-    const int t3 = tune("FNET3", 0);
+    const int t3 = tune("FNET3", 2);
     const EpiNHWC eo3{fea3, w->b[16], nullptr, H3, W3, 48, 48, 0};
     switch (t3) {                                                                         // layer3 -> l3[3]  [H/8][W/8][48]; output3 (net.py:59)
         case 1:

@@ -119,6 +119,13 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// m16n8k8 FP16: A = 2 regs (row g / g+8, k = 2t, 2t+1), B = 1 reg (k = 2t, 2t+1; n = g) -- 8-channel inputs
+__device__ __forceinline__ void mma_f16_k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+
 // (v.x, v.y) = channels (k, k+1) -> hi = half2(fp16(v.x), fp16(v.y)) [k in the low half], lo = the remainder
 __device__ __forceinline__ void split_f16(float2 v, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
@@ -144,18 +151,23 @@ struct MmaCfg {
     static constexpr int TH = WARPS * MT;
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int NT = NB / 8;                       // n-tiles per CTA
-    static constexpr bool F16 = PASSES == 4;
-    static constexpr int CINK = F16 ? (CINP + 15) / 16 * 16 : CINP;   // K extent staged in smem (zero-filled beyond CINP)
+    static constexpr bool F16 = PASSES == 4 || PASSES == 5;
+    // PASSES = 5: mode 4 for 8-channel inputs on m16n8k8 (one k-step of 8 instead of a half-empty k-step of 16:
+    // half the A fragments, splits and tensor work); same packed weights, only the first 4 channel-pair rows are read
+    static constexpr bool K8 = PASSES == 5;
+    static_assert(!K8 || CINP == 8, "the k8 variant serves 8-channel inputs");
+    static constexpr int CINK = F16 ? (K8 ? 8 : (CINP + 15) / 16 * 16) : CINP;   // K extent staged in smem (zero-filled beyond CINP)
+    static constexpr int WROWS = (CINP + 15) / 16 * 8;      // FP16: channel-pair rows per tap in the PACKED weights
     // smem channel pitch (floats): TF32: CP/4 odd -> conflict-free LDS.32 A loads; FP16: CP = 8 or 24 mod 32
-    // -> conflict-free LDS.64 A loads
-    static constexpr int CP = F16 ? CINK + 8 : CINP + 4;
+    // -> conflict-free LDS.64 A loads (k8: 8 for stride 1, 12 for stride 2)
+    static constexpr int CP = K8 ? (STRIDE == 2 ? 12 : 8) : (F16 ? CINK + 8 : CINP + 4);
     // smem cout pitch: TF32: floats, = 8 or 24 mod 32; FP16: uint2 (hi, lo) units, 2*NP = 8 or 24 mod 32
     static constexpr int NP = F16 ? NB + 4 : NB + 8 + (NB == 8 ? 8 : 0);
     static constexpr int KSTEPS = F16 ? CINK / 16 : CINP / 8;
     static constexpr int WBUF = CINK * NP;                  // floats per weight stage (FP16: CINK/2 rows of NP uint2)
     static constexpr int RING = 3;
     static_assert(CINP % 8 == 0 && NB % 8 == 0, "channel padding");
-    static_assert(PASSES == 1 || PASSES == 3 || PASSES == 4, "PASSES");
+    static_assert(PASSES == 1 || PASSES == 3 || PASSES == 4 || PASSES == 5, "PASSES");
     static size_t smem_bytes(const TapTables& tt) {
         size_t tile = 0, taps = 0;
         for (int v = 0; v < tt.count; ++v) {
@@ -244,7 +256,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
     auto issue_weights = [&](int tap, int buf) {
         float* dst = sW + buf * Cfg::WBUF;
         if constexpr (Cfg::F16) {      // rows = channel pairs, NB (hi, lo) uint2 per row
-            const float* src = wg + 2 * (((size_t)taps.widx[tap] * (Cfg::CINK / 2)) * cout_total + cb * NB);
+            const float* src = wg + 2 * (((size_t)taps.widx[tap] * Cfg::WROWS) * cout_total + cb * NB);
             constexpr int Q = NB / 2;
             for (int i = tid; i < (Cfg::CINK / 2) * Q; i += Cfg::THREADS) {
                 const int k = i / Q, q = i % Q;
@@ -321,7 +333,30 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
             slot0[r] = (row * taps.IW + g * Cfg::STRIDE + rx) * CP;
             slot1[r] = (row * taps.IW + (g + 8) * Cfg::STRIDE + rx) * CP;
         }
-        if constexpr (Cfg::F16) {
+        if constexpr (Cfg::K8) {
+            const uint2* wb2 = reinterpret_cast<const uint2*>(wb);
+            uint32_t a[MT][2], al[MT][2];
+#pragma unroll
+            for (int r = 0; r < MT; ++r) {
+                split_f16(*reinterpret_cast<const float2*>(sA + slot0[r] + 2 * t), a[r][0], al[r][0]);
+                split_f16(*reinterpret_cast<const float2*>(sA + slot1[r] + 2 * t), a[r][1], al[r][1]);
+            }
+            uint2 w0[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) w0[j] = wb2[t * NP + 8 * j + g];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int r = 0; r < MT; ++r) mma_f16_k8(acc[r][j], al[r][0], al[r][1], w0[j].x);
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int r = 0; r < MT; ++r) mma_f16_k8(acc[r][j], a[r][0], a[r][1], w0[j].y);
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int r = 0; r < MT; ++r) mma_f16_k8(acc[r][j], a[r][0], a[r][1], w0[j].x);
+        } else if constexpr (Cfg::F16) {
             const uint2* wb2 = reinterpret_cast<const uint2*>(wb);
 #pragma unroll
             for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
@@ -446,6 +481,10 @@ int mma_conv(const char* name, const In& in, const Epi& epi, const WSets& ws, co
     sel.period = ws.period; sel.split1 = ws.split1; sel.split2 = ws.split2;
     if (conv_passes() == 4) {
         for (int i = 0; i < 3; ++i) sel.w[i] = static_cast<const float*>(ws.w[i].f16x3);
+        if constexpr (CINP == 8) {
+            if (tune("K8", 1))
+                return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 5, WALL>>(name, in, epi, sel, tabs, N, cout_total, Hout, Wout, ncb, st);
+        }
         return launch_mma_conv<MmaCfg<CINP, NB, MT, WARPS, STRIDE, 4, WALL>>(name, in, epi, sel, tabs, N, cout_total, Hout, Wout, ncb, st);
     }
     if (conv_passes() == 3) {

@@ -101,9 +101,14 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParam
     for (int a = 0; a < 8; ++a) { e[a] = expf(l[a] - m); s += e[a]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    // probabilities e / s are needed (a) to find the arg-max and (b) inside the +-4 window around it.  An IEEE
+    // division whose numerator is denormal / tiny takes the slow path, and after a few iterations most of the
+    // 256 bins are that small (the kernel went from 14 us to 25 us over the iterations).  (a) only bins with
+    // e > 0.5 can reach the maximum e_max / s = 1 / s (e <= 0.5 gives exactly half of it or less), so only
+    // those are divided; (b) divides the <= 9 window bins.  Same values as dividing everything.
     float pr[8];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) pr[a] = e[a] / s;
+    for (int a = 0; a < 8; ++a) pr[a] = e[a] > 0.5f ? e[a] / s : 0.f;
     // arg-max over probabilities, first index on ties (torch.argmax)
     float bv = -1.f;
     int bi = 0;
@@ -126,8 +131,11 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParam
         int mult = (ch >= bi - IMVS_RADIUS && ch <= bi + IMVS_RADIUS) ? 1 : 0;
         if (ch == 0) mult = max(0, IMVS_RADIUS + 1 - bi);
         if (ch == IMVS_OUT_BINS - 1) mult = max(0, bi - (IMVS_OUT_BINS - 2 - IMVS_RADIUS));
-        num = fmaf((float)(mult * ch), pr[a], num);
-        den = fmaf((float)mult, pr[a], den);
+        if (mult) {
+            const float pw = e[a] > 0.5f ? pr[a] : e[a] / s;
+            num = fmaf((float)(mult * ch), pw, num);
+            den = fmaf((float)mult, pw, den);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParam
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
             const int ch = a < 4 ? 4 * lane + a : 128 + 4 * lane + (a - 4);
-            prm.prob[((size_t)b * IMVS_OUT_BINS + ch) * prm.P + p] = pr[a];
+            prm.prob[((size_t)b * IMVS_OUT_BINS + ch) * prm.P + p] = e[a] / s;
         }
     }
     const bool want_conf = (prm.conf != nullptr) || (prm.conf_logit != nullptr);
@@ -185,7 +193,7 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
     const EpiGruZR ezr{w->gru_zr_b, h, z, rh, H, W};
     const EpiGruQ eq{w->gru_q_b, z, h, H, W};
     const WSets wzr = WSets::single(w->gru_zr), wq = WSets::single(w->gru_q);
-    switch (tune("GRU", 0)) {
+    switch (tune("GRU", 2)) {
         case 1:      // 16-cout blocks: 4x / 2x the CTAs
             IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("gru.zr", in_zr, ezr, wzr, conv_tables(3, 1, 2, 8), B, 64, H, W, 4, st)));
             IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("gru.q", in_q, eq, wq, conv_tables(3, 1, 2, 8), B, 32, H, W, 2, st)));
@@ -228,7 +236,7 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     } else {
         const EpiNHWC e0{t, nullptr, nullptr, H, W, 64, 64, 1};
         const int nc = want_conf ? 2 : 1;
-        switch (tune("HEAD", 0)) {
+        switch (tune("HEAD", 2)) {
             case 1:
                 IMVS_TRY((mma_conv<32, 16, 2, 4, 1, false>("head.conv0", in_nhwc(hidden, H, W, 32), e0, WSets::single(w->head_conv0),
                                                            conv_tables(3, 1, 2, 8), B, 64, H, W, 2 * nc, st)));
@@ -249,7 +257,7 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
     {
         const EpiNHWC e1{h1, nullptr, nullptr, H, W, 64, 64, 1};
         const EpiNHWC e2{logits, w->head_fc2_b, nullptr, H, W, 256, 256, 0};
-        switch (tune("FC", 0)) {
+        switch (tune("FC", 2)) {
             case 1:      // fc1 in 16-cout blocks, fc2 in 32-cout blocks
                 IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), e1, WSets::single(w->head_fc1), conv_tables(1, 1, 1, 8), B, 64, H, W, 4, st)));
                 IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), e2, WSets::single(w->head_fc2), conv_tables(1, 1, 1, 8), B, 256, H, W, 8, st)));

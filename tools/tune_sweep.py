@@ -6,8 +6,14 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SWEEPS = [("", 0)] + [(k, v) for k, vals in (("GRU", (1, 2, 3)), ("HEAD", (1, 2, 3)), ("FC", (1, 2)), ("FNET2", (1, 2)),
-                                              ("FNET3", (1, 2, 3))) for v in vals]
+SWEEPS = [("", 0)] + [(k, v) for k, vals in (("PDL", (0,)), ("K8", (0,)), ("CONV0", (0,)), ("GRU", (0,)), ("HEAD", (0,)), ("FC", (0,)),
+                                              ("FNET3", (0,))) for v in vals]
+
+
+def setenv(env, k, v):
+    env["IMVS_PDL" if k == "PDL" else f"IMVS_TUNE_{k}"] = str(v)      # PDL is a global switch, the rest tile-shape switches
+
+
 if len(sys.argv) > 1:      # explicit settings: NAME=V,NAME=V ...
     SWEEPS = [(a, None) for a in sys.argv[1:]]
 for name, val in SWEEPS:
@@ -15,11 +21,11 @@ for name, val in SWEEPS:
     if val is None:
         for kv in name.split(","):
             k, v = kv.split("=")
-            env[f"IMVS_TUNE_{k}"] = v
+            setenv(env, k, v)
         label = name
     else:
         if name:
-            env[f"IMVS_TUNE_{name}"] = str(val)
+            setenv(env, name, val)
         label = f"{name}={val}" if name else "base"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-cpu-baseline"],
                        env=env, capture_output=True, text=True)
