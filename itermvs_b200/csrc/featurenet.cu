@@ -149,23 +149,23 @@ static FnetBuffers fnet_carve(float* base, size_t N, size_t H, size_t W) {
 
 // one residual stage (two ResidualBlocks, module.py:32-50):  x [Hin][Win][CI] -> buf[3] [Hin/2][Win/2][CO]
 // NBA / NBB: cout block of the stride-2 [conv1 | downsample] GEMM / of the CO -> CO convolutions; MT: row-tiles per warp
-template <int CI, int CO, bool WALL_A, bool WALL_B, int NBA = 2 * CO, int NBB = CO, int MT = 2>
+template <int CI, int CO, bool WALL_A, bool WALL_B, int NBA = 2 * CO, int NBB = CO, int MT = 2, int WARPS = 4>
 static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, float* const buf[4], int N, int Hin, int Win,
                      cudaStream_t st) {
     const int H = Hin / 2, W = Win / 2;
-    const TapTables s2 = conv_tables(3, 2, 1, 4 * MT), s1 = conv_tables(3, 1, 1, 4 * MT);
+    const TapTables s2 = conv_tables(3, 2, 1, WARPS * MT), s1 = conv_tables(3, 1, 1, WARPS * MT);
     constexpr int NCA = 2 * CO / NBA, NCB = CO / NBB;
     // block 0: [conv1 (stride 2, relu) | downsample (stride 2)] as one GEMM, then conv2 + downsample -> relu
     const int LS = 21 + (L - 1) / 5;           // stacked [conv1 | downsample] weights of this stage
-    IMVS_TRY((mma_conv<CI, NBA, MT, 4, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
+    IMVS_TRY((mma_conv<CI, NBA, MT, WARPS, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
                                                   EpiSplit2{buf[0], buf[1], w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO,
                                                   H, W, NCA, st)));
-    IMVS_TRY((mma_conv<CO, NBB, MT, 4, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
+    IMVS_TRY((mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
                                                   WSets::single(w->w[L + 1]), s1, N, CO, H, W, NCB, st)));
     // block 1: conv1 relu, conv2 + x -> relu
-    IMVS_TRY((mma_conv<CO, NBB, MT, 4, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
+    IMVS_TRY((mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
                                                   WSets::single(w->w[L + 3]), s1, N, CO, H, W, NCB, st)));
-    IMVS_TRY((mma_conv<CO, NBB, MT, 4, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
+    IMVS_TRY((mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
                                                   WSets::single(w->w[L + 4]), s1, N, CO, H, W, NCB, st)));
     return 0;
 }
@@ -204,7 +204,9 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
         IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                                 WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     }
-    IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
+    const int w8 = tune("FNETW", 0);     // 1: 8 warps x 1 row-tile per CTA instead of 4 x 2 (same tile, twice the resident warps)
+    if (w8) IMVS_TRY((res_stage<8, 16, true, true, 32, 16, 1, 8>(w, 1, b.a0, b.l1, N, H, W, st)));
+    else IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
     switch (tune("FNET2", 0)) {                                                          // layer2 -> l2[3]  [H/4][W/4][32]
         case 1: IMVS_TRY((res_stage<16, 32, true, false, 32, 16, 2>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
         case 2: IMVS_TRY((res_stage<16, 32, true, false, 64, 32, 1>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
@@ -229,15 +231,19 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
             IMVS_TRY((res_stage<32, 48, false, false>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
             IMVS_TRY((mma_conv<48, 48, 2, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), s1, N, 48, H3, W3, 1, st)));
     }
-    // intra2 = up2(f3) + inner2(f2); output2 (net.py:60-62)
-    IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2{b.intra2, w->b[17], b.l3[3], H2, W2, 48},
-                                              WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
-    IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), EpiNHWC{fea2, w->b[18], nullptr, H2, W2, 32, 32, 0},
-                                               WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
-    // intra1 = up2(intra2) + inner1(f1); output1 (net.py:63-64)
-    IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2{b.intra1, w->b[19], b.intra2, H1, W1, 48},
-                                              WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
-    IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), EpiNHWC{fea1, w->b[20], nullptr, H1, W1, 16, 16, 0},
-                                               WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
+    // intra2 = up2(f3) + inner2(f2); output2 (net.py:60-62); intra1 = up2(intra2) + inner1(f1); output1 (net.py:63-64)
+    const EpiAddUp2 ei2{b.intra2, w->b[17], b.l3[3], H2, W2, 48}, ei1{b.intra1, w->b[19], b.intra2, H1, W1, 48};
+    const EpiNHWC eo2{fea2, w->b[18], nullptr, H2, W2, 32, 32, 0}, eo1{fea1, w->b[20], nullptr, H1, W1, 16, 16, 0};
+    if (w8) {
+        IMVS_TRY((mma_conv<32, 48, 1, 8, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), ei2, WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<48, 32, 1, 8, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<16, 48, 1, 8, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), ei1, WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
+        IMVS_TRY((mma_conv<48, 16, 1, 8, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
+    } else {
+        IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), ei2, WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), ei1, WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
+        IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
+    }
     return 0;
 }

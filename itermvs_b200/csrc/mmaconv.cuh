@@ -128,6 +128,10 @@ __device__ __forceinline__ void mma_f16_k8(float (&c)[4], uint32_t a0, uint32_t 
 
 // (v.x, v.y) = channels (k, k+1) -> hi = half2(fp16(v.x), fp16(v.y)) [k in the low half], lo = the remainder
 __device__ __forceinline__ void split_f16(float2 v, uint32_t& hi, uint32_t& lo) {
+#ifdef IMVS_FAKE_SPLIT      // timing experiment only (wrong results): what the loop costs when the tile is already split
+    hi = __float_as_uint(v.x); lo = __float_as_uint(v.y);
+    return;
+#endif
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y - hf.y), "f"(v.x - hf.x));
@@ -307,13 +311,22 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         cp_async_commit();              // group 1: tap-1 weights
     }
 
-    float acc[MT][NT][4];
+    // FP16 3-product mode: the products of one output tile go to SEPARATE accumulator sets when the warp owns
+    // few tiles (set 0: hi*hi, set 1: cross terms, or one set per product), summed once in the epilogue.  With
+    // one set, consecutive HMMAs on a tile are MT*NT (= 4 for a 16-channel layer) instructions apart -- about the
+    // HMMA latency -- and the warps sat in fixed-latency dependency stalls (ncu: 'wait' 30 %, tensor pipe 34 %).
+    constexpr int NACC = !Cfg::F16 ? 1 : (MT * NT <= 4 ? 3 : (MT * NT <= 8 ? 2 : 1));
+    constexpr int ACC_LH = NACC == 3 ? 1 : NACC - 1, ACC_HL = NACC == 3 ? 2 : NACC - 1;     // lo*hi, hi*lo; hi*hi -> set 0
+    float accs[NACC][MT][NT][4];
+    float (&acc)[MT][NT][4] = accs[0];
 #pragma unroll
-    for (int r = 0; r < MT; ++r)
+    for (int s = 0; s < NACC; ++s)
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+        for (int r = 0; r < MT; ++r)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[r][j][q] = 0.f;
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) accs[s][r][j][q] = 0.f;
 
     for (int tap = 0; tap < ntaps; ++tap) {
         int wsel_buf = tap;
@@ -347,11 +360,11 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int r = 0; r < MT; ++r) mma_f16_k8(acc[r][j], al[r][0], al[r][1], w0[j].x);
+                for (int r = 0; r < MT; ++r) mma_f16_k8(accs[ACC_LH][r][j], al[r][0], al[r][1], w0[j].x);
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int r = 0; r < MT; ++r) mma_f16_k8(acc[r][j], a[r][0], a[r][1], w0[j].y);
+                for (int r = 0; r < MT; ++r) mma_f16_k8(accs[ACC_HL][r][j], a[r][0], a[r][1], w0[j].y);
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -380,11 +393,11 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
-                    for (int r = 0; r < MT; ++r) mma_f16(acc[r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0[j].x, w1[j].x);
+                    for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_LH][r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0[j].x, w1[j].x);
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
-                    for (int r = 0; r < MT; ++r) mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].y, w1[j].y);
+                    for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_HL][r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].y, w1[j].y);
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -429,6 +442,18 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         }
     }
 
+    if constexpr (NACC > 1) {           // small terms first, then onto the hi*hi sums
+#pragma unroll
+        for (int r = 0; r < MT; ++r)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float cross = accs[NACC - 1][r][j][q];
+                    if constexpr (NACC == 3) cross += accs[1][r][j][q];
+                    acc[r][j][q] += cross;
+                }
+    }
     // epilogue: thread holds, per row-tile r and half h, couts {8j + 2t, 8j + 2t + 1} of pixel x = g + 8h
 #pragma unroll
     for (int r = 0; r < MT; ++r) {

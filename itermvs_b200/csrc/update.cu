@@ -105,10 +105,11 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParam
     // division whose numerator is denormal / tiny takes the slow path, and after a few iterations most of the
     // 256 bins are that small (the kernel went from 14 us to 25 us over the iterations).  (a) only bins with
     // e > 0.5 can reach the maximum e_max / s = 1 / s (e <= 0.5 gives exactly half of it or less), so only
-    // those are divided; (b) divides the <= 9 window bins.  Same values as dividing everything.
+    // those are divided; (b) divides the <= 9 window bins.  Same values as dividing everything.  The guards
+    // are on the NUMERATOR (the compiler hoists a division out of a conditional and selects afterwards).
     float pr[8];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) pr[a] = e[a] > 0.5f ? e[a] / s : 0.f;
+    for (int a = 0; a < 8; ++a) pr[a] = e[a] > 0.5f ? fmaxf(e[a], 0.5f) / s : 0.f;
     // arg-max over probabilities, first index on ties (torch.argmax)
     float bv = -1.f;
     int bi = 0;
@@ -131,11 +132,9 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParam
         int mult = (ch >= bi - IMVS_RADIUS && ch <= bi + IMVS_RADIUS) ? 1 : 0;
         if (ch == 0) mult = max(0, IMVS_RADIUS + 1 - bi);
         if (ch == IMVS_OUT_BINS - 1) mult = max(0, bi - (IMVS_OUT_BINS - 2 - IMVS_RADIUS));
-        if (mult) {
-            const float pw = e[a] > 0.5f ? pr[a] : e[a] / s;
-            num = fmaf((float)(mult * ch), pw, num);
-            den = fmaf((float)mult, pw, den);
-        }
+        const float pw = (mult ? e[a] : 1.0f) / s;          // bins outside the window: harmless fast-path division
+        num = fmaf((float)(mult * ch), pw, num);
+        den = fmaf((float)mult, pw, den);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

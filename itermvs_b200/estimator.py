@@ -413,11 +413,68 @@ class IterMVS(nn.Module):
             nan_flag.ptr() if nan_flag is not None else None, ops._stream()), "itermvs_forward")
         return out
 
+    def _upsample_outputs(self, ref2: Tensor, nd: Tensor, conf: Optional[Tensor], depth_min: Tensor, depth_max: Tensor):
+        """itermvs.py:262-264 + 310-314 / 321-324 in one call: weight net on the level-2 reference feature, softmax
+        over the 9 taps, convex x4 upsampling of `nd`, depth_unnormalization, bilinear x4 of the confidence."""
+        b, _, h, w = ref2.shape
+        dev = ref2.device
+        fea = _nhwc(ref2)
+        depth_up = torch.empty(b, 1, 4 * h, 4 * w, device=dev)
+        conf_up = torch.empty(b, 1, 4 * h, 4 * w, device=dev) if conf is not None else None
+        scratch = torch.empty(b * 64 * h * w, device=dev)
+        nd = ops._chk(nd, "normalized_depth")
+        _lib.check(_lib.lib().imvs_upsample_outputs(self.packed(dev).ref, fea.data_ptr(), h * w * fea.shape[-1], nd.data_ptr(), h * w, 1,
+                                                    ops._p(conf), depth_min.data_ptr(), depth_max.data_ptr(), depth_up.data_ptr(),
+                                                    ops._p(conf_up), scratch.data_ptr(), b, h, w, ops._stream()), "upsample_outputs")
+        return depth_up, conf_up
+
+    def _forward_all_predictions(self, ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max):
+        """The test=False structure of itermvs.py:253-329 -- every intermediate prediction (initial depth, one
+        depth / probability / confidence logit per update) -- as a FORWARD pass on the CUDA operators.  This is what
+        train.py's validation loop (train.py:257, model.eval() under no_grad) and full_loss consume.  Gradients are
+        not provided: the backward kernels are not built ('next')."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "itermvs_b200.IterMVS(test=False): forward-only (validation) -- the backward kernels are not built; "
+                "call it under torch.no_grad() as train.py's validate_sample does, or freeze the parameters")
+        depths = {"combine": [], "probability": [], "initial": []}
+        confidences, depths_upsampled, confidence_upsampled = [], [], None
+        ref2 = ops._chk(ref_feature["level2"], "ref_feature")
+        dev = ref2.device
+        batch, _, height, width = ref2.shape
+        dmin, dmax = ops._chk(depth_min.float(), "depth_min"), ops._chk(depth_max.float(), "depth_max")
+        inv_min, inv_max = (1.0 / dmin).view(batch, 1, 1, 1), (1.0 / dmax).view(batch, 1, 1, 1)
+        upd = self.update
+        saved, upd.return_probability = upd.return_probability, True
+        try:
+            samples0 = self.depth_initialization(inv_min, inv_max, height // 2, width // 2, dev)
+            view_weights, corr, depth = self.evaluation(ref_feature, src_features, ref_proj, src_projs, samples0, inv_min, inv_max)
+            depths["initial"].append(depth)
+            hidden = upd.hidden_init(corr)
+            nd, prob, conf, conf0 = upd._heads_nhwc(_nhwc(hidden), True)          # depth_init + conf_init (itermvs.py:276-279)
+            depths["combine"].append(ops.depth_unnormalization(nd, inv_min, inv_max))
+            depths["probability"].append(prob)
+            confidences.append(conf0)
+            for it in range(self.iteration):
+                samples = {}
+                for lvl in ("level1", "level2", "level3"):                        # itermvs.py:289-293
+                    ns = torch.clamp(nd + self.corr_interval[lvl].to(dev) * self.interval_scale, min=0, max=1)
+                    samples[lvl] = ops.depth_unnormalization(ns, inv_min, inv_max)
+                corr = self.evaluation(ref_feature, src_features, ref_proj, src_projs, samples, view_weights=view_weights)
+                hidden, nd, prob, conf, conf0 = upd(hidden, nd, corr, confidence_flag=True)
+                depths["combine"].append(ops.depth_unnormalization(nd, inv_min, inv_max))
+                depths["probability"].append(prob)
+                confidences.append(conf0)
+                if it == self.iteration - 1:
+                    depth_up, confidence_upsampled = self._upsample_outputs(ref2, nd, conf, dmin, dmax)
+                    depths_upsampled.append(depth_up)
+        finally:
+            upd.return_probability = saved
+        return depths, depths_upsampled, confidences, confidence_upsampled
+
     def forward(self, ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max):
         if not self.test:
-            raise NotImplementedError(
-                "itermvs_b200.IterMVS: the training-mode forward (test=False) is not built in this round; "
-                "see DESIGN.md ('out of scope / next').  Inference (test=True) is the supported path.")
+            return self._forward_all_predictions(ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max)
         dev = ref_feature["level2"].device
         feas = [_stack_views(ops._chk(ref_feature[f"level{l}"], "ref_feature"), src_features[f"level{l}"]) for l in (1, 2, 3)]
         projs = [_stack_proj(ref_proj[f"level{l}"], src_projs[f"level{l}"]).to(dev) for l in (1, 2, 3)]
