@@ -3,7 +3,10 @@ signature, output dict keys and state_dict keys -- checkpoints saved by the refe
 load with `load_state_dict`, with or without the DataParallel 'module.' prefix stripped).
 
 Pipeline.forward(imgs, proj_matrices, depth_min, depth_max)            reference net.py:78
-    test mode  -> {"depths_upsampled", "confidence_upsampled"}         reference net.py:125-128
+    test=True  -> {"depths_upsampled", "confidence_upsampled"}         reference net.py:125-128
+    test=False -> {"depths": {"combine","probability","initial"}, "depths_upsampled", "confidences",
+                   "confidence_upsampled"}  (net.py:115-120) -- forward only (validation); no backward kernels
+full_loss(...)                                                         reference net.py:131-190
 """
 from __future__ import annotations
 
@@ -12,6 +15,7 @@ from typing import Dict
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib
 from . import _pack
@@ -121,13 +125,27 @@ class Pipeline(nn.Module):
             state_dict = {k[7:]: v for k, v in state_dict.items()}
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
+    def _forward_all_predictions(self, imgs, proj_matrices, depth_min, depth_max):
+        """test=False output structure (net.py:100-120), forward only: what train.py's validation pass
+        (train.py:250-262, model.eval() under no_grad) and full_loss consume."""
+        features = self.feature_net(imgs["level_0"])                      # reference format: level -> list of views
+        ref_feature = {k: v[0] for k, v in features.items()}
+        src_features = {k: v[1:] for k, v in features.items()}
+        ref_proj, src_projs = {}, {}
+        for l in (1, 2, 3):
+            pm = torch.unbind(proj_matrices[f"level_{l}"].float(), 1)
+            ref_proj[f"level{l}"], src_projs[f"level{l}"] = pm[0], list(pm[1:])
+        depths, depths_upsampled, confidences, confidence_upsampled = self.iter_mvs(
+            ref_feature, src_features, ref_proj, src_projs, depth_min.float(), depth_max.float())
+        return {"depths": depths, "depths_upsampled": depths_upsampled, "confidences": confidences,
+                "confidence_upsampled": confidence_upsampled}
+
     def forward(self, imgs, proj_matrices, depth_min, depth_max):
-        if not self.test:
-            raise NotImplementedError("itermvs_b200.Pipeline(test=False): training forward is not built in this round "
-                                      "(DESIGN.md, 'next'); use test=True")
         x = imgs["level_0"]
         if not x.is_cuda:
             raise RuntimeError("itermvs_b200.Pipeline: inputs must be CUDA tensors (there is no CPU path)")
+        if not self.test:
+            return self._forward_all_predictions(imgs, proj_matrices, depth_min, depth_max)
         f1, f2, f3 = self.feature_net.forward_nhwc(x)
         projs = [ops._chk(proj_matrices[f"level_{l}"].float(), "proj_matrices") for l in (1, 2, 3)]   # net.py:96-98
         flag = ops.NanFlag(x.device)
@@ -138,6 +156,55 @@ class Pipeline(nn.Module):
         return {"depths_upsampled": depth_up, "confidence_upsampled": conf_up}
 
 
-def full_loss(*args, **kwargs):
-    raise NotImplementedError("itermvs_b200.full_loss: the training loss (net.py:131-190) stays with the reference's "
-                              "PyTorch implementation; it is outside the hot path (SURVEY.md section 2, row 3)")
+def _masked_l1(a: Tensor, b: Tensor, mask: Tensor) -> Tensor:
+    return F.l1_loss(a[mask], b[mask], reduction="mean")
+
+
+def full_loss(depths, depths_upsampled, confidences, depths_gt, mask, depth_min, depth_max, regress=True):
+    """Training / validation loss of the reference (models/net.py:131-190), same signature and value.
+
+    Host-side PyTorch (it is not on the hot path: a handful of reductions over quarter-resolution maps); runs on
+    whatever device the predictions live on.  Terms, with N predictions (init + one per update) and 256 bins:
+      * 0.8^N   * 256 * L1(normalized initial depth, normalized gt)                        [level_2 mask]
+      * 0.8^(N-1-i) * cross-entropy of prediction i's 256-bin distribution against the one-hot gt bin
+        (D = probability.size(1) bins over the clamped normalized gt; probabilities clamped at 1e-5)
+      * if regress: 0.8^(N-1-i) * 256 * L1 on the pixels whose gt bin lies within +-4 of the arg-max bin,
+        and 0.8^(N-1-i) * BCE-with-logits of the confidence logit against [|nd - nd_gt| < 0.002]
+      * 256 * L1(normalized upsampled depth, normalized gt)                                [level_0 mask]
+    """
+    radius, out_num_samples = 4, 256
+    probs = depths["probability"]
+    num_sample = probs[0].size(1)
+    m0, m2 = mask["level_0"] > 0.5, mask["level_2"] > 0.5
+    gt0, gt2 = depths_gt["level_0"], depths_gt["level_2"]
+    batch = gt2.size(0)
+    inv_min = (1.0 / depth_min).view(batch, 1, 1, 1)
+    inv_max = (1.0 / depth_max).view(batch, 1, 1, 1)
+    nd_gt = ops.depth_normalization(gt2, inv_min, inv_max)
+    gt_bin = torch.floor(torch.clamp(nd_gt, min=0, max=1) * (num_sample - 1) * m2.float()).long()
+    onehot = torch.zeros_like(probs[0]).scatter_(1, gt_bin, 1)
+    n_pred = len(depths["combine"])
+
+    nd = ops.depth_normalization(depths["initial"][0], inv_min, inv_max)
+    loss = 0.8 ** n_pred * out_num_samples * _masked_l1(nd, nd_gt, m2)
+    bce = nn.BCEWithLogitsLoss()
+    for i in range(n_pred):
+        weight = 0.8 ** (n_pred - i - 1)
+        p = torch.clamp(probs[i], min=1e-5)
+        ce = -torch.sum(onehot * torch.log(p), dim=1, keepdim=True)
+        loss = loss + weight * torch.mean(ce[m2])
+        if not regress:
+            continue
+        with torch.no_grad():
+            top = torch.argmax(p, dim=1, keepdim=True).float()
+            near = (gt_bin >= top - radius) & (gt_bin <= top + radius)
+        nd = ops.depth_normalization(depths["combine"][i], inv_min, inv_max)
+        sel = m2 & near
+        if torch.sum(sel) > 0:
+            loss = loss + weight * out_num_samples * _masked_l1(nd, nd_gt, sel)
+        target = (torch.abs(nd[m2].detach() - nd_gt[m2]) < 0.002).float()
+        loss = loss + weight * bce(confidences[i][m2], target)
+
+    nd_gt0 = ops.depth_normalization(gt0, inv_min, inv_max)
+    nd_up = ops.depth_normalization(depths_upsampled[0], inv_min, inv_max)
+    return loss + out_num_samples * _masked_l1(nd_up, nd_gt0, m0)

@@ -48,3 +48,14 @@ def e2e_d8():
 @pytest.fixture(scope="session")
 def e2e_d32():
     return _load_npz("e2e_d32.npz")
+
+
+@pytest.fixture(scope="session")
+def e2e_allpred():
+    """Reference Pipeline(test=False).eval() outputs + full_loss (tests/golden/make_golden_train.py)."""
+    return _load_npz("e2e_allpred_d32.npz")
+
+
+@pytest.fixture(scope="session")
+def loss_kat():
+    return _load_npz("loss_kat.npz")

@@ -155,3 +155,37 @@ def test_synthetic_generator_is_deterministic():
     np.testing.assert_allclose(K3[:2] * 8, K0[:2], rtol=1e-12)
     gt = plane_depth_map(160, 128)
     assert 600 < gt.min() < gt.max() < 700
+
+
+def _loss_inputs(z, n_pred=3):
+    t = lambda k: torch.from_numpy(z[k])
+    depths = {"initial": [t("initial")], "combine": [t(f"combine{i}") for i in range(n_pred)],
+              "probability": [t(f"probability{i}") for i in range(n_pred)]}
+    conf = [t(f"confidence{i}") for i in range(n_pred)]
+    gt = {"level_0": t("gt0"), "level_2": t("gt2")}
+    mask = {"level_0": t("mask0"), "level_2": t("mask2")}
+    return depths, [t("upsampled")], conf, gt, mask, t("depth_min"), t("depth_max")
+
+
+def test_full_loss_matches_reference_value(loss_kat):
+    """full_loss (net.py:131-190) against the value the reference's own function returned for the same seeded
+    predictions (batch 2, masks, gt outside the depth range, arg-max near / far from the gt bin)."""
+    from itermvs_b200 import full_loss
+    args = _loss_inputs(loss_kat)
+    assert abs(float(full_loss(*args)) - float(loss_kat["loss"])) < 1e-5 * float(loss_kat["loss"])
+    assert abs(float(full_loss(*args, regress=False)) - float(loss_kat["loss_noregress"])) < 1e-5 * float(loss_kat["loss_noregress"])
+    # gradient flows to the predictions the reference trains on (host-side autograd; the CUDA backward is not built)
+    depths, ups, conf, gt, mask, dmin, dmax = args
+    ups[0].requires_grad_(True)
+    conf[-1].requires_grad_(True)
+    full_loss(depths, ups, conf, gt, mask, dmin, dmax).backward()
+    assert ups[0].grad.abs().sum() > 0 and conf[-1].grad.abs().sum() > 0
+
+
+def test_all_predictions_forward_refuses_autograd(dtu_weights):
+    """test=False is forward-only: with trainable parameters and grad enabled it must refuse, not silently detach."""
+    import itermvs_b200
+    m = itermvs_b200.IterMVS(2, 32, 32, test=False)
+    x = {f"level{l}": torch.zeros(1, c, 8, 8) for l, c in ((1, 16), (2, 32), (3, 48))}
+    with pytest.raises(NotImplementedError):
+        m(x, {k: [] for k in x}, {}, {}, torch.ones(1), torch.ones(1))

@@ -244,6 +244,59 @@ def test_pipeline_matches_reference_fixture(dev, dtu_weights, request, which):
     assert float((np.abs(cu_.cpu().numpy() - fix["confidence_upsampled"]) > 1e-3).mean()) < 0.03
 
 
+def test_all_predictions_forward_matches_reference(dev, dtu_weights, e2e_allpred):
+    """Pipeline(test=False).eval() under no_grad -- train.py's validation pass -- against the reference's own
+    outputs: initial depth, every intermediate depth / probability / confidence logit, the upsampled outputs,
+    and full_loss evaluated on them."""
+    import itermvs_b200
+    from itermvs_b200.synthetic import plane_depth_map
+    fix = e2e_allpred
+    w, h = int(fix["width"]), int(fix["height"])
+    m = itermvs_b200.Pipeline(iteration=int(fix["iteration"]), test=False)
+    m.load_state_dict(dtu_weights, strict=True)
+    m = m.to(dev).eval()
+    s = make_sample(w, h, n_src=int(fix["n_src"]), batch=1, seed=int(fix["seed"]), scene="plane")
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    with torch.no_grad():
+        out = m(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    assert set(out) == {"depths", "depths_upsampled", "confidences", "confidence_upsampled"}
+    assert set(out["depths"]) == {"combine", "probability", "initial"}
+    n_pred = int(fix["iteration"]) + 1
+    assert len(out["depths"]["combine"]) == n_pred and len(out["depths"]["probability"]) == n_pred
+    assert len(out["confidences"]) == n_pred and len(out["depths_upsampled"]) == 1
+    rel = lambda a, b: np.abs(a.cpu().numpy() - b) / np.abs(b)
+    assert np.median(rel(out["depths"]["initial"][0], fix["depth_initial"])) < 1e-5
+    assert (rel(out["depths"]["initial"][0], fix["depth_initial"]) > 1e-3).mean() < 0.01
+    for i in range(n_pred):
+        r = rel(out["depths"]["combine"][i], fix[f"combine{i}"])
+        assert np.median(r) < 2e-5 and (r > 1e-3).mean() < 0.02, (i, np.median(r), (r > 1e-3).mean())
+        p = out["depths"]["probability"][i]
+        assert p.shape == (1, 256, h // 4, w // 4)
+        assert float((p.sum(1) - 1).abs().max()) < 1e-4
+        same_bin = (p.argmax(1).cpu().numpy() == fix[f"probability{i}_argmax"]).mean()
+        assert same_bin > 0.98, (i, same_bin)
+        dp = np.abs(p[:, :, ::4, ::4].cpu().numpy() - fix[f"probability{i}_s4"])
+        assert np.median(dp.max(axis=1)) < 1e-4
+        dc = np.abs(out["confidences"][i].cpu().numpy() - fix[f"confidence_logit{i}"])
+        assert np.median(dc) < 1e-3 and (dc > 5e-2).mean() < 0.02, (i, np.median(dc))
+    r = rel(out["depths_upsampled"][0], fix["depths_upsampled"])
+    assert np.median(r) < 2e-5 and (r > 1e-3).mean() < 0.02
+    assert (np.abs(out["confidence_upsampled"].cpu().numpy() - fix["confidence_upsampled"]) > 1e-3).mean() < 0.03
+    # the loss of the reference on the reference's outputs vs our loss on our outputs (same gt / masks as the generator)
+    d0 = torch.from_numpy(plane_depth_map(w, h).astype(np.float32))[None, None].to(dev)
+    gt = {"level_0": d0, "level_2": torch.nn.functional.interpolate(d0, scale_factor=0.25, mode="nearest")}
+    mask = {k: torch.ones_like(v) for k, v in gt.items()}
+    mask["level_0"][..., :6, :] = 0
+    mask["level_2"][..., :2, :] = 0
+    loss = float(itermvs_b200.full_loss(out["depths"], out["depths_upsampled"], out["confidences"], gt, mask,
+                                        s["depth_min"].to(dev), s["depth_max"].to(dev)))
+    print(f"all-predictions forward: loss {loss:.5f} (reference {float(fix['loss']):.5f})")
+    assert abs(loss - float(fix["loss"])) < 2e-3 * float(fix["loss"])
+    # with trainable parameters and autograd enabled the forward-only path refuses
+    with pytest.raises(NotImplementedError):
+        m(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+
+
 def test_full_size_pipeline_vs_oracle(dev, model, dtu_weights):
     """BASELINE config 2 (640x512, 4 src, D=32, 4 iterations) on the consistent plane scene:
     depth within 1e-3 relative of the oracle (north star tolerance), stage traces tighter."""
