@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-one-in-flight", action="store_true",
+                    help="e2e: replay the graph slots one after the other on one stream (default: two reference views in flight)")
     ap.add_argument("--passes", type=int, default=4, choices=[1, 3, 4],
                     help="tensor-core conv precision: 4 = 3-product FP16 split (fp32-grade, default), 3 = 3xTF32 split (fp32-grade), 1 = single-pass TF32")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage timing table to stderr")
@@ -285,7 +287,7 @@ def main():
         # its inputs and D2H of its two result maps are inside the timed region, overlapped with the previous /
         # next step's compute on the copy engines
         from itermvs_b200.graph import StreamingPipeline
-        sp = StreamingPipeline(model, d_imgs, d_proj, d_dmin, d_dmax)
+        sp = StreamingPipeline(model, d_imgs, d_proj, d_dmin, d_dmax, n_slots=2, concurrent=not args.e2e_one_in_flight)
         outs = [(torch.empty(1, 1, H_IMG, W_IMG).pin_memory(), torch.empty(1, 1, H_IMG, W_IMG).pin_memory()) for _ in range(2)]
         for k in range(4):
             sp.submit(host["imgs"], host["proj"], host["dmin"], host["dmax"], *outs[k & 1])
@@ -299,7 +301,9 @@ def main():
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
-        e2e_mode = "streaming, 2 graph slots: H2D / forward / D2H of consecutive steps overlap (all copies inside the timed region)"
+        e2e_mode = ("streaming from pinned host buffers, 2 graph slots: H2D / forward / D2H of consecutive steps overlap, all copies "
+                    "inside the timed region; " + ("one forward on the device at a time" if args.e2e_one_in_flight else
+                                                   "two reference views in flight (own workspace + compute stream per slot)"))
         ref_d = model(d_imgs, d_proj, d_dmin, d_dmax)["depths_upsampled"]
         assert torch.allclose(outs[(args.steps - 1) & 1][0].to(dev), ref_d, rtol=0, atol=0), "streaming result differs"
     else:

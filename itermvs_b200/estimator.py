@@ -376,21 +376,22 @@ class IterMVS(nn.Module):
         self.upsample = nn.Sequential(
             nn.Conv2d(feature_dim, 64, 3, stride=1, padding=1, dilation=1, bias=False), nn.ReLU(inplace=True),
             nn.Conv2d(64, 16 * 9, 1, stride=1, padding=0, dilation=1, bias=False))
-        self._workspaces: Dict[tuple, Tensor] = {}
+        self._workspaces: Dict[int, tuple] = {}      # workspace slot -> (shape key, buffer): one live buffer per slot
+        self.workspace_slot = 0                        # concurrent replays (graph.StreamingPipeline) use one slot each
 
     def packed(self, device) -> _pack.PackedWeights:
         return _cached_pack(self, device, lambda: _pack.PackedWeights(_sd(self), device))
 
     def _workspace(self, pb: _lib.Problem, device) -> Tensor:
         key = (pb.B, pb.V, pb.H, pb.W, pb.D, pb.iterations, str(device))
-        ws = self._workspaces.get(key)
-        if ws is None:
+        held = self._workspaces.get(self.workspace_slot)
+        if held is None or held[0] != key:
             nbytes = _lib.lib().imvs_forward_workspace_bytes(C.byref(pb))
             if nbytes == 0:
                 _lib.check(1, "forward_workspace_bytes")
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            self._workspaces = {key: ws}            # one live workspace per module
-        return ws
+            held = (key, torch.empty(nbytes, dtype=torch.uint8, device=device))
+            self._workspaces[self.workspace_slot] = held
+        return held[1]
 
     def forward_packed(self, fea1: Tensor, fea2: Tensor, fea3: Tensor, proj1: Tensor, proj2: Tensor, proj3: Tensor,
                        depth_min: Tensor, depth_max: Tensor, out=None, nan_flag=None):

@@ -22,9 +22,10 @@ STAGE_NAMES = ["compose", "warpcorr_init", "pixel_view_weight", "aggregate_init"
 
 class GraphedPipeline:
     def __init__(self, model, imgs: Dict[str, torch.Tensor], proj_matrices: Dict[str, torch.Tensor],
-                 depth_min: torch.Tensor, depth_max: torch.Tensor, warmup: int = 3):
+                 depth_min: torch.Tensor, depth_max: torch.Tensor, warmup: int = 3, workspace_slot: int = 0):
         assert model.test and not model.training, "graph replay is for the inference pipeline (test=True, eval())"
         self.model = model
+        self.workspace_slot = workspace_slot      # graphs with different slots own disjoint workspaces -> may overlap
         dev = imgs["level_0"].device
         # static inputs: only what Pipeline.forward reads (net.py:78-109): imgs['level_0'], proj level_1..3
         self.s_img = imgs["level_0"].detach().clone().float().contiguous()
@@ -44,7 +45,11 @@ class GraphedPipeline:
         self.nan_flag = model._last_nan_flag
 
     def _run(self):
-        return self.model({"level_0": self.s_img}, self.s_proj, self.s_dmin, self.s_dmax)
+        self.model.set_workspace_slot(self.workspace_slot)
+        try:
+            return self.model({"level_0": self.s_img}, self.s_proj, self.s_dmin, self.s_dmax)
+        finally:
+            self.model.set_workspace_slot(0)
 
     def load_inputs(self, imgs, proj_matrices, depth_min, depth_max, non_blocking=True):
         """Copies (H2D when the sources are pinned host tensors) into the graph's static inputs."""
@@ -81,40 +86,48 @@ def profile_stages(fn, capacity: int = 4096):
 
 
 class StreamingPipeline:
-    """Serving loop from pinned HOST buffers with two graph slots: the H2D copy of sample k+1 (copy
-    engine 1) and the D2H copy of result k-1 (copy engine 2) overlap the graph replay of sample k.
+    """Serving loop from pinned HOST buffers with `n_slots` graph slots, each with its own static inputs,
+    workspace and compute stream: the H2D copy of sample k+1 (copy engine 1), the D2H copy of result k-1
+    (copy engine 2) and the graph replays of up to `n_slots` consecutive samples overlap on the device.
+    Reference views are independent units, so two of them in flight fill the SMs that the
+    small quarter-resolution kernels of one forward (GRU, heads: 2-4 CTAs per SM) leave idle.
 
         sp = StreamingPipeline(model, imgs, proj, dmin, dmax)        # device sample, shapes only
         sp.submit(host_imgs, host_proj, host_dmin, host_dmax, out_depth_pinned, out_conf_pinned)   # per sample
         sp.drain()                                                   # all results are in their host buffers
     """
 
-    def __init__(self, model, imgs, proj_matrices, depth_min, depth_max):
+    def __init__(self, model, imgs, proj_matrices, depth_min, depth_max, n_slots: int = 2, concurrent: bool = True):
         dev = imgs["level_0"].device
         self.dev = dev
-        self.slots = [GraphedPipeline(model, imgs, proj_matrices, depth_min, depth_max) for _ in range(2)]
+        self.n = n_slots
+        self.slots = [GraphedPipeline(model, imgs, proj_matrices, depth_min, depth_max, workspace_slot=i if concurrent else 0)
+                      for i in range(n_slots)]
+        main = torch.cuda.current_stream(dev)
+        self.comp = [torch.cuda.Stream(device=dev) if concurrent else main for _ in range(n_slots)]
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(2)]
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]
-        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(n_slots)]
+        self.ev_done = [torch.cuda.Event() for _ in range(n_slots)]
+        self.ev_out = [torch.cuda.Event() for _ in range(n_slots)]
         self.k = 0
-        main = torch.cuda.current_stream(dev)
         for e in self.ev_done + self.ev_out:
             e.record(main)
 
     def submit(self, imgs, proj_matrices, depth_min, depth_max, out_depth, out_conf):
-        s = self.k & 1
-        slot = self.slots[s]
-        main = torch.cuda.current_stream(self.dev)
+        s = self.k % self.n
+        slot, comp = self.slots[s], self.comp[s]
+        if self.k < self.n:
+            comp.wait_stream(torch.cuda.current_stream(self.dev))      # work the caller queued before the first submit
         with torch.cuda.stream(self.h2d):
             self.h2d.wait_event(self.ev_done[s])          # slot's previous replay has consumed its inputs
             slot.load_inputs(imgs, proj_matrices, depth_min, depth_max)
             self.ev_in[s].record(self.h2d)
-        main.wait_event(self.ev_in[s])
-        main.wait_event(self.ev_out[s])                    # slot's previous outputs have left the device
-        out = slot.replay()
-        self.ev_done[s].record(main)
+        comp.wait_event(self.ev_in[s])
+        comp.wait_event(self.ev_out[s])                    # slot's previous outputs have left the device
+        with torch.cuda.stream(comp):
+            out = slot.replay()
+            self.ev_done[s].record(comp)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(self.ev_done[s])
             out_depth.copy_(out["depths_upsampled"], non_blocking=True)

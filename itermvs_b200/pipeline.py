@@ -63,7 +63,8 @@ class FeatureNet(nn.Module):
         self.inner1 = nn.Conv2d(16, 48, 1, stride=1, padding=0, bias=True)
         self.inner2 = nn.Conv2d(32, 48, 1, stride=1, padding=0, bias=True)
         self.inner3 = nn.Conv2d(48, 48, 1, stride=1, padding=0, bias=True)   # unused in forward, as in net.py:25
-        self._ws = {}
+        self._ws = {}                 # workspace slot -> (shape key, buffer)
+        self.workspace_slot = 0
 
     def _packed(self, device) -> _pack.PackedFeatureNet:
         def build():
@@ -83,13 +84,14 @@ class FeatureNet(nn.Module):
         dev = x.device
         n = b * v
         key = (n, h, w, str(dev))
-        ws = self._ws.get(key)
-        if ws is None:
+        held = self._ws.get(self.workspace_slot)
+        if held is None or held[0] != key:
             nbytes = _lib.lib().imvs_featurenet_workspace_bytes(n, h, w)
             if nbytes == 0:
                 raise ValueError(f"FeatureNet: unsupported shape {tuple(x.shape)}")
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._ws = {key: ws}
+            held = (key, torch.empty(nbytes, dtype=torch.uint8, device=dev))
+            self._ws[self.workspace_slot] = held
+        ws = held[1]
         f1 = torch.empty(b, v, h // 2, w // 2, 16, device=dev)
         f2 = torch.empty(b, v, h // 4, w // 4, 32, device=dev)
         f3 = torch.empty(b, v, h // 8, w // 8, 48, device=dev)
@@ -118,6 +120,12 @@ class Pipeline(nn.Module):
         self.feature_net = FeatureNet(test=test)
         self.iter_mvs = IterMVS(iteration, self.feature_dim[2], self.hidden_dim, test)
         self._last_nan_flag = None
+
+    def set_workspace_slot(self, slot: int) -> None:
+        """Workspaces are cached per slot; forwards that may overlap on the device (two CUDA graphs replayed on
+        different streams) must run under different slots."""
+        self.feature_net.workspace_slot = slot
+        self.iter_mvs.workspace_slot = slot
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts checkpoints with the DataParallel 'module.' prefix (train.py:153-157) too."""
