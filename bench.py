@@ -10,10 +10,14 @@ initial hypotheses, 4 GRU iterations, batch 1 per GPU, synthetic consistent-plan
 checkpoint weights (tests/golden/dtu_weights.npz).  A step = one `Pipeline.forward` (FeatureNet +
 the whole estimator), test mode.  Metric = reference views per second.
 
-value : device-resident inputs, one CUDA-graph replay per step, per-step CUDA events, L2 flushed
-        between steps (outside the event windows), max over ranks.
-e2e   : same call from pinned HOST buffers: H2D of images/cameras + forward + D2H of the two
-        full-resolution outputs inside the per-step event window.
+value : K steps with device-resident inputs through graph.StreamingPipeline: `--in-flight` (default 4)
+        reference views on the device at once, each a CUDA-graph replay on its own stream / workspace
+        (independent units); the inputs rotate over 8 resident sets (> L2); one CUDA-event
+        pair around the K steps, barrier + synchronize on both sides, max over ranks.
+        `single_stream` in the JSON line is the latency figure: one forward at a time, L2 flushed
+        between steps, per-step events.
+e2e   : the same K steps from pinned HOST buffers: H2D of images/cameras + forward + D2H of the two
+        full-resolution outputs of every step inside the timed region.
 roofline : fused warp+correlate iteration kernel, algorithmic bytes / its in-step
         duration from the library's CUDA-event stage taps, against MEASURED_PEAKS.json.
 """
@@ -37,6 +41,7 @@ import torch  # noqa: E402
 W_IMG, H_IMG, N_SRC, D_HYP, ITERS = 640, 512, 4, 32, 4
 METRIC = "reference-views/sec at 640x512, 4 src, D=32, 4 iters"
 HBM_FALLBACK_GBS = 6650.0
+NROT = 8          # device-resident input sets the timed loop rotates over (8 x 19.7 MB > the 126 MB L2)
 
 
 def algorithmic_bytes(h, w, s, d):
@@ -169,8 +174,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-one-in-flight", action="store_true",
-                    help="e2e: replay the graph slots one after the other on one stream (default: two reference views in flight)")
+    ap.add_argument("--in-flight", type=int, default=4,
+                    help="reference views in flight per GPU (graph slots with their own workspace and compute stream); "
+                         "1 = one forward on the device at a time")
     ap.add_argument("--passes", type=int, default=4, choices=[1, 3, 4],
                     help="tensor-core conv precision: 4 = 3-product FP16 split (fp32-grade, default), 3 = 3xTF32 split (fp32-grade), 1 = single-pass TF32")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage timing table to stderr")
@@ -249,18 +255,55 @@ def main():
     iter_ms = [m for rep in stage_ms.get("warpcorr_iter", []) for m in rep]
     init_ms = [m for rep in stage_ms.get("warpcorr_init", []) for m in rep]
 
-    # ---- timed region: device-resident inputs
+    # ---- single-stream figure: one forward on the device at a time, L2 flushed between steps (latency-oriented)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    t_wall = time.perf_counter()
     for a, b in ev:
         flush.zero_()
         a.record()
         step()
         b.record()
     barrier()
-    t_wall = time.perf_counter() - t_wall
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    serial_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- timed region (the metric): K reference views, device-resident inputs, `in_flight` of them on the device
+    #      at once (independent units).  The inputs rotate over NROT resident sets (> L2 in total).
+    sp = None
+    if graphed is not None:
+        from itermvs_b200.graph import StreamingPipeline
+        nfl = max(1, args.in_flight)
+        sp = StreamingPipeline(model, d_imgs, d_proj, d_dmin, d_dmax, n_slots=nfl, concurrent=nfl > 1)
+        rot = [({"level_0": d_imgs["level_0"].clone()}, {k: v.clone() for k, v in d_proj.items()}, d_dmin.clone(), d_dmax.clone())
+               for _ in range(NROT)]
+        d_outs = [(torch.empty(1, 1, H_IMG, W_IMG, device=dev), torch.empty(1, 1, H_IMG, W_IMG, device=dev)) for _ in range(nfl)]
+        for k in range(2 * nfl):
+            sp.submit(*rot[k % NROT], *d_outs[k % nfl])
+        sp.drain()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        e0.record()
+        for k in range(args.steps):
+            sp.submit(*rot[k % NROT], *d_outs[k % nfl])
+        sp.drain()
+        e1.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        total_ms = e0.elapsed_time(e1)
+        ref_d = model(*rot[(args.steps - 1) % NROT])["depths_upsampled"]
+        assert torch.equal(d_outs[(args.steps - 1) % nfl][0], ref_d), "in-flight replay differs from the plain forward"
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t_wall = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            step()
+            b.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
 
     # ---- end to end from pinned host buffers
     out_host = {"d": torch.empty(1, 1, H_IMG, W_IMG).pin_memory(), "c": torch.empty(1, 1, H_IMG, W_IMG).pin_memory()}
@@ -282,30 +325,28 @@ def main():
     for _ in range(3):
         e2e_step()
     e2e_mode = "serial (H2D -> forward -> D2H per step)"
-    if graphed is not None:
-        # the call a serving user makes: double-buffered streaming from pinned host buffers; every step's H2D of
-        # its inputs and D2H of its two result maps are inside the timed region, overlapped with the previous /
-        # next step's compute on the copy engines
-        from itermvs_b200.graph import StreamingPipeline
-        sp = StreamingPipeline(model, d_imgs, d_proj, d_dmin, d_dmax, n_slots=2, concurrent=not args.e2e_one_in_flight)
-        outs = [(torch.empty(1, 1, H_IMG, W_IMG).pin_memory(), torch.empty(1, 1, H_IMG, W_IMG).pin_memory()) for _ in range(2)]
-        for k in range(4):
-            sp.submit(host["imgs"], host["proj"], host["dmin"], host["dmax"], *outs[k & 1])
+    if sp is not None:
+        # the call a serving user makes: streaming from pinned host buffers; every step's H2D of its inputs and D2H of
+        # its two result maps are inside the timed region, overlapped with other steps' compute on the copy engines
+        ns = sp.n
+        outs = [(torch.empty(1, 1, H_IMG, W_IMG).pin_memory(), torch.empty(1, 1, H_IMG, W_IMG).pin_memory()) for _ in range(ns)]
+        for k in range(2 * ns):
+            sp.submit(host["imgs"], host["proj"], host["dmin"], host["dmax"], *outs[k % ns])
         sp.drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(args.steps):
-            sp.submit(host["imgs"], host["proj"], host["dmin"], host["dmax"], *outs[k & 1])
+            sp.submit(host["imgs"], host["proj"], host["dmin"], host["dmax"], *outs[k % ns])
         sp.drain()
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
-        e2e_mode = ("streaming from pinned host buffers, 2 graph slots: H2D / forward / D2H of consecutive steps overlap, all copies "
-                    "inside the timed region; " + ("one forward on the device at a time" if args.e2e_one_in_flight else
-                                                   "two reference views in flight (own workspace + compute stream per slot)"))
+        e2e_mode = (f"streaming from pinned host buffers through graph.StreamingPipeline: {ns} reference view(s) in flight "
+                    "(own static buffers, workspace and compute stream per slot), H2D / forward / D2H of different steps overlap; "
+                    "all copies inside the timed region")
         ref_d = model(d_imgs, d_proj, d_dmin, d_dmax)["depths_upsampled"]
-        assert torch.allclose(outs[(args.steps - 1) & 1][0].to(dev), ref_d, rtol=0, atol=0), "streaming result differs"
+        assert torch.allclose(outs[(args.steps - 1) % ns][0].to(dev), ref_d, rtol=0, atol=0), "streaming result differs"
     else:
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
@@ -394,9 +435,14 @@ def main():
         "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 per GPU (BASELINE configs[1])",
                    "step": "Pipeline.forward test mode: FeatureNet + estimator, all in hand-written sm_100a kernels (no cuDNN/cuBLAS)",
                    "launch": "eager" if graphed is None else "cuda-graph replay",
-                   "l2": "256 MiB memset between steps, outside the per-step CUDA-event windows",
+                   "in_flight": (sp.n if sp is not None else 1),
+                   "l2": (f"device-resident inputs rotate over {NROT} sets ({NROT * h2d / 1e6:.0f} MB > 126 MB L2), no flush inside the timed region"
+                          if sp is not None else "256 MiB memset between steps, outside the per-step CUDA-event windows"),
                    "weights": "DTU checkpoint", "parallelism": f"replicas x{world} (one reference view per GPU, no collectives)"},
         "e2e": {"value": e2e_value, "unit": "refs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mode": e2e_mode},
+        "single_stream": {"value": args.steps / (serial_ms * 1e-3), "unit": "refs/s", "ms_per_step": serial_ms / args.steps,
+                          "what": "one forward on the device at a time (graph replay), L2 flushed by a 256 MiB memset between steps, "
+                                  "per-step CUDA events: the latency-oriented figure"},
         "gpu_launches": fwd_launches * args.steps,
         "gpu_launches_per_step": fwd_launches,
         "roofline": {"kernel": "warpcorr_iter_kernel (fused warp+sample+group-corr+view-weighted aggregation)",

@@ -285,6 +285,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         issue_weights(0, 0);
     }
     pdl_wait();
+#ifndef IMVS_EXP_NO_TILE             // (timing experiment: no input staging -- wrong results)
     {   // input tile (with halo)
         const int iy0 = oy0 * Cfg::STRIDE + taps.dy_min, ix0 = ox0 * Cfg::STRIDE + taps.dx_min;
         constexpr int C4 = Cfg::CINK / 4;
@@ -301,6 +302,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
             }
         }
     }
+#endif
     if constexpr (Cfg::WALL) {
         cp_async_commit();
         cp_async_wait<0>();
@@ -391,6 +393,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
                     w1[j] = wb2[(ks * 8 + t + 4) * NP + 8 * j + g];
                 }
 #pragma unroll
+#ifndef IMVS_EXP_ONE_PRODUCT     // (timing experiment: hi*hi only -- wrong results)
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
                     for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_LH][r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0[j].x, w1[j].x);
@@ -398,6 +401,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
                     for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_HL][r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].y, w1[j].y);
+#endif
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
