@@ -124,6 +124,16 @@ int imvs_differentiable_warping(const float* src_fea, const float* src_proj, con
                                 const float* depth_samples, float* out, int B, int C, int H1, int W1,
                                 int D, int H, int W, float* rt_scratch, int* nan_flag, void* stream);
 
+/* Backward of differentiable_warping with respect to src_fea -- what autograd derives from F.grid_sample at
+ * module.py:118 (the sampling grid is built under torch.no_grad(), module.py:77, so nothing flows to the
+ * projections or the depth samples):  grad_src_fea[b,c,y0+dy,x0+dx] += w_tap * grad_out[b,c,d,y,x] over the four
+ * in-range taps.  grad_out [B][C][D][H][W] -> grad_src_fea [B][C][H1][W1] (zeroed by the call, accumulated with
+ * fp32 atomics: the summation order is not deterministic, as in ATen's CUDA grid_sampler backward).
+ * rt_scratch: B*12 floats. */
+int imvs_differentiable_warping_backward(const float* grad_out, const float* src_proj, const float* ref_proj,
+                                         const float* depth_samples, float* grad_src_fea, int B, int C, int H1, int W1,
+                                         int D, int H, int W, float* rt_scratch, int* nan_flag, void* stream);
+
 /* layout helpers: [N][C][H][W] <-> [N][H][W][C] */
 int imvs_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, void* stream);
 int imvs_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, void* stream);

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "imvs_profile_end": (ci, [vp, vp, ci]),
     "imvs_compose_projections": (ci, [vp, ci, ci, vp, vp, vp]),
     "imvs_differentiable_warping": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]),
+    "imvs_differentiable_warping_backward": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]),
     "imvs_nchw_to_nhwc": (ci, [vp, vp, ci, ci, ci, ci, vp]),
     "imvs_nhwc_to_nchw": (ci, [vp, vp, ci, ci, ci, ci, vp]),
     "imvs_warpcorr_init": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),

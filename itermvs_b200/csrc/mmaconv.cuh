@@ -285,7 +285,6 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         issue_weights(0, 0);
     }
     pdl_wait();
-#ifndef IMVS_EXP_NO_TILE             // (timing experiment: no input staging -- wrong results)
     {   // input tile (with halo)
         const int iy0 = oy0 * Cfg::STRIDE + taps.dy_min, ix0 = ox0 * Cfg::STRIDE + taps.dx_min;
         constexpr int C4 = Cfg::CINK / 4;
@@ -302,7 +301,6 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
             }
         }
     }
-#endif
     if constexpr (Cfg::WALL) {
         cp_async_commit();
         cp_async_wait<0>();

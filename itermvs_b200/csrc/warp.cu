@@ -186,6 +186,41 @@ __global__ void warp_nchw_kernel(const float* __restrict__ fea, const float* __r
     }
 }
 
+// Backward of the operator above with respect to src_fea (grid_sample's d/d input; the grid itself carries no
+// gradient, module.py:77).  Same thread mapping as the forward: the sampling position of (b, d, y, x) is computed
+// once, then one scatter of four weighted atomics per channel.
+__global__ void warp_nchw_backward_kernel(const float* __restrict__ gout, const float* __restrict__ rt,
+                                          const float* __restrict__ depth, float* __restrict__ gfea,
+                                          int B, int C, int H1, int W1, int D, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    int bd = blockIdx.z;
+    if (x >= W) return;
+    int b = bd / D, d = bd % D;
+    const float* P = rt + (size_t)b * 12;
+    float dep = depth[((size_t)bd * H + y) * W + x];
+    float sx = (float)((double)W1 / (double)W), sy = (float)((double)H1 / (double)H);
+    Tap tp = project_tap(P, (float)x * sx, (float)y * sy, dep, (float)W, (float)H, W1, H1);
+    if (tp.mask == 0) return;
+    float w00 = (1.f - tp.fx) * (1.f - tp.fy), w01 = tp.fx * (1.f - tp.fy);
+    float w10 = (1.f - tp.fx) * tp.fy, w11 = tp.fx * tp.fy;
+    const size_t plane = (size_t)H1 * W1;
+    float* base = gfea + (size_t)b * C * plane;
+    size_t o = (((size_t)b * C) * D + d) * (size_t)H * W + (size_t)y * W + x;
+    const size_t ostride = (size_t)D * H * W;
+    int i00 = tp.y0 * W1 + tp.x0;
+    for (int c = 0; c < C; ++c) {
+        float* p = base + (size_t)c * plane;
+        const float g = ldg(gout + o + (size_t)c * ostride);
+        if (tp.mask & 1) atomicAdd(p + i00, g * w00);
+        if (tp.mask & 2) atomicAdd(p + i00 + 1, g * w01);
+        if (tp.mask & 4) atomicAdd(p + i00 + W1, g * w10);
+        if (tp.mask & 8) atomicAdd(p + i00 + W1 + 1, g * w11);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // layout helpers (tiled transpose through shared memory, 32x32 tiles over (C, H*W))
 // ---------------------------------------------------------------------------------------------
@@ -297,6 +332,24 @@ extern "C" int imvs_differentiable_warping(const float* src_fea, const float* sr
     IMVS_CUDA(launch_k(compose_pair_kernel, dim3(cdiv(B, 32)), dim3(32), 0, st, src_proj, ref_proj, B, rt, nan_flag));
     dim3 grid(cdiv(W, 128), H, B * D);
     IMVS_CUDA(launch_k(warp_nchw_kernel, grid, dim3(128), 0, st, src_fea, (const float*)rt, depth_samples, out, B, C, H1, W1, D, H, W));
+    return 0;
+}
+
+extern "C" int imvs_differentiable_warping_backward(const float* grad_out, const float* src_proj, const float* ref_proj,
+                                                    const float* depth_samples, float* grad_src_fea, int B, int C, int H1,
+                                                    int W1, int D, int H, int W, float* rt_scratch, int* nan_flag, void* stream) {
+    IMVS_REQUIRE(grad_out && src_proj && ref_proj && depth_samples && grad_src_fea && rt_scratch,
+                 "differentiable_warping_backward: null pointer");
+    IMVS_REQUIRE(B >= 1 && C >= 1 && H1 >= 1 && W1 >= 1 && D >= 1 && H >= 1 && W >= 1,
+                 "differentiable_warping_backward: bad shape");
+    IMVS_REQUIRE(H <= 65535 && (long long)B * D <= 65535, "differentiable_warping_backward: H or B*D exceeds grid limits");
+    cudaStream_t st = (cudaStream_t)stream;
+    ApiScope api_;
+    IMVS_CUDA(cudaMemsetAsync(grad_src_fea, 0, sizeof(float) * (size_t)B * C * H1 * W1, st));
+    IMVS_CUDA(launch_k(compose_pair_kernel, dim3(cdiv(B, 32)), dim3(32), 0, st, src_proj, ref_proj, B, rt_scratch, nan_flag));
+    dim3 grid(cdiv(W, 128), H, B * D);
+    IMVS_CUDA(launch_k(warp_nchw_backward_kernel, grid, dim3(128), 0, st, grad_out, (const float*)rt_scratch, depth_samples,
+                       grad_src_fea, B, C, H1, W1, D, H, W));
     return 0;
 }
 

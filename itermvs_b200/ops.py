@@ -63,14 +63,7 @@ def compose_projections(proj: Tensor, nan_flag: Optional[NanFlag] = None) -> Ten
     return out
 
 
-def differentiable_warping(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, depth_samples: Tensor,
-                           return_mask: bool = False):
-    """Drop-in for reference models/module.py:68.  src_fea [B,C,H1,W1], projections [B,4,4],
-    depth_samples [B,D,H,W] -> [B,C,D,H,W] (and the validity mask when return_mask=True)."""
-    src_fea = _chk(src_fea, "src_fea")
-    depth_samples = _chk(depth_samples, "depth_samples")
-    src_proj = _chk(src_proj.float(), "src_proj")
-    ref_proj = _chk(ref_proj.float(), "ref_proj")
+def _warp_forward(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, depth_samples: Tensor):
     b, c, h1, w1 = src_fea.shape
     _, d, h, w = depth_samples.shape
     out = torch.empty(b, c, d, h, w, device=src_fea.device, dtype=torch.float32)
@@ -80,6 +73,50 @@ def differentiable_warping(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, 
                                                       depth_samples.data_ptr(), out.data_ptr(), b, c, h1, w1, d, h, w,
                                                       rt.data_ptr(), flag.ptr(), _stream()), "differentiable_warping")
     flag.raise_if_set()     # the reference asserts (and therefore synchronises) on every call as well
+    return out, rt
+
+
+class _WarpFn(torch.autograd.Function):
+    """differentiable_warping with its CUDA backward.  Only src_fea receives a gradient: the reference builds the
+    sampling grid under torch.no_grad() (module.py:77), so projections and depth samples are constants."""
+
+    @staticmethod
+    def forward(ctx, src_fea, src_proj, ref_proj, depth_samples):
+        out, _ = _warp_forward(src_fea, src_proj, ref_proj, depth_samples)
+        ctx.save_for_backward(src_proj, ref_proj, depth_samples)
+        ctx.fea_shape = tuple(src_fea.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        src_proj, ref_proj, depth_samples = ctx.saved_tensors
+        b, c, h1, w1 = ctx.fea_shape
+        _, d, h, w = depth_samples.shape
+        grad_out = _chk(grad_out.float(), "grad_out")
+        grad_fea = torch.empty(b, c, h1, w1, device=grad_out.device, dtype=torch.float32)
+        rt = torch.empty(b, 12, device=grad_out.device, dtype=torch.float32)
+        _lib.check(_lib.lib().imvs_differentiable_warping_backward(
+            grad_out.data_ptr(), src_proj.data_ptr(), ref_proj.data_ptr(), depth_samples.data_ptr(), grad_fea.data_ptr(),
+            b, c, h1, w1, d, h, w, rt.data_ptr(), None, _stream()), "differentiable_warping_backward")
+        return grad_fea, None, None, None
+
+
+def differentiable_warping(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, depth_samples: Tensor,
+                           return_mask: bool = False):
+    """Drop-in for reference models/module.py:68.  src_fea [B,C,H1,W1], projections [B,4,4],
+    depth_samples [B,D,H,W] -> [B,C,D,H,W] (and the validity mask when return_mask=True).
+    Differentiable with respect to src_fea (CUDA backward), like the reference."""
+    src_fea = _chk(src_fea, "src_fea")
+    depth_samples = _chk(depth_samples.detach(), "depth_samples")
+    src_proj = _chk(src_proj.detach().float(), "src_proj")
+    ref_proj = _chk(ref_proj.detach().float(), "ref_proj")
+    b, c, h1, w1 = src_fea.shape
+    _, d, h, w = depth_samples.shape
+    if torch.is_grad_enabled() and src_fea.requires_grad:
+        out = _WarpFn.apply(src_fea, src_proj, ref_proj, depth_samples)
+        rt = compose_projections(torch.stack([ref_proj, src_proj], dim=1))[:, 0] if return_mask else None
+    else:
+        out, rt = _warp_forward(src_fea, src_proj, ref_proj, depth_samples)
     if not return_mask:
         return out
     # module.py:104-111 (no caller in the reference passes return_mask=True; small torch epilogue)
