@@ -209,6 +209,32 @@ int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea2, size_t r
                           int B, int H2, int W2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Depth-map filtering for fusion (eval.py:154-309) -- the caller after the hot path
+ * ---------------------------------------------------------------------------------------- */
+
+/* cams68 (HOST pointer, 68 floats per (reference, source) pair, row-major float32 exactly as numpy forms them in
+ * eval.py:162-190):  inv(K_ref)[9] | E_src @ inv(E_ref) [16] | K_src [9] | inv(K_src) [9] | E_ref @ inv(E_src) [16] |
+ * K_ref [9].  Depth maps are [H][W] float32 on the device.
+ *
+ * eval.py:199-215 check_geometric_consistency for one pair: mask [H][W] bytes (1 = consistent), depth_reprojected
+ * (0 where inconsistent), x2d_src / y2d_src; any output may be NULL.  acc_sum / acc_count (may be NULL) additionally
+ * accumulate depth_reprojected and mask (eval.py:259-260); successive calls on one stream add in call order. */
+int imvs_check_geometric_consistency(const float* depth_ref, const float* depth_src, const float* cams68_host,
+                                     float geo_pixel_thres, float geo_depth_thres, unsigned char* mask,
+                                     float* depth_reprojected, float* x2d_src, float* y2d_src,
+                                     float* acc_sum, int* acc_count, int H, int W, void* stream);
+
+/* eval.py:243-265 for one reference view: S sources (depth_srcs [S][H][W], cams68_host [S][68]) checked in order,
+ * depth_averaged = (sum of masked reprojections + depth_ref) / (count + 1) as float64, photo_mask = confidence >
+ * photo_thres, geo_mask = count >= geo_mask_thres, final_mask = both.  acc_sum [H][W] float and acc_count [H][W]
+ * int are caller-owned scratch (zeroed by the call); photo_mask / geo_mask may be NULL. */
+int imvs_filter_depth_view(const float* depth_ref, const float* confidence, const float* depth_srcs,
+                           const float* cams68_host, int S, float geo_pixel_thres, float geo_depth_thres,
+                           float photo_thres, int geo_mask_thres, float* acc_sum, int* acc_count,
+                           double* depth_averaged, unsigned char* photo_mask, unsigned char* geo_mask,
+                           unsigned char* final_mask, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Whole estimator: IterMVS.forward in test mode (itermvs.py:253-329), one call = all launches.
  * ---------------------------------------------------------------------------------------- */
 typedef struct imvs_problem {

@@ -14,7 +14,8 @@ from .ops import (differentiable_warping, depth_normalization, depth_unnormaliza
 from .estimator import (ConvGRU, CorrNet, DepthInitialization, Evaluation, IterMVS, PixelViewWeight,  # noqa: F401
                         Update)
 from .pipeline import FeatureNet, Pipeline, full_loss  # noqa: F401
+from .fusion import check_geometric_consistency, filter_depth_view  # noqa: F401
 
 __all__ = ["Pipeline", "FeatureNet", "IterMVS", "Evaluation", "Update", "ConvGRU", "CorrNet", "PixelViewWeight",
            "DepthInitialization", "differentiable_warping", "depth_normalization", "depth_unnormalization", "upsample",
-           "compose_projections", "nchw_to_nhwc", "nhwc_to_nchw", "full_loss"]
+           "compose_projections", "nchw_to_nhwc", "nhwc_to_nchw", "full_loss", "check_geometric_consistency", "filter_depth_view"]

@@ -59,3 +59,9 @@ def e2e_allpred():
 @pytest.fixture(scope="session")
 def loss_kat():
     return _load_npz("loss_kat.npz")
+
+
+@pytest.fixture(scope="session")
+def fusion_kat():
+    """Outputs of the reference's reproject_with_depth / check_geometric_consistency (tests/golden/make_golden_fusion.py)."""
+    return _load_npz("fusion_kat.npz")

@@ -1,0 +1,85 @@
+"""Depth-map filtering (reference eval.py:154-265): oracle vs the reference's own outputs (CPU), and
+the CUDA kernels through the C ABI vs both (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_oracle as FO
+
+
+def _views(z):
+    n = int(z["n_src"])
+    return ([z[f"depth{v}"] for v in range(1, n + 1)], [z[f"K{v}"] for v in range(1, n + 1)], [z[f"E{v}"] for v in range(1, n + 1)])
+
+
+def test_oracle_remap_is_cv2_remap(fusion_kat):
+    z = fusion_kat
+    out = FO.remap_linear(z["remap_img"], z["remap_x"], z["remap_y"])
+    assert np.array_equal(out, z["remap_out"])          # incl. +-1e9, inf, nan coordinates and the last row / column
+
+
+def test_oracle_matches_reference_functions(fusion_kat):
+    z = fusion_kat
+    depths, ks, es = _views(z)
+    for v, (d, k, e) in enumerate(zip(depths, ks, es), start=1):
+        m, rep, xs, ys = FO.check_geometric_consistency(z["depth0"], z["K0"], z["E0"], d, k, e, 1.0, 0.01)
+        assert np.array_equal(m, z[f"mask{v}"]) and np.array_equal(rep, z[f"reprojected{v}"])
+        assert np.array_equal(xs, z[f"x_src{v}"], equal_nan=True) and np.array_equal(ys, z[f"y_src{v}"], equal_nan=True)
+    avg, pm, gm, fm = FO.filter_depth_view(z["depth0"], z["confidence"], z["K0"], z["E0"], depths, ks, es, 1.0, 0.01, 0.3, 3)
+    assert avg.dtype == np.float64 and np.array_equal(avg, z["depth_est_averaged"])
+    assert np.array_equal(pm, z["photo_mask"]) and np.array_equal(gm, z["geo_mask"]) and np.array_equal(fm, z["final_mask"])
+    assert 0.3 < z["geo_mask"].mean() < 0.9            # the fixture exercises both outcomes
+
+
+@pytest.mark.gpu
+def test_cuda_check_geometric_consistency(fusion_kat):
+    from itermvs_b200 import check_geometric_consistency
+    z = fusion_kat
+    depths, ks, es = _views(z)
+    flips = 0
+    for v, (d, k, e) in enumerate(zip(depths, ks, es), start=1):
+        m, rep, xs, ys = check_geometric_consistency(z["depth0"], z["K0"], z["E0"], d, k, e, 1.0, 0.01)     # numpy in -> numpy out
+        assert m.dtype == np.bool_ and rep.dtype == np.float32 and m.shape == z["depth0"].shape
+        # the float64 dot products may round differently from the host BLAS by an ulp: values to 1e-6, and a pixel
+        # sitting exactly on a threshold may flip
+        ok = np.isfinite(z[f"x_src{v}"])
+        assert np.allclose(xs[ok], z[f"x_src{v}"][ok], rtol=1e-6, atol=1e-4) and np.allclose(ys[ok], z[f"y_src{v}"][ok], rtol=1e-6, atol=1e-4)
+        diff = m != z[f"mask{v}"]
+        flips += int(diff.sum())
+        same = ~diff
+        assert np.allclose(rep[same], z[f"reprojected{v}"][same], rtol=2e-6, atol=1e-4)
+    assert flips <= 3, flips
+    # CUDA tensors in -> CUDA tensors out
+    dev = torch.device("cuda:0")
+    m, rep, xs, ys = check_geometric_consistency(torch.from_numpy(z["depth0"]).to(dev), z["K0"], z["E0"],
+                                                 torch.from_numpy(depths[0]).to(dev), ks[0], es[0], 1.0, 0.01)
+    assert m.is_cuda and m.dtype == torch.bool and int((m.cpu().numpy() != z["mask1"]).sum()) <= 1
+
+
+@pytest.mark.gpu
+def test_cuda_filter_depth_view(fusion_kat):
+    from itermvs_b200 import filter_depth_view
+    z = fusion_kat
+    depths, ks, es = _views(z)
+    avg, pm, gm, fm = filter_depth_view(z["depth0"], z["confidence"], z["K0"], z["E0"], depths, ks, es, 1.0, 0.01, 0.3, 3)
+    assert avg.dtype == np.float64
+    assert np.array_equal(pm, z["photo_mask"])
+    assert int((gm != z["geo_mask"]).sum()) <= 2 and int((fm != z["final_mask"]).sum()) <= 2
+    same = gm == z["geo_mask"]
+    with np.errstate(invalid="ignore"):
+        close = np.isclose(avg, z["depth_est_averaged"], rtol=2e-6, atol=1e-4, equal_nan=True)
+    assert (close | ~same).mean() > 0.9995
+    # properties at a full-size map (1600 x 1152, DTU evaluation size): identical views are consistent with
+    # themselves wherever the depth is valid, and the average of identical reprojections is the depth itself
+    rng = np.random.RandomState(0)
+    h, w = 1152, 1600
+    k = z["K0"].copy()
+    k[0] *= w / 160.0
+    k[1] *= h / 128.0
+    d = (600 + 100 * rng.rand(h, w)).astype(np.float32)
+    d[::7, ::5] = 0
+    conf = np.ones((h, w), np.float32)
+    avg, pm, gm, fm = filter_depth_view(d, conf, k, z["E0"], [d, d, d], [k, k, k], [z["E0"]] * 3, 1.0, 0.01, 0.3, 3)
+    valid = d > 0
+    assert gm[valid].all() and not gm[~valid].any() and pm.all()
+    assert np.allclose(avg[valid], d[valid], rtol=1e-6)
