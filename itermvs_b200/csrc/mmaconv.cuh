@@ -40,6 +40,7 @@ struct TapTable {
     int widx[9];            // weight slice of each tap in the packed [slice][CINP][COUT] array
     int dy_min, dx_min;     // tile origin offset
     int IH, IW;             // smem input tile extent for a TH x 16 output tile
+    unsigned iw_magic;      // floor(2^22 / IW) + 1: slot / IW == (slot * iw_magic) >> 22 for every slot of a tile
 };
 
 struct TapTables {          // launch variants (blockIdx.z % count)
@@ -59,6 +60,7 @@ inline TapTable make_taps_conv(int ks, int stride, int dil, int TH) {
     t.dy_min = -pad; t.dx_min = -pad;
     t.IH = (TH - 1) * stride + (ks - 1) * dil + 1;
     t.IW = 15 * stride + (ks - 1) * dil + 1;
+    t.iw_magic = (1u << 22) / (unsigned)t.IW + 1u;
     return t;
 }
 
@@ -88,6 +90,7 @@ inline TapTables tconv_tables(int TH) {
             }
         t.dy_min = 0; t.dx_min = 0;
         t.IH = TH + 1; t.IW = 17;
+        t.iw_magic = (1u << 22) / 17u + 1u;
     }
     tt.count = 4;
     return tt;
@@ -189,10 +192,18 @@ struct InNHWC {
     const float* p;
     int H, W, C;            // C = stored channel count (>= CINP used by the kernel)
     size_t nstride;         // floats between consecutive images n (H*W*C when dense)
-    __device__ __forceinline__ const float* ptr4(int n, int iy, int ix, int c4, bool& valid) const {
-        valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
-        return valid ? p + (size_t)n * nstride + ((size_t)iy * W + ix) * C + 4 * c4 : p;
-    }
+    bool fits(int) const { return (double)H * W * C < 4294967296.0; }
+    // per-CTA view of image n: the 64-bit part of the address is formed once, the staging loop adds 32-bit offsets
+    // (one image holds < 2^32 floats, checked by the launcher)
+    struct Image {
+        const float* p;
+        int H, W, C;
+        __device__ __forceinline__ const float* ptr4(int iy, int ix, int c4, bool& valid) const {
+            valid = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            return p + (valid ? (unsigned)((iy * W + ix) * C + 4 * c4) : 0u);
+        }
+    };
+    __device__ __forceinline__ Image image(int n) const { return Image{p + (size_t)n * nstride, H, W, C}; }
 };
 inline InNHWC in_nhwc(const float* p, int H, int W, int C, size_t nstride = 0) {
     return InNHWC{p, H, W, C, nstride ? nstride : (size_t)H * W * C};
@@ -203,12 +214,21 @@ struct InNHWC2 {            // channels [0,CA) from a, then [CA, CA+CB) from b (
     const float* a;
     const float* b;
     int H, W, CA, CBc;
-    __device__ __forceinline__ const float* ptr4(int n, int iy, int ix, int c4, bool& valid) const {
-        valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
-        if (!valid) return a;
-        const size_t pix = ((size_t)n * H + iy) * W + ix;
-        const int c = 4 * c4;
-        return c < CA ? a + pix * CA + c : b + pix * CBc + (c - CA);
+    bool fits(int) const { return (double)H * W * (CA > CBc ? CA : CBc) < 4294967296.0; }
+    struct Image {
+        const float* a;
+        const float* b;
+        int H, W, CA, CBc;
+        __device__ __forceinline__ const float* ptr4(int iy, int ix, int c4, bool& valid) const {
+            valid = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            const unsigned pix = valid ? (unsigned)(iy * W + ix) : 0u;
+            const int c = 4 * c4;
+            return c < CA ? a + (pix * (unsigned)CA + (unsigned)c) : b + (pix * (unsigned)CBc + (unsigned)(c - CA));
+        }
+    };
+    __device__ __forceinline__ Image image(int n) const {
+        const size_t px = (size_t)n * H * W;
+        return Image{a + px * CA, b + px * CBc, H, W, CA, CBc};
     }
 };
 
@@ -216,11 +236,17 @@ struct InNCHW3 {            // 3-channel planar image [N][3][H][W] -> channels (
     static constexpr bool kAsync = false;
     const float* p;
     int H, W;
-    __device__ __forceinline__ float4 load4(int n, int iy, int ix, int c4) const {
-        if (c4 != 0 || iy < 0 || iy >= H || ix < 0 || ix >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const size_t plane = (size_t)H * W, o = (size_t)n * 3 * plane + (size_t)iy * W + ix;
-        return make_float4(ldg(p + o), ldg(p + o + plane), ldg(p + o + 2 * plane), 0.f);
-    }
+    bool fits(int) const { return true; }
+    struct Image {
+        const float* p;
+        int H, W;
+        __device__ __forceinline__ float4 load4(int iy, int ix, int c4) const {
+            if (c4 != 0 || iy < 0 || iy >= H || ix < 0 || ix >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t plane = (size_t)H * W, o = (size_t)iy * W + ix;
+            return make_float4(ldg(p + o), ldg(p + o + plane), ldg(p + o + 2 * plane), 0.f);
+        }
+    };
+    __device__ __forceinline__ Image image(int n) const { return Image{p + (size_t)n * 3 * H * W, H, W}; }
 };
 
 struct MmaWeightSel {       // image n of a batched launch picks one of up to three weight sets
@@ -228,6 +254,7 @@ struct MmaWeightSel {       // image n of a batched launch picks one of up to th
                             // PASSES 4: [slice][CINK/2][cout_total] uint2 = (hi half2, lo half2) of a channel pair
     int period, split1, split2;
     __device__ __forceinline__ const float* pick(int n) const {
+        if (period == 1) return w[0];
         const int r = n % period;
         return r < split1 ? w[0] : (r < split2 ? w[1] : w[2]);
     }
@@ -243,9 +270,10 @@ __global__ void __launch_bounds__(Cfg::THREADS)
 mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTables tabs, int cout_total, int Hout, int Wout, int ncb) {
     constexpr int CP = Cfg::CP, NP = Cfg::NP, CINP = Cfg::CINP, NB = Cfg::NB, MT = Cfg::MT, NT = Cfg::NT;
     extern __shared__ __align__(16) float smem[];
-    const int variant = blockIdx.z % tabs.count;
-    const int ncbz = blockIdx.z / tabs.count;
-    const int n = ncbz / ncb, cb = ncbz % ncb;
+    // (uniform special cases: most launches have one stencil variant and / or one cout block -- no runtime divisions)
+    const int variant = tabs.count == 1 ? 0 : blockIdx.z % tabs.count;
+    const int ncbz = tabs.count == 1 ? blockIdx.z : blockIdx.z / tabs.count;
+    const int n = ncb == 1 ? ncbz : ncbz / ncb, cb = ncb == 1 ? 0 : ncbz % ncb;
     const TapTable& taps = tabs.t[variant];
     int tile_floats = 0;
     for (int v = 0; v < tabs.count; ++v) tile_floats = max(tile_floats, tabs.t[v].IH * tabs.t[v].IW * CP);
@@ -289,15 +317,19 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         const int iy0 = oy0 * Cfg::STRIDE + taps.dy_min, ix0 = ox0 * Cfg::STRIDE + taps.dx_min;
         constexpr int C4 = Cfg::CINK / 4;
         const int total = taps.IH * taps.IW * C4;
+        const unsigned magic = taps.iw_magic;
+        const int IW = taps.IW;
+        const auto img = in.image(n);
         for (int i = tid; i < total; i += Cfg::THREADS) {
-            const int slot = i / C4, c4 = i % C4;
-            const int iy = iy0 + slot / taps.IW, ix = ix0 + slot % taps.IW;
+            const int slot = i / C4, c4 = i % C4;                      // C4 is a compile-time constant
+            const int row = (int)(((unsigned)slot * magic) >> 22);     // slot / IW without the runtime division
+            const int iy = iy0 + row, ix = ix0 + (slot - row * IW);
             if constexpr (In::kAsync) {
                 bool valid;
-                const float* src = in.ptr4(n, iy, ix, c4 < CINP / 4 ? c4 : 0, valid);
+                const float* src = img.ptr4(iy, ix, c4 < CINP / 4 ? c4 : 0, valid);
                 cp_async16(sA + (size_t)slot * CP + 4 * c4, src, valid && c4 < CINP / 4);
             } else {
-                *reinterpret_cast<float4*>(sA + (size_t)slot * CP + 4 * c4) = in.load4(n, iy, ix, c4);
+                *reinterpret_cast<float4*>(sA + (size_t)slot * CP + 4 * c4) = img.load4(iy, ix, c4);
             }
         }
     }
@@ -328,14 +360,17 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
 #pragma unroll
                 for (int q = 0; q < 4; ++q) accs[s][r][j][q] = 0.f;
 
+    int ring_cur = 0, ring_fill = 2 % Cfg::RING;       // ring slots of this tap / of the tap loaded two ahead
     for (int tap = 0; tap < ntaps; ++tap) {
         int wsel_buf = tap;
         if constexpr (!Cfg::WALL) {
             cp_async_wait<1>();            // everything but the newest group has landed: tile + this tap's weights
             __syncthreads();               // ... for all threads; also: everyone is done with tap-1's buffer
-            if (tap + 2 < ntaps) issue_weights(tap + 2, (tap + 2) % Cfg::RING);
+            if (tap + 2 < ntaps) issue_weights(tap + 2, ring_fill);
             cp_async_commit();
-            wsel_buf = tap % Cfg::RING;
+            wsel_buf = ring_cur;
+            ring_cur = ring_cur + 1 == Cfg::RING ? 0 : ring_cur + 1;
+            ring_fill = ring_fill + 1 == Cfg::RING ? 0 : ring_fill + 1;
         }
         const float* wb = sW + wsel_buf * Cfg::WBUF;
         const int ry = taps.dy[tap] - taps.dy_min, rx = taps.dx[tap] - taps.dx_min;
@@ -479,6 +514,7 @@ int launch_mma_conv(const char* name, const In& in, const Epi& epi, const MmaWei
     // (a persistent, tile-double-buffered variant of this kernel for the small layers was measured in round 1
     //  and was 5% SLOWER end to end: the doubled tile buffer halves the resident warps and these layers are
     //  issue/latency bound, not load bound -- see profiles/README.md)
+    IMVS_REQUIRE(in.fits(N), "%s: input too large for 32-bit in-image offsets", name);
     const size_t smem = Cfg::smem_bytes(tabs);
     IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
     auto kern = mma_conv_kernel<Cfg, In, Epi>;

@@ -160,6 +160,7 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
         constexpr int MAXIT = 7;                                  // ceil(nslot_max / 64), nslot_max = 394 + padding
         const int kcl = lane & 3, sl = lane >> 2;
         float4 v[MAXIT][KG];
+        const auto img = in.image(n);
 #pragma unroll
         for (int it = 0; it < MAXIT; ++it) {
             const int s = (it * (TC5_THREADS / 32) + warp) * 8 + sl;
@@ -167,7 +168,7 @@ tc5_conv_kernel(const In in, const Epi epi, const float* __restrict__ w_umma, co
 #pragma unroll
             for (int kg = 0; kg < KG; ++kg) {
                 bool valid;
-                const float* src = in.ptr4(n, iy, ix, kg * 4 + kcl, valid);
+                const float* src = img.ptr4(iy, ix, kg * 4 + kcl, valid);
                 v[it][kg] = (valid && s < nslot) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
