@@ -292,14 +292,14 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
             constexpr int Q = NB / 2;
             for (int i = tid; i < (Cfg::CINK / 2) * Q; i += Cfg::THREADS) {
                 const int k = i / Q, q = i % Q;
-                cp_async16(dst + 2 * (k * NP) + 4 * q, src + 2 * ((size_t)k * cout_total) + 4 * q, true);
+                cp_async16(dst + 2 * (k * NP) + 4 * q, src + (unsigned)(2 * (k * cout_total) + 4 * q), true);
             }
         } else {
             const float* src = wg + ((size_t)taps.widx[tap] * CINP) * cout_total + cb * NB;
             constexpr int Q = NB / 4;
             for (int i = tid; i < CINP * Q; i += Cfg::THREADS) {
                 const int k = i / Q, q = i % Q;
-                cp_async16(dst + k * NP + 4 * q, src + (size_t)k * cout_total + 4 * q, true);
+                cp_async16(dst + k * NP + 4 * q, src + (unsigned)(k * cout_total + 4 * q), true);
             }
         }
     };
@@ -360,6 +360,9 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
 #pragma unroll
                 for (int q = 0; q < 4; ++q) accs[s][r][j][q] = 0.f;
 
+    int slot_base[MT];              // smem offset of this lane's first pixel (x = g) of row-tile r at tap offset (0, 0)
+#pragma unroll
+    for (int r = 0; r < MT; ++r) slot_base[r] = ((warp * MT + r) * Cfg::STRIDE * taps.IW + g * Cfg::STRIDE) * CP;
     int ring_cur = 0, ring_fill = 2 % Cfg::RING;       // ring slots of this tap / of the tap loaded two ahead
     for (int tap = 0; tap < ntaps; ++tap) {
         int wsel_buf = tap;
@@ -374,12 +377,12 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
         }
         const float* wb = sW + wsel_buf * Cfg::WBUF;
         const int ry = taps.dy[tap] - taps.dy_min, rx = taps.dx[tap] - taps.dx_min;
+        const int tap_off = (ry * taps.IW + rx) * CP;              // the tap = the same tile read at a shifted address
         int slot0[MT], slot1[MT];
 #pragma unroll
         for (int r = 0; r < MT; ++r) {
-            const int row = (warp * MT + r) * Cfg::STRIDE + ry;
-            slot0[r] = (row * taps.IW + g * Cfg::STRIDE + rx) * CP;
-            slot1[r] = (row * taps.IW + (g + 8) * Cfg::STRIDE + rx) * CP;
+            slot0[r] = slot_base[r] + tap_off;
+            slot1[r] = slot0[r] + 8 * Cfg::STRIDE * CP;
         }
         if constexpr (Cfg::K8) {
             const uint2* wb2 = reinterpret_cast<const uint2*>(wb);
