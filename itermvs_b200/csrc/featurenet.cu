@@ -206,6 +206,7 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     }
     const int w8 = tune("FNETW", 0);     // 1: 8 warps x 1 row-tile per CTA instead of 4 x 2 (same tile, twice the resident warps)
     if (w8) IMVS_TRY((res_stage<8, 16, true, true, 32, 16, 1, 8>(w, 1, b.a0, b.l1, N, H, W, st)));
+    else if (tune("FNET1", 0)) IMVS_TRY((res_stage<8, 16, true, true, 32, 16, 1, 4>(w, 1, b.a0, b.l1, N, H, W, st)));
     else IMVS_TRY((res_stage<8, 16, true, true>(w, 1, b.a0, b.l1, N, H, W, st)));          // layer1 -> l1[3]  [H/2][W/2][16]
     switch (tune("FNET2", 0)) {                                                          // layer2 -> l2[3]  [H/4][W/4][32]
         case 1: IMVS_TRY((res_stage<16, 32, true, false, 32, 16, 2>(w, 6, b.l1[3], b.l2, N, H1, W1, st))); break;
@@ -239,6 +240,12 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
         IMVS_TRY((mma_conv<48, 32, 1, 8, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
         IMVS_TRY((mma_conv<16, 48, 1, 8, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), ei1, WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
         IMVS_TRY((mma_conv<48, 16, 1, 8, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
+    } else if (tune("FNETO", 0)) {      // 4-row tiles: smaller haloed tile in shared memory, more CTAs per SM
+        const TapTables s1m = conv_tables(3, 1, 1, 4), k1m = conv_tables(1, 1, 1, 4);
+        IMVS_TRY((mma_conv<32, 48, 1, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), ei2, WSets::single(w->w[17]), k1m, N, 48, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<48, 32, 1, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1m, N, 32, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<16, 48, 1, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), ei1, WSets::single(w->w[19]), k1m, N, 48, H1, W1, 1, st)));
+        IMVS_TRY((mma_conv<48, 16, 1, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1m, N, 16, H1, W1, 1, st)));
     } else {
         IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), ei2, WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
         IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
