@@ -15,6 +15,7 @@ from .estimator import (ConvGRU, CorrNet, DepthInitialization, Evaluation, IterM
                         Update)
 from .pipeline import FeatureNet, Pipeline, full_loss  # noqa: F401
 from .fusion import check_geometric_consistency, filter_depth_view  # noqa: F401
+from . import io  # noqa: F401  (read_pfm / save_pfm / read_cam_file / read_pair_file / load_views)
 
 __all__ = ["Pipeline", "FeatureNet", "IterMVS", "Evaluation", "Update", "ConvGRU", "CorrNet", "PixelViewWeight",
            "DepthInitialization", "differentiable_warping", "depth_normalization", "depth_unnormalization", "upsample",

@@ -1,0 +1,145 @@
+"""On-disk formats either side of the hot path, byte-compatible with the reference:
+
+    read_pfm / save_pfm            datasets/data_io.py:6-73   (depth_est/*.pfm, confidence/*.pfm)
+    read_cam_file                  datasets/dtu_yao_eval.py:42-53 (cams_1/*_cam.txt: extrinsic 4x4, intrinsic 3x3, depth range)
+    read_pair_file                 eval.py:90-100 (pair.txt)
+    projection_pyramid             datasets/dtu_yao_eval.py:106-126 (4x4 = [K_l @ E[:3,:4]; E[3]] for levels 3..0)
+    image_pyramid / read_img       datasets/dtu_yao_eval.py:61-76
+    load_views                     datasets/dtu_yao_eval.py:78-158 (__getitem__): the dict Pipeline.forward takes
+
+Host-side numpy; nothing here touches the GPU (Pipeline.forward reads imgs['level_0'] and proj_matrices['level_1..3'] only).
+"""
+from __future__ import annotations
+
+import os
+import re
+import sys
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------- PFM --
+def read_pfm(filename: str) -> Tuple[np.ndarray, float]:
+    """-> (data [H,W,1] (Pf) or [H,W,3] (PF), float32, top row first; scale).  Byte order from the sign of the scale."""
+    with open(filename, "rb") as f:
+        header = f.readline().decode("utf-8").rstrip()
+        if header == "PF":
+            channels = 3
+        elif header == "Pf":
+            channels = 1
+        else:
+            raise Exception("Not a PFM file.")
+        m = re.match(r"^(\d+)\s(\d+)\s$", f.readline().decode("utf-8"))
+        if not m:
+            raise Exception("Malformed PFM header.")
+        width, height = int(m.group(1)), int(m.group(2))
+        scale = float(f.readline().rstrip())
+        endian = "<" if scale < 0 else ">"
+        data = np.fromfile(f, endian + "f")
+    return np.flipud(data.reshape(height, width, channels)), abs(scale)
+
+
+def save_pfm(filename: str, image: np.ndarray, scale: float = 1) -> None:
+    """float32 [H,W], [H,W,1] (written as 'Pf') or [H,W,3] ('PF'); rows bottom-up, scale negative = little endian."""
+    if image.dtype.name != "float32":
+        raise Exception("Image dtype must be float32.")
+    if image.ndim == 3 and image.shape[2] == 3:
+        tag = b"PF\n"
+    elif image.ndim == 2 or (image.ndim == 3 and image.shape[2] == 1):
+        tag = b"Pf\n"
+    else:
+        raise Exception("Image must have H x W x 3, H x W x 1 or H x W dimensions.")
+    order = image.dtype.byteorder
+    if order == "<" or (order == "=" and sys.byteorder == "little"):
+        scale = -scale
+    with open(filename, "wb") as f:
+        f.write(tag)
+        f.write(("%d %d\n" % (image.shape[1], image.shape[0])).encode("utf-8"))
+        f.write(("%f\n" % scale).encode("utf-8"))
+        np.flipud(image).tofile(f)
+
+
+# ----------------------------------------------------------------------------------------- cameras --
+def read_cam_file(filename: str):
+    """-> intrinsics [3,3] f32, extrinsics [4,4] f32, depth_min, depth_max (first / last number of line 11)."""
+    with open(filename) as f:
+        lines = [line.rstrip() for line in f.readlines()]
+    extrinsics = np.array(" ".join(lines[1:5]).split(), dtype=np.float32).reshape(4, 4)
+    intrinsics = np.array(" ".join(lines[7:10]).split(), dtype=np.float32).reshape(3, 3)
+    rng = lines[11].split()
+    return intrinsics, extrinsics, float(rng[0]), float(rng[-1])
+
+
+def read_pair_file(filename: str) -> List[Tuple[int, List[int]]]:
+    """pair.txt: view count, then per view its id and '<n> id score id score ...'; views without sources are dropped."""
+    out = []
+    with open(filename) as f:
+        n = int(f.readline())
+        for _ in range(n):
+            ref = int(f.readline().rstrip())
+            srcs = [int(x) for x in f.readline().rstrip().split()[1::2]]
+            if srcs:
+                out.append((ref, srcs))
+    return out
+
+
+def projection_pyramid(intrinsics: np.ndarray, extrinsics: np.ndarray, img_wh: Sequence[int], orig_wh: Sequence[int] = (1600, 1200)
+                       ) -> Dict[str, np.ndarray]:
+    """Per-level 4x4 projection matrices: intrinsics rescaled from the original to the working resolution, then
+    K[:2] *= 1/8, 1/4, 1/2, 1 for levels 3..0 (successive float32 doublings, as the loader does)."""
+    k = np.array(intrinsics, dtype=np.float32, copy=True)
+    e = np.asarray(extrinsics, dtype=np.float32)
+    k[0] *= img_wh[0] / orig_wh[0]
+    k[1] *= img_wh[1] / orig_wh[1]
+    out = {}
+    k[:2, :] *= 0.125
+    for level in (3, 2, 1, 0):
+        p = e.copy()
+        p[:3, :4] = np.matmul(k, p[:3, :4])
+        out[f"level_{level}"] = p
+        k[:2, :] *= 2
+    return out
+
+
+# ------------------------------------------------------------------------------------------ images --
+def image_pyramid(img0: np.ndarray) -> Dict[str, np.ndarray]:
+    """[H,W,3] float32 -> level_0..3 by cv2.resize(INTER_LINEAR) to (W/2^k, H/2^k)."""
+    import cv2
+    h, w = img0.shape[:2]
+    out = {"level_0": img0}
+    for k in (1, 2, 3):
+        out[f"level_{k}"] = cv2.resize(img0, (w // 2 ** k, h // 2 ** k), interpolation=cv2.INTER_LINEAR)
+    return out
+
+
+def read_img(filename: str, img_wh: Sequence[int]) -> Dict[str, np.ndarray]:
+    """8-bit image -> [-1, 1] float32, resized to img_wh, 4-level pyramid."""
+    import cv2
+    from PIL import Image
+    img = 2 * np.array(Image.open(filename), dtype=np.float32) / 255.0 - 1
+    img = cv2.resize(img, tuple(img_wh), interpolation=cv2.INTER_LINEAR)
+    return image_pyramid(img)
+
+
+def load_views(datapath: str, scan: str, ref_view: int, src_views: Sequence[int], nviews: int = 5,
+               img_wh: Sequence[int] = (1600, 1152), orig_wh: Sequence[int] = (1600, 1200)) -> Dict[str, object]:
+    """One sample in the loader's format: imgs {'level_k': [V,3,H_k,W_k]}, proj_matrices {'level_k': [V,4,4]},
+    depth_min / depth_max of the reference view, filename pattern."""
+    view_ids = [ref_view] + list(src_views)[: nviews - 1]
+    imgs = {f"level_{k}": [] for k in range(4)}
+    proj = {f"level_{k}": [] for k in range(4)}
+    depth_min = depth_max = None
+    for i, vid in enumerate(view_ids):
+        pyr = read_img(os.path.join(datapath, "{}/images/{:0>8}.jpg".format(scan, vid)), img_wh)
+        k, e, dmin, dmax = read_cam_file(os.path.join(datapath, "{}/cams_1/{:0>8}_cam.txt".format(scan, vid)))
+        pp = projection_pyramid(k, e, img_wh, orig_wh)
+        for lv in imgs:
+            imgs[lv].append(pyr[lv])
+            proj[lv].append(pp[lv])
+        if i == 0:
+            depth_min, depth_max = dmin, dmax
+    return {"imgs": {lv: np.stack(v).transpose([0, 3, 1, 2]) for lv, v in imgs.items()},
+            "proj_matrices": {lv: np.stack(v) for lv, v in proj.items()},
+            "depth_min": depth_min, "depth_max": depth_max,
+            "filename": scan + "/{}/" + "{:0>8}".format(view_ids[0]) + "{}"}
