@@ -5,9 +5,6 @@
 
 namespace imvs {
 
-int tune(const char* name, int def);      // warp.cu
-int conv_passes();
-
 struct Workspace {
     float *rt1, *rt2, *rt3;
     float *corr_init, *pvw_logits, *vw3, *vw2, *agg_init, *corrnet_scratch, *corr0;
@@ -72,9 +69,7 @@ extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
 
 extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     if (check_problem(pb) != 0) return -1;
-    // mode 4: the head's last 1x1 convolution carries the regression in its epilogue (one launch less per head call)
-    const bool fused_head = conv_passes() == 4 && tune("HEADFUSE", 1);
-    return (fused_head ? 23 : 24) + (fused_head ? 12 : 13) * pb->iterations;
+    return 24 + 13 * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,

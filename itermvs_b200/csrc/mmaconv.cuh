@@ -46,7 +46,6 @@ struct TapTable {
 struct TapTables {          // launch variants (blockIdx.z % count)
     TapTable t[4];
     int count;
-    int max_slots;          // max over the variants of IH * IW (the shared-memory tile is carved for the largest)
 };
 
 inline TapTable make_taps_conv(int ks, int stride, int dil, int TH) {
@@ -69,7 +68,6 @@ inline TapTables conv_tables(int ks, int stride, int dil, int TH) {
     TapTables tt{};
     tt.t[0] = make_taps_conv(ks, stride, dil, TH);
     tt.count = 1;
-    tt.max_slots = tt.t[0].IH * tt.t[0].IW;
     return tt;
 }
 
@@ -95,7 +93,6 @@ inline TapTables tconv_tables(int TH) {
         t.iw_magic = (1u << 22) / 17u + 1u;
     }
     tt.count = 4;
-    tt.max_slots = (TH + 1) * 17;
     return tt;
 }
 
@@ -278,7 +275,8 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
     const int ncbz = tabs.count == 1 ? blockIdx.z : blockIdx.z / tabs.count;
     const int n = ncb == 1 ? ncbz : ncbz / ncb, cb = ncb == 1 ? 0 : ncbz % ncb;
     const TapTable& taps = tabs.t[variant];
-    const int tile_floats = tabs.max_slots * CP;
+    int tile_floats = 0;
+    for (int v = 0; v < tabs.count; ++v) tile_floats = max(tile_floats, tabs.t[v].IH * tabs.t[v].IW * CP);
     float* sA = smem;
     float* sW = smem + tile_floats;
     const int oy0 = blockIdx.y * Cfg::TH, ox0 = blockIdx.x * 16;
@@ -422,34 +420,28 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
                     split_f16(*reinterpret_cast<const float2*>(sA + slot0[r] + k0 + 8), a[r][2], al[r][2]);
                     split_f16(*reinterpret_cast<const float2*>(sA + slot1[r] + k0 + 8), a[r][3], al[r][3]);
                 }
-                // the three products of one accumulator tile are issued MT*JC MMAs apart: back-to-back they
-                // serialise on the accumulator (HMMA latency), which left the tensor pipe 26 % busy.  Wide cout
-                // blocks go through in chunks of 8 n-tiles so that the weight fragments stay in registers.
-                constexpr int JC = NT % 8 == 0 ? 8 : (NT % 6 == 0 ? 6 : (NT % 4 == 0 ? 4 : (NT <= 8 ? NT : 1)));
-                static_assert(NT % JC == 0 && JC > 1 || NT == 1, "n-tile chunking");
+                // the three products of one accumulator tile are issued MT*NT MMAs apart: back-to-back they
+                // serialise on the accumulator (HMMA latency), which left the tensor pipe 26 % busy
+                uint2 w0[NT], w1[NT];
 #pragma unroll
-                for (int j0 = 0; j0 < NT; j0 += JC) {
-                    uint2 w0[JC], w1[JC];
+                for (int j = 0; j < NT; ++j) {
+                    w0[j] = wb2[(ks * 8 + t) * NP + 8 * j + g];
+                    w1[j] = wb2[(ks * 8 + t + 4) * NP + 8 * j + g];
+                }
 #pragma unroll
-                    for (int j = 0; j < JC; ++j) {
-                        w0[j] = wb2[(ks * 8 + t) * NP + 8 * (j0 + j) + g];
-                        w1[j] = wb2[(ks * 8 + t + 4) * NP + 8 * (j0 + j) + g];
-                    }
 #ifndef IMVS_EXP_ONE_PRODUCT     // (timing experiment: hi*hi only -- wrong results)
+                for (int j = 0; j < NT; ++j)
 #pragma unroll
-                    for (int j = 0; j < JC; ++j)
+                    for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_LH][r][j], al[r][0], al[r][1], al[r][2], al[r][3], w0[j].x, w1[j].x);
 #pragma unroll
-                        for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_LH][r][j0 + j], al[r][0], al[r][1], al[r][2], al[r][3], w0[j].x, w1[j].x);
+                for (int j = 0; j < NT; ++j)
 #pragma unroll
-                    for (int j = 0; j < JC; ++j)
-#pragma unroll
-                        for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_HL][r][j0 + j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].y, w1[j].y);
+                    for (int r = 0; r < MT; ++r) mma_f16(accs[ACC_HL][r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].y, w1[j].y);
 #endif
 #pragma unroll
-                    for (int j = 0; j < JC; ++j)
+                for (int j = 0; j < NT; ++j)
 #pragma unroll
-                        for (int r = 0; r < MT; ++r) mma_f16(acc[r][j0 + j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].x, w1[j].x);
-                }
+                    for (int r = 0; r < MT; ++r) mma_f16(acc[r][j], a[r][0], a[r][1], a[r][2], a[r][3], w0[j].x, w1[j].x);
             }
         } else {
 #pragma unroll

@@ -168,94 +168,6 @@ __global__ void __launch_bounds__(256) softmax_regress_kernel(const RegressParam
     }
 }
 
-
-// depth_head.4 (1x1, 64 -> 256, + bias) with the whole regression in the epilogue.  The CTA's cout block is all
-// 256 bins, so the four lanes of a quad hold the 256 logits of a pixel (lane t: bins 8j + 2t, 8j + 2t + 1,
-// j = 0..31): softmax statistics, arg-max (first maximum) and the clamped +-4 window reduce with two xor-shuffles
-// each, and the [B][P][256] logits tensor is never written (21 MB out + 21 MB back in per call at 640x512).
-// Same arithmetic as softmax_regress_kernel bin by bin; only the order of the sums over bins differs.
-struct EpiRegress {
-    RegressParams prm;       // .logits unused; .prob must be null (the probability volume is the other path)
-    const float* bias;       // [256]
-    int H, W;
-    template <int NT>
-    __device__ __forceinline__ void row(int n, int oy, int ox, int, int t, const float (&vin)[2 * NT], int) const {
-        static_assert(NT == IMVS_OUT_BINS / 8, "the cout block must hold all bins");
-        constexpr unsigned FULL = 0xffffffffu;
-        float e[2 * NT];
-        float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const float2 b = ldg2(bias + 8 * j + 2 * t);
-            e[2 * j] = vin[2 * j] + b.x;
-            e[2 * j + 1] = vin[2 * j + 1] + b.y;
-            m = fmaxf(m, fmaxf(e[2 * j], e[2 * j + 1]));
-        }
-        m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 2 * NT; ++k) { e[k] = expf(e[k] - m); s += e[k]; }
-        s += __shfl_xor_sync(FULL, s, 1);
-        s += __shfl_xor_sync(FULL, s, 2);
-        // arg-max over probabilities, first index on ties; only bins with e > 0.5 can reach the maximum 1 / s
-        float bv = -1.f;
-        int bi = 0;
-#pragma unroll
-        for (int k = 0; k < 2 * NT; ++k) {
-            const int ch = 8 * (k >> 1) + 2 * t + (k & 1);                 // increasing in k
-            const float pr = e[k] > 0.5f ? fmaxf(e[k], 0.5f) / s : 0.f;
-            if (pr > bv) { bv = pr; bi = ch; }
-        }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            const float ov = __shfl_xor_sync(FULL, bv, o);
-            const int oi = __shfl_xor_sync(FULL, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        // window: indices clamp(bi-4 .. bi+4, 0, 255); clamped duplicates are counted repeatedly (itermvs.py:203-219)
-        float num = 0.f, den = 0.f;
-#pragma unroll
-        for (int k = 0; k < 2 * NT; ++k) {
-            const int ch = 8 * (k >> 1) + 2 * t + (k & 1);
-            int mult = (ch >= bi - IMVS_RADIUS && ch <= bi + IMVS_RADIUS) ? 1 : 0;
-            if (ch == 0) mult = max(0, IMVS_RADIUS + 1 - bi);
-            if (ch == IMVS_OUT_BINS - 1) mult = max(0, bi - (IMVS_OUT_BINS - 2 - IMVS_RADIUS));
-            const float pw = (mult ? e[k] : 1.0f) / s;
-            num = fmaf((float)(mult * ch), pw, num);
-            den = fmaf((float)mult, pw, den);
-        }
-        num += __shfl_xor_sync(FULL, num, 1);
-        den += __shfl_xor_sync(FULL, den, 1);
-        num += __shfl_xor_sync(FULL, num, 2);
-        den += __shfl_xor_sync(FULL, den, 2);
-        const float ndv = (num / (1e-6f + den)) / (float)(IMVS_OUT_BINS - 1);
-        const bool inside = oy < H && ox < W;
-        const size_t p = inside ? (size_t)oy * W + ox : 0, gw = (size_t)n * prm.P + p;
-        const bool want_conf = (prm.conf != nullptr) || (prm.conf_logit != nullptr);
-        float cs = 0.f;
-        if (want_conf) {                    // confidence_head.2: 32 features of the conv0 output, 8 per lane of the quad
-            const float* tf = prm.t + gw * 64 + 32 + 8 * t;
-            const float4 a0 = ldg4(tf), a1 = ldg4(tf + 4), w0 = ldg4(prm.conf_w + 8 * t), w1 = ldg4(prm.conf_w + 8 * t + 4);
-            cs = a0.x * w0.x;
-            cs = fmaf(a0.y, w0.y, cs); cs = fmaf(a0.z, w0.z, cs); cs = fmaf(a0.w, w0.w, cs);
-            cs = fmaf(a1.x, w1.x, cs); cs = fmaf(a1.y, w1.y, cs); cs = fmaf(a1.z, w1.z, cs); cs = fmaf(a1.w, w1.w, cs);
-            cs += __shfl_xor_sync(FULL, cs, 1);
-            cs += __shfl_xor_sync(FULL, cs, 2);
-            cs += ldg(prm.conf_b);
-        }
-        if (t == 0 && inside) {
-            prm.nd_out[(size_t)n * prm.nd_bstride + p * prm.nd_pstride] = ndv;
-            if (prm.depth_out) {
-                const float inv_min = 1.0f / prm.depth_min[n], inv_max = 1.0f / prm.depth_max[n];
-                prm.depth_out[gw] = unnormalize_depth(ndv, inv_min, inv_max);
-            }
-            if (prm.conf_logit) prm.conf_logit[gw] = cs;
-            if (prm.conf) prm.conf[gw] = sigmoidf_(cs);
-        }
-    }
-};
-
 }  // namespace imvs
 
 using namespace imvs;
@@ -341,23 +253,9 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
                                                            conv_tables(3, 1, 2, 8), B, 64, H, W, nc, st)));
         }
     }
-    RegressParams prm;
-    prm.logits = logits; prm.t = t; prm.conf_w = w->conf_fc; prm.conf_b = w->conf_fc_b;
-    prm.nd_out = nd_out; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
-    prm.prob = probability; prm.conf = conf; prm.conf_logit = conf_logit; prm.depth_out = depth_out;
-    prm.depth_min = depth_min; prm.depth_max = depth_max;
-    prm.B = B; prm.P = (int)P;
-    // inference (no probability volume requested): fc2 + softmax + regression in one kernel, logits never stored
-    const bool fuse_tail = probability == nullptr && conv_passes() == 4 && tune("HEADFUSE", 1);
     {
         const EpiNHWC e1{h1, nullptr, nullptr, H, W, 64, 64, 1};
         const EpiNHWC e2{logits, w->head_fc2_b, nullptr, H, W, 256, 256, 0};
-        if (fuse_tail) {
-            IMVS_TRY((mma_conv<32, 64, 1, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), e1, WSets::single(w->head_fc1), conv_tables(1, 1, 1, 4), B, 64, H, W, 1, st)));
-            IMVS_TRY((mma_conv<64, 256, 1, 4, 1, true>("head.fc2+regress", in_nhwc(h1, H, W, 64), EpiRegress{prm, w->head_fc2_b, H, W},
-                                                       WSets::single(w->head_fc2), conv_tables(1, 1, 1, 4), B, 256, H, W, 1, st)));
-            return 0;
-        }
         switch (tune("FC", 2)) {
             case 1:      // fc1 in 16-cout blocks, fc2 in 32-cout blocks
                 IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("head.fc1", in_nhwc(t, H, W, 64), e1, WSets::single(w->head_fc1), conv_tables(1, 1, 1, 8), B, 64, H, W, 4, st)));
@@ -372,6 +270,12 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
                 IMVS_TRY((mma_conv<64, 64, 2, 4, 1, true>("head.fc2", in_nhwc(h1, H, W, 64), e2, WSets::single(w->head_fc2), conv_tables(1, 1, 1, 8), B, 256, H, W, 4, st)));
         }
     }
+    RegressParams prm;
+    prm.logits = logits; prm.t = t; prm.conf_w = w->conf_fc; prm.conf_b = w->conf_fc_b;
+    prm.nd_out = nd_out; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
+    prm.prob = probability; prm.conf = conf; prm.conf_logit = conf_logit; prm.depth_out = depth_out;
+    prm.depth_min = depth_min; prm.depth_max = depth_max;
+    prm.B = B; prm.P = (int)P;
     const size_t warps = (size_t)B * P;
     IMVS_CUDA(launch_k(softmax_regress_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, prm));
     return 0;

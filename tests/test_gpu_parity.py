@@ -325,37 +325,6 @@ def test_all_predictions_forward_matches_reference(dev, dtu_weights, e2e_allpred
         m(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
 
 
-def test_fused_head_tail_matches_unfused_incl_window_edges(dev, dtu_weights):
-    """The inference head (fc2 + softmax + arg-max + window regression + confidence in one kernel, logits never
-    stored) against the three-kernel path that also serves the probability volume, on random hidden states and with
-    the arg-max forced to bins 0, 1, 3, 252, 254, 255 through the fc2 bias (window clamping with duplicate edge bins)."""
-    import os
-    import itermvs_b200
-    from itermvs_b200.estimator import _nhwc
-    torch.manual_seed(3)
-    hidden = torch.tanh(torch.randn(2, 32, 24, 40, device=dev))
-    for forced in (None, 0, 1, 3, 252, 254, 255):
-        sd = {k[len("iter_mvs.update."):]: v.clone() for k, v in dtu_weights.items() if k.startswith("iter_mvs.update.")}
-        if forced is not None:
-            sd["depth_head.4.bias"][forced] += 60.0
-        upd = itermvs_b200.Update(11, 32, 32)
-        upd.load_state_dict(sd, strict=True)
-        upd = upd.to(dev).eval()
-        hn = _nhwc(hidden)
-        os.environ["IMVS_TUNE_HEADFUSE"] = "0"
-        try:
-            nd_a, _, conf_a, logit_a = upd._heads_nhwc(hn, True)
-        finally:
-            os.environ.pop("IMVS_TUNE_HEADFUSE")
-        nd_b, prob_b, conf_b, logit_b = upd._heads_nhwc(hn, True)            # fused (no probability requested in eval mode)
-        assert prob_b is None
-        assert maxerr(nd_a, nd_b) < 2e-6, (forced, maxerr(nd_a, nd_b))
-        assert maxerr(conf_a, conf_b) < 1e-6 and maxerr(logit_a, logit_b) < 1e-5
-        if forced is not None:
-            want = O.window_regression(torch.softmax(torch.full((1, 256, 1, 1), -60.0).index_fill_(1, torch.tensor([forced]), 0.0), dim=1))
-            assert abs(float(nd_b.mean()) - float(want)) < 1e-4, (forced, float(nd_b.mean()), float(want))
-
-
 def test_streaming_two_in_flight_is_race_free(dev, model):
     """graph.StreamingPipeline with two reference views in flight (own workspace, static buffers and compute
     stream per slot): every result must equal the plain forward of the same inputs, bit for bit."""
