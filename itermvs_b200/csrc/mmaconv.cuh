@@ -46,6 +46,7 @@ struct TapTable {
 struct TapTables {          // launch variants (blockIdx.z % count)
     TapTable t[4];
     int count;
+    int max_slots;          // max over the variants of IH * IW (the shared-memory tile is carved for the largest)
 };
 
 inline TapTable make_taps_conv(int ks, int stride, int dil, int TH) {
@@ -68,6 +69,7 @@ inline TapTables conv_tables(int ks, int stride, int dil, int TH) {
     TapTables tt{};
     tt.t[0] = make_taps_conv(ks, stride, dil, TH);
     tt.count = 1;
+    tt.max_slots = tt.t[0].IH * tt.t[0].IW;
     return tt;
 }
 
@@ -93,6 +95,7 @@ inline TapTables tconv_tables(int TH) {
         t.iw_magic = (1u << 22) / 17u + 1u;
     }
     tt.count = 4;
+    tt.max_slots = (TH + 1) * 17;
     return tt;
 }
 
@@ -275,8 +278,7 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
     const int ncbz = tabs.count == 1 ? blockIdx.z : blockIdx.z / tabs.count;
     const int n = ncb == 1 ? ncbz : ncbz / ncb, cb = ncb == 1 ? 0 : ncbz % ncb;
     const TapTable& taps = tabs.t[variant];
-    int tile_floats = 0;
-    for (int v = 0; v < tabs.count; ++v) tile_floats = max(tile_floats, tabs.t[v].IH * tabs.t[v].IW * CP);
+    const int tile_floats = tabs.max_slots * CP;
     float* sA = smem;
     float* sW = smem + tile_floats;
     const int oy0 = blockIdx.y * Cfg::TH, ox0 = blockIdx.x * 16;
