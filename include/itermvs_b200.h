@@ -44,6 +44,9 @@ extern "C" {
 #define IMVS_XCH 16            /* stored channels of the GRU input x (11 used) */
 #define IMVS_MAX_VIEWS 16      /* source views per reference view supported by the fused kernels */
 
+/* Library plumbing -- no reference counterpart (the reference reports errors as Python exceptions, e.g. the
+ * assert at module.py:83,87): ABI version checked by the binding at load time, text of the last failed call on
+ * this thread, number of kernels launched by this library so far (bench.py's gpu_launches). */
 int imvs_abi_version(void);
 const char* imvs_last_error(void);
 long long imvs_launches_total(void);
@@ -134,7 +137,8 @@ int imvs_differentiable_warping_backward(const float* grad_out, const float* src
                                          const float* depth_samples, float* grad_src_fea, int B, int C, int H1, int W1,
                                          int D, int H, int W, float* rt_scratch, int* nan_flag, void* stream);
 
-/* layout helpers: [N][C][H][W] <-> [N][H][W][C] */
+/* layout helpers: [N][C][H][W] <-> [N][H][W][C].  The reference keeps every tensor NCHW (e.g. the feature lists
+ * returned by FeatureNet.forward, net.py:56-66); the single-operator mirrors convert at their boundary. */
 int imvs_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, void* stream);
 int imvs_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, void* stream);
 
