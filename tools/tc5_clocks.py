@@ -1,3 +1,5 @@
+"""Phase clock stamps of CTA 0 of the tcgen05 convolution (ConvGRU, TF32 mode): staging / MMA / epilogue cycles.
+ncu cannot replay that kernel on this pool's driver, hence the in-kernel stamps.  Needs a GPU."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, itermvs_b200
