@@ -172,6 +172,27 @@ int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
                        const float* samples1, const float* samples2, const float* samples3, float* agg,
                        int B, int V, int H2, int W2, void* stream);
 
+/* Backward of imvs_warpcorr_init with respect to the feature pyramid (the sampling grid carries no
+ * gradient, module.py:77; source views receive grid_sample's input gradient, the reference view the gradient
+ * through the product of itermvs.py:50).  Same inputs as the forward (the hypotheses are recomputed, nothing is
+ * saved between the passes); grad_corr [B][S][D][P3][8]; grad_fea3 [B][V][H3][W3][48] is overwritten.
+ * No counterpart call in the reference: there torch.autograd walks the saved [C,D,H,W] volumes. */
+int imvs_warpcorr_init_backward(const float* fea3, const float* rt3, const float* depth_min, const float* depth_max,
+                                const float* depth_samples, const float* grad_corr, float* grad_fea3,
+                                int B, int V, int H3, int W3, int D, void* stream);
+
+/* Backward of imvs_warpcorr_iter with respect to the three feature pyramids (reference view incl. its resampling of
+ * itermvs.py:95-98, and source views).  The view weights and the hypotheses are constants here, as in the reference
+ * (itermvs.py:295 view_weights.detach(); 282-283 normalized_depth.detach()).  grad_agg [B][10][P2][8];
+ * grad_fea1/2/3 have the shapes of fea1/2/3 and are overwritten. */
+int imvs_warpcorr_iter_backward(const float* fea1, const float* fea2, const float* fea3,
+                                const float* rt1, const float* rt2, const float* rt3,
+                                const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
+                                const float* depth_min, const float* depth_max,
+                                const float* samples1, const float* samples2, const float* samples3,
+                                const float* grad_agg, float* grad_fea1, float* grad_fea2, float* grad_fea3,
+                                int B, int V, int H2, int W2, void* stream);
+
 /* itermvs.py:367-381 -- CorrNet on N slices of a [N][P][8] volume.  Slice n uses weight set
  * sets[(n % period) < split1 ? 0 : (n % period) < split2 ? 1 : 2].  The scalar output of slice n, pixel p
  * goes to out[(n / period) * out_batch_stride + p * out_pixel_stride + (n % period)].

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "imvs_pixel_view_weight": (ci, [PW, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "imvs_aggregate_init": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_warpcorr_iter": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "imvs_warpcorr_init_backward": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "imvs_warpcorr_iter_backward": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_corrnet_scratch_floats": (sz, [ci, ci, ci]),
     "imvs_corrnet": (ci, [C.POINTER(CorrNetWeights), ci, ci, ci, vp, vp, sz, sz, vp, ci, ci, ci, vp]),
     "imvs_hidden_init": (ci, [PW, vp, vp, vp, ci, ci, ci, ci, vp]),

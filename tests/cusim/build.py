@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "itermvs_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libitermvs_sim.so")
-SIM_SOURCES = ["warp.cu", "warpcorr.cu", "fusion.cu"]
+SIM_SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "fusion.cu"]
 HEADERS = ["common.cuh", "sampling.cuh"]
 CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
             "-fno-strict-aliasing"]

@@ -141,6 +141,12 @@ static inline T __ldg(const T* p) {
 // fibers never pre-empt each other between sync points: plain read-modify-write is atomic here
 template <class T>
 static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+static inline float4 atomicAdd(float4* p, float4 v) {          // red.global.add.v4.f32 (sm_90+): 16-byte aligned
+    if (reinterpret_cast<uintptr_t>(p) % 16 != 0) cusim::die("misaligned vector atomicAdd");
+    float4 o = *p;
+    p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+    return o;
+}
 static inline unsigned atomicAdd(unsigned* p, int v) { unsigned o = *p; *p = o + (unsigned)v; return o; }
 template <class T>
 static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }

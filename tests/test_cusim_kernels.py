@@ -245,3 +245,82 @@ def test_fusion_kernels_source_on_cpu(sim, fusion_kat):
     with np.errstate(invalid="ignore"):
         close = np.isclose(avg, z["depth_est_averaged"], rtol=2e-6, atol=1e-4, equal_nan=True)
     assert (close | ~same).mean() > 0.9995
+
+
+def _unstack_grad(g, n_src):
+    """[B][V][H][W][C] gradient -> (reference NCHW, [source NCHW])."""
+    g = g.permute(0, 1, 4, 2, 3)
+    return g[:, 0], [g[:, v + 1] for v in range(n_src)]
+
+
+def _sig():
+    return [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp], \
+           [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+
+
+@pytest.mark.parametrize("batch,n_src,d,explicit", [(1, 2, 8, True), (2, 3, 5, False)])
+def test_warpcorr_init_backward_source_on_cpu(sim, batch, n_src, d, explicit):
+    """warpcorr_init_bwd_kernel against torch autograd through the oracle's warp -> group correlation chain."""
+    sim.imvs_warpcorr_init_backward.restype, sim.imvs_warpcorr_init_backward.argtypes = ci, _sig()[0]
+    ref, srcs, rp, sp, s = feature_inputs(96, 64, n_src, batch, seed=21)
+    h3, w3 = ref["level3"].shape[2:]
+    inv_min = (1.0 / s["depth_min"]).view(batch, 1, 1, 1)
+    inv_max = (1.0 / s["depth_max"]).view(batch, 1, 1, 1)
+    ds = O.initial_depth_samples(inv_min, inv_max, d, h3, w3)
+    if explicit:
+        ds[:, 1, :2] = -10.0                      # z <= 0.01 substitution: those samples land outside the map
+    r3 = ref["level3"].clone().requires_grad_(True)
+    s3 = [t.clone().requires_grad_(True) for t in srcs["level3"]]
+    corr = torch.stack([O.group_correlation(O.differentiable_warping(src, p, rp["level3"], ds), r3)
+                        for src, p in zip(s3, sp["level3"])], dim=1)              # [B,S,G,D,H,W]
+    gcorr = torch.randn(corr.shape, generator=torch.Generator().manual_seed(4))
+    (corr * gcorr).sum().backward()
+    fea3 = stack_views(ref["level3"], srcs["level3"])
+    rt3 = compose(sim, rp["level3"], sp["level3"])
+    g_k = f32(gcorr.permute(0, 1, 3, 4, 5, 2).reshape(batch, n_src, d, h3 * w3, 8))
+    gfea = torch.full(fea3.shape, float("nan"))
+    dmin, dmax = f32(s["depth_min"]), f32(s["depth_max"])
+    ok(sim, sim.imvs_warpcorr_init_backward(P(fea3), P(rt3), None if explicit else P(dmin), None if explicit else P(dmax),
+                                            P(f32(ds)) if explicit else None, P(g_k), P(gfea), batch, n_src + 1, h3, w3, d, None))
+    gref, gsrcs = _unstack_grad(gfea, n_src)
+    assert maxerr(gref, r3.grad) < 2e-4 * max(1.0, float(r3.grad.abs().max()))
+    for got, t in zip(gsrcs, s3):
+        assert maxerr(got, t.grad) < 2e-4 * max(1.0, float(t.grad.abs().max()))
+
+
+@pytest.mark.parametrize("batch,n_src,explicit", [(1, 3, True), (2, 2, False)])
+def test_warpcorr_iter_backward_source_on_cpu(sim, batch, n_src, explicit):
+    """warpcorr_iter_bwd_kernel<level> against torch autograd through the oracle's iteration branch up to (not
+    including) CorrNet: source features, reference features through the 2x2 mean / bilinear x2 resampling."""
+    sim.imvs_warpcorr_iter_backward.restype, sim.imvs_warpcorr_iter_backward.argtypes = ci, _sig()[1]
+    ref, srcs, rp, sp, s = feature_inputs(64, 64, n_src, batch, seed=22)
+    h2, w2 = ref["level2"].shape[2:]
+    g = torch.Generator().manual_seed(6)
+    inv_min = (1.0 / s["depth_min"]).view(batch, 1, 1, 1)
+    inv_max = (1.0 / s["depth_max"]).view(batch, 1, 1, 1)
+    nd = torch.rand(batch, 1, h2, w2, generator=g)
+    nd[:, :, 0, :4] = torch.tensor([0.0, 1.0, 0.001, 0.999])
+    samples = {f"level{l}": O.iteration_depth_samples(nd, l, inv_min, inv_max) for l in (1, 2, 3)}
+    vw = torch.rand(batch, n_src, h2, w2, generator=g)
+    rg = {k: v.clone().requires_grad_(True) for k, v in ref.items()}
+    sg = {k: [t.clone().requires_grad_(True) for t in v] for k, v in srcs.items()}
+    want = torch.cat(_aggregated_only(rg, sg, rp, sp, samples, vw), dim=2)            # [B,8,10,H2,W2]
+    gagg = torch.randn(want.shape, generator=g)
+    (want * gagg).sum().backward()
+    feas = [stack_views(ref[f"level{l}"], srcs[f"level{l}"]) for l in (1, 2, 3)]
+    rts = [compose(sim, rp[f"level{l}"], sp[f"level{l}"]) for l in (1, 2, 3)]
+    smp = [f32(samples[f"level{l}"]) for l in (1, 2, 3)] if explicit else [None] * 3
+    gk = f32(gagg.permute(0, 2, 3, 4, 1).reshape(batch, 10, h2 * w2, 8))
+    gf = [torch.full(f.shape, float("nan")) for f in feas]
+    dmin, dmax, ndc = f32(s["depth_min"]), f32(s["depth_max"]), f32(nd)
+    ok(sim, sim.imvs_warpcorr_iter_backward(P(feas[0]), P(feas[1]), P(feas[2]), P(rts[0]), P(rts[1]), P(rts[2]),
+                                            None if explicit else P(ndc), h2 * w2, 1, P(f32(vw)),
+                                            None if explicit else P(dmin), None if explicit else P(dmax),
+                                            P(smp[0]), P(smp[1]), P(smp[2]), P(gk), P(gf[0]), P(gf[1]), P(gf[2]),
+                                            batch, n_src + 1, h2, w2, None))
+    for l in (1, 2, 3):
+        gref, gsrcs = _unstack_grad(gf[l - 1], n_src)
+        want_ref = rg[f"level{l}"].grad
+        assert maxerr(gref, want_ref) < 2e-4 * max(1.0, float(want_ref.abs().max())), l
+        for got, t in zip(gsrcs, sg[f"level{l}"]):
+            assert maxerr(got, t.grad) < 2e-4 * max(1.0, float(t.grad.abs().max())), l
