@@ -5,7 +5,8 @@ load with `load_state_dict`, with or without the DataParallel 'module.' prefix s
 Pipeline.forward(imgs, proj_matrices, depth_min, depth_max)            reference net.py:78
     test=True  -> {"depths_upsampled", "confidence_upsampled"}         reference net.py:125-128
     test=False -> {"depths": {"combine","probability","initial"}, "depths_upsampled", "confidences",
-                   "confidence_upsampled"}  (net.py:115-120) -- forward only (validation); no backward kernels
+                   "confidence_upsampled"}  (net.py:115-120): eval() = forward only on the inference kernels
+                   (validation, train.py:257); train() = differentiable training path (training.py)
 full_loss(...)                                                         reference net.py:131-190
 """
 from __future__ import annotations
@@ -152,6 +153,11 @@ class Pipeline(nn.Module):
         x = imgs["level_0"]
         if not x.is_cuda:
             raise RuntimeError("itermvs_b200.Pipeline: inputs must be CUDA tensors (there is no CPU path)")
+        if self.training and not self.test:
+            # train.py:205 (model.train(); BatchNorm batch statistics; gradients): fused plane sweep with its CUDA
+            # backward + the convolution stacks under torch autograd -- itermvs_b200/training.py
+            from . import training
+            return training.pipeline_train_forward(self, imgs, proj_matrices, depth_min, depth_max)
         if not self.test:
             return self._forward_all_predictions(imgs, proj_matrices, depth_min, depth_max)
         f1, f2, f3 = self.feature_net.forward_nhwc(x)

@@ -1,0 +1,110 @@
+"""Training path (itermvs_b200/training.py) against a training step of the REFERENCE ITSELF
+(tests/golden/train_step_kat.npz, made by tests/golden/make_golden_train_step.py: Pipeline.train() forward,
+full_loss, backward with the DTU checkpoint).
+
+On this CPU-only suite the fused plane-sweep operators (forward and backward CUDA kernels) execute through
+tests/cusim -- the real kernel sources, emulated -- by pointing training.py's three backend hooks at the simulation;
+the convolution stacks are the same ATen modules the GPU path uses.  The GPU twin of this test is
+tests/test_gpu_training.py.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cusim"))
+import build as cusim_build  # noqa: E402
+
+from itermvs_b200.synthetic import make_sample, plane_depth_map  # noqa: E402
+
+
+def _ground_truth(width, height, batch):
+    d0 = torch.from_numpy(plane_depth_map(width, height).astype(np.float32))[None, None].repeat(batch, 1, 1, 1)
+    gt = {"level_0": d0, "level_2": F.interpolate(d0, scale_factor=0.25, mode="nearest")}
+    mask = {k: torch.ones_like(v) for k, v in gt.items()}
+    mask["level_0"][..., :6, :] = 0
+    mask["level_2"][..., :2, :] = 0
+    return gt, mask
+
+
+@pytest.fixture()
+def sim_backend(monkeypatch):
+    from itermvs_b200 import _lib, training
+    lib = C.CDLL(cusim_build.build())
+    for name in ("imvs_compose_projections", "imvs_warpcorr_init", "imvs_warpcorr_iter", "imvs_warpcorr_init_backward",
+                 "imvs_warpcorr_iter_backward", "imvs_last_error"):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = _lib._SIGNATURES[name]
+    monkeypatch.setattr(training, "_L", lambda: lib)
+    monkeypatch.setattr(training, "_st", lambda: None)
+    monkeypatch.setattr(training, "_chk", lambda t, name: t.float().contiguous())
+    return lib
+
+
+@pytest.fixture(scope="module")
+def kat():
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_step_kat.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_training_step_matches_reference(sim_backend, kat, dtu_weights):
+    import itermvs_b200
+    from itermvs_b200 import training
+    w, h, n_src, iters, batch, seed = (int(kat[k]) for k in ("width", "height", "n_src", "iteration", "batch", "seed"))
+    torch.manual_seed(0)
+    m = itermvs_b200.Pipeline(iteration=iters, test=False)
+    m.load_state_dict(dtu_weights, strict=True)
+    m.train()
+    s = make_sample(w, h, n_src=n_src, batch=batch, seed=seed, scene="plane")
+    gt, mask = _ground_truth(w, h, batch)
+    out = training.pipeline_train_forward(m, s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"])
+    # forward: every prediction of the training structure (net.py:115-120)
+    assert len(out["depths"]["combine"]) == iters + 1 and len(out["confidences"]) == iters + 1
+    rel = lambda a, b: float(((a - b).abs() / b.abs().clamp_min(1e-6)).max())
+    assert rel(out["depths"]["initial"][0].detach(), torch.from_numpy(kat["depth_initial"])) < 1e-3
+    for i in range(iters + 1):
+        same = (out["depths"]["probability"][i].argmax(1).numpy() == kat[f"probability{i}_argmax"])
+        assert same.mean() > 0.995, (i, same.mean())
+        d, dref = out["depths"]["combine"][i].detach(), torch.from_numpy(kat[f"combine{i}"])
+        ok = torch.from_numpy(same).unsqueeze(1)
+        assert rel(d[ok], dref[ok]) < 1e-3, i
+        c, cref = out["confidences"][i].detach(), torch.from_numpy(kat[f"confidence_logit{i}"])
+        assert float((c - cref).abs()[ok].max()) < 5e-3, i
+    loss = itermvs_b200.full_loss(out["depths"], out["depths_upsampled"], out["confidences"], gt, mask, s["depth_min"], s["depth_max"])
+    assert abs(loss.item() - float(kat["loss"])) < 1e-4 * float(kat["loss"])       # measured 1e-6
+    # BatchNorm batch statistics were used and the running statistics updated, as in the reference's train() mode
+    assert np.allclose(m.feature_net.conv1.bn.running_mean.numpy(), kat["bn_running_mean"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(m.feature_net.conv1.bn.running_var.numpy(), kat["bn_running_var"], rtol=1e-4, atol=1e-6)
+    # backward: through the CUDA backward kernels of the plane sweep into FeatureNet
+    loss.backward()
+    params = dict(m.named_parameters())
+    total_ref = float(np.sqrt((kat["grad_norms"] ** 2).sum()))
+    worst = 0.0
+    for name, ref_norm in zip(kat["grad_names"], kat["grad_norms"]):
+        p = params[str(name)]
+        got = 0.0 if p.grad is None else float(p.grad.double().norm())
+        if ref_norm == 0.0:
+            assert got == 0.0, name                                  # feature_net.inner3: unused in forward (net.py:25)
+            continue
+        worst = max(worst, abs(got - ref_norm) / max(ref_norm, 1e-3 * total_ref))
+    assert worst < 1e-3, worst           # measured 2e-5
+    for key in kat:
+        if not key.startswith("grad:"):
+            continue
+        g, gref = params[key[5:]].grad, torch.from_numpy(kat[key])
+        assert float((g - gref).abs().max()) < 1e-3 * max(float(gref.abs().max()), 1e-3 * total_ref), key
+
+
+def test_train_mode_dispatch_and_errors(dtu_weights):
+    """Pipeline.forward in train() mode goes to the training path (and, like every entry, refuses CPU tensors: the
+    fused operators have no CPU implementation in the product)."""
+    import itermvs_b200
+    m = itermvs_b200.Pipeline(iteration=1, test=False)
+    m.train()
+    s = make_sample(64, 64, n_src=1, batch=1, seed=1, scene="plane")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"])
