@@ -15,7 +15,7 @@ Split of work (SURVEY 8b "Autograd"):
     that hold the parameters for the inference kernels, so state_dict, optimizer and checkpoints are shared.  The
     tensor-core inference kernels have no backward; they stay the eval()/test path.
 
-There is no CPU path: the fused operators need the CUDA library (tests substitute tests/cusim for it; the product
+There is no CPU path: the fused operators need the CUDA library (the CPU test-suite substitutes an emulation of the kernel sources for it; the product
 never does).
 """
 from __future__ import annotations

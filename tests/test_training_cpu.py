@@ -108,3 +108,36 @@ def test_train_mode_dispatch_and_errors(dtu_weights):
     s = make_sample(64, 64, n_src=1, batch=1, seed=1, scene="plane")
     with pytest.raises(RuntimeError, match="CUDA"):
         m(s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"])
+
+
+def test_train_step_with_flat_bucket(sim_backend, dtu_weights):
+    """train_step (train.py:194-215) through FlatBucketDDP on the real model: gradients land in the bucket, the
+    clipped Adam step moves the parameters, the unused FPN branch stays where it was, a second step reuses the views."""
+    import itermvs_b200
+    from itermvs_b200 import training
+    from itermvs_b200.ddp import FlatBucketDDP, train_step
+
+    class OnSim(torch.nn.Module):               # Pipeline.forward itself insists on CUDA tensors
+        def __init__(self, pipe):
+            super().__init__()
+            self.pipe = pipe
+
+        def forward(self, imgs, proj, dmin, dmax):
+            return training.pipeline_train_forward(self.pipe, imgs, proj, dmin, dmax)
+
+    m = itermvs_b200.Pipeline(iteration=1, test=False)
+    m.load_state_dict(dtu_weights, strict=True)
+    s = make_sample(64, 64, n_src=2, batch=1, seed=3, scene="plane")
+    gt, mask = _ground_truth(64, 64, 1)
+    sample = dict(s, depth=gt, mask=mask)
+    ddp = FlatBucketDDP(OnSim(m))
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4)
+    w0 = {k: p.detach().clone() for k, p in m.named_parameters()}
+    l1, _ = train_step(ddp, opt, sample, itermvs_b200.full_loss)
+    assert torch.isfinite(l1) and float(ddp.gradient_bucket.abs().sum()) > 0
+    assert float(torch.sqrt((ddp.gradient_bucket.double() ** 2).sum())) <= 2.0 + 1e-4        # clip_grad_norm_(…, 2.0)
+    l2, _ = train_step(ddp, opt, sample, itermvs_b200.full_loss)
+    assert torch.isfinite(l2)
+    moved = [k for k, p in m.named_parameters() if not torch.equal(p.detach(), w0[k])]
+    assert "feature_net.conv1.conv.weight" in moved and "iter_mvs.update.gru.convq.weight" in moved
+    assert not any(k.startswith("feature_net.inner3") for k in moved)
