@@ -99,14 +99,24 @@ inline TapTables tconv_tables(int TH) {
     return tt;
 }
 
+// Under CUSIM (tests/cusim: the CPU emulation the test-suite builds, never the product) the PTX helpers of this
+// header have plain C++ bodies with the documented fragment layouts; nvcc never sees those branches.
 __device__ __forceinline__ uint32_t f2tf32(float x) {
+#ifdef CUSIM
+    return cusim::cvt_rna_tf32(x);
+#else
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
+#endif
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
+#ifdef CUSIM
+    cusim::mma_m16n8k8_tf32(c, a0, a1, a2, a3, b0, b1);
+    return;
+#endif
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -120,6 +130,10 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                         uint32_t b0, uint32_t b1) {
+#ifdef CUSIM
+    cusim::mma_m16n8k16_f16(c, a0, a1, a2, a3, b0, b1);
+    return;
+#endif
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -127,6 +141,10 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
 
 // m16n8k8 FP16: A = 2 regs (row g / g+8, k = 2t, 2t+1), B = 1 reg (k = 2t, 2t+1; n = g) -- 8-channel inputs
 __device__ __forceinline__ void mma_f16_k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+#ifdef CUSIM
+    cusim::mma_m16n8k8_f16(c, a0, a1, b0);
+    return;
+#endif
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(b0));
@@ -138,12 +156,22 @@ __device__ __forceinline__ void split_f16(float2 v, uint32_t& hi, uint32_t& lo) 
     hi = __float_as_uint(v.x); lo = __float_as_uint(v.y);
     return;
 #endif
+#ifdef CUSIM
+    hi = cusim::cvt_f16x2(v.y, v.x);
+    const float2 hs = cusim::unpack_f16x2(hi);
+    lo = cusim::cvt_f16x2(v.y - hs.y, v.x - hs.x);
+    return;
+#endif
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y - hf.y), "f"(v.x - hf.x));
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+#ifdef CUSIM
+    cusim::cp_async16(smem, gmem, valid);     // completes at once: a legal outcome of an asynchronous copy
+    return;
+#endif
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     const int bytes = valid ? 16 : 0;            // src-size 0 -> the 16 destination bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));

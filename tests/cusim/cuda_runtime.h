@@ -6,7 +6,7 @@
 // protocols, warp shuffles, persistent-block work queues) against the oracle without a GPU.
 //
 // This is test infrastructure: it lives under tests/, is built into tests/cusim/_build/ only by
-// tests/cusim/build.py, and nothing in the itermvs_b200 package ever loads it -- the product path has no CPU
+// tests/cusim/cusim_build.py, and nothing in the itermvs_b200 package ever loads it -- the product path has no CPU
 // fallback (itermvs_b200/_lib.py raises LibraryMissing).  It is slow (one ucontext fiber per CUDA thread) and
 // proves nothing about performance, memory-model races across warps, or alignment faults beyond the
 // explicit checks in __ldg.
@@ -50,6 +50,7 @@ struct int2 { int x, y; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 struct uint2 { unsigned x, y; };
 struct uint3 { unsigned x, y, z; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
 struct dim3 {
     unsigned x, y, z;
@@ -60,6 +61,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 // ---- the runtime (tests/cusim/cusim.cpp) -----------------------------------------------------------
@@ -73,6 +75,7 @@ void block_barrier();
 void warp_barrier();
 uint32_t shfl(uint32_t v, int src_lane);
 void* dyn_smem();
+uint32_t (*warp_xchg())[12];           // the current warp's [32][12]-word exchange area (tensor-core emulation)
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 [[noreturn]] void die(const char* what);
 }  // namespace cusim
@@ -185,6 +188,83 @@ static inline float cusim_expf(float a) { return expf(a); }
 static inline float __saturatef(float a) { return fminf(fmaxf(a, 0.f), 1.f); }
 using std::isnan;
 using std::isinf;
+
+// ---- tensor-core / async-copy emulation used by the CUSIM branches of csrc/mmaconv.cuh -----------------------------
+// Fragment layouts as in the PTX ISA (mma.sync.aligned.m16n8k8 / m16n8k16, .row.col): g = lane >> 2, t = lane & 3;
+// C/D: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+namespace cusim {
+static inline float tf32_value(uint32_t u) { u &= 0xffffe000u; float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t cvt_rna_tf32(float x) {          // round to nearest, ties away from zero, 10-bit mantissa
+    uint32_t u; std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return u;
+    return (u + 0x1000u) & 0xffffe000u;
+}
+static inline float half_bits_to_float(uint16_t h) { _Float16 v; std::memcpy(&v, &h, 2); return (float)v; }
+static inline uint16_t float_to_half_bits(float f) {     // cvt.rn.satfinite.f16.f32
+    f = f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f);
+    _Float16 v = (_Float16)f; uint16_t h; std::memcpy(&h, &v, 2); return h;
+}
+static inline uint32_t cvt_f16x2(float upper, float lower) { return ((uint32_t)float_to_half_bits(upper) << 16) | float_to_half_bits(lower); }
+static inline float2 unpack_f16x2(uint32_t u) { return float2{half_bits_to_float((uint16_t)(u & 0xffffu)), half_bits_to_float((uint16_t)(u >> 16))}; }
+static inline float half_of(uint32_t reg, int k) { return half_bits_to_float((uint16_t)((k & 1) ? (reg >> 16) : (reg & 0xffffu))); }
+
+// A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B: b0 (k = t, n = g) b1 (k = t+4, n = g)
+static inline void mma_m16n8k8_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    uint32_t (*x)[12] = warp_xchg();
+    const int lane = cur->lane, g = lane >> 2, t = lane & 3;
+    x[lane][0] = a0; x[lane][1] = a1; x[lane][2] = a2; x[lane][3] = a3; x[lane][4] = b0; x[lane][5] = b1;
+    warp_barrier();
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + (i >= 2 ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = c[i];
+        for (int k = 0; k < 8; ++k)
+            acc = fmaf(tf32_value(x[(row & 7) * 4 + (k & 3)][(row >= 8) + 2 * (k >= 4)]), tf32_value(x[col * 4 + (k & 3)][4 + (k >= 4)]), acc);
+        c[i] = acc;
+    }
+    warp_barrier();
+}
+// A: a0 (g; k = 2t, 2t+1) a1 (g+8; same) a2 (g; 2t+8, 2t+9) a3 (g+8; same);  B: b0 (k = 2t, 2t+1; n = g) b1 (k = 2t+8, 2t+9)
+// Every lane first unpacks its own fragments to floats: slot [lane][2 * reg + half].
+static inline void mma_m16n8k16_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    float (*x)[12] = reinterpret_cast<float (*)[12]>(warp_xchg());
+    const int lane = cur->lane, g = lane >> 2, t = lane & 3;
+    const uint32_t regs[6] = {a0, a1, a2, a3, b0, b1};
+    for (int r = 0; r < 6; ++r) { x[lane][2 * r] = half_of(regs[r], 0); x[lane][2 * r + 1] = half_of(regs[r], 1); }
+    warp_barrier();
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + (i >= 2 ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = c[i];
+        for (int k = 0; k < 16; ++k)
+            acc = fmaf(x[(row & 7) * 4 + ((k & 7) >> 1)][2 * ((row >= 8) + 2 * (k >= 8)) + (k & 1)],
+                       x[col * 4 + ((k & 7) >> 1)][2 * (4 + (k >= 8)) + (k & 1)], acc);
+        c[i] = acc;
+    }
+    warp_barrier();
+}
+// A: a0 (g; k = 2t, 2t+1) a1 (g+8; same);  B: b0 (k = 2t, 2t+1; n = g)
+static inline void mma_m16n8k8_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    float (*x)[12] = reinterpret_cast<float (*)[12]>(warp_xchg());
+    const int lane = cur->lane, g = lane >> 2, t = lane & 3;
+    x[lane][0] = half_of(a0, 0); x[lane][1] = half_of(a0, 1); x[lane][2] = half_of(a1, 0); x[lane][3] = half_of(a1, 1);
+    x[lane][8] = half_of(b0, 0); x[lane][9] = half_of(b0, 1);
+    warp_barrier();
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + (i >= 2 ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = c[i];
+        for (int k = 0; k < 8; ++k)
+            acc = fmaf(x[(row & 7) * 4 + (k >> 1)][2 * (row >= 8) + (k & 1)], x[col * 4 + (k >> 1)][8 + (k & 1)], acc);
+        c[i] = acc;
+    }
+    warp_barrier();
+}
+static inline void cp_async16(void* smem, const void* gmem, bool valid) {
+    if (reinterpret_cast<uintptr_t>(smem) % 16 != 0 || (valid && reinterpret_cast<uintptr_t>(gmem) % 16 != 0)) die("misaligned cp.async 16");
+    if (valid) std::memcpy(smem, gmem, 16); else std::memset(smem, 0, 16);
+}
+}  // namespace cusim
+static inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
+static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) {}
 
 // ---- host API stubs --------------------------------------------------------------------------------
 typedef int cudaError_t;

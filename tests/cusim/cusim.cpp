@@ -22,11 +22,14 @@ struct Fiber {
     Thread t;
     ucontext_t ctx;
     bool done = false;
+    const unsigned long long* wait_gen = nullptr;      // parked on a barrier: runnable again once *wait_gen != wait_val
+    unsigned long long wait_val = 0;
 };
 struct WarpState {
     unsigned long long gen = 0;
     int arrived = 0, live = 0;
     uint32_t slot[32];
+    uint32_t xchg[32][12];
 };
 struct BlockState {
     std::vector<Fiber> fibers;
@@ -44,6 +47,13 @@ std::vector<char> g_stacks;
 unsigned long long g_events = 0;       // barrier releases + thread exits: the scheduler's notion of progress
 
 void yield_() { swapcontext(&g_fiber->ctx, &g_main); }
+void park_until_changed(const unsigned long long& gen, unsigned long long seen) {
+    Fiber* f = g_fiber;
+    f->wait_gen = &gen;
+    f->wait_val = seen;
+    while (gen == seen) yield_();                  // the scheduler does not switch to a parked fiber before the release
+    f->wait_gen = nullptr;
+}
 
 void release_warp_if_complete(WarpState& w) {
     if (w.live > 0 && w.arrived == w.live) { w.arrived = 0; ++w.gen; ++g_events; }
@@ -74,13 +84,14 @@ void die(const char* what) {
 }
 
 void* dyn_smem() { return g_dyn_smem; }
+uint32_t (*warp_xchg())[12] { return g_blk->warps[cur->warp].xchg; }
 
 void warp_barrier() {
     WarpState& w = g_blk->warps[cur->warp];
     const unsigned long long g = w.gen;
     ++w.arrived;
     release_warp_if_complete(w);
-    while (w.gen == g) yield_();
+    if (w.gen == g) park_until_changed(w.gen, g);
 }
 
 void block_barrier() {
@@ -88,7 +99,7 @@ void block_barrier() {
     const unsigned long long g = b.gen;
     ++b.arrived;
     release_block_if_complete(b);
-    while (b.gen == g) yield_();
+    if (b.gen == g) park_until_changed(b.gen, g);
 }
 
 uint32_t shfl(uint32_t v, int src_lane) {
@@ -141,6 +152,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
                     for (int i = 0; i < nthreads; ++i) {
                         Fiber& f = blk.fibers[i];
                         if (f.done) continue;
+                        if (f.wait_gen && *f.wait_gen == f.wait_val) continue;      // still parked
                         g_fiber = &f;
                         cur = &f.t;
                         threadIdx = f.t.tid;

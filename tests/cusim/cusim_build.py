@@ -1,7 +1,7 @@
 """Build the CPU simulation of the non-tensor-core kernel sources (TEST INFRASTRUCTURE, never used by the
 product path -- see tests/cusim/cuda_runtime.h).
 
-    python tests/cusim/build.py          # -> tests/cusim/_build/libitermvs_sim.so
+    python tests/cusim/cusim_build.py          # -> tests/cusim/_build/libitermvs_sim.so
 
 The *.cu files are taken from itermvs_b200/csrc as they are; three textual rewrites make them host C++:
   * `extern __shared__ T name[];`  ->  `T* name = (T*)cusim::dyn_smem();`
@@ -11,6 +11,7 @@ The *.cu files are taken from itermvs_b200/csrc as they are; three textual rewri
 """
 from __future__ import annotations
 
+import concurrent.futures as cf
 import hashlib
 import os
 import re
@@ -22,12 +23,22 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "itermvs_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libitermvs_sim.so")
-SIM_SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "fusion.cu"]
-HEADERS = ["common.cuh", "sampling.cuh"]
-CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
+SIM_SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "fusion.cu", "evalnets.cu", "update.cu", "upsample.cu", "forward.cu",
+               "featurenet.cu"]
+HEADERS = ["common.cuh", "sampling.cuh", "mmaconv.cuh", "tc5conv.cuh"]
+def _isa_flags():
+    """F16C / FMA when this CPU has them (hardware half<->float conversion for the tensor-core emulation)."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return []
+    return [f for f, name in (("-mf16c", " f16c"), ("-mfma", " fma")) if name in flags]
+
+
+CXXFLAGS = ["-std=c++17", "-O2", *_isa_flags(), "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
             "-fno-strict-aliasing"]
 
-_DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\s*\[\s*\]\s*;")
+_DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?((?:unsigned\s+)?\w+)\s+(\w+)\s*\[\s*\]\s*;")
 _ASM = re.compile(r"\basm\s+volatile\s*\(|\basm\s*\(")
 
 
@@ -49,7 +60,7 @@ def build(force: bool = False) -> str:
     if gxx is None:
         raise RuntimeError("g++ not found")
     inputs = [os.path.join(CSRC, f) for f in SIM_SOURCES + HEADERS] + \
-             [os.path.join(HERE, f) for f in ("cuda_runtime.h", "cusim.cpp", "build.py")] + \
+             [os.path.join(HERE, f) for f in ("cuda_runtime.h", "cuda_fp16.h", "cusim.cpp", "cusim_build.py")] + \
              [os.path.join(ROOT, "include", "itermvs_b200.h")]
     stamp = os.path.join(OUT, "stamp")
     digest = _digest(inputs)
@@ -66,10 +77,19 @@ def build(force: bool = False) -> str:
         with open(os.path.join(gen, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as dst:
             dst.write(text)
     cpps = [os.path.join(gen, f.replace(".cu", ".cpp")) for f in SIM_SOURCES] + [os.path.join(HERE, "cusim.cpp")]
-    cmd = [gxx, *CXXFLAGS, "-I", HERE, "-shared", "-o", LIB + ".tmp", *cpps]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+
+    def compile_one(src):
+        obj = os.path.join(OUT, os.path.basename(src) + ".o")
+        r = subprocess.run([gxx, *CXXFLAGS, "-I", HERE, "-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"cusim build failed on {src}:\n" + r.stdout + r.stderr[-8000:])
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(cpps))) as ex:
+        objs = list(ex.map(compile_one, cpps))
+    r = subprocess.run([gxx, "-shared", "-o", LIB + ".tmp", *objs], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("cusim build failed:\n" + r.stdout + r.stderr[-8000:])
+        raise RuntimeError("cusim link failed:\n" + r.stdout + r.stderr[-8000:])
     os.replace(LIB + ".tmp", LIB)
     with open(stamp, "w") as f:
         f.write(digest)

@@ -15,6 +15,7 @@ checkpoint, runs reference functions / modules on seeded inputs and stores input
                       convex upsample, Update.forward, F.interpolate resamplers)
     e2e_d8.npz        config 1: 160x128, 2 src views, D=8 (patched as SURVEY 8c), 1 iteration
     e2e_d32.npz       320x256, 4 src views, D=32 (checkpoint-compatible), 2 iterations
+    e2e_tiny.npz      64x64, 1 src view, D=32, 2 iterations (`make_golden.py tiny`): the emulated end-to-end case of the CPU suite
                       both on the geometrically consistent plane scene, with every intermediate
                       of IterMVS.forward captured through hooks.
 
@@ -216,6 +217,10 @@ def run_e2e(name, width, height, n_src, num_sample, iteration, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["tiny"]:
+        # the end-to-end case of the CPU suite (kernel sources executed through tests/cusim): small enough to emulate
+        run_e2e("e2e_tiny.npz", 64, 64, n_src=1, num_sample=32, iteration=2, seed=2)
+        sys.exit(0)
     dump_weights()
     model, _ = load_reference_model(iteration=1)
     stage_kats(model)

@@ -19,7 +19,7 @@ from oracle import itermvs_oracle as O
 from itermvs_b200.synthetic import make_sample, random_feature_pyramids
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cusim"))
-import build as cusim_build  # noqa: E402
+import cusim_build  # noqa: E402
 
 vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cusim"))
-import build as cusim_build  # noqa: E402
+import cusim_build  # noqa: E402
 
 from itermvs_b200.synthetic import make_sample, plane_depth_map  # noqa: E402
 
