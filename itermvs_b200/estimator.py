@@ -432,12 +432,12 @@ class IterMVS(nn.Module):
     def _forward_all_predictions(self, ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max):
         """The test=False structure of itermvs.py:253-329 -- every intermediate prediction (initial depth, one
         depth / probability / confidence logit per update) -- as a FORWARD pass on the CUDA operators.  This is what
-        train.py's validation loop (train.py:257, model.eval() under no_grad) and full_loss consume.  Gradients are
-        not provided: the backward kernels are not built ('next')."""
+        train.py's validation loop (train.py:257, model.eval() under no_grad) and full_loss consume.  The inference
+        kernels carry no gradient; the differentiable path is the train() mode (itermvs_b200/training.py)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "itermvs_b200.IterMVS(test=False): forward-only (validation) -- the backward kernels are not built; "
-                "call it under torch.no_grad() as train.py's validate_sample does, or freeze the parameters")
+                "itermvs_b200.IterMVS(test=False).eval(): forward-only (validation) on the inference kernels -- call it "
+                "under torch.no_grad() as train.py's validate_sample does, or switch to .train() for the differentiable path")
         depths = {"combine": [], "probability": [], "initial": []}
         confidences, depths_upsampled, confidence_upsampled = [], [], None
         ref2 = ops._chk(ref_feature["level2"], "ref_feature")
@@ -474,6 +474,13 @@ class IterMVS(nn.Module):
         return depths, depths_upsampled, confidences, confidence_upsampled
 
     def forward(self, ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max):
+        if not self.test and self.training:
+            # itermvs.py:253-329 as train.py drives it: fused plane sweep with CUDA backward + torch autograd (training.py)
+            from . import training
+            levels = ("level1", "level2", "level3")
+            feas = [torch.stack([ref_feature[k], *src_features[k]], dim=1).permute(0, 1, 3, 4, 2).contiguous() for k in levels]
+            projs = [_stack_proj(ref_proj[k], src_projs[k]).to(feas[0].device) for k in levels]
+            return training.itermvs_train_forward(self, feas[0], feas[1], feas[2], projs, depth_min.float(), depth_max.float())
         if not self.test:
             return self._forward_all_predictions(ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max)
         dev = ref_feature["level2"].device

@@ -183,9 +183,16 @@ def test_full_loss_matches_reference_value(loss_kat):
 
 
 def test_all_predictions_forward_refuses_autograd(dtu_weights):
-    """test=False is forward-only: with trainable parameters and grad enabled it must refuse, not silently detach."""
+    """test=False in eval() mode is forward-only (the inference kernels): with trainable parameters and grad enabled
+    it must refuse, not silently detach.  train() mode is the differentiable path and, like every entry, insists on
+    CUDA tensors."""
     import itermvs_b200
-    m = itermvs_b200.IterMVS(2, 32, 32, test=False)
+    m = itermvs_b200.IterMVS(2, 32, 32, test=False).eval()
     x = {f"level{l}": torch.zeros(1, c, 8, 8) for l, c in ((1, 16), (2, 32), (3, 48))}
     with pytest.raises(NotImplementedError):
         m(x, {k: [] for k in x}, {}, {}, torch.ones(1), torch.ones(1))
+    m.train()
+    srcs = {k: [v.clone()] for k, v in x.items()}
+    proj = {k: torch.eye(4)[None] for k in x}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(x, srcs, proj, {k: [v] for k, v in proj.items()}, torch.ones(1), torch.ones(1))
