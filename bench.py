@@ -166,6 +166,93 @@ def run_reference(args, rank):
     }))
 
 
+def run_train(args, rank, world, local):
+    """BASELINE configs[3]: data-parallel training on synthetic DTU-shape samples, one process per GPU, one reference view
+    per GPU and step.  A step is train.py:194-215 -- zero_grad, Pipeline.train() forward (fused plane sweep + cuDNN
+    convolution stacks), full_loss, backward (CUDA backward of the plane sweep), ONE all-reduce of the flat 1.37 MB
+    gradient bucket over NCCL, clip_grad_norm_(2.0), Adam.  Prints one JSON line (rank 0); the per-phase split comes
+    from CUDA events on the training stream."""
+    import torch.distributed as dist
+    import itermvs_b200
+    from itermvs_b200.ddp import FlatBucketDDP
+    from itermvs_b200.synthetic import make_sample, plane_depth_map
+    import torch.nn.functional as F
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the CUDA path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    model = itermvs_b200.Pipeline(iteration=ITERS, test=False)
+    model.load_state_dict(load_weights(), strict=True)
+    model = model.to(dev).train()
+    ddp = FlatBucketDDP(model, grad_dtype=torch.bfloat16 if args.train_bf16_wire else None)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-5, betas=(0.9, 0.999))
+    s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=rank, scene="plane")
+    d0 = torch.from_numpy(plane_depth_map(W_IMG, H_IMG).astype("float32"))[None, None]
+    gt = {"level_0": d0.to(dev), "level_2": F.interpolate(d0, scale_factor=0.25, mode="nearest").to(dev)}
+    mask = {k: torch.ones_like(v) for k, v in gt.items()}
+    imgs = {k: v.to(dev) for k, v in s["imgs"].items()}
+    proj = {k: v.to(dev) for k, v in s["proj_matrices"].items()}
+    dmin, dmax = s["depth_min"].to(dev), s["depth_max"].to(dev)
+    marks = []
+
+    def step(timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed else None
+        ddp.zero_grad()
+        if timed: ev[0].record()
+        out = ddp(imgs, proj, dmin, dmax)
+        loss = itermvs_b200.full_loss(out["depths"], out["depths_upsampled"], out["confidences"], gt, mask, dmin, dmax)
+        if timed: ev[1].record()
+        loss.backward()
+        if timed: ev[2].record()
+        ddp.reduce_gradients()
+        if timed: ev[3].record()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 2.0)
+        opt.step()
+        if timed:
+            ev[4].record()
+            marks.append(ev)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(True)
+    e1.record()
+    barrier()
+    clock_info = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    phases = [sum(ev[i].elapsed_time(ev[i + 1]) for ev in marks) / len(marks) for i in range(4)]
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training reference-views/sec at 640x512, 4 src, D=32, 4 iters (forward + full_loss + backward + gradient all-reduce + Adam)",
+            "value": world * args.steps / (ms / 1000.0), "unit": "refs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (gradients on the wire: %s)" % ("bf16" if args.train_bf16_wire else "f32"), "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: train step, 640x512, 4 src views, D=32, 4 iters, 1 reference view per GPU",
+                       "parallelism": f"data parallel x{world}: one flat {ddp.gradient_bucket.numel() * 4} byte gradient bucket, one all-reduce per step",
+                       "convolutions": "ATen/cuDNN under torch autograd", "plane_sweep": "fused sm_100a kernels, forward and backward"},
+            "phase_ms": {"forward+loss": phases[0], "backward": phases[1], "allreduce": phases[2], "clip+adam": phases[3]},
+            "loss": float(loss.item()), "clocks": clock_info}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +267,10 @@ def main():
     ap.add_argument("--passes", type=int, default=4, choices=[1, 3, 4],
                     help="tensor-core conv precision: 4 = 3-product FP16 split (fp32-grade, default), 3 = 3xTF32 split (fp32-grade), 1 = single-pass TF32")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage timing table to stderr")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default) = the headline metric; train = BASELINE configs[3]: training steps with the "
+                         "flat-bucket gradient all-reduce (not a driver line; see run_train)")
+    ap.add_argument("--train-bf16-wire", action="store_true", help="train mode: all-reduce the gradient bucket in bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -188,6 +279,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.mode == "train":
+        run_train(args, rank, world, local)
         return
 
     import torch.distributed as dist
