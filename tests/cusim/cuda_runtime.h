@@ -36,7 +36,6 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static               // block-static storage; `extern __shared__` is rewritten by build.py
@@ -78,6 +77,10 @@ void* dyn_smem();
 uint32_t (*warp_xchg())[12];           // the current warp's [32][12]-word exchange area (tensor-core emulation)
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 [[noreturn]] void die(const char* what);
+// optional access-pattern tracer (CUSIM_TRACE=<json path>): groups the __ldg calls of a warp into warp-level requests
+// and counts requests / 32-byte sectors / 128-byte lines per launch -- tools/wavefront_model.py
+extern bool g_trace;
+void trace_load(const void* p, int bytes, const void* site);
 }  // namespace cusim
 
 // the built-in variables: plain globals, rewritten by the scheduler at every fiber switch
@@ -136,9 +139,10 @@ static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mas
 
 // ---- memory access ---------------------------------------------------------------------------------
 template <class T>
-static inline T __ldg(const T* p) {
+static __attribute__((noinline)) T __ldg(const T* p) {       // noinline: the return address identifies the static load site
     if (reinterpret_cast<uintptr_t>(p) % alignof(T) != 0 || reinterpret_cast<uintptr_t>(p) % sizeof(T) != 0)
         cusim::die("misaligned __ldg");
+    if (cusim::g_trace) cusim::trace_load(p, (int)sizeof(T), __builtin_extract_return_addr(__builtin_return_address(0)));
     return *p;
 }
 // fibers never pre-empt each other between sync points: plain read-modify-write is atomic here

@@ -4,6 +4,9 @@
 
 #include <ucontext.h>
 
+#include <algorithm>
+#include <map>
+#include <string>
 #include <vector>
 
 uint3 threadIdx;
@@ -77,6 +80,70 @@ void trampoline() {
 
 }  // namespace
 
+// ---- access-pattern tracer ---------------------------------------------------------------------------------------
+bool g_trace = false;
+namespace {
+struct LoadRec { uint64_t site; uint32_t k; uint16_t warp; uint16_t bytes; uint64_t addr; };
+struct SiteStats { uint64_t requests = 0, lanes = 0, bytes = 0, sectors = 0, lines = 0, wavefronts = 0; };
+std::vector<LoadRec> g_recs;                                   // of the block being executed
+std::vector<std::map<uint64_t, uint32_t>> g_site_count;        // per thread: executions of each load site so far
+std::map<uint64_t, SiteStats> g_sites;                         // per launch
+std::string g_trace_path;
+int g_launch_index = 0;
+
+void trace_flush_block() {
+    std::sort(g_recs.begin(), g_recs.end(), [](const LoadRec& a, const LoadRec& b) {
+        return a.warp != b.warp ? a.warp < b.warp : (a.site != b.site ? a.site < b.site : a.k < b.k);
+    });
+    size_t i = 0;
+    std::vector<uint64_t> sectors, lines;
+    while (i < g_recs.size()) {
+        size_t j = i;
+        sectors.clear(); lines.clear();
+        uint64_t bytes = 0;
+        while (j < g_recs.size() && g_recs[j].warp == g_recs[i].warp && g_recs[j].site == g_recs[i].site && g_recs[j].k == g_recs[i].k) {
+            for (uint64_t a = g_recs[j].addr >> 5; a <= (g_recs[j].addr + g_recs[j].bytes - 1) >> 5; ++a) sectors.push_back(a);
+            bytes += g_recs[j].bytes;
+            ++j;
+        }
+        std::sort(sectors.begin(), sectors.end());
+        sectors.erase(std::unique(sectors.begin(), sectors.end()), sectors.end());
+        for (uint64_t s : sectors) lines.push_back(s >> 2);
+        lines.erase(std::unique(lines.begin(), lines.end()), lines.end());
+        SiteStats& st = g_sites[g_recs[i].site];
+        st.requests += 1; st.lanes += j - i; st.bytes += bytes; st.sectors += sectors.size(); st.lines += lines.size();
+        // data-stage model: a wavefront returns at most 128 bytes of register data and touches one 128-byte line
+        st.wavefronts += std::max<uint64_t>(lines.size(), (bytes + 127) / 128);
+        i = j;
+    }
+    g_recs.clear();
+}
+
+void trace_end_launch(dim3 grid, dim3 block) {
+    FILE* f = fopen(g_trace_path.c_str(), "a");
+    if (!f) return;
+    fprintf(f, "{\"launch\": %d, \"grid\": [%u, %u, %u], \"block\": [%u, %u, %u], \"sites\": [", g_launch_index++, grid.x, grid.y, grid.z,
+            block.x, block.y, block.z);
+    bool first = true;
+    for (auto& kv : g_sites) {
+        const SiteStats& s = kv.second;
+        fprintf(f, "%s{\"site\": \"%llx\", \"requests\": %llu, \"lanes\": %llu, \"bytes\": %llu, \"sectors\": %llu, \"lines\": %llu, \"wavefronts\": %llu}",
+                first ? "" : ", ", (unsigned long long)kv.first, (unsigned long long)s.requests, (unsigned long long)s.lanes,
+                (unsigned long long)s.bytes, (unsigned long long)s.sectors, (unsigned long long)s.lines, (unsigned long long)s.wavefronts);
+        first = false;
+    }
+    fprintf(f, "]}\n");
+    fclose(f);
+    g_sites.clear();
+}
+}  // namespace
+
+void trace_load(const void* p, int bytes, const void* site) {
+    const int tid = (int)(g_fiber - g_blk->fibers.data());
+    const uint32_t k = g_site_count[tid][(uint64_t)site]++;
+    g_recs.push_back(LoadRec{(uint64_t)site, k, (uint16_t)cur->warp, (uint16_t)bytes, (uint64_t)p});
+}
+
 void die(const char* what) {
     fprintf(stderr, "cusim: %s (block %u,%u,%u thread %u,%u,%u)\n", what, blockIdx.x, blockIdx.y, blockIdx.z,
             cur ? cur->tid.x : 0, cur ? cur->tid.y : 0, cur ? cur->tid.z : 0);
@@ -117,6 +184,9 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     if (smem > DYN_SMEM_BYTES) die("dynamic shared memory request exceeds 228 KB");
     if (g_blk) die("nested launch");
     const int nwarps = (nthreads + 31) / 32;
+    const char* tr = getenv("CUSIM_TRACE");
+    g_trace = tr && *tr;
+    if (g_trace) g_trace_path = tr;
     g_stacks.resize((size_t)nthreads * STACK_BYTES);
     BlockState blk;
     g_blk = &blk;
@@ -132,6 +202,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
                 blk.fibers.assign(nthreads, Fiber());
                 blk.warps.assign(nwarps, WarpState());
                 blk.gen = 0; blk.arrived = 0; blk.live = nthreads;
+                if (g_trace) g_site_count.assign(nthreads, {});
                 for (int i = 0; i < nthreads; ++i) {
                     Fiber& f = blk.fibers[i];
                     f.t.tid.x = i % block.x;
@@ -162,7 +233,9 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
                     // every live fiber is parked on a barrier that cannot complete (divergent barrier, lost lane)
                     if (remaining > 0 && g_events == before) die("deadlock: no fiber makes progress");
                 }
+                if (g_trace) trace_flush_block();
             }
+    if (g_trace) trace_end_launch(grid, block);
     cur = nullptr;
     g_fiber = nullptr;
     g_blk = nullptr;
