@@ -75,13 +75,15 @@ class FlatBucketDDP(nn.Module):
         (train.py:153-157) -- interchangeable with them."""
         return super().state_dict(*args, **kwargs)
 
+    def _views_intact(self) -> bool:
+        lo = self._bucket.data_ptr()
+        hi = lo + self._bucket.numel() * self._bucket.element_size()
+        return all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self._params)
+
     def zero_grad(self, set_to_none: bool = False) -> None:      # noqa: ARG002  (the views must survive)
         self._bucket.zero_()
-        for p in self._params:
-            if p.grad is None or p.grad.data_ptr() < self._bucket.data_ptr() or \
-                    p.grad.data_ptr() >= self._bucket.data_ptr() + self._bucket.numel() * self._bucket.element_size():
-                self._attach()                                     # someone replaced a .grad (optimizer.zero_grad())
-                break
+        if not self._views_intact():          # someone replaced a .grad (e.g. optimizer.zero_grad(set_to_none=True))
+            self._attach()
 
     @property
     def gradient_bucket(self) -> torch.Tensor:

@@ -324,3 +324,40 @@ def test_warpcorr_iter_backward_source_on_cpu(sim, batch, n_src, explicit):
         assert maxerr(gref, want_ref) < 2e-4 * max(1.0, float(want_ref.abs().max())), l
         for got, t in zip(gsrcs, sg[f"level{l}"]):
             assert maxerr(got, t.grad) < 2e-4 * max(1.0, float(t.grad.abs().max())), l
+
+
+def test_kernels_stay_inside_their_buffers():
+    """Memcheck without a GPU: the plane-sweep / warping kernels, forward and backward, on buffers that end (and, in a
+    second pass, start) flush against an inaccessible page (tests/cusim/guarded.py).  An out-of-bounds read or write by
+    one element would end the child with SIGSEGV."""
+    import subprocess
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cusim", "memcheck_run.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MEMCHECK-OK" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+
+
+def test_load_tracer_counts(sim, tmp_path, monkeypatch):
+    """The access-pattern tracer behind tools/wavefront_model.py: warp-level grouping of the __ldg calls.  For
+    aggregate_init (one float + one float4 per thread and view, fully coalesced) the counts are known in closed form."""
+    import json
+    trace = tmp_path / "trace.jsonl"
+    b, s_, d, p3 = 1, 3, 4, 256
+    def aligned128(t):                                            # line counts depend on the 128-byte phase of the base
+        buf = torch.empty(t.numel() + 32)
+        off = ((-buf.data_ptr()) % 128) // 4
+        out = buf[off:off + t.numel()].view(t.shape)
+        out.copy_(t)
+        return out
+    corr, vw3, agg = aligned128(torch.rand(b, s_, d, p3, 8)), aligned128(torch.rand(b, s_, p3)), torch.empty(b, d, p3, 8)
+    monkeypatch.setenv("CUSIM_TRACE", str(trace))
+    ok(sim, sim.imvs_aggregate_init(P(corr), P(vw3), P(agg), b, s_, d, p3, None))
+    monkeypatch.setenv("CUSIM_TRACE", "")
+    rec = json.loads(trace.read_text().splitlines()[-1])
+    tot = {k: sum(site[k] for site in rec["sites"]) for k in ("requests", "lanes", "bytes", "sectors", "lines", "wavefronts")}
+    threads = b * d * p3 * 2
+    assert tot["lanes"] == threads * s_ * 2                         # per thread and view: one weight, one float4 of corr
+    assert tot["requests"] == threads // 32 * s_ * 2
+    assert tot["bytes"] == threads * s_ * (4 + 16)
+    # a warp's 32 float4 are 512 contiguous bytes = 16 sectors / 4 lines; its 32 weights (16 pixels x 2 halves) 64 bytes
+    assert tot["sectors"] == threads // 32 * s_ * (16 + 2) and tot["lines"] == threads // 32 * s_ * (4 + 1)
+    assert tot["wavefronts"] == tot["lines"]
