@@ -79,5 +79,48 @@ def main():
     print("MEMCHECK-OK")
 
 
+
+
+def whole_forward():
+    """imvs_featurenet_forward + imvs_itermvs_forward (every inference kernel incl. the tensor-core engine) with all
+    inputs, outputs, weights-independent scratch and workspaces on guard-page buffers (trailing guard)."""
+    import numpy as np
+    import itermvs_b200
+    from itermvs_b200 import ops
+    lib = C.CDLL(cusim_build.build())
+    for name, (res, args) in _lib._SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib._lib = lib
+    ops._chk = lambda t, name: t.contiguous()
+    ops._stream = lambda: None
+    golden = os.path.join(os.path.dirname(HERE), "golden", "dtu_weights.npz")
+    with np.load(golden) as z:
+        weights = {k: torch.from_numpy(z[k]) for k in z.files}
+    w = h = 32
+    n_src, iters = 2, 1
+    m = itermvs_b200.Pipeline(iteration=iters, test=True)
+    m.load_state_dict(weights, strict=True)
+    m.eval()
+    s = make_sample(w, h, n_src=n_src, batch=1, seed=4, scene="plane")
+    x = guarded(s["imgs"]["level_0"].float().contiguous())
+    n = n_src + 1
+
+    def gbytes(nbytes):
+        return guarded(torch.zeros((nbytes + 255) // 256 * 256, dtype=torch.uint8))[:nbytes]
+    m.feature_net._ws[0] = ((n, h, w, "cpu"), gbytes(lib.imvs_featurenet_workspace_bytes(n, h, w)))
+    pb = _lib.Problem(1, n, h, w, 32, iters)
+    m.iter_mvs._workspaces[0] = ((1, n, h, w, 32, iters, "cpu"), gbytes(lib.imvs_forward_workspace_bytes(C.byref(pb))))
+    with torch.no_grad():
+        f1, f2, f3 = m.feature_net.forward_nhwc(x)
+        f1, f2, f3 = guarded(f1), guarded(f2), guarded(f3)
+        projs = [guarded(s["proj_matrices"][f"level_{l}"].float().contiguous()) for l in (1, 2, 3)]
+        dmin, dmax = guarded(s["depth_min"].float().repeat(4)), guarded(s["depth_max"].float().repeat(4))
+        out = tuple(guarded(torch.zeros(1, 1, hh, ww)) for hh, ww in ((h // 4, w // 4), (h, w), (h // 4, w // 4), (h, w)))
+        m.iter_mvs.forward_packed(f1, f2, f3, projs[0], projs[1], projs[2], dmin, dmax, out=out)
+    assert all(torch.isfinite(t).all() for t in out)
+    print("MEMCHECK-FORWARD-OK")
+
+
 if __name__ == "__main__":
-    main()
+    whole_forward() if "--forward" in sys.argv else main()

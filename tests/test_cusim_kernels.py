@@ -334,6 +334,10 @@ def test_kernels_stay_inside_their_buffers():
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cusim", "memcheck_run.py")
     r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MEMCHECK-OK" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+    # every inference kernel (FeatureNet + estimator, tensor-core engine included) at 32x32 with images, pyramids,
+    # projections, outputs and both workspaces on guarded buffers
+    r = subprocess.run([sys.executable, script, "--forward"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MEMCHECK-FORWARD-OK" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
 
 
 def test_load_tracer_counts(sim, tmp_path, monkeypatch):
