@@ -145,7 +145,7 @@ def featurenet_pyramids(fnet, imgs: Tensor):
     out1 = fnet.output1(intra)
 
     def cl(t):
-        return t.view(b, v, t.shape[1], t.shape[2], t.shape[3]).permute(0, 1, 3, 4, 2).contiguous()
+        return t.reshape(b, v, t.shape[1], t.shape[2], t.shape[3]).permute(0, 1, 3, 4, 2).contiguous()
     return cl(out1), cl(out2), cl(out3)
 
 
@@ -158,7 +158,7 @@ def _slices(vol: Tensor) -> Tensor:
 def pixel_view_weight(m, corr: Tensor) -> Tensor:
     """itermvs.py:341-350.  corr [B,G,N,H,W] -> [B,1,H,W]."""
     b, _, n, h, w = corr.shape
-    x = m.conv[1](F.relu(m.conv[0].conv(_slices(corr)))).view(b, n, h, w)
+    x = m.conv[1](F.relu(m.conv[0].conv(_slices(corr)))).reshape(b, n, h, w)     # reshape: cuDNN may answer channels-last
     return torch.softmax(x, dim=1).max(dim=1)[0].unsqueeze(1)
 
 
@@ -170,7 +170,7 @@ def corr_net(m, corr: Tensor) -> Tensor:
     x = F.relu(m.conv2.conv(c1))
     x = c1 + m.conv3(x)
     x = c0 + m.conv4(x)
-    return m.conv5(x).view(b, n, h, w)
+    return m.conv5(x).reshape(b, n, h, w)
 
 
 def conv_gru(m, h: Tensor, x: Tensor) -> Tensor:
@@ -225,9 +225,9 @@ def itermvs_train_forward(net, fea1: Tensor, fea2: Tensor, fea3: Tensor, projs: 
     rts = [_compose(p) for p in projs]
 
     ref2 = fea2[:, 0].permute(0, 3, 1, 2)                                   # NCHW view of the reference feature
-    up_w = torch.softmax(net.upsample(ref2).view(b, 1, 9, 4, 4, h2, w2), dim=2)        # itermvs.py:262-264
-    inv_min = (1.0 / depth_min).view(b, 1, 1, 1)
-    inv_max = (1.0 / depth_max).view(b, 1, 1, 1)
+    up_w = torch.softmax(net.upsample(ref2).reshape(b, 1, 9, 4, 4, h2, w2), dim=2)        # itermvs.py:262-264
+    inv_min = (1.0 / depth_min).reshape(b, 1, 1, 1)
+    inv_max = (1.0 / depth_max).reshape(b, 1, 1, 1)
 
     # ---- initialisation (itermvs.py:270-283; Evaluation's view_weights == None branch, 36-82)
     d = net.num_sample
