@@ -5,9 +5,9 @@ the reference (DepthInitialization, Evaluation, Update, IterMVS, PixelViewWeight
 ConvGRU), so `Pipeline`, `train.py` / `eval.py` and the shipped checkpoints stay drop-in -- but
 every forward runs the sm_100a kernels through the C ABI (no cuDNN / ATen call chains, no CPU path).
 
-The nn.Conv2d / nn.ConvTranspose2d members are parameter holders only (names + shapes +
-initialisation identical to the reference); their own forward is never called on the inference
-path.  Parameters are re-packed to the kernel layout lazily whenever their version counters change.
+The nn.Conv2d / nn.ConvTranspose2d members hold the parameters (names + shapes + initialisation identical
+to the reference); their own forward is never called on the inference path.  In train() mode with autograd on, every
+module here runs its differentiable implementation instead (itermvs_b200/training.py).  Parameters are re-packed to the kernel layout lazily whenever their version counters change.
 The single-operator modules accept and return the reference's NCHW tensors (converted at the
 boundary); `IterMVS.forward_packed` is the zero-copy channels-last path `Pipeline` uses.
 """
@@ -53,6 +53,13 @@ def _nhwc(x: Tensor) -> Tensor:
 
 def _nchw(x: Tensor) -> Tensor:
     return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _differentiable(mod: nn.Module) -> bool:
+    """train() mode with autograd on: the module runs its differentiable implementation (itermvs_b200/training.py) --
+    torch autograd over the parameter-holding convolutions, the fused plane sweep with its CUDA backward; eval() or
+    no_grad: the inference kernels."""
+    return mod.training and torch.is_grad_enabled()
 
 
 class _ConvHolder(nn.Module):
@@ -116,6 +123,9 @@ class PixelViewWeight(nn.Module):
         return _cached_pack(self, device, build)
 
     def forward(self, x: Tensor) -> Tensor:
+        if _differentiable(self):
+            from . import training
+            return training.pixel_view_weight(self, ops._chk(x, "x"))
         b, g, n, h, w = x.shape
         vol = ops._chk(x, "x").permute(0, 2, 3, 4, 1).contiguous()          # [B,N,H,W,8] == [B][S=1][D][P][8]
         logits = torch.empty(b, n, h * w, device=x.device)
@@ -149,6 +159,9 @@ class CorrNet(nn.Module):
         return _cached_pack(self, device, build)
 
     def forward(self, x: Tensor) -> Tensor:
+        if _differentiable(self):
+            from . import training
+            return training.corr_net(self, ops._chk(x, "x"))
         b, g, n, h, w = x.shape
         vol = ops._chk(x, "x").permute(0, 2, 3, 4, 1).contiguous()          # [B*N][P][8]
         out = torch.empty(b * n, h, w, device=x.device)
@@ -188,6 +201,9 @@ class ConvGRU(nn.Module):
         return h
 
     def forward(self, h: Tensor, x: Tensor) -> Tensor:
+        if _differentiable(self):
+            from . import training
+            return training.conv_gru(self, ops._chk(h, "h"), ops._chk(x, "x"))
         hn = _nhwc(ops._chk(h, "h"))
         x = ops._chk(x, "x")
         b, c, hh, ww = x.shape
@@ -216,6 +232,10 @@ class Evaluation(nn.Module):
 
     def forward(self, ref_feature, src_features, ref_proj, src_projs, depth_sample, inverse_depth_min=None,
                 inverse_depth_max=None, view_weights=None):
+        if _differentiable(self):
+            from . import training
+            return training.evaluation_forward(self, ref_feature, src_features, ref_proj, src_projs, depth_sample,
+                                               inverse_depth_min, inverse_depth_max, view_weights)
         L = _lib.lib()
         st = ops._stream()
         if view_weights is None:
@@ -314,6 +334,9 @@ class Update(nn.Module):
         return self.training if self.return_probability is None else self.return_probability
 
     def hidden_init(self, corr: Tensor) -> Tensor:
+        if _differentiable(self):
+            from . import training
+            return training.update_hidden_init(self, ops._chk(corr, "corr"))
         corr = _nhwc(ops._chk(corr, "corr"))
         b, h3, w3, d = corr.shape
         hidden = torch.empty(b, 2 * h3, 2 * w3, self.hidden_dim, device=corr.device)
@@ -336,14 +359,23 @@ class Update(nn.Module):
         return nd, prob, conf, conf0
 
     def conf_init(self, hidden):
+        if _differentiable(self):
+            conf0 = self.confidence_head(ops._chk(hidden, "hidden"))
+            return torch.sigmoid(conf0), conf0
         _, _, conf, conf0 = self._heads_nhwc(_nhwc(ops._chk(hidden, "hidden")), True)
         return conf, conf0
 
     def depth_init(self, hidden):
+        if _differentiable(self):
+            from . import training
+            return training.update_depth(self, ops._chk(hidden, "hidden"))
         nd, prob, _, _ = self._heads_nhwc(_nhwc(ops._chk(hidden, "hidden")), False)
         return nd, prob
 
     def forward(self, hidden, normalized_depth, corr, confidence=None, confidence_flag=False):
+        if _differentiable(self):
+            from . import training
+            return training.update_forward(self, ops._chk(hidden, "hidden"), normalized_depth, corr, confidence_flag)
         x = torch.cat([normalized_depth, corr], dim=1)
         b, c, hh, ww = x.shape
         x16 = torch.zeros(b, hh, ww, XCH, device=x.device)

@@ -207,6 +207,74 @@ def _to_planar(vol: Tensor, h: int, w: int) -> Tensor:
     return vol.reshape(*lead, n, h, w, 8).permute(*range(k), k + 3, k, k + 1, k + 2)
 
 
+# ---- Evaluation (itermvs.py:33-126) on channels-last pyramids --------------------------------------------------
+def evaluation_init(ev, fea3: Tensor, rt3: Tensor, depth_sample: Tensor, inv_min: Tensor, inv_max: Tensor):
+    """The `view_weights == None` branch (itermvs.py:36-82): per-view correlation on the fused kernel, PixelViewWeight,
+    aggregation (training form: no in-place adds), CorrNet, the soft-argmax initial depth.
+    Returns (view_weights [B,S,H2,W2] -- NOT detached, as in the reference --, corr [B,D,H3,W3], depth [B,1,H2,W2])."""
+    b, v, h3, w3, _ = fea3.shape
+    d = depth_sample.shape[1]
+    corr_views = _to_planar(FusedCorrInit.apply(fea3, rt3, depth_sample), h3, w3)      # [B,S,8,D,H3,W3]
+    corr_sum, vw_sum, view_weights = 0, 1e-5, []
+    for i in range(v - 1):
+        c = corr_views[:, i]
+        vw_i = pixel_view_weight(ev.pixel_view_weight, c)                              # [B,1,H3,W3]
+        view_weights.append(F.interpolate(vw_i, scale_factor=2, mode="bilinear"))
+        corr_sum = corr_sum + c * vw_i.unsqueeze(1)
+        vw_sum = vw_sum + vw_i.unsqueeze(1)
+    corr = corr_net(ev.corr_conv1[2], corr_sum / vw_sum)                                # [B,D,H3,W3]
+    prob0 = torch.softmax(corr, dim=1)
+    index = torch.arange(0, d, 1, device=corr.device, dtype=torch.float32).view(1, d, 1, 1)
+    nd0 = torch.sum(index * prob0, dim=1, keepdim=True) / (d - 1.0)
+    depth0 = F.interpolate(ops.depth_unnormalization(nd0, inv_min, inv_max), scale_factor=2, mode="bilinear")
+    return torch.cat(view_weights, dim=1), corr, depth0
+
+
+def evaluation_iter(ev, fea1: Tensor, fea2: Tensor, fea3: Tensor, rts: Sequence[Tensor], samples: Sequence[Tensor],
+                    view_weights: Tensor) -> Tensor:
+    """The iteration branch (itermvs.py:84-126): fused warp + correlation + view-weighted aggregation of the three
+    levels, one CorrNet per level.  `view_weights` is used as a constant (the caller passes .detach(), itermvs.py:295).
+    Returns corr [B,10,H2,W2]."""
+    _, _, h2, w2, _ = fea2.shape
+    agg = _to_planar(FusedCorrIter.apply(fea1, fea2, fea3, rts[0], rts[1], rts[2], samples[0].contiguous(), samples[1].contiguous(),
+                                         samples[2].contiguous(), view_weights.detach().contiguous()), h2, w2)     # [B,8,10,H2,W2]
+    return torch.cat([corr_net(ev.corr_conv1[0], agg[:, :, 0:4]), corr_net(ev.corr_conv1[1], agg[:, :, 4:8]),
+                      corr_net(ev.corr_conv1[2], agg[:, :, 8:10])], dim=1)
+
+
+def evaluation_forward(ev, ref_feature, src_features, ref_proj, src_projs, depth_sample, inverse_depth_min=None,
+                       inverse_depth_max=None, view_weights=None):
+    """Evaluation.forward with the reference's own arguments (dicts of NCHW maps, itermvs.py:33), differentiable."""
+    def stack(level):
+        maps = [ref_feature[level], *src_features[level]]
+        fea = torch.stack(maps, dim=1).permute(0, 1, 3, 4, 2).contiguous()
+        proj = torch.stack([ref_proj[level], *src_projs[level]], dim=1).float().to(fea.device)
+        return fea, _compose(proj)
+    if view_weights is None:
+        fea3, rt3 = stack("level3")
+        return evaluation_init(ev, fea3, rt3, depth_sample, inverse_depth_min, inverse_depth_max)
+    (f1, r1), (f2, r2), (f3, r3) = stack("level1"), stack("level2"), stack("level3")
+    return evaluation_iter(ev, f1, f2, f3, (r1, r2, r3), [depth_sample[f"level{l}"] for l in (1, 2, 3)], view_weights)
+
+
+# ---- Update (itermvs.py:159-220) ---------------------------------------------------------------------------------
+def update_hidden_init(upd, corr: Tensor) -> Tensor:
+    return torch.tanh(F.interpolate(upd.hidden_init_head(corr), scale_factor=2, mode="bilinear"))
+
+
+def update_depth(upd, hidden: Tensor):
+    probability = torch.softmax(upd.depth_head(hidden), dim=1)
+    return window_regression(probability, upd.radius), probability
+
+
+def update_forward(upd, hidden: Tensor, normalized_depth: Tensor, corr: Tensor, confidence_flag: bool):
+    """Update.forward (itermvs.py:192-220): (hidden, normalized_depth, probability, confidence, confidence_logit)."""
+    hidden = conv_gru(upd.gru, hidden, torch.cat([normalized_depth, corr], dim=1))
+    conf0 = upd.confidence_head(hidden) if confidence_flag else None
+    nd, probability = update_depth(upd, hidden)
+    return hidden, nd, probability, (torch.sigmoid(conf0) if confidence_flag else None), conf0
+
+
 # ---- the estimator, training structure (itermvs.py:253-329 with test=False) ------------------------------------
 def itermvs_train_forward(net, fea1: Tensor, fea2: Tensor, fea3: Tensor, projs: Sequence[Tensor], depth_min: Tensor,
                           depth_max: Tensor):
@@ -229,28 +297,13 @@ def itermvs_train_forward(net, fea1: Tensor, fea2: Tensor, fea3: Tensor, projs: 
     inv_min = (1.0 / depth_min).reshape(b, 1, 1, 1)
     inv_max = (1.0 / depth_max).reshape(b, 1, 1, 1)
 
-    # ---- initialisation (itermvs.py:270-283; Evaluation's view_weights == None branch, 36-82)
-    d = net.num_sample
+    # ---- initialisation (itermvs.py:270-283)
     samples0 = net.depth_initialization(inv_min, inv_max, h3, w3, dev)
-    corr_views = _to_planar(FusedCorrInit.apply(fea3, rts[2], samples0), h3, w3)      # [B,S,8,D,H3,W3]
-    corr_sum, vw_sum, view_weights = 0, 1e-5, []
-    for i in range(s):
-        c = corr_views[:, i]
-        vw_i = pixel_view_weight(ev.pixel_view_weight, c)                              # [B,1,H3,W3]
-        view_weights.append(F.interpolate(vw_i, scale_factor=2, mode="bilinear"))
-        corr_sum = corr_sum + c * vw_i.unsqueeze(1)
-        vw_sum = vw_sum + vw_i.unsqueeze(1)
-    corr = corr_net(ev.corr_conv1[2], corr_sum / vw_sum)                                # [B,D,H3,W3]
-    view_weights = torch.cat(view_weights, dim=1)
-    prob0 = torch.softmax(corr, dim=1)
-    index = torch.arange(0, d, 1, device=dev, dtype=torch.float32).view(1, d, 1, 1)
-    nd0 = torch.sum(index * prob0, dim=1, keepdim=True) / (d - 1.0)
-    depth0 = F.interpolate(ops.depth_unnormalization(nd0, inv_min, inv_max), scale_factor=2, mode="bilinear")
+    view_weights, corr, depth0 = evaluation_init(ev, fea3, rts[2], samples0, inv_min, inv_max)
     depths["initial"].append(depth0)
 
-    hidden = torch.tanh(F.interpolate(upd.hidden_init_head(corr), scale_factor=2, mode="bilinear"))   # itermvs.py:159-164
-    probability = torch.softmax(upd.depth_head(hidden), dim=1)
-    nd = window_regression(probability, upd.radius)
+    hidden = update_hidden_init(upd, corr)                                              # itermvs.py:275-279
+    nd, probability = update_depth(upd, hidden)
     conf0 = upd.confidence_head(hidden)
     depths["combine"].append(ops.depth_unnormalization(nd, inv_min, inv_max))
     depths["probability"].append(probability)
@@ -264,20 +317,14 @@ def itermvs_train_forward(net, fea1: Tensor, fea2: Tensor, fea3: Tensor, projs: 
         for lvl in ("level1", "level2", "level3"):
             ns = torch.clamp(nd + net.corr_interval[lvl].to(dev) * net.interval_scale, min=0, max=1)
             smp.append(ops.depth_unnormalization(ns, inv_min, inv_max).contiguous())
-        agg = _to_planar(FusedCorrIter.apply(fea1, fea2, fea3, rts[0], rts[1], rts[2], smp[0], smp[1], smp[2], vw_const),
-                         h2, w2)                                                        # [B,8,10,H2,W2]
-        corr = torch.cat([corr_net(ev.corr_conv1[0], agg[:, :, 0:4]), corr_net(ev.corr_conv1[1], agg[:, :, 4:8]),
-                          corr_net(ev.corr_conv1[2], agg[:, :, 8:10])], dim=1)
-        hidden = conv_gru(upd.gru, hidden, torch.cat([nd, corr], dim=1))                # itermvs.py:192-220
-        conf0 = upd.confidence_head(hidden)
-        probability = torch.softmax(upd.depth_head(hidden), dim=1)
-        nd = window_regression(probability, upd.radius)
+        corr = evaluation_iter(ev, fea1, fea2, fea3, rts, smp, vw_const)
+        hidden, nd, probability, conf, conf0 = update_forward(upd, hidden, nd, corr, True)
         depths["combine"].append(ops.depth_unnormalization(nd, inv_min, inv_max))
         depths["probability"].append(probability)
         confidences.append(conf0)
         if it == net.iteration - 1:
             depths_upsampled.append(ops.depth_unnormalization(ops.upsample(nd, up_w), inv_min, inv_max))
-            confidence_upsampled = F.interpolate(torch.sigmoid(conf0), scale_factor=4, mode="bilinear")
+            confidence_upsampled = F.interpolate(conf, scale_factor=4, mode="bilinear")
         nd = nd.detach()
     return depths, depths_upsampled, confidences, confidence_upsampled
 

@@ -141,3 +141,50 @@ def test_train_step_with_flat_bucket(sim_backend, dtu_weights):
     moved = [k for k, p in m.named_parameters() if not torch.equal(p.detach(), w0[k])]
     assert "feature_net.conv1.conv.weight" in moved and "iter_mvs.update.gru.convq.weight" in moved
     assert not any(k.startswith("feature_net.inner3") for k in moved)
+
+
+def test_modules_are_differentiable_in_train_mode(sim_backend, dtu_weights, monkeypatch):
+    """Operator level: in train() mode with autograd on, the mirrored modules -- Evaluation (both branches, the
+    reference's dict-of-NCHW arguments), Update, ConvGRU, CorrNet, PixelViewWeight -- return tensors that carry a graph,
+    with the same values as the oracle; in eval() mode / under no_grad they stay on the inference kernels."""
+    import itermvs_b200
+    from itermvs_b200 import ops
+    from itermvs_b200.synthetic import random_feature_pyramids
+    from oracle import itermvs_oracle as O
+    monkeypatch.setattr(ops, "_chk", lambda t, name: t.float().contiguous())
+    m = itermvs_b200.Pipeline(iteration=1, test=False)
+    m.load_state_dict(dtu_weights, strict=True)
+    m.train()
+    ev, upd = m.iter_mvs.evaluation, m.iter_mvs.update
+    w, h, n_src = 64, 64, 2
+    ref, srcs = random_feature_pyramids(w, h, n_src, 1, 5)
+    s = make_sample(w, h, n_src=n_src, batch=1, seed=5, scene="noise")
+    rp, sp = {}, {}
+    for l in (1, 2, 3):
+        pm = torch.unbind(s["proj_matrices"][f"level_{l}"].float(), 1)
+        rp[f"level{l}"], sp[f"level{l}"] = pm[0], list(pm[1:])
+    ref = {k: v.requires_grad_(True) for k, v in ref.items()}
+    inv_min, inv_max = (1.0 / s["depth_min"]).view(1, 1, 1, 1), (1.0 / s["depth_max"]).view(1, 1, 1, 1)
+    ds = O.initial_depth_samples(inv_min, inv_max, 32, h // 8, w // 8)
+    vw, corr, depth = ev(ref, srcs, rp, sp, ds, inv_min, inv_max)
+    want = O.evaluation_init(dtu_weights, ref["level3"].detach(), srcs["level3"], rp["level3"], sp["level3"], ds, inv_min, inv_max)
+    assert float((vw.detach() - want["view_weights"]).abs().max()) < 2e-5 and float((corr.detach() - want["corr"]).abs().max()) < 1e-4
+    assert corr.requires_grad and vw.requires_grad and depth.requires_grad
+    nd = torch.rand(1, 1, h // 4, w // 4, generator=torch.Generator().manual_seed(1))
+    samples = {f"level{l}": O.iteration_depth_samples(nd, l, inv_min, inv_max) for l in (1, 2, 3)}
+    corr_it = ev(ref, srcs, rp, sp, samples, view_weights=vw.detach())
+    want_it = O.evaluation_iter(dtu_weights, {k: v.detach() for k, v in ref.items()}, srcs, rp, sp, samples, vw.detach())
+    assert float((corr_it.detach() - want_it).abs().max()) < 1e-4 and corr_it.requires_grad
+    hidden = upd.hidden_init(corr)
+    nd0, prob = upd.depth_init(hidden)
+    conf, conf0 = upd.conf_init(hidden)
+    hidden1, nd1, prob1, conf1, conf01 = upd(hidden, nd0.detach(), corr_it, confidence_flag=True)
+    assert all(t.requires_grad for t in (hidden, nd0, prob, conf0, hidden1, nd1, prob1, conf01))
+    (nd1.sum() + conf01.sum() + depth.sum()).backward()
+    assert all(v.grad is not None and float(v.grad.abs().sum()) > 0 for v in ref.values())
+    assert upd.gru.convq.weight.grad is not None and ev.corr_conv1[0].conv5.weight.grad is not None
+    assert ev.pixel_view_weight.conv[0].conv.weight.grad is not None
+    # the small modules on their own
+    x = torch.randn(1, 8, 3, 8, 8)
+    assert ev.corr_conv1[1](x).requires_grad and ev.pixel_view_weight(x).requires_grad
+    assert upd.gru(torch.randn(1, 32, 8, 8), torch.randn(1, 11, 8, 8)).requires_grad
