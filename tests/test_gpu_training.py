@@ -163,3 +163,37 @@ def test_training_step_matches_reference(dev, dtu_weights):
     before = params["iter_mvs.update.gru.convq.weight"].detach().clone()
     step_loss, _ = train_step(ddp, opt, sample, itermvs_b200.full_loss)
     assert torch.isfinite(step_loss) and not torch.equal(before, params["iter_mvs.update.gru.convq.weight"].detach())
+
+
+def test_modules_are_differentiable_in_train_mode(dev, dtu_weights):
+    """Operator level: Evaluation (reference-style dict arguments, both branches) and Update in train() mode carry a graph
+    and match the oracle; the same modules in eval() mode run the inference kernels and give the same numbers."""
+    import itermvs_b200
+    m = itermvs_b200.Pipeline(iteration=1, test=False)
+    m.load_state_dict(dtu_weights, strict=True)
+    m = m.to(dev).train()
+    ev, upd = m.iter_mvs.evaluation, m.iter_mvs.update
+    batch, n_src = 1, 2
+    ref, srcs, rp, sp, s = _inputs(160, 128, n_src, batch, seed=5)
+    to = lambda d: {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in d.items()}
+    gref, gsrcs, grp, gsp = to(ref), to(srcs), to(rp), to(sp)
+    gref = {k: v.requires_grad_(True) for k, v in gref.items()}
+    inv_min = (1.0 / s["depth_min"]).view(batch, 1, 1, 1)
+    inv_max = (1.0 / s["depth_max"]).view(batch, 1, 1, 1)
+    ds = O.initial_depth_samples(inv_min, inv_max, 32, 16, 20)
+    vw, corr, depth = ev(gref, gsrcs, grp, gsp, ds.to(dev), inv_min.to(dev), inv_max.to(dev))
+    want = O.evaluation_init(dtu_weights, ref["level3"], srcs["level3"], rp["level3"], sp["level3"], ds, inv_min, inv_max)
+    assert maxerr(vw, want["view_weights"]) < 1e-4 and maxerr(corr, want["corr"]) < 2e-4
+    assert corr.requires_grad and vw.requires_grad
+    hidden = upd.hidden_init(corr)
+    nd0, _ = upd.depth_init(hidden)
+    samples = {f"level{l}": O.iteration_depth_samples(nd0.detach().cpu(), l, inv_min, inv_max).to(dev) for l in (1, 2, 3)}
+    corr_it = ev(gref, gsrcs, grp, gsp, samples, view_weights=vw.detach())
+    hidden1, nd1, prob1, conf1, conf01 = upd(hidden, nd0.detach(), corr_it, confidence_flag=True)
+    (nd1.sum() + conf01.sum() + depth.sum()).backward()
+    assert all(v.grad is not None and float(v.grad.abs().sum()) > 0 for v in gref.values())
+    assert upd.gru.convq.weight.grad is not None and ev.pixel_view_weight.conv[0].conv.weight.grad is not None
+    m.eval()
+    with torch.no_grad():
+        vw_e, corr_e, _ = ev(gref, gsrcs, grp, gsp, ds.to(dev), inv_min.to(dev), inv_max.to(dev))
+    assert maxerr(vw_e, vw) < 1e-4 and maxerr(corr_e, corr) < 2e-4           # inference kernels == differentiable path
