@@ -106,3 +106,24 @@ def test_end_to_end_fixture_on_cpu(sim_product, dtu_weights):
     rel = np.abs(depth_up.numpy() - fix["depths_upsampled"]) / fix["depths_upsampled"]
     assert float(np.median(rel)) < 2e-5 and float((rel > 1e-3).mean()) < 0.03            # the GPU test's bounds
     assert float((np.abs(conf_up.numpy() - fix["confidence_upsampled"]) > 1e-3).mean()) < 0.03
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+def test_tf32_modes_on_cpu(sim_product, model, stage_kats, passes):
+    """The other two precision modes of the convolution engine (mma.sync.m16n8k8 TF32): 3 = 3xTF32 error-compensated
+    (fp32-grade: the GPU test's bounds), 1 = single-pass TF32 (the reference's stock cuDNN precision; 10-bit mantissa
+    bounds).  tcgen05 is switched off: that variant is the one source the emulation does not cover."""
+    from itermvs_b200 import _lib
+    sim_product.imvs_set_tcgen05(0)
+    _lib.set_conv_passes(passes)
+    try:
+        if passes == 3:
+            G.test_corrnet_pvw_gru_hinit_golden(CPU, stage_kats, model)
+        else:
+            k = stage_kats
+            h = model.iter_mvs.update.gru(G.T(k["gru_h"]), G.T(k["gru_x"]))
+            assert G.maxerr(h, G.T(k["gru_out"])) < 2e-2          # |h| <= 1, K = 387 products of 10-bit operands
+            assert G.maxerr(h, G.T(k["gru_out"])) > 1e-6          # ... and it really ran in reduced precision
+    finally:
+        _lib.set_conv_passes(4)
+        sim_product.imvs_set_tcgen05(1)
