@@ -49,12 +49,14 @@ def _check(rc: int, what: str) -> None:
         raise RuntimeError(f"itermvs_b200 {what}: {_L().imvs_last_error().decode('utf-8', 'replace')}")
 
 
-def _compose(proj: Tensor) -> Tensor:
-    """[B,V,4,4] (view 0 = reference) -> [B,V-1,12] rot|trans of src @ inverse(ref); constants for autograd."""
+def _compose(proj: Tensor, nan_flag=None) -> Tensor:
+    """[B,V,4,4] (view 0 = reference) -> [B,V-1,12] rot|trans of src @ inverse(ref); constants for autograd.
+    `nan_flag` (ops.NanFlag): the deferred form of the reference's `assert not isnan(proj)` (module.py:83, 87)."""
     proj = _chk(proj.detach().float(), "proj")
     b, v = proj.shape[:2]
     out = torch.empty(b, v - 1, 12, device=proj.device, dtype=torch.float32)
-    _check(_L().imvs_compose_projections(proj.data_ptr(), b, v, out.data_ptr(), None, _st()), "compose_projections")
+    _check(_L().imvs_compose_projections(proj.data_ptr(), b, v, out.data_ptr(), nan_flag.ptr() if nan_flag is not None else None,
+                                         _st()), "compose_projections")
     return out
 
 
@@ -249,7 +251,10 @@ def evaluation_forward(ev, ref_feature, src_features, ref_proj, src_projs, depth
         maps = [ref_feature[level], *src_features[level]]
         fea = torch.stack(maps, dim=1).permute(0, 1, 3, 4, 2).contiguous()
         proj = torch.stack([ref_proj[level], *src_projs[level]], dim=1).float().to(fea.device)
-        return fea, _compose(proj)
+        flag = ops.NanFlag(fea.device)
+        rt = _compose(proj, flag)
+        flag.raise_if_set()
+        return fea, rt
     if view_weights is None:
         fea3, rt3 = stack("level3")
         return evaluation_init(ev, fea3, rt3, depth_sample, inverse_depth_min, inverse_depth_max)
@@ -290,7 +295,9 @@ def itermvs_train_forward(net, fea1: Tensor, fea2: Tensor, fea3: Tensor, projs: 
     confidences: List[Tensor] = []
     depths_upsampled: List[Tensor] = []
     confidence_upsampled = None
-    rts = [_compose(p) for p in projs]
+    flag = ops.NanFlag(dev)
+    rts = [_compose(p, flag) for p in projs]
+    flag.raise_if_set()                      # "nan in proj" (module.py:87); the reference synchronises on every warp call
 
     ref2 = fea2[:, 0].permute(0, 3, 1, 2)                                   # NCHW view of the reference feature
     up_w = torch.softmax(net.upsample(ref2).reshape(b, 1, 9, 4, 4, h2, w2), dim=2)        # itermvs.py:262-264

@@ -188,3 +188,16 @@ def test_modules_are_differentiable_in_train_mode(sim_backend, dtu_weights, monk
     x = torch.randn(1, 8, 3, 8, 8)
     assert ev.corr_conv1[1](x).requires_grad and ev.pixel_view_weight(x).requires_grad
     assert upd.gru(torch.randn(1, 32, 8, 8), torch.randn(1, 11, 8, 8)).requires_grad
+
+
+def test_nan_projection_raises_like_the_reference(sim_backend, dtu_weights):
+    """module.py:83-87: `assert not torch.isnan(proj).any()` -- the training path keeps the AssertionError."""
+    import itermvs_b200
+    from itermvs_b200 import training
+    m = itermvs_b200.Pipeline(iteration=1, test=False)
+    m.load_state_dict(dtu_weights, strict=True)
+    m.train()
+    s = make_sample(64, 64, n_src=1, batch=1, seed=1, scene="plane")
+    s["proj_matrices"]["level_2"][0, 1, 0, 0] = float("nan")
+    with pytest.raises(AssertionError, match="nan in proj"):
+        training.pipeline_train_forward(m, s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"])
