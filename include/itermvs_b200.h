@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IMVS_ABI_VERSION 2
+#define IMVS_ABI_VERSION 3
 #define IMVS_GROUPS 8          /* reference models/itermvs.py:28 */
 #define IMVS_OUT_BINS 256      /* reference models/itermvs.py:134 */
 #define IMVS_RADIUS 4          /* reference models/itermvs.py:135 */

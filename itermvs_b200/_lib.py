@@ -18,7 +18,7 @@ _lib = None
 vp = C.c_void_p
 ci = C.c_int
 sz = C.c_size_t
-ABI_VERSION = 2
+ABI_VERSION = 3
 FNET_CONVS = 24
 
 
@@ -112,11 +112,12 @@ def lib():
                     f"itermvs_b200: CUDA library {path} is missing and could not be built ({e}). "
                     "There is no CPU fallback; run `python -m itermvs_b200._build` where nvcc is available.") from e
         handle = C.CDLL(path)
+        handle.imvs_abi_version.restype = ci
+        if handle.imvs_abi_version() != ABI_VERSION:        # before binding: a stale library may lack newer symbols
+            raise LibraryMissing(f"itermvs_b200: ABI version mismatch in {path} (rebuild with python -m itermvs_b200._build --force)")
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.imvs_abi_version() != ABI_VERSION:
-            raise LibraryMissing(f"itermvs_b200: ABI version mismatch in {path} (rebuild with python -m itermvs_b200._build --force)")
         _lib = handle
         return _lib
 
