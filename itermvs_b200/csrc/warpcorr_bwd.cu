@@ -132,17 +132,15 @@ __global__ void __launch_bounds__(128) warpcorr_iter_bwd_kernel(const IterBwdPar
     float* gb = prm.gfea + (size_t)b * V * view_elems + c0;
 
     // the reference feature of this level-2 pixel and the (<= 4) texels of the reference map it is made of
+    constexpr int NREF = LVL == 1 ? 1 : 4;
     int ro[4];
     float rw[4];
-    int nref;
     if (LVL == 1) {
-        nref = 1; ro[0] = (y * Wf + x) * C; rw[0] = 1.f;
+        ro[0] = (y * Wf + x) * C; rw[0] = 1.f;
     } else if (LVL == 0) {                     // F.interpolate(scale 0.5, bilinear) == 2x2 mean
-        nref = 4;
         ro[0] = ((2 * y) * Wf + 2 * x) * C; ro[1] = ro[0] + C; ro[2] = ro[0] + Wf * C; ro[3] = ro[2] + C;
         rw[0] = rw[1] = rw[2] = rw[3] = 0.25f;
     } else {                                   // F.interpolate(scale 2, bilinear, align_corners=False)
-        nref = 4;
         int h0, h1, w0, w1;
         float lh, lw;
         up_index(y, 0.5f, Hf, h0, h1, lh);
@@ -151,7 +149,8 @@ __global__ void __launch_bounds__(128) warpcorr_iter_bwd_kernel(const IterBwdPar
         rw[0] = (1.f - lh) * (1.f - lw); rw[1] = (1.f - lh) * lw; rw[2] = lh * (1.f - lw); rw[3] = lh * lw;
     }
     float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < nref; ++i) {
+#pragma unroll
+    for (int i = 0; i < NREF; ++i) {
         const float4 a = ldg4(fb + ro[i]);
         ref.x = fmaf(a.x, rw[i], ref.x); ref.y = fmaf(a.y, rw[i], ref.y);
         ref.z = fmaf(a.z, rw[i], ref.z); ref.w = fmaf(a.w, rw[i], ref.w);
@@ -189,7 +188,8 @@ __global__ void __launch_bounds__(128) warpcorr_iter_bwd_kernel(const IterBwdPar
         }
     }
     // adjoint of the reference resampling: several level-2 pixels share a level-3 texel -> atomics
-    for (int i = 0; i < nref; ++i)
+#pragma unroll
+    for (int i = 0; i < NREF; ++i)
         red_add4(gb + ro[i], make_float4(gref.x * rw[i], gref.y * rw[i], gref.z * rw[i], gref.w * rw[i]));
 }
 
