@@ -187,6 +187,13 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     const char* tr = getenv("CUSIM_TRACE");
     g_trace = tr && *tr;
     if (g_trace) g_trace_path = tr;
+    // CUSIM_SHUFFLE=<seed>: run the fibers of a block in a random order that changes every scheduling round -- a missing
+    // barrier between a producer and a consumer then shows up as a result that depends on the seed
+    const char* sh = getenv("CUSIM_SHUFFLE");
+    const bool shuffle = sh && *sh;
+    unsigned long long rng = shuffle ? strtoull(sh, nullptr, 10) * 0x9E3779B97F4A7C15ULL + 1 : 0;
+    std::vector<int> order(nthreads);
+    for (int i = 0; i < nthreads; ++i) order[i] = i;
     g_stacks.resize((size_t)nthreads * STACK_BYTES);
     BlockState blk;
     g_blk = &blk;
@@ -220,7 +227,14 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
                 int remaining = nthreads;
                 while (remaining > 0) {
                     const unsigned long long before = g_events;
-                    for (int i = 0; i < nthreads; ++i) {
+                    if (shuffle) {                      // a different legal interleaving every round
+                        for (int i = nthreads - 1; i > 0; --i) {
+                            rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+                            std::swap(order[i], order[(rng >> 33) % (unsigned)(i + 1)]);
+                        }
+                    }
+                    for (int oi = 0; oi < nthreads; ++oi) {
+                        const int i = order[oi];
                         Fiber& f = blk.fibers[i];
                         if (f.done) continue;
                         if (f.wait_gen && *f.wait_gen == f.wait_val) continue;      // still parked

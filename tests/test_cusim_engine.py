@@ -127,3 +127,22 @@ def test_tf32_modes_on_cpu(sim_product, model, stage_kats, passes):
     finally:
         _lib.set_conv_passes(4)
         sim_product.imvs_set_tcgen05(1)
+
+
+def test_results_do_not_depend_on_the_thread_schedule(sim_product, model, stage_kats, monkeypatch):
+    """CUSIM_SHUFFLE: the fibers of a block run in a random order that changes every scheduling round.  A missing barrier
+    between the warps that stage a tile / weights and the warps that consume them would make the output depend on the
+    seed; it must be bit-identical."""
+    k = stage_kats
+    upd, ev = model.iter_mvs.update, model.iter_mvs.evaluation
+
+    def run():
+        with torch.no_grad():
+            return (upd.gru(G.T(k["gru_h"]), G.T(k["gru_x"])), ev.corr_conv1[0](G.T(k["corrnet_in"])),
+                    upd.hidden_init(G.T(k["hinit_in"])))
+    base = run()
+    for seed in ("1", "2"):
+        monkeypatch.setenv("CUSIM_SHUFFLE", seed)
+        for a, b in zip(base, run()):
+            assert torch.equal(a, b), seed
+    monkeypatch.delenv("CUSIM_SHUFFLE")

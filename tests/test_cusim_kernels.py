@@ -177,9 +177,15 @@ def test_warpcorr_iter_source_on_cpu(sim, batch, n_src, width, height, sms, monk
                                        P(smp[0]), P(smp[1]), P(smp[2]), P(agg), batch, n_src + 1, h2, w2, None))
         return agg.view(batch, 10, h2, w2, 8).permute(0, 4, 1, 2, 3)
 
-    assert maxerr(run(True), want) < 1e-4
+    first = run(True)
+    assert maxerr(first, want) < 1e-4
     # hypotheses generated in the kernel from nd (itermvs.py:289-293): same result up to the rounding of 1/depth
     assert maxerr(run(False), want) < 2e-4
+    # a different interleaving of the block's warps (who draws which item from the shared-memory queue, when) must
+    # not change a single bit
+    monkeypatch.setenv("CUSIM_SHUFFLE", str(7 + sms))
+    assert torch.equal(run(True), first)
+    monkeypatch.delenv("CUSIM_SHUFFLE")
 
 
 def _aggregated_only(ref, srcs, rp, sp, samples, vw):
