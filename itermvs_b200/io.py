@@ -6,6 +6,7 @@
     projection_pyramid             datasets/dtu_yao_eval.py:106-126 (4x4 = [K_l @ E[:3,:4]; E[3]] for levels 3..0)
     image_pyramid / read_img       datasets/dtu_yao_eval.py:61-76
     load_views                     datasets/dtu_yao_eval.py:78-158 (__getitem__): the dict Pipeline.forward takes
+    backproject_points / save_ply  eval.py:281-309 (the filtered depth maps as a coloured point cloud; read_ply reads it back)
 
 Host-side numpy; nothing here touches the GPU (Pipeline.forward reads imgs['level_0'] and proj_matrices['level_1..3'] only).
 """
@@ -143,3 +144,60 @@ def load_views(datapath: str, scan: str, ref_view: int, src_views: Sequence[int]
             "proj_matrices": {lv: np.stack(v) for lv, v in proj.items()},
             "depth_min": depth_min, "depth_max": depth_max,
             "filename": scan + "/{}/" + "{:0>8}".format(view_ids[0]) + "{}"}
+
+
+# --------------------------------------------------------------------------------- point cloud --
+def backproject_points(depth_est_averaged: np.ndarray, final_mask: np.ndarray, ref_img: np.ndarray, ref_intrinsics: np.ndarray,
+                       ref_extrinsics: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """The tail of filter_depth's loop body (eval.py:281-296): the pixels that survive the photometric + geometric
+    filter (what `filter_depth_view` returns) lifted to world coordinates, with their colours.
+    -> (vertices [N,3] float64 world xyz, colours [N,3] uint8), same arithmetic / promotions as the numpy original."""
+    height, width = depth_est_averaged.shape[:2]
+    xs, ys = np.meshgrid(np.arange(0, width), np.arange(0, height))
+    valid = np.asarray(final_mask, dtype=bool)
+    xs, ys, depth = xs[valid], ys[valid], depth_est_averaged[valid]
+    xyz_ref = np.matmul(np.linalg.inv(ref_intrinsics), np.vstack((xs, ys, np.ones_like(xs))) * depth)
+    xyz_world = np.matmul(np.linalg.inv(ref_extrinsics), np.vstack((xyz_ref, np.ones_like(xs))))[:3]
+    return xyz_world.transpose((1, 0)), (ref_img[valid] * 255).astype(np.uint8)
+
+
+_PLY_HEADER = ("ply\nformat binary_little_endian 1.0\nelement vertex {n}\nproperty float x\nproperty float y\nproperty float z\n"
+               "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
+_PLY_VERTEX = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+
+
+def save_ply(filename: str, vertices: np.ndarray, colors: np.ndarray) -> None:
+    """The fused point cloud as eval.py:298-309 writes it through plyfile (`PlyData([PlyElement.describe(vertex_all,
+    'vertex')]).write(...)`): binary little-endian, one 15-byte record per point (x, y, z float32; red, green, blue
+    uchar).  plyfile is not installed in the build image, so the header text is restated from its writer (format line,
+    element line, one property line per field, end_header) rather than compared byte for byte -- parity unpinned for
+    this one function; read_ply below and any PLY reader (MeshLab, Open3D, the DTU evaluation scripts) accept it."""
+    vertices = np.asarray(vertices)
+    colors = np.asarray(colors)
+    if vertices.ndim != 2 or vertices.shape[1] != 3 or colors.shape != vertices.shape:
+        raise ValueError("save_ply: vertices and colors must both be [N,3]")
+    rec = np.empty(len(vertices), dtype=_PLY_VERTEX)
+    for i, name in enumerate(("x", "y", "z")):
+        rec[name] = vertices[:, i].astype(np.float32)
+    for i, name in enumerate(("red", "green", "blue")):
+        rec[name] = colors[:, i].astype(np.uint8)
+    with open(filename, "wb") as f:
+        f.write(_PLY_HEADER.format(n=len(rec)).encode("ascii"))
+        rec.tofile(f)
+
+
+def read_ply(filename: str) -> Tuple[np.ndarray, np.ndarray]:
+    """Reader for the files save_ply writes: -> (vertices [N,3] float32, colours [N,3] uint8)."""
+    with open(filename, "rb") as f:
+        header = b""
+        while not header.endswith(b"end_header\n"):
+            line = f.readline()
+            if not line:
+                raise ValueError("read_ply: no end_header")
+            header += line
+        text = header.decode("ascii")
+        if "format binary_little_endian 1.0" not in text:
+            raise ValueError("read_ply: only the binary little-endian vertex files of save_ply are supported")
+        n = int(re.search(r"element vertex (\d+)", text).group(1))
+        rec = np.fromfile(f, dtype=_PLY_VERTEX, count=n)
+    return (np.stack([rec["x"], rec["y"], rec["z"]], axis=1), np.stack([rec["red"], rec["green"], rec["blue"]], axis=1))

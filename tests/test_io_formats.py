@@ -71,3 +71,23 @@ def test_load_views_matches_reference_loader(kat, tmp_path):
         assert s["proj_matrices"][lv].dtype == np.float32 and np.array_equal(s["proj_matrices"][lv], kat[f"proj_{lv}"]), lv
     assert s["depth_min"] == float(kat["depth_min"]) and s["depth_max"] == float(kat["depth_max"])
     assert s["filename"] == kat["filename"].tobytes().decode()
+
+
+def test_point_cloud_tail_matches_reference_lines(tmp_path):
+    """backproject_points == eval.py:281-296 executed verbatim (tests/golden/make_golden_points.py); save_ply / read_ply
+    round trip with the float32 / uint8 casts eval.py:300-301 applies before plyfile writes."""
+    with np.load(os.path.join(os.path.dirname(__file__), "golden", "points_kat.npz")) as z:
+        k = {n: z[n] for n in z.files}
+    v, c = mio.backproject_points(k["depth_est_averaged"], k["final_mask"], k["ref_img"], k["ref_intrinsics"], k["ref_extrinsics"])
+    assert v.dtype == k["vertices"].dtype and np.array_equal(v, k["vertices"])
+    assert c.dtype == np.uint8 and np.array_equal(c, k["colors"])
+    fn = str(tmp_path / "fused.ply")
+    mio.save_ply(fn, v, c)
+    raw = open(fn, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert head.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\n" % len(v))
+    assert len(body) == 15 * len(v)                                  # 3 x float32 + 3 x uchar per point, packed
+    v2, c2 = mio.read_ply(fn)
+    assert np.array_equal(v2, v.astype(np.float32)) and np.array_equal(c2, c)
+    with pytest.raises(ValueError):
+        mio.save_ply(fn, v[:, :2], c)
