@@ -371,3 +371,20 @@ def test_load_tracer_counts(sim, tmp_path, monkeypatch):
     # a warp's 32 float4 are 512 contiguous bytes = 16 sectors / 4 lines; its 32 weights (16 pixels x 2 halves) 64 bytes
     assert tot["sectors"] == threads // 32 * s_ * (16 + 2) and tot["lines"] == threads // 32 * s_ * (4 + 1)
     assert tot["wavefronts"] == tot["lines"]
+
+
+def test_wavefront_model_tool_runs():
+    """tools/wavefront_model.py (the offline access-pattern model used for DESIGN section 8) at a toy size: both plane-sweep
+    launches are traced, the counters are consistent with each other."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "wavefront_model.py"), "--width", "64", "--height", "64",
+                        "--views", "2", "--sms", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout)
+    for name in ("init", "iter"):
+        m = out[name]["model"]
+        assert m["requests"] > 0 and m["lines"] <= m["sectors"] <= 4 * m["lines"]
+        assert m["wavefronts"] >= max(m["lines"], out[name]["delivered_floor_wavefronts"] - 1)
+        assert "ncu" not in out[name]                     # the measured counters belong to the benchmark configuration only
