@@ -149,7 +149,8 @@ def test_warpcorr_init_source_on_cpu(sim, batch, n_src, d):
 # 1..8 source views run the unrolled instantiations, 9 the rolled one; CUSIM_SMS picks how many persistent blocks
 # share the tile range (1 block; 3 blocks with a ragged split; more blocks than tiles)
 @pytest.mark.parametrize("batch,n_src,width,height,sms", [(1, 4, 96, 64, 3), (2, 3, 64, 64, 1), (1, 1, 64, 32, 64),
-                                                          (1, 7, 64, 32, 2), (1, 9, 64, 32, 3), (1, 2, 96, 96, 5)])
+                                                          (1, 7, 64, 32, 2), (1, 9, 64, 32, 3), (1, 2, 96, 96, 5),
+                                                          (1, 16, 64, 32, 3)])       # 16 = IMVS_MAX_VIEWS
 def test_warpcorr_iter_source_on_cpu(sim, batch, n_src, width, height, sms, monkeypatch):
     monkeypatch.setenv("CUSIM_SMS", str(sms))
     ref, srcs, rp, sp, s = feature_inputs(width, height, n_src, batch, seed=12)
