@@ -6,8 +6,9 @@ Split of work (SURVEY 8b "Autograd"):
     aggregation in the iterations) -- runs on the fused sm_100a kernels in BOTH directions: `FusedCorrInit` /
     `FusedCorrIter` are torch.autograd.Functions over imvs_warpcorr_init / _iter and their *_backward twins.  Nothing
     is saved for the backward except the inputs: the reference's autograd graph keeps a [C,R,H,W] warped volume and
-    the same-size product per differentiable_warping call (52 calls at 4 views / 4 iterations, ~0.4 GB per iteration
-    at 640x512); here the backward recomputes the sampling positions.  Gradients go to the feature pyramids only --
+    the same-size product per differentiable_warping call (52 calls at 4 views / 4 iterations: 574 MB of the 1 721 MB
+    a 640x512 training forward saves for backward, tools/saved_for_backward.py); here the backward recomputes the
+    sampling positions.  Gradients go to the feature pyramids only --
     the grid is built under no_grad in the reference (module.py:77), the iteration's view weights and hypotheses are
     detached (itermvs.py:295, 282-283).
   * the convolution stacks (FeatureNet with BatchNorm batch statistics, PixelViewWeight, CorrNet, ConvGRU, heads,
