@@ -37,6 +37,25 @@ def test_host_side_validation_without_gpu():
         assert len(L.imvs_last_error()) > 0
     assert L.imvs_featurenet_workspace_bytes(5, 512, 640) > 0
     assert L.imvs_get_conv_passes() == 4
+    # argument errors of the plane-sweep entry points (forward and backward) are reported before anything is launched
+    a = 0x1000                                    # a 16-byte aligned non-null address; never dereferenced on these paths
+    cases = [
+        (L.imvs_warpcorr_init, (None, a, a, a, None, a, 1, 5, 64, 80, 32, None), "null pointer"),
+        (L.imvs_warpcorr_init, (a, a, a, a, None, a, 1, 18, 64, 80, 32, None), "source views"),
+        (L.imvs_warpcorr_init, (a + 4, a, a, a, None, a, 1, 5, 64, 80, 32, None), "16-byte aligned"),
+        (L.imvs_warpcorr_init_backward, (a, a, a, a, None, None, a, 1, 5, 64, 80, 32, None), "null pointer"),
+        (L.imvs_warpcorr_init_backward, (a, a, None, None, None, a, a, 1, 5, 64, 80, 32, None), "null pointer"),
+        (L.imvs_warpcorr_init_backward, (a, a, a, a, None, a, a, 1, 1, 64, 80, 32, None), "source views"),
+        (L.imvs_warpcorr_init_backward, (a, a, a, a, None, a, a, 1, 5, 64, 80, 1, None), "bad shape"),
+        (L.imvs_warpcorr_iter_backward, (a, a, a, a, a, a, a, 1, 1, a, a, a, a, None, None, a, a, a, a, 1, 5, 128, 160, None), "either all three"),
+        (L.imvs_warpcorr_iter_backward, (a, a, a, a, a, a, None, 0, 1, a, None, None, None, None, None, a, a, a, a, 1, 5, 128, 160, None),
+         "either all three"),
+        (L.imvs_warpcorr_iter_backward, (a, a, a, a, a, a, a, 1, 1, a, a, a, None, None, None, a, a, a, a, 1, 5, 127, 160, None), "must be even"),
+        (L.imvs_warpcorr_iter_backward, (a, a, a, a, a, a, a, 1, 1, a, a, a, None, None, None, a, a, a + 8, a, 1, 5, 128, 160, None),
+         "16-byte aligned"),
+    ]
+    for fn, args, expect in cases:
+        assert fn(*args) != 0 and expect in L.imvs_last_error().decode(), (fn.__name__, expect, L.imvs_last_error())
 
 
 def test_tf32_split_and_packing(dtu_weights):
