@@ -134,16 +134,38 @@ def pick_cpu_threads(run, budget_s=10.0):
     return best
 
 
+def reference_runner(device="cpu"):
+    """(run, kind, note): one forward of the reference arm on the benchmark workload.  kind = "reference" when the
+    UNMODIFIED reference installed in baseline/_ref (tools/install_ref.py) is importable -- its own
+    models.net.Pipeline(test=True) with the DTU checkpoint, reference models/net.py:78 -- else "port" (oracle/)."""
+    from itermvs_b200.synthetic import make_sample
+    from oracle import reference_arm as RA
+    s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=0, scene="plane")
+    if RA.available():
+        m = RA.load_pipeline(iteration=ITERS).to(device)
+        imgs = {k: v.to(device) for k, v in s["imgs"].items()}
+        proj = {k: v.to(device) for k, v in s["proj_matrices"].items()}
+        dmin, dmax = s["depth_min"].to(device), s["depth_max"].to(device)
+
+        def run():
+            with torch.no_grad():
+                return m(imgs, proj, dmin, dmax)
+        return run, "reference", ("the unmodified reference (baseline/_ref: models/net.py Pipeline(test=True), DTU checkpoint) "
+                                  "through its own public API")
+    from oracle import itermvs_oracle as O
+    weights = {k: v.to(device) for k, v in load_weights().items()}
+    imgs = {k: v.to(device) for k, v in s["imgs"].items()}
+    proj = {k: v.to(device) for k, v in s["proj_matrices"].items()}
+    dmin, dmax = s["depth_min"].to(device), s["depth_max"].to(device)
+    run = lambda: O.pipeline_forward(weights, imgs, proj, dmin, dmax, iteration=ITERS, num_sample=D_HYP)
+    return run, "port", "baseline/_ref absent: CPU port of the reference algorithm (oracle/itermvs_oracle.py)"
+
+
 def run_reference(args, rank):
-    """Reference arm: the CPU port of the reference's algorithm (oracle/), all host threads."""
+    """Reference arm: the reference's own CPU path (baseline/_ref) on the box's host cores; rank 0 only."""
     if rank != 0:
         return
-    from oracle import itermvs_oracle as O
-    from itermvs_b200.synthetic import make_sample
-    weights = load_weights()
-    s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=0, scene="plane")
-    run = lambda: O.pipeline_forward(weights, s["imgs"], s["proj_matrices"], s["depth_min"], s["depth_max"],
-                                     iteration=ITERS, num_sample=D_HYP)
+    run, kind, note = reference_runner("cpu")
     pick_cpu_threads(run)
     for _ in range(args.warmup):
         run()
@@ -158,9 +180,8 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 (BASELINE configs[1])",
-                   "note": "CPU port of the reference algorithm (oracle/itermvs_oracle.py, pinned to reference-generated "
-                           "golden vectors); the Python reference itself cannot travel to the GPU box"},
-        "cpu_baseline": {"value": v, "unit": "refs/s", "cores": cores, "kind": "port",
+                   "note": note + "; torch CPU fp32, thread count probed over 8/16/32"},
+        "cpu_baseline": {"value": v, "unit": "refs/s", "cores": cores, "kind": kind, "host_cpus": os.cpu_count(),
                          "sample": f"{args.steps} full forward passes of the workload"},
         "e2e": {"value": v, "unit": "refs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -459,46 +480,56 @@ def main():
     e2e_value = replicas.aggregate_throughput(args.steps, e2e_ms, device=dev)
     total_ms = replicas.max_over_ranks([total_ms], device=dev)[0]
 
-    # ---- CPU baseline: oracle port on this box's host cores (rank 0, N=1 only)
+    # ---- CPU baseline: the reference itself (baseline/_ref) on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import itermvs_oracle as O
-        s0 = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=0, scene="plane")
-        run = lambda: O.pipeline_forward(weights, s0["imgs"], s0["proj_matrices"], s0["depth_min"], s0["depth_max"],
-                                         iteration=ITERS, num_sample=D_HYP)
+        run, kind, note = reference_runner("cpu")
         nthr = pick_cpu_threads(run)
         ts, t_begin = [], time.perf_counter()
-        for _ in range(3):
+        for _ in range(5):
             t0 = time.perf_counter()
             run()
             ts.append(time.perf_counter() - t0)
             if time.perf_counter() - t_begin > 20.0:      # bounded sample
                 break
-        cpu = {"value": 1.0 / statistics.median(ts), "unit": "refs/s", "cores": nthr, "kind": "port",
+        cpu = {"value": 1.0 / statistics.median(ts), "unit": "refs/s", "cores": nthr, "kind": kind,
                "host_cpus": os.cpu_count(),
-               "sample": f"{len(ts)} full forward passes of the workload (median) after a thread-count probe, "
-                         "oracle/itermvs_oracle.py on torch CPU fp32"}
+               "sample": f"{len(ts)} full forward passes of the workload (median) after a thread-count probe; " + note}
 
-    # ---- the same port on THIS GPU through stock ATen/cuDNN ops (proxy for the reference's stock GPU path,
-    #      which cannot travel to the box): eager, cudnn.benchmark as eval.py:21, TF32 convs as torch defaults
+    # ---- the reference's stock PyTorch/cuDNN path on THIS GPU (BASELINE.md section 2, B-GPU): the same unmodified
+    #      module .cuda(), cudnn.benchmark=True as eval.py:21, torch's default TF32 settings, inputs resident,
+    #      CUDA events around every forward, >= 50 repetitions
     gpu_stock = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import itermvs_oracle as O
         torch.backends.cudnn.benchmark = True
-        wd = {k: v.to(dev) for k, v in weights.items()}
-        di = {k: v.to(dev) for k, v in s["imgs"].items()}
-        dp = {k: v.to(dev) for k, v in s["proj_matrices"].items()}
-        run_g = lambda: O.pipeline_forward(wd, di, dp, d_dmin, d_dmax, iteration=ITERS, num_sample=D_HYP)
-        for _ in range(3):
+        run_g, kind_g, note_g = reference_runner(dev)
+        for _ in range(5):
             run_g()
         torch.cuda.synchronize()
+        reps = 50
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         t0 = time.perf_counter()
-        for _ in range(10):
+        for a_, b_ in evs:
+            a_.record()
             run_g()
+            b_.record()
         torch.cuda.synchronize()
-        gpu_stock = {"value": 10 / (time.perf_counter() - t0), "unit": "refs/s",
-                     "what": "oracle port executed on this GPU with stock ATen/cuDNN ops (eager, cudnn.benchmark, default TF32): "
-                             "proxy for the reference's stock PyTorch path, wall clock over 10 forwards"}
+        wall = time.perf_counter() - t0
+        ms = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
+        # parity of this path against the reference itself on the same GPU and inputs (rank 0: seed 0 for both)
+        parity = None
+        if kind_g == "reference":
+            out_ref = run_g()
+            out_new = eager()
+            rel = ((out_new["depths_upsampled"] - out_ref["depths_upsampled"]).abs() / out_ref["depths_upsampled"].abs())
+            dc = (out_new["confidence_upsampled"] - out_ref["confidence_upsampled"]).abs()
+            parity = {"depth_rel_max": float(rel.max()), "depth_rel_median": float(rel.median()),
+                      "depth_frac_gt_1e-3": float((rel > 1e-3).float().mean()), "confidence_abs_max": float(dc.max()),
+                      "note": "reference runs cuDNN with torch's default TF32 convolutions here; this path is fp32-grade"}
+        gpu_stock = {"value": reps / (sum(ms) / 1000.0), "unit": "refs/s", "kind": kind_g, "reps": reps,
+                     "ms_median": statistics.median(ms), "ms_min": ms[0], "wall_refs_per_s": reps / wall, "parity": parity,
+                     "what": note_g + " on this GPU: .cuda(), cudnn.benchmark=True (eval.py:21), torch default TF32 flags, "
+                             "device-resident inputs, CUDA events around each forward"}
 
     if rank != 0:
         if world > 1:
@@ -551,7 +582,9 @@ def main():
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if gpu_stock is not None:
-        line["gpu_stock_port"] = gpu_stock
+        line["gpu_stock_ref" if gpu_stock["kind"] == "reference" else "gpu_stock_port"] = gpu_stock
+        line["speedup_vs_gpu_stock"] = {"e2e": e2e_value / gpu_stock["value"], "single_stream": line["single_stream"]["value"] / gpu_stock["value"],
+                                        "what": "this path / the reference's stock PyTorch-cuDNN path on the same GPU (target >= 5x)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -7,8 +7,10 @@ and overlap machinery buys nothing at that size, launch count does.  So:
   * `FlatBucketDDP(model)` broadcasts rank 0's parameters and buffers once, then makes every parameter's `.grad` a
     view into one contiguous fp32 buffer -- backward writes the bucket in place, no flatten copy;
   * `reduce_gradients()` is a single `all_reduce(SUM)` over that buffer (NCCL over NVLink on GPUs, gloo in the CPU
-    tests) followed by one in-place scale; with `grad_dtype=torch.bfloat16` the wire format is bf16 (0.69 MB) and the
-    accumulation stays fp32 on both sides (BASELINE config 4);
+    tests) followed by one in-place scale; with `grad_dtype=torch.bfloat16` the bucket is rounded to bf16 for the
+    collective (0.69 MB on the wire; the cross-rank SUM itself then runs in bf16 inside NCCL / gloo -- about 3 significant
+    digits per gradient element, fine under clip_grad_norm_ + Adam) while backward's accumulation into the bucket, the
+    scale, the clipping and the optimizer stay fp32 (BASELINE config 4);
   * parameters that take no part in the forward (feature_net.inner3, net.py:25) simply keep a zero gradient: no
     unused-parameter search.  With Adam and weight_decay = 0 (train.py:98 defaults) a zero gradient leaves the
     parameter where `grad is None` would.
@@ -55,11 +57,14 @@ class FlatBucketDDP(nn.Module):
             p.grad = self._bucket[off:off + n].view_as(p)
             off += n
 
+    @torch.no_grad()
     def _broadcast_state(self) -> None:
-        tensors = [p.data for p in self.module.parameters()] + [b.data for b in self.module.buffers()]
+        # copy_ on the parameters / buffers themselves (not on `.data`): the version counters move, so packed-weight
+        # caches keyed on them (estimator._pack_key) see the new values
+        tensors = list(self.module.parameters()) + list(self.module.buffers())
         for dtype in sorted({t.dtype for t in tensors}, key=str):       # same order on every rank
             group = [t for t in tensors if t.dtype == dtype]
-            flat = torch.cat([t.reshape(-1) for t in group])
+            flat = torch.cat([t.detach().reshape(-1) for t in group])
             dist.broadcast(flat, src=0, group=self.process_group)
             off = 0
             for t in group:
@@ -108,10 +113,11 @@ class FlatBucketDDP(nn.Module):
         if not self._active():
             return
         world = dist.get_world_size(self.process_group)
-        for b in self.module.buffers():
-            if b.is_floating_point():
-                dist.all_reduce(b.data, op=dist.ReduceOp.SUM, group=self.process_group)
-                b.data.div_(world)
+        with torch.no_grad():                  # in-place ops on the buffers themselves: their version counters move,
+            for b in self.module.buffers():    # so cached BN-folded weight packs (estimator._pack_key) are rebuilt
+                if b.is_floating_point():
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.process_group)
+                    b.div_(world)
 
 
 def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, sample: Dict, loss_fn, regress: bool = True,

@@ -32,8 +32,25 @@ XCH = 16          # stored channels of the GRU input x (IMVS_XCH)
 _PACK_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
+def _pack_key(mod: nn.Module, device):
+    """Version / storage of every parameter AND buffer (BatchNorm running statistics are buffers): a change of any of
+    them -- optimizer step, load_state_dict, BN re-calibration, a broadcast -- invalidates the packed copy."""
+    named = list(mod.named_parameters()) + list(mod.named_buffers())
+    return (str(device),) + tuple((k, t._version, t.data_ptr()) for k, t in named)
+
+
+def invalidate_packs(root: nn.Module = None) -> None:
+    """Drop cached packed weights (all, or those of `root`'s submodules).  Needed only after writes that bypass
+    autograd's version counter (`tensor.data` assignment, raw pointer writes)."""
+    if root is None:
+        _PACK_CACHE.clear()
+        return
+    for m in root.modules():
+        _PACK_CACHE.pop(m, None)
+
+
 def _cached_pack(mod: nn.Module, device, build):
-    key = (str(device),) + tuple((k, p._version, p.data_ptr()) for k, p in mod.named_parameters())
+    key = _pack_key(mod, device)
     cache = _PACK_CACHE.get(mod)
     if cache is None:
         cache = {}
@@ -53,6 +70,10 @@ def _nhwc(x: Tensor) -> Tensor:
 
 def _nchw(x: Tensor) -> Tensor:
     return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _wants_grad(mod: nn.Module) -> bool:
+    return torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters())
 
 
 def _differentiable(mod: nn.Module) -> bool:
@@ -466,10 +487,6 @@ class IterMVS(nn.Module):
         depth / probability / confidence logit per update) -- as a FORWARD pass on the CUDA operators.  This is what
         train.py's validation loop (train.py:257, model.eval() under no_grad) and full_loss consume.  The inference
         kernels carry no gradient; the differentiable path is the train() mode (itermvs_b200/training.py)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "itermvs_b200.IterMVS(test=False).eval(): forward-only (validation) on the inference kernels -- call it "
-                "under torch.no_grad() as train.py's validate_sample does, or switch to .train() for the differentiable path")
         depths = {"combine": [], "probability": [], "initial": []}
         confidences, depths_upsampled, confidence_upsampled = [], [], None
         ref2 = ops._chk(ref_feature["level2"], "ref_feature")
@@ -506,7 +523,9 @@ class IterMVS(nn.Module):
         return depths, depths_upsampled, confidences, confidence_upsampled
 
     def forward(self, ref_feature, src_features, ref_proj, src_projs, depth_min, depth_max):
-        if not self.test and self.training:
+        # differentiable path: train() mode, or eval() with autograd on (fine-tuning with frozen BatchNorm statistics works in
+        # the reference; the modules of training.py follow `m.training`, so eval() uses running statistics there too)
+        if not self.test and (self.training or _wants_grad(self)):
             # itermvs.py:253-329 as train.py drives it: fused plane sweep with CUDA backward + torch autograd (training.py)
             from . import training
             levels = ("level1", "level2", "level3")

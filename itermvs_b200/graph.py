@@ -43,6 +43,14 @@ class GraphedPipeline:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.s_out = self._run()
         self.nan_flag = model._last_nan_flag
+        # the captured launches hold RAW pointers into the model's workspaces and packed weights: keep those objects alive
+        # for the life of the graph (a later forward at another shape / a repack replaces the model's cache entries,
+        # which would otherwise free the memory under the graph), and remember the weight versions to refuse stale replays
+        from . import estimator as _est
+        self._held = (model.feature_net._ws.get(workspace_slot), model.iter_mvs._workspaces.get(workspace_slot),
+                      model.feature_net._packed(dev), model.iter_mvs.packed(dev))
+        watched = [t for m in (model.feature_net, model.iter_mvs) for t in list(m.parameters()) + list(m.buffers())]
+        self._watch = (watched, [t._version for t in watched])      # ~10 us per replay to compare
 
     def _run(self):
         self.model.set_workspace_slot(self.workspace_slot)
@@ -59,9 +67,22 @@ class GraphedPipeline:
         self.s_dmin.copy_(depth_min, non_blocking=non_blocking)
         self.s_dmax.copy_(depth_max, non_blocking=non_blocking)
 
+    def weights_current(self) -> bool:
+        tensors, versions = self._watch
+        return all(t._version == v for t, v in zip(tensors, versions))
+
     def replay(self):
+        if not self.weights_current():
+            raise RuntimeError("GraphedPipeline: the model's parameters / buffers changed after capture (optimizer step, "
+                               "load_state_dict, BatchNorm update); the graph still reads the old packed weights -- re-capture")
         self.graph.replay()
         return self.s_out
+
+    def check_nan(self) -> None:
+        """The reference asserts 'nan in proj' on every warp (module.py:83,87); here one device flag per forward.
+        Synchronises the flag's stream; raises if a composed projection contained NaN in the last replay."""
+        if self.nan_flag is not None:
+            self.nan_flag.raise_if_set()
 
     def __call__(self, imgs, proj_matrices, depth_min, depth_max):
         self.load_inputs(imgs, proj_matrices, depth_min, depth_max)
@@ -135,7 +156,10 @@ class StreamingPipeline:
             self.ev_out[s].record(self.d2h)
         self.k += 1
 
-    def drain(self):
+    def drain(self, check_nan: bool = False):
         main = torch.cuda.current_stream(self.dev)
         for e in self.ev_out:
             main.wait_event(e)
+        if check_nan:            # the host is about to read the results anyway: surface the reference's 'nan in proj' assert
+            for slot in self.slots:
+                slot.check_nan()

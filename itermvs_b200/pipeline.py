@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from . import _lib
 from . import _pack
 from . import ops
-from .estimator import IterMVS, _cached_pack
+from .estimator import IterMVS, _cached_pack, _wants_grad
 
 Tensor = torch.Tensor
 
@@ -71,14 +71,15 @@ class FeatureNet(nn.Module):
         def build():
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             return _pack.PackedFeatureNet(sd, device)
-        # BN running statistics are buffers: include their versions in the cache key through a cheap proxy
+        # the cache key covers parameters and buffers (BatchNorm running statistics): estimator._pack_key
         return _cached_pack(self, device, build)
 
     def forward_nhwc(self, x: Tensor):
         """x [B,V,3,H,W] -> channels-last pyramids (fea1 [B,V,H/2,W/2,16], fea2 [...,32], fea3 [...,48])."""
         if self.training:
-            raise NotImplementedError("itermvs_b200.FeatureNet: BatchNorm in training mode (batch statistics) is not "
-                                      "built; call .eval() (the inference path of eval.py:126 does)")
+            raise NotImplementedError("itermvs_b200.FeatureNet.forward_nhwc is the inference kernel path (BatchNorm folded "
+                                      "with running statistics); in train() mode use Pipeline.forward, which runs "
+                                      "itermvs_b200/training.py (batch statistics, autograd)")
         x = ops._chk(x.float(), "imgs")
         b, v, c, h, w = x.shape
         assert c == 3
@@ -153,7 +154,7 @@ class Pipeline(nn.Module):
         x = imgs["level_0"]
         if not x.is_cuda:
             raise RuntimeError("itermvs_b200.Pipeline: inputs must be CUDA tensors (there is no CPU path)")
-        if self.training and not self.test:
+        if not self.test and (self.training or _wants_grad(self)):
             # train.py:205 (model.train(); BatchNorm batch statistics; gradients): fused plane sweep with its CUDA
             # backward + the convolution stacks under torch autograd -- itermvs_b200/training.py
             from . import training

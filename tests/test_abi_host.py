@@ -201,15 +201,17 @@ def test_full_loss_matches_reference_value(loss_kat):
     assert ups[0].grad.abs().sum() > 0 and conf[-1].grad.abs().sum() > 0
 
 
-def test_all_predictions_forward_refuses_autograd(dtu_weights):
-    """test=False in eval() mode is forward-only (the inference kernels): with trainable parameters and grad enabled
-    it must refuse, not silently detach.  train() mode is the differentiable path and, like every entry, insists on
-    CUDA tensors."""
+def test_differentiable_entry_insists_on_cuda(dtu_weights):
+    """test=False with trainable parameters and autograd on -- train() mode, or eval() as in fine-tuning with frozen
+    BatchNorm statistics (works in the reference) -- is the differentiable path (itermvs_b200/training.py) and, like
+    every entry, insists on CUDA tensors: there is no CPU fallback to fall into silently."""
     import itermvs_b200
     m = itermvs_b200.IterMVS(2, 32, 32, test=False).eval()
     x = {f"level{l}": torch.zeros(1, c, 8, 8) for l, c in ((1, 16), (2, 32), (3, 48))}
-    with pytest.raises(NotImplementedError):
-        m(x, {k: [] for k in x}, {}, {}, torch.ones(1), torch.ones(1))
+    srcs0 = {k: [v.clone()] for k, v in x.items()}
+    proj0 = {k: torch.eye(4)[None] for k in x}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(x, srcs0, proj0, {k: [v] for k, v in proj0.items()}, torch.ones(1), torch.ones(1))
     m.train()
     srcs = {k: [v.clone()] for k, v in x.items()}
     proj = {k: torch.eye(4)[None] for k in x}

@@ -320,9 +320,16 @@ def test_all_predictions_forward_matches_reference(dev, dtu_weights, e2e_allpred
                                         s["depth_min"].to(dev), s["depth_max"].to(dev)))
     print(f"all-predictions forward: loss {loss:.5f} (reference {float(fix['loss']):.5f})")
     assert abs(loss - float(fix["loss"])) < 2e-3 * float(fix["loss"])
-    # with trainable parameters and autograd enabled the forward-only path refuses
-    with pytest.raises(NotImplementedError):
-        m(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    # eval() with autograd on (fine-tuning with frozen BatchNorm statistics, as the reference allows) runs the
+    # differentiable path: same predictions as the forward-only kernels, and gradients reach the parameters
+    out_g = m(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    rel_g = ((out_g["depths_upsampled"][0] - out["depths_upsampled"][0]).abs() / out["depths_upsampled"][0]).median()
+    assert float(rel_g) < 1e-3, float(rel_g)          # cuDNN convolutions (possibly TF32) vs the fp32-grade kernels
+    itermvs_b200.full_loss(out_g["depths"], out_g["depths_upsampled"], out_g["confidences"], gt, mask,
+                           s["depth_min"].to(dev), s["depth_max"].to(dev)).backward()
+    gw = m.iter_mvs.update.gru.convz.weight.grad
+    assert gw is not None and torch.isfinite(gw).all() and float(gw.abs().sum()) > 0
+    m.zero_grad(set_to_none=True)
 
 
 def test_streaming_two_in_flight_is_race_free(dev, model):
@@ -372,6 +379,100 @@ def test_full_size_pipeline_vs_oracle(dev, model, dtu_weights):
     assert float((c - cref).abs().mean()) < 1e-4
 
 
+def _golden(name):
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_cfg2_matches_reference_fixture(dev, model):
+    """BASELINE configs[1] (640x512, 4 src, D=32, 4 iterations) against outputs of THE REFERENCE ITSELF
+    (tests/golden/make_golden_cfg.py -> e2e_cfg2.npz): the north star's bar -- every pixel of depth within 1e-3
+    relative -- asserted as a maximum, not a fraction."""
+    fix = _golden("e2e_cfg2.npz")
+    s = make_sample(640, 512, n_src=4, batch=1, seed=0, scene="plane")
+    chk = np.array([float(s["imgs"]["level_0"].double().sum()), float(s["imgs"]["level_0"].double().abs().sum())])
+    assert np.allclose(chk, fix["img_checksum"], rtol=1e-9), "synthetic generator drifted from the fixture's inputs"
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    with torch.no_grad():
+        out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    torch.cuda.synchronize()
+    d, c = out["depths_upsampled"].cpu().numpy(), out["confidence_upsampled"].cpu().numpy()
+    rel = np.abs(d - fix["depths_upsampled"]) / fix["depths_upsampled"]
+    cerr = np.abs(c - fix["confidence_upsampled"])
+    print(f"cfg2 vs reference: depth rel err max {rel.max():.2e} mean {rel.mean():.2e}; confidence abs err max {cerr.max():.2e}")
+    assert rel.max() < 1e-3, rel.max()
+    assert rel.mean() < 1e-6
+    assert cerr.max() < 1e-3, cerr.max()
+
+
+def test_cfg5_full_size_matches_reference_fixture(dev, dtu_weights):
+    """BASELINE configs[4] at FULL size (1920x1056, 7 source views, 4 iterations) against the reference itself
+    (e2e_cfg5.npz, every 4th pixel of every 4th row).  D=32 is the checkpoint's configuration: every sampled pixel
+    within 1e-3.  D=48 needs a re-created (random, stored) hidden_init_head[0]: the estimator then runs
+    outside its trained regime (the reference's own mean confidence is 0.06), arg-max bins of flat distributions flip
+    at fp32-reassociation level, so that case is median-tight with a bounded fraction of moved pixels."""
+    import itermvs_b200
+    fix = _golden("e2e_cfg5.npz")
+    s = make_sample(1920, 1056, n_src=7, batch=1, seed=3, scene="plane")
+    chk = np.array([float(s["imgs"]["level_0"].double().sum()), float(s["imgs"]["level_0"].double().abs().sum())])
+    assert np.allclose(chk, fix["img_checksum"], rtol=1e-9)
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    for D in (32, 48):
+        m = itermvs_b200.Pipeline(iteration=4, test=True)
+        sd = dict(dtu_weights)
+        if D != 32:
+            m.iter_mvs.update.hidden_init_head[0] = torch.nn.Conv2d(D, 64, 3, stride=1, padding=1, bias=False)
+            sd["iter_mvs.update.hidden_init_head.0.weight"] = T(fix[f"hidden_init_head0_d{D}"])
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev).eval()
+        with torch.no_grad():
+            out = m(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+        torch.cuda.synchronize()
+        m._last_nan_flag.raise_if_set()
+        d = out["depths_upsampled"].cpu().numpy()[..., ::4, ::4]
+        c = out["confidence_upsampled"].cpu().numpy()[..., ::4, ::4]
+        want_d, want_c = fix[f"depths_upsampled_d{D}"], fix[f"confidence_upsampled_d{D}"]
+        rel = np.abs(d - want_d) / want_d
+        cerr = np.abs(c - want_c)
+        print(f"cfg5 D={D} vs reference: depth rel err max {rel.max():.2e} median {np.median(rel):.2e}, px>1e-3 {100 * (rel > 1e-3).mean():.4f}%; "
+              f"confidence abs err max {cerr.max():.2e}")
+        if D == 32:
+            assert rel.max() < 1e-3, rel.max()
+            assert cerr.max() < 1e-3, cerr.max()
+        else:
+            assert np.median(rel) < 1e-5 and (rel > 1e-3).mean() < 0.2
+        del m
+        torch.cuda.empty_cache()
+
+
+def test_reference_itself_on_this_gpu(dev, model):
+    """The unmodified reference (baseline/_ref, tools/install_ref.py) executed on this GPU through its stock ATen/cuDNN
+    path (TF32 off, so that it is the fp32 computation its CPU path does) against this path, same inputs, at the
+    benchmark configuration: every pixel within 1e-3."""
+    from oracle import reference_arm as RA
+    if not RA.available():
+        pytest.skip(RA.why_unavailable())
+    ref = RA.load_pipeline(iteration=4).to(dev)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        s = make_sample(640, 512, n_src=4, batch=1, seed=5, scene="plane")
+        cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+        with torch.no_grad():
+            want = ref(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+            out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    rel = ((out["depths_upsampled"] - want["depths_upsampled"]).abs() / want["depths_upsampled"])
+    cerr = (out["confidence_upsampled"] - want["confidence_upsampled"]).abs()
+    print(f"reference on this GPU (fp32 cuDNN) vs this path: depth rel err max {float(rel.max()):.2e} mean {float(rel.mean()):.2e}; "
+          f"confidence abs err max {float(cerr.max()):.2e}")
+    assert float(rel.max()) < 1e-3 and float(cerr.max()) < 1e-3
+
+
 def test_size_independent_properties(dev, model):
     """Properties that hold at any size: (1) batch elements are independent (replicas) -- a batch of two
     different scenes equals the two run alone, bit for bit; (2) all outputs are finite and inside
@@ -387,8 +488,11 @@ def test_size_independent_properties(dev, model):
             one = model({k: v[b:b + 1].to(dev) for k, v in s2["imgs"].items()},
                         {k: v[b:b + 1].to(dev) for k, v in s2["proj_matrices"].items()},
                         s2["depth_min"][b:b + 1].to(dev), s2["depth_max"][b:b + 1].to(dev))
-            # FeatureNet runs on cuDNN whose algorithm choice may depend on batch size -> allow fp32 noise there
-            assert _frac_bad(one["depths_upsampled"], both["depths_upsampled"][b:b + 1].cpu().numpy(), 1e-3) < 5e-3
+            # every kernel tiles per image and reduces in a fixed order: a batch element is bit-identical to itself alone
+            nd_ = int((one["depths_upsampled"] != both["depths_upsampled"][b:b + 1]).sum())
+            print(f"batch element {b}: {nd_} of {one['depths_upsampled'].numel()} depth values differ from the batch-of-one run")
+            assert torch.equal(one["depths_upsampled"], both["depths_upsampled"][b:b + 1])
+            assert torch.equal(one["confidence_upsampled"], both["confidence_upsampled"][b:b + 1])
     d = both["depths_upsampled"]
     assert torch.isfinite(d).all() and float(d.min()) >= 425.0 - 1e-2 and float(d.max()) <= 935.0 + 1e-2
     c = both["confidence_upsampled"]
