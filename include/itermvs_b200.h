@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IMVS_ABI_VERSION 3
+#define IMVS_ABI_VERSION 4
 #define IMVS_GROUPS 8          /* reference models/itermvs.py:28 */
 #define IMVS_OUT_BINS 256      /* reference models/itermvs.py:134 */
 #define IMVS_RADIUS 4          /* reference models/itermvs.py:135 */
@@ -109,6 +109,10 @@ typedef struct imvs_weights {
     /* iter_mvs.upsample (itermvs.py:246-250) */
     imvs_wpair ups_conv0;          /* [9][32][64] */
     const float* ups_fc;           /* [64][144] (fp32) */
+    /* depth_head.2 / depth_head.4 (+ bias) for the fused tcgen05 head (csrc/headfused.cuh): fp16 hi / lo split in the UMMA
+     * K-major canonical order [K/8][N][8 halves]: W1 hi | W1 lo (K = 32, N = 64) | W2 hi | W2 lo (K = 80: 64 inputs, the
+     * bias as row 64, zeros; N = 256) = 90 112 bytes, 16-byte aligned.  May be NULL: then the unfused kernels run. */
+    const void* head_fused;
 } imvs_weights;
 
 /* ------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ _lib = None
 vp = C.c_void_p
 ci = C.c_int
 sz = C.c_size_t
-ABI_VERSION = 3
+ABI_VERSION = 4
 FNET_CONVS = 24
 
 
@@ -37,7 +37,7 @@ class Weights(C.Structure):
                 ("head_conv0", WPair), ("head_fc1", WPair), ("head_fc2", WPair), ("head_fc2_b", vp),
                 ("conf_fc", vp), ("conf_fc_b", vp),
                 ("hinit_conv0", WPair), ("hinit_fc", WPair), ("hinit_fc_b", vp),
-                ("ups_conv0", WPair), ("ups_fc", vp)]
+                ("ups_conv0", WPair), ("ups_fc", vp), ("head_fused", vp)]
 
 
 class Problem(C.Structure):

@@ -95,6 +95,35 @@ def pack_fc(w: Tensor) -> Tensor:
     return w.detach().float().reshape(w.shape[0], w.shape[1]).t().contiguous()
 
 
+def _split_f16(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """x = hi + lo with hi = fp16(x) (saturating), lo = fp16(x - hi): the kernels' cvt.rn.satfinite split."""
+    hi = x.clamp(-65504.0, 65504.0).half()
+    lo = (x - hi.float()).clamp(-65504.0, 65504.0).half()
+    return hi, lo
+
+
+def _umma_kmajor(w_nk: Tensor) -> Tensor:
+    """[N][K] fp16 (K a multiple of 8) -> the tcgen05 K-major / no-swizzle canonical order [K/8][N][8]."""
+    n, k = w_nk.shape
+    return w_nk.reshape(n, k // 8, 8).permute(1, 0, 2).contiguous()
+
+
+def pack_head_fused(fc1_w: Tensor, fc2_w: Tensor, fc2_b: Tensor) -> Tensor:
+    """depth_head.2.weight [64,32,1,1], depth_head.4.weight [256,64,1,1] + bias [256] -> the byte blob of
+    csrc/headfused.cuh: W1 hi | W1 lo | W2 hi | W2 lo, W2 extended to K = 80 with the bias as input row 64."""
+    w1 = fc1_w.detach().float().reshape(64, 32)
+    w2 = torch.zeros(256, 80, device=fc2_w.device, dtype=torch.float32)
+    w2[:, :64] = fc2_w.detach().float().reshape(256, 64)
+    w2[:, 64] = fc2_b.detach().float()
+    parts = []
+    for w in (w1, w2):
+        hi, lo = _split_f16(w)
+        parts += [_umma_kmajor(hi).reshape(-1), _umma_kmajor(lo).reshape(-1)]
+    blob = torch.cat(parts).contiguous()
+    assert blob.numel() * 2 == 90112
+    return blob
+
+
 def _vec(t: Tensor) -> Tensor:
     return t.detach().float().reshape(-1).contiguous()
 
@@ -149,6 +178,7 @@ def fill_update(h: _Holder, s: _lib.Weights, sd, prefix, dev) -> None:
     s.head_fc1 = h.pair(pack_mma_conv(g("depth_head.2.weight")))
     s.head_fc2 = h.pair(pack_mma_conv(g("depth_head.4.weight")))
     s.head_fc2_b = h.ptr(_vec(g("depth_head.4.bias")))
+    s.head_fused = h.ptr(pack_head_fused(g("depth_head.2.weight"), g("depth_head.4.weight"), g("depth_head.4.bias")))
     s.conf_fc = h.ptr(_vec(g("confidence_head.2.weight")))
     s.conf_fc_b = h.ptr(_vec(g("confidence_head.2.bias")))
     s.hinit_conv0 = h.pair(pack_mma_conv(g("hidden_init_head.0.weight")))

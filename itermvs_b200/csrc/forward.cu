@@ -69,7 +69,9 @@ extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
 
 extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     if (check_problem(pb) != 0) return -1;
-    return 24 + 13 * pb->iterations;
+    // the depth head is 2 launches (conv0 + the fused tcgen05 kernel) in the default fp32-grade mode, 4 otherwise
+    const int head = (conv_passes() == 4 && tune("HEADFUSED", 1)) ? 2 : 4;
+    return 20 + head + (9 + head) * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,

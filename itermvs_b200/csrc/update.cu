@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "mmaconv.cuh"
 #include "tc5conv.cuh"
+#include "headfused.cuh"
 
 namespace imvs {
 
@@ -253,6 +254,22 @@ extern "C" int imvs_depth_head(const imvs_weights* w, const float* hidden, float
                                                            conv_tables(3, 1, 2, 8), B, 64, H, W, nc, st)));
         }
     }
+    // fp32-grade mode without a probability output (test mode): fc1 + fc2 + softmax / arg-max / window regression (+ the
+    // confidence 1x1) as ONE tcgen05 kernel -- logits and the fc1 activation stay in TMEM / shared memory
+#ifndef CUSIM        // (the CPU emulation of the test-suite has no tensor-core / TMEM model: it runs the unfused kernels)
+    if (conv_passes() == 4 && !probability && w->head_fused && tune("HEADFUSED", 1)) {
+        hf::Params hp;
+        hp.t = t; hp.blob = w->head_fused; hp.conf_w = w->conf_fc; hp.conf_b = w->conf_fc_b;
+        hp.nd_out = nd_out; hp.nd_bstride = nd_batch_stride; hp.nd_pstride = nd_pixel_stride;
+        hp.conf = conf; hp.conf_logit = conf_logit; hp.depth_out = depth_out;
+        hp.depth_min = depth_min; hp.depth_max = depth_max;
+        hp.n_px = (int)((size_t)B * P); hp.P = (int)P;
+        hp.err_flag = tc5_error_flag();
+        IMVS_REQUIRE((size_t)B * P < 2147483647ull, "depth_head: too many pixels");
+        IMVS_REQUIRE((reinterpret_cast<uintptr_t>(w->head_fused) & 15u) == 0, "depth_head: head_fused blob must be 16-byte aligned");
+        return hf::launch(hp, st);
+    }
+#endif
     {
         const EpiNHWC e1{h1, nullptr, nullptr, H, W, 64, 64, 1};
         const EpiNHWC e2{logits, w->head_fc2_b, nullptr, H, W, 256, 256, 0};

@@ -134,6 +134,19 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     for (int l = 0; l < 32; ++l) r |= (cusim_shfl_<unsigned>(pred ? 1u : 0u, l) & 1u) << l;
     return r;
 }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __reduce_min_sync(unsigned mask, int v) {
+    if (mask != 0xffffffffu) cusim::die("__reduce_min_sync with a partial mask");
+    int r = v;
+    for (int l = 0; l < 32; ++l) { const int o = cusim_shfl_<int>(v, l); r = o < r ? o : r; }
+    return r;
+}
+static inline int __reduce_max_sync(unsigned mask, int v) {
+    if (mask != 0xffffffffu) cusim::die("__reduce_max_sync with a partial mask");
+    int r = v;
+    for (int l = 0; l < 32; ++l) { const int o = cusim_shfl_<int>(v, l); r = o > r ? o : r; }
+    return r;
+}
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
 

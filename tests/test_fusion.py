@@ -48,6 +48,7 @@ def test_cuda_check_geometric_consistency(fusion_kat):
         flips += int(diff.sum())
         same = ~diff
         assert np.allclose(rep[same], z[f"reprojected{v}"][same], rtol=2e-6, atol=1e-4)
+    print(f"geometric consistency: {flips} mask flips over {len(depths)} views")
     assert flips <= 3, flips
     # CUDA tensors in -> CUDA tensors out
     dev = torch.device("cuda:0")
@@ -64,6 +65,7 @@ def test_cuda_filter_depth_view(fusion_kat):
     avg, pm, gm, fm = filter_depth_view(z["depth0"], z["confidence"], z["K0"], z["E0"], depths, ks, es, 1.0, 0.01, 0.3, 3)
     assert avg.dtype == np.float64
     assert np.array_equal(pm, z["photo_mask"])
+    print(f"filter_depth_view: geo mask flips {int((gm != z['geo_mask']).sum())}, final mask flips {int((fm != z['final_mask']).sum())}")
     assert int((gm != z["geo_mask"]).sum()) <= 2 and int((fm != z["final_mask"]).sum()) <= 2
     same = gm == z["geo_mask"]
     with np.errstate(invalid="ignore"):
