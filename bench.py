@@ -40,6 +40,36 @@ import torch  # noqa: E402
 
 W_IMG, H_IMG, N_SRC, D_HYP, ITERS = 640, 512, 4, 32, 4
 METRIC = "reference-views/sec at 640x512, 4 src, D=32, 4 iters"
+CONFIG_NAME = "BASELINE configs[1]"
+CONFIGS = {        # BASELINE.json configs by index: (W, H, source views, D, iterations)
+    1: (640, 512, 4, 32, 4),         # configs[1]: the metric's configuration (default; the only driver line)
+    4: (1920, 1056, 7, 48, 4),       # configs[4]: Tanks&Temples-shape memory / throughput stress (--config 4)
+}
+
+
+def set_config(idx):
+    global W_IMG, H_IMG, N_SRC, D_HYP, ITERS, METRIC, CONFIG_NAME
+    W_IMG, H_IMG, N_SRC, D_HYP, ITERS = CONFIGS[idx]
+    METRIC = f"reference-views/sec at {W_IMG}x{H_IMG}, {N_SRC} src, D={D_HYP}, {ITERS} iters"
+    CONFIG_NAME = f"BASELINE configs[{idx}]"
+
+
+def hidden_init_weight(d):
+    """D is hard-coded to 32 in the reference (itermvs.py:237); for D != 32 hidden_init_head[0] is re-created with D input
+    channels under a fixed seed (SURVEY 8c recipe) -- the same tensor for this path and for the reference arm."""
+    g = torch.Generator().manual_seed(0)
+    return (torch.rand(64, d, 3, 3, generator=g) * 2 - 1) * (1.0 / (d * 9)) ** 0.5
+
+
+def build_model(test=True):
+    import itermvs_b200
+    model = itermvs_b200.Pipeline(iteration=ITERS, test=test)
+    sd = load_weights()
+    if D_HYP != 32:
+        model.iter_mvs.update.hidden_init_head[0] = torch.nn.Conv2d(D_HYP, 64, 3, stride=1, padding=1, bias=False)
+        sd["iter_mvs.update.hidden_init_head.0.weight"] = hidden_init_weight(D_HYP)
+    model.load_state_dict(sd, strict=True)
+    return model
 HBM_FALLBACK_GBS = 6650.0
 NROT = 8          # device-resident input sets the timed loop rotates over (8 x 19.7 MB > the 126 MB L2)
 
@@ -142,7 +172,11 @@ def reference_runner(device="cpu"):
     from oracle import reference_arm as RA
     s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=0, scene="plane")
     if RA.available():
-        m = RA.load_pipeline(iteration=ITERS).to(device)
+        m = RA.load_pipeline(iteration=ITERS, num_sample=D_HYP)
+        if D_HYP != 32:
+            with torch.no_grad():
+                m.iter_mvs.update.hidden_init_head[0].weight.copy_(hidden_init_weight(D_HYP))
+        m = m.to(device)
         imgs = {k: v.to(device) for k, v in s["imgs"].items()}
         proj = {k: v.to(device) for k, v in s["proj_matrices"].items()}
         dmin, dmax = s["depth_min"].to(device), s["depth_max"].to(device)
@@ -153,7 +187,10 @@ def reference_runner(device="cpu"):
         return run, "reference", ("the unmodified reference (baseline/_ref: models/net.py Pipeline(test=True), DTU checkpoint) "
                                   "through its own public API")
     from oracle import itermvs_oracle as O
-    weights = {k: v.to(device) for k, v in load_weights().items()}
+    weights = load_weights()
+    if D_HYP != 32:
+        weights["iter_mvs.update.hidden_init_head.0.weight"] = hidden_init_weight(D_HYP)
+    weights = {k: v.to(device) for k, v in weights.items()}
     imgs = {k: v.to(device) for k, v in s["imgs"].items()}
     proj = {k: v.to(device) for k, v in s["proj_matrices"].items()}
     dmin, dmax = s["depth_min"].to(device), s["depth_max"].to(device)
@@ -179,7 +216,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "refs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 (BASELINE configs[1])",
+        "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 ({CONFIG_NAME})",
                    "note": note + "; torch CPU fp32, thread count probed over 8/16/32"},
         "cpu_baseline": {"value": v, "unit": "refs/s", "cores": cores, "kind": kind, "host_cpus": os.cpu_count(),
                          "sample": f"{args.steps} full forward passes of the workload"},
@@ -292,7 +329,11 @@ def main():
                     help="infer (default) = the headline metric; train = BASELINE configs[3]: training steps with the "
                          "flat-bucket gradient all-reduce (not a driver line; see run_train)")
     ap.add_argument("--train-bf16-wire", action="store_true", help="train mode: all-reduce the gradient bucket in bf16")
+    ap.add_argument("--no-u8", action="store_true", help="skip the extra e2e leg with uint8 images")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs index: 1 = the metric's configuration (default), 4 = 1920x1056 / 7 src / D=48 stress")
     args = ap.parse_args()
+    set_config(args.config)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", 0))
@@ -319,10 +360,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_conv_passes(args.passes)
 
-    weights = load_weights()
-    model = itermvs_b200.Pipeline(iteration=ITERS, test=True)
-    model.load_state_dict(weights, strict=True)
-    model = model.to(dev).eval()
+    model = build_model(test=True).to(dev).eval()
     s = make_sample(W_IMG, H_IMG, n_src=N_SRC, batch=1, seed=rank, scene="plane")   # one reference view per GPU
     host = {"imgs": {"level_0": s["imgs"]["level_0"].pin_memory()},
             "proj": {k: s["proj_matrices"][k].float().pin_memory() for k in ("level_1", "level_2", "level_3")},
@@ -472,14 +510,39 @@ def main():
             b.record()
         barrier()
         e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    # ---- the same serving loop fed with the raw 8-bit images (f-4: the first FeatureNet layer normalises x / 255. as the
+    #      reference's loaders do): a quarter of the H2D bytes per step.  Extra line, the contract's `e2e` stays fp32 images.
+    e2e_u8 = None
+    if sp is not None and not args.no_u8:
+        u8 = ((host["imgs"]["level_0"] + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).pin_memory()
+        sp8 = StreamingPipeline(model, {"level_0": u8.to(dev)}, d_proj, d_dmin, d_dmax, n_slots=sp.n, concurrent=sp.n > 1)
+        h8 = {"level_0": u8}
+        for k in range(2 * sp8.n):
+            sp8.submit(h8, host["proj"], host["dmin"], host["dmax"], *outs[k % sp8.n])
+        sp8.drain()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(args.steps):
+            sp8.submit(h8, host["proj"], host["dmin"], host["dmax"], *outs[k % sp8.n])
+        sp8.drain()
+        e1.record()
+        barrier()
+        e2e_u8 = {"ms": e0.elapsed_time(e1), "h2d_bytes_per_step": u8.numel() + sum(v.numel() * 4 for v in host["proj"].values()) + 8}
+        del sp8
     clk = clocks.stop()
 
     # replicas: every rank processed `steps` reference views; whole-job rate = all units / slowest rank
     from itermvs_b200 import replicas
     value = replicas.aggregate_throughput(args.steps, total_ms, device=dev)
     e2e_value = replicas.aggregate_throughput(args.steps, e2e_ms, device=dev)
+    if e2e_u8 is not None:
+        e2e_u8["value"] = replicas.aggregate_throughput(args.steps, e2e_u8.pop("ms"), device=dev)
     total_ms = replicas.max_over_ranks([total_ms], device=dev)[0]
 
+    mem_ours = torch.cuda.max_memory_allocated(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+    mem_held = torch.cuda.memory_allocated(dev)          # this path's live tensors stay allocated while the reference runs
     # ---- CPU baseline: the reference itself (baseline/_ref) on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -528,6 +591,7 @@ def main():
                       "note": "reference runs cuDNN with torch's default TF32 convolutions here; this path is fp32-grade"}
         gpu_stock = {"value": reps / (sum(ms) / 1000.0), "unit": "refs/s", "kind": kind_g, "reps": reps,
                      "ms_median": statistics.median(ms), "ms_min": ms[0], "wall_refs_per_s": reps / wall, "parity": parity,
+                     "max_allocated_MB": (torch.cuda.max_memory_allocated(dev) - mem_held) / 1e6,
                      "what": note_g + " on this GPU: .cuda(), cudnn.benchmark=True (eval.py:21), torch default TF32 flags, "
                              "device-resident inputs, CUDA events around each forward"}
 
@@ -557,7 +621,7 @@ def main():
         "dtype": {4: "f32 (fp32-grade tensor-core convolutions: 3-product FP16 hi/lo split, fp32 accumulate; sampling/softmax/regression fp32)",
                   3: "f32 (3xTF32 tensor-core convolutions, fp32 accumulate; sampling/softmax/regression fp32)",
                   1: "tf32 (single-pass TF32 tensor-core convolutions, fp32 accumulate; rest fp32)"}[args.passes], "data": "synthetic",
-        "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 per GPU (BASELINE configs[1])",
+        "config": {"workload": f"{W_IMG}x{H_IMG}, {N_SRC} src views, D={D_HYP}, {ITERS} iters, batch 1 per GPU ({CONFIG_NAME})",
                    "step": "Pipeline.forward test mode: FeatureNet + estimator, all in hand-written sm_100a kernels (no cuDNN/cuBLAS)",
                    "launch": "eager" if graphed is None else "cuda-graph replay",
                    "in_flight": (sp.n if sp is not None else 1),
@@ -576,9 +640,17 @@ def main():
                      "avg_launch_ms": mean_iter_ms, "launches_timed": len(iter_ms),
                      "init_kernel": {"algorithmic_bytes": init_b, "avg_launch_ms": statistics.mean(init_ms) if init_ms else None}},
         "stage_ms": breakdown,
+        "memory": {"max_allocated_MB": mem_ours / 1e6,
+                   "what": "torch.cuda.max_memory_allocated up to the end of this path's timed regions: weights, the caller-owned "
+                           "workspaces of all in-flight slots (FeatureNet + estimator), the rotating input sets, outputs"},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
         "wall_s_timed_region": t_wall,
     }
+    if e2e_u8 is not None:
+        line["e2e_uint8_images"] = {"value": e2e_u8["value"], "unit": "refs/s", "h2d_bytes_per_step": e2e_u8["h2d_bytes_per_step"],
+                                    "d2h_bytes_per_step": d2h,
+                                    "what": "the e2e loop fed with raw 8-bit images from pinned host memory; x / 255. (the loaders' normalisation, "
+                                            "dtu_yao_eval.py:56-59) happens in the first FeatureNet kernel"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if gpu_stock is not None:

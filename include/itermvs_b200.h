@@ -71,6 +71,9 @@ typedef struct imvs_wpair {      /* packed conv weight [tap][CinP][CoutP] */
                                     with NB = min(CoutP, 64); may be NULL (then the mma.sync kernels run) */
     const void* f16x3;           /* fp16 hi/lo split for mode 4: [tap][CinK/2][CoutP] of 8-byte entries
                                     {half2 hi(k, k+1), half2 lo(k, k+1)}, CinK = CinP rounded up to 16 (zeros) */
+    const void* f16umma;         /* fp16 hi/lo split in the tcgen05 K-major canonical order (mode 4 on the 5th-generation
+                                    tensor core, csrc/tc5conv.cuh:tc5h_conv_kernel): [tap][hi | lo][CinK/8][CoutP][8 halves];
+                                    NULL when the shape is not served (CoutP % 16 != 0 or CoutP > 64) */
 } imvs_wpair;
 
 typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */
@@ -110,8 +113,8 @@ typedef struct imvs_weights {
     imvs_wpair ups_conv0;          /* [9][32][64] */
     const float* ups_fc;           /* [64][144] (fp32) */
     /* depth_head.2 / depth_head.4 (+ bias) for the fused tcgen05 head (csrc/headfused.cuh): fp16 hi / lo split in the UMMA
-     * K-major canonical order [K/8][N][8 halves]: W1 hi | W1 lo (K = 32, N = 64) | W2 hi | W2 lo (K = 80: 64 inputs, the
-     * bias as row 64, zeros; N = 256) = 90 112 bytes, 16-byte aligned.  May be NULL: then the unfused kernels run. */
+     * K-major canonical order [K/8][N][8 halves]: W1 hi | W1 lo (K = 32, N = 64) | W2 hi | W2 lo (K = 64, N = 256), then
+     * the fp32 bias [256] = 74 752 bytes, 16-byte aligned.  May be NULL: then the unfused kernels run. */
     const void* head_fused;
 } imvs_weights;
 
@@ -305,6 +308,10 @@ typedef struct imvs_featurenet_weights {
 size_t imvs_featurenet_workspace_bytes(int N, int H, int W);
 int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs, float* fea1, float* fea2, float* fea3,
                             void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream);
+/* Same with the raw 8-bit images [N][3][H][W]: the first layer normalises them as the reference's loaders do
+ * (np.array(img, dtype=np.float32) / 255., datasets/dtu_yao_eval.py:56-59) -- f-4: a quarter of the host-to-device bytes. */
+int imvs_featurenet_forward_u8(const imvs_featurenet_weights* w, const unsigned char* imgs, float* fea1, float* fea2, float* fea3,
+                               void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream);
 int imvs_featurenet_launch_count(void);
 
 /* profiling taps (bench.py): CUDA-event pair around every stage of the two forward functions */

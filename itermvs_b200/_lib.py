@@ -23,7 +23,7 @@ FNET_CONVS = 24
 
 
 class WPair(C.Structure):
-    _fields_ = [("tf32", vp), ("fp32", vp), ("umma", vp), ("f16x3", vp)]
+    _fields_ = [("tf32", vp), ("fp32", vp), ("umma", vp), ("f16x3", vp), ("f16umma", vp)]
 
 
 class CorrNetWeights(C.Structure):
@@ -84,6 +84,7 @@ _SIGNATURES = {
                                   vp, sz, vp, vp, vp, vp, vp, vp]),
     "imvs_featurenet_workspace_bytes": (sz, [ci, ci, ci]),
     "imvs_featurenet_forward": (ci, [C.POINTER(FeatureNetWeights), vp, vp, vp, vp, vp, sz, ci, ci, ci, vp]),
+    "imvs_featurenet_forward_u8": (ci, [C.POINTER(FeatureNetWeights), vp, vp, vp, vp, vp, sz, ci, ci, ci, vp]),
     "imvs_featurenet_launch_count": (ci, []),
 }
 

@@ -67,9 +67,27 @@ def pack_f16x3(w: Tensor) -> Tensor:
     return torch.stack([pairs(hi), pairs(lo)], dim=-1).contiguous()
 
 
+def pack_umma_f16(w: Tensor):
+    """[tap][CinP][CoutP] fp32 -> fp16 hi / lo in the tcgen05 K-major canonical order [tap][hi | lo][CinK/8][CoutP][8 halves]
+    (element (n, k) of a tap at ((k/8) * CoutP + n) * 16 B + (k%8) * 2 B), CinK = CinP rounded up to 16."""
+    taps, cinp, coutp = w.shape
+    if coutp % 16 != 0 or coutp > 64:
+        return None
+    cink = (cinp + 15) // 16 * 16
+    x = torch.zeros(taps, cink, coutp, device=w.device, dtype=torch.float32)
+    x[:, :cinp] = w
+    hi = x.clamp(-65504.0, 65504.0).half()
+    lo = (x - hi.float()).clamp(-65504.0, 65504.0).half()
+
+    def canon(h):    # [tap][CinK][CoutP] -> [tap][CinK/8][CoutP][8]
+        return h.reshape(taps, cink // 8, 8, coutp).permute(0, 1, 3, 2)
+
+    return torch.stack([canon(hi), canon(lo)], dim=1).contiguous()
+
+
 def _packs(out: Tensor):
     t, f = split_tf32(out)
-    return t, f, pack_umma(t), pack_f16x3(f)
+    return t, f, pack_umma(t), pack_f16x3(f), pack_umma_f16(f)
 
 
 def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0):
@@ -110,17 +128,16 @@ def _umma_kmajor(w_nk: Tensor) -> Tensor:
 
 def pack_head_fused(fc1_w: Tensor, fc2_w: Tensor, fc2_b: Tensor) -> Tensor:
     """depth_head.2.weight [64,32,1,1], depth_head.4.weight [256,64,1,1] + bias [256] -> the byte blob of
-    csrc/headfused.cuh: W1 hi | W1 lo | W2 hi | W2 lo, W2 extended to K = 80 with the bias as input row 64."""
+    csrc/headfused.cuh: W1 hi | W1 lo | W2 hi | W2 lo (fp16, UMMA canonical order) | bias (fp32)."""
     w1 = fc1_w.detach().float().reshape(64, 32)
-    w2 = torch.zeros(256, 80, device=fc2_w.device, dtype=torch.float32)
-    w2[:, :64] = fc2_w.detach().float().reshape(256, 64)
-    w2[:, 64] = fc2_b.detach().float()
+    w2 = fc2_w.detach().float().reshape(256, 64)
     parts = []
     for w in (w1, w2):
         hi, lo = _split_f16(w)
-        parts += [_umma_kmajor(hi).reshape(-1), _umma_kmajor(lo).reshape(-1)]
+        parts += [_umma_kmajor(hi).reshape(-1).view(torch.uint8), _umma_kmajor(lo).reshape(-1).view(torch.uint8)]
+    parts.append(fc2_b.detach().float().contiguous().view(torch.uint8))
     blob = torch.cat(parts).contiguous()
-    assert blob.numel() * 2 == 90112
+    assert blob.numel() == 74752
     return blob
 
 
@@ -136,8 +153,9 @@ class _Holder:
         self.keep = []
 
     def pair(self, hl) -> _lib.WPair:
-        self.keep.extend(hl)
-        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if hl[2] is not None else None, hl[3].data_ptr())
+        self.keep.extend(t for t in hl if t is not None)
+        return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if hl[2] is not None else None, hl[3].data_ptr(),
+                          hl[4].data_ptr() if hl[4] is not None else None)
 
     def ptr(self, t: Tensor) -> int:
         self.keep.append(t)

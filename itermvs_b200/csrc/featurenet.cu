@@ -5,6 +5,7 @@
 // (no transposes).  All views of all reference views run as one batch (net.py:56-65 loops).
 #include "common.cuh"
 #include "mmaconv.cuh"
+#include "tc5conv.cuh"
 
 namespace imvs {
 
@@ -64,9 +65,14 @@ struct EpiSplit2 {
 // time staging zeros (112 us at 5 x 640 x 512).  Here it is exact fp32 FFMA: a 32 x 8-pixel tile per
 // 128-thread block, the three image planes with halo in shared memory, each thread two vertically adjacent
 // pixels x 8 output channels (432 FFMA per 12 image + 54 broadcast weight LDS).
+// PixT = float: the image as the reference's loaders deliver it; PixT = unsigned char: the raw 8-bit image, normalised here
+// exactly as the loaders do (np.array(img, float32) / 255., datasets/dtu_yao_eval.py:56-59) -- a quarter of the H2D bytes.
 constexpr int C0_TW = 32, C0_TH = 8, C0_PITCH = C0_TW + 2;
+__device__ __forceinline__ float c0_pixel(const float* p) { return ldg(p); }
+__device__ __forceinline__ float c0_pixel(const unsigned char* p) { return (float)__ldg(p) / 255.0f; }
+template <class PixT>
 __global__ void __launch_bounds__(128)
-fnet_conv0_kernel(const float* __restrict__ img, const float* __restrict__ wgt, const float* __restrict__ bias,
+fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, const float* __restrict__ bias,
                   float* __restrict__ out, int H, int W) {
     __shared__ float sI[3][C0_TH + 2][C0_PITCH];
     __shared__ __align__(16) float sW[27][8];       // [(ky*3 + kx)*3 + cin][cout]
@@ -81,12 +87,12 @@ fnet_conv0_kernel(const float* __restrict__ img, const float* __restrict__ wgt, 
     if (tid < 8) sB[tid] = ldg(bias + tid);
     pdl_wait();
     const size_t plane = (size_t)H * W;
-    const float* src = img + (size_t)n * 3 * plane;
+    const PixT* src = img + (size_t)n * 3 * plane;
     for (int i = tid; i < 3 * (C0_TH + 2) * C0_PITCH; i += 128) {
         const int c = i / ((C0_TH + 2) * C0_PITCH), rem = i % ((C0_TH + 2) * C0_PITCH);
         const int r = rem / C0_PITCH, col = rem % C0_PITCH;
         const int y = y0 - 1 + r, x = x0 - 1 + col;
-        sI[c][r][col] = (y >= 0 && y < H && x >= 0 && x < W) ? ldg(src + c * plane + (size_t)y * W + x) : 0.f;
+        sI[c][r][col] = (y >= 0 && y < H && x >= 0 && x < W) ? c0_pixel(src + c * plane + (size_t)y * W + x) : 0.f;
     }
     __syncthreads();
     const int tx = tid & 31, ty = tid >> 5;
@@ -147,6 +153,20 @@ static FnetBuffers fnet_carve(float* base, size_t N, size_t H, size_t W) {
     return b;
 }
 
+// Stride-1 3x3 convolution CI -> CO (bias, optional residual, optional ReLU), NHWC.  Default (fp32-grade mode 4): the
+// tcgen05 kernel with the fp16 hi/lo 3-product split (tc5conv.cuh:tc5h_conv_kernel); otherwise / under the CPU emulation
+// of the test-suite the mma.sync engine with the tile shape passed in.
+template <int CI, int CO, class Fallback>
+static int conv3x3_s1(const char* name, const imvs_wpair& wp, const float* bias, const float* x, float* out, const float* residual,
+                      int relu, int N, int H, int W, cudaStream_t st, Fallback&& fallback) {
+#ifndef CUSIM
+    if (conv_passes() == 4 && wp.f16umma && tune("TC5H", 1))
+        return tc5::launch_h<CI, CO>(name, in_nhwc(x, H, W, CI), tc5::PixNHWC{out, bias, residual, H, W, CO, relu}, wp.f16umma, 3, 1, N,
+                                     H, W, tc5_error_flag(), st);
+#endif
+    return fallback();
+}
+
 // one residual stage (two ResidualBlocks, module.py:32-50):  x [Hin][Win][CI] -> buf[3] [Hin/2][Win/2][CO]
 // NBA / NBB: cout block of the stride-2 [conv1 | downsample] GEMM / of the CO -> CO convolutions; MT: row-tiles per warp
 template <int CI, int CO, bool WALL_A, bool WALL_B, int NBA = 2 * CO, int NBB = CO, int MT = 2, int WARPS = 4>
@@ -160,13 +180,16 @@ static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, fl
     IMVS_TRY((mma_conv<CI, NBA, MT, WARPS, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
                                                   EpiSplit2{buf[0], buf[1], w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO,
                                                   H, W, NCA, st)));
-    IMVS_TRY((mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
-                                                  WSets::single(w->w[L + 1]), s1, N, CO, H, W, NCB, st)));
+    IMVS_TRY((conv3x3_s1<CO, CO>("fnet.block0.conv2", w->w[L + 1], w->b[L + 1], buf[0], buf[2], buf[1], 1, N, H, W, st, [&] {
+        return mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block0.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[2], w->b[L + 1], buf[1], H, W, CO, CO, 1},
+                                                       WSets::single(w->w[L + 1]), s1, N, CO, H, W, NCB, st); })));
     // block 1: conv1 relu, conv2 + x -> relu
-    IMVS_TRY((mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
-                                                  WSets::single(w->w[L + 3]), s1, N, CO, H, W, NCB, st)));
-    IMVS_TRY((mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
-                                                  WSets::single(w->w[L + 4]), s1, N, CO, H, W, NCB, st)));
+    IMVS_TRY((conv3x3_s1<CO, CO>("fnet.block1.conv1", w->w[L + 3], w->b[L + 3], buf[2], buf[0], nullptr, 1, N, H, W, st, [&] {
+        return mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block1.conv1", in_nhwc(buf[2], H, W, CO), EpiNHWC{buf[0], w->b[L + 3], nullptr, H, W, CO, CO, 1},
+                                                       WSets::single(w->w[L + 3]), s1, N, CO, H, W, NCB, st); })));
+    IMVS_TRY((conv3x3_s1<CO, CO>("fnet.block1.conv2", w->w[L + 4], w->b[L + 4], buf[0], buf[3], buf[2], 1, N, H, W, st, [&] {
+        return mma_conv<CO, NBB, MT, WARPS, 1, WALL_B>("fnet.block1.conv2", in_nhwc(buf[0], H, W, CO), EpiNHWC{buf[3], w->b[L + 4], buf[2], H, W, CO, CO, 1},
+                                                       WSets::single(w->w[L + 4]), s1, N, CO, H, W, NCB, st); })));
     return 0;
 }
 
@@ -181,9 +204,9 @@ extern "C" size_t imvs_featurenet_workspace_bytes(int N, int H, int W) {
 
 extern "C" int imvs_featurenet_launch_count(void) { return 18; }
 
-extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs, float* fea1, float* fea2, float* fea3,
-                                       void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
-    IMVS_REQUIRE(w && imgs && fea1 && fea2 && fea3 && workspace, "featurenet_forward: null pointer");
+static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float* imgs, const unsigned char* imgs_u8, float* fea1,
+                                   float* fea2, float* fea3, void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
+    IMVS_REQUIRE(w && (imgs || imgs_u8) && fea1 && fea2 && fea3 && workspace, "featurenet_forward: null pointer");
     IMVS_REQUIRE(N >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "featurenet_forward: H, W must be multiples of 8 (H=%d W=%d)", H, W);
     IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "featurenet_forward: workspace must be 256-byte aligned");
     FnetBuffers b = fnet_carve(static_cast<float*>(workspace), N, H, W);
@@ -195,11 +218,12 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8;
     const TapTables s1 = conv_tables(3, 1, 1, 8), k1 = conv_tables(1, 1, 1, 8);
     // conv1: 3 -> 8, BN, ReLU on the planar image (net.py:13)
-    if (tune("CONV0", 1)) {
+    if (imgs_u8 || tune("CONV0", 1)) {
         IMVS_REQUIRE(w->w[0].fp32 && w->b[0], "featurenet_forward: conv1 weights missing");
         dim3 grid(cdiv(W, C0_TW), cdiv(H, C0_TH), N);
         IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "fnet.conv1: grid too large");
-        IMVS_CUDA(launch_k(fnet_conv0_kernel, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+        if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
+        else IMVS_CUDA(launch_k(fnet_conv0_kernel<float>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
     } else {
         IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                                 WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
@@ -222,7 +246,8 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
             break;
         case 2:
             IMVS_TRY((res_stage<32, 48, false, false, 96, 48, 1>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
-            IMVS_TRY((mma_conv<48, 48, 1, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), conv_tables(3, 1, 1, 4), N, 48, H3, W3, 1, st)));
+            IMVS_TRY((conv3x3_s1<48, 48>("fnet.output3", w->w[16], w->b[16], b.l3[3], fea3, nullptr, 0, N, H3, W3, st, [&] {
+                return mma_conv<48, 48, 1, 4, 1, false>("fnet.output3", in_nhwc(b.l3[3], H3, W3, 48), eo3, WSets::single(w->w[16]), conv_tables(3, 1, 1, 4), N, 48, H3, W3, 1, st); })));
             break;
         case 3:
             IMVS_TRY((res_stage<32, 48, false, false, 32, 16, 1>(w, 11, b.l2[3], b.l3, N, H2, W2, st)));
@@ -248,9 +273,21 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
         IMVS_TRY((mma_conv<48, 16, 1, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1m, N, 16, H1, W1, 1, st)));
     } else {
         IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), ei2, WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
-        IMVS_TRY((mma_conv<48, 32, 2, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st)));
+        IMVS_TRY((conv3x3_s1<48, 32>("fnet.output2", w->w[18], w->b[18], b.intra2, fea2, nullptr, 0, N, H2, W2, st, [&] {
+            return mma_conv<48, 32, 2, 4, 1, false>("fnet.output2", in_nhwc(b.intra2, H2, W2, 48), eo2, WSets::single(w->w[18]), s1, N, 32, H2, W2, 1, st); })));
         IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), ei1, WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
-        IMVS_TRY((mma_conv<48, 16, 2, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st)));
+        IMVS_TRY((conv3x3_s1<48, 16>("fnet.output1", w->w[20], w->b[20], b.intra1, fea1, nullptr, 0, N, H1, W1, st, [&] {
+            return mma_conv<48, 16, 2, 4, 1, false>("fnet.output1", in_nhwc(b.intra1, H1, W1, 48), eo1, WSets::single(w->w[20]), s1, N, 16, H1, W1, 1, st); })));
     }
     return 0;
+}
+
+extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs, float* fea1, float* fea2, float* fea3,
+                                       void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
+    return featurenet_forward_impl(w, imgs, nullptr, fea1, fea2, fea3, workspace, workspace_bytes, N, H, W, stream);
+}
+
+extern "C" int imvs_featurenet_forward_u8(const imvs_featurenet_weights* w, const unsigned char* imgs, float* fea1, float* fea2,
+                                          float* fea3, void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
+    return featurenet_forward_impl(w, nullptr, imgs, fea1, fea2, fea3, workspace, workspace_bytes, N, H, W, stream);
 }

@@ -7,13 +7,14 @@
 // One CTA = 128 consecutive pixels = the 128 TMEM lanes of one UMMA M-block.  Both 1x1 convolutions are GEMMs whose
 // fp32-grade product x*w = hi*hi + hi*lo + lo*hi (x = hi + lo in fp16, 22 significant bits, fp32 accumulation in TMEM;
 // the same 3-product split the mma.sync engine uses in mode 4) is three UMMA chains over the same accumulator:
-//     fc1: D1[128 x 64]  (TMEM columns   0.. 63)  = A1[128 x 32] * W1^T        6 x tcgen05.mma.kind::f16 (K = 16)
-//     fc2: D2[128 x 256] (TMEM columns  64..319)  = A2[128 x 80] * W2^T       15 x tcgen05.mma.kind::f16
-// A2 = split(ReLU(D1)) is produced by the CTA itself (tcgen05.ld -> registers -> shared memory); its K = 64 column is
-// the constant 1 and row 64 of W2 holds the bias, so the logits leave the tensor core with the bias added.  The
-// 256 logits of a pixel then sit in ONE TMEM lane: thread = pixel reads them twice (max / arg-max, then exp-sum and the
-// window sums) -- the 21 MB logits tensor of the unfused path (written by fc2, re-read by the regression kernel) and the
-// 5 MB fc1 activation never exist.  Operands live in shared memory in the UMMA K-major / no-swizzle canonical layout
+//     fc1: D1[128 x 64]  (TMEM columns 0.. 63)  = A1[128 x 32] * W1^T        6 x tcgen05.mma.kind::f16 (K = 16)
+//     fc2: D2[128 x 256] (TMEM columns 0..255)  = A2[128 x 64] * W2^T       12 x tcgen05.mma.kind::f16
+// A2 = split(ReLU(D1)) is produced by the CTA itself (tcgen05.ld -> registers -> shared memory, over A1's buffer);
+// D2 then overwrites D1's columns.  The 256 logits of a pixel sit in ONE TMEM lane: thread = (pixel, column half) reads
+// them twice (max / arg-max, then exp-sum and the window sums; the bias is added from shared memory on the way) -- the
+// 21 MB logits tensor of the unfused path (written by fc2, re-read by the regression kernel) and the 5 MB fc1 activation
+// never exist.  109 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so the 160 CTAs of a 640x512
+// reference view are one wave on 148 SMs.  Operands live in shared memory in the UMMA K-major / no-swizzle canonical layout
 // [K/8][rows][8 halves] (core matrix = 8 rows x 16 bytes, SBO = 128 B, LBO = rows * 16 B); the weights arrive pre-split
 // and pre-ordered from the host (itermvs_b200/_pack.py:pack_head_fused) with four 1-D bulk copies (TMA engine).
 #pragma once
@@ -28,12 +29,14 @@ namespace hf {
 constexpr int HF_THREADS = 256;
 constexpr int HF_M = 128;
 constexpr int KC1 = 4, N1 = 64;                  // fc1: K = 32 = 4 chunks of 8 halves
-constexpr int KC2 = 10, N2 = 256;                // fc2: K = 64 + 16 (bias row, zero padding) = 10 chunks
+constexpr int KC2 = 8, N2 = 256;                 // fc2: K = 64 = 8 chunks
 constexpr uint32_t W1_BYTES = KC1 * N1 * 16, W2_BYTES = KC2 * N2 * 16;
-constexpr uint32_t BLOB_BYTES = 2 * W1_BYTES + 2 * W2_BYTES;           // [W1 hi | W1 lo | W2 hi | W2 lo] = 90 112
+constexpr uint32_t BIAS_BYTES = N2 * 4;
+constexpr uint32_t BLOB_BYTES = 2 * W1_BYTES + 2 * W2_BYTES + BIAS_BYTES;   // [W1 hi | W1 lo | W2 hi | W2 lo | bias fp32] = 74 752
 constexpr uint32_t A1_BYTES = KC1 * HF_M * 16, A2_BYTES = KC2 * HF_M * 16;
 constexpr uint32_t X_BYTES = 2 * HF_M * 4 * sizeof(float);
-constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * A1_BYTES + 2 * A2_BYTES + X_BYTES + 64;
+constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * A2_BYTES + X_BYTES + 64;      // A1 (hi | lo) aliases the head of A2: 111 680
+constexpr uint32_t TMEM_COLS = 256;
 
 struct Params {
     const float* t;          // [n_px][64]: ReLU(conv0); channels 0..31 depth head, 32..63 confidence head
@@ -68,11 +71,12 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     split_f16(make_float2(x[6], x[7]), hi.w, lo.w);
 }
 
-__global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params prm) {
+__global__ void __launch_bounds__(HF_THREADS, 2) head_fused_kernel(const Params prm) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* sW = smem;                                  // W1 hi | W1 lo | W2 hi | W2 lo
-    unsigned char* sA1 = sW + BLOB_BYTES;                      // hi | lo
-    unsigned char* sA2 = sA1 + 2 * A1_BYTES;                   // hi | lo
+    unsigned char* sW = smem;                                  // W1 hi | W1 lo | W2 hi | W2 lo | bias
+    const float* sBias = reinterpret_cast<const float*>(sW + 2 * W1_BYTES + 2 * W2_BYTES);
+    unsigned char* sA2 = sW + BLOB_BYTES;                      // hi | lo
+    unsigned char* sA1 = sA2;                                  // hi | lo in A2's first 16 KB: dead once fc1 has completed
     float* sX = reinterpret_cast<float*>(sA2 + 2 * A2_BYTES);  // [2 halves][128 pixels][4]
     uint64_t* sBar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sX) + X_BYTES);   // weights, fc1, fc2
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 3);   // TMEM base: fc1 accumulator at column 0, fc2 at column 64
@@ -80,9 +84,7 @@ __global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params 
     const uint32_t bar_w = tc5::smem_u32(sBar), bar_1 = tc5::smem_u32(sBar + 1), bar_2 = tc5::smem_u32(sBar + 2);
     const int row0 = blockIdx.x * HF_M;
 
-    // 64 + 256 accumulator columns; allocations are powers of two and a CTA may allocate once before it relinquishes the
-    // permit -> 512 (shared memory already limits this kernel to one CTA per SM)
-    if (warp == 0) tc5::tmem_alloc(tc5::smem_u32(sTmem), 512);
+    if (warp == 0) tc5::tmem_alloc(tc5::smem_u32(sTmem), TMEM_COLS);
     if (tid == 32) {
         tc5::mbar_init(bar_w, 1);
         tc5::mbar_init(bar_1, 1);
@@ -92,37 +94,37 @@ __global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params 
         const unsigned char* g = static_cast<const unsigned char*>(prm.blob);
         tc5::bulk_g2s(tc5::smem_u32(sW), g, 2 * W1_BYTES, bar_w);
         tc5::bulk_g2s(tc5::smem_u32(sW + 2 * W1_BYTES), g + 2 * W1_BYTES, W2_BYTES, bar_w);
-        tc5::bulk_g2s(tc5::smem_u32(sW + 2 * W1_BYTES + W2_BYTES), g + 2 * W1_BYTES + W2_BYTES, W2_BYTES, bar_w);
-    }
-    // constant K chunks 8, 9 of A2: column k = 64 is 1 (multiplies the bias row of W2), the rest zero
-    if (tid < HF_M) {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(sA2 + (8 * HF_M + tid) * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);      // half(1.0) in the low 16 bits
-        *reinterpret_cast<uint4*>(sA2 + (9 * HF_M + tid) * 16) = z;
-        *reinterpret_cast<uint4*>(sA2 + A2_BYTES + (8 * HF_M + tid) * 16) = z;
-        *reinterpret_cast<uint4*>(sA2 + A2_BYTES + (9 * HF_M + tid) * 16) = z;
+        tc5::bulk_g2s(tc5::smem_u32(sW + 2 * W1_BYTES + W2_BYTES), g + 2 * W1_BYTES + W2_BYTES, W2_BYTES + BIAS_BYTES, bar_w);
     }
     pdl_trigger();
     pdl_wait();                  // TMEM allocation and the weight copies overlap the predecessor's tail
-    // ---- A1 = split(t[:, 0:32]): thread -> (pixel row, 8-channel chunk); consecutive threads = consecutive rows
-    for (int i = tid; i < HF_M * KC1; i += HF_THREADS) {
-        const int row = i & (HF_M - 1), kc = i >> 7;
-        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // ---- A1 = split(t[:, 0:32]): thread -> (pixel row, two 8-channel chunks); consecutive threads = consecutive rows;
+    //      all four 16-byte loads of a thread are in flight before the first conversion
+    {
+        static_assert(HF_M * KC1 == 2 * HF_THREADS, "two chunks per thread");
+        const int row = tid & (HF_M - 1), kc0 = tid >> 7;                  // chunks kc0 and kc0 + 2
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + row < prm.n_px) {
-            const float* src = prm.t + (size_t)(row0 + row) * 64 + kc * 8;
-            const float4 a = ldg4(src), b = ldg4(src + 4);
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            const float* src = prm.t + (size_t)(row0 + row) * 64 + kc0 * 8;
+            q[0] = ldg4(src); q[1] = ldg4(src + 4); q[2] = ldg4(src + 16); q[3] = ldg4(src + 20);
         }
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        *reinterpret_cast<uint4*>(sA1 + (kc * HF_M + row) * 16) = hi;
-        *reinterpret_cast<uint4*>(sA1 + A1_BYTES + (kc * HF_M + row) * 16) = lo;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float x[8] = {q[2 * u].x, q[2 * u].y, q[2 * u].z, q[2 * u].w, q[2 * u + 1].x, q[2 * u + 1].y, q[2 * u + 1].z, q[2 * u + 1].w};
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int kc = kc0 + 2 * u;
+            *reinterpret_cast<uint4*>(sA1 + (kc * HF_M + row) * 16) = hi;
+            *reinterpret_cast<uint4*>(sA1 + A1_BYTES + (kc * HF_M + row) * 16) = lo;
+        }
     }
     tc5::fence_async_shared();           // generic-proxy writes -> visible to the tensor core's async proxy
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
-    const uint32_t tm1 = sTmem[0], tm2 = tm1 + 64;
+    const uint32_t tm1 = sTmem[0], tm2 = tm1;        // D2 overwrites D1's columns once A2 has been built from them
 
     // ---- fc1: one thread issues 3 products x 2 K-steps and commits
     bool ok = true;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params 
     __syncthreads();
     tc5::fence_after_sync();
 
-    // ---- fc2 (+ bias through the constant column): 3 products x 5 K-steps
+    // ---- fc2: 3 products x 4 K-steps into the same TMEM columns (every thread has read D1: the barrier above)
     if (tid == 0) {
         if (ok && done) {
             constexpr uint32_t idesc = make_idesc_f16(N2);
@@ -208,6 +210,11 @@ __global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params 
             float v[16];
             tc5::tmem_ld16(tm2 + lane_base + (uint32_t)(col0 + c * 16), v);
 #pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 bq = *reinterpret_cast<const float4*>(sBias + col0 + c * 16 + i);       // broadcast read
+                v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+            }
+#pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (v[i] > mx) { mx = v[i]; bi = col0 + c * 16 + i; }          // first maximum, like torch.argmax
         }
@@ -222,23 +229,41 @@ __global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params 
         const bool take = half == 0 ? (omx > mx) : (omx >= mx);
         if (take) { mx = omx; bi = obi; }
     }
+    // exp(v - mx) = 2^(v * log2e - mx * log2e): one FFMA + one MUFU.EX2 per bin.  The rounding of the common offset
+    // mx * log2e scales every bin of the pixel by the same factor, which cancels in e / sum(e); what remains is the
+    // 2-ulp error of ex2.approx, the same grade as expf.
     float s = 0.f, num = 0.f, den = 0.f;
     if (done) {
+        const float L2E = 1.4426950408889634f, mL = -mx * L2E;
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
             float v[16];
             tc5::tmem_ld16(tm2 + lane_base + (uint32_t)(col0 + c * 16), v);
 #pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 bq = *reinterpret_cast<const float4*>(sBias + col0 + c * 16 + i);
+                v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+            }
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const int ch = col0 + c * 16 + i;
-                const float e = expf(v[i] - mx);
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[i], L2E, mL)));
+                v[i] = e;
                 s += e;
-                // window: indices clamp(bi-4 .. bi+4, 0, 255); clamped duplicates are counted repeatedly (itermvs.py:205-218)
-                int mult = (ch >= bi - IMVS_RADIUS && ch <= bi + IMVS_RADIUS) ? 1 : 0;
-                if (ch == 0) mult = max(0, IMVS_RADIUS + 1 - bi);
-                if (ch == IMVS_OUT_BINS - 1) mult = max(0, bi - (IMVS_OUT_BINS - 2 - IMVS_RADIUS));
-                num = fmaf((float)(mult * ch), e, num);
-                den = fmaf((float)mult, e, den);
+            }
+            // window: indices clamp(bi-4 .. bi+4, 0, 255); clamped duplicates are counted repeatedly (itermvs.py:205-218).
+            // Only the (at most two) 16-column chunks that intersect the window take this branch.
+            const int ch0 = col0 + c * 16;
+            if (ch0 + 15 >= bi - IMVS_RADIUS && ch0 <= bi + IMVS_RADIUS) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int ch = ch0 + i;
+                    int mult = (ch >= bi - IMVS_RADIUS && ch <= bi + IMVS_RADIUS) ? 1 : 0;
+                    if (ch == 0) mult = max(0, IMVS_RADIUS + 1 - bi);
+                    if (ch == IMVS_OUT_BINS - 1) mult = max(0, bi - (IMVS_OUT_BINS - 2 - IMVS_RADIUS));
+                    num = fmaf((float)(mult * ch), v[i], num);
+                    den = fmaf((float)mult, v[i], den);
+                }
             }
         }
     }
@@ -278,7 +303,7 @@ __global__ void __launch_bounds__(HF_THREADS, 1) head_fused_kernel(const Params 
     if ((!ok || !done) && lane == 0 && prm.err_flag) atomicExch(prm.err_flag, 1);
     tc5::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc5::tmem_dealloc(tm1, 512);
+    if (warp == 0) tc5::tmem_dealloc(tm1, TMEM_COLS);
 }
 
 inline int launch(const Params& prm, cudaStream_t st) {

@@ -271,6 +271,226 @@ int launch(const char* name, const In& in, const Epi& epi, const float* w_umma, 
     return 0;
 }
 
+// ==================================================================================================
+// fp32-grade variant (the DEFAULT precision mode 4): the same slot-shifted implicit GEMM with the operands split
+// x = hi + lo in fp16 (hi = fp16(x), lo = fp16(x - hi)) and three tcgen05.mma.kind::f16 chains per tap into the same TMEM
+// accumulator -- hi*hi + hi*lo + lo*hi, fp32 accumulation: 22 significant bits, the products of the mma.sync engine's
+// mode 4.  hi + lo of a value take the 4 bytes its TF32 copy took, so the shared-memory budget is unchanged; K per MMA
+// is 16 instead of 8, so the three products cost 1.5x the TF32 MMA count -- on a tensor pipe that idles either way
+// (these layers are staging / epilogue bound).
+//   tile  : [hi | lo] x [CINP/8 chunks][nslot][8 halves]   element (slot, k) at (k/8)*LBO + slot*16 B + (k%8)*2 B
+//   weights (host-packed, _pack.py:pack_umma_f16): [cout block][tap][hi | lo][CINP/8][NB][8 halves]
+// ==================================================================================================
+__device__ __forceinline__ void umma_f16k(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16k(int n) {       // D = F32, A = B = F16, K-major, M = 128
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+inline Geometry make_geometry_h(int ks, int dil, int Wout, int kc) {
+    Geometry g = make_geometry(ks, dil, Wout);
+    // tile width by staged slots per output row: ceil(W / valid) * WT * (THo + 2 pad) / THo
+    {
+        const int p2 = 2 * g.pad;
+        auto cost = [&](int wt) { const int tho = 128 / wt; return (double)((Wout + wt - p2 - 1) / (wt - p2)) * wt * (tho + p2) / tho; };
+        g.WT = (p2 < 32 && cost(32) < cost(64)) ? 32 : 64;
+        g.THo = 128 / g.WT;
+    }
+    // staging stores of a quarter-warp (8 lanes = (8 / min(kc,4)) slots x min(kc,4) chunks) hit 8 distinct 16-byte bank
+    // groups when nslot = 2 (mod 8) for >= 4 chunks, 4 (mod 8) for 2 chunks
+    const int want = kc >= 4 ? 2 : 4;
+    int n = (g.THo + 2 * g.pad) * g.WT + 2 * g.pad;
+    while (n % 8 != want) ++n;
+    g.nslot = n;
+    return g;
+}
+
+template <int CINP, int NB, class In, class Epi>
+__global__ void __launch_bounds__(TC5_THREADS)
+tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, const Geometry geo, int Hout, int Wout, int* err_flag) {
+    static_assert(CINP % 16 == 0 && NB % 16 == 0 && NB <= 256, "UMMA kind::f16 shape");
+    constexpr int KC = CINP / 8;                                 // 16-byte K chunks (8 halves)
+    constexpr int CPL = KC >= 4 ? 4 : 2;                         // chunks handled by consecutive lanes
+    constexpr int SPW = 32 / CPL;                                // slots per warp and staging iteration
+    constexpr int TMEM_COLS = NB <= 32 ? 32 : (NB <= 64 ? 64 : (NB <= 128 ? 128 : 256));
+    constexpr int NC = NB / 2;                                   // epilogue columns per thread
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nslot = geo.nslot, WT = geo.WT, pad = geo.pad, dil = geo.dil, ks = geo.ks;
+    const int ntaps = ks * ks;
+    const uint32_t a_bytes = (uint32_t)KC * nslot * 16;          // one of hi / lo
+    constexpr uint32_t b_tap_bytes = KC * NB * 16;               // one of hi / lo, one tap
+    unsigned char* sA = smem_raw;                                // hi | lo
+    unsigned char* sB = sA + 2 * a_bytes;                        // [tap][hi | lo][KC][NB][8]
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + (size_t)ntaps * 2 * b_tap_bytes);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.z;
+    const int wvalid = WT - 2 * pad;
+    const int oy0 = blockIdx.y * geo.THo, ox0 = blockIdx.x * wvalid;
+    const uint32_t bar_w = smem_u32(sBar), bar_d = smem_u32(sBar + 1);
+
+    if (warp == 0) tmem_alloc(smem_u32(sTmem), TMEM_COLS);
+    if (tid == 32) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_d, 1);
+        fence_mbar_init();
+        const uint32_t total = (uint32_t)ntaps * 2 * b_tap_bytes;
+        mbar_expect_tx(bar_w, total);
+        // one bulk copy per tap (hi and lo of a tap are adjacent): <= 2 * KC * NB * 16 bytes each
+        for (int tap = 0; tap < ntaps; ++tap)
+            bulk_g2s(smem_u32(sB) + tap * 2 * b_tap_bytes, static_cast<const unsigned char*>(w_f16) + (size_t)tap * 2 * b_tap_bytes,
+                     2 * b_tap_bytes, bar_w);
+    }
+    pdl_trigger();
+    pdl_wait();
+    // ---- stage the haloed input tile, splitting into fp16 hi / lo on the way: slot s -> pixel (oy0 - pad + s / WT,
+    //      ox0 - pad + s % WT).  lane -> (slot sl = lane / CPL, chunk kcl = lane % CPL [+ CPL * g]): a quarter-warp reads
+    //      128 contiguous bytes per pixel; UI iterations (32 registers of loads) are in flight before the first conversion.
+    {
+        constexpr int G = (KC + CPL - 1) / CPL;                  // chunk groups per slot
+        constexpr int UI = 4 / G > 0 ? 4 / G : 1;                // iterations in flight
+        constexpr int PER_IT = (TC5_THREADS / 32) * SPW;         // slots per iteration of the whole CTA
+        const int kcl = lane % CPL, sl = lane / CPL;
+        const auto img = in.image(n);
+#pragma unroll 1
+        for (int s0 = 0; s0 < nslot; s0 += UI * PER_IT) {
+            float4 v[UI][G][2];
+#pragma unroll
+            for (int u = 0; u < UI; ++u) {
+                const int s = s0 + u * PER_IT + warp * SPW + sl;
+                const int iy = oy0 - pad + s / WT, ix = ox0 - pad + (s & (WT - 1));
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int kc = g * CPL + kcl;
+                    bool valid;
+                    const float* src = img.ptr4(iy, ix, 2 * (kc < KC ? kc : 0), valid);
+                    const bool ok = valid && s < nslot && kc < KC;
+                    v[u][g][0] = ok ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u][g][1] = ok ? ldg4(src + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UI; ++u) {
+                const int s = s0 + u * PER_IT + warp * SPW + sl;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int kc = g * CPL + kcl;
+                    if (s < nslot && kc < KC) {
+                        uint4 hi, lo;
+                        split_f16(make_float2(v[u][g][0].x, v[u][g][0].y), hi.x, lo.x);
+                        split_f16(make_float2(v[u][g][0].z, v[u][g][0].w), hi.y, lo.y);
+                        split_f16(make_float2(v[u][g][1].x, v[u][g][1].y), hi.z, lo.z);
+                        split_f16(make_float2(v[u][g][1].z, v[u][g][1].w), hi.w, lo.w);
+                        *reinterpret_cast<uint4*>(sA + ((size_t)kc * nslot + s) * 16) = hi;
+                        *reinterpret_cast<uint4*>(sA + a_bytes + ((size_t)kc * nslot + s) * 16) = lo;
+                    }
+                }
+            }
+        }
+    }
+    fence_async_shared();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = *sTmem;
+
+    bool ok_w = true;
+    if (tid == 0) {
+        ok_w = mbar_wait_bounded(bar_w, 0);
+        constexpr uint32_t idesc = make_idesc_f16k(NB);
+        const uint32_t lbo_a = (uint32_t)nslot * 16u, lbo_b = (uint32_t)NB * 16u;
+        const uint64_t da_hi = make_desc(smem_u32(sA), lbo_a, 128u), da_lo = make_desc(smem_u32(sA + a_bytes), lbo_a, 128u);
+        const uint32_t ka = (2u * lbo_a) >> 4, kb = (2u * lbo_b) >> 4;            // per K-step (16 elements) advance, 16 B units
+        uint32_t acc = 0;
+        if (ok_w) {
+            for (int tap = 0; tap < ntaps; ++tap) {
+                const uint32_t shift = (uint32_t)((tap / ks) * dil * WT + (tap % ks) * dil);       // slots == 16 B units
+                const uint64_t db_hi = make_desc(smem_u32(sB) + tap * 2 * b_tap_bytes, lbo_b, 128u);
+                const uint64_t db_lo = make_desc(smem_u32(sB) + tap * 2 * b_tap_bytes + b_tap_bytes, lbo_b, 128u);
+#pragma unroll
+                for (int prod = 0; prod < 3; ++prod) {
+                    uint64_t da = (prod == 2 ? da_lo : da_hi) + shift, db = prod == 1 ? db_lo : db_hi;
+#pragma unroll
+                    for (int k16 = 0; k16 < CINP / 16; ++k16) {
+                        umma_f16k(tmem_d, da, db, idesc, acc);
+                        acc = 1;
+                        da += ka; db += kb;
+                    }
+                }
+            }
+        }
+        umma_commit(bar_d);
+    }
+    // ---- epilogue: warp w owns TMEM lanes 32*(w&3).. (= slots) and the column half (w>>2); thread = one pixel
+    {
+        const bool done = mbar_wait_bounded(bar_d, 0);
+        fence_after_sync();
+        if (!done) {
+            if (lane == 0 && err_flag) atomicExch(err_flag, 1);
+        } else {
+            const int lg = warp & 3, half = warp >> 2;
+            const int m = lg * 32 + lane;
+            const int oy = oy0 + m / WT, oxl = m & (WT - 1), ox = ox0 + oxl;
+            const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
+            float v[NC];
+            if constexpr (NC % 16 == 0) {
+#pragma unroll
+                for (int c = 0; c < NC; c += 16) {
+                    float t16[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NC + c), t16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[c + i] = t16[i];
+                }
+            } else {
+                static_assert(NC % 8 == 0, "epilogue column split");
+#pragma unroll
+                for (int c = 0; c < NC; c += 8) {
+                    uint32_t r[8];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                                 : "r"(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NC + c)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[c + i] = __uint_as_float(r[i]);
+                }
+            }
+            if (ok) epi.template part<NC>(n, oy, ox, half * NC, v);
+        }
+    }
+    if (tid == 0 && !ok_w && err_flag) atomicExch(err_flag, 1);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <int CINP, int NB>
+inline size_t smem_bytes_h(const Geometry& g) {
+    return (size_t)2 * (CINP / 8) * g.nslot * 16 + (size_t)g.ks * g.ks * 2 * (CINP / 8) * NB * 16 + 64;
+}
+
+// w_f16: packed weights of ALL cout blocks ([cout block][tap][hi|lo][KC][NB][8 halves]); blockIdx.z = n (one cout block per launch
+// when cout_total == NB; otherwise launch once per block with the pointer advanced -- the FeatureNet / estimator layers served
+// here have cout_total == NB)
+template <int CINP, int NB, class In, class Epi>
+int launch_h(const char* name, const In& in, const Epi& epi, const void* w_f16, int ks, int dil, int N, int Hout, int Wout,
+             int* err_flag, cudaStream_t st) {
+    IMVS_REQUIRE(w_f16, "%s: null tcgen05 fp16 weights", name);
+    const Geometry g = make_geometry_h(ks, dil, Wout, CINP / 8);
+    const size_t smem = smem_bytes_h<CINP, NB>(g);
+    IMVS_REQUIRE(smem <= 220 * 1024, "%s: %zu bytes of shared memory needed", name, smem);
+    auto kern = tc5h_conv_kernel<CINP, NB, In, Epi>;
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
+    dim3 grid(cdiv(Wout, g.WT - 2 * g.pad), cdiv(Hout, g.THo), N);
+    IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: grid too large", name);
+    if (launch_k(kern, grid, dim3(TC5_THREADS), smem, st, in, epi, w_f16, g, Hout, Wout, err_flag) != cudaSuccess)
+        return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 // ---- epilogues (one thread = one pixel, NC contiguous channels starting at c0) ---------------------
 // TF32 mode: gates use the fast exponential (ex2.approx; relative error ~1e-6, far below TF32's 5e-4)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }

@@ -28,7 +28,6 @@
 #include "sampling.cuh"
 
 #include <algorithm>
-#include <cstdlib>
 
 namespace imvs {
 
@@ -104,9 +103,6 @@ struct IterParams5 {
     unsigned int n_tiles;       // 4x4-pixel tiles of the level-2 maps of all batch items
     int tiles_x, tiles_y;
     unsigned long long strip_magic;     // fastdiv constant for 2 * tiles_x
-    int pf_mode;                // region prefetch: 0 off, 1 prefetch.global.L1 per line, 2 coalesced dummy loads
-    int pf_levels;              // bit l: prefetch the windows of pyramid level l+1
-    int dbg_levels, dbg_repeat; // diagnostics (IMVS_WC_LEVELS / IMVS_WC_REPEAT): levels computed, passes over the region
 };
 
 struct IterSmem {
@@ -400,135 +396,6 @@ __device__ __forceinline__ void fetch_header(ItemHeader<ST>& h, const IterParams
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Region prefetch.  A block owns a compact pixel region; every source line it gathers from is a compulsory L1 miss the
-// first time (22 % of the sectors at 640x512) and each of those misses stalls a consuming warp for an L2 round trip.  The
-// sampling positions are projective-linear in (x, y, inverse depth), so the taps of ALL pixels of a rectangle at ALL
-// hypotheses between the rectangle's smallest and largest normalized depth lie inside the bounding box of the 8 projected
-// corners: that window (per level and view, plus the rectangle itself in the reference view) is streamed into L1 with
-// independent, fully coalesced requests before the gathers need it.  Best effort: windows of regions with a large depth
-// range (discontinuities) are skipped; results never depend on it.
-// ---------------------------------------------------------------------------------------------
-struct PfWindow { const float* row0; int row_bytes, pitch_bytes, rows; };
-constexpr int PF_MAX_WIN = 3 * (IMVS_MAX_VIEWS + 1);
-constexpr int PF_MAX_BYTES = 80 * 1024;      // per (level, view): beyond this the window would evict itself
-
-template <int NW>
-__device__ void region_prefetch(const IterParams5& q, unsigned r0, unsigned r1, int S) {
-    __shared__ int s_ndmin, s_ndmax, s_nwin;
-    __shared__ PfWindow s_win[PF_MAX_WIN];
-    const IterParams& prm = q.p;
-    if (prm.samples[0] != nullptr || r1 <= r0) return;
-    const int H2 = prm.H2, W2 = prm.W2, V = prm.V;
-    const unsigned per_b = (unsigned)(q.tiles_x * q.tiles_y);
-    const unsigned t_first = r0 >> 2, t_last = (r1 - 1) >> 2;
-    const unsigned b = t_first / per_b;
-    if (t_last / per_b != b) return;                                    // region straddles two batch items: skip
-    const unsigned k_first = t_first - b * per_b, k_last = t_last - b * per_b;
-    const unsigned s_a = fastdiv(k_first, q.strip_magic), s_b = fastdiv(k_last, q.strip_magic);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float inv_min = 1.0f / ldg(prm.depth_min + b), inv_max = 1.0f / ldg(prm.depth_max + b);
-    for (unsigned strip = s_a; strip <= s_b && strip < s_a + 3; ++strip) {
-        const unsigned lo = strip == s_a ? k_first - strip * 2 * q.tiles_x : 0u;
-        const unsigned hi = strip == s_b ? k_last - strip * 2 * q.tiles_x : 2u * q.tiles_x - 1;
-        const bool two = (int)(2 * strip + 1) < q.tiles_y;
-        const int tx0 = two ? lo >> 1 : lo, tx1 = two ? hi >> 1 : hi;
-        const int X0 = tx0 * WC_NPX, X1 = min(tx1 * WC_NPX + WC_NPX, W2) - 1;
-        const int Y0 = (int)strip * 8, Y1 = min(Y0 + (two ? 8 : 4), H2) - 1;
-        if (X1 < X0 || Y1 < Y0) continue;
-        if (threadIdx.x == 0) { s_ndmin = 0x7f800000; s_ndmax = 0; s_nwin = 0; }
-        __syncthreads();
-        // smallest / largest normalized depth of the rectangle (non-negative floats order like their bit patterns)
-        const int rw = X1 - X0 + 1, npx = rw * (Y1 - Y0 + 1);
-        int mn = 0x7f800000, mx = 0;
-        for (int i = threadIdx.x; i < npx; i += NW * 32) {
-            const int yy = Y0 + i / rw, xx = X0 + i % rw;
-            const float v = fminf(fmaxf(ldg(prm.nd + (size_t)b * prm.nd_stride + ((size_t)yy * W2 + xx) * prm.nd_pstride), 0.f), 1.f);
-            mn = min(mn, __float_as_int(v)); mx = max(mx, __float_as_int(v));
-        }
-        if (mx >= mn) { atomicMin(&s_ndmin, mn); atomicMax(&s_ndmax, mx); }       // <= ~200 pixels: a few smem atomics
-        __syncthreads();
-        // one thread per (level, view): view 0 = the reference feature itself
-        if (threadIdx.x < 3 * (S + 1)) {
-            const int lvl = threadIdx.x / (S + 1), v = threadIdx.x % (S + 1);
-            if ((q.pf_levels >> lvl) & 1) {
-                const int C = lvl == 0 ? 16 : (lvl == 1 ? 32 : 48);
-                const float SC = lvl == 0 ? 2.f : (lvl == 1 ? 1.f : 0.5f);
-                const int Hf = lvl == 0 ? H2 * 2 : (lvl == 2 ? H2 / 2 : H2), Wf = lvl == 0 ? W2 * 2 : (lvl == 2 ? W2 / 2 : W2);
-                float ulo = 1e30f, uhi = -1e30f, vlo = 1e30f, vhi = -1e30f;
-                bool ok = true;
-                if (v == 0) {
-                    ulo = X0 * SC - 1.f; uhi = X1 * SC + 1.f; vlo = Y0 * SC - 1.f; vhi = Y1 * SC + 1.f;
-                } else {
-                    const float off = (lvl == 0 ? 2.f : (lvl == 1 ? 8.f : 32.f)) * (1.0f / 256.0f);
-                    const float slo = fmaxf(__int_as_float(s_ndmin) - off, 0.f), shi = fminf(__int_as_float(s_ndmax) + off, 1.f);
-                    const float* P = prm.rt[lvl] + ((size_t)b * S + (v - 1)) * 12;
-#pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
-                        const float X = (float)((c & 1) ? X1 : X0) * SC, Y = (float)((c & 2) ? Y1 : Y0) * SC;
-                        const float d = unnormalize_depth((c & 4) ? shi : slo, inv_min, inv_max);
-                        const float pz = fmaf(fmaf(P[6], X, fmaf(P[7], Y, P[8])), d, P[11]);
-                        if (!(pz > 1e-2f)) { ok = false; break; }
-                        const float u = fmaf(fmaf(P[0], X, fmaf(P[1], Y, P[2])), d, P[9]) / pz;
-                        const float w = fmaf(fmaf(P[3], X, fmaf(P[4], Y, P[5])), d, P[10]) / pz;
-                        ulo = fminf(ulo, u); uhi = fmaxf(uhi, u); vlo = fminf(vlo, w); vhi = fmaxf(vhi, w);
-                    }
-                }
-                if (ok && uhi > -1.f && vhi > -1.f && ulo < (float)Wf && vlo < (float)Hf) {
-                    const int xa = max((int)floorf(ulo - 0.01f), 0), xb = min((int)floorf(uhi + 0.01f) + 1, Wf - 1);
-                    const int ya = max((int)floorf(vlo - 0.01f), 0), yb = min((int)floorf(vhi + 0.01f) + 1, Hf - 1);
-                    const int row_bytes = (xb - xa + 1) * C * 4;
-                    if (xb >= xa && yb >= ya && row_bytes * (yb - ya + 1) <= PF_MAX_BYTES) {
-                        const int slot = atomicAdd(&s_nwin, 1);
-                        s_win[slot].row0 = prm.fea[lvl] + (((size_t)b * V + v) * Hf + ya) * ((size_t)Wf * C) + (size_t)xa * C;
-                        s_win[slot].row_bytes = row_bytes;
-                        s_win[slot].pitch_bytes = Wf * C * 4;
-                        s_win[slot].rows = yb - ya + 1;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int nwin = s_nwin;
-        for (int wi = 0; wi < nwin; ++wi) {
-            const PfWindow w = s_win[wi];
-            const uintptr_t a0 = reinterpret_cast<uintptr_t>(w.row0);
-            if (q.pf_mode == 1) {
-                // one prefetch per 128-byte line
-                const int mis = (int)(a0 & 127u), nl = (mis + w.row_bytes + 127) >> 7;
-                for (int i = threadIdx.x; i < nl * w.rows; i += NW * 32) {
-                    const int row = i / nl, l = i - row * nl;
-                    const char* pa = reinterpret_cast<const char*>(a0 - mis) + (size_t)row * w.pitch_bytes + ((size_t)l << 7);
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
-                }
-            } else {
-                // coalesced dummy loads: a warp reads 512 contiguous bytes per request, 4 requests in flight
-                const int mis = (int)(a0 & 15u), nc = (mis + w.row_bytes + 511) >> 9, total = nc * w.rows;
-                for (int i0 = warp; i0 < total; i0 += 4 * NW) {
-                    float4 t[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u * NW;
-                        t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (i < total) {
-                            const int row = i / nc, ch = i - row * nc;
-                            const int off = (ch << 9) + lane * 16;
-                            if (off < mis + w.row_bytes) {
-                                const char* pa = reinterpret_cast<const char*>(a0 - mis) + (size_t)row * w.pitch_bytes + off;
-                                asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                             : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w) : "l"(pa));
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) asm volatile("" ::"f"(t[u].x), "f"(t[u].y), "f"(t[u].z), "f"(t[u].w));
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // ST = number of source views when it is 1..8 (gather loops fully unrolled: the software pipeline becomes
 // straight-line code with statically renamed buffers), 0 = any number (rolled loops).
 // NW = warps of the (single) block an SM runs.
@@ -554,19 +421,16 @@ __global__ void __launch_bounds__(NW * 32, 1) warpcorr_iter_kernel(const IterPar
     const unsigned r0 = (unsigned)(((unsigned long long)q.n_tiles * 4 * blockIdx.x) / gridDim.x);
     const unsigned r1 = (unsigned)(((unsigned long long)q.n_tiles * 4 * (blockIdx.x + 1)) / gridDim.x);
     const unsigned per_level = r1 - r0, n_items = per_level * 3;
-    pdl_wait();                     // nd / view weights / pyramids come from the preceding kernels
-    if (q.pf_mode) region_prefetch<NW>(q, r0, r1, S);
-    for (int rep = 0; rep < q.dbg_repeat; ++rep) {
-    __syncthreads();
     if (threadIdx.x == 0) next_item = 2 * NW;
     __syncthreads();
+    pdl_wait();                     // nd / view weights / pyramids come from the preceding kernels
     ItemHeader<ST> cur, nxt;
     fetch_header<ST>(cur, q, warp, n_items, r0, per_level, S, lane);
     unsigned nxt_item = NW + warp;
     while (cur.lvl >= 0 || nxt_item < n_items) {
         // the next item's header loads fly while this item is processed
         fetch_header<ST>(nxt, q, nxt_item, n_items, r0, per_level, S, lane);
-        if (cur.lvl >= 0 && ((q.dbg_levels >> cur.lvl) & 1)) {
+        if (cur.lvl >= 0) {
 #pragma unroll
             for (int i = 0; i < ItemHeader<ST>::NRT; ++i)
                 if (lane + 32 * i < 12 * S) sm.sP[lane + 32 * i] = cur.rt[i];
@@ -600,7 +464,6 @@ __global__ void __launch_bounds__(NW * 32, 1) warpcorr_iter_kernel(const IterPar
         unsigned drawn = 0;
         if (lane == 0 && nxt_item < n_items) drawn = atomicAdd(&next_item, 1u);
         nxt_item = nxt_item < n_items ? __shfl_sync(0xffffffffu, drawn, 0) : n_items;
-    }
     }
 }
 
@@ -640,105 +503,24 @@ __device__ __forceinline__ float pair_dot(const Taps48& T, int k, const float4& 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: init plane sweep at level 3 (C = 48), per-view group correlation.
-//
-// The D hypotheses of a pixel walk along its epipolar line in steps of a fraction of a texel (0.2 - 0.5 at 640x512), so
-// their 4 D taps revisit the same texels again and again.  Correlation is linear in the taps -- <ref, sum_t w_t src_t> =
-// sum_t w_t <ref, src_t> -- so the kernel takes the dot products FIRST, once per texel of the line's bounding box
-// ("band"), and interpolates 8 group scalars per tap instead of 48 channels:
-//   phase A  lane = hypothesis: projection, clamped 2x2 tap base + permuted bilinear weights (zero padding folded in);
-//   box      REDUX min/max of the tap bases over the warp -> band [bw x bh] texels.  The band pays when the hypotheses
-//            are DENSE on the line (texels < ~3 per hypothesis and <= IB_CAP); a long or steep segment sampled
-//            sparsely (wide baselines, high resolution: > 1 texel per hypothesis) takes the direct path instead:
-//            8 lanes per hypothesis gather its 4 taps x 48 channels (12 x 64-byte pieces) and regroup with shuffles;
-//   phase B  band dots: 24 lanes read TWO x-adjacent texels (384 contiguous bytes, one float4 each) per instruction,
-//            multiply with their chunk of the reference feature and fold 12 chunk partials into 8 group sums with
-//            two shuffles (a group is 6 channels = 1.5 chunks); the 8 sums of a texel go to shared memory (32 bytes);
-//   phase C  lane = hypothesis again: 4 taps x 8 group sums from the band (8 LDS.128), 32 FMAs, two 16-byte stores.
-// No per-sample records, no per-sample global gathers: at 640x512 / 4 views the band has ~50 texels per (pixel, view)
-// against 128 taps, and each texel costs 2.25 L1 wavefronts instead of 3.
+// K2: init plane sweep at level 3 (C = 48), per-view group correlation.  One warp = one pixel; its D hypotheses in
+// chunks of 32: phase A, lane = hypothesis (projection, clamped 2x2 tap base, permuted bilinear weights with the
+// zero padding folded in) -> a 20-byte record per hypothesis in shared memory; phase B, 8 lanes per hypothesis
+// (lane g: channel pairs g, 8+g, 16+g -> every load instruction reads 64 contiguous bytes per hypothesis), 4
+// consecutive hypotheses per instruction (they lie within a few texels of each other on the epipolar line and share
+// cache lines), regrouped to the 8 correlation groups with three shuffles.
+// Measured alternative (round 2, profiles/ps_experiments_r02.md): taking the dot products first, once per texel of the
+// epipolar segment's bounding box, and interpolating 8 group scalars per tap ("band") executes MORE instructions than
+// this gather at the benchmark's hypothesis spacing (30 M vs 25 M warp instructions, 52 us vs 46 us) and 1.4x more at
+// the sparser spacing of 1920x1056 -- it was removed.
 //   grid (ceil(W3/2), ceil(H3/2), B), block 128 (4 warps = 2 x 2 pixels)
 // ---------------------------------------------------------------------------------------------
-constexpr int IB_CAP = 128;                 // band texels per warp (8 floats each)
-constexpr int IB_DENSE = 3;                 // band path when the box has at most this many texels per live hypothesis
-
-struct InitLane {                            // phase-A result of this lane's hypothesis
-    float4 w;                                // weights of taps (xb,yb) (xb+1,yb) (xb,yb+1) (xb+1,yb+1)
-    int xb, yb;
-    bool valid;                              // hypothesis index < D
-    bool zero;                               // all four taps outside the source map: the result is 0, no band needed
-};
-
-// band dots + interpolation for the hypotheses (lanes) [lo, hi) of the warp; all 32 lanes must call
-__device__ __forceinline__ void init_band(const InitLane& me, int lo, int hi, float* __restrict__ band,
-                                          const float* __restrict__ src, int W3, const float4& refc,
-                                          float* __restrict__ out8, int xlo, int xhi, int ylo, int yhi) {
-    const int lane = threadIdx.x & 31;
-    const int bw = xhi - xlo + 1, bh = yhi - ylo + 1;
-    const int ppr = (bw + 1) >> 1, np = ppr * bh;            // texel pairs per row / in the band
-    const int role = lane % 3, tex = lane >= 12 ? 1 : 0, grp = 2 * ((lane % 12) / 3) + (role == 2 ? 1 : 0);
-    const bool loader = lane < 24;
-    __syncwarp();                                            // the previous band of this warp has been consumed
-    // ---- phase B: pairs in row-major order, (r, j) advanced incrementally (no divisions), 4 requests in flight
-    const float* lanep = src + ((size_t)ylo * W3 + xlo) * 48 + lane * 4;
-    float* sto = band + tex * 8 + grp;
-    const int pitch = W3 * 48;
-    const bool writer = loader && role != 1;
-    int r = 0, j = 0;
-    for (int i0 = 0; i0 < np; i0 += 4) {
-        float4 t[4];
-        int eo[4];                                            // band offset of the pair's first texel, -1: nothing to store
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool mine = i0 + u < np && loader && 2 * j + tex < bw;       // the band's last column may be a single texel
-            eo[u] = mine ? (r * bw + 2 * j) * 8 : -1;
-            if (mine) t[u] = ldg4(lanep + (size_t)r * pitch + j * 96);
-            if (++j == ppr) { j = 0; ++r; }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (i0 + u < np) {                                // warp-uniform
-                const float lo2 = fmaf(t[u].y, refc.y, t[u].x * refc.x), hi2 = fmaf(t[u].w, refc.w, t[u].z * refc.z);
-                const float pa = role == 0 ? lo2 + hi2 : lo2;                  // roles 0, 1: share of the triple's even group
-                const float pb = role == 2 ? lo2 + hi2 : hi2;                  // roles 1, 2: share of the triple's odd group
-                const float va = __shfl_down_sync(0xffffffffu, pa, 1), vb = __shfl_up_sync(0xffffffffu, pb, 1);
-                if (writer && eo[u] >= 0) sto[eo[u]] = role == 0 ? pa + va : pb + vb;
-            }
-        }
-    }
-    __syncwarp();
-    // ---- phase C
-    if (lane >= lo && lane < hi && me.valid && !me.zero) {
-        const float4* e = reinterpret_cast<const float4*>(band) + ((me.yb - ylo) * bw + (me.xb - xlo)) * 2;
-        const float4 a0 = e[0], a1 = e[1], b0 = e[2], b1 = e[3];
-        const float4 c0 = e[2 * bw], c1 = e[2 * bw + 1], d0 = e[2 * bw + 2], d1 = e[2 * bw + 3];
-        const float k = 1.0f / 6.0f;
-        float4 o0, o1;
-        o0.x = bilerp(a0.x, b0.x, c0.x, d0.x, me.w) * k; o0.y = bilerp(a0.y, b0.y, c0.y, d0.y, me.w) * k;
-        o0.z = bilerp(a0.z, b0.z, c0.z, d0.z, me.w) * k; o0.w = bilerp(a0.w, b0.w, c0.w, d0.w, me.w) * k;
-        o1.x = bilerp(a1.x, b1.x, c1.x, d1.x, me.w) * k; o1.y = bilerp(a1.y, b1.y, c1.y, d1.y, me.w) * k;
-        o1.z = bilerp(a1.z, b1.z, c1.z, d1.z, me.w) * k; o1.w = bilerp(a1.w, b1.w, c1.w, d1.w, me.w) * k;
-        reinterpret_cast<float4*>(out8)[0] = o0;
-        reinterpret_cast<float4*>(out8)[1] = o1;
-    }
-}
-
-// bounding box of the 2x2 taps of lanes [lo, hi)
-__device__ __forceinline__ void init_box(const InitLane& me, int lo, int hi, int& xlo, int& xhi, int& ylo, int& yhi) {
-    const int lane = threadIdx.x & 31;
-    const bool in = lane >= lo && lane < hi && me.valid && !me.zero;
-    xlo = __reduce_min_sync(0xffffffffu, in ? me.xb : 0x7fffffff);
-    ylo = __reduce_min_sync(0xffffffffu, in ? me.yb : 0x7fffffff);
-    xhi = __reduce_max_sync(0xffffffffu, in ? me.xb + 1 : -1);
-    yhi = __reduce_max_sync(0xffffffffu, in ? me.yb + 1 : -1);
-}
-
-__global__ void __launch_bounds__(WC_WARPS * 32)
+__global__ void __launch_bounds__(WC_WARPS * 32, 6)
 warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ rt3,
                      const float* __restrict__ depth_min, const float* __restrict__ depth_max,
-                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D, int dense) {
-    __shared__ __align__(16) float s_band[WC_WARPS][IB_CAP * 8];
+                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D) {
+    __shared__ float4 s_recW[WC_WARPS][32];
+    __shared__ int s_recO[WC_WARPS][32];
     __shared__ float sP[IMVS_MAX_VIEWS * 12];
     const int S = V - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -749,66 +531,45 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
     __syncthreads();
     const int x = blockIdx.x * 2 + (warp & 1), y = blockIdx.y * 2 + (warp >> 1);
     if (x >= W3 || y >= H3) return;
+    const int g = lane & 7, slot = lane >> 3;
     const int P3 = H3 * W3, p = y * W3 + x;
     const float inv_min = samples ? 0.f : 1.0f / depth_min[b], inv_max = samples ? 0.f : 1.0f / depth_max[b];
     const float* fb = fea3 + (size_t)b * V * P3 * 48;
-    float* band = s_band[warp];
-    // this lane's chunk (4 channels) of the reference feature: chunk = lane % 12 (band path), and the channel
-    // pairs {g, 8+g, 16+g}, g = lane % 8 (direct path)
-    const float4 refc = ldg4(fb + (size_t)p * 48 + (lane % 12) * 4);
-    float2 ref2[3];
+    const int pitch = W3 * 48;
+    float4* recW = s_recW[warp];
+    int* recO = s_recO[warp];
+    float2 ref[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) ref2[k] = ldg2(fb + (size_t)p * 48 + 2 * (lane & 7) + 16 * k);
+    for (int k = 0; k < 3; ++k) ref[k] = ldg2(fb + (size_t)p * 48 + 2 * g + 16 * k);
 
     for (int d0 = 0; d0 < D; d0 += 32) {
-        const int d = d0 + lane;
-        InitLane me;
-        me.valid = d < D;
+        const int dc = min(d0 + lane, D - 1);
         // itermvs.py:13-17 (or the caller's explicit hypotheses, Evaluation.forward's depth_sample)
-        const int dc = min(d, D - 1);
         const float depth = samples ? ldg(samples + ((size_t)b * D + dc) * P3 + p)
                                     : 1.0f / (inv_max + ((float)dc / (float)(D - 1)) * (inv_min - inv_max));
+        const int nd = min(32, D - d0);
         for (int v = 0; v < S; ++v) {
             const Tap tp = project_tap(sP + v * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
+            float4 w;
             int off;
-            make_record(tp, W3, H3, 48, 0, me.w, off);
-            me.xb = min(max(tp.x0, 0), W3 - 2); me.yb = min(max(tp.y0, 0), H3 - 2);
-            me.zero = me.w.x == 0.f && me.w.y == 0.f && me.w.z == 0.f && me.w.w == 0.f;
-            const float* src = fb + (size_t)(v + 1) * P3 * 48;
-            float* out8 = corr + ((((size_t)b * S + v) * D + dc) * P3 + p) * 8;
-            if (me.valid && me.zero) {                                        // e.g. the z <= 0.01 substitution at level 3
-                reinterpret_cast<float4*>(out8)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                reinterpret_cast<float4*>(out8)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            int xlo, xhi, ylo, yhi;
-            init_box(me, 0, 32, xlo, xhi, ylo, yhi);
-            if (xhi < xlo) continue;                                          // every hypothesis of this view is outside
-            const int area = (xhi - xlo + 1) * (yhi - ylo + 1);
-            const int nlive = __popc(__ballot_sync(0xffffffffu, me.valid && !me.zero));
-            if (area <= IB_CAP && area <= dense * nlive) {
-                init_band(me, 0, 32, band, src, W3, refc, out8, xlo, xhi, ylo, yhi);
-            } else {
-                // direct path: records through shared memory (the band buffer is free), 4 hypotheses per instruction
-                float4* recW = reinterpret_cast<float4*>(band);
-                int* recO = reinterpret_cast<int*>(band + 32 * 4);
-                __syncwarp();
-                recW[lane] = me.w;
-                recO[lane] = (me.yb * W3 + me.xb) * 48;
-                __syncwarp();
-                const int g = lane & 7, slot = lane >> 3;
-                const int nd = min(32, D - d0);
+            make_record(tp, W3, H3, 48, v + 1, w, off);
+            __syncwarp();                               // the previous view's records have been consumed
+            recW[lane] = w;
+            recO[lane] = off;
+            __syncwarp();
+            const float* src = fb + 2 * g;
+            float* out = corr + ((((size_t)b * S + v) * D + d0) * P3 + p) * 8 + g;
 #pragma unroll 2
-                for (int dd = 0; dd < nd; dd += 4) {
-                    const int t = dd + slot;
-                    const float4 w = recW[t];
-                    Taps48 T;
-                    load48(T, src + recO[t] + 2 * g, W3 * 48);
-                    float acc[3];
+            for (int dd = 0; dd < nd; dd += 4) {
+                const int t = dd + slot;
+                const float4 wt = recW[t];
+                Taps48 T;
+                load48(T, src + recO[t], pitch);
+                float acc[3];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) acc[k] = pair_dot(T, k, w, ref2[k]);
-                    const float c = regroup48(acc, lane) * (1.0f / 6.0f);
-                    if (d0 + t < D) corr[((((size_t)b * S + v) * D + d0 + t) * P3 + p) * 8 + g] = c;
-                }
+                for (int k = 0; k < 3; ++k) acc[k] = pair_dot(T, k, wt, ref[k]);
+                const float c = regroup48(acc, lane) * (1.0f / 6.0f);
+                if (t < nd) out[(size_t)t * P3 * 8] = c;
             }
         }
     }
@@ -859,9 +620,8 @@ extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const flo
     dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B);
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
     ApiScope api_;
-    static const int dense = getenv("IMVS_INIT_DENSE") ? atoi(getenv("IMVS_INIT_DENSE")) : IB_DENSE;      // tuning switch
     IMVS_CUDA(launch_k(warpcorr_init_kernel, grid, dim3(WC_WARPS * 32), 0, (cudaStream_t)stream, fea3, rt3, depth_min, depth_max,
-                       depth_samples, corr, B, V, H3, W3, D, dense));
+                       depth_samples, corr, B, V, H3, W3, D));
     return 0;
 }
 
@@ -903,11 +663,6 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     IMVS_REQUIRE(2 * q.tiles_x <= 4096, "warpcorr_iter: W2=%d too wide", W2);
     q.n_tiles = (unsigned)tiles;
     q.strip_magic = ((1ULL << 40) + 2 * q.tiles_x - 1) / (2 * q.tiles_x);
-    static const int env_pf = getenv("IMVS_WC_PF") ? atoi(getenv("IMVS_WC_PF")) : 0;
-    static const int env_pfl = getenv("IMVS_WC_PF_LEVELS") ? atoi(getenv("IMVS_WC_PF_LEVELS")) : 7;
-    static const int env_lv = getenv("IMVS_WC_LEVELS") ? atoi(getenv("IMVS_WC_LEVELS")) : 7;
-    static const int env_rep = getenv("IMVS_WC_REPEAT") ? atoi(getenv("IMVS_WC_REPEAT")) : 1;
-    q.pf_mode = env_pf; q.pf_levels = env_pfl; q.dbg_levels = env_lv; q.dbg_repeat = env_rep;
     const int blocks = (int)std::min<long long>(tiles, sms);
     ApiScope api_;
     IMVS_CUDA(launch_k(kern, dim3(blocks), dim3(WC_ITER_WARPS * 32), smem, (cudaStream_t)stream, q));

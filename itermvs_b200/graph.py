@@ -28,7 +28,9 @@ class GraphedPipeline:
         self.workspace_slot = workspace_slot      # graphs with different slots own disjoint workspaces -> may overlap
         dev = imgs["level_0"].device
         # static inputs: only what Pipeline.forward reads (net.py:78-109): imgs['level_0'], proj level_1..3
-        self.s_img = imgs["level_0"].detach().clone().float().contiguous()
+        # (uint8 images stay uint8: the first FeatureNet layer normalises them, a quarter of the H2D bytes per step)
+        img0 = imgs["level_0"].detach().clone()
+        self.s_img = (img0 if img0.dtype == torch.uint8 else img0.float()).contiguous()
         self.s_proj = {k: proj_matrices[k].detach().clone().float().contiguous() for k in ("level_1", "level_2", "level_3")}
         self.s_dmin = depth_min.detach().clone().float().contiguous()
         self.s_dmax = depth_max.detach().clone().float().contiguous()

@@ -80,7 +80,14 @@ class FeatureNet(nn.Module):
             raise NotImplementedError("itermvs_b200.FeatureNet.forward_nhwc is the inference kernel path (BatchNorm folded "
                                       "with running statistics); in train() mode use Pipeline.forward, which runs "
                                       "itermvs_b200/training.py (batch statistics, autograd)")
-        x = ops._chk(x.float(), "imgs")
+        # uint8 = the raw 8-bit image: normalised on the device exactly as the reference's loaders do (x / 255., dtu_yao_eval.py:56-59)
+        u8 = x.dtype == torch.uint8
+        if u8:
+            if not x.is_cuda:
+                raise RuntimeError("itermvs_b200: imgs must be a CUDA tensor (there is no CPU path)")
+            x = x.contiguous()
+        else:
+            x = ops._chk(x.float(), "imgs")
         b, v, c, h, w = x.shape
         assert c == 3
         dev = x.device
@@ -97,9 +104,9 @@ class FeatureNet(nn.Module):
         f1 = torch.empty(b, v, h // 2, w // 2, 16, device=dev)
         f2 = torch.empty(b, v, h // 4, w // 4, 32, device=dev)
         f3 = torch.empty(b, v, h // 8, w // 8, 48, device=dev)
-        _lib.check(_lib.lib().imvs_featurenet_forward(self._packed(dev).ref, x.data_ptr(), f1.data_ptr(), f2.data_ptr(),
-                                                      f3.data_ptr(), ws.data_ptr(), ws.numel(), n, h, w, ops._stream()),
-                   "featurenet_forward")
+        fwd = _lib.lib().imvs_featurenet_forward_u8 if u8 else _lib.lib().imvs_featurenet_forward
+        _lib.check(fwd(self._packed(dev).ref, x.data_ptr(), f1.data_ptr(), f2.data_ptr(), f3.data_ptr(), ws.data_ptr(), ws.numel(),
+                       n, h, w, ops._stream()), "featurenet_forward")
         return f1, f2, f3
 
     def forward(self, x: Tensor):

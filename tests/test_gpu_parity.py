@@ -170,6 +170,49 @@ def test_window_regression_edges(dev, model):
     assert maxerr(nd, nd_ref) < 1e-6
 
 
+def test_fused_tcgen05_head(dev, model, e2e_d32):
+    """The default head (csrc/headfused.cuh: fc1 + fc2 + softmax / arg-max / window regression in one tcgen05 kernel, logits in
+    TMEM) against (a) the reference's own Update outputs on the reference's own hidden states (e2e_d32.npz) and (b) the unfused
+    kernels (IMVS_TUNE_HEADFUSED=0) on the same input; incl. the confidence branch and a ragged last 128-pixel tile."""
+    import os
+    from itermvs_b200 import _lib
+    assert _lib.get_conv_passes() == 4
+    upd = model.iter_mvs.update
+    fix = e2e_d32
+    its = sorted(int(k[len("hidden_iter"):]) for k in fix if k.startswith("hidden_iter"))
+    assert its
+    for it in its:
+        h = T(fix[f"hidden_iter{it}"]).to(dev)
+        want = fix[f"nd_iter{it}"]
+        nd_f, prob = upd.depth_init(h)
+        assert prob is None                                     # no probability requested -> the fused kernel ran
+        conf_f, conf0_f = upd.conf_init(h)
+        os.environ["IMVS_TUNE_HEADFUSED"] = "0"
+        try:
+            nd_u, _ = upd.depth_init(h)
+            conf_u, conf0_u = upd.conf_init(h)
+        finally:
+            del os.environ["IMVS_TUNE_HEADFUSED"]
+        err_f = np.abs(nd_f.cpu().numpy() - want)
+        err_u = np.abs(nd_u.cpu().numpy() - want)
+        d_fu = (nd_f - nd_u).abs()
+        print(f"head iter {it}: fused vs reference max {err_f.max():.2e} (>1e-4: {100 * (err_f > 1e-4).mean():.4f}%), unfused vs reference "
+              f"max {err_u.max():.2e}, fused vs unfused max {float(d_fu.max()):.2e}, conf logit fused vs unfused {float((conf0_f - conf0_u).abs().max()):.2e}")
+        assert (err_f > 1e-4).mean() < 1e-3 and np.median(err_f) < 1e-6
+        assert float((d_fu > 1e-4).float().mean()) < 1e-3
+        assert float((conf0_f - conf0_u).abs().max()) < 1e-4 and float((conf_f - conf_u).abs().max()) < 1e-5
+    # ragged tile: 5 x 7 pixels (35 < 128)
+    h = torch.randn(2, 32, 5, 7, device=dev).tanh()
+    nd_f, _ = upd.depth_init(h)
+    os.environ["IMVS_TUNE_HEADFUSED"] = "0"
+    try:
+        nd_u, _ = upd.depth_init(h)
+    finally:
+        del os.environ["IMVS_TUNE_HEADFUSED"]
+    assert float(((nd_f - nd_u).abs() > 1e-4).float().mean()) < 0.05           # near-flat random distributions: rare arg-max flips
+    assert model.iter_mvs.update is upd and _lib.lib().imvs_tcgen05_status() == 0
+
+
 def _feature_inputs(dev, width, height, n_src, batch, seed):
     ref, srcs = random_feature_pyramids(width, height, n_src, batch, seed)
     s = make_sample(width, height, n_src=n_src, batch=batch, seed=seed, scene="noise")
@@ -382,6 +425,32 @@ def test_full_size_pipeline_vs_oracle(dev, model, dtu_weights):
     assert rel.mean() < 1e-6
     assert rel.max() < 1e-4
     assert float((c - cref).abs().max()) < 1e-3
+
+
+def test_uint8_images_equal_loader_normalisation(dev, model):
+    """f-4: raw 8-bit images straight into the pipeline (a quarter of the H2D bytes); the first FeatureNet layer normalises
+    them as the reference's loaders do -- np.array(img, dtype=np.float32) / 255. (datasets/dtu_yao_eval.py:56-59) -- so
+    the result is bit-identical to feeding that float image."""
+    s = make_sample(320, 256, n_src=3, batch=1, seed=21, scene="plane")
+    u8 = ((s["imgs"]["level_0"] + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+    as_float = torch.from_numpy(u8.numpy().astype(np.float32) / 255.0)             # the loader's arithmetic, on the host
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    with torch.no_grad():
+        a = model({"level_0": u8.to(dev)}, cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+        a = {k: v.clone() for k, v in a.items()}
+        b = model({"level_0": as_float.to(dev)}, cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    assert torch.equal(a["depths_upsampled"], b["depths_upsampled"]) and torch.equal(a["confidence_upsampled"], b["confidence_upsampled"])
+    # and through the serving loop from pinned uint8 host buffers
+    from itermvs_b200.graph import StreamingPipeline
+    proj = {k: s["proj_matrices"][k].float() for k in ("level_1", "level_2", "level_3")}
+    sp = StreamingPipeline(model, {"level_0": u8.to(dev)}, cu(proj), s["depth_min"].to(dev), s["depth_max"].to(dev), n_slots=2)
+    outs = [(torch.empty(1, 1, 256, 320).pin_memory(), torch.empty(1, 1, 256, 320).pin_memory()) for _ in range(2)]
+    host = {"level_0": u8.pin_memory()}
+    for k in range(4):
+        sp.submit(host, {k_: v.pin_memory() for k_, v in proj.items()}, s["depth_min"].pin_memory(), s["depth_max"].pin_memory(), *outs[k % 2])
+    sp.drain(check_nan=True)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1][0].to(dev), b["depths_upsampled"])
 
 
 def _golden(name):
