@@ -63,6 +63,12 @@ int imvs_get_conv_passes(void);
  * mbarrier (never expected; guards against a hung GPU). */
 int imvs_set_tcgen05(int enabled);
 int imvs_tcgen05_status(void);
+/* Device status word of the library's kernels (synchronises the device; clear != 0 resets it): bit 0 = a tcgen05 kernel timed
+ * out on its mbarrier (never expected); bit 1 = FP16 RANGE: in the fp32-grade mode 4 a convolution produced a value beyond
+ * +-65504 -- the fp16 hi/lo split of the next layer saturates there (cvt.rn.satfinite) and the result would be a finite wrong
+ * number; the flag makes that loud.  Checked on every convolution's accumulators (mma.sync and tcgen05 kernels);
+ * 4 = CUDA error while reading the word. */
+int imvs_device_status(int clear);
 
 typedef struct imvs_wpair {      /* packed conv weight [tap][CinP][CoutP] */
     const float* tf32;           /* values rounded to TF32 (round-to-nearest): operand of the 1-pass mode */

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "imvs_get_conv_passes": (ci, []),
     "imvs_set_tcgen05": (ci, [ci]),
     "imvs_tcgen05_status": (ci, []),
+    "imvs_device_status": (ci, [ci]),
     "imvs_profile_begin": (ci, [ci]),
     "imvs_profile_end": (ci, [vp, vp, ci]),
     "imvs_compose_projections": (ci, [vp, ci, ci, vp, vp, vp]),
@@ -140,6 +141,22 @@ def launches_total() -> int:
 def set_conv_passes(passes: int) -> None:
     """1 = single-pass TF32 tensor-core convolutions, 3 = 3xTF32 error-compensated (fp32-grade, default)."""
     check(lib().imvs_set_conv_passes(int(passes)), "set_conv_passes")
+
+
+def device_status(clear: bool = True) -> int:
+    """Bitmask (synchronises): 1 = tcgen05 mbarrier time-out, 2 = a convolution output left the fp16 range in mode 4."""
+    return int(lib().imvs_device_status(1 if clear else 0))
+
+
+def check_device_status() -> None:
+    st = device_status(clear=True)
+    if st & 1:
+        raise RuntimeError("itermvs_b200: a tcgen05 kernel timed out on its mbarrier")
+    if st & 2:
+        raise OverflowError("itermvs_b200: a convolution output exceeded +-65504 in the fp32-grade fp16-split mode (mode 4): "
+                            "results are invalid; use imvs_set_conv_passes(3) (3xTF32) for inputs of this magnitude")
+    if st & 4:
+        raise RuntimeError("itermvs_b200: CUDA error while reading the device status word")
 
 
 def get_conv_passes() -> int:

@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(HF_THREADS, 2) head_fused_kernel(const Params 
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaxf(v[8 * j + i], 0.f);
+                float amax = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) amax = fmaxf(amax, x[i]);
+                if (!(amax <= 65504.f) && prm.err_flag) atomicOr(prm.err_flag, 2);      // fp16 range guard (imvs_device_status)
                 uint4 hi, lo;
                 split8(x, hi, lo);
                 const int kc = half * 4 + c * 2 + j;

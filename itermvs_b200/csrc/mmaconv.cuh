@@ -284,6 +284,7 @@ struct MmaWeightSel {       // image n of a batched launch picks one of up to th
     const float* w[3];      // [slice][CINP][cout_total]: TF32-rounded (PASSES 1) or plain fp32 (PASSES 3);
                             // PASSES 4: [slice][CINK/2][cout_total] uint2 = (hi half2, lo half2) of a channel pair
     int period, split1, split2;
+    int* status;            // device status word (imvs_device_status): bit 1 <- an accumulator left the fp16 range in mode 4
     __device__ __forceinline__ const float* pick(int n) const {
         if (period == 1) return w[0];
         const int r = n % period;
@@ -524,6 +525,17 @@ mma_conv_kernel(const In in, const Epi epi, const MmaWeightSel wsel, const TapTa
                     acc[r][j][q] += cross;
                 }
     }
+    // fp16-split modes: a value beyond +-65504 would saturate in the NEXT layer's split (cvt.rn.satfinite) -- raise the flag
+    if constexpr (Cfg::PASSES >= 4) {
+        float amax = 0.f;
+#pragma unroll
+        for (int r = 0; r < MT; ++r)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) amax = fmaxf(amax, fabsf(acc[r][j][q]));
+        if (!(amax <= 65504.f) && wsel.status) atomicOr(wsel.status, 2);
+    }
     // epilogue: thread holds, per row-tile r and half h, couts {8j + 2t, 8j + 2t + 1} of pixel x = g + 8h
 #pragma unroll
     for (int r = 0; r < MT; ++r) {
@@ -561,6 +573,7 @@ int launch_mma_conv(const char* name, const In& in, const Epi& epi, const MmaWei
 }
 
 int tune(const char* name, int def);   // IMVS_TUNE_<NAME> experiment switch, defined in warp.cu
+int* tc5_error_flag();                 // the device status word (warp.cu), or nullptr
 int conv_passes();       // process-wide precision switch (imvs_set_conv_passes), defined in warp.cu
 
 struct WSets {           // host-side: up to three packed weights + the slice -> set mapping
@@ -575,6 +588,7 @@ int mma_conv(const char* name, const In& in, const Epi& epi, const WSets& ws, co
              int cout_total, int Hout, int Wout, int ncb, cudaStream_t st) {
     MmaWeightSel sel;
     sel.period = ws.period; sel.split1 = ws.split1; sel.split2 = ws.split2;
+    sel.status = tc5_error_flag();
     if (conv_passes() == 4) {
         for (int i = 0; i < 3; ++i) sel.w[i] = static_cast<const float*>(ws.w[i].f16x3);
         if constexpr (CINP == 8) {

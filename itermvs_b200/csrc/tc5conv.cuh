@@ -308,7 +308,7 @@ inline Geometry make_geometry_h(int ks, int dil, int Wout, int kc) {
 }
 
 template <int CINP, int NB, class In, class Epi>
-__global__ void __launch_bounds__(TC5_THREADS)
+__global__ void __launch_bounds__(TC5_THREADS, 5)
 tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, const Geometry geo, int Hout, int Wout, int* err_flag) {
     static_assert(CINP % 16 == 0 && NB % 16 == 0 && NB <= 256, "UMMA kind::f16 shape");
     constexpr int KC = CINP / 8;                                 // 16-byte K chunks (8 halves)
@@ -318,6 +318,7 @@ tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, con
     constexpr int NC = NB / 2;                                   // epilogue columns per thread
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nslot = geo.nslot, WT = geo.WT, pad = geo.pad, dil = geo.dil, ks = geo.ks;
+    const int wsh = WT == 64 ? 6 : 5;                            // WT is 32 or 64
     const int ntaps = ks * ks;
     const uint32_t a_bytes = (uint32_t)KC * nslot * 16;          // one of hi / lo
     constexpr uint32_t b_tap_bytes = KC * NB * 16;               // one of hi / lo, one tap
@@ -351,7 +352,7 @@ tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, con
     //      128 contiguous bytes per pixel; UI iterations (32 registers of loads) are in flight before the first conversion.
     {
         constexpr int G = (KC + CPL - 1) / CPL;                  // chunk groups per slot
-        constexpr int UI = 4 / G > 0 ? 4 / G : 1;                // iterations in flight
+        constexpr int UI = CPL == 2 ? 2 : (4 / G > 0 ? 4 / G : 1);   // iterations in flight: 256 (G = 1) or 128 slots per round
         constexpr int PER_IT = (TC5_THREADS / 32) * SPW;         // slots per iteration of the whole CTA
         const int kcl = lane % CPL, sl = lane / CPL;
         const auto img = in.image(n);
@@ -361,7 +362,7 @@ tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, con
 #pragma unroll
             for (int u = 0; u < UI; ++u) {
                 const int s = s0 + u * PER_IT + warp * SPW + sl;
-                const int iy = oy0 - pad + s / WT, ix = ox0 - pad + (s & (WT - 1));
+                const int iy = oy0 - pad + (s >> wsh), ix = ox0 - pad + (s & (WT - 1));
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const int kc = g * CPL + kcl;
@@ -424,17 +425,20 @@ tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, con
         }
         umma_commit(bar_d);
     }
-    // ---- epilogue: warp w owns TMEM lanes 32*(w&3).. (= slots) and the column half (w>>2); thread = one pixel
+    // ---- epilogue: warp w owns TMEM lanes 32*(w&3).. (= slots) and the column half (w>>2); thread = one pixel.  What the
+    //      epilogue reads from global memory besides the accumulator (residual) is requested BEFORE the wait on the MMAs.
     {
+        const int lg = warp & 3, half = warp >> 2;
+        const int m = lg * 32 + lane;
+        const int oy = oy0 + (m >> wsh), oxl = m & (WT - 1), ox = ox0 + oxl;
+        const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
+        typename Epi::template Pre<NC> pre;
+        if (ok) epi.template prefetch<NC>(n, oy, ox, half * NC, pre);
         const bool done = mbar_wait_bounded(bar_d, 0);
         fence_after_sync();
         if (!done) {
             if (lane == 0 && err_flag) atomicExch(err_flag, 1);
         } else {
-            const int lg = warp & 3, half = warp >> 2;
-            const int m = lg * 32 + lane;
-            const int oy = oy0 + m / WT, oxl = m & (WT - 1), ox = ox0 + oxl;
-            const bool ok = (oxl < wvalid) && (oy < Hout) && (ox < Wout);
             float v[NC];
             if constexpr (NC % 16 == 0) {
 #pragma unroll
@@ -457,7 +461,13 @@ tc5h_conv_kernel(const In in, const Epi epi, const void* __restrict__ w_f16, con
                     for (int i = 0; i < 8; ++i) v[c + i] = __uint_as_float(r[i]);
                 }
             }
-            if (ok) epi.template part<NC>(n, oy, ox, half * NC, v);
+            if (ok) {
+                float amax = 0.f;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) amax = fmaxf(amax, fabsf(v[c]));
+                if (!(amax <= 65504.f) && err_flag) atomicOr(err_flag, 2);       // fp16 range guard, see imvs_device_status
+                epi.template part_pre<NC>(n, oy, ox, half * NC, v, pre);
+            }
         }
     }
     if (tid == 0 && !ok_w && err_flag) atomicExch(err_flag, 1);
@@ -501,6 +511,26 @@ struct PixNHWC {          // out[n][oy][ox][c0..c0+NC) = (v + bias) (+ residual)
     const float* bias;
     const float* residual;
     int H, W, C, relu;
+    template <int NC> struct Pre { float4 r[NC / 4]; };
+    template <int NC>
+    __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NC>& p) const {
+        if (!residual) return;
+        const size_t base = (((size_t)n * H + oy) * W + ox) * C + c0;
+#pragma unroll
+        for (int c = 0; c < NC; c += 4) p.r[c / 4] = ldg4(residual + base + c);
+    }
+    template <int NC>
+    __device__ __forceinline__ void part_pre(int n, int oy, int ox, int c0, const float (&v)[NC], const Pre<NC>& p) const {
+        const size_t base = (((size_t)n * H + oy) * W + ox) * C + c0;
+#pragma unroll
+        for (int c = 0; c < NC; c += 4) {
+            float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            if (bias) { const float4 b = ldg4(bias + c0 + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (residual) { const float4 r = p.r[c / 4]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(out + base + c) = o;
+        }
+    }
     template <int NC>
     __device__ __forceinline__ void part(int n, int oy, int ox, int c0, const float (&v)[NC]) const {
         const size_t base = (((size_t)n * H + oy) * W + ox) * C + c0;
@@ -521,6 +551,8 @@ struct PixGruZR {         // 64 stacked channels: c0 = 0 -> z = sigmoid (32), c0
     float* z;
     float* rh;
     int H, W;
+    int precise = 0;      // 1: expf-based sigmoid (the fp32-grade mode); 0: ex2.approx (TF32 mode)
+    __device__ __forceinline__ float sg(float x) const { return precise ? sigmoidf_(x) : fast_sigmoid(x); }
     template <int NC>
     __device__ __forceinline__ void part(int n, int oy, int ox, int c0, const float (&v)[NC]) const {
         static_assert(NC == 32, "z | r halves");
@@ -529,18 +561,21 @@ struct PixGruZR {         // 64 stacked channels: c0 = 0 -> z = sigmoid (32), c0
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
                 const float4 b = ldg4(bias + c);
-                *reinterpret_cast<float4*>(z + base + c) = make_float4(fast_sigmoid(v[c] + b.x), fast_sigmoid(v[c + 1] + b.y),
-                                                                        fast_sigmoid(v[c + 2] + b.z), fast_sigmoid(v[c + 3] + b.w));
+                *reinterpret_cast<float4*>(z + base + c) = make_float4(sg(v[c] + b.x), sg(v[c + 1] + b.y), sg(v[c + 2] + b.z), sg(v[c + 3] + b.w));
             }
         } else {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
                 const float4 b = ldg4(bias + 32 + c), hh = ldg4(h + base + c);
-                *reinterpret_cast<float4*>(rh + base + c) = make_float4(fast_sigmoid(v[c] + b.x) * hh.x, fast_sigmoid(v[c + 1] + b.y) * hh.y,
-                                                                         fast_sigmoid(v[c + 2] + b.z) * hh.z, fast_sigmoid(v[c + 3] + b.w) * hh.w);
+                *reinterpret_cast<float4*>(rh + base + c) = make_float4(sg(v[c] + b.x) * hh.x, sg(v[c + 1] + b.y) * hh.y,
+                                                                         sg(v[c + 2] + b.z) * hh.z, sg(v[c + 3] + b.w) * hh.w);
             }
         }
     }
+    template <int NC> struct Pre {};
+    template <int NC> __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NC>&) const {}
+    template <int NC>
+    __device__ __forceinline__ void part_pre(int n, int oy, int ox, int c0, const float (&v)[NC], const Pre<NC>&) const { part<NC>(n, oy, ox, c0, v); }
 };
 
 struct PixGruQ {          // 32 channels in two halves: q = tanh, h <- (1-z) h + z q in place   (module.py:63-64)
@@ -548,6 +583,8 @@ struct PixGruQ {          // 32 channels in two halves: q = tanh, h <- (1-z) h +
     const float* z;
     float* h;
     int H, W;
+    int precise = 0;      // 1: tanhf (the fp32-grade mode); 0: ex2.approx based (TF32 mode)
+    __device__ __forceinline__ float th(float x) const { return precise ? tanhf(x) : fast_tanh(x); }
     template <int NC>
     __device__ __forceinline__ void part(int n, int oy, int ox, int c0, const float (&v)[NC]) const {
         const size_t base = (((size_t)n * H + oy) * W + ox) * 32 + c0;
@@ -555,13 +592,17 @@ struct PixGruQ {          // 32 channels in two halves: q = tanh, h <- (1-z) h +
         for (int c = 0; c < NC; c += 4) {
             const float4 b = ldg4(bias + c0 + c), zz = ldg4(z + base + c);
             float4 hh = *reinterpret_cast<const float4*>(h + base + c);
-            hh.x = (1.f - zz.x) * hh.x + zz.x * fast_tanh(v[c] + b.x);
-            hh.y = (1.f - zz.y) * hh.y + zz.y * fast_tanh(v[c + 1] + b.y);
-            hh.z = (1.f - zz.z) * hh.z + zz.z * fast_tanh(v[c + 2] + b.z);
-            hh.w = (1.f - zz.w) * hh.w + zz.w * fast_tanh(v[c + 3] + b.w);
+            hh.x = (1.f - zz.x) * hh.x + zz.x * th(v[c] + b.x);
+            hh.y = (1.f - zz.y) * hh.y + zz.y * th(v[c + 1] + b.y);
+            hh.z = (1.f - zz.z) * hh.z + zz.z * th(v[c + 2] + b.z);
+            hh.w = (1.f - zz.w) * hh.w + zz.w * th(v[c + 3] + b.w);
             *reinterpret_cast<float4*>(h + base + c) = hh;
         }
     }
+    template <int NC> struct Pre {};
+    template <int NC> __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NC>&) const {}
+    template <int NC>
+    __device__ __forceinline__ void part_pre(int n, int oy, int ox, int c0, const float (&v)[NC], const Pre<NC>&) const { part<NC>(n, oy, ox, c0, v); }
 };
 
 }  // namespace tc5

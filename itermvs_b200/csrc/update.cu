@@ -189,6 +189,16 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
                                       w->gru_q.umma, 3, 2, B, H, W, tc5_error_flag(), st)));
         return 0;
     }
+#ifndef CUSIM
+    if (conv_passes() == 4 && w->gru_zr.f16umma && w->gru_q.f16umma && tune("TC5H_GRU", 0)) {
+        // fp32-grade mode on tcgen05: fp16 hi/lo 3-product chains (tc5conv.cuh:tc5h_conv_kernel), exact-grade gates
+        IMVS_TRY((tc5::launch_h<48, 64>("gru.zr(tcgen05 f16x3)", InNHWC2{h, x, H, W, 32, IMVS_XCH}, tc5::PixGruZR{w->gru_zr_b, h, z, rh, H, W, 1},
+                                        w->gru_zr.f16umma, 3, 2, B, H, W, tc5_error_flag(), st)));
+        IMVS_TRY((tc5::launch_h<48, 32>("gru.q(tcgen05 f16x3)", InNHWC2{rh, x, H, W, 32, IMVS_XCH}, tc5::PixGruQ{w->gru_q_b, z, h, H, W, 1},
+                                        w->gru_q.f16umma, 3, 2, B, H, W, tc5_error_flag(), st)));
+        return 0;
+    }
+#endif
     const InNHWC2 in_zr{h, x, H, W, 32, IMVS_XCH}, in_q{rh, x, H, W, 32, IMVS_XCH};
     const EpiGruZR ezr{w->gru_zr_b, h, z, rh, H, W};
     const EpiGruQ eq{w->gru_q_b, z, h, H, W};

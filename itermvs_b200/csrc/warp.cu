@@ -276,8 +276,18 @@ extern "C" int imvs_tc5_debug_clocks(int on, long long* out16) {   // debug: pha
 }
 extern "C" int imvs_tcgen05_status(void) {
     int v = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
-    if (cudaMemcpyFromSymbol(&v, g_tc5_err, sizeof(int)) != cudaSuccess) return 2;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 4;
+    if (cudaMemcpyFromSymbol(&v, g_tc5_err, sizeof(int)) != cudaSuccess) return 4;
+    return v & 1;
+}
+extern "C" int imvs_device_status(int clear) {
+    int v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 4;
+    if (cudaMemcpyFromSymbol(&v, g_tc5_err, sizeof(int)) != cudaSuccess) return 4;
+    if (clear && v) {
+        const int zero = 0;
+        if (cudaMemcpyToSymbol(g_tc5_err, &zero, sizeof(int)) != cudaSuccess) return 4;
+    }
     return v;
 }
 

@@ -318,6 +318,8 @@ template <class T>
 static inline cudaError_t cudaGetSymbolAddress(void** p, T& sym) { *p = (void*)&sym; return cudaSuccess; }
 template <class T>
 static inline cudaError_t cudaMemcpyFromSymbol(void* dst, const T& sym, size_t n) { std::memcpy(dst, &sym, n); return cudaSuccess; }
+template <class T>
+static inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) { std::memcpy((void*)&sym, src, n); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }

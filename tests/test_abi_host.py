@@ -70,14 +70,19 @@ def test_tf32_split_and_packing(dtu_weights):
     assert torch.equal(_pack.round_tf32(t), torch.tensor([1.0 + 2 ** -10, -(1.0 + 2 ** -10)]))
     # conv packing: [Cout,Cin,3,3] -> [9][CinP][CoutP]
     w = dtu_weights["iter_mvs.update.gru.convq.weight"]
-    hi, full, um, f16 = _pack.pack_mma_conv(w, cinp=48)
+    hi, full, um, f16, f16u = _pack.pack_mma_conv(w, cinp=48)
+    # tcgen05 fp16 order [tap][hi|lo][CinK/8][CoutP][8 halves]: hi + lo reproduces the weight to fp32 grade
+    assert f16u.shape == (9, 2, 6, 32, 8) and f16u.dtype == torch.float16
+    rec16 = (f16u[:, 0].float() + f16u[:, 1].float()).permute(0, 1, 3, 2).reshape(9, 48, 32)
+    assert bool(((rec16 - full).abs() <= full.abs() * 2.0 ** -21 + 2.0 ** -24).all())
+    assert torch.equal(f16u[4, 0, 1, 7, 3], full[4, 11, 7].half())
     assert um.shape == (1, 9, 12, 32, 4) and torch.equal(um[0, 4, 3, 7], hi[4, 12:16, 7])
     assert hi.shape == (9, 48, 32)
     rec = full[:, :43, :].reshape(3, 3, 43, 32).permute(3, 2, 0, 1)
     assert torch.equal(rec, w)
     assert float(hi[:, 43:, :].abs().max()) == 0.0
     wt = dtu_weights["iter_mvs.evaluation.corr_conv1.0.conv3.weight"]          # ConvTranspose [Cin,Cout,3,3]
-    hi, full, _, _ = _pack.pack_mma_tconv(wt)
+    hi, full, _, _, _ = _pack.pack_mma_tconv(wt)
     assert hi.shape == (9, 32, 16)
     assert torch.equal(full[4], wt[:, :, 1, 1])
 
@@ -99,9 +104,30 @@ def test_fp16_split_packing(dtu_weights):
     err = (rr - ww).abs()
     assert bool((err <= ww.abs() * 2.0 ** -21 + 2.0 ** -24).all())
     # a real layer: the packed pair order matches the fp32 packing
-    _, full, _, f16 = _pack.pack_mma_conv(dtu_weights["iter_mvs.update.gru.convq.weight"], cinp=48)
+    _, full, _, f16, _ = _pack.pack_mma_conv(dtu_weights["iter_mvs.update.gru.convq.weight"], cinp=48)
     h = f16.view(torch.float16).reshape(9, 24, 32, 2, 2)
     assert torch.equal(h[4, 5, 7, 0, 1], full[4, 11, 7].half()) and torch.equal(h[4, 5, 7, 0, 0], full[4, 10, 7].half())
+
+
+def test_fused_head_blob_layout(dtu_weights):
+    """csrc/headfused.cuh operand blob: W1 hi | W1 lo | W2 hi | W2 lo in the UMMA K-major canonical order [K/8][N][8 halves],
+    then the fp32 bias."""
+    from itermvs_b200 import _pack
+    w1 = dtu_weights["iter_mvs.update.depth_head.2.weight"]
+    w2 = dtu_weights["iter_mvs.update.depth_head.4.weight"]
+    b2 = dtu_weights["iter_mvs.update.depth_head.4.bias"]
+    blob = _pack.pack_head_fused(w1, w2, b2)
+    assert blob.dtype == torch.uint8 and blob.numel() == 2 * 4096 + 2 * 32768 + 1024
+    h = blob[:2 * 4096 + 2 * 32768].view(torch.float16)
+    w1hi, w1lo = h[:2048].reshape(4, 64, 8), h[2048:4096].reshape(4, 64, 8)
+    w2hi, w2lo = h[4096:4096 + 16384].reshape(8, 256, 8), h[4096 + 16384:].reshape(8, 256, 8)
+    n, k = 37, 21
+    assert torch.equal(w1hi[k // 8, n, k % 8], w1[n, k, 0, 0].half())
+    assert abs(float(w1hi[k // 8, n, k % 8]) + float(w1lo[k // 8, n, k % 8]) - float(w1[n, k, 0, 0])) <= abs(float(w1[n, k, 0, 0])) * 2.0 ** -21 + 2.0 ** -24   # fp16-subnormal remainder floor
+    n, k = 201, 60
+    assert torch.equal(w2hi[k // 8, n, k % 8], w2[n, k, 0, 0].half())
+    assert abs(float(w2hi[k // 8, n, k % 8]) + float(w2lo[k // 8, n, k % 8]) - float(w2[n, k, 0, 0])) <= abs(float(w2[n, k, 0, 0])) * 2.0 ** -21 + 2.0 ** -24
+    assert torch.equal(blob[-1024:].view(torch.float32), b2)
 
 
 def test_fp16_split_product_accuracy():

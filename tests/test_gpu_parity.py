@@ -453,6 +453,27 @@ def test_uint8_images_equal_loader_normalisation(dev, model):
     assert torch.equal(outs[1][0].to(dev), b["depths_upsampled"])
 
 
+def test_fp16_range_guard(dev, model):
+    """Mode 4 splits activations into fp16 hi + lo; beyond +-65504 the split saturates and the result would be a finite wrong
+    number.  Every convolution checks its accumulators and raises bit 1 of the device status word -- the silent failure
+    mode is loud: images scaled by 1e6 trip it, normal inputs do not."""
+    from itermvs_b200 import _lib
+    s = make_sample(320, 256, n_src=2, batch=1, seed=31, scene="plane")
+    cu = lambda x: {k: v.to(dev) for k, v in x.items()}
+    _lib.device_status(clear=True)
+    with torch.no_grad():
+        model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    assert _lib.device_status(clear=True) == 0
+    _lib.check_device_status()
+    big = {"level_0": (s["imgs"]["level_0"] * 1e6).to(dev)}
+    with torch.no_grad():
+        model(big, cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    assert _lib.device_status(clear=False) & 2
+    with pytest.raises(OverflowError):
+        _lib.check_device_status()
+    assert _lib.device_status(clear=True) == 0
+
+
 def _golden(name):
     import os
     with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)) as z:
