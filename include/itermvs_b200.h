@@ -283,6 +283,14 @@ typedef struct imvs_problem {
     int iterations;   /* GRU iterations (>= 1) */
 } imvs_problem;
 
+/* a7, models/itermvs.py:74-81 -- the init branch's own depth estimate (training loss term depths["initial"]): softmax over the
+ * D hypotheses of the init CorrNet output, expectation, depth_unnormalization, bilinear x2.
+ * corr element (b, d, p) at b*batch_stride + d*slice_stride + p*pixel_stride; scratch: B*H3*W3 floats;
+ * depth_out: [B][2*H3][2*W3]. */
+int imvs_init_depth(const float* corr, size_t batch_stride, size_t slice_stride, size_t pixel_stride,
+                    const float* depth_min, const float* depth_max, float* scratch, float* depth_out,
+                    int B, int D, int H3, int W3, void* stream);
+
 size_t imvs_forward_workspace_bytes(const imvs_problem* pb);
 
 /* fea1/2/3: channels-last pyramids [B][V][H_l][W_l][C_l]; proj1/2/3: [B][V][4][4] fp32.

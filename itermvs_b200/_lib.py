@@ -79,6 +79,7 @@ _SIGNATURES = {
     "imvs_upsample_outputs": (ci, [PW, vp, sz, vp, sz, sz, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]),
     "imvs_check_geometric_consistency": (ci, [vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
     "imvs_filter_depth_view": (ci, [vp, vp, vp, vp, ci, C.c_float, C.c_float, C.c_float, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
+    "imvs_init_depth": (ci, [vp, sz, sz, sz, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_forward_workspace_bytes": (sz, [C.POINTER(Problem)]),
     "imvs_forward_launch_count": (ci, [C.POINTER(Problem)]),
     "imvs_itermvs_forward": (ci, [C.POINTER(Problem), PW, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -99,6 +99,32 @@ int launch_upsample2x_nhwc(const float* in, float* out, int N, int H, int W, int
     return 0;
 }
 
+// a7, models/itermvs.py:74-81 (the init branch's own depth estimate; consumed by the training loss only): softmax over the D
+// hypotheses of the CorrNet output, expectation of the hypothesis index, / (D - 1), depth_unnormalization (module.py:148-152).
+// corr element (b, d, p) at b * bstride + d * dstride + p * pstride (planar [B][D][P] or channels-last [B][P][D]).
+__global__ void init_expectation_kernel(const float* __restrict__ corr, size_t bstride, size_t dstride, size_t pstride,
+                                        const float* __restrict__ depth_min, const float* __restrict__ depth_max,
+                                        float* __restrict__ depth3, int B, int D, int P) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)B * P) return;
+    const int b = (int)(t / P), p = (int)(t % P);
+    const float* c = corr + (size_t)b * bstride + (size_t)p * pstride;
+    float m = ldg(c);
+    for (int d = 1; d < D; ++d) m = fmaxf(m, ldg(c + (size_t)d * dstride));
+    float s = 0.f, num = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float e = expf(ldg(c + (size_t)d * dstride) - m);
+        s += e;
+        num = fmaf((float)d, e, num);
+    }
+    // sum_d d * (e_d / s), as torch.sum(index * softmax) does, up to the rounding of the common division
+    const float nd = (num / s) / (float)(D - 1);
+    const float inv_min = 1.0f / depth_min[b], inv_max = 1.0f / depth_max[b];
+    depth3[t] = unnormalize_depth(nd, inv_min, inv_max);
+}
+
 template <int D>
 static int hinit_conv0(const imvs_weights* w, const float* corr, float* t, int B, int H3, int W3, cudaStream_t st) {
     return mma_conv<D, 64, 2, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), EpiNHWC{t, nullptr, nullptr, H3, W3, 64, 64, 1},
@@ -181,4 +207,18 @@ extern "C" int imvs_hidden_init(const imvs_weights* w, const float* corr, float*
     IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("hidden_init.fc", in_nhwc(t, H3, W3, 64), EpiNHWC{u, w->hinit_fc_b, nullptr, H3, W3, 32, 32, 0},
                                               WSets::single(w->hinit_fc), conv_tables(1, 1, 1, 8), B, 32, H3, W3, 1, st)));
     return launch_upsample2x_nhwc(u, hidden, B, H3, W3, 32, true, st);
+}
+
+extern "C" int imvs_init_depth(const float* corr, size_t batch_stride, size_t slice_stride, size_t pixel_stride,
+                               const float* depth_min, const float* depth_max, float* scratch, float* depth_out,
+                               int B, int D, int H3, int W3, void* stream) {
+    IMVS_REQUIRE(corr && depth_min && depth_max && scratch && depth_out, "init_depth: null pointer");
+    IMVS_REQUIRE(B >= 1 && D >= 2 && H3 >= 1 && W3 >= 1, "init_depth: bad shape");
+    ApiScope api_;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)B * H3 * W3;
+    IMVS_CUDA(launch_k(init_expectation_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, corr, batch_stride, slice_stride,
+                       pixel_stride, depth_min, depth_max, scratch, B, D, H3 * W3));
+    // F.interpolate(depth, scale_factor=2, mode="bilinear") (itermvs.py:80)
+    return launch_upsample2x_nhwc(scratch, depth_out, B, H3, W3, 1, false, st);
 }

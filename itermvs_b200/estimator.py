@@ -288,12 +288,13 @@ class Evaluation(nn.Module):
             _lib.check(L.imvs_corrnet(sets, 1, 1, 1, agg.data_ptr(), out.data_ptr(), h3 * w3, 1, scratch.data_ptr(), b * d, h3, w3,
                                       st), "corrnet")
             flag.raise_if_set()
-            # itermvs.py:74-81 (only consumed by the training loss)
-            probability = torch.softmax(out, dim=1)
-            index = torch.arange(0, d, 1, device=dev, dtype=torch.float32).view(1, d, 1, 1)
-            nd = torch.sum(index * probability, dim=1, keepdim=True) / (d - 1.0)
-            depth = ops.depth_unnormalization(nd, inverse_depth_min, inverse_depth_max)
-            depth = torch.nn.functional.interpolate(depth, scale_factor=2, mode="bilinear")
+            # itermvs.py:74-81 (only consumed by the training loss): softmax expectation -> depth -> bilinear x2, one C call
+            dmin = (1.0 / inverse_depth_min.reshape(b).float()).contiguous()
+            dmax = (1.0 / inverse_depth_max.reshape(b).float()).contiguous()
+            depth = torch.empty(b, 1, 2 * h3, 2 * w3, device=dev)
+            scr = torch.empty(b * h3 * w3, device=dev)
+            _lib.check(L.imvs_init_depth(out.data_ptr(), d * h3 * w3, h3 * w3, 1, dmin.data_ptr(), dmax.data_ptr(), scr.data_ptr(),
+                                         depth.data_ptr(), b, d, h3, w3, st), "init_depth")
             return vw2, out, depth
         # ---- iteration branch (itermvs.py:84-126)
         ref2 = ops._chk(ref_feature["level2"], "ref_feature")
