@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IMVS_ABI_VERSION 4
+#define IMVS_ABI_VERSION 5
 #define IMVS_GROUPS 8          /* reference models/itermvs.py:28 */
 #define IMVS_OUT_BINS 256      /* reference models/itermvs.py:134 */
 #define IMVS_RADIUS 4          /* reference models/itermvs.py:135 */
@@ -327,6 +327,20 @@ int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs,
 int imvs_featurenet_forward_u8(const imvs_featurenet_weights* w, const unsigned char* imgs, float* fea1, float* fea2, float* fea3,
                                void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream);
 int imvs_featurenet_launch_count(void);
+
+/* Stride-1 3x3 convolution (dilation dil, zero padding dil) + bias (+ residual) (+ ReLU) on fp32 NHWC tensors through the
+ * persistent TMA + tcgen05 kernel (csrc/tc5pconv.cuh) in the fp32-grade mode: operands as fp16 hi / lo "split planes"
+ * [N][C/8][H][W][8 halves] loaded by cp.async.bulk.tensor, three products per tap into a TMEM accumulator.  The operator
+ * behind nn.Conv2d(Cin, Cout, 3, padding=dil, dilation=dil) of models/module.py:6-50 (ConvBnReLU / ResidualBlock with the
+ * BatchNorm folded) and models/net.py:18-20 (output convolutions) inside imvs_featurenet_forward, exposed for tests.
+ * w_f16umma: imvs_wpair::f16umma of the layer; (Cin, Cout) in {(16,16), (32,32), (48,48), (48,32), (48,16)} with dil = 1,
+ * (32,32) also with dil = 2;
+ * x: [N][H][W][Cin], residual (may be NULL) and out: [N][H][W][Cout]; via_split_output != 0 stores the result as split
+ * planes first (the layout the next layer's TMA loads read) and converts back. */
+size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int imvs_conv3x3_tcgen05(const float* x, const void* w_f16umma, const float* bias, const float* residual, float* out,
+                         void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int dil, int relu,
+                         int via_split_output, void* stream);
 
 /* profiling taps (bench.py): CUDA-event pair around every stage of the two forward functions */
 int imvs_profile_begin(int capacity);

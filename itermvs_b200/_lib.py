@@ -18,7 +18,7 @@ _lib = None
 vp = C.c_void_p
 ci = C.c_int
 sz = C.c_size_t
-ABI_VERSION = 4
+ABI_VERSION = 5
 FNET_CONVS = 24
 
 
@@ -80,6 +80,8 @@ _SIGNATURES = {
     "imvs_check_geometric_consistency": (ci, [vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
     "imvs_filter_depth_view": (ci, [vp, vp, vp, vp, ci, C.c_float, C.c_float, C.c_float, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
     "imvs_init_depth": (ci, [vp, sz, sz, sz, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "imvs_conv3x3_tcgen05_workspace_bytes": (sz, [ci, ci, ci, ci, ci]),
+    "imvs_conv3x3_tcgen05": (ci, [vp, vp, vp, vp, vp, vp, sz, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "imvs_forward_workspace_bytes": (sz, [C.POINTER(Problem)]),
     "imvs_forward_launch_count": (ci, [C.POINTER(Problem)]),
     "imvs_itermvs_forward": (ci, [C.POINTER(Problem), PW, vp, vp, vp, vp, vp, vp, vp, vp,

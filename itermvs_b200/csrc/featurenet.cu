@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "mmaconv.cuh"
 #include "tc5conv.cuh"
+#include "tc5pconv.cuh"
 
 namespace imvs {
 
@@ -35,6 +36,39 @@ struct EpiAddUp2 {
             const float uy = (1.f - lh) * ((1.f - lw) * a.y + lw * b.y) + lh * ((1.f - lw) * c.y + lw * d.y);
             *reinterpret_cast<float2*>(out + base + co) =
                 make_float2(ux + (v[2 * j] + ldg(bias + co)), uy + (v[2 * j + 1] + ldg(bias + co + 1)));
+        }
+    }
+};
+
+// EpiAddUp2 for the tcgen05 / TMA path: the sum is written as split planes [N][C/8][H][W][8 halves] (operand of the
+// output convolution, tc5pconv.cuh) and, when another lateral stage upsamples it, also as fp32 NHWC
+struct EpiAddUp2H {
+    float* out32;            // [N][H][W][C] or nullptr
+    tc5p::Split out;         // split planes
+    const float* bias;       // [C]
+    const float* coarse;     // [N][H/2][W/2][C] fp32
+    int H, W, C;
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
+        if (oy >= H || ox >= W) return;
+        const int Hc = H / 2, Wc = W / 2;
+        int h0, h1, w0, w1;
+        float lh, lw;
+        up_index(oy, 0.5f, Hc, h0, h1, lh);
+        up_index(ox, 0.5f, Wc, w0, w1, lw);
+        const float* cb = coarse + (size_t)n * Hc * Wc * C;
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int co = co0 + 8 * j + 2 * t;
+            if (co >= C) continue;
+            const float2 a = ldg2(cb + ((size_t)h0 * Wc + w0) * C + co), b = ldg2(cb + ((size_t)h0 * Wc + w1) * C + co);
+            const float2 c = ldg2(cb + ((size_t)h1 * Wc + w0) * C + co), d = ldg2(cb + ((size_t)h1 * Wc + w1) * C + co);
+            const float ux = (1.f - lh) * ((1.f - lw) * a.x + lw * b.x) + lh * ((1.f - lw) * c.x + lw * d.x);
+            const float uy = (1.f - lh) * ((1.f - lw) * a.y + lw * b.y) + lh * ((1.f - lw) * c.y + lw * d.y);
+            const float ox_ = ux + (v[2 * j] + ldg(bias + co)), oy_ = uy + (v[2 * j + 1] + ldg(bias + co + 1));
+            if (out32) *reinterpret_cast<float2*>(out32 + ((size_t)n * plane + pix) * C + co) = make_float2(ox_, oy_);
+            store_split_pair(out.hi, out.lo, (((size_t)n * (C / 8) + (co >> 3)) * plane + pix) * 8 + (co & 7), ox_, oy_);
         }
     }
 };
@@ -135,6 +169,7 @@ fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, c
 
 struct FnetBuffers {
     float *a0, *l1[4], *l2[4], *l3[4], *intra2, *intra1;
+    float *l3s, *intra2s;     // split-plane copies (tc5pconv.cuh) of l3[3] and intra2, which are also read as fp32
     size_t total;
 };
 
@@ -149,6 +184,8 @@ static FnetBuffers fnet_carve(float* base, size_t N, size_t H, size_t W) {
     for (int i = 0; i < 4; ++i) b.l3[i] = at(N * (hw / 64) * 48);
     b.intra2 = at(N * (hw / 16) * 48);
     b.intra1 = at(N * (hw / 4) * 48);
+    b.l3s = at(N * (hw / 64) * 48);
+    b.intra2s = at(N * (hw / 16) * 48);
     b.total = c;
     return b;
 }
@@ -193,6 +230,87 @@ static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, fl
     return 0;
 }
 
+// The same residual stage on the persistent TMA + tcgen05 kernel (tc5pconv.cuh): every activation between the stride-2
+// GEMM and the stage's last convolution lives as fp16 hi / lo split planes (written by the producers' epilogues, loaded
+// by TMA, never converted by a thread); the trunk output is fp32 NHWC for its fp32 consumers (next stride-2 GEMM, lateral
+// 1x1) plus, for stage 3, split planes for output3.
+template <int CI, int CO, bool WALL_A, int NBA = 2 * CO, int MT = 2, int WARPS = 4>
+static int res_stage_p(const imvs_featurenet_weights* w, int L, const float* x, float* const buf[4], float* trunk_split, int N, int Hin,
+                       int Win, cudaStream_t st) {
+    const int H = Hin / 2, W = Win / 2;
+    const size_t elems = (size_t)N * H * W * CO;
+    const tc5p::Split y1 = tc5p::split_at(buf[0], elems), ds = tc5p::split_at(buf[1], elems), b0 = tc5p::split_at(buf[2], elems);
+    const tc5p::Split none{nullptr, nullptr}, ts = trunk_split ? tc5p::split_at(trunk_split, elems) : none;
+    const TapTables s2 = conv_tables(3, 2, 1, WARPS * MT);
+    constexpr int NCA = 2 * CO / NBA;
+    const int LS = 21 + (L - 1) / 5;
+    int* flag = tc5_error_flag();
+    IMVS_TRY((mma_conv<CI, NBA, MT, WARPS, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
+                                                  EpiSplit2H{y1, ds, w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO, H, W, NCA, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block0.conv2", y1, tc5p::Epi{b0, nullptr, ds, w->b[L + 1], H, W, 1}, w->w[L + 1].f16umma, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv1", b0, tc5p::Epi{y1, nullptr, none, w->b[L + 3], H, W, 1}, w->w[L + 3].f16umma, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, buf[3], b0, w->b[L + 4], H, W, 1}, w->w[L + 4].f16umma, N, H, W, flag, st)));
+    return 0;
+}
+
+static bool fnet_tc5p_ready(const imvs_featurenet_weights* w) {
+#ifdef CUSIM
+    return false;
+#else
+    if (conv_passes() != 4 || !tune("TC5P", 1) || !tc5p::encode_tiled_fn()) return false;
+    for (int L : {2, 4, 5, 7, 9, 10, 12, 14, 15, 16, 18, 20})
+        if (!w->w[L].f16umma) return false;
+    return true;
+#endif
+}
+
+namespace tc5p {
+
+EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return (EncodeTiledFn) nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& c = cached[dev & 63];
+    if (!c && cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) c = 148;
+    return c > 0 ? c : 148;
+}
+
+__global__ void split_to_nhwc_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ x, size_t npix_total,
+                                     int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const int KC = C / 8;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // (n, kc, pixel)
+    if (i >= npix_total * KC) return;
+    const size_t pixg = i % ((size_t)HW), t = i / HW;
+    const int kc = (int)(t % KC);
+    const size_t n = t / KC;
+    const uint4 h = reinterpret_cast<const uint4*>(hi)[i], l = reinterpret_cast<const uint4*>(lo)[i];
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[q])), b = __half22float2(*reinterpret_cast<const __half2*>(&ll[q]));
+        o[2 * q] = a.x + b.x; o[2 * q + 1] = a.y + b.y;
+    }
+    float* dst = x + ((n * HW + pixg) * C + kc * 8);
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+}  // namespace tc5p
+
 }  // namespace imvs
 
 using namespace imvs;
@@ -227,6 +345,24 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
     } else {
         IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                                 WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
+    }
+    if (fnet_tc5p_ready(w)) {
+        // default: residual stages and output convolutions on the persistent TMA + tcgen05 kernel, split-plane activations
+        int* flag = tc5_error_flag();
+        const tc5p::Split none{nullptr, nullptr};
+        IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, nullptr, N, H, W, st)));              // layer1 -> l1[3]  [H/2][W/2][16]
+        IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, nullptr, N, H1, W1, st)));        // layer2 -> l2[3]  [H/4][W/4][32]
+        IMVS_TRY((res_stage_p<32, 48, false, 96, 1>(w, 11, b.l2[3], b.l3, b.l3s, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48] (+ split)
+        const tc5p::Split l3s = tc5p::split_at(b.l3s, (size_t)N * H3 * W3 * 48), i2s = tc5p::split_at(b.intra2s, (size_t)N * H2 * W2 * 48),
+                          i1s = tc5p::split_at(b.intra1, (size_t)N * H1 * W1 * 48);
+        IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16umma, N, H3, W3, flag, st)));
+        IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2H{b.intra2, i2s, w->b[17], b.l3[3], H2, W2, 48},
+                                                   WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
+        IMVS_TRY((tc5p::launch<48, 32>("fnet.output2", i2s, tc5p::Epi{none, fea2, none, w->b[18], H2, W2, 0}, w->w[18].f16umma, N, H2, W2, flag, st)));
+        IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2H{nullptr, i1s, w->b[19], b.intra2, H1, W1, 48},
+                                                   WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
+        IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16umma, N, H1, W1, flag, st)));
+        return 0;
     }
     const int w8 = tune("FNETW", 0);     // 1: 8 warps x 1 row-tile per CTA instead of 4 x 2 (same tile, twice the resident warps)
     if (w8) IMVS_TRY((res_stage<8, 16, true, true, 32, 16, 1, 8>(w, 1, b.a0, b.l1, N, H, W, st)));
@@ -290,4 +426,55 @@ extern "C" int imvs_featurenet_forward(const imvs_featurenet_weights* w, const f
 extern "C" int imvs_featurenet_forward_u8(const imvs_featurenet_weights* w, const unsigned char* imgs, float* fea1, float* fea2,
                                           float* fea3, void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
     return featurenet_forward_impl(w, nullptr, imgs, fea1, fea2, fea3, workspace, workspace_bytes, N, H, W, stream);
+}
+
+// Operator-level entry point of the persistent TMA + tcgen05 convolution (csrc/tc5pconv.cuh): stride-1 3x3 (dilation dil)
+// Cin -> Cout on fp32 NHWC tensors, fp32-grade (fp16 hi / lo split, three products, fp32 accumulation).  The fp32 operands
+// are converted to split planes in the workspace first; inside FeatureNet the producers write that layout directly.
+extern "C" size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int Cin, int Cout) {
+    if (N < 1 || H < 1 || W < 1 || Cin < 8 || Cout < 8) return 0;
+    const size_t px = (size_t)N * H * W;
+    return (px * Cin + 2 * px * Cout) * sizeof(float) + 3 * 256;
+}
+
+extern "C" int imvs_conv3x3_tcgen05(const float* x, const void* w_f16umma, const float* bias, const float* residual, float* out,
+                                    void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int dil, int relu,
+                                    int via_split_output, void* stream) {
+    IMVS_REQUIRE(x && w_f16umma && out && workspace, "conv3x3_tcgen05: null pointer");
+    IMVS_REQUIRE(N >= 1 && H >= 1 && W >= 1 && dil >= 1 && dil <= 3, "conv3x3_tcgen05: bad shape");
+    IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "conv3x3_tcgen05: workspace must be 256-byte aligned");
+    IMVS_REQUIRE(workspace_bytes >= imvs_conv3x3_tcgen05_workspace_bytes(N, H, W, Cin, Cout), "conv3x3_tcgen05: workspace too small");
+    ApiScope api_;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t px = (size_t)N * H * W;
+    auto carve = [&](size_t& off, size_t bytes) { void* p = static_cast<char*>(workspace) + off; off += (bytes + 255) / 256 * 256; return p; };
+    size_t off = 0;
+    const tc5p::Split xin = tc5p::split_at(carve(off, px * Cin * 4), px * Cin);
+    const tc5p::Split res = residual ? tc5p::split_at(carve(off, px * Cout * 4), px * Cout) : tc5p::Split{nullptr, nullptr};
+    const tc5p::Split outs = via_split_output ? tc5p::split_at(carve(off, px * Cout * 4), px * Cout) : tc5p::Split{nullptr, nullptr};
+    auto to_split = [&](const float* src, const tc5p::Split& dst, int C) -> int {
+        const size_t n = px * (C / 8);
+        IMVS_CUDA(launch_k(tc5p::nhwc_to_split_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, src, dst.hi, dst.lo, px, H * W, C));
+        return 0;
+    };
+    IMVS_TRY(to_split(x, xin, Cin));
+    if (residual) IMVS_TRY(to_split(residual, res, Cout));
+    const tc5p::Epi epi{outs, via_split_output ? nullptr : out, res, bias, H, W, relu};
+    int* flag = tc5_error_flag();
+    const int key = (Cin * 100 + Cout) * 10 + dil;
+    switch (key) {
+        case 16161: IMVS_TRY((tc5p::launch<16, 16>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        case 32321: IMVS_TRY((tc5p::launch<32, 32>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        case 32322: IMVS_TRY((tc5p::launch<32, 32, 2>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        case 48481: IMVS_TRY((tc5p::launch<48, 48>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        case 48321: IMVS_TRY((tc5p::launch<48, 32>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        case 48161: IMVS_TRY((tc5p::launch<48, 16>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        default: return fail("conv3x3_tcgen05: (Cin, Cout, dilation) = (%d, %d, %d) is not instantiated", Cin, Cout, dil);
+    }
+    if (via_split_output) {
+        const size_t n = px * (Cout / 8);
+        IMVS_CUDA(launch_k(tc5p::split_to_nhwc_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const __half*)outs.hi,
+                           (const __half*)outs.lo, out, px, H * W, Cout));
+    }
+    return 0;
 }

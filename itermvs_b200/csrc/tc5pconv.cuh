@@ -1,0 +1,463 @@
+// Persistent, warp-specialised tcgen05 implicit-GEMM convolution fed by TMA from PRE-SPLIT activations.
+//
+// The fp32-grade mode computes every convolution as three fp16 products (hi*hi + hi*lo + lo*hi, fp32 accumulation in
+// TMEM) of operands split x = hi + lo.  tc5conv.cuh:tc5h_conv_kernel reads fp32 activations and splits them while
+// staging: 17 M warp instructions per 16 -> 16 layer, one CTA per 128-pixel block, load -> convert -> MMA -> epilogue
+// strictly one after the other (ncu: long_scoreboard 9-13 per issue, no unit above 45 %).  Here the PRODUCER of an
+// activation writes it already split, as two fp16 tensors ("split planes")
+//         [N][C/8][H][W][8 halves]          (hi plane, lo plane; together the bytes of the fp32 tensor)
+// which is exactly the tcgen05 K-major / no-swizzle canonical operand order of a haloed tile: one
+// cp.async.bulk.tensor (TMA, 4-D tile {32 px * 8 halves, rows, C/8, 1}) per plane drops the tile
+//         element (slot, k)  at  (k / 8) * LBO + slot * 16 B + (k % 8) * 2 B,   slot = tile_row * 32 + tile_col
+// into shared memory, zero-filled outside the image (= the convolution's padding), with no thread touching it.
+// A stencil tap (dy, dx) is the same tile addressed (dy * 32 + dx) * 16 bytes further (tc5conv.cuh), so the A operand
+// of every tap is a shifted shared-memory descriptor.
+//
+//   grid = min(#tiles, #SMs) persistent CTAs of 320 threads:
+//     warp 0      TMA producer: tile t+1.. into a ring of NSTAGES shared-memory stages (full / empty mbarriers)
+//     warp 1      MMA issuer: MB (1 or 2) M-blocks of 128 slots x 9 taps x 3 products x CINP/16 k-steps of
+//                 tcgen05.mma.kind::f16 into one of TWO TMEM accumulator sets; tcgen05.commit frees the stage and
+//                 publishes the accumulator
+//     warps 2..9  epilogue: tcgen05.ld, bias / residual (read from split planes) / ReLU, fp16 range guard, and the
+//                 stores: split planes for the next tcgen05 layer and / or fp32 NHWC for the other consumers.  The
+//                 residual of tile t+1 is requested before tile t is processed.
+//   weights ([tap][hi | lo][CINP/8][NB][8 halves], _pack.py:pack_umma_f16) stay resident in shared memory.
+// Tile = 32 slots wide (30 valid output columns for a 3x3), 4 * MB output rows.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "mmaconv.cuh"
+#include "tc5conv.cuh"
+
+namespace imvs {
+namespace tc5p {
+
+using tc5::smem_u32;
+using tc5::mbar_init;
+using tc5::fence_mbar_init;
+using tc5::mbar_expect_tx;
+using tc5::mbar_wait_bounded;
+using tc5::bulk_g2s;
+using tc5::tmem_alloc;
+using tc5::tmem_dealloc;
+using tc5::fence_before_sync;
+using tc5::fence_after_sync;
+using tc5::umma_commit;
+using tc5::umma_f16k;
+using tc5::make_desc;
+using tc5::make_idesc_f16k;
+
+constexpr int WT = 32;                 // slots per tile row
+constexpr int THREADS = 320;           // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int MAX_STAGES = 6;
+
+// one activation tensor stored as split planes [N][C/8][H][W][8 halves]
+struct Split {
+    __half* hi;
+    __half* lo;
+};
+inline Split split_at(void* base, size_t elems) {     // the two planes of a tensor of `elems` values packed back to back
+    return Split{static_cast<__half*>(base), static_cast<__half*>(base) + elems};
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Geo {
+    int tiles_x, tiles_y, n_tiles;
+    int THo;             // output rows per tile = 4 * MB
+    int rows;            // tile rows staged = THo + 2 * pad
+    int pad, dil, ks;
+    int valid;           // valid output columns per tile = WT - 2 * pad
+    int nstages;
+    uint32_t a_bytes;    // bytes of one plane of one stage = KC * rows * WT * 16
+};
+
+// ---- epilogue: one thread = one pixel, channels [c0, c0 + NCH) ------------------------------------------------------
+// out = relu?(acc + bias + residual); written as split planes (the next tcgen05 layer's operand) and / or fp32 NHWC.
+struct Epi {
+    Split out;               // [N][NB/8][H][W][8] or {nullptr, nullptr}
+    float* out32;            // [N][H][W][NB] or nullptr
+    Split res;               // residual split planes (same shape as out) or {nullptr, nullptr}
+    const float* bias;       // [NB] or nullptr
+    int H, W, relu;
+
+    template <int NCH> struct Pre { uint4 h[NCH / 8], l[NCH / 8]; };
+
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NCH>& p) const {
+        if (!res.hi) return;
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+#pragma unroll
+        for (int j = 0; j < NCH / 8; ++j) {
+            const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
+            p.h[j] = __ldg(reinterpret_cast<const uint4*>(res.hi) + idx);
+            p.l[j] = __ldg(reinterpret_cast<const uint4*>(res.lo) + idx);
+        }
+    }
+
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>& p, int* status) const {
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH / 8; ++j) {
+            float* x = v + 8 * j;
+            if (bias) {
+                const float4 b0 = ldg4(bias + c0 + 8 * j), b1 = ldg4(bias + c0 + 8 * j + 4);
+                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if (res.hi) {
+                const uint32_t hh[4] = {p.h[j].x, p.h[j].y, p.h[j].z, p.h[j].w}, ll[4] = {p.l[j].x, p.l[j].y, p.l[j].z, p.l[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[q]));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ll[q]));
+                    x[2 * q] += a.x + b.x;
+                    x[2 * q + 1] += a.y + b.y;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (relu) x[q] = fmaxf(x[q], 0.f);
+                amax = fmaxf(amax, fabsf(x[q]));
+            }
+            if (out.hi) {
+                uint4 h, l;
+                split_f16(make_float2(x[0], x[1]), h.x, l.x);
+                split_f16(make_float2(x[2], x[3]), h.y, l.y);
+                split_f16(make_float2(x[4], x[5]), h.z, l.z);
+                split_f16(make_float2(x[6], x[7]), h.w, l.w);
+                const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
+                reinterpret_cast<uint4*>(out.hi)[idx] = h;
+                reinterpret_cast<uint4*>(out.lo)[idx] = l;
+            }
+        }
+        if (out32) {
+            float* o = out32 + ((size_t)n * plane + pix) * NB + c0;
+#pragma unroll
+            for (int c = 0; c < NCH; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+        // a value beyond +-65504 saturates in the split above / in the next layer's split: raise the flag (imvs_device_status bit 1)
+        if (!(amax <= 65504.f) && status) atomicOr(status, 2);
+    }
+};
+
+__device__ __forceinline__ uint32_t elect_one() {       // one lane of the (converged) warp; the compiler keeps the region uniform
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xffffffffu));
+    return pred;
+}
+
+// 3x3, dilation DIL.  Per (tap, k-step) TWO MMAs instead of three: the weights of a tap sit in shared memory as
+// [CINP/8][hi rows 0..NB) | lo rows NB..2NB)][8 halves], so  A_hi x [B_hi | B_lo]  is ONE N = 2*NB instruction filling the
+// accumulator columns [0, NB) (hi*hi) and [NB, 2NB) (hi*lo), and  A_lo x B_hi  (N = NB) adds the third product to columns
+// [0, NB); the epilogue sums the two column halves.  (The tensor core's cost per M=128, K=16 instruction is set by the A
+// operand it reads, not by N at these sizes -- tools/ubench/umma_chain.cu.)
+template <int CINP, int NB, int MB, int DIL>
+__global__ void __launch_bounds__(THREADS, 1)
+tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
+                 const void* __restrict__ w_f16, const Geo geo, int* err_flag) {
+    static_assert(CINP % 16 == 0 && NB % 16 == 0 && NB <= 64, "UMMA kind::f16 shape");
+    static_assert(MB == 1 || (MB == 2 && NB <= 32), "M-blocks per tile (TMEM: 2 sets x MB x 2*NB columns <= 256)");
+    constexpr int KC = CINP / 8, PAD = DIL, ROWS = 4 * MB + 2 * PAD, NSLOT = ROWS * WT;
+    constexpr int NBS = 2 * NB;                                  // TMEM columns per M-block: [hi*hi + lo*hi | hi*lo]
+    constexpr int ACC_COLS = MB * NBS;                           // one accumulator set
+    constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
+    static_assert(2 * ACC_COLS <= 256, "TMEM budget");
+    constexpr uint32_t A_BYTES = KC * NSLOT * 16;                // one plane of one stage
+    constexpr uint32_t B_TAP_BYTES = KC * 2 * NB * 16;           // hi and lo of one tap
+    constexpr uint32_t LBO_A = NSLOT * 16, LBO_B = 2 * NB * 16;
+    constexpr int NCH = MB == 2 ? NB : NB / 2;                   // channels per epilogue thread
+    static_assert(NCH % 8 == 0, "epilogue channel split");
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    const int nst = geo.nstages;
+    unsigned char* sA = smem_raw;                                               // [nst][hi | lo][KC][NSLOT][16 B]
+    unsigned char* sB = sA + (size_t)nst * 2 * A_BYTES;                         // [tap][KC][hi NB | lo NB][16 B]
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + 9 * B_TAP_BYTES);
+    // barriers: [0, S) full, [S, 2S) empty, 2S + {0,1} accumulator full, 2S + {2,3} accumulator empty, 2S + 4 weights
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2 * MAX_STAGES + 5);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(sBar);
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto bar_tfull = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + a); };
+    auto bar_tempty = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
+    const uint32_t bar_w = bar0 + 8u * (2 * MAX_STAGES + 4);
+
+    if (warp == 0) tmem_alloc(smem_u32(sTmem), TMEM_COLS);
+    if (tid == 32) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), THREADS - 64); }
+        mbar_init(bar_w, 1);
+        fence_mbar_init();
+        // weights are constants of the forward pass: requested before the grid-dependency wait.  Global order
+        // [tap][hi | lo][KC][NB][8] (_pack.py:pack_umma_f16) -> shared [tap][KC][hi | lo][NB][8]: one bulk copy per piece
+        mbar_expect_tx(bar_w, 9 * B_TAP_BYTES);
+        constexpr uint32_t piece = NB * 16;
+        for (int tap = 0; tap < 9; ++tap)
+            for (int pl = 0; pl < 2; ++pl)
+                for (int kc = 0; kc < KC; ++kc)
+                    bulk_g2s(smem_u32(sB) + tap * B_TAP_BYTES + (kc * 2 + pl) * piece,
+                             static_cast<const unsigned char*>(w_f16) + ((size_t)(tap * 2 + pl) * KC + kc) * piece, piece, bar_w);
+    }
+    pdl_trigger();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = *sTmem;
+    pdl_wait();
+
+    const int tiles_x = geo.tiles_x, tiles_y = geo.tiles_y, n_tiles = geo.n_tiles;
+    auto decode = [&](int tile, int& n, int& oy0, int& ox0) {
+        const int tx = tile % tiles_x, t2 = tile / tiles_x;
+        n = t2 / tiles_y;
+        oy0 = (t2 - n * tiles_y) * (4 * MB);
+        ox0 = tx * (WT - 2 * PAD);
+    };
+
+    if (warp == 0) {
+        // ---- TMA producer (the whole warp walks the tile list; one elected lane issues) ----------------------------
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % nst, ph = (it / nst) & 1;
+            if (!mbar_wait_bounded(bar_empty(s), ph ^ 1)) { if (lane == 0 && err_flag) atomicOr(err_flag, 1); break; }
+            int n, oy0, ox0;
+            decode(tile, n, oy0, ox0);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full(s), 2 * A_BYTES);
+                const uint32_t dst = smem_u32(sA) + (uint32_t)s * 2 * A_BYTES;
+                tma_load_4d(dst, &map_hi, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
+                tma_load_4d(dst + A_BYTES, &map_lo, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer (whole warp, one elected lane issues a tile's MMAs and both commits) -----------------------
+        bool ok = mbar_wait_bounded(bar_w, 0);
+        constexpr uint32_t idesc2 = make_idesc_f16k(2 * NB), idesc1 = make_idesc_f16k(NB);
+        constexpr uint64_t dconst_a = ((uint64_t)(LBO_A >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+        constexpr uint64_t dconst_b = ((uint64_t)(LBO_B >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+        const uint64_t db0 = dconst_b | (uint64_t)((smem_u32(sB) & 0x3FFFFu) >> 4);
+        int it = 0;
+        for (int tile = blockIdx.x; ok && tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % nst, ph = (it / nst) & 1, acc = it & 1, aph = (it >> 1) & 1;
+            ok = mbar_wait_bounded(bar_full(s), ph) && mbar_wait_bounded(bar_tempty(acc), aph ^ 1);
+            if (!ok) break;
+            fence_after_sync();
+            if (elect_one()) {
+                const uint64_t da_hi = dconst_a | (uint64_t)(((smem_u32(sA) + (uint32_t)s * 2 * A_BYTES) & 0x3FFFFu) >> 4);
+                const uint64_t da_lo = da_hi + (A_BYTES >> 4);
+                const uint32_t dcol = tmem_d + (uint32_t)(acc * ACC_COLS);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int k16 = 0; k16 < CINP / 16; ++k16) {
+                        // slots == 16-byte units: tap shift + k-step advance (two K chunks per MMA)
+                        constexpr uint32_t KA = (2u * LBO_A) >> 4, KB = (2u * LBO_B) >> 4;
+                        const uint32_t shift = (uint32_t)((tap / 3) * DIL * WT + (tap % 3) * DIL) + (uint32_t)k16 * KA;
+                        const uint64_t db = db0 + (uint64_t)(tap * (B_TAP_BYTES >> 4) + k16 * KB);
+                        const uint32_t accum = (tap | k16) != 0;
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb)          // A_hi x [B_hi | B_lo]
+                            umma_f16k(dcol + mb * NBS, da_hi + (shift + mb * 128), db, idesc2, accum);
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb)          // A_lo x B_hi
+                            umma_f16k(dcol + mb * NBS, da_lo + (shift + mb * 128), db, idesc1, 1u);
+                    }
+                }
+                umma_commit(bar_empty(s));          // the stage may be refilled once these MMAs have read it
+                umma_commit(bar_tfull(acc));        // ... and the accumulator set is complete
+            }
+            __syncwarp();
+        }
+        if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 1);
+    } else {
+        // ---- epilogue -------------------------------------------------------------------------------------------
+        const int ew = warp - 2, lg = warp & 3, grp = ew >> 2;       // TMEM lanes 32 * (warp % 4) ..; grp: M-block (MB = 2) / channel half
+        const int mb = MB == 2 ? grp : 0, c0 = MB == 2 ? 0 : grp * NCH;
+        const int slot = mb * 128 + lg * 32 + lane, r = slot >> 5, c = slot & 31;
+        auto pixel = [&](int tile, int& n, int& oy, int& ox) {
+            int oy0, ox0;
+            decode(tile, n, oy0, ox0);
+            oy = oy0 + r; ox = ox0 + c;
+            return c < WT - 2 * PAD && oy < epi.H && ox < epi.W;
+        };
+        typename Epi::template Pre<NCH> pre{}, pre_next{};
+        {
+            int n, oy, ox;
+            if (blockIdx.x < n_tiles && pixel(blockIdx.x, n, oy, ox)) epi.template prefetch<NB, NCH>(n, oy, ox, c0, pre);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1, aph = (it >> 1) & 1;
+            int n, oy, ox;
+            const bool okp = pixel(tile, n, oy, ox);
+            {
+                int n2, oy2, ox2;
+                const int nxt = tile + gridDim.x;
+                if (nxt < n_tiles && pixel(nxt, n2, oy2, ox2)) epi.template prefetch<NB, NCH>(n2, oy2, ox2, c0, pre_next);
+            }
+            if (!mbar_wait_bounded(bar_tfull(acc), aph)) { if (lane == 0 && err_flag) atomicOr(err_flag, 1); break; }
+            fence_after_sync();
+            float v[NCH], u[NCH];
+            const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_COLS + mb * NBS + c0);
+#pragma unroll
+            for (int j = 0; j < NCH / 8; ++j) {
+                tmem_ld8_nowait(taddr + 8 * j, v + 8 * j);
+                tmem_ld8_nowait(taddr + NB + 8 * j, u + 8 * j);
+            }
+            tmem_ld_wait();
+            fence_before_sync();
+            mbar_arrive(bar_tempty(acc));           // the accumulator set is in registers: the MMA warp may overwrite it
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) v[q] += u[q];
+            if (okp) epi.template store<NB, NCH>(n, oy, ox, c0, v, pre, err_flag);
+            pre = pre_next;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();       // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (featurenet.cu); nullptr if absent
+int sm_count();                        // multiprocessors of the current device (cached per device)
+
+// tensor map over one split plane [N][KC][H][W][8 halves] as the 4-D tensor {W*8, H, KC, N}; box {256, rows, KC, 1}
+inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, int H, int W, int rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    IMVS_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)KC, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)KC * H * W * 16};
+    const cuuint32_t box[4] = {256, (cuuint32_t)rows, (cuuint32_t)KC, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(plane), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IMVS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for a [%d][%d][%d][%d][8] plane", (int)r, N, KC, H, W);
+    return 0;
+}
+
+template <int CINP, int NB, int MB, int DIL>
+int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
+    constexpr int KC = CINP / 8, PAD = DIL;
+    Geo g{};
+    g.ks = 3; g.dil = DIL; g.pad = PAD;
+    g.valid = WT - 2 * PAD;
+    g.THo = 4 * MB;
+    g.rows = g.THo + 2 * PAD;
+    g.tiles_x = cdiv(W, g.valid); g.tiles_y = cdiv(H, g.THo);
+    g.n_tiles = g.tiles_x * g.tiles_y * N;
+    g.a_bytes = (uint32_t)KC * g.rows * WT * 16;
+    const size_t fixed = (size_t)9 * 2 * KC * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
+    const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
+    IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
+    const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, sm_count()));
+    g.nstages = (int)std::min<size_t>(std::min(std::min(MAX_STAGES, std::max(2, tune("TC5P_ST", MAX_STAGES))), std::max(2, per_cta)),
+                                      (budget - fixed) / (2 * (size_t)g.a_bytes));
+    const size_t smem = fixed + (size_t)g.nstages * 2 * g.a_bytes;
+    CUtensorMap mh, ml;
+    IMVS_TRY(make_plane_map(&mh, in.hi, N, KC, H, W, g.rows));
+    IMVS_TRY(make_plane_map(&ml, in.lo, N, KC, H, W, g.rows));
+    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL>;
+    static int smem_ok = 0;
+    IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
+    const int grid = std::min(g.n_tiles, sm_count());
+    if (launch_k(kern, dim3(grid), dim3(THREADS), smem, st, mh, ml, epi, w_f16, g, err_flag) != cudaSuccess)
+        return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+// stride-1 3x3 convolution (dilation DIL) CINP -> NB of a split-plane tensor; out / out32 / res / bias / relu in `epi`
+template <int CINP, int NB, int DIL = 1>
+int launch(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
+    IMVS_REQUIRE(w_f16 && in.hi && in.lo, "%s: null tcgen05 operand", name);
+    IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
+    if constexpr (NB <= 32) {
+        const int tiles2 = cdiv(W, WT - 2 * DIL) * cdiv(H, 8) * N;
+        const int force = tune("TC5P_MB", 0);
+        // 8-row tiles (two M-blocks share one haloed tile: 1.25x instead of 1.5x halo rows) when they still fill the machine
+        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL>(name, in, epi, w_f16, N, H, W, err_flag, st);
+    }
+    return launch_mb<CINP, NB, 1, DIL>(name, in, epi, w_f16, N, H, W, err_flag, st);
+}
+
+// ---- layout conversion (operator-level entry point and tests) --------------------------------------------------------
+__global__ void nhwc_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t npix_total,
+                                     int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const int KC = C / 8;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // (n, kc, pixel)
+    if (i >= npix_total * KC) return;
+    const size_t pixg = i % ((size_t)HW), t = i / HW;
+    const int kc = (int)(t % KC);
+    const size_t n = t / KC;
+    const float* src = x + ((n * HW + pixg) * C + kc * 8);
+    const float4 a = ldg4(src), b = ldg4(src + 4);
+    uint4 h, l;
+    split_f16(make_float2(a.x, a.y), h.x, l.x);
+    split_f16(make_float2(a.z, a.w), h.y, l.y);
+    split_f16(make_float2(b.x, b.y), h.z, l.z);
+    split_f16(make_float2(b.z, b.w), h.w, l.w);
+    reinterpret_cast<uint4*>(hi)[i] = h;
+    reinterpret_cast<uint4*>(lo)[i] = l;
+}
+
+}  // namespace tc5p
+
+// ---- mma.sync epilogues that WRITE split planes (producers of a tcgen05 layer's operand) ------------------------------
+__device__ __forceinline__ void store_split_pair(__half* hi, __half* lo, size_t half_index, float a, float b) {
+    uint32_t h, l;
+    split_f16(make_float2(a, b), h, l);
+    *reinterpret_cast<uint32_t*>(hi + half_index) = h;
+    *reinterpret_cast<uint32_t*>(lo + half_index) = l;
+}
+
+// EpiSplit2 (featurenet.cu) with both halves written as split planes [N][CO/8][H][W][8]
+struct EpiSplit2H {
+    tc5p::Split out_relu;    // couts [0, CO)      -> relu(v + bias)
+    tc5p::Split out_lin;     // couts [CO, 2*CO)   -> v + bias
+    const float* bias;       // [2*CO]
+    int H, W, CO;
+    template <int NT>
+    __device__ __forceinline__ void row(int n, int oy, int ox, int co0, int t, const float (&v)[2 * NT], int) const {
+        if (oy >= H || ox >= W) return;
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int co = co0 + 8 * j + 2 * t;
+            float a = v[2 * j] + ldg(bias + co), b = v[2 * j + 1] + ldg(bias + co + 1);
+            const bool first = co < CO;
+            if (first) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            const int c = first ? co : co - CO;
+            const size_t idx = (((size_t)n * (CO / 8) + (c >> 3)) * plane + pix) * 8 + (c & 7);
+            const tc5p::Split& o = first ? out_relu : out_lin;
+            store_split_pair(o.hi, o.lo, idx, a, b);
+        }
+    }
+};
+
+}  // namespace imvs

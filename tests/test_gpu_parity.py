@@ -749,3 +749,42 @@ def test_tcgen05_path_matches_mma_sync(dev, stage_kats, model):
     finally:
         _lib.set_conv_passes(4)
     assert maxerr(out, T(k["gru_out"])) < 5e-3
+
+
+@pytest.mark.parametrize("cin,cout,dil", [(16, 16, 1), (32, 32, 1), (48, 48, 1), (48, 32, 1), (48, 16, 1), (32, 32, 2)])
+@pytest.mark.parametrize("shape", [(2, 40, 72), (1, 9, 31), (5, 128, 160)])
+def test_conv3x3_tma_tcgen05_vs_fp64(dev, cin, cout, dil, shape):
+    """The persistent TMA + tcgen05 convolution (csrc/tc5pconv.cuh; split-plane operands, three fp16 products, fp32
+    accumulation in TMEM) against an fp64 convolution of the same fp32 operands.  Measured on B200: max error 0.7 / 1.4 /
+    2.0e-6 of the output scale for 27 / 54 / 81 accumulation steps (the tensor core's fp32 accumulate truncates), asserted 5e-6.  Shapes: ragged tiles (W = 72: two full 30-column tiles + 12; 9 x 31: one partial tile, single M-block
+    path), and 5 x 128 x 160 (the two-M-block persistent path with several tiles per CTA).  Both store paths (fp32 NHWC,
+    split planes) and the residual / ReLU / bias epilogue are exercised."""
+    from itermvs_b200 import _lib, _pack
+    L = _lib.lib()
+    n, h, w = shape
+    g = torch.Generator().manual_seed(cin * 1000 + cout + h)
+    x = torch.randn(n, h, w, cin, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(n, h, w, cout, generator=g)
+    packs = _pack.pack_mma_conv(wt.to(dev))
+    wumma = packs[4]
+    assert wumma is not None
+    ws_bytes = L.imvs_conv3x3_tcgen05_workspace_bytes(n, h, w, cin, cout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    xd, bd, rd = x.to(dev).contiguous(), bias.to(dev), res.to(dev).contiguous()
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double(), padding=dil, dilation=dil)
+    want_res = torch.relu(want + res.permute(0, 3, 1, 2).double())
+    st = torch.cuda.current_stream().cuda_stream
+    for use_res, relu, via_split in ((False, 0, 0), (True, 1, 0), (True, 1, 1), (False, 0, 1)):
+        out = torch.full((n, h, w, cout), float("nan"), device=dev)
+        _lib.check(L.imvs_conv3x3_tcgen05(xd.data_ptr(), wumma.data_ptr(), bd.data_ptr(), rd.data_ptr() if use_res else None, out.data_ptr(),
+                                          ws.data_ptr(), ws_bytes, n, h, w, cin, cout, dil, relu, via_split, st), "conv3x3_tcgen05")
+        torch.cuda.synchronize()
+        assert _lib.device_status(clear=True) == 0
+        ref = (want_res if use_res else want).permute(0, 2, 3, 1)
+        err = float((out.cpu().double() - ref).abs().max())
+        scale = float(ref.abs().max())
+        print(f"tc5p {cin}->{cout} dil {dil} {shape} res={use_res} split_out={via_split}: max err {err:.2e} (scale {scale:.2f})")
+        assert torch.isfinite(out).all()
+        assert err < 5e-6 * max(scale, 1.0), err
