@@ -80,6 +80,8 @@ typedef struct imvs_wpair {      /* packed conv weight [tap][CinP][CoutP] */
     const void* f16umma;         /* fp16 hi/lo split in the tcgen05 K-major canonical order (mode 4 on the 5th-generation
                                     tensor core, csrc/tc5conv.cuh:tc5h_conv_kernel): [tap][hi | lo][CinK/8][CoutP][8 halves];
                                     NULL when the shape is not served (CoutP % 16 != 0 or CoutP > 64) */
+    const void* f16ummai;        /* the same with hi and lo interleaved per K chunk: [tap][CinK/8][hi | lo][CoutP][8 halves]
+                                    (csrc/tc5pconv.cuh: A_hi x [B_hi | B_lo] is one N = 2 CoutP instruction); NULL alike */
 } imvs_wpair;
 
 typedef struct imvs_corrnet_weights {   /* models/itermvs.py:352-381, one CorrNet */
@@ -221,7 +223,8 @@ int imvs_hidden_init(const imvs_weights* w, const float* corr, float* hidden, fl
                      int B, int D, int H3, int W3, void* stream);
 
 /* module.py:59-66 -- ConvGRU.forward(h, x), in place on h.
- * h [B][H][W][32], x [B][H][W][16] (channels 11..15 must be zero); scratch 2*B*32*H*W floats. */
+ * h [B][H][W][32], x [B][H][W][16] (channels 11..15 must be zero); scratch 4*B*32*H*W floats (z, and the [h|x] and
+ * [r*h|x] operands as fp16 hi / lo split planes for the TMA + tcgen05 path). */
 int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, float* scratch, int B, int H, int W, void* stream);
 
 /* itermvs.py:171-190 / 196-219 -- depth_head (+ confidence_head when conf or conf_logit != NULL),
@@ -333,12 +336,12 @@ int imvs_featurenet_launch_count(void);
  * [N][C/8][H][W][8 halves] loaded by cp.async.bulk.tensor, three products per tap into a TMEM accumulator.  The operator
  * behind nn.Conv2d(Cin, Cout, 3, padding=dil, dilation=dil) of models/module.py:6-50 (ConvBnReLU / ResidualBlock with the
  * BatchNorm folded) and models/net.py:18-20 (output convolutions) inside imvs_featurenet_forward, exposed for tests.
- * w_f16umma: imvs_wpair::f16umma of the layer; (Cin, Cout) in {(16,16), (32,32), (48,48), (48,32), (48,16)} with dil = 1,
+ * w_f16ummai: imvs_wpair::f16ummai of the layer; (Cin, Cout) in {(16,16), (32,32), (48,48), (48,32), (48,16)} with dil = 1,
  * (32,32) also with dil = 2;
  * x: [N][H][W][Cin], residual (may be NULL) and out: [N][H][W][Cout]; via_split_output != 0 stores the result as split
  * planes first (the layout the next layer's TMA loads read) and converts back. */
 size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int Cin, int Cout);
-int imvs_conv3x3_tcgen05(const float* x, const void* w_f16umma, const float* bias, const float* residual, float* out,
+int imvs_conv3x3_tcgen05(const float* x, const void* w_f16ummai, const float* bias, const float* residual, float* out,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int dil, int relu,
                          int via_split_output, void* stream);
 

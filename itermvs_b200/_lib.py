@@ -23,7 +23,7 @@ FNET_CONVS = 24
 
 
 class WPair(C.Structure):
-    _fields_ = [("tf32", vp), ("fp32", vp), ("umma", vp), ("f16x3", vp), ("f16umma", vp)]
+    _fields_ = [("tf32", vp), ("fp32", vp), ("umma", vp), ("f16x3", vp), ("f16umma", vp), ("f16ummai", vp)]
 
 
 class CorrNetWeights(C.Structure):

@@ -85,9 +85,19 @@ def pack_umma_f16(w: Tensor):
     return torch.stack([canon(hi), canon(lo)], dim=1).contiguous()
 
 
+def pack_umma_f16i(w: Tensor):
+    """pack_umma_f16 with hi and lo interleaved per K chunk: [tap][CinK/8][hi | lo][CoutP][8 halves].  One tap is then ONE
+    contiguous block whose rows [0, CoutP) / [CoutP, 2 CoutP) of every chunk are B_hi / B_lo: the persistent TMA + tcgen05
+    kernel (csrc/tc5pconv.cuh) issues A_hi x [B_hi | B_lo] as a single N = 2 CoutP instruction."""
+    u = pack_umma_f16(w)
+    if u is None:
+        return None
+    return u.permute(0, 2, 1, 3, 4).contiguous()          # [tap][hi|lo][KC][N][8] -> [tap][KC][hi|lo][N][8]
+
+
 def _packs(out: Tensor):
     t, f = split_tf32(out)
-    return t, f, pack_umma(t), pack_f16x3(f), pack_umma_f16(f)
+    return t, f, pack_umma(t), pack_f16x3(f), pack_umma_f16(f), pack_umma_f16i(f)
 
 
 def pack_mma_conv(w: Tensor, cinp: int = 0, coutp: int = 0):
@@ -155,7 +165,7 @@ class _Holder:
     def pair(self, hl) -> _lib.WPair:
         self.keep.extend(t for t in hl if t is not None)
         return _lib.WPair(hl[0].data_ptr(), hl[1].data_ptr(), hl[2].data_ptr() if hl[2] is not None else None, hl[3].data_ptr(),
-                          hl[4].data_ptr() if hl[4] is not None else None)
+                          hl[4].data_ptr() if hl[4] is not None else None, hl[5].data_ptr() if hl[5] is not None else None)
 
     def ptr(self, t: Tensor) -> int:
         self.keep.append(t)

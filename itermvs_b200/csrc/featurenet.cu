@@ -247,9 +247,9 @@ static int res_stage_p(const imvs_featurenet_weights* w, int L, const float* x, 
     int* flag = tc5_error_flag();
     IMVS_TRY((mma_conv<CI, NBA, MT, WARPS, 2, WALL_A>("fnet.block0.conv1|downsample", in_nhwc(x, Hin, Win, CI),
                                                   EpiSplit2H{y1, ds, w->b[LS], H, W, CO}, WSets::single(w->w[LS]), s2, N, 2 * CO, H, W, NCA, st)));
-    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block0.conv2", y1, tc5p::Epi{b0, nullptr, ds, w->b[L + 1], H, W, 1}, w->w[L + 1].f16umma, N, H, W, flag, st)));
-    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv1", b0, tc5p::Epi{y1, nullptr, none, w->b[L + 3], H, W, 1}, w->w[L + 3].f16umma, N, H, W, flag, st)));
-    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, buf[3], b0, w->b[L + 4], H, W, 1}, w->w[L + 4].f16umma, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block0.conv2", y1, tc5p::Epi{b0, nullptr, ds, w->b[L + 1], H, W, 1}, w->w[L + 1].f16ummai, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv1", b0, tc5p::Epi{y1, nullptr, none, w->b[L + 3], H, W, 1}, w->w[L + 3].f16ummai, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, buf[3], b0, w->b[L + 4], H, W, 1}, w->w[L + 4].f16ummai, N, H, W, flag, st)));
     return 0;
 }
 
@@ -259,7 +259,7 @@ static bool fnet_tc5p_ready(const imvs_featurenet_weights* w) {
 #else
     if (conv_passes() != 4 || !tune("TC5P", 1) || !tc5p::encode_tiled_fn()) return false;
     for (int L : {2, 4, 5, 7, 9, 10, 12, 14, 15, 16, 18, 20})
-        if (!w->w[L].f16umma) return false;
+        if (!w->w[L].f16ummai) return false;
     return true;
 #endif
 }
@@ -284,6 +284,28 @@ int sm_count() {
     int& c = cached[dev & 63];
     if (!c && cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) c = 148;
     return c > 0 ? c : 148;
+}
+
+// layout conversion for the operator-level entry point (inside FeatureNet the producers write split planes directly)
+__global__ void nhwc_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t npix_total,
+                                     int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const int KC = C / 8;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // (n, kc, pixel)
+    if (i >= npix_total * KC) return;
+    const size_t pixg = i % ((size_t)HW), t = i / HW;
+    const int kc = (int)(t % KC);
+    const size_t n = t / KC;
+    const float* src = x + ((n * HW + pixg) * C + kc * 8);
+    const float4 a = ldg4(src), b = ldg4(src + 4);
+    uint4 h, l;
+    split_f16(make_float2(a.x, a.y), h.x, l.x);
+    split_f16(make_float2(a.z, a.w), h.y, l.y);
+    split_f16(make_float2(b.x, b.y), h.z, l.z);
+    split_f16(make_float2(b.z, b.w), h.w, l.w);
+    reinterpret_cast<uint4*>(hi)[i] = h;
+    reinterpret_cast<uint4*>(lo)[i] = l;
 }
 
 __global__ void split_to_nhwc_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ x, size_t npix_total,
@@ -355,13 +377,13 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
         IMVS_TRY((res_stage_p<32, 48, false, 96, 1>(w, 11, b.l2[3], b.l3, b.l3s, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48] (+ split)
         const tc5p::Split l3s = tc5p::split_at(b.l3s, (size_t)N * H3 * W3 * 48), i2s = tc5p::split_at(b.intra2s, (size_t)N * H2 * W2 * 48),
                           i1s = tc5p::split_at(b.intra1, (size_t)N * H1 * W1 * 48);
-        IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16umma, N, H3, W3, flag, st)));
+        IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16ummai, N, H3, W3, flag, st)));
         IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2H{b.intra2, i2s, w->b[17], b.l3[3], H2, W2, 48},
                                                    WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
-        IMVS_TRY((tc5p::launch<48, 32>("fnet.output2", i2s, tc5p::Epi{none, fea2, none, w->b[18], H2, W2, 0}, w->w[18].f16umma, N, H2, W2, flag, st)));
+        IMVS_TRY((tc5p::launch<48, 32>("fnet.output2", i2s, tc5p::Epi{none, fea2, none, w->b[18], H2, W2, 0}, w->w[18].f16ummai, N, H2, W2, flag, st)));
         IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2H{nullptr, i1s, w->b[19], b.intra2, H1, W1, 48},
                                                    WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
-        IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16umma, N, H1, W1, flag, st)));
+        IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16ummai, N, H1, W1, flag, st)));
         return 0;
     }
     const int w8 = tune("FNETW", 0);     // 1: 8 warps x 1 row-tile per CTA instead of 4 x 2 (same tile, twice the resident warps)
@@ -437,10 +459,10 @@ extern "C" size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int 
     return (px * Cin + 2 * px * Cout) * sizeof(float) + 3 * 256;
 }
 
-extern "C" int imvs_conv3x3_tcgen05(const float* x, const void* w_f16umma, const float* bias, const float* residual, float* out,
+extern "C" int imvs_conv3x3_tcgen05(const float* x, const void* w_f16ummai, const float* bias, const float* residual, float* out,
                                     void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int dil, int relu,
                                     int via_split_output, void* stream) {
-    IMVS_REQUIRE(x && w_f16umma && out && workspace, "conv3x3_tcgen05: null pointer");
+    IMVS_REQUIRE(x && w_f16ummai && out && workspace, "conv3x3_tcgen05: null pointer");
     IMVS_REQUIRE(N >= 1 && H >= 1 && W >= 1 && dil >= 1 && dil <= 3, "conv3x3_tcgen05: bad shape");
     IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "conv3x3_tcgen05: workspace must be 256-byte aligned");
     IMVS_REQUIRE(workspace_bytes >= imvs_conv3x3_tcgen05_workspace_bytes(N, H, W, Cin, Cout), "conv3x3_tcgen05: workspace too small");
@@ -463,12 +485,12 @@ extern "C" int imvs_conv3x3_tcgen05(const float* x, const void* w_f16umma, const
     int* flag = tc5_error_flag();
     const int key = (Cin * 100 + Cout) * 10 + dil;
     switch (key) {
-        case 16161: IMVS_TRY((tc5p::launch<16, 16>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
-        case 32321: IMVS_TRY((tc5p::launch<32, 32>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
-        case 32322: IMVS_TRY((tc5p::launch<32, 32, 2>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
-        case 48481: IMVS_TRY((tc5p::launch<48, 48>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
-        case 48321: IMVS_TRY((tc5p::launch<48, 32>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
-        case 48161: IMVS_TRY((tc5p::launch<48, 16>("conv3x3_tcgen05", xin, epi, w_f16umma, N, H, W, flag, st))); break;
+        case 16161: IMVS_TRY((tc5p::launch<16, 16>("conv3x3_tcgen05", xin, epi, w_f16ummai, N, H, W, flag, st))); break;
+        case 32321: IMVS_TRY((tc5p::launch<32, 32>("conv3x3_tcgen05", xin, epi, w_f16ummai, N, H, W, flag, st))); break;
+        case 32322: IMVS_TRY((tc5p::launch<32, 32, 2>("conv3x3_tcgen05", xin, epi, w_f16ummai, N, H, W, flag, st))); break;
+        case 48481: IMVS_TRY((tc5p::launch<48, 48>("conv3x3_tcgen05", xin, epi, w_f16ummai, N, H, W, flag, st))); break;
+        case 48321: IMVS_TRY((tc5p::launch<48, 32>("conv3x3_tcgen05", xin, epi, w_f16ummai, N, H, W, flag, st))); break;
+        case 48161: IMVS_TRY((tc5p::launch<48, 16>("conv3x3_tcgen05", xin, epi, w_f16ummai, N, H, W, flag, st))); break;
         default: return fail("conv3x3_tcgen05: (Cin, Cout, dilation) = (%d, %d, %d) is not instantiated", Cin, Cout, dil);
     }
     if (via_split_output) {

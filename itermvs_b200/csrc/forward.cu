@@ -44,7 +44,7 @@ static Workspace carve(const imvs_problem& pb, float* base) {
     w.hidden = at(B * 32 * P2);
     w.xbuf = at(B * IMVS_XCH * P2);
     w.agg_iter = at(B * IMVS_ITER_SLICES * P2 * 8);
-    w.gru_scratch = at(B * 64 * P2);
+    w.gru_scratch = at(B * 128 * P2);
     w.head_scratch = at(B * 384 * P2);
     w.ups_scratch = at(B * 64 * P2);
     w.conf_buf = at(B * P2);
@@ -75,12 +75,14 @@ extern "C" size_t imvs_forward_workspace_bytes(const imvs_problem* pb) {
 extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     if (check_problem(pb) != 0) return -1;
     // the depth head is 2 launches (conv0 + the fused tcgen05 kernel) in the default fp32-grade mode, 4 otherwise
+    // the ConvGRU is 3 launches (operand split + z|r + q on the TMA / tcgen05 kernel) in the default mode, 2 otherwise
 #ifdef CUSIM
-    const int head = 4;
+    const int head = 4, gru = 2;
 #else
     const int head = (conv_passes() == 4 && tune("HEADFUSED", 1)) ? 2 : 4;
+    const int gru = (conv_passes() == 4 && tune("TC5P_GRU", 1)) ? 3 : 2;
 #endif
-    return 20 + head + (9 + head) * pb->iterations;
+    return 20 + head + (7 + gru + head) * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,

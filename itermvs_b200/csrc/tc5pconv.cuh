@@ -21,7 +21,7 @@
 //     warps 2..9  epilogue: tcgen05.ld, bias / residual (read from split planes) / ReLU, fp16 range guard, and the
 //                 stores: split planes for the next tcgen05 layer and / or fp32 NHWC for the other consumers.  The
 //                 residual of tile t+1 is requested before tile t is processed.
-//   weights ([tap][hi | lo][CINP/8][NB][8 halves], _pack.py:pack_umma_f16) stay resident in shared memory.
+//   weights ([tap][CINP/8][hi | lo][NB][8 halves], _pack.py:pack_umma_f16i) stay resident in shared memory.
 // Tile = 32 slots wide (30 valid output columns for a 3x3), 4 * MB output rows.
 #pragma once
 #include <cuda.h>
@@ -90,6 +90,8 @@ struct Geo {
 };
 
 // ---- epilogue: one thread = one pixel, channels [c0, c0 + NCH) ------------------------------------------------------
+// Interface of an epilogue class: members H, W; Pre<NCH>; prefetch<NB, NCH>(n, oy, ox, c0, pre) (global reads that do not
+// depend on the accumulator, issued one tile ahead); store<NB, NCH>(n, oy, ox, c0, v, pre, status).
 // out = relu?(acc + bias + residual); written as split planes (the next tcgen05 layer's operand) and / or fp32 NHWC.
 struct Epi {
     Split out;               // [N][NB/8][H][W][8] or {nullptr, nullptr}
@@ -170,7 +172,7 @@ __device__ __forceinline__ uint32_t elect_one() {       // one lane of the (conv
 // accumulator columns [0, NB) (hi*hi) and [NB, 2NB) (hi*lo), and  A_lo x B_hi  (N = NB) adds the third product to columns
 // [0, NB); the epilogue sums the two column halves.  (The tensor core's cost per M=128, K=16 instruction is set by the A
 // operand it reads, not by N at these sizes -- tools/ubench/umma_chain.cu.)
-template <int CINP, int NB, int MB, int DIL>
+template <int CINP, int NB, int MB, int DIL, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
                  const void* __restrict__ w_f16, const Geo geo, int* err_flag) {
@@ -208,15 +210,11 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), THREADS - 64); }
         mbar_init(bar_w, 1);
         fence_mbar_init();
-        // weights are constants of the forward pass: requested before the grid-dependency wait.  Global order
-        // [tap][hi | lo][KC][NB][8] (_pack.py:pack_umma_f16) -> shared [tap][KC][hi | lo][NB][8]: one bulk copy per piece
+        // weights are constants of the forward pass: requested before the grid-dependency wait; global order = shared
+        // order [tap][KC][hi | lo][NB][8] (_pack.py:pack_umma_f16i), one bulk copy per tap
         mbar_expect_tx(bar_w, 9 * B_TAP_BYTES);
-        constexpr uint32_t piece = NB * 16;
         for (int tap = 0; tap < 9; ++tap)
-            for (int pl = 0; pl < 2; ++pl)
-                for (int kc = 0; kc < KC; ++kc)
-                    bulk_g2s(smem_u32(sB) + tap * B_TAP_BYTES + (kc * 2 + pl) * piece,
-                             static_cast<const unsigned char*>(w_f16) + ((size_t)(tap * 2 + pl) * KC + kc) * piece, piece, bar_w);
+            bulk_g2s(smem_u32(sB) + tap * B_TAP_BYTES, static_cast<const unsigned char*>(w_f16) + (size_t)tap * B_TAP_BYTES, B_TAP_BYTES, bar_w);
     }
     pdl_trigger();
     fence_before_sync();
@@ -360,7 +358,7 @@ inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, 
     return 0;
 }
 
-template <int CINP, int NB, int MB, int DIL>
+template <int CINP, int NB, int MB, int DIL, class Epi>
 int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
     constexpr int KC = CINP / 8, PAD = DIL;
     Geo g{};
@@ -381,7 +379,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
     CUtensorMap mh, ml;
     IMVS_TRY(make_plane_map(&mh, in.hi, N, KC, H, W, g.rows));
     IMVS_TRY(make_plane_map(&ml, in.lo, N, KC, H, W, g.rows));
-    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL>;
+    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL, Epi>;
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     const int grid = std::min(g.n_tiles, sm_count());
@@ -391,39 +389,17 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
 }
 
 // stride-1 3x3 convolution (dilation DIL) CINP -> NB of a split-plane tensor; out / out32 / res / bias / relu in `epi`
-template <int CINP, int NB, int DIL = 1>
+template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, class Epi>
 int launch(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
     IMVS_REQUIRE(w_f16 && in.hi && in.lo, "%s: null tcgen05 operand", name);
     IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
-    if constexpr (NB <= 32) {
+    if constexpr (NB <= 32 && ALLOW_MB2) {
         const int tiles2 = cdiv(W, WT - 2 * DIL) * cdiv(H, 8) * N;
         const int force = tune("TC5P_MB", 0);
         // 8-row tiles (two M-blocks share one haloed tile: 1.25x instead of 1.5x halo rows) when they still fill the machine
-        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL>(name, in, epi, w_f16, N, H, W, err_flag, st);
+        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
     }
-    return launch_mb<CINP, NB, 1, DIL>(name, in, epi, w_f16, N, H, W, err_flag, st);
-}
-
-// ---- layout conversion (operator-level entry point and tests) --------------------------------------------------------
-__global__ void nhwc_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t npix_total,
-                                     int HW, int C) {
-    pdl_trigger();
-    pdl_wait();
-    const int KC = C / 8;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // (n, kc, pixel)
-    if (i >= npix_total * KC) return;
-    const size_t pixg = i % ((size_t)HW), t = i / HW;
-    const int kc = (int)(t % KC);
-    const size_t n = t / KC;
-    const float* src = x + ((n * HW + pixg) * C + kc * 8);
-    const float4 a = ldg4(src), b = ldg4(src + 4);
-    uint4 h, l;
-    split_f16(make_float2(a.x, a.y), h.x, l.x);
-    split_f16(make_float2(a.z, a.w), h.y, l.y);
-    split_f16(make_float2(b.x, b.y), h.z, l.z);
-    split_f16(make_float2(b.z, b.w), h.w, l.w);
-    reinterpret_cast<uint4*>(hi)[i] = h;
-    reinterpret_cast<uint4*>(lo)[i] = l;
+    return launch_mb<CINP, NB, 1, DIL, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
 }
 
 }  // namespace tc5p

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "mmaconv.cuh"
 #include "tc5conv.cuh"
+#include "tc5pconv.cuh"
 #include "headfused.cuh"
 
 namespace imvs {
@@ -55,6 +56,107 @@ struct EpiGruQ {
             hh.x = (1.f - zz.x) * hh.x + zz.x * q0;
             hh.y = (1.f - zz.y) * hh.y + zz.y * q1;
             *reinterpret_cast<float2*>(h + base + co) = hh;
+        }
+    }
+};
+
+// ---- the same two GEMMs on the persistent TMA + tcgen05 kernel (tc5pconv.cuh), the default in the fp32-grade mode -------
+// hx = [h (32) | x (16)] and rhx = [r*h (32) | x (16)] live as 48-channel split-plane tensors [B][6][H][W][8 halves]: one
+// conversion kernel writes h and x into hx and x into rhx, the z|r kernel's epilogue writes r*h into rhx.
+__global__ void gru_split_inputs_kernel(const float* __restrict__ h, const float* __restrict__ x, __half* __restrict__ a_hi,
+                                        __half* __restrict__ a_lo, __half* __restrict__ q_hi, __half* __restrict__ q_lo, int B, int P) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // (b, chunk, pixel)
+    if (i >= (size_t)B * 6 * P) return;
+    const int p = (int)(i % P), kc = (int)((i / P) % 6), b = (int)(i / ((size_t)6 * P));
+    const float* src = kc < 4 ? h + ((size_t)b * P + p) * 32 + kc * 8 : x + ((size_t)b * P + p) * IMVS_XCH + (kc - 4) * 8;
+    const float4 u = ldg4(src), v = ldg4(src + 4);
+    uint4 hi, lo;
+    split_f16(make_float2(u.x, u.y), hi.x, lo.x);
+    split_f16(make_float2(u.z, u.w), hi.y, lo.y);
+    split_f16(make_float2(v.x, v.y), hi.z, lo.z);
+    split_f16(make_float2(v.z, v.w), hi.w, lo.w);
+    reinterpret_cast<uint4*>(a_hi)[i] = hi;
+    reinterpret_cast<uint4*>(a_lo)[i] = lo;
+    if (kc >= 4) {
+        reinterpret_cast<uint4*>(q_hi)[i] = hi;
+        reinterpret_cast<uint4*>(q_lo)[i] = lo;
+    }
+}
+
+struct EpiGruZRp {           // 64 stacked channels: thread's 32 are z (c0 = 0) or r (c0 = 32)   (module.py:61-62)
+    const float* bias;       // [64]
+    const float* h;          // [B][P][32]
+    float* z;                // [B][P][32]
+    tc5p::Split rhx;         // [B][6][P][8]: chunks 0..3 <- r * h
+    int H, W;
+    template <int NCH> struct Pre { float4 hh[NCH / 4]; };
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NCH>& p) const {
+        static_assert(NB == 64 && NCH == 32, "z | r halves");
+        if (c0 == 0) return;
+        const float* src = h + (((size_t)n * H + oy) * W + ox) * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p.hh[c] = ldg4(src + 4 * c);
+    }
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>& p, int*) const {
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        if (c0 == 0) {
+            float* dst = z + ((size_t)n * plane + pix) * 32;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 b = ldg4(bias + c);
+                *reinterpret_cast<float4*>(dst + c) =
+                    make_float4(sigmoidf_(v[c] + b.x), sigmoidf_(v[c + 1] + b.y), sigmoidf_(v[c + 2] + b.z), sigmoidf_(v[c + 3] + b.w));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b0 = ldg4(bias + 32 + 8 * j), b1 = ldg4(bias + 36 + 8 * j), h0 = p.hh[2 * j], h1 = p.hh[2 * j + 1];
+                const float* a = v + 8 * j;
+                uint4 hi, lo;
+                split_f16(make_float2(sigmoidf_(a[0] + b0.x) * h0.x, sigmoidf_(a[1] + b0.y) * h0.y), hi.x, lo.x);
+                split_f16(make_float2(sigmoidf_(a[2] + b0.z) * h0.z, sigmoidf_(a[3] + b0.w) * h0.w), hi.y, lo.y);
+                split_f16(make_float2(sigmoidf_(a[4] + b1.x) * h1.x, sigmoidf_(a[5] + b1.y) * h1.y), hi.z, lo.z);
+                split_f16(make_float2(sigmoidf_(a[6] + b1.z) * h1.z, sigmoidf_(a[7] + b1.w) * h1.w), hi.w, lo.w);
+                const size_t idx = ((size_t)n * 6 + j) * plane + pix;
+                reinterpret_cast<uint4*>(rhx.hi)[idx] = hi;
+                reinterpret_cast<uint4*>(rhx.lo)[idx] = lo;
+            }
+        }
+    }
+};
+
+struct EpiGruQp {            // q = tanh, h <- (1 - z) h + z q in place   (module.py:63-64)
+    const float* bias;       // [32]
+    const float* z;          // [B][P][32]
+    float* h;                // [B][P][32]
+    int H, W;
+    template <int NCH> struct Pre { float4 zz[NCH / 4], hh[NCH / 4]; };
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NCH>& p) const {
+        static_assert(NB == 32, "convq");
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32 + c0;
+#pragma unroll
+        for (int c = 0; c < NCH / 4; ++c) {
+            p.zz[c] = ldg4(z + base + 4 * c);
+            p.hh[c] = *reinterpret_cast<const float4*>(h + base + 4 * c);
+        }
+    }
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>& p, int*) const {
+        const size_t base = (((size_t)n * H + oy) * W + ox) * 32 + c0;
+#pragma unroll
+        for (int c = 0; c < NCH / 4; ++c) {
+            const float4 b = ldg4(bias + c0 + 4 * c), zz = p.zz[c];
+            float4 hh = p.hh[c];
+            hh.x = (1.f - zz.x) * hh.x + zz.x * tanhf(v[4 * c] + b.x);
+            hh.y = (1.f - zz.y) * hh.y + zz.y * tanhf(v[4 * c + 1] + b.y);
+            hh.z = (1.f - zz.z) * hh.z + zz.z * tanhf(v[4 * c + 2] + b.z);
+            hh.w = (1.f - zz.w) * hh.w + zz.w * tanhf(v[4 * c + 3] + b.w);
+            *reinterpret_cast<float4*>(h + base + 4 * c) = hh;
         }
     }
 };
@@ -190,6 +292,21 @@ extern "C" int imvs_conv_gru(const imvs_weights* w, float* h, const float* x, fl
         return 0;
     }
 #ifndef CUSIM
+    if (conv_passes() == 4 && w->gru_zr.f16ummai && w->gru_q.f16ummai && tune("TC5P_GRU", 1) && tc5p::encode_tiled_fn()) {
+        // default: persistent TMA + tcgen05 kernel on split-plane operands (tc5pconv.cuh)
+        const size_t P = (size_t)H * W, e48 = (size_t)B * 48 * P;
+        float* zbuf = scratch;                                               // [B][P][32] fp32
+        const tc5p::Split hx = tc5p::split_at(scratch + n, e48), rhx = tc5p::split_at(scratch + n + e48, e48);
+        const size_t items = (size_t)B * 6 * P;
+        IMVS_REQUIRE(items < 2147483647ull, "conv_gru: too many pixels");
+        IMVS_CUDA(launch_k(gru_split_inputs_kernel, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st, (const float*)h, x, hx.hi, hx.lo,
+                           rhx.hi, rhx.lo, B, (int)P));
+        IMVS_TRY((tc5p::launch<48, 64, 2>("gru.zr(tma+tcgen05)", hx, EpiGruZRp{w->gru_zr_b, h, zbuf, rhx, H, W}, w->gru_zr.f16ummai, B, H, W,
+                                          tc5_error_flag(), st)));
+        IMVS_TRY((tc5p::launch<48, 32, 2, false>("gru.q(tma+tcgen05)", rhx, EpiGruQp{w->gru_q_b, zbuf, h, H, W}, w->gru_q.f16ummai, B, H, W,
+                                          tc5_error_flag(), st)));
+        return 0;
+    }
     if (conv_passes() == 4 && w->gru_zr.f16umma && w->gru_q.f16umma && tune("TC5H_GRU", 0)) {
         // fp32-grade mode on tcgen05: fp16 hi/lo 3-product chains (tc5conv.cuh:tc5h_conv_kernel), exact-grade gates
         IMVS_TRY((tc5::launch_h<48, 64>("gru.zr(tcgen05 f16x3)", InNHWC2{h, x, H, W, 32, IMVS_XCH}, tc5::PixGruZR{w->gru_zr_b, h, z, rh, H, W, 1},

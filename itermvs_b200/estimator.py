@@ -216,7 +216,7 @@ class ConvGRU(nn.Module):
     def forward_nhwc(self, h: Tensor, x16: Tensor, wref=None) -> Tensor:
         """h [B,H,W,32] (updated IN PLACE and returned), x16 [B,H,W,16]."""
         b, hh, ww, _ = h.shape
-        scratch = torch.empty(2 * h.numel(), device=h.device)
+        scratch = torch.empty(4 * h.numel(), device=h.device)
         _lib.check(_lib.lib().imvs_conv_gru(wref if wref is not None else self._packed(h.device).ref, h.data_ptr(), x16.data_ptr(),
                                             scratch.data_ptr(), b, hh, ww, ops._stream()), "conv_gru")
         return h

@@ -30,7 +30,8 @@ def test_host_side_validation_without_gpu():
     pb = _lib.Problem(1, 5, 512, 640, 32, 4)
     nbytes = L.imvs_forward_workspace_bytes(C.byref(pb))
     assert 50e6 < nbytes < 200e6
-    assert L.imvs_forward_launch_count(C.byref(pb)) == 22 + 11 * 4       # fused tcgen05 head: conv0 + one kernel per head call
+    # fused tcgen05 head: conv0 + one kernel per head call; ConvGRU: operand split + z|r + q on the TMA / tcgen05 kernel
+    assert L.imvs_forward_launch_count(C.byref(pb)) == 22 + 12 * 4
     for bad in (_lib.Problem(1, 1, 512, 640, 32, 4), _lib.Problem(1, 5, 512, 650, 32, 4), _lib.Problem(1, 5, 512, 640, 30, 4),
                 _lib.Problem(0, 5, 512, 640, 32, 4), _lib.Problem(1, 40, 512, 640, 32, 4)):
         assert L.imvs_forward_workspace_bytes(C.byref(bad)) == 0
@@ -70,19 +71,21 @@ def test_tf32_split_and_packing(dtu_weights):
     assert torch.equal(_pack.round_tf32(t), torch.tensor([1.0 + 2 ** -10, -(1.0 + 2 ** -10)]))
     # conv packing: [Cout,Cin,3,3] -> [9][CinP][CoutP]
     w = dtu_weights["iter_mvs.update.gru.convq.weight"]
-    hi, full, um, f16, f16u = _pack.pack_mma_conv(w, cinp=48)
+    hi, full, um, f16, f16u, f16i = _pack.pack_mma_conv(w, cinp=48)
     # tcgen05 fp16 order [tap][hi|lo][CinK/8][CoutP][8 halves]: hi + lo reproduces the weight to fp32 grade
     assert f16u.shape == (9, 2, 6, 32, 8) and f16u.dtype == torch.float16
     rec16 = (f16u[:, 0].float() + f16u[:, 1].float()).permute(0, 1, 3, 2).reshape(9, 48, 32)
     assert bool(((rec16 - full).abs() <= full.abs() * 2.0 ** -21 + 2.0 ** -24).all())
     assert torch.equal(f16u[4, 0, 1, 7, 3], full[4, 11, 7].half())
+    # the TMA + tcgen05 kernel's order [tap][CinK/8][hi|lo][CoutP][8]: rows [0, CoutP) / [CoutP, 2 CoutP) of a chunk are B_hi / B_lo
+    assert f16i.shape == (9, 6, 2, 32, 8) and torch.equal(f16i.permute(0, 2, 1, 3, 4), f16u) and f16i.is_contiguous()
     assert um.shape == (1, 9, 12, 32, 4) and torch.equal(um[0, 4, 3, 7], hi[4, 12:16, 7])
     assert hi.shape == (9, 48, 32)
     rec = full[:, :43, :].reshape(3, 3, 43, 32).permute(3, 2, 0, 1)
     assert torch.equal(rec, w)
     assert float(hi[:, 43:, :].abs().max()) == 0.0
     wt = dtu_weights["iter_mvs.evaluation.corr_conv1.0.conv3.weight"]          # ConvTranspose [Cin,Cout,3,3]
-    hi, full, _, _, _ = _pack.pack_mma_tconv(wt)
+    hi, full, _, _, _, _ = _pack.pack_mma_tconv(wt)
     assert hi.shape == (9, 32, 16)
     assert torch.equal(full[4], wt[:, :, 1, 1])
 
@@ -104,7 +107,7 @@ def test_fp16_split_packing(dtu_weights):
     err = (rr - ww).abs()
     assert bool((err <= ww.abs() * 2.0 ** -21 + 2.0 ** -24).all())
     # a real layer: the packed pair order matches the fp32 packing
-    _, full, _, f16, _ = _pack.pack_mma_conv(dtu_weights["iter_mvs.update.gru.convq.weight"], cinp=48)
+    _, full, _, f16, _, _ = _pack.pack_mma_conv(dtu_weights["iter_mvs.update.gru.convq.weight"], cinp=48)
     h = f16.view(torch.float16).reshape(9, 24, 32, 2, 2)
     assert torch.equal(h[4, 5, 7, 0, 1], full[4, 11, 7].half()) and torch.equal(h[4, 5, 7, 0, 0], full[4, 10, 7].half())
 

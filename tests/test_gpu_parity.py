@@ -768,7 +768,7 @@ def test_conv3x3_tma_tcgen05_vs_fp64(dev, cin, cout, dil, shape):
     bias = torch.randn(cout, generator=g) * 0.1
     res = torch.randn(n, h, w, cout, generator=g)
     packs = _pack.pack_mma_conv(wt.to(dev))
-    wumma = packs[4]
+    wumma = packs[5]
     assert wumma is not None
     ws_bytes = L.imvs_conv3x3_tcgen05_workspace_bytes(n, h, w, cin, cout)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
