@@ -73,6 +73,66 @@ struct EpiAddUp2H {
     }
 };
 
+// The lateral stage on the TMA + tcgen05 kernel (tc5pconv.cuh, 1x1): out = conv1x1(x) + bias + up2(coarse), written as split
+// planes (operand of the output convolution) and, when the next lateral stage upsamples it, as fp32 NHWC too.  One thread =
+// one pixel x NCH channels: the four bilinear taps are 4 x NCH/4 float4 loads from the (L2-resident) coarse map.
+struct EpiLateral {
+    static constexpr int kAhead = 1;
+    tc5p::Split out;         // [N][C/8][H][W][8]
+    float* out32;            // [N][H][W][C] or nullptr
+    const float* bias;       // [C]
+    const float* coarse;     // [N][H/2][W/2][C] fp32
+    int H, W;
+    template <int NCH> struct Pre {};
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NCH>&) const {}
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>&, int* status) const {
+        const int Hc = H / 2, Wc = W / 2;
+        int h0, h1, w0, w1;
+        float lh, lw;
+        up_index(oy, 0.5f, Hc, h0, h1, lh);
+        up_index(ox, 0.5f, Wc, w0, w1, lw);
+        const float* cb = coarse + (size_t)n * Hc * Wc * NB + c0;
+        const float* t00 = cb + ((size_t)h0 * Wc + w0) * NB;
+        const float* t01 = cb + ((size_t)h0 * Wc + w1) * NB;
+        const float* t10 = cb + ((size_t)h1 * Wc + w0) * NB;
+        const float* t11 = cb + ((size_t)h1 * Wc + w1) * NB;
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH / 8; ++j) {
+            float* x = v + 8 * j;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = 8 * j + 4 * q;
+                const float4 a = ldg4(t00 + c), b = ldg4(t01 + c), cc = ldg4(t10 + c), d = ldg4(t11 + c), bi = ldg4(bias + c0 + c);
+                // same association as EpiAddUp2 / the oracle: up + (conv + bias)
+                x[4 * q + 0] = ((1.f - lh) * ((1.f - lw) * a.x + lw * b.x) + lh * ((1.f - lw) * cc.x + lw * d.x)) + (x[4 * q + 0] + bi.x);
+                x[4 * q + 1] = ((1.f - lh) * ((1.f - lw) * a.y + lw * b.y) + lh * ((1.f - lw) * cc.y + lw * d.y)) + (x[4 * q + 1] + bi.y);
+                x[4 * q + 2] = ((1.f - lh) * ((1.f - lw) * a.z + lw * b.z) + lh * ((1.f - lw) * cc.z + lw * d.z)) + (x[4 * q + 2] + bi.z);
+                x[4 * q + 3] = ((1.f - lh) * ((1.f - lw) * a.w + lw * b.w) + lh * ((1.f - lw) * cc.w + lw * d.w)) + (x[4 * q + 3] + bi.w);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(x[q]));
+            uint4 h, l;
+            split_f16(make_float2(x[0], x[1]), h.x, l.x);
+            split_f16(make_float2(x[2], x[3]), h.y, l.y);
+            split_f16(make_float2(x[4], x[5]), h.z, l.z);
+            split_f16(make_float2(x[6], x[7]), h.w, l.w);
+            const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
+            reinterpret_cast<uint4*>(out.hi)[idx] = h;
+            reinterpret_cast<uint4*>(out.lo)[idx] = l;
+        }
+        if (out32) {
+            float* o = out32 + ((size_t)n * plane + pix) * NB + c0;
+#pragma unroll
+            for (int c = 0; c < NCH; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+        if (!(amax <= 65504.f) && status) atomicOr(status, 2);
+    }
+};
+
 // block-0 of a residual stage: conv1 (ReLU) and downsample (no ReLU) read the same input with the same
 // stride-2 stencil -> one implicit GEMM over the stacked output channels [conv1 | downsample]
 struct EpiSplit2 {
@@ -169,7 +229,7 @@ fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, c
 
 struct FnetBuffers {
     float *a0, *l1[4], *l2[4], *l3[4], *intra2, *intra1;
-    float *l3s, *intra2s;     // split-plane copies (tc5pconv.cuh) of l3[3] and intra2, which are also read as fp32
+    float *l1s, *l2s, *l3s, *intra2s;     // split-plane copies (tc5pconv.cuh) of the trunk outputs and of intra2, which are also read as fp32
     size_t total;
 };
 
@@ -184,6 +244,8 @@ static FnetBuffers fnet_carve(float* base, size_t N, size_t H, size_t W) {
     for (int i = 0; i < 4; ++i) b.l3[i] = at(N * (hw / 64) * 48);
     b.intra2 = at(N * (hw / 16) * 48);
     b.intra1 = at(N * (hw / 4) * 48);
+    b.l1s = at(N * (hw / 4) * 16);
+    b.l2s = at(N * (hw / 16) * 32);
     b.l3s = at(N * (hw / 64) * 48);
     b.intra2s = at(N * (hw / 16) * 48);
     b.total = c;
@@ -372,17 +434,22 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
         // default: residual stages and output convolutions on the persistent TMA + tcgen05 kernel, split-plane activations
         int* flag = tc5_error_flag();
         const tc5p::Split none{nullptr, nullptr};
-        IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, nullptr, N, H, W, st)));              // layer1 -> l1[3]  [H/2][W/2][16]
-        IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, nullptr, N, H1, W1, st)));        // layer2 -> l2[3]  [H/4][W/4][32]
-        IMVS_TRY((res_stage_p<32, 48, false, 96, 1>(w, 11, b.l2[3], b.l3, b.l3s, N, H2, W2, st))); // layer3 -> l3[3]  [H/8][W/8][48] (+ split)
-        const tc5p::Split l3s = tc5p::split_at(b.l3s, (size_t)N * H3 * W3 * 48), i2s = tc5p::split_at(b.intra2s, (size_t)N * H2 * W2 * 48),
+        IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, b.l1s, N, H, W, st)));                 // layer1 -> l1[3]  [H/2][W/2][16] (+ split)
+        IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, b.l2s, N, H1, W1, st)));           // layer2 -> l2[3]  [H/4][W/4][32] (+ split)
+        IMVS_TRY((res_stage_p<32, 48, false, 96, 1>(w, 11, b.l2[3], b.l3, b.l3s, N, H2, W2, st)));  // layer3 -> l3[3]  [H/8][W/8][48] (+ split)
+        const tc5p::Split l1s = tc5p::split_at(b.l1s, (size_t)N * H1 * W1 * 16), l2s = tc5p::split_at(b.l2s, (size_t)N * H2 * W2 * 32),
+                          l3s = tc5p::split_at(b.l3s, (size_t)N * H3 * W3 * 48), i2s = tc5p::split_at(b.intra2s, (size_t)N * H2 * W2 * 48),
                           i1s = tc5p::split_at(b.intra1, (size_t)N * H1 * W1 * 48);
+        const bool lat = tune("TC5P_LAT", 1) && w->w[17].f16ummai && w->w[19].f16ummai;
         IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16ummai, N, H3, W3, flag, st)));
-        IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2H{b.intra2, i2s, w->b[17], b.l3[3], H2, W2, 48},
-                                                   WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
+        // intra2 = up2(f3) + inner2(f2) (net.py:60): 1x1 on the tensor core, bilinear taps in the epilogue
+        if (lat) IMVS_TRY((tc5p::launch<32, 48, 1, true, 1>("fnet.inner2", l2s, EpiLateral{i2s, b.intra2, w->b[17], b.l3[3], H2, W2}, w->w[17].f16ummai, N, H2, W2, flag, st)));
+        else IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2H{b.intra2, i2s, w->b[17], b.l3[3], H2, W2, 48},
+                                                        WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
         IMVS_TRY((tc5p::launch<48, 32>("fnet.output2", i2s, tc5p::Epi{none, fea2, none, w->b[18], H2, W2, 0}, w->w[18].f16ummai, N, H2, W2, flag, st)));
-        IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2H{nullptr, i1s, w->b[19], b.intra2, H1, W1, 48},
-                                                   WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
+        if (lat) IMVS_TRY((tc5p::launch<16, 48, 1, true, 1>("fnet.inner1", l1s, EpiLateral{i1s, nullptr, w->b[19], b.intra2, H1, W1}, w->w[19].f16ummai, N, H1, W1, flag, st)));
+        else IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2H{nullptr, i1s, w->b[19], b.intra2, H1, W1, 48},
+                                                        WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
         IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16ummai, N, H1, W1, flag, st)));
         return 0;
     }

@@ -13,14 +13,14 @@
 // A stencil tap (dy, dx) is the same tile addressed (dy * 32 + dx) * 16 bytes further (tc5conv.cuh), so the A operand
 // of every tap is a shifted shared-memory descriptor.
 //
-//   grid = min(#tiles, #SMs) persistent CTAs of 320 threads:
+//   grid = min(#tiles, #SMs) persistent CTAs of 320 .. 576 threads:
 //     warp 0      TMA producer: tile t+1.. into a ring of NSTAGES shared-memory stages (full / empty mbarriers)
 //     warp 1      MMA issuer: MB (1 or 2) M-blocks of 128 slots x 9 taps x 3 products x CINP/16 k-steps of
 //                 tcgen05.mma.kind::f16 into one of TWO TMEM accumulator sets; tcgen05.commit frees the stage and
 //                 publishes the accumulator
-//     warps 2..9  epilogue: tcgen05.ld, bias / residual (read from split planes) / ReLU, fp16 range guard, and the
+//     warps 2..   epilogue (8 .. 16 warps): tcgen05.ld, bias / residual (read from split planes) / ReLU, fp16 range guard, and the
 //                 stores: split planes for the next tcgen05 layer and / or fp32 NHWC for the other consumers.  The
-//                 residual of tile t+1 is requested before tile t is processed.
+//                 residual of tile t+2 is requested before tile t is processed.
 //   weights ([tap][CINP/8][hi | lo][NB][8 halves], _pack.py:pack_umma_f16i) stay resident in shared memory.
 // Tile = 32 slots wide (30 valid output columns for a 3x3), 4 * MB output rows.
 #pragma once
@@ -50,7 +50,16 @@ using tc5::make_desc;
 using tc5::make_idesc_f16k;
 
 constexpr int WT = 32;                 // slots per tile row
-constexpr int THREADS = 320;           // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+// CTA: warp 0 producer, warp 1 MMA issuer, then 4 * MB * CS epilogue warps: a warp reads the TMEM lanes 32 * (warp % 4) ..,
+// its group index selects the M-block and one of CS channel slices (the epilogue, not the tensor core, was the pipeline's
+// slowest stage with 8 warps: ncu r2c17 -- the MMA warp spinning on the accumulator-empty barrier)
+template <int NB, int MB> struct Shape {
+    static constexpr int CS = MB == 2 ? 2 : (NB % 32 == 0 ? 4 : (NB == 48 ? 3 : 2));      // channel slices per M-block
+    static constexpr int NCH = NB / CS;                                                  // channels per epilogue thread (8 or 16)
+    static constexpr int EPI_WARPS = 4 * MB * CS;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static_assert(NCH % 8 == 0, "epilogue channel slice");
+};
 constexpr int MAX_STAGES = 6;
 
 // one activation tensor stored as split planes [N][C/8][H][W][8 halves]
@@ -94,6 +103,7 @@ struct Geo {
 // depend on the accumulator, issued one tile ahead); store<NB, NCH>(n, oy, ox, c0, v, pre, status).
 // out = relu?(acc + bias + residual); written as split planes (the next tcgen05 layer's operand) and / or fp32 NHWC.
 struct Epi {
+    static constexpr int kAhead = 2;
     Split out;               // [N][NB/8][H][W][8] or {nullptr, nullptr}
     float* out32;            // [N][H][W][NB] or nullptr
     Split res;               // residual split planes (same shape as out) or {nullptr, nullptr}
@@ -172,13 +182,14 @@ __device__ __forceinline__ uint32_t elect_one() {       // one lane of the (conv
 // accumulator columns [0, NB) (hi*hi) and [NB, 2NB) (hi*lo), and  A_lo x B_hi  (N = NB) adds the third product to columns
 // [0, NB); the epilogue sums the two column halves.  (The tensor core's cost per M=128, K=16 instruction is set by the A
 // operand it reads, not by N at these sizes -- tools/ubench/umma_chain.cu.)
-template <int CINP, int NB, int MB, int DIL, class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int CINP, int NB, int MB, int DIL, int KS, class Epi>
+__global__ void __launch_bounds__((Shape<NB, MB>::THREADS), 1)
 tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
                  const void* __restrict__ w_f16, const Geo geo, int* err_flag) {
     static_assert(CINP % 16 == 0 && NB % 16 == 0 && NB <= 64, "UMMA kind::f16 shape");
     static_assert(MB == 1 || (MB == 2 && NB <= 32), "M-blocks per tile (TMEM: 2 sets x MB x 2*NB columns <= 256)");
-    constexpr int KC = CINP / 8, PAD = DIL, ROWS = 4 * MB + 2 * PAD, NSLOT = ROWS * WT;
+    static_assert(KS == 1 || KS == 3, "1x1 or 3x3");
+    constexpr int KC = CINP / 8, PAD = DIL * (KS - 1) / 2, ROWS = 4 * MB + 2 * PAD, NSLOT = ROWS * WT, TAPS = KS * KS;
     constexpr int NBS = 2 * NB;                                  // TMEM columns per M-block: [hi*hi + lo*hi | hi*lo]
     constexpr int ACC_COLS = MB * NBS;                           // one accumulator set
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
@@ -186,14 +197,13 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     constexpr uint32_t A_BYTES = KC * NSLOT * 16;                // one plane of one stage
     constexpr uint32_t B_TAP_BYTES = KC * 2 * NB * 16;           // hi and lo of one tap
     constexpr uint32_t LBO_A = NSLOT * 16, LBO_B = 2 * NB * 16;
-    constexpr int NCH = MB == 2 ? NB : NB / 2;                   // channels per epilogue thread
-    static_assert(NCH % 8 == 0, "epilogue channel split");
+    constexpr int CS = Shape<NB, MB>::CS, NCH = Shape<NB, MB>::NCH, THREADS = Shape<NB, MB>::THREADS;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
     const int nst = geo.nstages;
     unsigned char* sA = smem_raw;                                               // [nst][hi | lo][KC][NSLOT][16 B]
     unsigned char* sB = sA + (size_t)nst * 2 * A_BYTES;                         // [tap][KC][hi NB | lo NB][16 B]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + 9 * B_TAP_BYTES);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + TAPS * B_TAP_BYTES);
     // barriers: [0, S) full, [S, 2S) empty, 2S + {0,1} accumulator full, 2S + {2,3} accumulator empty, 2S + 4 weights
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2 * MAX_STAGES + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -212,8 +222,8 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         fence_mbar_init();
         // weights are constants of the forward pass: requested before the grid-dependency wait; global order = shared
         // order [tap][KC][hi | lo][NB][8] (_pack.py:pack_umma_f16i), one bulk copy per tap
-        mbar_expect_tx(bar_w, 9 * B_TAP_BYTES);
-        for (int tap = 0; tap < 9; ++tap)
+        mbar_expect_tx(bar_w, TAPS * B_TAP_BYTES);
+        for (int tap = 0; tap < TAPS; ++tap)
             bulk_g2s(smem_u32(sB) + tap * B_TAP_BYTES, static_cast<const unsigned char*>(w_f16) + (size_t)tap * B_TAP_BYTES, B_TAP_BYTES, bar_w);
     }
     pdl_trigger();
@@ -265,12 +275,12 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 const uint64_t da_lo = da_hi + (A_BYTES >> 4);
                 const uint32_t dcol = tmem_d + (uint32_t)(acc * ACC_COLS);
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
                     for (int k16 = 0; k16 < CINP / 16; ++k16) {
                         // slots == 16-byte units: tap shift + k-step advance (two K chunks per MMA)
                         constexpr uint32_t KA = (2u * LBO_A) >> 4, KB = (2u * LBO_B) >> 4;
-                        const uint32_t shift = (uint32_t)((tap / 3) * DIL * WT + (tap % 3) * DIL) + (uint32_t)k16 * KA;
+                        const uint32_t shift = (uint32_t)((tap / KS) * DIL * WT + (tap % KS) * DIL) + (uint32_t)k16 * KA;
                         const uint64_t db = db0 + (uint64_t)(tap * (B_TAP_BYTES >> 4) + k16 * KB);
                         const uint32_t accum = (tap | k16) != 0;
 #pragma unroll
@@ -289,8 +299,8 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 1);
     } else {
         // ---- epilogue -------------------------------------------------------------------------------------------
-        const int ew = warp - 2, lg = warp & 3, grp = ew >> 2;       // TMEM lanes 32 * (warp % 4) ..; grp: M-block (MB = 2) / channel half
-        const int mb = MB == 2 ? grp : 0, c0 = MB == 2 ? 0 : grp * NCH;
+        const int ew = warp - 2, lg = warp & 3, grp = ew >> 2;       // TMEM lanes 32 * (warp % 4) ..; grp: (M-block, channel slice)
+        const int mb = grp / CS, c0 = (grp % CS) * NCH;
         const int slot = mb * 128 + lg * 32 + lane, r = slot >> 5, c = slot & 31;
         auto pixel = [&](int tile, int& n, int& oy, int& ox) {
             int oy0, ox0;
@@ -298,10 +308,13 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             oy = oy0 + r; ox = ox0 + c;
             return c < WT - 2 * PAD && oy < epi.H && ox < epi.W;
         };
-        typename Epi::template Pre<NCH> pre{}, pre_next{};
+        // accumulator-independent global reads (residual, gate operands) are requested Epi::kAhead (1 or 2) tiles ahead
+        constexpr int AHEAD = Epi::kAhead;
+        typename Epi::template Pre<NCH> pre{}, pre1{}, pre2{};
         {
             int n, oy, ox;
             if (blockIdx.x < n_tiles && pixel(blockIdx.x, n, oy, ox)) epi.template prefetch<NB, NCH>(n, oy, ox, c0, pre);
+            if (AHEAD == 2 && blockIdx.x + gridDim.x < n_tiles && pixel(blockIdx.x + gridDim.x, n, oy, ox)) epi.template prefetch<NB, NCH>(n, oy, ox, c0, pre1);
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -310,8 +323,8 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             const bool okp = pixel(tile, n, oy, ox);
             {
                 int n2, oy2, ox2;
-                const int nxt = tile + gridDim.x;
-                if (nxt < n_tiles && pixel(nxt, n2, oy2, ox2)) epi.template prefetch<NB, NCH>(n2, oy2, ox2, c0, pre_next);
+                const int nxt = tile + AHEAD * gridDim.x;
+                if (nxt < n_tiles && pixel(nxt, n2, oy2, ox2)) epi.template prefetch<NB, NCH>(n2, oy2, ox2, c0, AHEAD == 2 ? pre2 : pre1);
             }
             if (!mbar_wait_bounded(bar_tfull(acc), aph)) { if (lane == 0 && err_flag) atomicOr(err_flag, 1); break; }
             fence_after_sync();
@@ -328,7 +341,8 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
             for (int q = 0; q < NCH; ++q) v[q] += u[q];
             if (okp) epi.template store<NB, NCH>(n, oy, ox, c0, v, pre, err_flag);
-            pre = pre_next;
+            pre = pre1;
+            if (AHEAD == 2) pre1 = pre2;
         }
     }
     fence_before_sync();
@@ -358,18 +372,18 @@ inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, 
     return 0;
 }
 
-template <int CINP, int NB, int MB, int DIL, class Epi>
+template <int CINP, int NB, int MB, int DIL, int KS, class Epi>
 int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
-    constexpr int KC = CINP / 8, PAD = DIL;
+    constexpr int KC = CINP / 8, PAD = DIL * (KS - 1) / 2;
     Geo g{};
-    g.ks = 3; g.dil = DIL; g.pad = PAD;
+    g.ks = KS; g.dil = DIL; g.pad = PAD;
     g.valid = WT - 2 * PAD;
     g.THo = 4 * MB;
     g.rows = g.THo + 2 * PAD;
     g.tiles_x = cdiv(W, g.valid); g.tiles_y = cdiv(H, g.THo);
     g.n_tiles = g.tiles_x * g.tiles_y * N;
     g.a_bytes = (uint32_t)KC * g.rows * WT * 16;
-    const size_t fixed = (size_t)9 * 2 * KC * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
+    const size_t fixed = (size_t)KS * KS * 2 * KC * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
     const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
     const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, sm_count()));
@@ -379,27 +393,28 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
     CUtensorMap mh, ml;
     IMVS_TRY(make_plane_map(&mh, in.hi, N, KC, H, W, g.rows));
     IMVS_TRY(make_plane_map(&ml, in.lo, N, KC, H, W, g.rows));
-    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL, Epi>;
+    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL, KS, Epi>;
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     const int grid = std::min(g.n_tiles, sm_count());
-    if (launch_k(kern, dim3(grid), dim3(THREADS), smem, st, mh, ml, epi, w_f16, g, err_flag) != cudaSuccess)
+    if (launch_k(kern, dim3(grid), dim3(Shape<NB, MB>::THREADS), smem, st, mh, ml, epi, w_f16, g, err_flag) != cudaSuccess)
         return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
 
-// stride-1 3x3 convolution (dilation DIL) CINP -> NB of a split-plane tensor; out / out32 / res / bias / relu in `epi`
-template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, class Epi>
+// stride-1 KS x KS (3x3 with dilation DIL, or 1x1) convolution CINP -> NB of a split-plane tensor; the epilogue class decides
+// what happens to the accumulators (Epi: bias / residual / ReLU; featurenet.cu:EpiLateral; update.cu: the GRU gates)
+template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, int KS = 3, class Epi>
 int launch(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
     IMVS_REQUIRE(w_f16 && in.hi && in.lo, "%s: null tcgen05 operand", name);
     IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
     if constexpr (NB <= 32 && ALLOW_MB2) {
-        const int tiles2 = cdiv(W, WT - 2 * DIL) * cdiv(H, 8) * N;
+        const int tiles2 = cdiv(W, WT - DIL * (KS - 1)) * cdiv(H, 8) * N;
         const int force = tune("TC5P_MB", 0);
         // 8-row tiles (two M-blocks share one haloed tile: 1.25x instead of 1.5x halo rows) when they still fill the machine
-        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
+        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, KS, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
     }
-    return launch_mb<CINP, NB, 1, DIL, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
+    return launch_mb<CINP, NB, 1, DIL, KS, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
 }
 
 }  // namespace tc5p

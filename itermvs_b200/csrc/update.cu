@@ -85,7 +85,8 @@ __global__ void gru_split_inputs_kernel(const float* __restrict__ h, const float
     }
 }
 
-struct EpiGruZRp {           // 64 stacked channels: thread's 32 are z (c0 = 0) or r (c0 = 32)   (module.py:61-62)
+struct EpiGruZRp {           // 64 stacked channels: a thread's slice is part of z (c0 < 32) or of r (c0 >= 32)   (module.py:61-62)
+    static constexpr int kAhead = 1;
     const float* bias;       // [64]
     const float* h;          // [B][P][32]
     float* z;                // [B][P][32]
@@ -94,34 +95,34 @@ struct EpiGruZRp {           // 64 stacked channels: thread's 32 are z (c0 = 0) 
     template <int NCH> struct Pre { float4 hh[NCH / 4]; };
     template <int NB, int NCH>
     __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NCH>& p) const {
-        static_assert(NB == 64 && NCH == 32, "z | r halves");
-        if (c0 == 0) return;
-        const float* src = h + (((size_t)n * H + oy) * W + ox) * 32;
+        static_assert(NB == 64 && 32 % NCH == 0, "z | r halves");
+        if (c0 < 32) return;
+        const float* src = h + (((size_t)n * H + oy) * W + ox) * 32 + (c0 - 32);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) p.hh[c] = ldg4(src + 4 * c);
+        for (int c = 0; c < NCH / 4; ++c) p.hh[c] = ldg4(src + 4 * c);
     }
     template <int NB, int NCH>
     __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>& p, int*) const {
         const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
-        if (c0 == 0) {
-            float* dst = z + ((size_t)n * plane + pix) * 32;
+        if (c0 < 32) {
+            float* dst = z + ((size_t)n * plane + pix) * 32 + c0;
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-                const float4 b = ldg4(bias + c);
+            for (int c = 0; c < NCH; c += 4) {
+                const float4 b = ldg4(bias + c0 + c);
                 *reinterpret_cast<float4*>(dst + c) =
                     make_float4(sigmoidf_(v[c] + b.x), sigmoidf_(v[c + 1] + b.y), sigmoidf_(v[c + 2] + b.z), sigmoidf_(v[c + 3] + b.w));
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 b0 = ldg4(bias + 32 + 8 * j), b1 = ldg4(bias + 36 + 8 * j), h0 = p.hh[2 * j], h1 = p.hh[2 * j + 1];
+            for (int j = 0; j < NCH / 8; ++j) {
+                const float4 b0 = ldg4(bias + c0 + 8 * j), b1 = ldg4(bias + c0 + 4 + 8 * j), h0 = p.hh[2 * j], h1 = p.hh[2 * j + 1];
                 const float* a = v + 8 * j;
                 uint4 hi, lo;
                 split_f16(make_float2(sigmoidf_(a[0] + b0.x) * h0.x, sigmoidf_(a[1] + b0.y) * h0.y), hi.x, lo.x);
                 split_f16(make_float2(sigmoidf_(a[2] + b0.z) * h0.z, sigmoidf_(a[3] + b0.w) * h0.w), hi.y, lo.y);
                 split_f16(make_float2(sigmoidf_(a[4] + b1.x) * h1.x, sigmoidf_(a[5] + b1.y) * h1.y), hi.z, lo.z);
                 split_f16(make_float2(sigmoidf_(a[6] + b1.z) * h1.z, sigmoidf_(a[7] + b1.w) * h1.w), hi.w, lo.w);
-                const size_t idx = ((size_t)n * 6 + j) * plane + pix;
+                const size_t idx = ((size_t)n * 6 + ((c0 - 32) / 8 + j)) * plane + pix;
                 reinterpret_cast<uint4*>(rhx.hi)[idx] = hi;
                 reinterpret_cast<uint4*>(rhx.lo)[idx] = lo;
             }
@@ -130,6 +131,7 @@ struct EpiGruZRp {           // 64 stacked channels: thread's 32 are z (c0 = 0) 
 };
 
 struct EpiGruQp {            // q = tanh, h <- (1 - z) h + z q in place   (module.py:63-64)
+    static constexpr int kAhead = 1;
     const float* bias;       // [32]
     const float* z;          // [B][P][32]
     float* h;                // [B][P][32]

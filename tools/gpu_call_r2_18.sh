@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# round 2, GPU call 18: 16 epilogue warps + 2-tile prefetch, lateral 1x1 stages on the TMA + tcgen05 kernel
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+timeout 600 python -m pytest tests -q -m gpu > gpurun_out/r2c18_tests.log 2>&1
+echo "suite rc=$?"; tail -4 gpurun_out/r2c18_tests.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2c18_launches.csv \
+    python tools/profile_forward.py 1 > gpurun_out/r2c18_ncu1.log 2>&1
+tail -1 gpurun_out/r2c18_ncu1.log
+timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2c18_bench.json 2> gpurun_out/r2c18_bench.err
+IMVS_TUNE_TC5P_LAT=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-u8 > gpurun_out/r2c18_bench_latoff.json 2> gpurun_out/r2c18_bench_latoff.err
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/r2c18_bench*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, round(d["value"], 1), round(d["e2e"]["value"], 1), round(d["single_stream"]["value"], 1), d["stage_ms"])
+    except Exception as e:
+        print(f, "unreadable", e)
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r2c18_launches.csv')) if len(r)>10]
+hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
+for r in rows[1:19]+rows[46:50]:
+    print(r[ki][:100], r[vi])
+PY
