@@ -54,6 +54,37 @@ __device__ __forceinline__ long long run_chain(uint32_t tmem, uint32_t smem_base
     return clock64() - t0;
 }
 
+
+// the issue pattern of tc5pconv.cuh for 16 -> 16 channels, two M-blocks: per tap  A_hi(mb0), A_hi(mb1) x [B_hi | B_lo] (N = 32),
+// A_lo(mb0), A_lo(mb1) x B_hi (N = 16); tap shifts 0,1,2,32,33,34,64,65,66 slots; B block per tap.  VAR: 0 = as in the kernel,
+// 1 = all A start addresses 128-byte aligned (shift rounded down to 8 slots), 2 = same B for every tap
+template <int VAR>
+__device__ __forceinline__ long long run_conv_pattern(uint32_t tmem, uint32_t smem_base, uint32_t bar, uint32_t& ph, int tiles) {
+    constexpr uint32_t LBO_A = 320 * 16, LBO_B = 32 * 16, A_BYTES = 2 * 320 * 16, B_TAP = 2 * 32 * 16;
+    const uint64_t da_hi = make_desc(smem_base, LBO_A, 128), da_lo = da_hi + (A_BYTES >> 4);
+    const uint64_t db0 = make_desc(smem_base + 64 * 1024, LBO_B, 128);
+    const long long t0 = clock64();
+    if (elect_one()) {
+        for (int t = 0; t < tiles; ++t) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                uint32_t shift = (tap / 3) * 32 + (tap % 3);
+                if (VAR == 1) shift &= ~7u;
+                const uint64_t db = db0 + (VAR == 2 ? 0 : tap * (B_TAP >> 4));
+                umma(tmem, da_hi + shift, db, idesc_f16(32), (t | tap) ? 1u : 0u);
+                umma(tmem + 32, da_hi + shift + 128, db, idesc_f16(32), (t | tap) ? 1u : 0u);
+                umma(tmem, da_lo + shift, db, idesc_f16(16), 1u);
+                umma(tmem + 32, da_lo + shift + 128, db, idesc_f16(16), 1u);
+            }
+        }
+        commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, ph);
+    ph ^= 1;
+    return clock64() - t0;
+}
+
 // out[case] = clocks for 216 MMAs.  cases: N in {16,32,64,128,256} x chains in {1,2,4}
 __global__ void __launch_bounds__(128) chain_kernel(long long* out, int) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -81,6 +112,8 @@ __global__ void __launch_bounds__(128) chain_kernel(long long* out, int) {
         r[9] = run_chain<128, 1>(tmem, sb, b, ph); r[10] = run_chain<128, 2>(tmem, sb, b, ph); r[11] = run_chain<128, 4>(tmem, sb, b, ph);
         r[12] = run_chain<256, 1>(tmem, sb, b, ph); r[13] = run_chain<256, 2>(tmem, sb, b, ph); r[14] = -1;
         if (tid == 0) for (int i = 0; i < 15; ++i) out[blockIdx.x * 32 + i] = r[i];
+        const long long c0 = run_conv_pattern<0>(tmem, sb, b, ph, 6), c1 = run_conv_pattern<1>(tmem, sb, b, ph, 6), c2 = run_conv_pattern<2>(tmem, sb, b, ph, 6);
+        if (tid == 0) { out[blockIdx.x * 32 + 16] = c0; out[blockIdx.x * 32 + 17] = c1; out[blockIdx.x * 32 + 18] = c2; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -136,6 +169,8 @@ int main() {
             for (int ci = 0; ci < 3; ++ci, ++c) printf(" %7.1f", out[(grid - 1) * 32 + c] < 0 ? -1.0 : (double)out[(grid - 1) * 32 + c] / nmma);
             printf("\n");
         }
+        printf("  conv pattern (36 MMAs per tile, 6 tiles): clocks per MMA as in the kernel %.1f, A aligned to 128 B %.1f, one B block %.1f\n",
+               out[(grid - 1) * 32 + 16] / 216.0, out[(grid - 1) * 32 + 17] / 216.0, out[(grid - 1) * 32 + 18] / 216.0);
     }
     // TMA
     void* fn = nullptr;
