@@ -164,7 +164,9 @@ struct EpiSplit2 {
 constexpr int C0_TW = 32, C0_TH = 8, C0_PITCH = C0_TW + 2;
 __device__ __forceinline__ float c0_pixel(const float* p) { return ldg(p); }
 __device__ __forceinline__ float c0_pixel(const unsigned char* p) { return (float)__ldg(p) / 255.0f; }
-template <class PixT>
+// PSPLIT: the output goes out as fp16 hi / lo PARITY PLANES [4N][1][H/2][W/2][8] (tc5pconv.cuh: operand of layer1's stride-2
+// GEMM on the TMA + tcgen05 kernel) instead of fp32 NHWC-8; `out` then points at the hi plane, the lo plane follows it.
+template <class PixT, bool PSPLIT = false>
 __global__ void __launch_bounds__(128)
 fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, const float* __restrict__ bias,
                   float* __restrict__ out, int H, int W) {
@@ -215,6 +217,24 @@ fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, c
     }
     const int x = x0 + tx, y = y0 + 2 * ty;
     if (x >= W) return;
+    if constexpr (PSPLIT) {
+        uint4* ohi = reinterpret_cast<uint4*>(out);
+        uint4* olo = ohi + (size_t)gridDim.z * H * W;            // 16-byte units: N * H * W pixels x one 8-channel chunk
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (y + r >= H) break;
+            const float* a = r ? a1 : a0;
+            uint4 h, l;
+            split_f16(make_float2(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f)), h.x, l.x);
+            split_f16(make_float2(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f)), h.y, l.y);
+            split_f16(make_float2(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f)), h.z, l.z);
+            split_f16(make_float2(fmaxf(a[6], 0.f), fmaxf(a[7], 0.f)), h.w, l.w);
+            const size_t idx = tc5p::parity_index(n, y + r, x, 0, 1, H, W);
+            ohi[idx] = h;
+            olo[idx] = l;
+        }
+        return;
+    }
     if (y < H) {
         float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H + y) * W + x) * 8);
         o[0] = make_float4(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f), fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f));
@@ -312,6 +332,33 @@ static int res_stage_p(const imvs_featurenet_weights* w, int L, const float* x, 
     IMVS_TRY((tc5p::launch<CO, CO>("fnet.block0.conv2", y1, tc5p::Epi{b0, nullptr, ds, w->b[L + 1], H, W, 1}, w->w[L + 1].f16ummai, N, H, W, flag, st)));
     IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv1", b0, tc5p::Epi{y1, nullptr, none, w->b[L + 3], H, W, 1}, w->w[L + 3].f16ummai, N, H, W, flag, st)));
     IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, buf[3], b0, w->b[L + 4], H, W, 1}, w->w[L + 4].f16ummai, N, H, W, flag, st)));
+    return 0;
+}
+
+// ... and with the stride-2 GEMM on that kernel too: the stage's input arrives as PARITY PLANES (tc5pconv.cuh) from its
+// producer (conv1 / the previous stage's last epilogue); the trunk goes out as fp32 NHWC (trunk32), split planes (trunk_split)
+// and / or parity planes for the next stage (trunk_parity), whichever are non-null.  H, W: the stage's OUTPUT size.
+template <int CI, int CO>
+static int res_stage_p2(const imvs_featurenet_weights* w, int L, const tc5p::Split& xp, float* const buf[4], float* trunk32,
+                        float* trunk_split, float* trunk_parity, int N, int H, int W, cudaStream_t st) {
+    const size_t elems = (size_t)N * H * W * CO;
+    const tc5p::Split y1 = tc5p::split_at(buf[0], elems), ds = tc5p::split_at(buf[1], elems), b0 = tc5p::split_at(buf[2], elems);
+    const tc5p::Split none{nullptr, nullptr}, ts = trunk_split ? tc5p::split_at(trunk_split, elems) : none,
+                      tp = trunk_parity ? tc5p::split_at(trunk_parity, elems) : none;
+    const int LS = 21 + (L - 1) / 5;
+    int* flag = tc5_error_flag();
+    if constexpr (2 * CO <= 64) {
+        IMVS_TRY((tc5p::launch<CI, 2 * CO, 1, true, 3, 2>("fnet.block0.conv1|downsample", xp, tc5p::EpiStack2{y1, ds, w->b[LS], H, W, CO},
+                                                          w->w[LS].f16ummai, N, H, W, flag, st)));
+    } else {
+        IMVS_TRY((tc5p::launch<CI, CO, 1, true, 3, 2>("fnet.block0.conv1", xp, tc5p::Epi{y1, nullptr, none, w->b[L], H, W, 1}, w->w[L].f16ummai,
+                                                      N, H, W, flag, st)));
+        IMVS_TRY((tc5p::launch<CI, CO, 1, true, 3, 2>("fnet.block0.downsample", xp, tc5p::Epi{ds, nullptr, none, w->b[L + 2], H, W, 0},
+                                                      w->w[L + 2].f16ummai, N, H, W, flag, st)));
+    }
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block0.conv2", y1, tc5p::Epi{b0, nullptr, ds, w->b[L + 1], H, W, 1}, w->w[L + 1].f16ummai, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv1", b0, tc5p::Epi{y1, nullptr, none, w->b[L + 3], H, W, 1}, w->w[L + 3].f16ummai, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, trunk32, b0, w->b[L + 4], H, W, 1, tp}, w->w[L + 4].f16ummai, N, H, W, flag, st)));
     return 0;
 }
 
@@ -420,27 +467,42 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8;
     const TapTables s1 = conv_tables(3, 1, 1, 8), k1 = conv_tables(1, 1, 1, 8);
     // conv1: 3 -> 8, BN, ReLU on the planar image (net.py:13)
+    const bool p_ready = fnet_tc5p_ready(w);
+    const bool lat = p_ready && tune("TC5P_LAT", 1) && w->w[17].f16ummai && w->w[19].f16ummai;
+    // stride-2 GEMMs on the TMA + tcgen05 kernel too (then no layer of the default FeatureNet runs on mma.sync)
+    const bool s2p = lat && tune("TC5P_S2", 1) && w->w[21].f16ummai && w->w[22].f16ummai && w->w[11].f16ummai && w->w[13].f16ummai;
     if (imgs_u8 || tune("CONV0", 1)) {
         IMVS_REQUIRE(w->w[0].fp32 && w->b[0], "featurenet_forward: conv1 weights missing");
         dim3 grid(cdiv(W, C0_TW), cdiv(H, C0_TH), N);
         IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "fnet.conv1: grid too large");
-        if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
-        else IMVS_CUDA(launch_k(fnet_conv0_kernel<float>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+        if (s2p) {      // output as fp16 hi / lo parity planes (same bytes, in a0)
+            if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char, true>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
+            else IMVS_CUDA(launch_k(fnet_conv0_kernel<float, true>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+        } else {
+            if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
+            else IMVS_CUDA(launch_k(fnet_conv0_kernel<float>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+        }
     } else {
         IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                                 WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     }
-    if (fnet_tc5p_ready(w)) {
+    if (p_ready) {
         // default: residual stages and output convolutions on the persistent TMA + tcgen05 kernel, split-plane activations
         int* flag = tc5_error_flag();
         const tc5p::Split none{nullptr, nullptr};
-        IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, b.l1s, N, H, W, st)));                 // layer1 -> l1[3]  [H/2][W/2][16] (+ split)
-        IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, b.l2s, N, H1, W1, st)));           // layer2 -> l2[3]  [H/4][W/4][32] (+ split)
-        IMVS_TRY((res_stage_p<32, 48, false, 96, 1>(w, 11, b.l2[3], b.l3, b.l3s, N, H2, W2, st)));  // layer3 -> l3[3]  [H/8][W/8][48] (+ split)
+        if (s2p && (imgs_u8 || tune("CONV0", 1))) {
+            // trunk of stage 1 / 2: split planes for the lateral 1x1 and parity planes (in the fp32 trunk's buffer) for the next stage
+            IMVS_TRY((res_stage_p2<8, 16>(w, 1, tc5p::split_at(b.a0, (size_t)N * H * W * 8), b.l1, nullptr, b.l1s, b.l1[3], N, H1, W1, st)));
+            IMVS_TRY((res_stage_p2<16, 32>(w, 6, tc5p::split_at(b.l1[3], (size_t)N * H1 * W1 * 16), b.l2, nullptr, b.l2s, b.l2[3], N, H2, W2, st)));
+            IMVS_TRY((res_stage_p2<32, 48>(w, 11, tc5p::split_at(b.l2[3], (size_t)N * H2 * W2 * 32), b.l3, b.l3[3], b.l3s, nullptr, N, H3, W3, st)));
+        } else {
+            IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, b.l1s, N, H, W, st)));                 // layer1 -> l1[3]  [H/2][W/2][16] (+ split)
+            IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, b.l2s, N, H1, W1, st)));           // layer2 -> l2[3]  [H/4][W/4][32] (+ split)
+            IMVS_TRY((res_stage_p<32, 48, false, 96, 1>(w, 11, b.l2[3], b.l3, b.l3s, N, H2, W2, st)));  // layer3 -> l3[3]  [H/8][W/8][48] (+ split)
+        }
         const tc5p::Split l1s = tc5p::split_at(b.l1s, (size_t)N * H1 * W1 * 16), l2s = tc5p::split_at(b.l2s, (size_t)N * H2 * W2 * 32),
                           l3s = tc5p::split_at(b.l3s, (size_t)N * H3 * W3 * 48), i2s = tc5p::split_at(b.intra2s, (size_t)N * H2 * W2 * 48),
                           i1s = tc5p::split_at(b.intra1, (size_t)N * H1 * W1 * 48);
-        const bool lat = tune("TC5P_LAT", 1) && w->w[17].f16ummai && w->w[19].f16ummai;
         IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16ummai, N, H3, W3, flag, st)));
         // intra2 = up2(f3) + inner2(f2) (net.py:60): 1x1 on the tensor core, bilinear taps in the epilogue
         if (lat) IMVS_TRY((tc5p::launch<32, 48, 1, true, 1>("fnet.inner2", l2s, EpiLateral{i2s, b.intra2, w->b[17], b.l3[3], H2, W2}, w->w[17].f16ummai, N, H2, W2, flag, st)));

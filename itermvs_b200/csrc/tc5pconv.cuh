@@ -102,6 +102,12 @@ struct Geo {
 // Interface of an epilogue class: members H, W; Pre<NCH>; prefetch<NB, NCH>(n, oy, ox, c0, pre) (global reads that do not
 // depend on the accumulator, issued one tile ahead); store<NB, NCH>(n, oy, ox, c0, v, pre, status).
 // out = relu?(acc + bias + residual); written as split planes (the next tcgen05 layer's operand) and / or fp32 NHWC.
+// index (in 16-byte units) of chunk kc of pixel (oy, ox) of image n in the PARITY-PLANE layout [4N][KCo][H/2][W/2][8] that a
+// stride-2 layer reads (image 4n + 2 (oy & 1) + (ox & 1) holds the pixels of that parity); H, W even
+__device__ __forceinline__ size_t parity_index(int n, int oy, int ox, int kc, int KCo, int H, int W) {
+    return (((size_t)(4 * n + 2 * (oy & 1) + (ox & 1)) * KCo + kc) * (H >> 1) + (oy >> 1)) * (W >> 1) + (ox >> 1);
+}
+
 struct Epi {
     static constexpr int kAhead = 2;
     Split out;               // [N][NB/8][H][W][8] or {nullptr, nullptr}
@@ -109,6 +115,7 @@ struct Epi {
     Split res;               // residual split planes (same shape as out) or {nullptr, nullptr}
     const float* bias;       // [NB] or nullptr
     int H, W, relu;
+    Split outp = {nullptr, nullptr};     // the same values as parity planes (operand of a following stride-2 layer) or null
 
     template <int NCH> struct Pre { uint4 h[NCH / 8], l[NCH / 8]; };
 
@@ -150,15 +157,22 @@ struct Epi {
                 if (relu) x[q] = fmaxf(x[q], 0.f);
                 amax = fmaxf(amax, fabsf(x[q]));
             }
-            if (out.hi) {
+            if (out.hi || outp.hi) {
                 uint4 h, l;
                 split_f16(make_float2(x[0], x[1]), h.x, l.x);
                 split_f16(make_float2(x[2], x[3]), h.y, l.y);
                 split_f16(make_float2(x[4], x[5]), h.z, l.z);
                 split_f16(make_float2(x[6], x[7]), h.w, l.w);
-                const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
-                reinterpret_cast<uint4*>(out.hi)[idx] = h;
-                reinterpret_cast<uint4*>(out.lo)[idx] = l;
+                if (out.hi) {
+                    const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
+                    reinterpret_cast<uint4*>(out.hi)[idx] = h;
+                    reinterpret_cast<uint4*>(out.lo)[idx] = l;
+                }
+                if (outp.hi) {
+                    const size_t idx = parity_index(n, oy, ox, c0 / 8 + j, NB / 8, H, W);
+                    reinterpret_cast<uint4*>(outp.hi)[idx] = h;
+                    reinterpret_cast<uint4*>(outp.lo)[idx] = l;
+                }
             }
         }
         if (out32) {
@@ -167,6 +181,46 @@ struct Epi {
             for (int c = 0; c < NCH; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
         }
         // a value beyond +-65504 saturates in the split above / in the next layer's split: raise the flag (imvs_device_status bit 1)
+        if (!(amax <= 65504.f) && status) atomicOr(status, 2);
+    }
+};
+
+// [conv1 | downsample] of a ResidualBlock's first stage as one GEMM over the stacked output channels (module.py:36-49):
+// channels [0, CO) -> relu(v + bias) -> y, channels [CO, 2 CO) -> v + bias -> ds; both written as split planes
+struct EpiStack2 {
+    static constexpr int kAhead = 1;
+    Split y, ds;             // [N][CO/8][H][W][8] each
+    const float* bias;       // [2 CO]
+    int H, W, CO;
+    template <int NCH> struct Pre {};
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NCH>&) const {}
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>&, int* status) const {
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        const bool first = c0 < CO;                      // a thread's channel slice lies in one half (NCH divides CO)
+        const Split& o = first ? y : ds;
+        const int cb = first ? c0 : c0 - CO;
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH / 8; ++j) {
+            float* x = v + 8 * j;
+            const float4 b0 = ldg4(bias + c0 + 8 * j), b1 = ldg4(bias + c0 + 8 * j + 4);
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (first) x[q] = fmaxf(x[q], 0.f);
+                amax = fmaxf(amax, fabsf(x[q]));
+            }
+            uint4 h, l;
+            split_f16(make_float2(x[0], x[1]), h.x, l.x);
+            split_f16(make_float2(x[2], x[3]), h.y, l.y);
+            split_f16(make_float2(x[4], x[5]), h.z, l.z);
+            split_f16(make_float2(x[6], x[7]), h.w, l.w);
+            const size_t idx = ((size_t)n * (CO / 8) + (cb / 8 + j)) * plane + pix;
+            reinterpret_cast<uint4*>(o.hi)[idx] = h;
+            reinterpret_cast<uint4*>(o.lo)[idx] = l;
+        }
         if (!(amax <= 65504.f) && status) atomicOr(status, 2);
     }
 };
@@ -182,21 +236,33 @@ __device__ __forceinline__ uint32_t elect_one() {       // one lane of the (conv
 // accumulator columns [0, NB) (hi*hi) and [NB, 2NB) (hi*lo), and  A_lo x B_hi  (N = NB) adds the third product to columns
 // [0, NB); the epilogue sums the two column halves.  (The tensor core's cost per M=128, K=16 instruction is set by the A
 // operand it reads, not by N at these sizes -- tools/ubench/umma_chain.cu.)
-template <int CINP, int NB, int MB, int DIL, int KS, class Epi>
+// STRIDE = 2 (3x3, padding 1): the input is stored as PARITY PLANES -- image (n, row parity rp, column parity cp) holds the
+// pixels (2i + rp, 2j + cp) as an ordinary split-plane image [4N][C/8][H/2][W/2][8] -- so that every tap of the strided stencil
+// is again a shifted view of a dense tile: tap (ky, kx) reads parity (ky != 1, kx != 1) at offset (ky == 2, kx == 2).  A stage
+// holds the four parity sub-tiles (4 MB + 1 rows x 32 slots each, the odd ones starting one row / column earlier): eight TMA
+// loads per tile, 31 valid output columns per 32.  CINP = 8 (one K chunk): the MMA's second K chunk aliases the first
+// (descriptor LBO = 0) against zero weights.
+template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
 __global__ void __launch_bounds__((Shape<NB, MB>::THREADS), 1)
 tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
                  const void* __restrict__ w_f16, const Geo geo, int* err_flag) {
-    static_assert(CINP % 16 == 0 && NB % 16 == 0 && NB <= 64, "UMMA kind::f16 shape");
+    static_assert((CINP % 16 == 0 || CINP == 8) && NB % 16 == 0 && NB <= 64, "UMMA kind::f16 shape");
     static_assert(MB == 1 || (MB == 2 && NB <= 32), "M-blocks per tile (TMEM: 2 sets x MB x 2*NB columns <= 256)");
     static_assert(KS == 1 || KS == 3, "1x1 or 3x3");
-    constexpr int KC = CINP / 8, PAD = DIL * (KS - 1) / 2, ROWS = 4 * MB + 2 * PAD, NSLOT = ROWS * WT, TAPS = KS * KS;
+    static_assert(STRIDE == 1 || (STRIDE == 2 && KS == 3 && DIL == 1), "stride 2: 3x3, no dilation");
+    constexpr int KC = CINP / 8, KCW = (CINP + 15) / 16 * 2, KSTEPS = (CINP + 15) / 16, TAPS = KS * KS;
+    constexpr int PAD = STRIDE == 2 ? 0 : DIL * (KS - 1) / 2;                         // halo columns lost per tile side
+    constexpr int VALID = STRIDE == 2 ? WT - 1 : WT - 2 * PAD;                        // valid output columns per tile
+    constexpr int ROWS = STRIDE == 2 ? 4 * MB + 1 : 4 * MB + 2 * PAD;                 // rows of one (sub-)tile
+    constexpr int NSUB = STRIDE == 2 ? 4 : 1, SUBSLOT = ROWS * WT, NSLOT = NSUB * SUBSLOT;
     constexpr int NBS = 2 * NB;                                  // TMEM columns per M-block: [hi*hi + lo*hi | hi*lo]
     constexpr int ACC_COLS = MB * NBS;                           // one accumulator set
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
     static_assert(2 * ACC_COLS <= 256, "TMEM budget");
-    constexpr uint32_t A_BYTES = KC * NSLOT * 16;                // one plane of one stage
-    constexpr uint32_t B_TAP_BYTES = KC * 2 * NB * 16;           // hi and lo of one tap
-    constexpr uint32_t LBO_A = NSLOT * 16, LBO_B = 2 * NB * 16;
+    constexpr uint32_t SUB_BYTES = KC * SUBSLOT * 16;            // one plane of one (sub-)tile
+    constexpr uint32_t A_BYTES = NSUB * SUB_BYTES;               // one plane of one stage
+    constexpr uint32_t B_TAP_BYTES = KCW * 2 * NB * 16;          // hi and lo of one tap
+    constexpr uint32_t LBO_A = CINP == 8 ? 0u : SUBSLOT * 16u, LBO_B = 2 * NB * 16;
     constexpr int CS = Shape<NB, MB>::CS, NCH = Shape<NB, MB>::NCH, THREADS = Shape<NB, MB>::THREADS;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
@@ -238,7 +304,7 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         const int tx = tile % tiles_x, t2 = tile / tiles_x;
         n = t2 / tiles_y;
         oy0 = (t2 - n * tiles_y) * (4 * MB);
-        ox0 = tx * (WT - 2 * PAD);
+        ox0 = tx * VALID;
     };
 
     if (warp == 0) {
@@ -252,8 +318,16 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             if (elect_one()) {
                 mbar_expect_tx(bar_full(s), 2 * A_BYTES);
                 const uint32_t dst = smem_u32(sA) + (uint32_t)s * 2 * A_BYTES;
-                tma_load_4d(dst, &map_hi, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
-                tma_load_4d(dst + A_BYTES, &map_lo, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
+                if constexpr (STRIDE == 1) {
+                    tma_load_4d(dst, &map_hi, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
+                    tma_load_4d(dst + A_BYTES, &map_lo, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
+                } else {
+#pragma unroll
+                    for (int par = 0; par < 4; ++par) {          // par = 2 * rp + cp; odd parities start one row / column earlier
+                        tma_load_4d(dst + par * SUB_BYTES, &map_hi, bar_full(s), (ox0 - (par & 1)) * 8, oy0 - (par >> 1), 0, 4 * n + par);
+                        tma_load_4d(dst + A_BYTES + par * SUB_BYTES, &map_lo, bar_full(s), (ox0 - (par & 1)) * 8, oy0 - (par >> 1), 0, 4 * n + par);
+                    }
+                }
             }
             __syncwarp();
         }
@@ -277,10 +351,14 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
-                    for (int k16 = 0; k16 < CINP / 16; ++k16) {
+                    for (int k16 = 0; k16 < KSTEPS; ++k16) {
                         // slots == 16-byte units: tap shift + k-step advance (two K chunks per MMA)
                         constexpr uint32_t KA = (2u * LBO_A) >> 4, KB = (2u * LBO_B) >> 4;
-                        const uint32_t shift = (uint32_t)((tap / KS) * DIL * WT + (tap % KS) * DIL) + (uint32_t)k16 * KA;
+                        constexpr uint32_t SUB16 = SUB_BYTES >> 4;
+                        const int ky = tap / KS, kx = tap % KS;
+                        const uint32_t tapoff = STRIDE == 1 ? (uint32_t)(ky * DIL * WT + kx * DIL)
+                                                            : (uint32_t)(2 * (ky != 1) + (kx != 1)) * SUB16 + (uint32_t)((ky == 2) * WT + (kx == 2));
+                        const uint32_t shift = tapoff + (uint32_t)k16 * KA;
                         const uint64_t db = db0 + (uint64_t)(tap * (B_TAP_BYTES >> 4) + k16 * KB);
                         const uint32_t accum = (tap | k16) != 0;
 #pragma unroll
@@ -306,7 +384,7 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             int oy0, ox0;
             decode(tile, n, oy0, ox0);
             oy = oy0 + r; ox = ox0 + c;
-            return c < WT - 2 * PAD && oy < epi.H && ox < epi.W;
+            return c < VALID && oy < epi.H && ox < epi.W;
         };
         // accumulator-independent global reads (residual, gate operands) are requested Epi::kAhead (1 or 2) tiles ahead
         constexpr int AHEAD = Epi::kAhead;
@@ -358,6 +436,7 @@ EncodeTiledFn encode_tiled_fn();       // cuTensorMapEncodeTiled through cudaGet
 int sm_count();                        // multiprocessors of the current device (cached per device)
 
 // tensor map over one split plane [N][KC][H][W][8 halves] as the 4-D tensor {W*8, H, KC, N}; box {256, rows, KC, 1}
+// (parity planes of a stride-2 layer's input: N = 4 * images, H and W = half the image's)
 inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, int H, int W, int rows) {
     EncodeTiledFn enc = encode_tiled_fn();
     IMVS_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
@@ -372,18 +451,19 @@ inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, 
     return 0;
 }
 
-template <int CINP, int NB, int MB, int DIL, int KS, class Epi>
+// H, W: OUTPUT size (= input size for STRIDE 1; the input of a STRIDE 2 layer is 2H x 2W, stored as parity planes)
+template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
 int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
-    constexpr int KC = CINP / 8, PAD = DIL * (KS - 1) / 2;
+    constexpr int KC = CINP / 8, KCW = (CINP + 15) / 16 * 2, PAD = STRIDE == 2 ? 0 : DIL * (KS - 1) / 2;
     Geo g{};
     g.ks = KS; g.dil = DIL; g.pad = PAD;
-    g.valid = WT - 2 * PAD;
+    g.valid = STRIDE == 2 ? WT - 1 : WT - 2 * PAD;
     g.THo = 4 * MB;
-    g.rows = g.THo + 2 * PAD;
+    g.rows = STRIDE == 2 ? g.THo + 1 : g.THo + 2 * PAD;
     g.tiles_x = cdiv(W, g.valid); g.tiles_y = cdiv(H, g.THo);
     g.n_tiles = g.tiles_x * g.tiles_y * N;
-    g.a_bytes = (uint32_t)KC * g.rows * WT * 16;
-    const size_t fixed = (size_t)KS * KS * 2 * KC * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
+    g.a_bytes = (uint32_t)(STRIDE == 2 ? 4 : 1) * KC * g.rows * WT * 16;
+    const size_t fixed = (size_t)KS * KS * 2 * KCW * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
     const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
     const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, sm_count()));
@@ -391,9 +471,9 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
                                       (budget - fixed) / (2 * (size_t)g.a_bytes));
     const size_t smem = fixed + (size_t)g.nstages * 2 * g.a_bytes;
     CUtensorMap mh, ml;
-    IMVS_TRY(make_plane_map(&mh, in.hi, N, KC, H, W, g.rows));
-    IMVS_TRY(make_plane_map(&ml, in.lo, N, KC, H, W, g.rows));
-    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL, KS, Epi>;
+    IMVS_TRY(make_plane_map(&mh, in.hi, STRIDE == 2 ? 4 * N : N, KC, H, W, g.rows));     // stride 2: parity planes are H x W (= the output size)
+    IMVS_TRY(make_plane_map(&ml, in.lo, STRIDE == 2 ? 4 * N : N, KC, H, W, g.rows));
+    auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL, KS, STRIDE, Epi>;
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     const int grid = std::min(g.n_tiles, sm_count());
@@ -404,17 +484,17 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
 
 // stride-1 KS x KS (3x3 with dilation DIL, or 1x1) convolution CINP -> NB of a split-plane tensor; the epilogue class decides
 // what happens to the accumulators (Epi: bias / residual / ReLU; featurenet.cu:EpiLateral; update.cu: the GRU gates)
-template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, int KS = 3, class Epi>
+template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, int KS = 3, int STRIDE = 1, class Epi>
 int launch(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
     IMVS_REQUIRE(w_f16 && in.hi && in.lo, "%s: null tcgen05 operand", name);
-    IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
+    IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 * STRIDE * STRIDE < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
     if constexpr (NB <= 32 && ALLOW_MB2) {
-        const int tiles2 = cdiv(W, WT - DIL * (KS - 1)) * cdiv(H, 8) * N;
+        const int tiles2 = cdiv(W, STRIDE == 2 ? WT - 1 : WT - DIL * (KS - 1)) * cdiv(H, 8) * N;
         const int force = tune("TC5P_MB", 0);
         // 8-row tiles (two M-blocks share one haloed tile: 1.25x instead of 1.5x halo rows) when they still fill the machine
-        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, KS, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
+        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, KS, STRIDE, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
     }
-    return launch_mb<CINP, NB, 1, DIL, KS, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
+    return launch_mb<CINP, NB, 1, DIL, KS, STRIDE, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
 }
 
 }  // namespace tc5p
