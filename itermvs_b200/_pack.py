@@ -68,19 +68,21 @@ def pack_f16x3(w: Tensor) -> Tensor:
 
 
 def pack_umma_f16(w: Tensor):
-    """[tap][CinP][CoutP] fp32 -> fp16 hi / lo in the tcgen05 K-major canonical order [tap][hi | lo][CinK/8][CoutP][8 halves]
-    (element (n, k) of a tap at ((k/8) * CoutP + n) * 16 B + (k%8) * 2 B), CinK = CinP rounded up to 16."""
+    """[tap][CinP][CoutP] fp32 -> fp16 hi / lo in the tcgen05 K-major canonical order [tap][hi | lo][CinK/8][CoutN][8 halves]
+    (element (n, k) of a tap at ((k/8) * CoutN + n) * 16 B + (k%8) * 2 B), CinK = CinP rounded up to 16, CoutN = CoutP
+    rounded up to 16 (the UMMA N granularity at M = 128; the extra output channels have zero weights)."""
     taps, cinp, coutp = w.shape
-    if coutp % 16 != 0 or coutp > 64:
+    coutn = (coutp + 15) // 16 * 16
+    if coutn > 64:
         return None
     cink = (cinp + 15) // 16 * 16
-    x = torch.zeros(taps, cink, coutp, device=w.device, dtype=torch.float32)
-    x[:, :cinp] = w
+    x = torch.zeros(taps, cink, coutn, device=w.device, dtype=torch.float32)
+    x[:, :cinp, :coutp] = w
     hi = x.clamp(-65504.0, 65504.0).half()
     lo = (x - hi.float()).clamp(-65504.0, 65504.0).half()
 
-    def canon(h):    # [tap][CinK][CoutP] -> [tap][CinK/8][CoutP][8]
-        return h.reshape(taps, cink // 8, 8, coutp).permute(0, 1, 3, 2)
+    def canon(h):    # [tap][CinK][CoutN] -> [tap][CinK/8][CoutN][8]
+        return h.reshape(taps, cink // 8, 8, coutn).permute(0, 1, 3, 2)
 
     return torch.stack([canon(hi), canon(lo)], dim=1).contiguous()
 

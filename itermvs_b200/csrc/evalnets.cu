@@ -4,6 +4,7 @@
 //   activations channels-last.
 #include "common.cuh"
 #include "mmaconv.cuh"
+#include "tc5pconv.cuh"
 
 namespace imvs {
 
@@ -22,6 +23,104 @@ struct EpiCorrOut {          // conv5 (1 valid cout): + bias, scatter to out[(n/
         out[(size_t)(n / period) * bstride + ((size_t)oy * W + ox) * pstride + r] = v[0] + ldg(b);
     }
 };
+
+// ---- CorrNet on the persistent TMA + tcgen05 kernel (tc5pconv.cuh) ------------------------------------------------------
+// transposed convolution + U-Net skip (itermvs.py:374-377): thread = (input pixel, output parity); H, W = INPUT grid
+struct EpiTconvP {
+    static constexpr int kAhead = 1;
+    tc5p::Split out;         // [N][kco][2H][2W][8]
+    tc5p::Split skip;        // same shape
+    int H, W, kco;
+    template <int NCH> struct Pre { uint4 h[NCH / 8], l[NCH / 8]; };
+    __device__ __forceinline__ size_t index(int n, int iy, int ix, int c0, int NB, int j) const {
+        const int par = c0 / NB, oy = 2 * iy + (par >> 1), ox = 2 * ix + (par & 1);
+        return (((size_t)n * kco + j) * (2 * H) + oy) * (size_t)(2 * W) + ox;
+    }
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int n, int iy, int ix, int c0, Pre<NCH>& p) const {
+#pragma unroll
+        for (int j = 0; j < NCH / 8; ++j) {
+            if (j >= kco) break;
+            const size_t idx = index(n, iy, ix, c0, NB, j);
+            p.h[j] = __ldg(reinterpret_cast<const uint4*>(skip.hi) + idx);
+            p.l[j] = __ldg(reinterpret_cast<const uint4*>(skip.lo) + idx);
+        }
+    }
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int iy, int ix, int c0, float (&v)[NCH], const Pre<NCH>& p, int* status) const {
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH / 8; ++j) {
+            if (j >= kco) break;
+            float* x = v + 8 * j;
+            const uint32_t hh[4] = {p.h[j].x, p.h[j].y, p.h[j].z, p.h[j].w}, ll[4] = {p.l[j].x, p.l[j].y, p.l[j].z, p.l[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[q]));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ll[q]));
+                x[2 * q] += a.x + b.x;
+                x[2 * q + 1] += a.y + b.y;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(x[q]));
+            uint4 h, l;
+            split_f16(make_float2(x[0], x[1]), h.x, l.x);
+            split_f16(make_float2(x[2], x[3]), h.y, l.y);
+            split_f16(make_float2(x[4], x[5]), h.z, l.z);
+            split_f16(make_float2(x[6], x[7]), h.w, l.w);
+            const size_t idx = index(n, iy, ix, c0, NB, j);
+            reinterpret_cast<uint4*>(out.hi)[idx] = h;
+            reinterpret_cast<uint4*>(out.lo)[idx] = l;
+        }
+        if (!(amax <= 65504.f) && status) atomicOr(status, 2);
+    }
+};
+
+struct EpiCorrOutP {         // EpiCorrOut for the tcgen05 kernel: channel 0 + bias -> out[(n/period)*bstride + p*pstride + n%period]
+    static constexpr int kAhead = 1;
+    float* out;
+    const float* bias[3];
+    int period, split1, split2;
+    size_t bstride, pstride;
+    int H, W;
+    template <int NCH> struct Pre {};
+    template <int NB, int NCH>
+    __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NCH>&) const {}
+    template <int NB, int NCH>
+    __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>&, int*) const {
+        if (c0 != 0) return;
+        const int r = n % period;
+        const float* b = r < split1 ? bias[0] : (r < split2 ? bias[1] : bias[2]);
+        out[(size_t)(n / period) * bstride + ((size_t)oy * W + ox) * pstride + r] = v[0] + ldg(b);
+    }
+};
+
+static tc5p::WSel wsel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
+    tc5p::WSel s;
+    for (int i = 0; i < 3; ++i) {
+        const imvs_corrnet_weights& c = sets[i];
+        const imvs_wpair& p = which == 0 ? c.conv0 : which == 1 ? c.conv1 : which == 2 ? c.conv2 : which == 3 ? c.conv3 : which == 4 ? c.conv4 : c.conv5;
+        s.w[i] = p.f16ummai;
+    }
+    s.nsets = period == 1 ? 1 : 3;
+    s.period = period; s.split1 = split1; s.split2 = split2;
+    return s;
+}
+
+static bool corrnet_tc5p_ready(const imvs_corrnet_weights* sets) {
+#ifdef CUSIM
+    return false;
+#else
+    // OFF by default: measured on B200 (gpurun call r2c22) the seven tcgen05 launches of a pass take 75 us against 66 us for the
+    // six mma.sync launches -- every persistent launch has a ~7 us floor (TMEM allocation, barrier and weight staging, first
+    // TMA round trip, drain) that these 160..960-tile layers cannot amortise.  IMVS_TUNE_TC5P_CORR=1 selects it (parity-tested).
+    if (conv_passes() != 4 || !tune("TC5P_CORR", 0) || !tc5p::encode_tiled_fn()) return false;
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 6; ++k)
+            if (!wsel_of(sets, 1, 1, 1, k).w[i]) return false;
+    return true;
+#endif
+}
 
 static WSets sel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
     WSets s;
@@ -135,7 +234,7 @@ static int hinit_conv0(const imvs_weights* w, const float* corr, float* t, int B
 
 using namespace imvs;
 
-extern "C" size_t imvs_corrnet_scratch_floats(int N, int H, int W) { return (size_t)N * 26 * H * W; }
+extern "C" size_t imvs_corrnet_scratch_floats(int N, int H, int W) { return (size_t)N * 48 * H * W; }
 
 extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int split1, int split2, const float* vol,
                             float* out, size_t out_batch_stride, size_t out_pixel_stride, float* scratch,
@@ -152,6 +251,33 @@ extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int sp
     float* x3 = c2 + (size_t)N * 2 * HW;    // [N][H/2][W/2][16]
     float* x4 = x3 + (size_t)N * 4 * HW;    // [N][H][W][8]
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
+#ifndef CUSIM
+    if (corrnet_tc5p_ready(sets)) {
+        // optional (IMVS_TUNE_TC5P_CORR=1): all six layers on the TMA + tcgen05 kernel; activations as fp16 hi / lo split planes, the inputs of the two
+        // stride-2 layers also as parity planes, the transposed layers with four parity accumulators (tc5pconv.cuh)
+        float* p = scratch;
+        auto take = [&](size_t floats) { float* q = p; p += floats; return q; };
+        const size_t n8 = (size_t)N * 8 * HW, n4 = (size_t)N * 4 * HW, n2 = (size_t)N * 2 * HW;
+        const tc5p::Split vs = tc5p::split_at(take(n8), n8), c0s = tc5p::split_at(take(n8), n8), c0p = tc5p::split_at(take(n8), n8),
+                          c1s = tc5p::split_at(take(n4), n4), c1p = tc5p::split_at(take(n4), n4), c2s = tc5p::split_at(take(n2), n2),
+                          x3s = tc5p::split_at(take(n4), n4), x4s = tc5p::split_at(take(n8), n8), none{nullptr, nullptr};
+        int* flag = tc5_error_flag();
+        auto ws = [&](int which) { return wsel_of(sets, period, split1, split2, which); };
+        IMVS_TRY(tc5p::launch_nhwc_to_split(vol, vs, (size_t)N * HW, (int)HW, 8, st));
+        IMVS_TRY((tc5p::launch<8, 16>("corrnet.conv0", vs, tc5p::Epi{c0s, nullptr, none, nullptr, H, W, 1, c0p, 1}, ws(0), N, H, W, flag, st)));
+        IMVS_TRY((tc5p::launch<8, 16, 1, true, 3, 2>("corrnet.conv1", c0p, tc5p::Epi{c1s, nullptr, none, nullptr, H1, W1, 1, c1p, 0}, ws(1), N, H1, W1, flag, st)));
+        IMVS_TRY((tc5p::launch<16, 32, 1, true, 3, 2>("corrnet.conv2", c1p, tc5p::Epi{c2s, nullptr, none, nullptr, H2, W2, 1}, ws(2), N, H2, W2, flag, st)));
+        IMVS_TRY((tc5p::launch<32, 16, 1, false, 3, 0>("corrnet.conv3", c2s, EpiTconvP{x3s, c1s, H2, W2, 2}, ws(3), N, H2, W2, flag, st)));
+        IMVS_TRY((tc5p::launch<16, 16, 1, false, 3, 0>("corrnet.conv4", x3s, EpiTconvP{x4s, c0s, H1, W1, 1}, ws(4), N, H1, W1, flag, st)));
+        EpiCorrOutP e5;
+        e5.out = out;
+        for (int i = 0; i < 3; ++i) e5.bias[i] = sets[i].conv5_b;
+        e5.period = period; e5.split1 = split1; e5.split2 = split2;
+        e5.bstride = out_batch_stride; e5.pstride = out_pixel_stride; e5.H = H; e5.W = W;
+        IMVS_TRY((tc5p::launch<8, 16>("corrnet.conv5", x4s, e5, ws(5), N, H, W, flag, st)));
+        return 0;
+    }
+#endif
     auto sel = [&](int which) { return sel_of(sets, period, split1, split2, which); };
     IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), EpiNHWC{c0, nullptr, nullptr, H, W, 8, 8, 1},
                                             sel(0), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));

@@ -417,6 +417,14 @@ __global__ void nhwc_to_split_kernel(const float* __restrict__ x, __half* __rest
     reinterpret_cast<uint4*>(lo)[i] = l;
 }
 
+int launch_nhwc_to_split(const float* x, const Split& dst, size_t npix_total, int HW, int C, cudaStream_t st) {
+    IMVS_REQUIRE(x && dst.hi && dst.lo && C % 8 == 0, "nhwc_to_split: bad argument");
+    const size_t n = npix_total * (C / 8);
+    IMVS_REQUIRE(n < 4294967296ull * 256, "nhwc_to_split: too many pixels");
+    IMVS_CUDA(launch_k(nhwc_to_split_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, dst.hi, dst.lo, npix_total, HW, C));
+    return 0;
+}
+
 __global__ void split_to_nhwc_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ x, size_t npix_total,
                                      int HW, int C) {
     pdl_trigger();

@@ -37,7 +37,7 @@ static Workspace carve(const imvs_problem& pb, float* base) {
     w.vw3 = at(B * S * P3);
     w.vw2 = at(B * S * P2);
     w.agg_init = at(B * D * P3 * 8);
-    size_t cn = B * D * P3 * 26, ci = B * IMVS_ITER_SLICES * P2 * 26;
+    size_t cn = B * D * P3 * 48, ci = B * IMVS_ITER_SLICES * P2 * 48;     // = imvs_corrnet_scratch_floats
     w.corrnet_scratch = at(cn > ci ? cn : ci);
     w.corr0 = at(B * D * P3);
     w.hinit_scratch = at(B * 96 * P3);

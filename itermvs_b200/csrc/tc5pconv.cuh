@@ -53,9 +53,9 @@ constexpr int WT = 32;                 // slots per tile row
 // CTA: warp 0 producer, warp 1 MMA issuer, then 4 * MB * CS epilogue warps: a warp reads the TMEM lanes 32 * (warp % 4) ..,
 // its group index selects the M-block and one of CS channel slices (the epilogue, not the tensor core, was the pipeline's
 // slowest stage with 8 warps: ncu r2c17 -- the MMA warp spinning on the accumulator-empty barrier)
-template <int NB, int MB> struct Shape {
-    static constexpr int CS = MB == 2 ? 2 : (NB % 32 == 0 ? 4 : (NB == 48 ? 3 : 2));      // channel slices per M-block
-    static constexpr int NCH = NB / CS;                                                  // channels per epilogue thread (8 or 16)
+template <int NB, int MB, bool TC = false> struct Shape {     // TC: transposed convolution -- the four slices are the output parities
+    static constexpr int CS = TC ? 4 : (MB == 2 ? 2 : (NB % 32 == 0 ? 4 : (NB == 48 ? 3 : 2)));      // slices per M-block
+    static constexpr int NCH = TC ? NB : NB / CS;                                        // channels per epilogue thread (8 or 16)
     static constexpr int EPI_WARPS = 4 * MB * CS;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static_assert(NCH % 8 == 0, "epilogue channel slice");
@@ -88,6 +88,19 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// weights of a launch: one packed set (_pack.py:pack_umma_f16i) or three, chosen per image n as the mma.sync engine's
+// MmaWeightSel does (CorrNet batches the slices of three pyramid levels, each with its own network)
+struct WSel {
+    const void* w[3];
+    int nsets, period, split1, split2;
+    __host__ __device__ int pick(int n) const {
+        if (nsets == 1) return 0;
+        const int r = n % period;
+        return r < split1 ? 0 : (r < split2 ? 1 : 2);
+    }
+};
+inline WSel wsel_single(const void* w) { return WSel{{w, w, w}, 1, 1, 1, 1}; }
+
 struct Geo {
     int tiles_x, tiles_y, n_tiles;
     int THo;             // output rows per tile = 4 * MB
@@ -116,6 +129,7 @@ struct Epi {
     const float* bias;       // [NB] or nullptr
     int H, W, relu;
     Split outp = {nullptr, nullptr};     // the same values as parity planes (operand of a following stride-2 layer) or null
+    int kco = 0;             // 8-channel chunks of the output / residual tensors when fewer than NB / 8 (cout padded to 16); 0: NB / 8
 
     template <int NCH> struct Pre { uint4 h[NCH / 8], l[NCH / 8]; };
 
@@ -123,9 +137,11 @@ struct Epi {
     __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NCH>& p) const {
         if (!res.hi) return;
         const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        const int KCo = kco ? kco : NB / 8;
 #pragma unroll
         for (int j = 0; j < NCH / 8; ++j) {
-            const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
+            if (c0 / 8 + j >= KCo) break;
+            const size_t idx = ((size_t)n * KCo + (c0 / 8 + j)) * plane + pix;
             p.h[j] = __ldg(reinterpret_cast<const uint4*>(res.hi) + idx);
             p.l[j] = __ldg(reinterpret_cast<const uint4*>(res.lo) + idx);
         }
@@ -134,9 +150,11 @@ struct Epi {
     template <int NB, int NCH>
     __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>& p, int* status) const {
         const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        const int KCo = kco ? kco : NB / 8;
         float amax = 0.f;
 #pragma unroll
         for (int j = 0; j < NCH / 8; ++j) {
+            if (c0 / 8 + j >= KCo) break;                // padded output channels
             float* x = v + 8 * j;
             if (bias) {
                 const float4 b0 = ldg4(bias + c0 + 8 * j), b1 = ldg4(bias + c0 + 8 * j + 4);
@@ -164,21 +182,22 @@ struct Epi {
                 split_f16(make_float2(x[4], x[5]), h.z, l.z);
                 split_f16(make_float2(x[6], x[7]), h.w, l.w);
                 if (out.hi) {
-                    const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
+                    const size_t idx = ((size_t)n * KCo + (c0 / 8 + j)) * plane + pix;
                     reinterpret_cast<uint4*>(out.hi)[idx] = h;
                     reinterpret_cast<uint4*>(out.lo)[idx] = l;
                 }
                 if (outp.hi) {
-                    const size_t idx = parity_index(n, oy, ox, c0 / 8 + j, NB / 8, H, W);
+                    const size_t idx = parity_index(n, oy, ox, c0 / 8 + j, KCo, H, W);
                     reinterpret_cast<uint4*>(outp.hi)[idx] = h;
                     reinterpret_cast<uint4*>(outp.lo)[idx] = l;
                 }
             }
         }
         if (out32) {
-            float* o = out32 + ((size_t)n * plane + pix) * NB + c0;
+            float* o = out32 + ((size_t)n * plane + pix) * (8 * KCo) + c0;
 #pragma unroll
-            for (int c = 0; c < NCH; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            for (int c = 0; c < NCH; c += 4)
+                if (c0 + c < 8 * KCo) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
         }
         // a value beyond +-65504 saturates in the split above / in the next layer's split: raise the flag (imvs_device_status bit 1)
         if (!(amax <= 65504.f) && status) atomicOr(status, 2);
@@ -242,20 +261,26 @@ __device__ __forceinline__ uint32_t elect_one() {       // one lane of the (conv
 // holds the four parity sub-tiles (4 MB + 1 rows x 32 slots each, the odd ones starting one row / column earlier): eight TMA
 // loads per tile, 31 valid output columns per 32.  CINP = 8 (one K chunk): the MMA's second K chunk aliases the first
 // (descriptor LBO = 0) against zero weights.
+// STRIDE = 0: ConvTranspose2d(k = 3, stride 2, padding 1, output_padding 1).  The tile lives on the INPUT grid (one extra row /
+// column below / right); output parity (a, b) of input pixel (iy, ix) -> output (2 iy + a, 2 ix + b) is a stride-1 stencil over
+// the input with 1, 2, 2 or 4 taps (mmaconv.cuh:tconv_tables): four accumulators per M-block, one per parity, nine tap MMAs in
+// total as for a 3x3; the epilogue's four warp groups are the four parities (Epi::store gets c0 = parity * NB).
 template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
-__global__ void __launch_bounds__((Shape<NB, MB>::THREADS), 1)
+__global__ void __launch_bounds__((Shape<NB, MB, STRIDE == 0>::THREADS), 1)
 tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
-                 const void* __restrict__ w_f16, const Geo geo, int* err_flag) {
+                 const WSel wsel, const Geo geo, int* err_flag) {
     static_assert((CINP % 16 == 0 || CINP == 8) && NB % 16 == 0 && NB <= 64, "UMMA kind::f16 shape");
     static_assert(MB == 1 || (MB == 2 && NB <= 32), "M-blocks per tile (TMEM: 2 sets x MB x 2*NB columns <= 256)");
     static_assert(KS == 1 || KS == 3, "1x1 or 3x3");
-    static_assert(STRIDE == 1 || (STRIDE == 2 && KS == 3 && DIL == 1), "stride 2: 3x3, no dilation");
+    static_assert(STRIDE == 1 || ((STRIDE == 2 || STRIDE == 0) && KS == 3 && DIL == 1), "stride 2 / transposed: 3x3, no dilation");
+    constexpr bool TCONV = STRIDE == 0;
+    static_assert(!TCONV || (MB == 1 && NB == 16), "transposed: four parity accumulators of 2 * NB columns, two sets, in 256 TMEM columns");
     constexpr int KC = CINP / 8, KCW = (CINP + 15) / 16 * 2, KSTEPS = (CINP + 15) / 16, TAPS = KS * KS;
-    constexpr int PAD = STRIDE == 2 ? 0 : DIL * (KS - 1) / 2;                         // halo columns lost per tile side
-    constexpr int VALID = STRIDE == 2 ? WT - 1 : WT - 2 * PAD;                        // valid output columns per tile
-    constexpr int ROWS = STRIDE == 2 ? 4 * MB + 1 : 4 * MB + 2 * PAD;                 // rows of one (sub-)tile
+    constexpr int PAD = STRIDE != 1 ? 0 : DIL * (KS - 1) / 2;                         // halo columns lost per tile side
+    constexpr int VALID = STRIDE != 1 ? WT - 1 : WT - 2 * PAD;                        // valid output columns per tile
+    constexpr int ROWS = STRIDE != 1 ? 4 * MB + 1 : 4 * MB + 2 * PAD;                 // rows of one (sub-)tile
     constexpr int NSUB = STRIDE == 2 ? 4 : 1, SUBSLOT = ROWS * WT, NSLOT = NSUB * SUBSLOT;
-    constexpr int NBS = 2 * NB;                                  // TMEM columns per M-block: [hi*hi + lo*hi | hi*lo]
+    constexpr int NBS = TCONV ? 8 * NB : 2 * NB;                 // TMEM columns per M-block: [hi*hi + lo*hi | hi*lo] (x 4 parities)
     constexpr int ACC_COLS = MB * NBS;                           // one accumulator set
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
     static_assert(2 * ACC_COLS <= 256, "TMEM budget");
@@ -263,13 +288,14 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     constexpr uint32_t A_BYTES = NSUB * SUB_BYTES;               // one plane of one stage
     constexpr uint32_t B_TAP_BYTES = KCW * 2 * NB * 16;          // hi and lo of one tap
     constexpr uint32_t LBO_A = CINP == 8 ? 0u : SUBSLOT * 16u, LBO_B = 2 * NB * 16;
-    constexpr int CS = Shape<NB, MB>::CS, NCH = Shape<NB, MB>::NCH, THREADS = Shape<NB, MB>::THREADS;
+    using Sh = Shape<NB, MB, TCONV>;
+    constexpr int CS = Sh::CS, NCH = Sh::NCH, THREADS = Sh::THREADS;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
     const int nst = geo.nstages;
     unsigned char* sA = smem_raw;                                               // [nst][hi | lo][KC][NSLOT][16 B]
     unsigned char* sB = sA + (size_t)nst * 2 * A_BYTES;                         // [tap][KC][hi NB | lo NB][16 B]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + TAPS * B_TAP_BYTES);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + (size_t)wsel.nsets * TAPS * B_TAP_BYTES);   // [set][tap][...]
     // barriers: [0, S) full, [S, 2S) empty, 2S + {0,1} accumulator full, 2S + {2,3} accumulator empty, 2S + 4 weights
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2 * MAX_STAGES + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -288,9 +314,11 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         fence_mbar_init();
         // weights are constants of the forward pass: requested before the grid-dependency wait; global order = shared
         // order [tap][KC][hi | lo][NB][8] (_pack.py:pack_umma_f16i), one bulk copy per tap
-        mbar_expect_tx(bar_w, TAPS * B_TAP_BYTES);
-        for (int tap = 0; tap < TAPS; ++tap)
-            bulk_g2s(smem_u32(sB) + tap * B_TAP_BYTES, static_cast<const unsigned char*>(w_f16) + (size_t)tap * B_TAP_BYTES, B_TAP_BYTES, bar_w);
+        mbar_expect_tx(bar_w, (uint32_t)wsel.nsets * TAPS * B_TAP_BYTES);
+        for (int set = 0; set < wsel.nsets; ++set)
+            for (int tap = 0; tap < TAPS; ++tap)
+                bulk_g2s(smem_u32(sB) + (set * TAPS + tap) * B_TAP_BYTES,
+                         static_cast<const unsigned char*>(wsel.w[set]) + (size_t)tap * B_TAP_BYTES, B_TAP_BYTES, bar_w);
     }
     pdl_trigger();
     fence_before_sync();
@@ -318,7 +346,7 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             if (elect_one()) {
                 mbar_expect_tx(bar_full(s), 2 * A_BYTES);
                 const uint32_t dst = smem_u32(sA) + (uint32_t)s * 2 * A_BYTES;
-                if constexpr (STRIDE == 1) {
+                if constexpr (STRIDE != 2) {
                     tma_load_4d(dst, &map_hi, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
                     tma_load_4d(dst + A_BYTES, &map_lo, bar_full(s), (ox0 - PAD) * 8, oy0 - PAD, 0, n);
                 } else {
@@ -344,29 +372,56 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             ok = mbar_wait_bounded(bar_full(s), ph) && mbar_wait_bounded(bar_tempty(acc), aph ^ 1);
             if (!ok) break;
             fence_after_sync();
+            int nimg, oy0_, ox0_;
+            decode(tile, nimg, oy0_, ox0_);
+            const uint32_t set16 = (uint32_t)wsel.pick(nimg) * (TAPS * (B_TAP_BYTES >> 4));      // this image's weight set
             if (elect_one()) {
                 const uint64_t da_hi = dconst_a | (uint64_t)(((smem_u32(sA) + (uint32_t)s * 2 * A_BYTES) & 0x3FFFFu) >> 4);
                 const uint64_t da_lo = da_hi + (A_BYTES >> 4);
                 const uint32_t dcol = tmem_d + (uint32_t)(acc * ACC_COLS);
+                constexpr uint32_t KA = (2u * LBO_A) >> 4, KB = (2u * LBO_B) >> 4;     // k-step advance (two K chunks), 16-byte units
+                if constexpr (!TCONV) {
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
-                    for (int k16 = 0; k16 < KSTEPS; ++k16) {
-                        // slots == 16-byte units: tap shift + k-step advance (two K chunks per MMA)
-                        constexpr uint32_t KA = (2u * LBO_A) >> 4, KB = (2u * LBO_B) >> 4;
-                        constexpr uint32_t SUB16 = SUB_BYTES >> 4;
-                        const int ky = tap / KS, kx = tap % KS;
-                        const uint32_t tapoff = STRIDE == 1 ? (uint32_t)(ky * DIL * WT + kx * DIL)
-                                                            : (uint32_t)(2 * (ky != 1) + (kx != 1)) * SUB16 + (uint32_t)((ky == 2) * WT + (kx == 2));
-                        const uint32_t shift = tapoff + (uint32_t)k16 * KA;
-                        const uint64_t db = db0 + (uint64_t)(tap * (B_TAP_BYTES >> 4) + k16 * KB);
-                        const uint32_t accum = (tap | k16) != 0;
+                        for (int k16 = 0; k16 < KSTEPS; ++k16) {
+                            // slots == 16-byte units: tap shift + k-step advance
+                            constexpr uint32_t SUB16 = SUB_BYTES >> 4;
+                            const int ky = tap / KS, kx = tap % KS;
+                            const uint32_t tapoff = STRIDE == 1 ? (uint32_t)(ky * DIL * WT + kx * DIL)
+                                                                : (uint32_t)(2 * (ky != 1) + (kx != 1)) * SUB16 + (uint32_t)((ky == 2) * WT + (kx == 2));
+                            const uint32_t shift = tapoff + (uint32_t)k16 * KA;
+                            const uint64_t db = db0 + (uint64_t)(set16 + tap * (B_TAP_BYTES >> 4) + k16 * KB);
+                            const uint32_t accum = (tap | k16) != 0;
 #pragma unroll
-                        for (int mb = 0; mb < MB; ++mb)          // A_hi x [B_hi | B_lo]
-                            umma_f16k(dcol + mb * NBS, da_hi + (shift + mb * 128), db, idesc2, accum);
+                            for (int mb = 0; mb < MB; ++mb)          // A_hi x [B_hi | B_lo]
+                                umma_f16k(dcol + mb * NBS, da_hi + (shift + mb * 128), db, idesc2, accum);
 #pragma unroll
-                        for (int mb = 0; mb < MB; ++mb)          // A_lo x B_hi
-                            umma_f16k(dcol + mb * NBS, da_lo + (shift + mb * 128), db, idesc1, 1u);
+                            for (int mb = 0; mb < MB; ++mb)          // A_lo x B_hi
+                                umma_f16k(dcol + mb * NBS, da_lo + (shift + mb * 128), db, idesc1, 1u);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int par = 0; par < 4; ++par) {              // output parity (a, b) = (par >> 1, par & 1)
+                        const int a = par >> 1, b = par & 1;
+#pragma unroll
+                        for (int i = 0; i <= a; ++i) {               // a = 0: ky = 1 (dy 0);  a = 1: ky = 0 (dy +1), ky = 2 (dy 0)
+#pragma unroll
+                            for (int j = 0; j <= b; ++j) {
+                                const int ky = a == 0 ? 1 : (i == 0 ? 0 : 2), dy = (a == 1 && i == 0) ? 1 : 0;
+                                const int kx = b == 0 ? 1 : (j == 0 ? 0 : 2), dx = (b == 1 && j == 0) ? 1 : 0;
+                                const int tap = ky * 3 + kx;
+#pragma unroll
+                                for (int k16 = 0; k16 < KSTEPS; ++k16) {
+                                    const uint32_t shift = (uint32_t)(dy * WT + dx) + (uint32_t)k16 * KA;
+                                    const uint64_t db = db0 + (uint64_t)(set16 + tap * (B_TAP_BYTES >> 4) + k16 * KB);
+                                    const uint32_t accum = (i | j | k16) != 0;
+                                    umma_f16k(dcol + par * 2 * NB, da_hi + shift, db, idesc2, accum);
+                                    umma_f16k(dcol + par * 2 * NB, da_lo + shift, db, idesc1, 1u);
+                                }
+                            }
+                        }
                     }
                 }
                 umma_commit(bar_empty(s));          // the stage may be refilled once these MMAs have read it
@@ -378,7 +433,8 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     } else {
         // ---- epilogue -------------------------------------------------------------------------------------------
         const int ew = warp - 2, lg = warp & 3, grp = ew >> 2;       // TMEM lanes 32 * (warp % 4) ..; grp: (M-block, channel slice)
-        const int mb = grp / CS, c0 = (grp % CS) * NCH;
+        const int mb = grp / CS, c0 = (grp % CS) * NCH;               // transposed: c0 = parity * NB
+        const int col0 = TCONV ? (grp % CS) * 2 * NB : c0;            // the slice's first accumulator column inside its M-block
         const int slot = mb * 128 + lg * 32 + lane, r = slot >> 5, c = slot & 31;
         auto pixel = [&](int tile, int& n, int& oy, int& ox) {
             int oy0, ox0;
@@ -407,7 +463,7 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             if (!mbar_wait_bounded(bar_tfull(acc), aph)) { if (lane == 0 && err_flag) atomicOr(err_flag, 1); break; }
             fence_after_sync();
             float v[NCH], u[NCH];
-            const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_COLS + mb * NBS + c0);
+            const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_COLS + mb * NBS + col0);
 #pragma unroll
             for (int j = 0; j < NCH / 8; ++j) {
                 tmem_ld8_nowait(taddr + 8 * j, v + 8 * j);
@@ -453,17 +509,17 @@ inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, 
 
 // H, W: OUTPUT size (= input size for STRIDE 1; the input of a STRIDE 2 layer is 2H x 2W, stored as parity planes)
 template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
-int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
-    constexpr int KC = CINP / 8, KCW = (CINP + 15) / 16 * 2, PAD = STRIDE == 2 ? 0 : DIL * (KS - 1) / 2;
+int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wsel, int N, int H, int W, int* err_flag, cudaStream_t st) {
+    constexpr int KC = CINP / 8, KCW = (CINP + 15) / 16 * 2, PAD = STRIDE != 1 ? 0 : DIL * (KS - 1) / 2;
     Geo g{};
     g.ks = KS; g.dil = DIL; g.pad = PAD;
-    g.valid = STRIDE == 2 ? WT - 1 : WT - 2 * PAD;
+    g.valid = STRIDE != 1 ? WT - 1 : WT - 2 * PAD;
     g.THo = 4 * MB;
-    g.rows = STRIDE == 2 ? g.THo + 1 : g.THo + 2 * PAD;
+    g.rows = STRIDE != 1 ? g.THo + 1 : g.THo + 2 * PAD;
     g.tiles_x = cdiv(W, g.valid); g.tiles_y = cdiv(H, g.THo);
     g.n_tiles = g.tiles_x * g.tiles_y * N;
     g.a_bytes = (uint32_t)(STRIDE == 2 ? 4 : 1) * KC * g.rows * WT * 16;
-    const size_t fixed = (size_t)KS * KS * 2 * KCW * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
+    const size_t fixed = (size_t)wsel.nsets * KS * KS * 2 * KCW * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
     const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
     const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, sm_count()));
@@ -477,7 +533,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     const int grid = std::min(g.n_tiles, sm_count());
-    if (launch_k(kern, dim3(grid), dim3(Shape<NB, MB>::THREADS), smem, st, mh, ml, epi, w_f16, g, err_flag) != cudaSuccess)
+    if (launch_k(kern, dim3(grid), dim3(Shape<NB, MB, STRIDE == 0>::THREADS), smem, st, mh, ml, epi, wsel, g, err_flag) != cudaSuccess)
         return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
@@ -485,17 +541,25 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const void* w_f
 // stride-1 KS x KS (3x3 with dilation DIL, or 1x1) convolution CINP -> NB of a split-plane tensor; the epilogue class decides
 // what happens to the accumulators (Epi: bias / residual / ReLU; featurenet.cu:EpiLateral; update.cu: the GRU gates)
 template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, int KS = 3, int STRIDE = 1, class Epi>
-int launch(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
-    IMVS_REQUIRE(w_f16 && in.hi && in.lo, "%s: null tcgen05 operand", name);
-    IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 * STRIDE * STRIDE < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
-    if constexpr (NB <= 32 && ALLOW_MB2) {
+int launch(const char* name, const Split& in, const Epi& epi, const WSel& wsel, int N, int H, int W, int* err_flag, cudaStream_t st) {
+    IMVS_REQUIRE(in.hi && in.lo, "%s: null tcgen05 operand", name);
+    for (int i = 0; i < wsel.nsets; ++i) IMVS_REQUIRE(wsel.w[i], "%s: null tcgen05 weights", name);
+    IMVS_REQUIRE((double)N * (CINP / 8) * H * W * 16 * (STRIDE == 2 ? 4 : 1) < 1.8e19 && W >= 1 && H >= 1, "%s: bad shape", name);
+    if constexpr (NB <= 32 && ALLOW_MB2 && STRIDE != 0) {
         const int tiles2 = cdiv(W, STRIDE == 2 ? WT - 1 : WT - DIL * (KS - 1)) * cdiv(H, 8) * N;
         const int force = tune("TC5P_MB", 0);
         // 8-row tiles (two M-blocks share one haloed tile: 1.25x instead of 1.5x halo rows) when they still fill the machine
-        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, KS, STRIDE, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
+        if (force == 2 || (force == 0 && tiles2 >= 2 * sm_count())) return launch_mb<CINP, NB, 2, DIL, KS, STRIDE, Epi>(name, in, epi, wsel, N, H, W, err_flag, st);
     }
-    return launch_mb<CINP, NB, 1, DIL, KS, STRIDE, Epi>(name, in, epi, w_f16, N, H, W, err_flag, st);
+    return launch_mb<CINP, NB, 1, DIL, KS, STRIDE, Epi>(name, in, epi, wsel, N, H, W, err_flag, st);
 }
+template <int CINP, int NB, int DIL = 1, bool ALLOW_MB2 = true, int KS = 3, int STRIDE = 1, class Epi>
+int launch(const char* name, const Split& in, const Epi& epi, const void* w_f16, int N, int H, int W, int* err_flag, cudaStream_t st) {
+    return launch<CINP, NB, DIL, ALLOW_MB2, KS, STRIDE, Epi>(name, in, epi, wsel_single(w_f16), N, H, W, err_flag, st);
+}
+
+// fp32 NHWC [N][H][W][C] -> split planes (featurenet.cu); C a multiple of 8
+int launch_nhwc_to_split(const float* x, const Split& dst, size_t npix_total, int HW, int C, cudaStream_t st);
 
 }  // namespace tc5p
 

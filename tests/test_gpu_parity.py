@@ -788,3 +788,37 @@ def test_conv3x3_tma_tcgen05_vs_fp64(dev, cin, cout, dil, shape):
         print(f"tc5p {cin}->{cout} dil {dil} {shape} res={use_res} split_out={via_split}: max err {err:.2e} (scale {scale:.2f})")
         assert torch.isfinite(out).all()
         assert err < 5e-6 * max(scale, 1.0), err
+
+
+def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch):
+    """CorrNet with all six layers on the persistent TMA + tcgen05 kernel (IMVS_TUNE_TC5P_CORR=1; off by default because it is
+    slower for these small maps): 8-channel layers through an aliased K chunk, the two stride-2 layers on parity planes, the two
+    transposed layers with four parity accumulators, three weight sets chosen per slice -- against the reference's KAT and,
+    in the three-set batched form the iterations use, against the default mma.sync path."""
+    from itermvs_b200 import _lib
+    k = stage_kats
+    ev = model.iter_mvs.evaluation
+    x = T(k["corrnet_in"]).to(dev)
+    monkeypatch.setenv("IMVS_TUNE_TC5P_CORR", "1")
+    got = ev.corr_conv1[0](x)
+    torch.cuda.synchronize()
+    assert _lib.device_status(clear=True) == 0
+    monkeypatch.setenv("IMVS_TUNE_TC5P_CORR", "0")
+    ref = ev.corr_conv1[0](x)
+    print("corrnet tcgen05 vs KAT", maxerr(got, T(k["corrnet0_out"])), "vs mma.sync", maxerr(got, ref))
+    assert maxerr(got, T(k["corrnet0_out"])) < 2e-5
+    assert maxerr(got, ref) < 2e-5
+    # the batched three-set form (10 slices: 4 + 4 + 2) through the iteration branch of Evaluation
+    s = make_sample(320, 256, n_src=2, batch=1, seed=7, scene="plane")
+    cu = lambda d: {kk: v.to(dev) for kk, v in d.items()}
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("IMVS_TUNE_TC5P_CORR", flag)
+        with torch.no_grad():
+            out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+        torch.cuda.synchronize()
+        outs.append(out["depths_upsampled"].clone())
+    assert _lib.device_status(clear=True) == 0
+    rel = ((outs[0] - outs[1]).abs() / outs[1]).max()
+    print("pipeline with CorrNet on tcgen05 vs default: max rel depth difference", float(rel))
+    assert float(rel) < 1e-4
