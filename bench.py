@@ -510,7 +510,7 @@ def main():
             b.record()
         barrier()
         e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
-    # ---- the same serving loop fed with the raw 8-bit images (f-4: the first FeatureNet layer normalises x / 255. as the
+    # ---- the same serving loop fed with the raw 8-bit images (f-4: the first FeatureNet layer normalises 2 x / 255. - 1 as the
     #      reference's loaders do): a quarter of the H2D bytes per step.  Extra line, the contract's `e2e` stays fp32 images.
     e2e_u8 = None
     if sp is not None and not args.no_u8:
@@ -649,8 +649,8 @@ def main():
     if e2e_u8 is not None:
         line["e2e_uint8_images"] = {"value": e2e_u8["value"], "unit": "refs/s", "h2d_bytes_per_step": e2e_u8["h2d_bytes_per_step"],
                                     "d2h_bytes_per_step": d2h,
-                                    "what": "the e2e loop fed with raw 8-bit images from pinned host memory; x / 255. (the loaders' normalisation, "
-                                            "dtu_yao_eval.py:56-59) happens in the first FeatureNet kernel"}
+                                    "what": "the e2e loop fed with raw 8-bit images from pinned host memory; 2 x / 255. - 1 (the loaders' normalisation, "
+                                            "dtu_yao_eval.py:63-64) happens in the first FeatureNet kernel"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if gpu_stock is not None:

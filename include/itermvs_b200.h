@@ -326,10 +326,17 @@ size_t imvs_featurenet_workspace_bytes(int N, int H, int W);
 int imvs_featurenet_forward(const imvs_featurenet_weights* w, const float* imgs, float* fea1, float* fea2, float* fea3,
                             void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream);
 /* Same with the raw 8-bit images [N][3][H][W]: the first layer normalises them as the reference's loaders do
- * (np.array(img, dtype=np.float32) / 255., datasets/dtu_yao_eval.py:56-59) -- f-4: a quarter of the host-to-device bytes. */
+ * (2 * np.array(img, dtype=np.float32) / 255. - 1, datasets/dtu_yao_eval.py:63-64) -- f-4: a quarter of the host-to-device bytes. */
 int imvs_featurenet_forward_u8(const imvs_featurenet_weights* w, const unsigned char* imgs, float* fea1, float* fea2, float* fea3,
                                void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream);
 int imvs_featurenet_launch_count(void);
+
+/* f-4, datasets/dtu_yao_eval.py:61-76 (`read_img`) after the image decode, on the device: raw 8-bit image [H0][W0][3] ->
+ * level0 [3][H][W] = cv2.resize(2 * img / 255. - 1, (W, H), INTER_LINEAR) and, where non-NULL, level k = cv2.resize(level0,
+ * (W >> k, H >> k), INTER_LINEAR), k = 1..3 (float32, planar: the loader's transpose([0, 3, 1, 2]) of one view).
+ * Agrees with OpenCV to 1 ulp of the interpolated value (its SIMD paths may fuse one product of the interpolation). */
+int imvs_image_pyramid_u8(const unsigned char* img, int H0, int W0, float* level0, float* level1, float* level2, float* level3,
+                          int H, int W, void* stream);
 
 /* Stride-1 3x3 convolution (dilation dil, zero padding dil) + bias (+ residual) (+ ReLU) on fp32 NHWC tensors through the
  * persistent TMA + tcgen05 kernel (csrc/tc5pconv.cuh) in the fp32-grade mode: operands as fp16 hi / lo "split planes"

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libitermvs_b200.so")
-SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "evalnets.cu", "update.cu", "upsample.cu", "forward.cu", "featurenet.cu", "fusion.cu"]
+SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "evalnets.cu", "update.cu", "upsample.cu", "forward.cu", "featurenet.cu", "fusion.cu", "imageprep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

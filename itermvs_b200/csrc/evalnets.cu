@@ -4,7 +4,9 @@
 //   activations channels-last.
 #include "common.cuh"
 #include "mmaconv.cuh"
+#ifndef CUSIM
 #include "tc5pconv.cuh"
+#endif
 
 namespace imvs {
 
@@ -24,6 +26,7 @@ struct EpiCorrOut {          // conv5 (1 valid cout): + bias, scatter to out[(n/
     }
 };
 
+#ifndef CUSIM     // (the CPU emulation of the test-suite has no TMA / tcgen05 model)
 // ---- CorrNet on the persistent TMA + tcgen05 kernel (tc5pconv.cuh) ------------------------------------------------------
 // transposed convolution + U-Net skip (itermvs.py:374-377): thread = (input pixel, output parity); H, W = INPUT grid
 struct EpiTconvP {
@@ -108,9 +111,6 @@ static tc5p::WSel wsel_of(const imvs_corrnet_weights* sets, int period, int spli
 }
 
 static bool corrnet_tc5p_ready(const imvs_corrnet_weights* sets) {
-#ifdef CUSIM
-    return false;
-#else
     // OFF by default: measured on B200 (gpurun call r2c22) the seven tcgen05 launches of a pass take 75 us against 66 us for the
     // six mma.sync launches -- every persistent launch has a ~7 us floor (TMEM allocation, barrier and weight staging, first
     // TMA round trip, drain) that these 160..960-tile layers cannot amortise.  IMVS_TUNE_TC5P_CORR=1 selects it (parity-tested).
@@ -119,8 +119,9 @@ static bool corrnet_tc5p_ready(const imvs_corrnet_weights* sets) {
         for (int k = 0; k < 6; ++k)
             if (!wsel_of(sets, 1, 1, 1, k).w[i]) return false;
     return true;
-#endif
 }
+
+#endif  // !CUSIM
 
 static WSets sel_of(const imvs_corrnet_weights* sets, int period, int split1, int split2, int which) {
     WSets s;

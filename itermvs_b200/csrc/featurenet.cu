@@ -6,7 +6,9 @@
 #include "common.cuh"
 #include "mmaconv.cuh"
 #include "tc5conv.cuh"
+#ifndef CUSIM
 #include "tc5pconv.cuh"
+#endif
 
 namespace imvs {
 
@@ -40,6 +42,7 @@ struct EpiAddUp2 {
     }
 };
 
+#ifndef CUSIM     // (the CPU emulation of the test-suite has no TMA / tcgen05 model)
 // EpiAddUp2 for the tcgen05 / TMA path: the sum is written as split planes [N][C/8][H][W][8 halves] (operand of the
 // output convolution, tc5pconv.cuh) and, when another lateral stage upsamples it, also as fp32 NHWC
 struct EpiAddUp2H {
@@ -133,6 +136,7 @@ struct EpiLateral {
     }
 };
 
+#endif  // !CUSIM
 // block-0 of a residual stage: conv1 (ReLU) and downsample (no ReLU) read the same input with the same
 // stride-2 stencil -> one implicit GEMM over the stacked output channels [conv1 | downsample]
 struct EpiSplit2 {
@@ -160,10 +164,11 @@ struct EpiSplit2 {
 // 128-thread block, the three image planes with halo in shared memory, each thread two vertically adjacent
 // pixels x 8 output channels (432 FFMA per 12 image + 54 broadcast weight LDS).
 // PixT = float: the image as the reference's loaders deliver it; PixT = unsigned char: the raw 8-bit image, normalised here
-// exactly as the loaders do (np.array(img, float32) / 255., datasets/dtu_yao_eval.py:56-59) -- a quarter of the H2D bytes.
+// exactly as the loaders do (2 * np.array(img, float32) / 255. - 1, datasets/dtu_yao_eval.py:63-64: float32 multiply, divide,
+// subtract in that order) -- a quarter of the H2D bytes.
 constexpr int C0_TW = 32, C0_TH = 8, C0_PITCH = C0_TW + 2;
 __device__ __forceinline__ float c0_pixel(const float* p) { return ldg(p); }
-__device__ __forceinline__ float c0_pixel(const unsigned char* p) { return (float)__ldg(p) / 255.0f; }
+__device__ __forceinline__ float c0_pixel(const unsigned char* p) { return __fsub_rn(__fdiv_rn(2.0f * (float)__ldg(p), 255.0f), 1.0f); }
 // PSPLIT: the output goes out as fp16 hi / lo PARITY PLANES [4N][1][H/2][W/2][8] (tc5pconv.cuh: operand of layer1's stride-2
 // GEMM on the TMA + tcgen05 kernel) instead of fp32 NHWC-8; `out` then points at the hi plane, the lo plane follows it.
 template <class PixT, bool PSPLIT = false>
@@ -217,6 +222,7 @@ fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, c
     }
     const int x = x0 + tx, y = y0 + 2 * ty;
     if (x >= W) return;
+#ifndef CUSIM     // (the CPU emulation of the test-suite has no TMA / tcgen05 model)
     if constexpr (PSPLIT) {
         uint4* ohi = reinterpret_cast<uint4*>(out);
         uint4* olo = ohi + (size_t)gridDim.z * H * W;            // 16-byte units: N * H * W pixels x one 8-channel chunk
@@ -235,6 +241,7 @@ fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, c
         }
         return;
     }
+#endif  // !CUSIM
     if (y < H) {
         float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H + y) * W + x) * 8);
         o[0] = make_float4(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f), fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f));
@@ -312,6 +319,7 @@ static int res_stage(const imvs_featurenet_weights* w, int L, const float* x, fl
     return 0;
 }
 
+#ifndef CUSIM     // (the CPU emulation of the test-suite has no TMA / tcgen05 model)
 // The same residual stage on the persistent TMA + tcgen05 kernel (tc5pconv.cuh): every activation between the stride-2
 // GEMM and the stage's last convolution lives as fp16 hi / lo split planes (written by the producers' epilogues, loaded
 // by TMA, never converted by a thread); the trunk output is fp32 NHWC for its fp32 consumers (next stride-2 GEMM, lateral
@@ -450,6 +458,7 @@ __global__ void split_to_nhwc_kernel(const __half* __restrict__ hi, const __half
 
 }  // namespace tc5p
 
+#endif  // !CUSIM
 }  // namespace imvs
 
 using namespace imvs;
@@ -475,17 +484,23 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8;
     const TapTables s1 = conv_tables(3, 1, 1, 8), k1 = conv_tables(1, 1, 1, 8);
     // conv1: 3 -> 8, BN, ReLU on the planar image (net.py:13)
+#ifndef CUSIM
     const bool p_ready = fnet_tc5p_ready(w);
     const bool lat = p_ready && tune("TC5P_LAT", 1) && w->w[17].f16ummai && w->w[19].f16ummai;
     // stride-2 GEMMs on the TMA + tcgen05 kernel too (then no layer of the default FeatureNet runs on mma.sync)
     const bool s2p = lat && tune("TC5P_S2", 1) && w->w[21].f16ummai && w->w[22].f16ummai && w->w[11].f16ummai && w->w[13].f16ummai;
+#else
+    const bool s2p = false;
+#endif
     if (imgs_u8 || tune("CONV0", 1)) {
         IMVS_REQUIRE(w->w[0].fp32 && w->b[0], "featurenet_forward: conv1 weights missing");
         dim3 grid(cdiv(W, C0_TW), cdiv(H, C0_TH), N);
         IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "fnet.conv1: grid too large");
         if (s2p) {      // output as fp16 hi / lo parity planes (same bytes, in a0)
+#ifndef CUSIM
             if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char, true>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
             else IMVS_CUDA(launch_k(fnet_conv0_kernel<float, true>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+#endif
         } else {
             if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
             else IMVS_CUDA(launch_k(fnet_conv0_kernel<float>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
@@ -494,6 +509,7 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
         IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("fnet.conv1", InNCHW3{imgs, H, W}, EpiNHWC{b.a0, w->b[0], nullptr, H, W, 8, 8, 1},
                                                 WSets::single(w->w[0]), s1, N, 8, H, W, 1, st)));
     }
+#ifndef CUSIM
     if (p_ready) {
         // default: residual stages and output convolutions on the persistent TMA + tcgen05 kernel, split-plane activations
         int* flag = tc5_error_flag();
@@ -523,6 +539,7 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
         IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16ummai, N, H1, W1, flag, st)));
         return 0;
     }
+#endif  // !CUSIM
     const int w8 = tune("FNETW", 0);     // 1: 8 warps x 1 row-tile per CTA instead of 4 x 2 (same tile, twice the resident warps)
     if (w8) IMVS_TRY((res_stage<8, 16, true, true, 32, 16, 1, 8>(w, 1, b.a0, b.l1, N, H, W, st)));
     else if (tune("FNET1", 0)) IMVS_TRY((res_stage<8, 16, true, true, 32, 16, 1, 4>(w, 1, b.a0, b.l1, N, H, W, st)));
@@ -599,6 +616,9 @@ extern "C" size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int 
 extern "C" int imvs_conv3x3_tcgen05(const float* x, const void* w_f16ummai, const float* bias, const float* residual, float* out,
                                     void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int dil, int relu,
                                     int via_split_output, void* stream) {
+#ifdef CUSIM
+    return fail("conv3x3_tcgen05: not available in the CPU emulation build");
+#else
     IMVS_REQUIRE(x && w_f16ummai && out && workspace, "conv3x3_tcgen05: null pointer");
     IMVS_REQUIRE(N >= 1 && H >= 1 && W >= 1 && dil >= 1 && dil <= 3, "conv3x3_tcgen05: bad shape");
     IMVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "conv3x3_tcgen05: workspace must be 256-byte aligned");
@@ -636,4 +656,5 @@ extern "C" int imvs_conv3x3_tcgen05(const float* x, const void* w_f16ummai, cons
                            (const __half*)outs.lo, out, px, H * W, Cout));
     }
     return 0;
+#endif
 }

@@ -5,7 +5,9 @@
 #include "common.cuh"
 #include "mmaconv.cuh"
 #include "tc5conv.cuh"
+#ifndef CUSIM
 #include "tc5pconv.cuh"
+#endif
 #include "headfused.cuh"
 
 namespace imvs {
@@ -60,6 +62,7 @@ struct EpiGruQ {
     }
 };
 
+#ifndef CUSIM     // (the CPU emulation of the test-suite has no TMA / tcgen05 model)
 // ---- the same two GEMMs on the persistent TMA + tcgen05 kernel (tc5pconv.cuh), the default in the fp32-grade mode -------
 // hx = [h (32) | x (16)] and rhx = [r*h (32) | x (16)] live as 48-channel split-plane tensors [B][6][H][W][8 halves]: one
 // conversion kernel writes h and x into hx and x into rhx, the z|r kernel's epilogue writes r*h into rhx.
@@ -162,6 +165,8 @@ struct EpiGruQp {            // q = tanh, h <- (1 - z) h + z q in place   (modul
         }
     }
 };
+
+#endif  // !CUSIM
 
 // ------------------------------------------------------------------------------------ heads ----
 // depth_head: 3x3 dilated conv (tensor cores) -> fc1 32->64 relu (1x1, tensor cores) -> fc2 64->256 + b

@@ -146,6 +146,103 @@ def load_views(datapath: str, scan: str, ref_view: int, src_views: Sequence[int]
             "filename": scan + "/{}/" + "{:0>8}".format(view_ids[0]) + "{}"}
 
 
+# ------------------------------------------------------------------ images on the device (f-4) --
+def image_pyramid_device(img_u8, img_wh: Sequence[int], levels: int = 4, stream=None):
+    """`read_img` (dtu_yao_eval.py:61-76) after the decode, on the GPU: `img_u8` is the raw 8-bit image as a CUDA uint8 tensor
+    [H0, W0, 3]; returns {'level_k': float32 CUDA tensor [3, H >> k, W >> k]} with level_0 = cv2.resize(2 * img / 255. - 1,
+    img_wh, INTER_LINEAR) and level_k = cv2.resize(level_0, (W >> k, H >> k), INTER_LINEAR) (C entry point
+    `imvs_image_pyramid_u8`, csrc/imageprep.cu).  There is no CPU path: a CPU tensor raises."""
+    import torch
+    from . import _lib
+    if not (isinstance(img_u8, torch.Tensor) and img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3):
+        raise RuntimeError("itermvs_b200.io.image_pyramid_device: expected a CUDA uint8 tensor [H0, W0, 3] (there is no CPU path)")
+    img_u8 = img_u8.contiguous()
+    w, h = int(img_wh[0]), int(img_wh[1])
+    out = {f"level_{k}": torch.empty(3, h >> k, w >> k, device=img_u8.device, dtype=torch.float32) for k in range(levels)}
+    ptr = lambda k: out[f"level_{k}"].data_ptr() if k < levels else None
+    st = stream if stream is not None else torch.cuda.current_stream(img_u8.device).cuda_stream
+    _lib.check(_lib.lib().imvs_image_pyramid_u8(img_u8.data_ptr(), img_u8.shape[0], img_u8.shape[1], ptr(0), ptr(1), ptr(2), ptr(3), h, w, st),
+               "image_pyramid_u8")
+    return out
+
+
+class PrefetchLoader:
+    """Serving-side replacement of the evaluation DataLoader (eval.py:45-50 / dtu_yao_eval.py `__getitem__`): a background
+    thread decodes the views of reference view i + 1 (PIL, host) into PINNED uint8 buffers and reads its cameras while
+    reference view i is on the GPU; `__next__` uploads the raw 8-bit images on a copy stream and runs normalisation, resize and
+    the pyramid there (`image_pyramid_device`), so the host never touches float images.  Yields the loader's sample dict with
+    CUDA tensors: imgs {'level_k': [1, V, 3, H_k, W_k]}, proj_matrices {'level_k': [1, V, 4, 4]}, depth_min / depth_max [1].
+
+    items: sequence of (image paths of the V views, camera-file paths of the V views), reference view first."""
+
+    def __init__(self, items, img_wh: Sequence[int], orig_wh: Sequence[int] = (1600, 1200), device="cuda", depth: int = 2):
+        import queue
+        import threading
+        import torch
+        self.items, self.img_wh, self.orig_wh = list(items), tuple(img_wh), tuple(orig_wh)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._q = queue.Queue(maxsize=depth)
+        self._pool = {}                 # (V, H0, W0) -> ring of pinned buffers, reused: no pinned allocation per sample
+        self._depth = depth
+        self._t = threading.Thread(target=self._work, daemon=True)
+        self._t.start()
+
+    def _pinned(self, slot: int, shape):
+        import torch
+        key = (slot,) + tuple(shape)
+        if key not in self._pool:
+            self._pool[key] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+        return self._pool[key]
+
+    def _work(self):
+        from PIL import Image
+        try:
+            for n, (img_paths, cam_paths) in enumerate(self.items):
+                raw = [np.array(Image.open(f).convert("RGB"), dtype=np.uint8) for f in img_paths]
+                h0, w0 = raw[0].shape[:2]
+                buf = self._pinned(n % (self._depth + 1), (len(raw), h0, w0, 3))
+                for v, r in enumerate(raw):
+                    if r.shape[:2] != (h0, w0):
+                        raise ValueError(f"view {v} of sample {n} has a different size")
+                    buf[v].numpy()[...] = r
+                proj = {f"level_{k}": [] for k in range(4)}
+                dmin = dmax = None
+                for v, f in enumerate(cam_paths):
+                    k_, e_, dmin_, dmax_ = read_cam_file(f)
+                    pp = projection_pyramid(k_, e_, self.img_wh, self.orig_wh)
+                    for lv in proj:
+                        proj[lv].append(pp[lv])
+                    if v == 0:
+                        dmin, dmax = dmin_, dmax_
+                self._q.put((buf, {lv: np.stack(p) for lv, p in proj.items()}, dmin, dmax))
+            self._q.put(None)
+        except BaseException as e:      # surfaced by __next__
+            self._q.put(e)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        import torch
+        item = self._q.get()
+        if item is None:
+            raise StopIteration
+        if isinstance(item, BaseException):
+            raise item
+        buf, proj, dmin, dmax = item
+        with torch.cuda.stream(self.copy_stream):
+            dev_u8 = buf.to(self.device, non_blocking=True)
+            per_view = [image_pyramid_device(dev_u8[v], self.img_wh, stream=self.copy_stream.cuda_stream) for v in range(dev_u8.shape[0])]
+            imgs = {lv: torch.stack([p[lv] for p in per_view]).unsqueeze(0) for lv in per_view[0]}
+            pm = {lv: torch.from_numpy(p).unsqueeze(0).to(self.device, non_blocking=True) for lv, p in proj.items()}
+            dm = torch.tensor([dmin], dtype=torch.float32).to(self.device, non_blocking=True)
+            dx = torch.tensor([dmax], dtype=torch.float32).to(self.device, non_blocking=True)
+        torch.cuda.current_stream(self.device).wait_stream(self.copy_stream)
+        dev_u8.record_stream(torch.cuda.current_stream(self.device))
+        return {"imgs": imgs, "proj_matrices": pm, "depth_min": dm, "depth_max": dx}
+
+
 # --------------------------------------------------------------------------------- point cloud --
 def backproject_points(depth_est_averaged: np.ndarray, final_mask: np.ndarray, ref_img: np.ndarray, ref_intrinsics: np.ndarray,
                        ref_extrinsics: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -80,7 +80,7 @@ class FeatureNet(nn.Module):
             raise NotImplementedError("itermvs_b200.FeatureNet.forward_nhwc is the inference kernel path (BatchNorm folded "
                                       "with running statistics); in train() mode use Pipeline.forward, which runs "
                                       "itermvs_b200/training.py (batch statistics, autograd)")
-        # uint8 = the raw 8-bit image: normalised on the device exactly as the reference's loaders do (x / 255., dtu_yao_eval.py:56-59)
+        # uint8 = the raw 8-bit image: normalised on the device exactly as the reference's loaders do (2 * x / 255. - 1, dtu_yao_eval.py:63-64)
         u8 = x.dtype == torch.uint8
         if u8:
             if not x.is_cuda:

@@ -24,7 +24,7 @@ CSRC = os.path.join(ROOT, "itermvs_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libitermvs_sim.so")
 SIM_SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "fusion.cu", "evalnets.cu", "update.cu", "upsample.cu", "forward.cu",
-               "featurenet.cu"]
+               "featurenet.cu", "imageprep.cu"]
 HEADERS = ["common.cuh", "sampling.cuh", "mmaconv.cuh", "tc5conv.cuh", "headfused.cuh"]
 def _isa_flags():
     """F16C / FMA when this CPU has them (hardware half<->float conversion for the tensor-core emulation)."""

@@ -389,3 +389,25 @@ def test_wavefront_model_tool_runs():
         assert m["requests"] > 0 and m["lines"] <= m["sectors"] <= 4 * m["lines"]
         assert m["wavefronts"] >= max(m["lines"], out[name]["delivered_floor_wavefronts"] - 1)
         assert "ncu" not in out[name]                     # the measured counters belong to the benchmark configuration only
+
+
+def test_image_pyramid_kernels_vs_cv2_on_cpu():
+    """f-4 on the device (csrc/imageprep.cu) executed through the CPU emulation: raw 8-bit image -> 2 x / 255 - 1 ->
+    cv2.resize(INTER_LINEAR) -> three coarser levels, against OpenCV itself (1 ulp: its SIMD paths may fuse one product)."""
+    cv2 = pytest.importorskip("cv2")
+    lib = C.CDLL(cusim_build.build())
+    vp, ci = C.c_void_p, C.c_int
+    lib.imvs_image_pyramid_u8.restype = ci
+    lib.imvs_image_pyramid_u8.argtypes = [vp, ci, ci, vp, vp, vp, vp, ci, ci, vp]
+    rng = np.random.default_rng(3)
+    for (h0, w0), (w, h) in (((60, 80), (64, 32)), ((48, 64), (64, 48)), ((33, 47), (96, 64))):
+        img = rng.integers(0, 256, size=(h0, w0, 3), dtype=np.uint8)
+        f = 2 * img.astype(np.float32) / 255. - 1
+        want0 = cv2.resize(f, (w, h), interpolation=cv2.INTER_LINEAR)
+        outs = [np.full((3, h >> k, w >> k), np.nan, np.float32) for k in range(4)]
+        rc = lib.imvs_image_pyramid_u8(img.ctypes.data, h0, w0, *[o.ctypes.data for o in outs], h, w, None)
+        assert rc == 0
+        assert np.abs(outs[0] - want0.transpose(2, 0, 1)).max() <= 2.5e-7, (h0, w0, w, h)
+        for k in (1, 2, 3):
+            wantk = cv2.resize(want0, (w >> k, h >> k), interpolation=cv2.INTER_LINEAR)
+            assert np.abs(outs[k] - wantk.transpose(2, 0, 1)).max() <= 5e-7, k

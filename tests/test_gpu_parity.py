@@ -429,11 +429,11 @@ def test_full_size_pipeline_vs_oracle(dev, model, dtu_weights):
 
 def test_uint8_images_equal_loader_normalisation(dev, model):
     """f-4: raw 8-bit images straight into the pipeline (a quarter of the H2D bytes); the first FeatureNet layer normalises
-    them as the reference's loaders do -- np.array(img, dtype=np.float32) / 255. (datasets/dtu_yao_eval.py:56-59) -- so
+    them as the reference's loaders do -- 2 * np.array(img, dtype=np.float32) / 255. - 1 (datasets/dtu_yao_eval.py:63-64) -- so
     the result is bit-identical to feeding that float image."""
     s = make_sample(320, 256, n_src=3, batch=1, seed=21, scene="plane")
     u8 = ((s["imgs"]["level_0"] + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
-    as_float = torch.from_numpy(u8.numpy().astype(np.float32) / 255.0)             # the loader's arithmetic, on the host
+    as_float = torch.from_numpy(2 * u8.numpy().astype(np.float32) / 255. - 1)       # the loader's arithmetic, on the host
     cu = lambda x: {k: v.to(dev) for k, v in x.items()}
     with torch.no_grad():
         a = model({"level_0": u8.to(dev)}, cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
@@ -821,4 +821,71 @@ def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch):
     assert _lib.device_status(clear=True) == 0
     rel = ((outs[0] - outs[1]).abs() / outs[1]).max()
     print("pipeline with CorrNet on tcgen05 vs default: max rel depth difference", float(rel))
+    assert float(rel) < 1e-4
+
+
+def test_image_pyramid_and_prefetch_loader_on_device(dev, model, tmp_path):
+    """f-4 on the GPU: (1) `imvs_image_pyramid_u8` -- raw 8-bit image -> 2 x / 255 - 1 -> cv2.resize(INTER_LINEAR) -> levels 1..3 --
+    against OpenCV (1 ulp of the value: its SIMD / IPP paths may fuse a product); (2) `io.PrefetchLoader`: PNG files decoded on
+    a background thread into pinned uint8 buffers, uploaded and prepared on a copy stream, yields the loader's sample dict on the
+    device; its level_0 equals the host loader's (`io.load_views` = the reference's `__getitem__`) to 1 ulp and the pipeline's
+    depth map from it equals the one from the host-loaded sample."""
+    cv2 = pytest.importorskip("cv2")
+    from PIL import Image
+    from itermvs_b200 import io as mio
+    rng = np.random.default_rng(11)
+    for (h0, w0), (w, h) in (((1200, 1600), (1152, 864)), ((300, 400), (320, 256)), ((256, 320), (320, 256))):
+        img = rng.integers(0, 256, size=(h0, w0, 3), dtype=np.uint8)
+        want0 = cv2.resize(2 * img.astype(np.float32) / 255. - 1, (w, h), interpolation=cv2.INTER_LINEAR)
+        got = mio.image_pyramid_device(torch.from_numpy(img).to(dev), (w, h))
+        torch.cuda.synchronize()
+        e0 = float(np.abs(got["level_0"].cpu().numpy() - want0.transpose(2, 0, 1)).max())
+        assert e0 <= 2.5e-7, e0
+        for k in (1, 2, 3):
+            wantk = cv2.resize(want0, (w >> k, h >> k), interpolation=cv2.INTER_LINEAR)
+            assert float(np.abs(got[f"level_{k}"].cpu().numpy() - wantk.transpose(2, 0, 1)).max()) <= 5e-7
+    with pytest.raises(RuntimeError):
+        mio.image_pyramid_device(torch.zeros(4, 4, 3, dtype=torch.uint8), (4, 4))
+    # a scan on disk in the loader's directory layout
+    s = make_sample(320, 256, n_src=2, batch=1, seed=13, scene="plane")
+    scan = tmp_path / "scan1"
+    (scan / "images").mkdir(parents=True)
+    (scan / "cams_1").mkdir()
+    u8 = ((s["imgs"]["level_0"][0] + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)          # [V, 3, H, W]
+    proj0 = s["proj_matrices"]["level_0"][0].double().numpy()
+    for v in range(3):
+        Image.fromarray(u8[v].permute(1, 2, 0).numpy()).save(str(scan / "images" / f"{v:08d}.png"))
+        # cam file: extrinsics = identity-free form is not recoverable from a projection; store K = P[:3,:3], E = [I | K^-1 t]
+        K = proj0[v][:3, :3]
+        E = np.eye(4)
+        E[:3, 3] = np.linalg.solve(K, proj0[v][:3, 3])
+        with open(scan / "cams_1" / f"{v:08d}_cam.txt", "w") as f:
+            f.write("extrinsic\n" + "\n".join(" ".join(f"{x:.9g}" for x in row) for row in E) + "\n\nintrinsic\n" +
+                    "\n".join(" ".join(f"{x:.9g}" for x in row) for row in K) + f"\n\n{float(s['depth_min'][0])} 1.0 192 {float(s['depth_max'][0])}\n")
+    items = [([str(scan / "images" / f"{v:08d}.png") for v in order], [str(scan / "cams_1" / f"{v:08d}_cam.txt") for v in order])
+             for order in ((0, 1, 2), (1, 0, 2), (2, 0, 1))]
+    outs = []
+    with torch.no_grad():
+        for sample in mio.PrefetchLoader(items, img_wh=(320, 256), orig_wh=(320, 256), device=dev):
+            assert sample["imgs"]["level_0"].shape == (1, 3, 3, 256, 320) and sample["imgs"]["level_3"].shape == (1, 3, 3, 32, 40)
+            out = model(sample["imgs"], sample["proj_matrices"], sample["depth_min"], sample["depth_max"])
+            outs.append((sample, out["depths_upsampled"].clone()))
+    assert len(outs) == 3
+    # the host loader on the same files (jpg in the reference; the decode is not what is under test)
+    def host_sample(order):
+        imgs, proj = [], []
+        for v in order:
+            k_, e_, dmin, dmax = mio.read_cam_file(str(scan / "cams_1" / f"{v:08d}_cam.txt"))
+            imgs.append(2 * np.array(Image.open(str(scan / "images" / f"{v:08d}.png")), dtype=np.float32) / 255. - 1)
+            proj.append(mio.projection_pyramid(k_, e_, (320, 256), (320, 256)))
+        return np.stack(imgs).transpose(0, 3, 1, 2), {lv: np.stack([p[lv] for p in proj]) for lv in proj[0]}
+    himg, hproj = host_sample((0, 1, 2))
+    assert float((outs[0][0]["imgs"]["level_0"][0].cpu() - torch.from_numpy(himg)).abs().max()) <= 2.5e-7
+    for lv in hproj:
+        assert torch.equal(outs[0][0]["proj_matrices"][lv][0].cpu(), torch.from_numpy(hproj[lv]))
+    with torch.no_grad():
+        ref = model({"level_0": torch.from_numpy(himg)[None].to(dev)}, {lv: torch.from_numpy(p)[None].to(dev) for lv, p in hproj.items()},
+                    outs[0][0]["depth_min"], outs[0][0]["depth_max"])
+    rel = ((outs[0][1] - ref["depths_upsampled"]).abs() / ref["depths_upsampled"]).max()
+    print("prefetch loader vs host loader: max rel depth difference", float(rel))
     assert float(rel) < 1e-4
