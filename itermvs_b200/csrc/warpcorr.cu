@@ -31,6 +31,8 @@
 
 namespace imvs {
 
+int tune(const char* name, int def);   // IMVS_TUNE_<NAME> experiment switch, defined in warp.cu
+
 constexpr int WC_WARPS = 4;     // warps per block = rows of the pixel tile
 constexpr int WC_NPX = 4;       // consecutive pixels of a row handled by one warp
 constexpr int WC_ITER_WARPS = 24;   // iteration kernel: one 768-thread block per SM (<= 85 registers)
@@ -400,7 +402,7 @@ __device__ __forceinline__ void fetch_header(ItemHeader<ST>& h, const IterParams
 // straight-line code with statically renamed buffers), 0 = any number (rolled loops).
 // NW = warps of the (single) block an SM runs.
 template <int ST, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) warpcorr_iter_kernel(const IterParams5 q) {
+__global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) warpcorr_iter_kernel(const IterParams5 q) {
     extern __shared__ float4 smem4[];
     __shared__ unsigned int next_item;
     pdl_trigger();
@@ -649,8 +651,11 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     prm.B = B; prm.V = V; prm.H2 = H2; prm.W2 = W2;
     // one persistent block per SM, each owning a contiguous, compact range of 4-pixel rows
     const int S = V - 1;
-    auto kern = iter_kernel_for<WC_ITER_WARPS>(S);
-    const size_t smem = iter_smem_bytes(S, WC_ITER_WARPS);
+    // occupancy experiment (IMVS_TUNE_WC_WARPS): 24 warps x 1 block per SM (default, <= 85 registers), 32 warps x 1 block or
+    // 16 warps x 2 blocks (both <= 64 registers: 32 resident warps per SM) -- profiles/ps_experiments_r02.md section 5
+    const int nw = tune("WC_WARPS", WC_ITER_WARPS) == 32 ? 32 : (tune("WC_WARPS", WC_ITER_WARPS) == 16 ? 16 : WC_ITER_WARPS);
+    auto kern = nw == 32 ? iter_kernel_for<32>(S) : (nw == 16 ? iter_kernel_for<16>(S) : iter_kernel_for<WC_ITER_WARPS>(S));
+    const size_t smem = iter_smem_bytes(S, nw);
     int dev = 0, sms = 0;
     IMVS_CUDA(cudaGetDevice(&dev));
     IMVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -663,9 +668,9 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     IMVS_REQUIRE(2 * q.tiles_x <= 4096, "warpcorr_iter: W2=%d too wide", W2);
     q.n_tiles = (unsigned)tiles;
     q.strip_magic = ((1ULL << 40) + 2 * q.tiles_x - 1) / (2 * q.tiles_x);
-    const int blocks = (int)std::min<long long>(tiles, sms);
+    const int blocks = (int)std::min<long long>(tiles, nw == 16 ? 2 * sms : sms);
     ApiScope api_;
-    IMVS_CUDA(launch_k(kern, dim3(blocks), dim3(WC_ITER_WARPS * 32), smem, (cudaStream_t)stream, q));
+    IMVS_CUDA(launch_k(kern, dim3(blocks), dim3(nw * 32), smem, (cudaStream_t)stream, q));
     return 0;
 }
 
