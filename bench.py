@@ -606,7 +606,7 @@ def main():
     achieved = iter_b / (mean_iter_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.config == 1:          # the capture was taken at configs[1]
         try:
             traffic = json.load(open(tp)).get("warpcorr_iter_kernel_dram_bytes_per_launch")
         except Exception:
@@ -636,7 +636,14 @@ def main():
         "gpu_launches_per_step": fwd_launches,
         "roofline": {"kernel": "warpcorr_iter_kernel (fused warp+sample+group-corr+view-weighted aggregation)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": iter_b,
+                     "traffic": traffic,
+                     "traffic_source": ("constant from one `ncu --set full` capture of this kernel at this configuration "
+                                        "(profiles/ncu_traffic.json, profiles/ncu_warpcorr_r02.txt), not measured in this run") if traffic else None,
+                     # bytes the gathers deliver to registers through the L1 data pipe: P2 * S * sum_l(R_l * C_l) * 4 taps * 4 B with
+                     # (R, C) = (4, 16), (4, 32), (2, 48) -- what actually bounds this kernel
+                     "l1_tap_bytes_per_launch": (H_IMG // 4) * (W_IMG // 4) * N_SRC * 288 * 16,
+                     "l1_tap_bytes_over_algorithmic": (H_IMG // 4) * (W_IMG // 4) * N_SRC * 288 * 16 / iter_b,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": iter_b,
                      "avg_launch_ms": mean_iter_ms, "launches_timed": len(iter_ms),
                      "init_kernel": {"algorithmic_bytes": init_b, "avg_launch_ms": statistics.mean(init_ms) if init_ms else None}},
         "stage_ms": breakdown,

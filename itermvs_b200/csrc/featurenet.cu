@@ -468,7 +468,15 @@ extern "C" size_t imvs_featurenet_workspace_bytes(int N, int H, int W) {
     return fnet_carve(nullptr, N, H, W).total * sizeof(float);
 }
 
-extern "C" int imvs_featurenet_launch_count(void) { return 18; }
+// 18 convolution launches; 19 in the default mode, where layer3's [conv1 | downsample] (96 stacked channels > the tcgen05 kernel's
+// 64) are two launches
+extern "C" int imvs_featurenet_launch_count(void) {
+#ifdef CUSIM
+    return 18;
+#else
+    return (conv_passes() == 4 && tune("TC5P", 1) && tune("TC5P_LAT", 1) && tune("TC5P_S2", 1) && tc5p::encode_tiled_fn()) ? 19 : 18;
+#endif
+}
 
 static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float* imgs, const unsigned char* imgs_u8, float* fea1,
                                    float* fea2, float* fea3, void* workspace, size_t workspace_bytes, int N, int H, int W, void* stream) {
