@@ -347,6 +347,11 @@ int imvs_image_pyramid_u8(const unsigned char* img, int H0, int W0, float* level
  * (32,32) also with dil = 2;
  * x: [N][H][W][Cin], residual (may be NULL) and out: [N][H][W][Cout]; via_split_output != 0 stores the result as split
  * planes first (the layout the next layer's TMA loads read) and converts back. */
+/* Persistent (TMA + tcgen05) launches use sm_count / share CTAs from now on (share >= 1; default 1 = the whole GPU).  A serving
+ * loop with several reference views in flight on different streams sets 2 while it captures / enqueues them, so that launches
+ * of different streams run side by side instead of one after the other (graph.StreamingPipeline does).  Process-wide. */
+int imvs_set_sm_share(int share);
+
 size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int Cin, int Cout);
 int imvs_conv3x3_tcgen05(const float* x, const void* w_f16ummai, const float* bias, const float* residual, float* out,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int Cin, int Cout, int dil, int relu,

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "imvs_conv3x3_tcgen05_workspace_bytes": (sz, [ci, ci, ci, ci, ci]),
     "imvs_conv3x3_tcgen05": (ci, [vp, vp, vp, vp, vp, vp, sz, ci, ci, ci, ci, ci, ci, ci, ci, vp]),
     "imvs_image_pyramid_u8": (ci, [vp, ci, ci, vp, vp, vp, vp, ci, ci, vp]),
+    "imvs_set_sm_share": (ci, [ci]),
     "imvs_forward_workspace_bytes": (sz, [C.POINTER(Problem)]),
     "imvs_forward_launch_count": (ci, [C.POINTER(Problem)]),
     "imvs_itermvs_forward": (ci, [C.POINTER(Problem), PW, vp, vp, vp, vp, vp, vp, vp, vp,

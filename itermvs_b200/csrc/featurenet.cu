@@ -404,6 +404,19 @@ int sm_count() {
 }
 
 // layout conversion for the operator-level entry point (inside FeatureNet the producers write split planes directly)
+// Persistent launches take one CTA per SM and hold it (TMEM, up to 220 KB of shared memory) until their last tile.  A serving
+// loop that keeps several reference views in flight on different streams can let each launch use 1 / share of the SMs, so
+// that launches of different streams run side by side and each one's launch gap, prologue and tail overlap the other's work
+// (imvs_set_sm_share; graph.StreamingPipeline sets it while it captures its slots).  1 = the whole GPU (latency mode).
+static int g_sm_share = 1;
+int grid_limit() {
+    const int t = tune("TC5P_SHARE", 0);
+    const int share = t > 0 ? t : g_sm_share;
+    return std::max(1, sm_count() / std::max(1, share));
+}
+void set_sm_share(int share) { g_sm_share = share < 1 ? 1 : share; }
+int get_sm_share() { return g_sm_share; }
+
 __global__ void nhwc_to_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t npix_total,
                                      int HW, int C) {
     pdl_trigger();
@@ -615,6 +628,13 @@ extern "C" int imvs_featurenet_forward_u8(const imvs_featurenet_weights* w, cons
 // Operator-level entry point of the persistent TMA + tcgen05 convolution (csrc/tc5pconv.cuh): stride-1 3x3 (dilation dil)
 // Cin -> Cout on fp32 NHWC tensors, fp32-grade (fp16 hi / lo split, three products, fp32 accumulation).  The fp32 operands
 // are converted to split planes in the workspace first; inside FeatureNet the producers write that layout directly.
+extern "C" int imvs_set_sm_share(int share) {
+#ifndef CUSIM
+    tc5p::set_sm_share(share);
+#endif
+    return 0;
+}
+
 extern "C" size_t imvs_conv3x3_tcgen05_workspace_bytes(int N, int H, int W, int Cin, int Cout) {
     if (N < 1 || H < 1 || W < 1 || Cin < 8 || Cout < 8) return 0;
     const size_t px = (size_t)N * H * W;

@@ -490,6 +490,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();       // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (featurenet.cu); nullptr if absent
 int sm_count();                        // multiprocessors of the current device (cached per device)
+int grid_limit();                      // CTAs a persistent launch may use: sm_count() / imvs_set_sm_share() (featurenet.cu)
+void set_sm_share(int share);
+int get_sm_share();
 
 // tensor map over one split plane [N][KC][H][W][8 halves] as the 4-D tensor {W*8, H, KC, N}; box {256, rows, KC, 1}
 // (parity planes of a stride-2 layer's input: N = 4 * images, H and W = half the image's)
@@ -522,7 +525,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wse
     const size_t fixed = (size_t)wsel.nsets * KS * KS * 2 * KCW * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
     const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
-    const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, sm_count()));
+    const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, grid_limit()));
     g.nstages = (int)std::min<size_t>(std::min(std::min(MAX_STAGES, std::max(2, tune("TC5P_ST", MAX_STAGES))), std::max(2, per_cta)),
                                       (budget - fixed) / (2 * (size_t)g.a_bytes));
     const size_t smem = fixed + (size_t)g.nstages * 2 * g.a_bytes;
@@ -532,7 +535,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wse
     auto kern = tc5p_conv_kernel<CINP, NB, MB, DIL, KS, STRIDE, Epi>;
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
-    const int grid = std::min(g.n_tiles, sm_count());
+    const int grid = std::min(g.n_tiles, grid_limit());
     if (launch_k(kern, dim3(grid), dim3(Shape<NB, MB, STRIDE == 0>::THREADS), smem, st, mh, ml, epi, wsel, g, err_flag) != cudaSuccess)
         return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
     return 0;
