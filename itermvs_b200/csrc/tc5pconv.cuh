@@ -265,10 +265,14 @@ __device__ __forceinline__ uint32_t elect_one() {       // one lane of the (conv
 // column below / right); output parity (a, b) of input pixel (iy, ix) -> output (2 iy + a, 2 ix + b) is a stride-1 stencil over
 // the input with 1, 2, 2 or 4 taps (mmaconv.cuh:tconv_tables): four accumulators per M-block, one per parity, nine tap MMAs in
 // total as for a 3x3; the epilogue's four warp groups are the four parities (Epi::store gets c0 = parity * NB).
-template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
-__global__ void __launch_bounds__((Shape<NB, MB, STRIDE == 0>::THREADS), 1)
-tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
-                 const WSel wsel, const Geo geo, int* err_flag) {
+// The body of one layer, shared by the stand-alone kernel below and by multi-layer persistent kernels (evalnets.cu: the fused
+// CorrNet): smem_raw = 128-byte aligned shared memory ([0, 256): mbarriers; then the stages; then the weights), tmem_d = 256
+// allocated TMEM columns' base.  (Re-)initialises its mbarriers, stages its weights, runs the three roles over the layer's
+// tiles and returns after a block barrier.  STANDALONE: the grid-dependency wait sits between the weight requests and the
+// first access to the input.  Threads beyond Shape::THREADS (a fused kernel's block is sized for its widest layer) idle.
+template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, bool STANDALONE, class Epi>
+__device__ __forceinline__ void layer_body(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const Epi& epi, const WSel& wsel,
+                                           const Geo& geo, int* err_flag, unsigned char* smem_raw, const uint32_t tmem_d) {
     static_assert((CINP % 16 == 0 || CINP == 8) && NB % 16 == 0 && NB <= 64, "UMMA kind::f16 shape");
     static_assert(MB == 1 || (MB == 2 && NB <= 32), "M-blocks per tile (TMEM: 2 sets x MB x 2*NB columns <= 256)");
     static_assert(KS == 1 || KS == 3, "1x1 or 3x3");
@@ -284,20 +288,18 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     constexpr int ACC_COLS = MB * NBS;                           // one accumulator set
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
     static_assert(2 * ACC_COLS <= 256, "TMEM budget");
+    constexpr int SMEM_HEAD = 256;                               // = SMEM_HEAD_BYTES (mbarriers + TMEM slot)
     constexpr uint32_t SUB_BYTES = KC * SUBSLOT * 16;            // one plane of one (sub-)tile
     constexpr uint32_t A_BYTES = NSUB * SUB_BYTES;               // one plane of one stage
     constexpr uint32_t B_TAP_BYTES = KCW * 2 * NB * 16;          // hi and lo of one tap
     constexpr uint32_t LBO_A = CINP == 8 ? 0u : SUBSLOT * 16u, LBO_B = 2 * NB * 16;
     using Sh = Shape<NB, MB, TCONV>;
     constexpr int CS = Sh::CS, NCH = Sh::NCH, THREADS = Sh::THREADS;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
     const int nst = geo.nstages;
-    unsigned char* sA = smem_raw;                                               // [nst][hi | lo][KC][NSLOT][16 B]
-    unsigned char* sB = sA + (size_t)nst * 2 * A_BYTES;                         // [tap][KC][hi NB | lo NB][16 B]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sB + (size_t)wsel.nsets * TAPS * B_TAP_BYTES);   // [set][tap][...]
     // barriers: [0, S) full, [S, 2S) empty, 2S + {0,1} accumulator full, 2S + {2,3} accumulator empty, 2S + 4 weights
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2 * MAX_STAGES + 5);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* sA = smem_raw + SMEM_HEAD;                                   // [nst][hi | lo][KC][NSLOT][16 B]
+    unsigned char* sB = sA + (size_t)nst * 2 * A_BYTES;                         // [set][tap][KC][hi NB | lo NB][16 B]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(sBar);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -306,8 +308,11 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     auto bar_tempty = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
     const uint32_t bar_w = bar0 + 8u * (2 * MAX_STAGES + 4);
 
-    if (warp == 0) tmem_alloc(smem_u32(sTmem), TMEM_COLS);
+    static_assert(TMEM_COLS <= 256, "layers share a 256-column TMEM allocation");
     if (tid == 32) {
+        if constexpr (!STANDALONE) {        // a previous layer used these barriers: all of its phases are complete
+            for (int b = 0; b < 2 * MAX_STAGES + 5; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar0 + 8u * b) : "memory");
+        }
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), THREADS - 64); }
         mbar_init(bar_w, 1);
@@ -320,12 +325,10 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 bulk_g2s(smem_u32(sB) + (set * TAPS + tap) * B_TAP_BYTES,
                          static_cast<const unsigned char*>(wsel.w[set]) + (size_t)tap * B_TAP_BYTES, B_TAP_BYTES, bar_w);
     }
-    pdl_trigger();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem_d = *sTmem;
-    pdl_wait();
+    if constexpr (STANDALONE) pdl_wait();
 
     const int tiles_x = geo.tiles_x, tiles_y = geo.tiles_y, n_tiles = geo.n_tiles;
     auto decode = [&](int tile, int& n, int& oy0, int& ox0) {
@@ -430,7 +433,7 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             __syncwarp();
         }
         if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 1);
-    } else {
+    } else if (warp < THREADS / 32) {
         // ---- epilogue -------------------------------------------------------------------------------------------
         const int ew = warp - 2, lg = warp & 3, grp = ew >> 2;       // TMEM lanes 32 * (warp % 4) ..; grp: (M-block, channel slice)
         const int mb = grp / CS, c0 = (grp % CS) * NCH;               // transposed: c0 = parity * NB
@@ -481,7 +484,30 @@ tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+constexpr int SMEM_HEAD_BYTES = 256;       // mbarriers (2 * MAX_STAGES + 5) + the TMEM base slot, in front of the stages
+template <int NB, int MB, int STRIDE> constexpr int tmem_cols() {      // two accumulator sets of MB x (2 NB, or 8 NB transposed) columns
+    constexpr int c = 2 * MB * (STRIDE == 0 ? 8 * NB : 2 * NB);
+    return c <= 64 ? 64 : (c <= 128 ? 128 : 256);
+}
+
+template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
+__global__ void __launch_bounds__((Shape<NB, MB, STRIDE == 0>::THREADS), 1)
+tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
+                 const WSel wsel, const Geo geo, int* err_flag) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem_raw + SMEM_HEAD_BYTES - 16);
+    constexpr int COLS = tmem_cols<NB, MB, STRIDE>();
+    if (threadIdx.x < 32) tmem_alloc(smem_u32(sTmem), COLS);
+    pdl_trigger();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = *sTmem;
+    layer_body<CINP, NB, MB, DIL, KS, STRIDE, true, Epi>(map_hi, map_lo, epi, wsel, geo, err_flag, smem_raw, tmem_d);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_d, COLS);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
@@ -522,7 +548,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wse
     g.tiles_x = cdiv(W, g.valid); g.tiles_y = cdiv(H, g.THo);
     g.n_tiles = g.tiles_x * g.tiles_y * N;
     g.a_bytes = (uint32_t)(STRIDE == 2 ? 4 : 1) * KC * g.rows * WT * 16;
-    const size_t fixed = (size_t)wsel.nsets * KS * KS * 2 * KCW * NB * 16 + (2 * MAX_STAGES + 5) * 8 + 16 + 128 + 256;   // weights, barriers, TMEM slot, alignment, overshoot
+    const size_t fixed = (size_t)wsel.nsets * KS * KS * 2 * KCW * NB * 16 + SMEM_HEAD_BYTES + 128 + 256;   // weights, barriers + TMEM slot, alignment, overshoot
     const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
     const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, grid_limit()));
