@@ -31,6 +31,7 @@ struct EpiCorrOut {          // conv5 (1 valid cout): + bias, scatter to out[(n/
 // transposed convolution + U-Net skip (itermvs.py:374-377): thread = (input pixel, output parity); H, W = INPUT grid
 struct EpiTconvP {
     static constexpr int kAhead = 1;
+    __device__ __forceinline__ bool wants_prefetch() const { return true; }
     tc5p::Split out;         // [N][kco][2H][2W][8]
     tc5p::Split skip;        // same shape
     int H, W, kco;
@@ -45,8 +46,8 @@ struct EpiTconvP {
         for (int j = 0; j < NCH / 8; ++j) {
             if (j >= kco) break;
             const size_t idx = index(n, iy, ix, c0, NB, j);
-            p.h[j] = __ldg(reinterpret_cast<const uint4*>(skip.hi) + idx);
-            p.l[j] = __ldg(reinterpret_cast<const uint4*>(skip.lo) + idx);
+            p.h[j] = __ldcg(reinterpret_cast<const uint4*>(skip.hi) + idx);     // .cg: in the fused kernel the skip tensor was written by other
+            p.l[j] = __ldcg(reinterpret_cast<const uint4*>(skip.lo) + idx);     // CTAs earlier in the same launch (never through the read-only path)
         }
     }
     template <int NB, int NCH>
@@ -81,6 +82,7 @@ struct EpiTconvP {
 
 struct EpiCorrOutP {         // EpiCorrOut for the tcgen05 kernel: channel 0 + bias -> out[(n/period)*bstride + p*pstride + n%period]
     static constexpr int kAhead = 1;
+    __device__ __forceinline__ bool wants_prefetch() const { return false; }
     float* out;
     const float* bias[3];
     int period, split1, split2;
@@ -110,11 +112,95 @@ static tc5p::WSel wsel_of(const imvs_corrnet_weights* sets, int period, int spli
     return s;
 }
 
+// ---- the whole CorrNet pass as ONE persistent cooperative launch ---------------------------------------------------------
+// Seven phases -- operand split of the input volume, conv0, conv1, conv2, conv3^T, conv4^T, conv5 -- each the layer body of
+// tc5pconv.cuh over all CTAs, separated by grid-wide barriers.  What it removes is not work but the six launch gaps, TMEM
+// allocations and pipeline fills / drains of the per-layer launches (~7 us each against 1..5 us of work on these small maps).
+// Launched with cudaLaunchAttributeCooperative: all CTAs are co-resident, so the barriers cannot deadlock against other
+// streams' kernels.  Data written in one phase and read in a later one travels through L2 only (st.global -> membar.gl ->
+// barrier -> TMA loads / ld.global.cg); `counter` must be zero at launch (a memset node precedes the kernel).
+struct CorrFusedParams {
+    CUtensorMap m[12];           // layer L: m[2L] hi plane, m[2L + 1] lo plane of its input
+    tc5p::Epi e0, e1, e2;
+    EpiTconvP e3, e4;
+    EpiCorrOutP e5;
+    tc5p::WSel w[6];
+    tc5p::Geo g[6];
+    const float* vol;            // [N][HW][8] fp32
+    __half* vs_hi;
+    __half* vs_lo;
+    unsigned long long npix;
+    unsigned int* counter;
+    int* err_flag;
+};
+
+constexpr int CF_THREADS = 576;          // the widest layer: 2 + 16 warps
+static_assert(sizeof(CorrFusedParams) <= 4000, "kernel parameter space");
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target, int* err_flag) {
+    __threadfence();                     // this thread's global writes are visible device-wide before the arrival below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned int seen = 0;
+        int spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen >= target) break;
+            __nanosleep(32);
+        } while (++spins < (1 << 22));
+        if (seen < target && err_flag) atomicOr(err_flag, 1);
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.global;" ::: "memory");      // later TMA (async proxy) reads are ordered after the barrier
+}
+
+__global__ void __launch_bounds__(CF_THREADS, 1) corrnet_fused_kernel(const __grid_constant__ CorrFusedParams P) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem_raw + tc5p::SMEM_HEAD_BYTES - 16);
+    const int tid = threadIdx.x;
+    if (tid < 32) tc5p::tmem_alloc(tc5p::smem_u32(sTmem), 256);
+    if (tid == 32) {                      // the layer bodies invalidate and re-initialise these between phases
+        for (int b = 0; b < 2 * tc5p::MAX_STAGES + 5; ++b) tc5p::mbar_init(tc5p::smem_u32(smem_raw) + 8u * b, 1);
+        tc5p::fence_mbar_init();
+    }
+    tc5p::fence_before_sync();
+    __syncthreads();
+    tc5p::fence_after_sync();
+    const uint32_t tmem_d = *sTmem;
+    // phase 0: the aggregated correlation volume -> fp16 hi / lo split planes (one 8-channel chunk per pixel)
+    for (unsigned long long i = (unsigned long long)blockIdx.x * CF_THREADS + tid; i < P.npix; i += (unsigned long long)gridDim.x * CF_THREADS) {
+        const float4 a = ldg4(P.vol + i * 8), b = ldg4(P.vol + i * 8 + 4);
+        uint4 h, l;
+        split_f16(make_float2(a.x, a.y), h.x, l.x);
+        split_f16(make_float2(a.z, a.w), h.y, l.y);
+        split_f16(make_float2(b.x, b.y), h.z, l.z);
+        split_f16(make_float2(b.z, b.w), h.w, l.w);
+        reinterpret_cast<uint4*>(P.vs_hi)[i] = h;
+        reinterpret_cast<uint4*>(P.vs_lo)[i] = l;
+    }
+    unsigned int target = gridDim.x;
+    grid_barrier(P.counter, target, P.err_flag); target += gridDim.x;
+    tc5p::layer_body<8, 16, 2, 1, 3, 1, false>(P.m[0], P.m[1], P.e0, P.w[0], P.g[0], P.err_flag, smem_raw, tmem_d);
+    grid_barrier(P.counter, target, P.err_flag); target += gridDim.x;
+    tc5p::layer_body<8, 16, 1, 1, 3, 2, false>(P.m[2], P.m[3], P.e1, P.w[1], P.g[1], P.err_flag, smem_raw, tmem_d);
+    grid_barrier(P.counter, target, P.err_flag); target += gridDim.x;
+    tc5p::layer_body<16, 32, 1, 1, 3, 2, false>(P.m[4], P.m[5], P.e2, P.w[2], P.g[2], P.err_flag, smem_raw, tmem_d);
+    grid_barrier(P.counter, target, P.err_flag); target += gridDim.x;
+    tc5p::layer_body<32, 16, 1, 1, 3, 0, false>(P.m[6], P.m[7], P.e3, P.w[3], P.g[3], P.err_flag, smem_raw, tmem_d);
+    grid_barrier(P.counter, target, P.err_flag); target += gridDim.x;
+    tc5p::layer_body<16, 16, 1, 1, 3, 0, false>(P.m[8], P.m[9], P.e4, P.w[4], P.g[4], P.err_flag, smem_raw, tmem_d);
+    grid_barrier(P.counter, target, P.err_flag);
+    tc5p::layer_body<8, 16, 2, 1, 3, 1, false>(P.m[10], P.m[11], P.e5, P.w[5], P.g[5], P.err_flag, smem_raw, tmem_d);
+    if (tid < 32) tc5p::tmem_dealloc(tmem_d, 256);
+}
+
 static bool corrnet_tc5p_ready(const imvs_corrnet_weights* sets) {
     // OFF by default: measured on B200 (gpurun call r2c22) the seven tcgen05 launches of a pass take 75 us against 66 us for the
     // six mma.sync launches -- every persistent launch has a ~7 us floor (TMEM allocation, barrier and weight staging, first
     // TMA round trip, drain) that these 160..960-tile layers cannot amortise.  IMVS_TUNE_TC5P_CORR=1 selects it (parity-tested).
-    if (conv_passes() != 4 || !tune("TC5P_CORR", 0) || !tc5p::encode_tiled_fn()) return false;
+    if (conv_passes() != 4 || !(tune("TC5P_CORR", 0) || tune("CORR_FUSED", 0)) || !tc5p::encode_tiled_fn()) return false;
     for (int i = 0; i < 3; ++i)
         for (int k = 0; k < 6; ++k)
             if (!wsel_of(sets, 1, 1, 1, k).w[i]) return false;
@@ -264,17 +350,60 @@ extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int sp
                           x3s = tc5p::split_at(take(n4), n4), x4s = tc5p::split_at(take(n8), n8), none{nullptr, nullptr};
         int* flag = tc5_error_flag();
         auto ws = [&](int which) { return wsel_of(sets, period, split1, split2, which); };
+        EpiCorrOutP e5;
+        e5.out = out;
+        for (int i = 0; i < 3; ++i) e5.bias[i] = sets[i].conv5_b;
+        e5.period = period; e5.split1 = split1; e5.split2 = split2;
+        e5.bstride = out_batch_stride; e5.pstride = out_pixel_stride; e5.H = H; e5.W = W;
+        if (tune("CORR_FUSED", 0)) {
+            // one cooperative launch for the whole pass
+            CorrFusedParams P{};
+            const size_t budget = 200 * 1024;
+            const int ctas = tc5p::sm_count();
+            size_t smem = 0, need = 0;
+            for (int k = 0; k < 6; ++k) P.w[k] = ws(k);
+            IMVS_TRY((tc5p::plan_layer<8, 16, 2, 1, 3, 1>("corrnet.conv0", P.w[0], N, H, W, ctas, budget, P.g[0], need))); smem = std::max(smem, need);
+            IMVS_TRY((tc5p::plan_layer<8, 16, 1, 1, 3, 2>("corrnet.conv1", P.w[1], N, H1, W1, ctas, budget, P.g[1], need))); smem = std::max(smem, need);
+            IMVS_TRY((tc5p::plan_layer<16, 32, 1, 1, 3, 2>("corrnet.conv2", P.w[2], N, H2, W2, ctas, budget, P.g[2], need))); smem = std::max(smem, need);
+            IMVS_TRY((tc5p::plan_layer<32, 16, 1, 1, 3, 0>("corrnet.conv3", P.w[3], N, H2, W2, ctas, budget, P.g[3], need))); smem = std::max(smem, need);
+            IMVS_TRY((tc5p::plan_layer<16, 16, 1, 1, 3, 0>("corrnet.conv4", P.w[4], N, H1, W1, ctas, budget, P.g[4], need))); smem = std::max(smem, need);
+            IMVS_TRY((tc5p::plan_layer<8, 16, 2, 1, 3, 1>("corrnet.conv5", P.w[5], N, H, W, ctas, budget, P.g[5], need))); smem = std::max(smem, need);
+            struct In { const tc5p::Split* t; int n, kc, h, w, rows; };
+            const In ins[6] = {{&vs, N, 1, H, W, P.g[0].rows}, {&c0p, 4 * N, 1, H1, W1, P.g[1].rows}, {&c1p, 4 * N, 2, H2, W2, P.g[2].rows},
+                               {&c2s, N, 4, H2, W2, P.g[3].rows}, {&x3s, N, 2, H1, W1, P.g[4].rows}, {&x4s, N, 1, H, W, P.g[5].rows}};
+            for (int k = 0; k < 6; ++k) {
+                IMVS_TRY(tc5p::make_plane_map(&P.m[2 * k], ins[k].t->hi, ins[k].n, ins[k].kc, ins[k].h, ins[k].w, ins[k].rows));
+                IMVS_TRY(tc5p::make_plane_map(&P.m[2 * k + 1], ins[k].t->lo, ins[k].n, ins[k].kc, ins[k].h, ins[k].w, ins[k].rows));
+            }
+            P.e0 = tc5p::Epi{c0s, nullptr, none, nullptr, H, W, 1, c0p, 1};
+            P.e1 = tc5p::Epi{c1s, nullptr, none, nullptr, H1, W1, 1, c1p, 0};
+            P.e2 = tc5p::Epi{c2s, nullptr, none, nullptr, H2, W2, 1};
+            P.e3 = EpiTconvP{x3s, c1s, H2, W2, 2};
+            P.e4 = EpiTconvP{x4s, c0s, H1, W1, 1};
+            P.e5 = e5;
+            P.vol = vol; P.vs_hi = vs.hi; P.vs_lo = vs.lo; P.npix = (unsigned long long)N * HW;
+            P.counter = reinterpret_cast<unsigned int*>(take(64));
+            P.err_flag = flag;
+            static int smem_ok = 0;
+            IMVS_TRY(ensure_dynamic_smem(corrnet_fused_kernel, smem, &smem_ok));
+            IMVS_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), st));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(CF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            *pdl_armed() = false;            // the next launch of this call must not be a programmatic dependent of the memset / this kernel
+            count_launch();
+            IMVS_CUDA(cudaLaunchKernelEx(&cfg, corrnet_fused_kernel, P));
+            return 0;
+        }
         IMVS_TRY(tc5p::launch_nhwc_to_split(vol, vs, (size_t)N * HW, (int)HW, 8, st));
         IMVS_TRY((tc5p::launch<8, 16>("corrnet.conv0", vs, tc5p::Epi{c0s, nullptr, none, nullptr, H, W, 1, c0p, 1}, ws(0), N, H, W, flag, st)));
         IMVS_TRY((tc5p::launch<8, 16, 1, true, 3, 2>("corrnet.conv1", c0p, tc5p::Epi{c1s, nullptr, none, nullptr, H1, W1, 1, c1p, 0}, ws(1), N, H1, W1, flag, st)));
         IMVS_TRY((tc5p::launch<16, 32, 1, true, 3, 2>("corrnet.conv2", c1p, tc5p::Epi{c2s, nullptr, none, nullptr, H2, W2, 1}, ws(2), N, H2, W2, flag, st)));
         IMVS_TRY((tc5p::launch<32, 16, 1, false, 3, 0>("corrnet.conv3", c2s, EpiTconvP{x3s, c1s, H2, W2, 2}, ws(3), N, H2, W2, flag, st)));
         IMVS_TRY((tc5p::launch<16, 16, 1, false, 3, 0>("corrnet.conv4", x3s, EpiTconvP{x4s, c0s, H1, W1, 1}, ws(4), N, H1, W1, flag, st)));
-        EpiCorrOutP e5;
-        e5.out = out;
-        for (int i = 0; i < 3; ++i) e5.bias[i] = sets[i].conv5_b;
-        e5.period = period; e5.split1 = split1; e5.split2 = split2;
-        e5.bstride = out_batch_stride; e5.pstride = out_pixel_stride; e5.H = H; e5.W = W;
         IMVS_TRY((tc5p::launch<8, 16>("corrnet.conv5", x4s, e5, ws(5), N, H, W, flag, st)));
         return 0;
     }

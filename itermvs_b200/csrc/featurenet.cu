@@ -81,6 +81,7 @@ struct EpiAddUp2H {
 // one pixel x NCH channels: the four bilinear taps are 4 x NCH/4 float4 loads from the (L2-resident) coarse map.
 struct EpiLateral {
     static constexpr int kAhead = 1;
+    __device__ __forceinline__ bool wants_prefetch() const { return false; }
     tc5p::Split out;         // [N][C/8][H][W][8]
     float* out32;            // [N][H][W][C] or nullptr
     const float* bias;       // [C]

@@ -108,12 +108,13 @@ struct Geo {
     int pad, dil, ks;
     int valid;           // valid output columns per tile = WT - 2 * pad
     int nstages;
+    int dbg;             // timing experiments only (IMVS_TUNE_TC5P_DBG, results wrong): 1 = epilogue does not store, 2 = one tap's MMAs only
     uint32_t a_bytes;    // bytes of one plane of one stage = KC * rows * WT * 16
 };
 
 // ---- epilogue: one thread = one pixel, channels [c0, c0 + NCH) ------------------------------------------------------
 // Interface of an epilogue class: members H, W; Pre<NCH>; prefetch<NB, NCH>(n, oy, ox, c0, pre) (global reads that do not
-// depend on the accumulator, issued one tile ahead); store<NB, NCH>(n, oy, ox, c0, v, pre, status).
+// depend on the accumulator, issued kAhead tiles ahead when wants_prefetch()); store<NB, NCH>(n, oy, ox, c0, v, pre, status).
 // out = relu?(acc + bias + residual); written as split planes (the next tcgen05 layer's operand) and / or fp32 NHWC.
 // index (in 16-byte units) of chunk kc of pixel (oy, ox) of image n in the PARITY-PLANE layout [4N][KCo][H/2][W/2][8] that a
 // stride-2 layer reads (image 4n + 2 (oy & 1) + (ox & 1) holds the pixels of that parity); H, W even
@@ -132,6 +133,7 @@ struct Epi {
     int kco = 0;             // 8-channel chunks of the output / residual tensors when fewer than NB / 8 (cout padded to 16); 0: NB / 8
 
     template <int NCH> struct Pre { uint4 h[NCH / 8], l[NCH / 8]; };
+    __device__ __forceinline__ bool wants_prefetch() const { return res.hi != nullptr; }
 
     template <int NB, int NCH>
     __device__ __forceinline__ void prefetch(int n, int oy, int ox, int c0, Pre<NCH>& p) const {
@@ -208,6 +210,7 @@ struct Epi {
 // channels [0, CO) -> relu(v + bias) -> y, channels [CO, 2 CO) -> v + bias -> ds; both written as split planes
 struct EpiStack2 {
     static constexpr int kAhead = 1;
+    __device__ __forceinline__ bool wants_prefetch() const { return false; }
     Split y, ds;             // [N][CO/8][H][W][8] each
     const float* bias;       // [2 CO]
     int H, W, CO;
@@ -386,6 +389,7 @@ __device__ __forceinline__ void layer_body(const CUtensorMap& map_hi, const CUte
                 if constexpr (!TCONV) {
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
+                        if ((geo.dbg & 2) && tap > 0) break;
 #pragma unroll
                         for (int k16 = 0; k16 < KSTEPS; ++k16) {
                             // slots == 16-byte units: tap shift + k-step advance
@@ -447,8 +451,9 @@ __device__ __forceinline__ void layer_body(const CUtensorMap& map_hi, const CUte
         };
         // accumulator-independent global reads (residual, gate operands) are requested Epi::kAhead (1 or 2) tiles ahead
         constexpr int AHEAD = Epi::kAhead;
+        const bool wants_pre = epi.wants_prefetch();
         typename Epi::template Pre<NCH> pre{}, pre1{}, pre2{};
-        {
+        if (wants_pre) {
             int n, oy, ox;
             if (blockIdx.x < n_tiles && pixel(blockIdx.x, n, oy, ox)) epi.template prefetch<NB, NCH>(n, oy, ox, c0, pre);
             if (AHEAD == 2 && blockIdx.x + gridDim.x < n_tiles && pixel(blockIdx.x + gridDim.x, n, oy, ox)) epi.template prefetch<NB, NCH>(n, oy, ox, c0, pre1);
@@ -458,7 +463,7 @@ __device__ __forceinline__ void layer_body(const CUtensorMap& map_hi, const CUte
             const int acc = it & 1, aph = (it >> 1) & 1;
             int n, oy, ox;
             const bool okp = pixel(tile, n, oy, ox);
-            {
+            if (wants_pre) {
                 int n2, oy2, ox2;
                 const int nxt = tile + AHEAD * gridDim.x;
                 if (nxt < n_tiles && pixel(nxt, n2, oy2, ox2)) epi.template prefetch<NB, NCH>(n2, oy2, ox2, c0, AHEAD == 2 ? pre2 : pre1);
@@ -477,7 +482,7 @@ __device__ __forceinline__ void layer_body(const CUtensorMap& map_hi, const CUte
             mbar_arrive(bar_tempty(acc));           // the accumulator set is in registers: the MMA warp may overwrite it
 #pragma unroll
             for (int q = 0; q < NCH; ++q) v[q] += u[q];
-            if (okp) epi.template store<NB, NCH>(n, oy, ox, c0, v, pre, err_flag);
+            if (okp && !(geo.dbg & 1)) epi.template store<NB, NCH>(n, oy, ox, c0, v, pre, err_flag);
             pre = pre1;
             if (AHEAD == 2) pre1 = pre2;
         }
@@ -548,6 +553,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wse
     g.tiles_x = cdiv(W, g.valid); g.tiles_y = cdiv(H, g.THo);
     g.n_tiles = g.tiles_x * g.tiles_y * N;
     g.a_bytes = (uint32_t)(STRIDE == 2 ? 4 : 1) * KC * g.rows * WT * 16;
+    g.dbg = tune("TC5P_DBG", 0);
     const size_t fixed = (size_t)wsel.nsets * KS * KS * 2 * KCW * NB * 16 + SMEM_HEAD_BYTES + 128 + 256;   // weights, barriers + TMEM slot, alignment, overshoot
     const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);

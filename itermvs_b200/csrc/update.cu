@@ -90,6 +90,7 @@ __global__ void gru_split_inputs_kernel(const float* __restrict__ h, const float
 
 struct EpiGruZRp {           // 64 stacked channels: a thread's slice is part of z (c0 < 32) or of r (c0 >= 32)   (module.py:61-62)
     static constexpr int kAhead = 1;
+    __device__ __forceinline__ bool wants_prefetch() const { return true; }
     const float* bias;       // [64]
     const float* h;          // [B][P][32]
     float* z;                // [B][P][32]
@@ -135,6 +136,7 @@ struct EpiGruZRp {           // 64 stacked channels: a thread's slice is part of
 
 struct EpiGruQp {            // q = tanh, h <- (1 - z) h + z q in place   (module.py:63-64)
     static constexpr int kAhead = 1;
+    __device__ __forceinline__ bool wants_prefetch() const { return true; }
     const float* bias;       // [32]
     const float* z;          // [B][P][32]
     float* h;                // [B][P][32]

@@ -790,22 +790,24 @@ def test_conv3x3_tma_tcgen05_vs_fp64(dev, cin, cout, dil, shape):
         assert err < 5e-6 * max(scale, 1.0), err
 
 
-def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch):
-    """CorrNet with all six layers on the persistent TMA + tcgen05 kernel (IMVS_TUNE_TC5P_CORR=1; off by default because it is
-    slower for these small maps): 8-channel layers through an aliased K chunk, the two stride-2 layers on parity planes, the two
-    transposed layers with four parity accumulators, three weight sets chosen per slice -- against the reference's KAT and,
-    in the three-set batched form the iterations use, against the default mma.sync path."""
+@pytest.mark.parametrize("switch", ["TC5P_CORR", "CORR_FUSED"])
+def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch, switch):
+    """CorrNet with all six layers on the persistent TMA + tcgen05 kernel: 8-channel layers through an aliased K chunk, the two
+    stride-2 layers on parity planes, the two transposed layers with four parity accumulators, three weight sets chosen per
+    slice.  IMVS_TUNE_TC5P_CORR=1: one launch per layer; IMVS_TUNE_CORR_FUSED=1: the whole pass as ONE cooperative launch with
+    grid-wide barriers between the layers.  Against the reference's KAT and, in the three-set batched form the iterations use
+    (graph-captured as the serving loop does), against the default mma.sync path."""
     from itermvs_b200 import _lib
     k = stage_kats
     ev = model.iter_mvs.evaluation
     x = T(k["corrnet_in"]).to(dev)
-    monkeypatch.setenv("IMVS_TUNE_TC5P_CORR", "1")
+    monkeypatch.setenv("IMVS_TUNE_" + switch, "1")
     got = ev.corr_conv1[0](x)
     torch.cuda.synchronize()
     assert _lib.device_status(clear=True) == 0
-    monkeypatch.setenv("IMVS_TUNE_TC5P_CORR", "0")
+    monkeypatch.setenv("IMVS_TUNE_" + switch, "0")
     ref = ev.corr_conv1[0](x)
-    print("corrnet tcgen05 vs KAT", maxerr(got, T(k["corrnet0_out"])), "vs mma.sync", maxerr(got, ref))
+    print(switch, "corrnet tcgen05 vs KAT", maxerr(got, T(k["corrnet0_out"])), "vs mma.sync", maxerr(got, ref))
     assert maxerr(got, T(k["corrnet0_out"])) < 2e-5
     assert maxerr(got, ref) < 2e-5
     # the batched three-set form (10 slices: 4 + 4 + 2) through the iteration branch of Evaluation
@@ -813,15 +815,24 @@ def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch):
     cu = lambda d: {kk: v.to(dev) for kk, v in d.items()}
     outs = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("IMVS_TUNE_TC5P_CORR", flag)
+        monkeypatch.setenv("IMVS_TUNE_" + switch, flag)
         with torch.no_grad():
             out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
         torch.cuda.synchronize()
         outs.append(out["depths_upsampled"].clone())
     assert _lib.device_status(clear=True) == 0
     rel = ((outs[0] - outs[1]).abs() / outs[1]).max()
-    print("pipeline with CorrNet on tcgen05 vs default: max rel depth difference", float(rel))
+    print(switch, "pipeline with CorrNet on tcgen05 vs default: max rel depth difference", float(rel))
     assert float(rel) < 1e-4
+    # captured in a CUDA graph and replayed (cooperative launch + memset node inside the capture)
+    from itermvs_b200.graph import GraphedPipeline
+    monkeypatch.setenv("IMVS_TUNE_" + switch, "1")
+    g = GraphedPipeline(model, cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev), workspace_slot=5)
+    for _ in range(3):
+        o = g(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+    torch.cuda.synchronize()
+    assert _lib.device_status(clear=True) == 0
+    assert torch.equal(o["depths_upsampled"], outs[0])
 
 
 def test_image_pyramid_and_prefetch_loader_on_device(dev, model, tmp_path):
