@@ -114,6 +114,10 @@ def lib():
             if _build.is_stale():
                 path = _build.build()
         except Exception as e:  # no nvcc on the box and no prebuilt library
+            if os.path.exists(path):
+                import sys
+                print(f"itermvs_b200: WARNING: {path} is older than its sources and rebuilding failed ({str(e)[:300]}...); "
+                      "loading the existing library", file=sys.stderr)
             if not os.path.exists(path):
                 raise LibraryMissing(
                     f"itermvs_b200: CUDA library {path} is missing and could not be built ({e}). "

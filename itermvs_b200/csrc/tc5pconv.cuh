@@ -541,11 +541,11 @@ inline int make_plane_map(CUtensorMap* map, const __half* plane, int N, int KC, 
     return 0;
 }
 
-// H, W: OUTPUT size (= input size for STRIDE 1; the input of a STRIDE 2 layer is 2H x 2W, stored as parity planes)
-template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
-int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wsel, int N, int H, int W, int* err_flag, cudaStream_t st) {
+// tile geometry, stage count and shared-memory need of one layer on `ctas` persistent CTAs (budget: bytes of dynamic shared memory)
+template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE>
+int plan_layer(const char* name, const WSel& wsel, int N, int H, int W, int ctas, size_t budget, Geo& g, size_t& smem) {
     constexpr int KC = CINP / 8, KCW = (CINP + 15) / 16 * 2, PAD = STRIDE != 1 ? 0 : DIL * (KS - 1) / 2;
-    Geo g{};
+    g = Geo{};
     g.ks = KS; g.dil = DIL; g.pad = PAD;
     g.valid = STRIDE != 1 ? WT - 1 : WT - 2 * PAD;
     g.THo = 4 * MB;
@@ -555,12 +555,22 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wse
     g.a_bytes = (uint32_t)(STRIDE == 2 ? 4 : 1) * KC * g.rows * WT * 16;
     g.dbg = tune("TC5P_DBG", 0);
     const size_t fixed = (size_t)wsel.nsets * KS * KS * 2 * KCW * NB * 16 + SMEM_HEAD_BYTES + 128 + 256;   // weights, barriers + TMEM slot, alignment, overshoot
-    const size_t budget = 220 * 1024;          // ensure_dynamic_smem() opts in to 220 KB
     IMVS_REQUIRE(fixed + 2 * (size_t)2 * g.a_bytes <= budget, "%s: tile does not fit shared memory", name);
-    const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, grid_limit()));
+    const int per_cta = cdiv(g.n_tiles, std::min(g.n_tiles, ctas));
     g.nstages = (int)std::min<size_t>(std::min(std::min(MAX_STAGES, std::max(2, tune("TC5P_ST", MAX_STAGES))), std::max(2, per_cta)),
                                       (budget - fixed) / (2 * (size_t)g.a_bytes));
-    const size_t smem = fixed + (size_t)g.nstages * 2 * g.a_bytes;
+    smem = fixed + (size_t)g.nstages * 2 * g.a_bytes;
+    return 0;
+}
+
+// H, W: OUTPUT size (= input size for STRIDE 1; the input of a STRIDE 2 layer is 2H x 2W, stored as parity planes; transposed:
+// the INPUT grid, the output is 2H x 2W)
+template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
+int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wsel, int N, int H, int W, int* err_flag, cudaStream_t st) {
+    constexpr int KC = CINP / 8;
+    Geo g;
+    size_t smem = 0;
+    IMVS_TRY((plan_layer<CINP, NB, MB, DIL, KS, STRIDE>(name, wsel, N, H, W, grid_limit(), 220 * 1024, g, smem)));   // ensure_dynamic_smem() opts in to 220 KB
     CUtensorMap mh, ml;
     IMVS_TRY(make_plane_map(&mh, in.hi, STRIDE == 2 ? 4 * N : N, KC, H, W, g.rows));     // stride 2: parity planes are H x W (= the output size)
     IMVS_TRY(make_plane_map(&ml, in.lo, STRIDE == 2 ? 4 * N : N, KC, H, W, g.rows));
