@@ -49,12 +49,12 @@ def test_cuda_check_geometric_consistency(fusion_kat):
         same = ~diff
         assert np.allclose(rep[same], z[f"reprojected{v}"][same], rtol=2e-6, atol=1e-4)
     print(f"geometric consistency: {flips} mask flips over {len(depths)} views")
-    assert flips <= 3, flips
+    assert flips == 0, flips            # measured on B200: 0 (bit-exact masks against the reference's own functions)
     # CUDA tensors in -> CUDA tensors out
     dev = torch.device("cuda:0")
     m, rep, xs, ys = check_geometric_consistency(torch.from_numpy(z["depth0"]).to(dev), z["K0"], z["E0"],
                                                  torch.from_numpy(depths[0]).to(dev), ks[0], es[0], 1.0, 0.01)
-    assert m.is_cuda and m.dtype == torch.bool and int((m.cpu().numpy() != z["mask1"]).sum()) <= 1
+    assert m.is_cuda and m.dtype == torch.bool and int((m.cpu().numpy() != z["mask1"]).sum()) == 0
 
 
 @pytest.mark.gpu
@@ -66,7 +66,7 @@ def test_cuda_filter_depth_view(fusion_kat):
     assert avg.dtype == np.float64
     assert np.array_equal(pm, z["photo_mask"])
     print(f"filter_depth_view: geo mask flips {int((gm != z['geo_mask']).sum())}, final mask flips {int((fm != z['final_mask']).sum())}")
-    assert int((gm != z["geo_mask"]).sum()) <= 2 and int((fm != z["final_mask"]).sum()) <= 2
+    assert int((gm != z["geo_mask"]).sum()) == 0 and int((fm != z["final_mask"]).sum()) == 0      # measured on B200: 0 / 0
     same = gm == z["geo_mask"]
     with np.errstate(invalid="ignore"):
         close = np.isclose(avg, z["depth_est_averaged"], rtol=2e-6, atol=1e-4, equal_nan=True)
