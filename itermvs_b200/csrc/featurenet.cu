@@ -77,19 +77,32 @@ struct EpiAddUp2H {
 };
 
 // The lateral stage on the TMA + tcgen05 kernel (tc5pconv.cuh, 1x1): out = conv1x1(x) + bias + up2(coarse), written as split
-// planes (operand of the output convolution) and, when the next lateral stage upsamples it, as fp32 NHWC too.  One thread =
-// one pixel x NCH channels: the four bilinear taps are 4 x NCH/4 float4 loads from the (L2-resident) coarse map.
+// planes (operand of the output convolution and, for intra2, the coarse map of the next lateral stage).  One thread = one
+// pixel x NCH channels.  The coarse map is read from its SPLIT PLANES (value = hi + lo, 2^-23 relative from the fp32 value):
+// in that chunk-planar layout the 32 pixels of a warp read 16 neighbouring texels x 16 bytes per instruction -- 2 L1
+// wavefronts instead of the ~24 of the channels-last fp32 map (thread stride 192 bytes), which bounded this kernel (ablation in
+// profiles/README.md: 37 of 50 us in the epilogue).
 struct EpiLateral {
     static constexpr int kAhead = 1;
     __device__ __forceinline__ bool wants_prefetch() const { return false; }
     tc5p::Split out;         // [N][C/8][H][W][8]
     float* out32;            // [N][H][W][C] or nullptr
     const float* bias;       // [C]
-    const float* coarse;     // [N][H/2][W/2][C] fp32
+    tc5p::Split coarse;      // [N][C/8][H/2][W/2][8] split planes
     int H, W;
     template <int NCH> struct Pre {};
     template <int NB, int NCH>
     __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NCH>&) const {}
+    __device__ __forceinline__ static void unpack8(const uint4& h, const uint4& l, float (&o)[8]) {
+        const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[q]));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ll[q]));
+            o[2 * q] = a.x + b.x;
+            o[2 * q + 1] = a.y + b.y;
+        }
+    }
     template <int NB, int NCH>
     __device__ __forceinline__ void store(int n, int oy, int ox, int c0, float (&v)[NCH], const Pre<NCH>&, int* status) const {
         const int Hc = H / 2, Wc = W / 2;
@@ -97,28 +110,27 @@ struct EpiLateral {
         float lh, lw;
         up_index(oy, 0.5f, Hc, h0, h1, lh);
         up_index(ox, 0.5f, Wc, w0, w1, lw);
-        const float* cb = coarse + (size_t)n * Hc * Wc * NB + c0;
-        const float* t00 = cb + ((size_t)h0 * Wc + w0) * NB;
-        const float* t01 = cb + ((size_t)h0 * Wc + w1) * NB;
-        const float* t10 = cb + ((size_t)h1 * Wc + w0) * NB;
-        const float* t11 = cb + ((size_t)h1 * Wc + w1) * NB;
-        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox;
+        const size_t plane = (size_t)H * W, pix = (size_t)oy * W + ox, cplane = (size_t)Hc * Wc;
+        const uint4* chi = reinterpret_cast<const uint4*>(coarse.hi);
+        const uint4* clo = reinterpret_cast<const uint4*>(coarse.lo);
         float amax = 0.f;
 #pragma unroll
         for (int j = 0; j < NCH / 8; ++j) {
             float* x = v + 8 * j;
+            const size_t cb = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * cplane;
+            const size_t i00 = cb + (size_t)h0 * Wc + w0, i01 = cb + (size_t)h0 * Wc + w1, i10 = cb + (size_t)h1 * Wc + w0, i11 = cb + (size_t)h1 * Wc + w1;
+            const uint4 ah = __ldg(chi + i00), al = __ldg(clo + i00), bh = __ldg(chi + i01), bl = __ldg(clo + i01);
+            const uint4 ch = __ldg(chi + i10), cl = __ldg(clo + i10), dh = __ldg(chi + i11), dl = __ldg(clo + i11);
+            const float4 bi0 = ldg4(bias + c0 + 8 * j), bi1 = ldg4(bias + c0 + 8 * j + 4);
+            const float bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+            float a[8], b[8], c[8], d[8];
+            unpack8(ah, al, a); unpack8(bh, bl, b); unpack8(ch, cl, c); unpack8(dh, dl, d);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int c = 8 * j + 4 * q;
-                const float4 a = ldg4(t00 + c), b = ldg4(t01 + c), cc = ldg4(t10 + c), d = ldg4(t11 + c), bi = ldg4(bias + c0 + c);
+            for (int q = 0; q < 8; ++q) {
                 // same association as EpiAddUp2 / the oracle: up + (conv + bias)
-                x[4 * q + 0] = ((1.f - lh) * ((1.f - lw) * a.x + lw * b.x) + lh * ((1.f - lw) * cc.x + lw * d.x)) + (x[4 * q + 0] + bi.x);
-                x[4 * q + 1] = ((1.f - lh) * ((1.f - lw) * a.y + lw * b.y) + lh * ((1.f - lw) * cc.y + lw * d.y)) + (x[4 * q + 1] + bi.y);
-                x[4 * q + 2] = ((1.f - lh) * ((1.f - lw) * a.z + lw * b.z) + lh * ((1.f - lw) * cc.z + lw * d.z)) + (x[4 * q + 2] + bi.z);
-                x[4 * q + 3] = ((1.f - lh) * ((1.f - lw) * a.w + lw * b.w) + lh * ((1.f - lw) * cc.w + lw * d.w)) + (x[4 * q + 3] + bi.w);
+                x[q] = ((1.f - lh) * ((1.f - lw) * a[q] + lw * b[q]) + lh * ((1.f - lw) * c[q] + lw * d[q])) + (x[q] + bi[q]);
+                amax = fmaxf(amax, fabsf(x[q]));
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fabsf(x[q]));
             uint4 h, l;
             split_f16(make_float2(x[0], x[1]), h.x, l.x);
             split_f16(make_float2(x[2], x[3]), h.y, l.y);
@@ -540,7 +552,7 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
             // trunk of stage 1 / 2: split planes for the lateral 1x1 and parity planes (in the fp32 trunk's buffer) for the next stage
             IMVS_TRY((res_stage_p2<8, 16>(w, 1, tc5p::split_at(b.a0, (size_t)N * H * W * 8), b.l1, nullptr, b.l1s, b.l1[3], N, H1, W1, st)));
             IMVS_TRY((res_stage_p2<16, 32>(w, 6, tc5p::split_at(b.l1[3], (size_t)N * H1 * W1 * 16), b.l2, nullptr, b.l2s, b.l2[3], N, H2, W2, st)));
-            IMVS_TRY((res_stage_p2<32, 48>(w, 11, tc5p::split_at(b.l2[3], (size_t)N * H2 * W2 * 32), b.l3, b.l3[3], b.l3s, nullptr, N, H3, W3, st)));
+            IMVS_TRY((res_stage_p2<32, 48>(w, 11, tc5p::split_at(b.l2[3], (size_t)N * H2 * W2 * 32), b.l3, nullptr, b.l3s, nullptr, N, H3, W3, st)));   // s2p implies lat: no fp32 trunk needed
         } else {
             IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, b.l1s, N, H, W, st)));                 // layer1 -> l1[3]  [H/2][W/2][16] (+ split)
             IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, b.l2s, N, H1, W1, st)));           // layer2 -> l2[3]  [H/4][W/4][32] (+ split)
@@ -551,11 +563,11 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
                           i1s = tc5p::split_at(b.intra1, (size_t)N * H1 * W1 * 48);
         IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16ummai, N, H3, W3, flag, st)));
         // intra2 = up2(f3) + inner2(f2) (net.py:60): 1x1 on the tensor core, bilinear taps in the epilogue
-        if (lat) IMVS_TRY((tc5p::launch<32, 48, 1, true, 1>("fnet.inner2", l2s, EpiLateral{i2s, b.intra2, w->b[17], b.l3[3], H2, W2}, w->w[17].f16ummai, N, H2, W2, flag, st)));
+        if (lat) IMVS_TRY((tc5p::launch<32, 48, 1, true, 1>("fnet.inner2", l2s, EpiLateral{i2s, nullptr, w->b[17], l3s, H2, W2}, w->w[17].f16ummai, N, H2, W2, flag, st)));
         else IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2H{b.intra2, i2s, w->b[17], b.l3[3], H2, W2, 48},
                                                         WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
         IMVS_TRY((tc5p::launch<48, 32>("fnet.output2", i2s, tc5p::Epi{none, fea2, none, w->b[18], H2, W2, 0}, w->w[18].f16ummai, N, H2, W2, flag, st)));
-        if (lat) IMVS_TRY((tc5p::launch<16, 48, 1, true, 1>("fnet.inner1", l1s, EpiLateral{i1s, nullptr, w->b[19], b.intra2, H1, W1}, w->w[19].f16ummai, N, H1, W1, flag, st)));
+        if (lat) IMVS_TRY((tc5p::launch<16, 48, 1, true, 1>("fnet.inner1", l1s, EpiLateral{i1s, nullptr, w->b[19], i2s, H1, W1}, w->w[19].f16ummai, N, H1, W1, flag, st)));
         else IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2H{nullptr, i1s, w->b[19], b.intra2, H1, W1, 48},
                                                         WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
         IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16ummai, N, H1, W1, flag, st)));

@@ -53,7 +53,10 @@ constexpr int WT = 32;                 // slots per tile row
 // CTA: warp 0 producer, warp 1 MMA issuer, then 4 * MB * CS epilogue warps: a warp reads the TMEM lanes 32 * (warp % 4) ..,
 // its group index selects the M-block and one of CS channel slices (the epilogue, not the tensor core, was the pipeline's
 // slowest stage with 8 warps: ncu r2c17 -- the MMA warp spinning on the accumulator-empty barrier)
-template <int NB, int MB, bool TC = false> struct Shape {     // TC: transposed convolution -- the four slices are the output parities
+// TC: transposed convolution -- the four slices are the output parities.  K1 (1x1 layers): 8-channel slices, i.e. 24 epilogue
+// warps, were measured for the lateral layers (gpurun call r2c36 / r2c37): same 49 us with twice the executed instructions
+// (32.7 M vs 17 M: the per-thread fixed part), issue slots 67 % busy -- that epilogue is instruction-bound, so K1 changes nothing
+template <int NB, int MB, bool TC = false, bool K1 = false> struct Shape {
     static constexpr int CS = TC ? 4 : (MB == 2 ? 2 : (NB % 32 == 0 ? 4 : (NB == 48 ? 3 : 2)));      // slices per M-block
     static constexpr int NCH = TC ? NB : NB / CS;                                        // channels per epilogue thread (8 or 16)
     static constexpr int EPI_WARPS = 4 * MB * CS;
@@ -296,7 +299,7 @@ __device__ __forceinline__ void layer_body(const CUtensorMap& map_hi, const CUte
     constexpr uint32_t A_BYTES = NSUB * SUB_BYTES;               // one plane of one stage
     constexpr uint32_t B_TAP_BYTES = KCW * 2 * NB * 16;          // hi and lo of one tap
     constexpr uint32_t LBO_A = CINP == 8 ? 0u : SUBSLOT * 16u, LBO_B = 2 * NB * 16;
-    using Sh = Shape<NB, MB, TCONV>;
+    using Sh = Shape<NB, MB, TCONV, KS == 1>;
     constexpr int CS = Sh::CS, NCH = Sh::NCH, THREADS = Sh::THREADS;
     const int nst = geo.nstages;
     // barriers: [0, S) full, [S, 2S) empty, 2S + {0,1} accumulator full, 2S + {2,3} accumulator empty, 2S + 4 weights
@@ -498,7 +501,7 @@ template <int NB, int MB, int STRIDE> constexpr int tmem_cols() {      // two ac
 }
 
 template <int CINP, int NB, int MB, int DIL, int KS, int STRIDE, class Epi>
-__global__ void __launch_bounds__((Shape<NB, MB, STRIDE == 0>::THREADS), 1)
+__global__ void __launch_bounds__((Shape<NB, MB, STRIDE == 0, KS == 1>::THREADS), 1)
 tc5p_conv_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Epi epi,
                  const WSel wsel, const Geo geo, int* err_flag) {
     extern __shared__ unsigned char smem_dyn[];
@@ -578,7 +581,7 @@ int launch_mb(const char* name, const Split& in, const Epi& epi, const WSel& wse
     static int smem_ok = 0;
     IMVS_TRY(ensure_dynamic_smem(kern, smem, &smem_ok));
     const int grid = std::min(g.n_tiles, grid_limit());
-    if (launch_k(kern, dim3(grid), dim3(Shape<NB, MB, STRIDE == 0>::THREADS), smem, st, mh, ml, epi, wsel, g, err_flag) != cudaSuccess)
+    if (launch_k(kern, dim3(grid), dim3(Shape<NB, MB, STRIDE == 0, KS == 1>::THREADS), smem, st, mh, ml, epi, wsel, g, err_flag) != cudaSuccess)
         return fail("launch of %s failed: %s", name, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
