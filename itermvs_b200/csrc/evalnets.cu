@@ -4,6 +4,7 @@
 //   activations channels-last.
 #include "common.cuh"
 #include "mmaconv.cuh"
+#include "corrnet_tile.cuh"
 #ifndef CUSIM
 #include "tc5pconv.cuh"
 #endif
@@ -338,6 +339,28 @@ extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int sp
     float* x3 = c2 + (size_t)N * 2 * HW;    // [N][H/2][W/2][16]
     float* x4 = x3 + (size_t)N * 4 * HW;    // [N][H][W][8]
     const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
+    if (tune("CORR_TILE", 0) && sets[0].conv0.fp32 && (size_t)cdiv(H, ctile::T) <= 65535 && N <= 65535) {
+        // option (IMVS_TUNE_CORR_TILE=1; measured 76 us per pass against 66 us for the six mma.sync launches, profiles/README.md):
+        // one launch, a 32 x 32 tile resident in shared memory through all six layers (corrnet_tile.cuh), exact fp32
+        ctile::Params P{};
+        P.vol = vol;
+        for (int i = 0; i < 3; ++i) {
+            const imvs_corrnet_weights& c = sets[i];
+            const imvs_wpair* wp[6] = {&c.conv0, &c.conv1, &c.conv2, &c.conv3, &c.conv4, &c.conv5};
+            for (int l = 0; l < 6; ++l) {
+                IMVS_REQUIRE(wp[l]->fp32, "corrnet: fp32 weights missing");
+                P.w[i][l] = wp[l]->fp32;
+            }
+            P.b5[i] = c.conv5_b;
+        }
+        P.period = period; P.split1 = split1; P.split2 = split2;
+        P.out = out; P.bstride = out_batch_stride; P.pstride = out_pixel_stride;
+        P.N = N; P.H = H; P.W = W; P.tiles_x = cdiv(W, ctile::T); P.tiles_y = cdiv(H, ctile::T);
+        static int smem_ok = 0;
+        IMVS_TRY(ensure_dynamic_smem(ctile::corrnet_tile_kernel, ctile::SMEM_BYTES, &smem_ok));
+        IMVS_CUDA(launch_k(ctile::corrnet_tile_kernel, dim3(P.tiles_x, P.tiles_y, N), dim3(ctile::THREADS), ctile::SMEM_BYTES, st, P));
+        return 0;
+    }
 #ifndef CUSIM
     if (corrnet_tc5p_ready(sets)) {
         // optional (IMVS_TUNE_TC5P_CORR=1): all six layers on the TMA + tcgen05 kernel; activations as fp16 hi / lo split planes, the inputs of the two

@@ -82,7 +82,9 @@ extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
     const int head = (conv_passes() == 4 && tune("HEADFUSED", 1)) ? 2 : 4;
     const int gru = (conv_passes() == 4 && tune("TC5P_GRU", 1)) ? 3 : 2;
 #endif
-    return 20 + head + (7 + gru + head) * pb->iterations;
+    // CorrNet is six launches per pass (one with IMVS_TUNE_CORR_TILE=1 / CORR_FUSED=1, seven with TC5P_CORR=1: experiment switches)
+    const int corr = tune("CORR_TILE", 0) ? 1 : 6;
+    return 14 + corr + head + (1 + corr + gru + head) * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,

@@ -25,7 +25,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libitermvs_sim.so")
 SIM_SOURCES = ["warp.cu", "warpcorr.cu", "warpcorr_bwd.cu", "fusion.cu", "evalnets.cu", "update.cu", "upsample.cu", "forward.cu",
                "featurenet.cu", "imageprep.cu"]
-HEADERS = ["common.cuh", "sampling.cuh", "mmaconv.cuh", "tc5conv.cuh", "headfused.cuh"]
+HEADERS = ["common.cuh", "sampling.cuh", "mmaconv.cuh", "tc5conv.cuh", "headfused.cuh", "corrnet_tile.cuh"]
 def _isa_flags():
     """F16C / FMA when this CPU has them (hardware half<->float conversion for the tensor-core emulation)."""
     try:

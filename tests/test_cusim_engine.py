@@ -66,6 +66,15 @@ def test_conv_stages_on_cpu(model, stage_kats, dtu_weights):
     G.test_corrnet_pvw_gru_hinit_golden(CPU, stage_kats, model)
     G.test_heads_probability_and_window_regression(CPU, stage_kats, model, dtu_weights)
     G.test_window_regression_edges(CPU, model)
+    # the tile-resident single-launch CorrNet (csrc/corrnet_tile.cuh, IMVS_TUNE_CORR_TILE=1) against the same KATs
+    os.environ["IMVS_TUNE_CORR_TILE"] = "1"
+    try:
+        ev = model.iter_mvs.evaluation
+        for i in range(3):
+            out = ev.corr_conv1[i](G.T(stage_kats["corrnet_in"]))
+            assert G.maxerr(out, G.T(stage_kats[f"corrnet{i}_out"])) < 2e-5
+    finally:
+        del os.environ["IMVS_TUNE_CORR_TILE"]
 
 
 def test_upsample_outputs_on_cpu(model, dtu_weights):

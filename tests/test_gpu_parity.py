@@ -790,12 +790,13 @@ def test_conv3x3_tma_tcgen05_vs_fp64(dev, cin, cout, dil, shape):
         assert err < 5e-6 * max(scale, 1.0), err
 
 
-@pytest.mark.parametrize("switch", ["TC5P_CORR", "CORR_FUSED"])
+@pytest.mark.parametrize("switch", ["TC5P_CORR", "CORR_FUSED", "CORR_TILE"])
 def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch, switch):
     """CorrNet with all six layers on the persistent TMA + tcgen05 kernel: 8-channel layers through an aliased K chunk, the two
     stride-2 layers on parity planes, the two transposed layers with four parity accumulators, three weight sets chosen per
     slice.  IMVS_TUNE_TC5P_CORR=1: one launch per layer; IMVS_TUNE_CORR_FUSED=1: the whole pass as ONE cooperative launch with
-    grid-wide barriers between the layers.  Against the reference's KAT and, in the three-set batched form the iterations use
+    grid-wide barriers between the layers; IMVS_TUNE_CORR_TILE=1: one launch that keeps a 32 x 32 tile in shared memory through
+    all six layers (exact fp32 FFMA, corrnet_tile.cuh).  Against the reference's KAT and, in the three-set batched form the iterations use
     (graph-captured as the serving loop does), against the default mma.sync path."""
     from itermvs_b200 import _lib
     k = stage_kats
