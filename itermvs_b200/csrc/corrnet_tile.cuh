@@ -22,7 +22,7 @@ namespace ctile {
 
 constexpr int T = 32;                                  // output tile (full resolution)
 constexpr int IN_R = 45, C0_R = 43, C1_R = 21, C2_R = 10, X3_R = 18, X4_R = 34;
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;
 constexpr int W0 = 9 * 8 * 8, W1 = 9 * 8 * 16, W2 = 9 * 16 * 32, W3 = 9 * 32 * 16, W4 = 9 * 16 * 8, W5 = 9 * 8 * 8;
 constexpr int W_FLOATS = W0 + W1 + W2 + W3 + W4 + W5;                      // 12 672
 constexpr int BUF_A = 8 * IN_R * IN_R;                                     // input window; later x3 | x4
@@ -41,7 +41,8 @@ struct Params {
     int N, H, W, tiles_x, tiles_y;
 };
 
-constexpr int PX = 4;            // output pixels of a row per work item: a weight vector is read once for PX pixels
+// PX = output pixels of a COLUMN per work item (a weight vector is read once for PX pixels; lanes = consecutive columns); chosen per layer so that a layer has
+// about one work item per thread: 473 / 462 / 400 / 360 / 340 / 512 items for the six layers
 
 struct W8 { float4 a, b; };
 __device__ __forceinline__ W8 ldw8(const float* __restrict__ w) {          // eight output channels' weights: two broadcast 16-byte reads
@@ -54,43 +55,43 @@ __device__ __forceinline__ void fma8(float (&acc)[8], float v, const W8& w) {
 
 // stride-1 / stride-2 3x3 convolution + ReLU on shared-memory planes: out[co][r][c] = relu(sum in[ci][S r + ky][S c + kx] w[tap][ci][co]),
 // zero where the output position (gy0 + r, gx0 + c) lies outside the Hl x Wl image of its resolution.
-// item = (8 couts, row, strip of PX columns): per (ci, ky) S * (PX - 1) + 3 input reads and 3 x 2 weight reads feed 3 * PX * 8 FMAs.
-// (Reads past a row's / plane's end stay inside the shared-memory allocation and only feed outputs that are not stored.)
-template <int CIN, int COUT, int S>
+// item = (8 couts, strip of PX ROWS, column): consecutive lanes = consecutive columns, so the plane reads are conflict-free
+// (stride S words); per (ci, kx) a column of S (PX - 1) + 3 inputs and 3 x 2 broadcast weight reads feed 3 * PX * 8 FMAs.
+template <int CIN, int COUT, int S, int PX>
 __device__ __forceinline__ void conv_relu(const float* __restrict__ in, int IR, float* __restrict__ out, int OR_, const float* __restrict__ w,
                                           int gy0, int gx0, int Hl, int Wl) {
     constexpr int G = COUT / 8, NV = S * (PX - 1) + 3;
-    const int strips = (OR_ + PX - 1) / PX, n_items = G * OR_ * strips;
+    const int strips = (OR_ + PX - 1) / PX, n_items = G * strips * OR_;
     for (int item = threadIdx.x; item < n_items; item += THREADS) {
-        const int g = item / (OR_ * strips), q = item - g * OR_ * strips, r = q / strips, c0 = (q - r * strips) * PX;
+        const int g = item / (strips * OR_), q = item - g * strips * OR_, r0 = (q / OR_) * PX, c = q - (q / OR_) * OR_;
         float acc[PX][8];
 #pragma unroll
         for (int p = 0; p < PX; ++p)
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[p][k] = 0.f;
-        if ((unsigned)(gy0 + r) < (unsigned)Hl) {
+        if ((unsigned)(gx0 + c) < (unsigned)Wl) {
 #pragma unroll 1
             for (int ci = 0; ci < CIN; ++ci) {
                 const float* wp = w + ci * COUT + 8 * g;
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const float* ip = in + (ci * IR + S * r + ky) * IR + S * c0;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* ip = in + (ci * IR + S * r0) * IR + S * c + kx;
                     float v[NV];
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) v[i] = ip[i];
+                    for (int i = 0; i < NV; ++i) v[i] = (S * r0 + i < IR) ? ip[i * IR] : 0.f;      // rows below the window feed unsaved outputs only
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
+                    for (int ky = 0; ky < 3; ++ky) {
                         const W8 wv = ldw8(wp + (ky * 3 + kx) * CIN * COUT);
 #pragma unroll
-                        for (int p = 0; p < PX; ++p) fma8(acc[p], v[S * p + kx], wv);
+                        for (int p = 0; p < PX; ++p) fma8(acc[p], v[S * p + ky], wv);
                     }
                 }
             }
         }
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-            const int c = c0 + p;
-            if (c >= OR_) break;
+            const int r = r0 + p;
+            if (r >= OR_) break;
             const bool inside = (unsigned)(gy0 + r) < (unsigned)Hl && (unsigned)(gx0 + c) < (unsigned)Wl;
 #pragma unroll
             for (int k = 0; k < 8; ++k) out[((8 * g + k) * OR_ + r) * OR_ + c] = inside ? fmaxf(acc[p][k], 0.f) : 0.f;
@@ -100,44 +101,45 @@ __device__ __forceinline__ void conv_relu(const float* __restrict__ in, int IR, 
 
 // ConvTranspose2d(k 3, stride 2, padding 1, output_padding 1) + skip: out[co][r][c] = skip[co][r + so][c + so] +
 // sum over the (ky, kx) of (r, c)'s parity of in[ci][(r - ky) / 2 + 1][(c - kx) / 2 + 1] w[tap][ci][co].  Items are ordered by
-// parity class (a warp's lanes share their tap set); item = (8 couts, row, strip of PX columns of the class: c = 2 j + b).
-template <int CIN, int COUT>
+// parity class (a warp's lanes share their tap set); item = (8 couts, strip of PX rows of the class: r = 2 i + a, column c = 2 j + b),
+// consecutive lanes = consecutive j: conflict-free input reads.
+template <int CIN, int COUT, int PX>
 __device__ __forceinline__ void tconv_skip(const float* __restrict__ in, int IR, float* __restrict__ out, int OR_, const float* __restrict__ skip,
                                            int SR, int so, const float* __restrict__ w, int gy0, int gx0, int Hl, int Wl) {
     constexpr int G = COUT / 8;
-    const int half = OR_ / 2, strips = (half + PX - 1) / PX, per_class = G * half * strips;
+    const int half = OR_ / 2, strips = (half + PX - 1) / PX, per_class = G * strips * half;
     for (int item = threadIdx.x; item < 4 * per_class; item += THREADS) {
-        const int cls = item / per_class, q0 = item - cls * per_class, g = q0 / (half * strips), q = q0 - g * half * strips;
-        const int a = cls >> 1, b = cls & 1, r = 2 * (q / strips) + a, j0 = (q % strips) * PX;
+        const int cls = item / per_class, q0 = item - cls * per_class, g = q0 / (strips * half), q = q0 - g * strips * half;
+        const int a = cls >> 1, b = cls & 1, i0 = (q / half) * PX, j = q % half, c = 2 * j + b;
         float acc[PX][8];
 #pragma unroll
         for (int p = 0; p < PX; ++p)
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[p][k] = 0.f;
-        if ((unsigned)(gy0 + r) < (unsigned)Hl) {
+        if ((unsigned)(gx0 + c) < (unsigned)Wl) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                if (i == 1 && a == 1) break;                      // r odd: ky = 1 only; r even: ky = 0 and 2
-                const int ky = a ? 1 : 2 * i, iy = (r - ky) / 2 + 1;
+            for (int jj = 0; jj < 2; ++jj) {
+                if (jj == 1 && b == 1) break;                     // c odd: kx = 1 only; c even: kx = 0 and 2
+                const int kx = b ? 1 : 2 * jj, ix = (c - kx) / 2 + 1;
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    if (jj == 1 && b == 1) break;
-                    const int kx = b ? 1 : 2 * jj, ix0 = (2 * j0 + b - kx) / 2 + 1;         // column of the strip's first pixel
-                    const float* ip = in + iy * IR + ix0;
+                for (int i = 0; i < 2; ++i) {
+                    if (i == 1 && a == 1) break;
+                    const int ky = a ? 1 : 2 * i, iy0 = (2 * i0 + a - ky) / 2 + 1;          // input row of the strip's first pixel
+                    const float* ip = in + iy0 * IR + ix;
                     const float* wp = w + (ky * 3 + kx) * CIN * COUT + 8 * g;
 #pragma unroll 2
                     for (int ci = 0; ci < CIN; ++ci) {
                         const W8 wv = ldw8(wp + ci * COUT);
 #pragma unroll
-                        for (int p = 0; p < PX; ++p) fma8(acc[p], ip[ci * IR * IR + p], wv);
+                        for (int p = 0; p < PX; ++p) fma8(acc[p], (iy0 + p < IR) ? ip[ci * IR * IR + p * IR] : 0.f, wv);
                     }
                 }
             }
         }
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-            const int j = j0 + p, c = 2 * j + b;
-            if (j >= half) break;
+            const int i = i0 + p, r = 2 * i + a;
+            if (i >= half) break;
             const bool inside = (unsigned)(gy0 + r) < (unsigned)Hl && (unsigned)(gx0 + c) < (unsigned)Wl;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -189,44 +191,45 @@ __global__ void __launch_bounds__(THREADS, 1) corrnet_tile_kernel(const Params P
     const float* w3 = w2 + W2;
     const float* w4 = w3 + W3;
     const float* w5 = w4 + W4;
-    conv_relu<8, 8, 1>(bufA, IN_R, c0, C0_R, w0, y0 - 7, x0 - 7, H, W);                              // itermvs.py:369
+    conv_relu<8, 8, 1, 4>(bufA, IN_R, c0, C0_R, w0, y0 - 7, x0 - 7, H, W);                              // itermvs.py:369
     __syncthreads();
-    conv_relu<8, 16, 2>(c0, C0_R, c1, C1_R, w1, h0 - 3, hx0 - 3, H / 2, W / 2);                     // :370
+    conv_relu<8, 16, 2, 2>(c0, C0_R, c1, C1_R, w1, h0 - 3, hx0 - 3, H / 2, W / 2);                     // :370
     __syncthreads();
-    conv_relu<16, 32, 2>(c1, C1_R, c2, C2_R, w2, q0 - 1, qx0 - 1, H / 4, W / 4);                    // :371
+    conv_relu<16, 32, 2, 1>(c1, C1_R, c2, C2_R, w2, q0 - 1, qx0 - 1, H / 4, W / 4);                    // :371
     __syncthreads();
-    tconv_skip<32, 16>(c2, C2_R, x3, X3_R, c1, C1_R, 2, w3, h0 - 1, hx0 - 1, H / 2, W / 2);         // :373  (bufA's input window is dead)
+    tconv_skip<32, 16, 2>(c2, C2_R, x3, X3_R, c1, C1_R, 2, w3, h0 - 1, hx0 - 1, H / 2, W / 2);         // :373  (bufA's input window is dead)
     __syncthreads();
-    tconv_skip<16, 8>(x3, X3_R, x4, X4_R, c0, C0_R, 6, w4, y0 - 1, x0 - 1, H, W);                   // :375
+    tconv_skip<16, 8, 4>(x3, X3_R, x4, X4_R, c0, C0_R, 6, w4, y0 - 1, x0 - 1, H, W);                   // :375
     __syncthreads();
     // conv5: 8 -> 1, + bias, scattered to the caller's layout (:378)
     const float bias = ldg(P.b5[set]);
-    for (int i = tid; i < T * (T / PX); i += THREADS) {
-        const int r = i / (T / PX), c0 = (i - r * (T / PX)) * PX, gy = y0 + r;
-        if (gy >= H) continue;
+    constexpr int PX = 2;
+    for (int i = tid; i < (T / PX) * T; i += THREADS) {
+        const int r0 = (i / T) * PX, c = i - (i / T) * T, gx = x0 + c;
+        if (gx >= W) continue;
         float acc[PX];
 #pragma unroll
         for (int p = 0; p < PX; ++p) acc[p] = 0.f;
 #pragma unroll 2
         for (int ci = 0; ci < 8; ++ci) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const float* ip = x4 + (ci * X4_R + r + ky) * X4_R + c0;
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* ip = x4 + (ci * X4_R + r0) * X4_R + c + kx;
                 float v[PX + 2];
 #pragma unroll
-                for (int k = 0; k < PX + 2; ++k) v[k] = ip[k];
+                for (int k = 0; k < PX + 2; ++k) v[k] = ip[k * X4_R];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
+                for (int ky = 0; ky < 3; ++ky) {
                     const float wv = w5[((ky * 3 + kx) * 8 + ci) * 8];
 #pragma unroll
-                    for (int p = 0; p < PX; ++p) acc[p] = fmaf(v[p + kx], wv, acc[p]);
+                    for (int p = 0; p < PX; ++p) acc[p] = fmaf(v[p + ky], wv, acc[p]);
                 }
             }
         }
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-            const int gx = x0 + c0 + p;
-            if (gx < W) P.out[(size_t)(n / P.period) * P.bstride + ((size_t)gy * W + gx) * P.pstride + rr] = acc[p] + bias;
+            const int gy = y0 + r0 + p;
+            if (gy < H) P.out[(size_t)(n / P.period) * P.bstride + ((size_t)gy * W + gx) * P.pstride + rr] = acc[p] + bias;
         }
     }
 }
