@@ -267,6 +267,91 @@ fnet_conv0_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, c
     }
 }
 
+// The same layer with FOUR vertically adjacent pixels per thread (32 x 16 tile): a tap's eight weights are read once for four
+// pixels (864 FFMA per 54 + 54 shared-memory reads instead of 432 per 54 + 36), 1.9x fewer instructions per pixel -- and
+// measured slower on B200 (51.5 us against 41.1 us: half as many CTAs / resident warps for a kernel that is bound by its
+// load -> barrier -> compute -> store latency, not by issue slots).  Kept behind IMVS_TUNE_CONV0R4=1.
+constexpr int C4_TH = 16;
+template <class PixT, bool PSPLIT>
+__global__ void __launch_bounds__(128)
+fnet_conv0_r4_kernel(const PixT* __restrict__ img, const float* __restrict__ wgt, const float* __restrict__ bias,
+                     float* __restrict__ out, int H, int W) {
+    __shared__ float sI[3][C4_TH + 2][C0_PITCH];
+    __shared__ __align__(16) float sW[27][8];       // [(ky*3 + kx)*3 + cin][cout]
+    __shared__ __align__(16) float sB[8];
+    const int tid = threadIdx.x, n = blockIdx.z;
+    const int x0 = blockIdx.x * C0_TW, y0 = blockIdx.y * C4_TH;
+    pdl_trigger();
+    for (int i = tid; i < 27 * 8; i += 128) {       // packed weight: [tap][8 cin (3 used)][8 cout]
+        const int row = i >> 3, co = i & 7, tap = row / 3, c = row % 3;
+        sW[row][co] = ldg(wgt + (tap * 8 + c) * 8 + co);
+    }
+    if (tid < 8) sB[tid] = ldg(bias + tid);
+    pdl_wait();
+    const size_t plane = (size_t)H * W;
+    const PixT* src = img + (size_t)n * 3 * plane;
+    for (int i = tid; i < 3 * (C4_TH + 2) * C0_PITCH; i += 128) {
+        const int c = i / ((C4_TH + 2) * C0_PITCH), rem = i % ((C4_TH + 2) * C0_PITCH);
+        const int r = rem / C0_PITCH, col = rem % C0_PITCH;
+        const int y = y0 - 1 + r, x = x0 - 1 + col;
+        sI[c][r][col] = (y >= 0 && y < H && x >= 0 && x < W) ? c0_pixel(src + c * plane + (size_t)y * W + x) : 0.f;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;          // rows 4 ty .. 4 ty + 3 of the tile
+    float acc[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[r][k] = sB[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v[6][3];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[r][k] = sI[c][4 * ty + r][tx + k];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 wa = *reinterpret_cast<const float4*>(&sW[(ky * 3 + kx) * 3 + c][0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&sW[(ky * 3 + kx) * 3 + c][4]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float p = v[r + ky][kx];
+                    acc[r][0] = fmaf(p, wa.x, acc[r][0]); acc[r][1] = fmaf(p, wa.y, acc[r][1]); acc[r][2] = fmaf(p, wa.z, acc[r][2]); acc[r][3] = fmaf(p, wa.w, acc[r][3]);
+                    acc[r][4] = fmaf(p, wb.x, acc[r][4]); acc[r][5] = fmaf(p, wb.y, acc[r][5]); acc[r][6] = fmaf(p, wb.z, acc[r][6]); acc[r][7] = fmaf(p, wb.w, acc[r][7]);
+                }
+            }
+    }
+    const int x = x0 + tx;
+    if (x >= W) return;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int y = y0 + 4 * ty + r;
+        if (y >= H) break;
+        const float* a = acc[r];
+        if constexpr (PSPLIT) {
+#ifndef CUSIM
+            uint4* ohi = reinterpret_cast<uint4*>(out);
+            uint4* olo = ohi + (size_t)gridDim.z * H * W;            // 16-byte units: N * H * W pixels x one 8-channel chunk
+            uint4 h, l;
+            split_f16(make_float2(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f)), h.x, l.x);
+            split_f16(make_float2(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f)), h.y, l.y);
+            split_f16(make_float2(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f)), h.z, l.z);
+            split_f16(make_float2(fmaxf(a[6], 0.f), fmaxf(a[7], 0.f)), h.w, l.w);
+            const size_t idx = tc5p::parity_index(n, y, x, 0, 1, H, W);
+            ohi[idx] = h;
+            olo[idx] = l;
+#endif
+        } else {
+            float4* o = reinterpret_cast<float4*>(out + (((size_t)n * H + y) * W + x) * 8);
+            o[0] = make_float4(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f), fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
+            o[1] = make_float4(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f), fmaxf(a[6], 0.f), fmaxf(a[7], 0.f));
+        }
+    }
+}
+
 struct FnetBuffers {
     float *a0, *l1[4], *l2[4], *l3[4], *intra2, *intra1;
     float *l1s, *l2s, *l3s, *intra2s;     // split-plane copies (tc5pconv.cuh) of the trunk outputs and of intra2, which are also read as fp32
@@ -530,11 +615,21 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
         IMVS_REQUIRE(w->w[0].fp32 && w->b[0], "featurenet_forward: conv1 weights missing");
         dim3 grid(cdiv(W, C0_TW), cdiv(H, C0_TH), N);
         IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "fnet.conv1: grid too large");
+        const bool r4 = tune("CONV0R4", 0) != 0;         // four rows per thread (32 x 16 tiles): measured SLOWER (51 vs 41 us, gpurun call r2c44), off
+        dim3 grid4(cdiv(W, C0_TW), cdiv(H, C4_TH), N);
         if (s2p) {      // output as fp16 hi / lo parity planes (same bytes, in a0)
 #ifndef CUSIM
-            if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char, true>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
-            else IMVS_CUDA(launch_k(fnet_conv0_kernel<float, true>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+            if (r4) {
+                if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_r4_kernel<unsigned char, true>, grid4, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
+                else IMVS_CUDA(launch_k(fnet_conv0_r4_kernel<float, true>, grid4, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+            } else {
+                if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char, true>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
+                else IMVS_CUDA(launch_k(fnet_conv0_kernel<float, true>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
+            }
 #endif
+        } else if (r4) {
+            if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_r4_kernel<unsigned char, false>, grid4, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
+            else IMVS_CUDA(launch_k(fnet_conv0_r4_kernel<float, false>, grid4, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
         } else {
             if (imgs_u8) IMVS_CUDA(launch_k(fnet_conv0_kernel<unsigned char>, grid, dim3(128), 0, st, imgs_u8, w->w[0].fp32, w->b[0], b.a0, H, W));
             else IMVS_CUDA(launch_k(fnet_conv0_kernel<float>, grid, dim3(128), 0, st, imgs, w->w[0].fp32, w->b[0], b.a0, H, W));
