@@ -358,6 +358,16 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
+        # one slice of the host cores per rank (submit loop + CUDA driver threads): 8 ranks on one NUMA node otherwise migrate
+        # over all cores while they feed 8 x 20 GB/s of pinned-memory H2D copies (IMVS_BENCH_PIN=0 disables)
+        if os.environ.get("IMVS_BENCH_PIN", "1") != "0" and hasattr(os, "sched_setaffinity"):
+            try:
+                cpus = sorted(os.sched_getaffinity(0))
+                per = len(cpus) // world
+                if per >= 1:
+                    os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+            except OSError:
+                pass
     _lib.set_conv_passes(args.passes)
 
     model = build_model(test=True).to(dev).eval()
