@@ -358,9 +358,10 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
-        # one slice of the host cores per rank (submit loop + CUDA driver threads): 8 ranks on one NUMA node otherwise migrate
-        # over all cores while they feed 8 x 20 GB/s of pinned-memory H2D copies (IMVS_BENCH_PIN=0 disables)
-        if os.environ.get("IMVS_BENCH_PIN", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        # optional (IMVS_BENCH_PIN=1): one slice of the host cores per rank.  Measured at 8 GPUs (gpurun calls r2c34): e2e with fp32
+        # images 8085 -> 7824 refs/s, with 8-bit images 8269 -> 8349, device-resident 8366 -> 8349: no clear gain, off by default --
+        # the fp32 e2e leg is bound by 8 x 21 GB/s of pinned-memory reads from one NUMA node, not by thread placement
+        if os.environ.get("IMVS_BENCH_PIN", "0") == "1" and hasattr(os, "sched_setaffinity"):
             try:
                 cpus = sorted(os.sched_getaffinity(0))
                 per = len(cpus) // world
