@@ -90,6 +90,11 @@ struct EpiLateral {
     const float* bias;       // [C]
     tc5p::Split coarse;      // [N][C/8][H/2][W/2][8] split planes
     int H, W;
+    // the coarse map as fp32 in the same chunk-planar order, when its producer wrote one (IMVS_TUNE_LAT32P=1): no hi + lo
+    // reconstruction (96 of the ~200 instructions per pixel and 8-channel chunk), same coalesced reads -- measured: inner1
+    // 48.5 -> 49.2 us, inner2 16.7 -> 18.3 us (gpurun call r2c46), so the split planes stay the source
+    const float* coarse32p = nullptr;
+    float* out32p = nullptr; // this stage's output in that order (coarse map of the next lateral stage) or null
     template <int NCH> struct Pre {};
     template <int NB, int NCH>
     __device__ __forceinline__ void prefetch(int, int, int, int, Pre<NCH>&) const {}
@@ -119,12 +124,21 @@ struct EpiLateral {
             float* x = v + 8 * j;
             const size_t cb = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * cplane;
             const size_t i00 = cb + (size_t)h0 * Wc + w0, i01 = cb + (size_t)h0 * Wc + w1, i10 = cb + (size_t)h1 * Wc + w0, i11 = cb + (size_t)h1 * Wc + w1;
-            const uint4 ah = __ldg(chi + i00), al = __ldg(clo + i00), bh = __ldg(chi + i01), bl = __ldg(clo + i01);
-            const uint4 ch = __ldg(chi + i10), cl = __ldg(clo + i10), dh = __ldg(chi + i11), dl = __ldg(clo + i11);
             const float4 bi0 = ldg4(bias + c0 + 8 * j), bi1 = ldg4(bias + c0 + 8 * j + 4);
             const float bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
             float a[8], b[8], c[8], d[8];
-            unpack8(ah, al, a); unpack8(bh, bl, b); unpack8(ch, cl, c); unpack8(dh, dl, d);
+            if (coarse32p) {
+                const float4* cp = reinterpret_cast<const float4*>(coarse32p);
+                auto ld8 = [&](size_t i, float (&o)[8]) {
+                    const float4 u = __ldg(cp + 2 * i), w = __ldg(cp + 2 * i + 1);
+                    o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w; o[4] = w.x; o[5] = w.y; o[6] = w.z; o[7] = w.w;
+                };
+                ld8(i00, a); ld8(i01, b); ld8(i10, c); ld8(i11, d);
+            } else {
+                const uint4 ah = __ldg(chi + i00), al = __ldg(clo + i00), bh = __ldg(chi + i01), bl = __ldg(clo + i01);
+                const uint4 ch = __ldg(chi + i10), cl = __ldg(clo + i10), dh = __ldg(chi + i11), dl = __ldg(clo + i11);
+                unpack8(ah, al, a); unpack8(bh, bl, b); unpack8(ch, cl, c); unpack8(dh, dl, d);
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 // same association as EpiAddUp2 / the oracle: up + (conv + bias)
@@ -139,6 +153,11 @@ struct EpiLateral {
             const size_t idx = ((size_t)n * (NB / 8) + (c0 / 8 + j)) * plane + pix;
             reinterpret_cast<uint4*>(out.hi)[idx] = h;
             reinterpret_cast<uint4*>(out.lo)[idx] = l;
+            if (out32p) {
+                float4* o = reinterpret_cast<float4*>(out32p) + idx * 2;
+                o[0] = make_float4(x[0], x[1], x[2], x[3]);
+                o[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
         }
         if (out32) {
             float* o = out32 + ((size_t)n * plane + pix) * NB + c0;
@@ -446,7 +465,7 @@ static int res_stage_p(const imvs_featurenet_weights* w, int L, const float* x, 
 // and / or parity planes for the next stage (trunk_parity), whichever are non-null.  H, W: the stage's OUTPUT size.
 template <int CI, int CO>
 static int res_stage_p2(const imvs_featurenet_weights* w, int L, const tc5p::Split& xp, float* const buf[4], float* trunk32,
-                        float* trunk_split, float* trunk_parity, int N, int H, int W, cudaStream_t st) {
+                        float* trunk_split, float* trunk_parity, int N, int H, int W, cudaStream_t st, float* trunk32p = nullptr) {
     const size_t elems = (size_t)N * H * W * CO;
     const tc5p::Split y1 = tc5p::split_at(buf[0], elems), ds = tc5p::split_at(buf[1], elems), b0 = tc5p::split_at(buf[2], elems);
     const tc5p::Split none{nullptr, nullptr}, ts = trunk_split ? tc5p::split_at(trunk_split, elems) : none,
@@ -464,7 +483,7 @@ static int res_stage_p2(const imvs_featurenet_weights* w, int L, const tc5p::Spl
     }
     IMVS_TRY((tc5p::launch<CO, CO>("fnet.block0.conv2", y1, tc5p::Epi{b0, nullptr, ds, w->b[L + 1], H, W, 1}, w->w[L + 1].f16ummai, N, H, W, flag, st)));
     IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv1", b0, tc5p::Epi{y1, nullptr, none, w->b[L + 3], H, W, 1}, w->w[L + 3].f16ummai, N, H, W, flag, st)));
-    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, trunk32, b0, w->b[L + 4], H, W, 1, tp}, w->w[L + 4].f16ummai, N, H, W, flag, st)));
+    IMVS_TRY((tc5p::launch<CO, CO>("fnet.block1.conv2", y1, tc5p::Epi{ts, trunk32, b0, w->b[L + 4], H, W, 1, tp, 0, trunk32p}, w->w[L + 4].f16ummai, N, H, W, flag, st)));
     return 0;
 }
 
@@ -647,7 +666,7 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
             // trunk of stage 1 / 2: split planes for the lateral 1x1 and parity planes (in the fp32 trunk's buffer) for the next stage
             IMVS_TRY((res_stage_p2<8, 16>(w, 1, tc5p::split_at(b.a0, (size_t)N * H * W * 8), b.l1, nullptr, b.l1s, b.l1[3], N, H1, W1, st)));
             IMVS_TRY((res_stage_p2<16, 32>(w, 6, tc5p::split_at(b.l1[3], (size_t)N * H1 * W1 * 16), b.l2, nullptr, b.l2s, b.l2[3], N, H2, W2, st)));
-            IMVS_TRY((res_stage_p2<32, 48>(w, 11, tc5p::split_at(b.l2[3], (size_t)N * H2 * W2 * 32), b.l3, nullptr, b.l3s, nullptr, N, H3, W3, st)));   // s2p implies lat: no fp32 trunk needed
+            IMVS_TRY((res_stage_p2<32, 48>(w, 11, tc5p::split_at(b.l2[3], (size_t)N * H2 * W2 * 32), b.l3, nullptr, b.l3s, nullptr, N, H3, W3, st, b.l3[3])));   // + fp32 chunk-planar copy in l3[3]: coarse map of inner2
         } else {
             IMVS_TRY((res_stage_p<8, 16, true>(w, 1, b.a0, b.l1, b.l1s, N, H, W, st)));                 // layer1 -> l1[3]  [H/2][W/2][16] (+ split)
             IMVS_TRY((res_stage_p<16, 32, true>(w, 6, b.l1[3], b.l2, b.l2s, N, H1, W1, st)));           // layer2 -> l2[3]  [H/4][W/4][32] (+ split)
@@ -658,11 +677,12 @@ static int featurenet_forward_impl(const imvs_featurenet_weights* w, const float
                           i1s = tc5p::split_at(b.intra1, (size_t)N * H1 * W1 * 48);
         IMVS_TRY((tc5p::launch<48, 48>("fnet.output3", l3s, tc5p::Epi{none, fea3, none, w->b[16], H3, W3, 0}, w->w[16].f16ummai, N, H3, W3, flag, st)));
         // intra2 = up2(f3) + inner2(f2) (net.py:60): 1x1 on the tensor core, bilinear taps in the epilogue
-        if (lat) IMVS_TRY((tc5p::launch<32, 48, 1, true, 1>("fnet.inner2", l2s, EpiLateral{i2s, nullptr, w->b[17], l3s, H2, W2}, w->w[17].f16ummai, N, H2, W2, flag, st)));
+        const bool planar = s2p && (imgs_u8 || tune("CONV0", 1)) && tune("LAT32P", 0);      // fp32 chunk-planar coarse maps (in l3[3] / intra2): measured no gain (call r2c46), off
+        if (lat) IMVS_TRY((tc5p::launch<32, 48, 1, true, 1>("fnet.inner2", l2s, EpiLateral{i2s, nullptr, w->b[17], l3s, H2, W2, planar ? b.l3[3] : nullptr, planar ? b.intra2 : nullptr}, w->w[17].f16ummai, N, H2, W2, flag, st)));
         else IMVS_TRY((mma_conv<32, 48, 2, 4, 1, true>("fnet.inner2", in_nhwc(b.l2[3], H2, W2, 32), EpiAddUp2H{b.intra2, i2s, w->b[17], b.l3[3], H2, W2, 48},
                                                         WSets::single(w->w[17]), k1, N, 48, H2, W2, 1, st)));
         IMVS_TRY((tc5p::launch<48, 32>("fnet.output2", i2s, tc5p::Epi{none, fea2, none, w->b[18], H2, W2, 0}, w->w[18].f16ummai, N, H2, W2, flag, st)));
-        if (lat) IMVS_TRY((tc5p::launch<16, 48, 1, true, 1>("fnet.inner1", l1s, EpiLateral{i1s, nullptr, w->b[19], i2s, H1, W1}, w->w[19].f16ummai, N, H1, W1, flag, st)));
+        if (lat) IMVS_TRY((tc5p::launch<16, 48, 1, true, 1>("fnet.inner1", l1s, EpiLateral{i1s, nullptr, w->b[19], i2s, H1, W1, planar ? b.intra2 : nullptr, nullptr}, w->w[19].f16ummai, N, H1, W1, flag, st)));
         else IMVS_TRY((mma_conv<16, 48, 2, 4, 1, true>("fnet.inner1", in_nhwc(b.l1[3], H1, W1, 16), EpiAddUp2H{nullptr, i1s, w->b[19], b.intra2, H1, W1, 48},
                                                         WSets::single(w->w[19]), k1, N, 48, H1, W1, 1, st)));
         IMVS_TRY((tc5p::launch<48, 16>("fnet.output1", i1s, tc5p::Epi{none, fea1, none, w->b[20], H1, W1, 0}, w->w[20].f16ummai, N, H1, W1, flag, st)));

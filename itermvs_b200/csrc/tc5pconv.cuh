@@ -134,6 +134,7 @@ struct Epi {
     int H, W, relu;
     Split outp = {nullptr, nullptr};     // the same values as parity planes (operand of a following stride-2 layer) or null
     int kco = 0;             // 8-channel chunks of the output / residual tensors when fewer than NB / 8 (cout padded to 16); 0: NB / 8
+    float* out32p = nullptr; // the same values as fp32 in the chunk-planar order [N][NB/8][H][W][8] (coarse map of a lateral stage) or null
 
     template <int NCH> struct Pre { uint4 h[NCH / 8], l[NCH / 8]; };
     __device__ __forceinline__ bool wants_prefetch() const { return res.hi != nullptr; }
@@ -196,6 +197,11 @@ struct Epi {
                     reinterpret_cast<uint4*>(outp.hi)[idx] = h;
                     reinterpret_cast<uint4*>(outp.lo)[idx] = l;
                 }
+            }
+            if (out32p) {
+                float4* o = reinterpret_cast<float4*>(out32p) + (((size_t)n * KCo + (c0 / 8 + j)) * plane + pix) * 2;
+                o[0] = make_float4(x[0], x[1], x[2], x[3]);
+                o[1] = make_float4(x[4], x[5], x[6], x[7]);
             }
         }
         if (out32) {
