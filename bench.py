@@ -456,6 +456,18 @@ def main():
         total_ms = e0.elapsed_time(e1)
         ref_d = model(*rot[(args.steps - 1) % NROT])["depths_upsampled"]
         assert torch.equal(d_outs[(args.steps - 1) % nfl][0], ref_d), "in-flight replay differs from the plain forward"
+        # spread of the figure: the same K-step region twice more (reported next to `value`, which stays the first region)
+        repeat_ms = []
+        for _ in range(2):
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for k in range(args.steps):
+                sp.submit(*rot[k % NROT], *d_outs[k % nfl])
+            sp.drain()
+            r1.record()
+            barrier()
+            repeat_ms.append(r0.elapsed_time(r1))
     else:
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
@@ -550,6 +562,9 @@ def main():
     if e2e_u8 is not None:
         e2e_u8["value"] = replicas.aggregate_throughput(args.steps, e2e_u8.pop("ms"), device=dev)
     total_ms = replicas.max_over_ranks([total_ms], device=dev)[0]
+    value_repeats = None
+    if sp is not None:
+        value_repeats = [replicas.aggregate_throughput(args.steps, m, device=dev) for m in repeat_ms]
 
     mem_ours = torch.cuda.max_memory_allocated(dev)
     torch.cuda.reset_peak_memory_stats(dev)
@@ -663,6 +678,7 @@ def main():
                            "workspaces of all in-flight slots (FeatureNet + estimator), the rotating input sets, outputs"},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
         "wall_s_timed_region": t_wall,
+        "value_repeats": value_repeats,          # the same K-step timed region run twice more (spread of `value`)
     }
     if e2e_u8 is not None:
         line["e2e_uint8_images"] = {"value": e2e_u8["value"], "unit": "refs/s", "h2d_bytes_per_step": e2e_u8["h2d_bytes_per_step"],
