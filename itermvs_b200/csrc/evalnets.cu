@@ -432,24 +432,44 @@ extern "C" int imvs_corrnet(const imvs_corrnet_weights* sets, int period, int sp
     }
 #endif
     auto sel = [&](int which) { return sel_of(sets, period, split1, split2, which); };
-    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), EpiNHWC{c0, nullptr, nullptr, H, W, 8, 8, 1},
-                                            sel(0), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));
-    IMVS_TRY((mma_conv<8, 16, 2, 4, 2, true>("corrnet.conv1", in_nhwc(c0, H, W, 8), EpiNHWC{c1, nullptr, nullptr, H1, W1, 16, 16, 1},
-                                             sel(1), conv_tables(3, 2, 1, 8), N, 16, H1, W1, 1, st)));
-    IMVS_TRY((mma_conv<16, 32, 2, 4, 2, true>("corrnet.conv2", in_nhwc(c1, H1, W1, 16), EpiNHWC{c2, nullptr, nullptr, H2, W2, 32, 32, 1},
-                                              sel(2), conv_tables(3, 2, 1, 8), N, 32, H2, W2, 1, st)));
+    // tile-shape experiment for the two full-resolution layers (IMVS_TUNE_CORR_TILE05: rows per CTA = 8 (default), 16 as 4 warps x 4
+    // row-tiles, 16 as 8 warps x 2, 4 as 4 warps x 1)
+    const int t05 = tune("CORR_TILE05", 0);
+    const EpiNHWC e0{c0, nullptr, nullptr, H, W, 8, 8, 1};
+    if (t05 == 1) IMVS_TRY((mma_conv<8, 8, 4, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), e0, sel(0), conv_tables(3, 1, 1, 16), N, 8, H, W, 1, st)));
+    else if (t05 == 2) IMVS_TRY((mma_conv<8, 8, 2, 8, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), e0, sel(0), conv_tables(3, 1, 1, 16), N, 8, H, W, 1, st)));
+    else if (t05 == 3) IMVS_TRY((mma_conv<8, 8, 1, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), e0, sel(0), conv_tables(3, 1, 1, 4), N, 8, H, W, 1, st)));
+    else IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv0", in_nhwc(vol, H, W, 8), e0, sel(0), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));
     // conv3 / conv4: transposed convolutions, the four output parities as variants of one launch,
-    // + U-Net skips c1 / c0 (itermvs.py:374-377)
-    IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("corrnet.conv3", in_nhwc(c2, H2, W2, 32), EpiTconvNHWC{x3, c1, H2, W2, 16},
-                                              sel(3), tconv_tables(8), N, 16, H2, W2, 1, st)));
-    IMVS_TRY((mma_conv<16, 8, 2, 4, 1, true>("corrnet.conv4", in_nhwc(x3, H1, W1, 16), EpiTconvNHWC{x4, c0, H1, W1, 8},
-                                             sel(4), tconv_tables(8), N, 8, H1, W1, 1, st)));
+    // + U-Net skips c1 / c0 (itermvs.py:374-377).  IMVS_TUNE_CORR_TILEMID=1: 4-row instead of 8-row tiles for the coarse layers
+    if (tune("CORR_TILEMID", 0) == 1) {
+        IMVS_TRY((mma_conv<8, 16, 1, 4, 2, true>("corrnet.conv1", in_nhwc(c0, H, W, 8), EpiNHWC{c1, nullptr, nullptr, H1, W1, 16, 16, 1},
+                                                 sel(1), conv_tables(3, 2, 1, 4), N, 16, H1, W1, 1, st)));
+        IMVS_TRY((mma_conv<16, 32, 1, 4, 2, true>("corrnet.conv2", in_nhwc(c1, H1, W1, 16), EpiNHWC{c2, nullptr, nullptr, H2, W2, 32, 32, 1},
+                                                  sel(2), conv_tables(3, 2, 1, 4), N, 32, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<32, 16, 1, 4, 1, true>("corrnet.conv3", in_nhwc(c2, H2, W2, 32), EpiTconvNHWC{x3, c1, H2, W2, 16},
+                                                  sel(3), tconv_tables(4), N, 16, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<16, 8, 1, 4, 1, true>("corrnet.conv4", in_nhwc(x3, H1, W1, 16), EpiTconvNHWC{x4, c0, H1, W1, 8},
+                                                 sel(4), tconv_tables(4), N, 8, H1, W1, 1, st)));
+    } else {
+        IMVS_TRY((mma_conv<8, 16, 2, 4, 2, true>("corrnet.conv1", in_nhwc(c0, H, W, 8), EpiNHWC{c1, nullptr, nullptr, H1, W1, 16, 16, 1},
+                                                 sel(1), conv_tables(3, 2, 1, 8), N, 16, H1, W1, 1, st)));
+        IMVS_TRY((mma_conv<16, 32, 2, 4, 2, true>("corrnet.conv2", in_nhwc(c1, H1, W1, 16), EpiNHWC{c2, nullptr, nullptr, H2, W2, 32, 32, 1},
+                                                  sel(2), conv_tables(3, 2, 1, 8), N, 32, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<32, 16, 2, 4, 1, true>("corrnet.conv3", in_nhwc(c2, H2, W2, 32), EpiTconvNHWC{x3, c1, H2, W2, 16},
+                                                  sel(3), tconv_tables(8), N, 16, H2, W2, 1, st)));
+        IMVS_TRY((mma_conv<16, 8, 2, 4, 1, true>("corrnet.conv4", in_nhwc(x3, H1, W1, 16), EpiTconvNHWC{x4, c0, H1, W1, 8},
+                                                 sel(4), tconv_tables(8), N, 8, H1, W1, 1, st)));
+    }
     EpiCorrOut e5;
     e5.out = out;
     for (int i = 0; i < 3; ++i) e5.bias[i] = sets[i].conv5_b;
     e5.period = period; e5.split1 = split1; e5.split2 = split2;
     e5.bstride = out_batch_stride; e5.pstride = out_pixel_stride; e5.H = H; e5.W = W;
-    IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));
+    if (t05 == 1) IMVS_TRY((mma_conv<8, 8, 4, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), conv_tables(3, 1, 1, 16), N, 8, H, W, 1, st)));
+    else if (t05 == 2) IMVS_TRY((mma_conv<8, 8, 2, 8, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), conv_tables(3, 1, 1, 16), N, 8, H, W, 1, st)));
+    else if (t05 == 3) IMVS_TRY((mma_conv<8, 8, 1, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), conv_tables(3, 1, 1, 4), N, 8, H, W, 1, st)));
+    else IMVS_TRY((mma_conv<8, 8, 2, 4, 1, true>("corrnet.conv5", in_nhwc(x4, H, W, 8), e5, sel(5), conv_tables(3, 1, 1, 8), N, 8, H, W, 1, st)));
     return 0;
 }
 

@@ -520,13 +520,16 @@ __device__ __forceinline__ float pair_dot(const Taps48& T, int k, const float4& 
 __global__ void __launch_bounds__(WC_WARPS * 32, 6)
 warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ rt3,
                      const float* __restrict__ depth_min, const float* __restrict__ depth_max,
-                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D) {
+                     const float* __restrict__ samples, float* __restrict__ corr, int B, int V, int H3, int W3, int D, int vper) {
     __shared__ float4 s_recW[WC_WARPS][32];
     __shared__ int s_recO[WC_WARPS][32];
     __shared__ float sP[IMVS_MAX_VIEWS * 12];
     const int S = V - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z;
+    // blockIdx.z = (batch item, group of vper source views): finer blocks fill the last wave (1 280 four-warp blocks at 6 per SM
+    // are 1.44 waves at 640x512)
+    const int nsplit = (S + vper - 1) / vper;
+    const int b = blockIdx.z / nsplit, v_lo = (blockIdx.z % nsplit) * vper, v_hi = min(S, v_lo + vper);
     pdl_trigger();
     pdl_wait();
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) sP[i] = rt3[(size_t)b * S * 12 + i];
@@ -550,7 +553,7 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
         const float depth = samples ? ldg(samples + ((size_t)b * D + dc) * P3 + p)
                                     : 1.0f / (inv_max + ((float)dc / (float)(D - 1)) * (inv_min - inv_max));
         const int nd = min(32, D - d0);
-        for (int v = 0; v < S; ++v) {
+        for (int v = v_lo; v < v_hi; ++v) {
             const Tap tp = project_tap(sP + v * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
             float4 w;
             int off;
@@ -619,11 +622,13 @@ extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const flo
     IMVS_REQUIRE(H3 >= 2 && W3 >= 2 && D >= 2, "warpcorr_init: bad shape H3=%d W3=%d D=%d", H3, W3, D);
     IMVS_REQUIRE((double)V * H3 * W3 * 48 < 2147483647.0, "warpcorr_init: one batch item's pyramid exceeds 2^31 elements");
     IMVS_REQUIRE(aligned16(fea3) && aligned16(corr), "warpcorr_init: feature/corr pointers must be 16-byte aligned");
-    dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B);
+    // source views per block (IMVS_TUNE_WCI_VPER, 0 = all of them in one block)
+    const int S = V - 1, vt = tune("WCI_VPER", 0), vper = vt >= 1 && vt < S ? vt : S;
+    dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B * cdiv(S, vper));
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
     ApiScope api_;
     IMVS_CUDA(launch_k(warpcorr_init_kernel, grid, dim3(WC_WARPS * 32), 0, (cudaStream_t)stream, fea3, rt3, depth_min, depth_max,
-                       depth_samples, corr, B, V, H3, W3, D));
+                       depth_samples, corr, B, V, H3, W3, D, vper));
     return 0;
 }
 
@@ -653,8 +658,11 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     const int S = V - 1;
     // occupancy experiment (IMVS_TUNE_WC_WARPS): 24 warps x 1 block per SM (default, <= 85 registers), 32 warps x 1 block or
     // 16 warps x 2 blocks (both <= 64 registers: 32 resident warps per SM) -- profiles/ps_experiments_r02.md section 5
-    const int nw = tune("WC_WARPS", WC_ITER_WARPS) == 32 ? 32 : (tune("WC_WARPS", WC_ITER_WARPS) == 16 ? 16 : WC_ITER_WARPS);
-    auto kern = nw == 32 ? iter_kernel_for<32>(S) : (nw == 16 ? iter_kernel_for<16>(S) : iter_kernel_for<WC_ITER_WARPS>(S));
+    // 26 / 28 warps (72 registers): 104 items per SM at 640x512 are 4 full rounds instead of 4.33
+    const int nwt = tune("WC_WARPS", WC_ITER_WARPS);
+    const int nw = nwt == 32 || nwt == 16 || nwt == 26 || nwt == 28 ? nwt : WC_ITER_WARPS;
+    auto kern = nw == 32 ? iter_kernel_for<32>(S) : nw == 16 ? iter_kernel_for<16>(S) : nw == 26 ? iter_kernel_for<26>(S)
+              : nw == 28 ? iter_kernel_for<28>(S) : iter_kernel_for<WC_ITER_WARPS>(S);
     const size_t smem = iter_smem_bytes(S, nw);
     int dev = 0, sms = 0;
     IMVS_CUDA(cudaGetDevice(&dev));
