@@ -836,6 +836,35 @@ def test_corrnet_on_tma_tcgen05_kernel(dev, stage_kats, model, monkeypatch, swit
     assert torch.equal(o["depths_upsampled"], outs[0])
 
 
+@pytest.mark.parametrize("switch,value", [("CORR_TILE05", 1), ("CORR_TILE05", 2), ("CORR_TILE05", 3), ("CORR_TILEMID", 1),
+                                          ("WCI_VPER", 1), ("WCI_VPER", 2), ("WC_WARPS", 26), ("WC_WARPS", 28)])
+def test_launch_granularity_switches_are_bit_identical(dev, model, monkeypatch, switch, value):
+    """The launch-granularity switches measured in round 2 (profiles/ps_experiments_r02.md section 6, profiles/README.md: tile
+    shapes of CorrNet's mma.sync layers, source views of the init plane sweep split over blocks, 26 / 28 warps in the iteration
+    kernel) only change which CTA / warp computes an output, never its summation order: the pipeline's outputs are bit-identical.
+    Exception: CORR_TILEMID (one row-tile per warp) changes the number of accumulator sets of the fp16 3-product MMAs
+    (mmaconv.cuh: NACC), i.e. the order of three fp32 additions per output: equal to the last few ulp."""
+    from itermvs_b200 import _lib
+    s = make_sample(320, 256, n_src=3, batch=2, seed=11, scene="plane")
+    cu = lambda d: {kk: v.to(dev) for kk, v in d.items()}
+    outs = []
+    for flag in (str(value), None):
+        if flag is None:
+            monkeypatch.delenv("IMVS_TUNE_" + switch, raising=False)
+        else:
+            monkeypatch.setenv("IMVS_TUNE_" + switch, flag)
+        with torch.no_grad():
+            out = model(cu(s["imgs"]), cu(s["proj_matrices"]), s["depth_min"].to(dev), s["depth_max"].to(dev))
+        torch.cuda.synchronize()
+        outs.append({k: out[k].clone() for k in ("depths_upsampled", "confidence_upsampled")})
+    assert _lib.device_status(clear=True) == 0
+    for k in outs[0]:
+        if switch == "CORR_TILEMID":
+            assert float(((outs[0][k] - outs[1][k]).abs() / outs[1][k].abs().clamp_min(1e-3)).max()) < 1e-5, (switch, value, k)
+        else:
+            assert torch.equal(outs[0][k], outs[1][k]), (switch, value, k)
+
+
 def test_image_pyramid_and_prefetch_loader_on_device(dev, model, tmp_path):
     """f-4 on the GPU: (1) `imvs_image_pyramid_u8` -- raw 8-bit image -> 2 x / 255 - 1 -> cv2.resize(INTER_LINEAR) -> levels 1..3 --
     against OpenCV (1 ulp of the value: its SIMD / IPP paths may fuse a product); (2) `io.PrefetchLoader`: PNG files decoded on
