@@ -187,6 +187,22 @@ int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
                        const float* samples1, const float* samples2, const float* samples3, float* agg,
                        int B, int V, int H2, int W2, void* stream);
 
+/* The same two kernels on a level-3 pyramid PADDED to 64 floats per texel (written by imvs_pad_level3 from the
+ * [B][V][H3][W3][48] pyramid: correlation group g's six channels at floats 4g..4g+3 and 32+4g, 32+4g+1 of the texel, the other
+ * 16 floats zero): a tap is then one aligned 128-byte line + one 64-byte piece per lane group instead of three 64-byte pieces,
+ * and a lane owns its group (no regrouping).  Same arguments, results equal up to fp32 summation order.  Used by
+ * imvs_itermvs_forward with IMVS_TUNE_WC_PAD3=1 (the padded copy lives in the workspace).
+ * Reference: the same lines as imvs_warpcorr_init / imvs_warpcorr_iter (itermvs.py:11-19, 45-51, 86-120). */
+int imvs_pad_level3(const float* fea3, float* fea3p, int B, int V, int H3, int W3, void* stream);
+int imvs_warpcorr_init_padded(const float* fea3p, const float* rt3, const float* depth_min, const float* depth_max,
+                              const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream);
+int imvs_warpcorr_iter_padded(const float* fea1, const float* fea2, const float* fea3p,
+                              const float* rt1, const float* rt2, const float* rt3,
+                              const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
+                              const float* depth_min, const float* depth_max,
+                              const float* samples1, const float* samples2, const float* samples3, float* agg,
+                              int B, int V, int H2, int W2, void* stream);
+
 /* Backward of imvs_warpcorr_init with respect to the feature pyramid (the sampling grid carries no
  * gradient, module.py:77; source views receive grid_sample's input gradient, the reference view the gradient
  * through the product of itermvs.py:50).  Same inputs as the forward (the hypotheses are recomputed, nothing is

@@ -69,6 +69,9 @@ _SIGNATURES = {
     "imvs_pixel_view_weight": (ci, [PW, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "imvs_aggregate_init": (ci, [vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_warpcorr_iter": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "imvs_pad_level3": (ci, [vp, vp, ci, ci, ci, ci, vp]),
+    "imvs_warpcorr_init_padded": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "imvs_warpcorr_iter_padded": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_warpcorr_init_backward": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "imvs_warpcorr_iter_backward": (ci, [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "imvs_corrnet_scratch_floats": (sz, [ci, ci, ci]),

@@ -107,6 +107,18 @@ __device__ __forceinline__ float ldg(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// one (texel, correlation group g) of the padded level-3 pyramid (include/itermvs_b200.h: imvs_pad_level3): channels 6g..6g+5 of the
+// 48-float texel go to floats 4g..4g+3 and 32+4g, 32+4g+1 of the 64-float texel; floats 32+4g+2, +3 are zero
+__device__ __forceinline__ void pad_level3_item(const float* __restrict__ src, float* __restrict__ dst, size_t t) {
+    const size_t tx = t >> 3;
+    const int g = (int)(t & 7);
+    const float* s = src + tx * 48 + 6 * g;
+    const float2 a = ldg2(s), b = ldg2(s + 2), c = ldg2(s + 4);
+    float* d = dst + tx * 64 + 4 * g;
+    *reinterpret_cast<float4*>(d) = make_float4(a.x, a.y, b.x, b.y);
+    *reinterpret_cast<float4*>(d + 32) = make_float4(c.x, c.y, 0.f, 0.f);
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // F.interpolate(scale_factor=f, mode='bilinear', align_corners=False) source index (ATen

@@ -6,6 +6,8 @@
 namespace imvs {
 int tune(const char* name, int def);   // defined in warp.cu
 int conv_passes();
+int forward_prologue(const float* proj1, const float* proj2, const float* proj3, int B, int V, float* rt1, float* rt2, float* rt3,
+                     int* nan_flag, const float* fea3, float* fea3p, int H3, int W3, cudaStream_t st);      // warp.cu
 }
 
 namespace imvs {
@@ -14,6 +16,7 @@ struct Workspace {
     float *rt1, *rt2, *rt3;
     float *corr_init, *pvw_logits, *vw3, *vw2, *agg_init, *corrnet_scratch, *corr0;
     float *hinit_scratch, *hidden, *xbuf, *agg_iter, *gru_scratch, *head_scratch, *ups_scratch, *conf_buf;
+    float *fea3p;          // level-3 pyramid padded to 64 floats per texel (imvs_pad_level3)
     size_t total_floats;
 };
 
@@ -48,6 +51,7 @@ static Workspace carve(const imvs_problem& pb, float* base) {
     w.head_scratch = at(B * 384 * P2);
     w.ups_scratch = at(B * 64 * P2);
     w.conf_buf = at(B * P2);
+    w.fea3p = at(B * (S + 1) * P3 * 64);
     w.total_floats = c;
     return w;
 }
@@ -84,7 +88,8 @@ extern "C" int imvs_forward_launch_count(const imvs_problem* pb) {
 #endif
     // CorrNet is six launches per pass (one with IMVS_TUNE_CORR_TILE=1 / CORR_FUSED=1, seven with TC5P_CORR=1: experiment switches)
     const int corr = tune("CORR_TILE", 0) ? 1 : 6;
-    return 14 + corr + head + (1 + corr + gru + head) * pb->iterations;
+    // default: ONE prologue launch (three projection compositions + the padded level-3 copy); IMVS_TUNE_WC_PAD3=0: three compose launches
+    return (tune("WC_PAD3", 1) ? 12 : 14) + corr + head + (1 + corr + gru + head) * pb->iterations;
 }
 
 extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* w,
@@ -110,16 +115,28 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
     // x channels 11..15 are zero padding of the GRU's 43 -> 48 input channels
     IMVS_CUDA(cudaMemsetAsync(ws.xbuf, 0, sizeof(float) * (size_t)B * xb, (cudaStream_t)stream));
 
+    // default (IMVS_TUNE_WC_PAD3=0 switches it off): the plane-sweep kernels read level 3 from a copy padded to 256 bytes per texel
+    // (one full line + one 64-byte piece per tap and lane group instead of three half-used 64-byte pieces, a lane owns its correlation
+    // group: no regrouping shuffles; warpcorr.cu), written by the same launch that composes the projections
+    const bool pad3 = tune("WC_PAD3", 1) != 0;
     // K1 (module.py:78-90), hoisted: once per level instead of once per warp call
     { StageTimer tm_(ST_COMPOSE, stream);
-    IMVS_TRY(imvs_compose_projections(proj1, B, V, ws.rt1, nan_flag, stream));
-    IMVS_TRY(imvs_compose_projections(proj2, B, V, ws.rt2, nan_flag, stream));
-    IMVS_TRY(imvs_compose_projections(proj3, B, V, ws.rt3, nan_flag, stream));
+    if (pad3) {
+        IMVS_TRY(forward_prologue(proj1, proj2, proj3, B, V, ws.rt1, ws.rt2, ws.rt3, nan_flag, fea3, ws.fea3p, H3, W3, (cudaStream_t)stream));
+    } else {
+        IMVS_TRY(imvs_compose_projections(proj1, B, V, ws.rt1, nan_flag, stream));
+        IMVS_TRY(imvs_compose_projections(proj2, B, V, ws.rt2, nan_flag, stream));
+        IMVS_TRY(imvs_compose_projections(proj3, B, V, ws.rt3, nan_flag, stream));
+    }
     }
 
     // init evaluation (itermvs.py:270-271, 36-70)
     { StageTimer tm_(ST_WARPCORR_INIT, stream);
-    IMVS_TRY(imvs_warpcorr_init(fea3, ws.rt3, depth_min, depth_max, nullptr, ws.corr_init, B, V, H3, W3, D, stream));
+    if (pad3) {
+        IMVS_TRY(imvs_warpcorr_init_padded(ws.fea3p, ws.rt3, depth_min, depth_max, nullptr, ws.corr_init, B, V, H3, W3, D, stream));
+    } else {
+        IMVS_TRY(imvs_warpcorr_init(fea3, ws.rt3, depth_min, depth_max, nullptr, ws.corr_init, B, V, H3, W3, D, stream));
+    }
     }
     { StageTimer tm_(ST_PVW, stream);
     IMVS_TRY(imvs_pixel_view_weight(w, ws.corr_init, ws.pvw_logits, ws.vw3, ws.vw2, B, S, D, H3, W3, stream));
@@ -146,8 +163,12 @@ extern "C" int imvs_itermvs_forward(const imvs_problem* pb, const imvs_weights* 
         const bool last = (it == I - 1);
         // itermvs.py:288-295
         { StageTimer tm_(ST_WARPCORR_ITER, stream);
-        IMVS_TRY(imvs_warpcorr_iter(fea1, fea2, fea3, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xb, xp, ws.vw2, depth_min, depth_max,
-                                    nullptr, nullptr, nullptr, ws.agg_iter, B, V, H2, W2, stream));
+        if (pad3)
+            IMVS_TRY(imvs_warpcorr_iter_padded(fea1, fea2, ws.fea3p, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xb, xp, ws.vw2, depth_min, depth_max,
+                                               nullptr, nullptr, nullptr, ws.agg_iter, B, V, H2, W2, stream));
+        else
+            IMVS_TRY(imvs_warpcorr_iter(fea1, fea2, fea3, ws.rt1, ws.rt2, ws.rt3, ws.xbuf, xb, xp, ws.vw2, depth_min, depth_max,
+                                        nullptr, nullptr, nullptr, ws.agg_iter, B, V, H2, W2, stream));
         }
         { StageTimer tm_(ST_CORRNET, stream);   // -> x channels 1..10
         IMVS_TRY(imvs_corrnet(w->corrnet, IMVS_ITER_SLICES, 4, 8, ws.agg_iter, ws.xbuf + 1, xb, xp, ws.corrnet_scratch,

@@ -139,6 +139,40 @@ __global__ void compose_kernel(const float* __restrict__ proj, int B, int V, flo
     compose_one(proj + (size_t)(b * V) * 16, proj + (size_t)(b * V + 1 + s) * 16, out + (size_t)t * 12, nan_flag);
 }
 
+// First launch of imvs_itermvs_forward (forward.cu): the composed projections of the three levels (K1, module.py:78-90) and the
+// padded copy of the level-3 pyramid in ONE launch -- blocks [0, pad_blocks) pad 256 (texel, group) items each, the blocks
+// after them compose the 3 * B * S projection pairs.
+__global__ void __launch_bounds__(256)
+forward_prologue_kernel(const float* __restrict__ proj1, const float* __restrict__ proj2, const float* __restrict__ proj3, int B, int V,
+                        float* __restrict__ rt1, float* __restrict__ rt2, float* __restrict__ rt3, int* nan_flag,
+                        const float* __restrict__ fea3, float* __restrict__ fea3p, size_t texels, unsigned pad_blocks) {
+    pdl_trigger();
+    pdl_wait();
+    if (blockIdx.x < pad_blocks) {
+        const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t < texels * 8) pad_level3_item(fea3, fea3p, t);
+        return;
+    }
+    const int S = V - 1, n = B * S;
+    const int t = (int)(blockIdx.x - pad_blocks) * (int)blockDim.x + (int)threadIdx.x;
+    if (t >= 3 * n) return;
+    const int lvl = t / n, r = t - lvl * n, b = r / S, s = r - b * S;
+    const float* proj = lvl == 0 ? proj1 : (lvl == 1 ? proj2 : proj3);
+    float* out = lvl == 0 ? rt1 : (lvl == 1 ? rt2 : rt3);
+    compose_one(proj + (size_t)(b * V) * 16, proj + (size_t)(b * V + 1 + s) * 16, out + (size_t)r * 12, nan_flag);
+}
+
+int forward_prologue(const float* proj1, const float* proj2, const float* proj3, int B, int V, float* rt1, float* rt2, float* rt3,
+                     int* nan_flag, const float* fea3, float* fea3p, int H3, int W3, cudaStream_t st) {
+    const size_t texels = (size_t)B * V * H3 * W3;
+    const size_t pad_blocks = (texels * 8 + 255) / 256;
+    const int comp_blocks = cdiv(3 * B * (V - 1), 256);
+    IMVS_REQUIRE(pad_blocks + comp_blocks < 2147483647ull, "forward prologue: grid too large");
+    IMVS_CUDA(launch_k(forward_prologue_kernel, dim3((unsigned)(pad_blocks + comp_blocks)), dim3(256), 0, st, proj1, proj2, proj3, B, V,
+                       rt1, rt2, rt3, nan_flag, fea3, fea3p, texels, (unsigned)pad_blocks));
+    return 0;
+}
+
 __global__ void compose_pair_kernel(const float* __restrict__ src_proj, const float* __restrict__ ref_proj, int B,
                                     float* __restrict__ out, int* nan_flag) {
     pdl_trigger();

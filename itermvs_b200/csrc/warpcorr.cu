@@ -117,10 +117,10 @@ struct IterSmem {
 };
 
 // LVL 0: level 1 (C=16, feature map 2x the depth map), 1: level 2 (C=32), 2: level 3 (C=48, half size)
-template <int LVL, int ST>
+template <int LVL, int ST, bool PAD3 = false>
 __device__ __forceinline__ void iter_build(const IterParams& prm, const IterSmem& sm, int b, int y, int x0,
                                            float inv_min, float inv_max, float o0, float o1, float o2, float o3) {
-    constexpr int C = LVL == 0 ? 16 : (LVL == 1 ? 32 : 48);
+    constexpr int C = LVL == 0 ? 16 : (LVL == 1 ? 32 : (PAD3 ? 64 : 48));
     constexpr int R = LVL == 2 ? 2 : 4;
     constexpr int NPR = WC_NPX * R;
     constexpr float SC = LVL == 0 ? 2.f : (LVL == 1 ? 1.f : 0.5f);       // module.py:95-96 (Wf / W2, exact)
@@ -348,6 +348,94 @@ __device__ __forceinline__ void iter_gather_l3(const IterParams& prm, const Iter
     }
 }
 
+// ---- level 3 on the PADDED pyramid (imvs_pad_level3: 64 floats = 256 bytes per texel; correlation group g's six channels at
+// floats 4g..4g+3 and 32+4g, 32+4g+1, the rest zero).  Lane g of a sample's 8 lanes then loads ITS OWN group: one float4 + one
+// float2 per tap, every instruction one full aligned 128-byte line per sample (the 48-channel layout needs three 64-byte pieces
+// per tap -- half-used wavefronts -- and three shuffles per (pixel, hypothesis) to regroup).
+struct Row64 { float4 la, ra; float2 lb, rb; float wl, wr, wv; };
+__device__ __forceinline__ void fetch_row64(Row64& R, const IterSmem& sm, const float* __restrict__ base, int pitch, int t, int row) {
+    const float4 w = sm.recW[t];
+    const int2 o = sm.recO[t];
+    R.wl = row ? w.z : w.x; R.wr = row ? w.w : w.y; R.wv = __int_as_float(o.y);
+    const float* p = base + o.x + (row ? pitch : 0);
+    R.la = ldg4(p); R.lb = ldg2(p + 32); R.ra = ldg4(p + 64); R.rb = ldg2(p + 96);
+}
+
+template <int ST>
+__device__ __forceinline__ void iter_gather_l3p(const IterParams& prm, const IterSmem& sm, int b, int y, int x0) {
+    constexpr int NPR = WC_NPX * 2;
+    const int lane = threadIdx.x & 31, g = lane & 7, slot = lane >> 3, r = slot & 1, pxpar = slot >> 1;
+    const int V = prm.V, S = ST ? ST : V - 1, H2 = prm.H2, W2 = prm.W2, Wf = W2 / 2, Hf = H2 / 2;
+    const float* base = prm.fea[2] + (size_t)b * V * Hf * Wf * 64 + 4 * g;
+    const int pitch = Wf * 64;
+    int h0, h1;
+    float lh;
+    up_index(y, 0.5f, Hf, h0, h1, lh);
+    float ref[6];
+#pragma unroll
+    for (int h = 1; h >= 0; --h) {          // second pixel pair first: parked in shared memory
+        const int xc = min(x0 + 2 * h + pxpar, W2 - 1);
+        int w0i, w1i;
+        float lw;
+        up_index(xc, 0.5f, Wf, w0i, w1i, lw);
+        const float* pa = base + ((size_t)h0 * Wf + w0i) * 64, *pb = base + ((size_t)h0 * Wf + w1i) * 64;
+        const float* pc = base + ((size_t)h1 * Wf + w0i) * 64, *pd = base + ((size_t)h1 * Wf + w1i) * 64;
+        const float4 a4 = ldg4(pa), b4 = ldg4(pb), c4 = ldg4(pc), d4 = ldg4(pd);
+        const float2 a2 = ldg2(pa + 32), b2 = ldg2(pb + 32), c2 = ldg2(pc + 32), d2 = ldg2(pd + 32);
+        ref[0] = (1.f - lh) * ((1.f - lw) * a4.x + lw * b4.x) + lh * ((1.f - lw) * c4.x + lw * d4.x);
+        ref[1] = (1.f - lh) * ((1.f - lw) * a4.y + lw * b4.y) + lh * ((1.f - lw) * c4.y + lw * d4.y);
+        ref[2] = (1.f - lh) * ((1.f - lw) * a4.z + lw * b4.z) + lh * ((1.f - lw) * c4.z + lw * d4.z);
+        ref[3] = (1.f - lh) * ((1.f - lw) * a4.w + lw * b4.w) + lh * ((1.f - lw) * c4.w + lw * d4.w);
+        ref[4] = (1.f - lh) * ((1.f - lw) * a2.x + lw * b2.x) + lh * ((1.f - lw) * c2.x + lw * d2.x);
+        ref[5] = (1.f - lh) * ((1.f - lw) * a2.y + lw * b2.y) + lh * ((1.f - lw) * c2.y + lw * d2.y);
+        if (h == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) *reinterpret_cast<float2*>(sm.park + (k * 32 + lane) * 2) = make_float2(ref[2 * k], ref[2 * k + 1]);
+        }
+    }
+    float acc = 0.f, wsum = 1e-5f;
+    float a[6];
+    auto tix = [&](int h, int v) { return v * NPR + (2 * h + pxpar) * 2 + r; };
+    Row64 A, Bb;
+    int h = 0, v = 0;
+    fetch_row64(A, sm, base, pitch, tix(0, 0), 0);
+    const int n = 2 * S;
+#pragma unroll (ST ? 64 : 1)
+    for (int i = 0; i < n; ++i) {
+        fetch_row64(Bb, sm, base, pitch, tix(h, v), 1);
+        if (v == 0) {
+            acc = 0.f; wsum = 1e-5f;
+            if (h == 1) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float2 q = *reinterpret_cast<const float2*>(sm.park + (k * 32 + lane) * 2);
+                    ref[2 * k] = q.x; ref[2 * k + 1] = q.y;
+                }
+            }
+        }
+        a[0] = fmaf(A.ra.x, A.wr, A.la.x * A.wl); a[1] = fmaf(A.ra.y, A.wr, A.la.y * A.wl);
+        a[2] = fmaf(A.ra.z, A.wr, A.la.z * A.wl); a[3] = fmaf(A.ra.w, A.wr, A.la.w * A.wl);
+        a[4] = fmaf(A.rb.x, A.wr, A.lb.x * A.wl); a[5] = fmaf(A.rb.y, A.wr, A.lb.y * A.wl);
+        const int hc = h, vc = v;
+        if (++v == S) { v = 0; ++h; }
+        if (i + 1 < n) fetch_row64(A, sm, base, pitch, tix(h, v), 0);
+        a[0] = fmaf(Bb.ra.x, Bb.wr, fmaf(Bb.la.x, Bb.wl, a[0])); a[1] = fmaf(Bb.ra.y, Bb.wr, fmaf(Bb.la.y, Bb.wl, a[1]));
+        a[2] = fmaf(Bb.ra.z, Bb.wr, fmaf(Bb.la.z, Bb.wl, a[2])); a[3] = fmaf(Bb.ra.w, Bb.wr, fmaf(Bb.la.w, Bb.wl, a[3]));
+        a[4] = fmaf(Bb.rb.x, Bb.wr, fmaf(Bb.lb.x, Bb.wl, a[4])); a[5] = fmaf(Bb.rb.y, Bb.wr, fmaf(Bb.lb.y, Bb.wl, a[5]));
+        float dot = a[0] * ref[0];
+#pragma unroll
+        for (int c = 1; c < 6; ++c) dot = fmaf(a[c], ref[c], dot);
+        acc = fmaf(dot, Bb.wv, acc);
+        wsum += Bb.wv;
+        if (vc == S - 1) {
+            const float num = acc * (1.0f / 6.0f);
+            const int x = x0 + 2 * hc + pxpar;
+            if (x < W2)
+                prm.agg[(((size_t)b * IMVS_ITER_SLICES + 8 + r) * ((size_t)H2 * W2) + (size_t)y * W2 + x) * 8 + g] = num / wsum;
+        }
+    }
+}
+
 // Item header: everything a warp needs before phase A of an item, fetched into registers one item ahead
 // (the loads fly while the current item is processed) and parked in shared memory when the item starts.
 template <int ST>
@@ -401,7 +489,7 @@ __device__ __forceinline__ void fetch_header(ItemHeader<ST>& h, const IterParams
 // ST = number of source views when it is 1..8 (gather loops fully unrolled: the software pipeline becomes
 // straight-line code with statically renamed buffers), 0 = any number (rolled loops).
 // NW = warps of the (single) block an SM runs.
-template <int ST, int NW>
+template <int ST, int NW, bool PAD3 = false>
 __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) warpcorr_iter_kernel(const IterParams5 q) {
     extern __shared__ float4 smem4[];
     __shared__ unsigned int next_item;
@@ -448,9 +536,10 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) warpcorr_iter_kerne
             const int b = cur.b, y = cur.y, x0 = cur.x0;
             // itermvs.py:231-235
             if (cur.lvl == 2) {
-                iter_build<2, ST>(prm, sm, b, y, x0, inv_min, inv_max, -32.f, 32.f, 0.f, 0.f);
+                iter_build<2, ST, PAD3>(prm, sm, b, y, x0, inv_min, inv_max, -32.f, 32.f, 0.f, 0.f);
                 __syncwarp();
-                iter_gather_l3<ST>(prm, sm, b, y, x0);
+                if constexpr (PAD3) iter_gather_l3p<ST>(prm, sm, b, y, x0);
+                else iter_gather_l3<ST>(prm, sm, b, y, x0);
             } else if (cur.lvl == 1) {
                 iter_build<1, ST>(prm, sm, b, y, x0, inv_min, inv_max, -8.f, -8.0f / 3, 8.0f / 3, 8.f);
                 __syncwarp();
@@ -470,6 +559,20 @@ __global__ void __launch_bounds__(NW * 32, NW <= 16 ? 2 : 1) warpcorr_iter_kerne
 }
 
 static size_t iter_smem_bytes(int S, int nw) { return (size_t)nw * (16 * S + 8 * S + 48 + 3 * S + S + 1) * sizeof(float4); }
+
+static void (*iter_kernel_padded_for(int S))(const IterParams5) {
+    switch (S) {
+        case 1: return warpcorr_iter_kernel<1, WC_ITER_WARPS, true>;
+        case 2: return warpcorr_iter_kernel<2, WC_ITER_WARPS, true>;
+        case 3: return warpcorr_iter_kernel<3, WC_ITER_WARPS, true>;
+        case 4: return warpcorr_iter_kernel<4, WC_ITER_WARPS, true>;
+        case 5: return warpcorr_iter_kernel<5, WC_ITER_WARPS, true>;
+        case 6: return warpcorr_iter_kernel<6, WC_ITER_WARPS, true>;
+        case 7: return warpcorr_iter_kernel<7, WC_ITER_WARPS, true>;
+        case 8: return warpcorr_iter_kernel<8, WC_ITER_WARPS, true>;
+        default: return warpcorr_iter_kernel<0, WC_ITER_WARPS, true>;
+    }
+}
 
 template <int NW>
 static void (*iter_kernel_for(int S))(const IterParams5) {
@@ -504,6 +607,23 @@ __device__ __forceinline__ float pair_dot(const Taps48& T, int k, const float4& 
     return fmaf(ay, ref.y, ax * ref.x);
 }
 
+// one sample of the padded level-3 pyramid: this lane's own group, 4 taps x (float4 + float2)
+struct Taps64 { float4 a[4]; float2 b[4]; };
+__device__ __forceinline__ void load64(Taps64& T, const float* __restrict__ p, int pitch) {
+    T.a[0] = ldg4(p); T.b[0] = ldg2(p + 32);
+    T.a[1] = ldg4(p + 64); T.b[1] = ldg2(p + 96);
+    T.a[2] = ldg4(p + pitch); T.b[2] = ldg2(p + pitch + 32);
+    T.a[3] = ldg4(p + pitch + 64); T.b[3] = ldg2(p + pitch + 96);
+}
+__device__ __forceinline__ float group_dot(const Taps64& T, const float4& w, const float (&ref)[6]) {
+    float dot = bilerp(T.a[0].x, T.a[1].x, T.a[2].x, T.a[3].x, w) * ref[0];
+    dot = fmaf(bilerp(T.a[0].y, T.a[1].y, T.a[2].y, T.a[3].y, w), ref[1], dot);
+    dot = fmaf(bilerp(T.a[0].z, T.a[1].z, T.a[2].z, T.a[3].z, w), ref[2], dot);
+    dot = fmaf(bilerp(T.a[0].w, T.a[1].w, T.a[2].w, T.a[3].w, w), ref[3], dot);
+    dot = fmaf(bilerp(T.b[0].x, T.b[1].x, T.b[2].x, T.b[3].x, w), ref[4], dot);
+    return fmaf(bilerp(T.b[0].y, T.b[1].y, T.b[2].y, T.b[3].y, w), ref[5], dot);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: init plane sweep at level 3 (C = 48), per-view group correlation.  One warp = one pixel; its D hypotheses in
 // chunks of 32: phase A, lane = hypothesis (projection, clamped 2x2 tap base, permuted bilinear weights with the
@@ -517,6 +637,7 @@ __device__ __forceinline__ float pair_dot(const Taps48& T, int k, const float4& 
 // the sparser spacing of 1920x1056 -- it was removed.
 //   grid (ceil(W3/2), ceil(H3/2), B), block 128 (4 warps = 2 x 2 pixels)
 // ---------------------------------------------------------------------------------------------
+template <bool PAD3>
 __global__ void __launch_bounds__(WC_WARPS * 32, 6)
 warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ rt3,
                      const float* __restrict__ depth_min, const float* __restrict__ depth_max,
@@ -539,13 +660,21 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
     const int g = lane & 7, slot = lane >> 3;
     const int P3 = H3 * W3, p = y * W3 + x;
     const float inv_min = samples ? 0.f : 1.0f / depth_min[b], inv_max = samples ? 0.f : 1.0f / depth_max[b];
-    const float* fb = fea3 + (size_t)b * V * P3 * 48;
-    const int pitch = W3 * 48;
+    constexpr int CS = PAD3 ? 64 : 48;          // floats per texel
+    const float* fb = fea3 + (size_t)b * V * P3 * CS;
+    const int pitch = W3 * CS;
     float4* recW = s_recW[warp];
     int* recO = s_recO[warp];
     float2 ref[3];
+    float refp[6];
+    if constexpr (PAD3) {
+        const float4 r4 = ldg4(fb + (size_t)p * 64 + 4 * g);
+        const float2 r2 = ldg2(fb + (size_t)p * 64 + 32 + 4 * g);
+        refp[0] = r4.x; refp[1] = r4.y; refp[2] = r4.z; refp[3] = r4.w; refp[4] = r2.x; refp[5] = r2.y;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) ref[k] = ldg2(fb + (size_t)p * 48 + 2 * g + 16 * k);
+        for (int k = 0; k < 3; ++k) ref[k] = ldg2(fb + (size_t)p * 48 + 2 * g + 16 * k);
+    }
 
     for (int d0 = 0; d0 < D; d0 += 32) {
         const int dc = min(d0 + lane, D - 1);
@@ -557,13 +686,25 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
             const Tap tp = project_tap(sP + v * 12, (float)x, (float)y, depth, (float)W3, (float)H3, W3, H3);
             float4 w;
             int off;
-            make_record(tp, W3, H3, 48, v + 1, w, off);
+            make_record(tp, W3, H3, CS, v + 1, w, off);
             __syncwarp();                               // the previous view's records have been consumed
             recW[lane] = w;
             recO[lane] = off;
             __syncwarp();
-            const float* src = fb + 2 * g;
             float* out = corr + ((((size_t)b * S + v) * D + d0) * P3 + p) * 8 + g;
+            if constexpr (PAD3) {
+                const float* src = fb + 4 * g;
+#pragma unroll 2
+                for (int dd = 0; dd < nd; dd += 4) {
+                    const int t = dd + slot;
+                    const float4 wt = recW[t];
+                    Taps64 T;
+                    load64(T, src + recO[t], pitch);
+                    const float c = group_dot(T, wt, refp) * (1.0f / 6.0f);
+                    if (t < nd) out[(size_t)t * P3 * 8] = c;
+                }
+            } else {
+            const float* src = fb + 2 * g;
 #pragma unroll 2
             for (int dd = 0; dd < nd; dd += 4) {
                 const int t = dd + slot;
@@ -576,8 +717,20 @@ warpcorr_init_kernel(const float* __restrict__ fea3, const float* __restrict__ r
                 const float c = regroup48(acc, lane) * (1.0f / 6.0f);
                 if (t < nd) out[(size_t)t * P3 * 8] = c;
             }
+            }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fea3 [B][V][P3][48] -> padded [B][V][P3][64]: thread = (texel, correlation group g): channels 6g..6g+5 go to floats
+// 4g..4g+3 and 32+4g, 32+4g+1 of the texel, floats 32+4g+2, +3 are zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void pad_level3_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t texels) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < texels * 8) pad_level3_item(src, dst, t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -615,29 +768,49 @@ using namespace imvs;
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const float* depth_min, const float* depth_max,
-                                  const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream) {
+static int warpcorr_init_impl(bool pad3, const float* fea3, const float* rt3, const float* depth_min, const float* depth_max,
+                              const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream) {
     IMVS_REQUIRE(fea3 && rt3 && corr && (depth_samples || (depth_min && depth_max)), "warpcorr_init: null pointer");
     IMVS_REQUIRE(B >= 1 && V >= 2 && V - 1 <= IMVS_MAX_VIEWS, "warpcorr_init: need 1..%d source views (V=%d)", IMVS_MAX_VIEWS, V);
     IMVS_REQUIRE(H3 >= 2 && W3 >= 2 && D >= 2, "warpcorr_init: bad shape H3=%d W3=%d D=%d", H3, W3, D);
-    IMVS_REQUIRE((double)V * H3 * W3 * 48 < 2147483647.0, "warpcorr_init: one batch item's pyramid exceeds 2^31 elements");
+    IMVS_REQUIRE((double)V * H3 * W3 * 64 < 2147483647.0, "warpcorr_init: one batch item's pyramid exceeds 2^31 elements");
     IMVS_REQUIRE(aligned16(fea3) && aligned16(corr), "warpcorr_init: feature/corr pointers must be 16-byte aligned");
     // source views per block (IMVS_TUNE_WCI_VPER, 0 = all of them in one block)
     const int S = V - 1, vt = tune("WCI_VPER", 0), vper = vt >= 1 && vt < S ? vt : S;
     dim3 grid(cdiv(W3, 2), cdiv(H3, 2), B * cdiv(S, vper));
     IMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "warpcorr_init: grid too large");
     ApiScope api_;
-    IMVS_CUDA(launch_k(warpcorr_init_kernel, grid, dim3(WC_WARPS * 32), 0, (cudaStream_t)stream, fea3, rt3, depth_min, depth_max,
-                       depth_samples, corr, B, V, H3, W3, D, vper));
+    IMVS_CUDA(launch_k(pad3 ? warpcorr_init_kernel<true> : warpcorr_init_kernel<false>, grid, dim3(WC_WARPS * 32), 0, (cudaStream_t)stream,
+                       fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, vper));
     return 0;
 }
 
-extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
-                                  const float* rt1, const float* rt2, const float* rt3,
-                                  const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
-                                  const float* depth_min, const float* depth_max,
-                                  const float* samples1, const float* samples2, const float* samples3, float* agg,
-                                  int B, int V, int H2, int W2, void* stream) {
+extern "C" int imvs_warpcorr_init(const float* fea3, const float* rt3, const float* depth_min, const float* depth_max,
+                                  const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream) {
+    return warpcorr_init_impl(false, fea3, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, stream);
+}
+
+extern "C" int imvs_warpcorr_init_padded(const float* fea3p, const float* rt3, const float* depth_min, const float* depth_max,
+                                         const float* depth_samples, float* corr, int B, int V, int H3, int W3, int D, void* stream) {
+    return warpcorr_init_impl(true, fea3p, rt3, depth_min, depth_max, depth_samples, corr, B, V, H3, W3, D, stream);
+}
+
+extern "C" int imvs_pad_level3(const float* fea3, float* fea3p, int B, int V, int H3, int W3, void* stream) {
+    IMVS_REQUIRE(fea3 && fea3p && B >= 1 && V >= 1 && H3 >= 1 && W3 >= 1, "pad_level3: bad argument");
+    IMVS_REQUIRE(aligned16(fea3) && aligned16(fea3p), "pad_level3: pointers must be 16-byte aligned");
+    const size_t texels = (size_t)B * V * H3 * W3;
+    IMVS_REQUIRE(texels * 8 < (size_t)2147483647 * 256, "pad_level3: too many texels");
+    ApiScope api_;
+    IMVS_CUDA(launch_k(pad_level3_kernel, dim3((unsigned)((texels * 8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, fea3, fea3p, texels));
+    return 0;
+}
+
+static int warpcorr_iter_impl(bool pad3, const float* fea1, const float* fea2, const float* fea3,
+                              const float* rt1, const float* rt2, const float* rt3,
+                              const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
+                              const float* depth_min, const float* depth_max,
+                              const float* samples1, const float* samples2, const float* samples3, float* agg,
+                              int B, int V, int H2, int W2, void* stream) {
     const bool explicit_samples = samples1 && samples2 && samples3;
     IMVS_REQUIRE(fea1 && fea2 && fea3 && rt1 && rt2 && rt3 && vw2 && agg, "warpcorr_iter: null pointer");
     IMVS_REQUIRE(explicit_samples || (!samples1 && !samples2 && !samples3 && nd && depth_min && depth_max),
@@ -660,8 +833,10 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     // 16 warps x 2 blocks (both <= 64 registers: 32 resident warps per SM) -- profiles/ps_experiments_r02.md section 5
     // 26 / 28 warps (72 registers): 104 items per SM at 640x512 are 4 full rounds instead of 4.33
     const int nwt = tune("WC_WARPS", WC_ITER_WARPS);
-    const int nw = nwt == 32 || nwt == 16 || nwt == 26 || nwt == 28 ? nwt : WC_ITER_WARPS;
-    auto kern = nw == 32 ? iter_kernel_for<32>(S) : nw == 16 ? iter_kernel_for<16>(S) : nw == 26 ? iter_kernel_for<26>(S)
+    const int nw0 = nwt == 32 || nwt == 16 || nwt == 26 || nwt == 28 ? nwt : WC_ITER_WARPS;
+    const int nw = pad3 ? WC_ITER_WARPS : nw0;       // the padded variant is built for the default block shape only
+    auto kern = pad3 ? iter_kernel_padded_for(S)
+              : nw == 32 ? iter_kernel_for<32>(S) : nw == 16 ? iter_kernel_for<16>(S) : nw == 26 ? iter_kernel_for<26>(S)
               : nw == 28 ? iter_kernel_for<28>(S) : iter_kernel_for<WC_ITER_WARPS>(S);
     const size_t smem = iter_smem_bytes(S, nw);
     int dev = 0, sms = 0;
@@ -680,6 +855,26 @@ extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const fl
     ApiScope api_;
     IMVS_CUDA(launch_k(kern, dim3(blocks), dim3(nw * 32), smem, (cudaStream_t)stream, q));
     return 0;
+}
+
+extern "C" int imvs_warpcorr_iter(const float* fea1, const float* fea2, const float* fea3,
+                                  const float* rt1, const float* rt2, const float* rt3,
+                                  const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
+                                  const float* depth_min, const float* depth_max,
+                                  const float* samples1, const float* samples2, const float* samples3, float* agg,
+                                  int B, int V, int H2, int W2, void* stream) {
+    return warpcorr_iter_impl(false, fea1, fea2, fea3, rt1, rt2, rt3, nd, nd_batch_stride, nd_pixel_stride, vw2, depth_min, depth_max,
+                              samples1, samples2, samples3, agg, B, V, H2, W2, stream);
+}
+
+extern "C" int imvs_warpcorr_iter_padded(const float* fea1, const float* fea2, const float* fea3p,
+                                         const float* rt1, const float* rt2, const float* rt3,
+                                         const float* nd, size_t nd_batch_stride, size_t nd_pixel_stride, const float* vw2,
+                                         const float* depth_min, const float* depth_max,
+                                         const float* samples1, const float* samples2, const float* samples3, float* agg,
+                                         int B, int V, int H2, int W2, void* stream) {
+    return warpcorr_iter_impl(true, fea1, fea2, fea3p, rt1, rt2, rt3, nd, nd_batch_stride, nd_pixel_stride, vw2, depth_min, depth_max,
+                              samples1, samples2, samples3, agg, B, V, H2, W2, stream);
 }
 
 extern "C" int imvs_aggregate_init(const float* corr, const float* vw3, float* agg, int B, int S, int D, int P3, void* stream) {

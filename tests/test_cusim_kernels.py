@@ -36,6 +36,9 @@ def sim():
         "imvs_warpcorr_init": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
         "imvs_aggregate_init": [vp, vp, vp, ci, ci, ci, ci, vp],
         "imvs_warpcorr_iter": [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp],
+        "imvs_pad_level3": [vp, vp, ci, ci, ci, ci, vp],
+        "imvs_warpcorr_init_padded": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
+        "imvs_warpcorr_iter_padded": [vp, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -62,6 +65,18 @@ def maxerr(a, b):
 def stack_views(ref, srcs):
     """NCHW per-view maps -> [B][V][H][W][C] (view 0 = reference), the layout of the fused kernels."""
     return f32(torch.stack([ref] + list(srcs), dim=1).permute(0, 1, 3, 4, 2))
+
+
+def pad_level3(lib, fea3):
+    """imvs_pad_level3: [B][V][H3][W3][48] -> 64 floats per texel; also checks the documented positions."""
+    b, v, h3, w3, _ = fea3.shape
+    out = torch.full((b, v, h3, w3, 64), float("nan"))
+    ok(lib, lib.imvs_pad_level3(P(fea3), P(out), b, v, h3, w3, None))
+    for g in range(8):
+        assert torch.equal(out[..., 4 * g:4 * g + 4], fea3[..., 6 * g:6 * g + 4])
+        assert torch.equal(out[..., 32 + 4 * g:32 + 4 * g + 2], fea3[..., 6 * g + 4:6 * g + 6])
+        assert float(out[..., 32 + 4 * g + 2:32 + 4 * g + 4].abs().max()) == 0.0
+    return out
 
 
 def compose(lib, ref_proj, src_projs):
@@ -110,8 +125,9 @@ def test_differentiable_warping_source_on_cpu(sim, stage_kats, tag):
     assert maxerr(gfea, f_cpu.grad) < 2e-4 * max(1.0, float(f_cpu.grad.abs().max()))
 
 
+@pytest.mark.parametrize("padded", [False, True])
 @pytest.mark.parametrize("batch,n_src,d", [(1, 2, 32), (2, 3, 8), (1, 1, 48)])
-def test_warpcorr_init_source_on_cpu(sim, batch, n_src, d):
+def test_warpcorr_init_source_on_cpu(sim, batch, n_src, d, padded):
     """warpcorr_init_kernel + aggregate_init_kernel against the oracle's warp -> group correlation -> aggregation,
     with explicit samples (incl. z <= 0.01 substitutions) and with in-kernel hypothesis generation."""
     ref, srcs, rp, sp, s = feature_inputs(96, 64, n_src, batch, seed=11)       # level 3: 12 x 8
@@ -120,6 +136,9 @@ def test_warpcorr_init_source_on_cpu(sim, batch, n_src, d):
     inv_max = (1.0 / s["depth_max"]).view(batch, 1, 1, 1)
     ds = O.initial_depth_samples(inv_min, inv_max, d, h3, w3)
     fea3 = stack_views(ref["level3"], srcs["level3"])
+    init_fn = sim.imvs_warpcorr_init
+    if padded:                    # the same kernel on the 256-byte-per-texel copy of the pyramid
+        fea3, init_fn = pad_level3(sim, fea3), sim.imvs_warpcorr_init_padded
     rt3 = compose(sim, rp["level3"], sp["level3"])
     dmin, dmax = f32(s["depth_min"]), f32(s["depth_max"])
 
@@ -128,13 +147,13 @@ def test_warpcorr_init_source_on_cpu(sim, batch, n_src, d):
                             for src, p in zip(srcs["level3"], sp["level3"])], dim=1)      # [B,S,G,D,H,W]
 
     corr = torch.full((batch, n_src, d, h3 * w3, 8), float("nan"))
-    ok(sim, sim.imvs_warpcorr_init(P(fea3), P(rt3), P(dmin), P(dmax), None, P(corr), batch, n_src + 1, h3, w3, d, None))
+    ok(sim, init_fn(P(fea3), P(rt3), P(dmin), P(dmax), None, P(corr), batch, n_src + 1, h3, w3, d, None))
     got = corr.view(batch, n_src, d, h3, w3, 8).permute(0, 1, 5, 2, 3, 4)
     want = want_for(ds)
     assert maxerr(got, want) < 1e-4
     ds2 = ds.clone()
     ds2[:, 3, :2] = -10.0
-    ok(sim, sim.imvs_warpcorr_init(P(fea3), P(rt3), None, None, P(f32(ds2)), P(corr), batch, n_src + 1, h3, w3, d, None))
+    ok(sim, init_fn(P(fea3), P(rt3), None, None, P(f32(ds2)), P(corr), batch, n_src + 1, h3, w3, d, None))
     want2 = want_for(ds2)
     assert maxerr(corr.view(batch, n_src, d, h3, w3, 8).permute(0, 1, 5, 2, 3, 4), want2) < 1e-4
     # aggregation (itermvs.py:59-69)
@@ -151,7 +170,8 @@ def test_warpcorr_init_source_on_cpu(sim, batch, n_src, d):
 @pytest.mark.parametrize("batch,n_src,width,height,sms", [(1, 4, 96, 64, 3), (2, 3, 64, 64, 1), (1, 1, 64, 32, 64),
                                                           (1, 7, 64, 32, 2), (1, 9, 64, 32, 3), (1, 2, 96, 96, 5),
                                                           (1, 16, 64, 32, 3)])       # 16 = IMVS_MAX_VIEWS
-def test_warpcorr_iter_source_on_cpu(sim, batch, n_src, width, height, sms, monkeypatch):
+@pytest.mark.parametrize("padded", [False, True])
+def test_warpcorr_iter_source_on_cpu(sim, batch, n_src, width, height, sms, monkeypatch, padded):
     monkeypatch.setenv("CUSIM_SMS", str(sms))
     ref, srcs, rp, sp, s = feature_inputs(width, height, n_src, batch, seed=12)
     h2, w2 = ref["level2"].shape[2:]
@@ -165,6 +185,9 @@ def test_warpcorr_iter_source_on_cpu(sim, batch, n_src, width, height, sms, monk
     aggs = _aggregated_only(ref, srcs, rp, sp, samples, vw)
     want = torch.cat(aggs, dim=2)                                       # [B,8,10,H2,W2]
     feas = [stack_views(ref[f"level{l}"], srcs[f"level{l}"]) for l in (1, 2, 3)]
+    iter_fn = sim.imvs_warpcorr_iter
+    if padded:
+        feas[2], iter_fn = pad_level3(sim, feas[2]), sim.imvs_warpcorr_iter_padded
     rts = [compose(sim, rp[f"level{l}"], sp[f"level{l}"]) for l in (1, 2, 3)]
     dmin, dmax = f32(s["depth_min"]), f32(s["depth_max"])
     ndc = f32(nd)
@@ -172,10 +195,10 @@ def test_warpcorr_iter_source_on_cpu(sim, batch, n_src, width, height, sms, monk
     def run(explicit):
         agg = torch.full((batch, 10, h2 * w2, 8), float("nan"))
         smp = [f32(samples[f"level{l}"]) for l in (1, 2, 3)] if explicit else [None] * 3
-        ok(sim, sim.imvs_warpcorr_iter(P(feas[0]), P(feas[1]), P(feas[2]), P(rts[0]), P(rts[1]), P(rts[2]),
-                                       None if explicit else P(ndc), h2 * w2, 1, P(f32(vw)),
-                                       None if explicit else P(dmin), None if explicit else P(dmax),
-                                       P(smp[0]), P(smp[1]), P(smp[2]), P(agg), batch, n_src + 1, h2, w2, None))
+        ok(sim, iter_fn(P(feas[0]), P(feas[1]), P(feas[2]), P(rts[0]), P(rts[1]), P(rts[2]),
+                        None if explicit else P(ndc), h2 * w2, 1, P(f32(vw)),
+                        None if explicit else P(dmin), None if explicit else P(dmax),
+                        P(smp[0]), P(smp[1]), P(smp[2]), P(agg), batch, n_src + 1, h2, w2, None))
         return agg.view(batch, 10, h2, w2, 8).permute(0, 4, 1, 2, 3)
 
     first = run(True)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--save", default=None)
     ap.add_argument("--check", default=None)
+    ap.add_argument("--pad3", action="store_true", help="level 3 from the padded copy (imvs_pad_level3 + the *_padded entry points)")
     args = ap.parse_args()
     from itermvs_b200 import _lib, ops
     from itermvs_b200.synthetic import make_sample, plane_depth_map, DEPTH_MIN, DEPTH_MAX
@@ -56,13 +57,22 @@ def main():
     corr = torch.zeros(1, S, D, H3 * W3, 8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
+    f3 = fea[2]
+    iter_fn, init_fn = L.imvs_warpcorr_iter, L.imvs_warpcorr_init
+    if args.pad3:
+        f3 = torch.empty(1, V, H // 8, W // 8, 64, device=dev)
+        iter_fn, init_fn = L.imvs_warpcorr_iter_padded, L.imvs_warpcorr_init_padded
+
+    def run_pad():
+        _lib.check(L.imvs_pad_level3(fea[2].data_ptr(), f3.data_ptr(), 1, V, H // 8, W // 8, st), "pad_level3")
+
     def run_iter():
-        _lib.check(L.imvs_warpcorr_iter(fea[0].data_ptr(), fea[1].data_ptr(), fea[2].data_ptr(), rts[0].data_ptr(), rts[1].data_ptr(),
+        _lib.check(iter_fn(fea[0].data_ptr(), fea[1].data_ptr(), f3.data_ptr(), rts[0].data_ptr(), rts[1].data_ptr(),
                                         rts[2].data_ptr(), nd.data_ptr(), H2 * W2, 1, vw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(),
                                         None, None, None, agg.data_ptr(), 1, V, H2, W2, st), "warpcorr_iter")
 
     def run_init():
-        _lib.check(L.imvs_warpcorr_init(fea[2].data_ptr(), rts[2].data_ptr(), dmin.data_ptr(), dmax.data_ptr(), None,
+        _lib.check(init_fn(f3.data_ptr(), rts[2].data_ptr(), dmin.data_ptr(), dmax.data_ptr(), None,
                                         corr.data_ptr(), 1, V, H3, W3, D, st), "warpcorr_init")
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -86,6 +96,9 @@ def main():
 
     out = {"tag": args.tag, "config": args.config, "noise": args.noise,
            "env": {k: v for k, v in os.environ.items() if k.startswith("IMVS_")}}
+    if args.pad3:
+        run_pad()
+        out["pad_warm"] = timed(run_pad, False)
     out["iter_warm"] = timed(run_iter, False)
     out["iter_cold"] = timed(run_iter, True)
     out["init_warm"] = timed(run_init, False)
