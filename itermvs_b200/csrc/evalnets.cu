@@ -480,8 +480,14 @@ extern "C" int imvs_pixel_view_weight(const imvs_weights* w, const float* corr, 
     ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
     const int N = B * S * D, P3 = H3 * W3;
-    IMVS_TRY((mma_conv<8, 16, 2, 4, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), EpiPvw{logits, w->pvw_conv1, w->pvw_conv1_b, H3, W3},
-                                             WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 8), N, 16, H3, W3, 1, st)));
+    // IMVS_TUNE_PVW_TILE: rows per CTA = 8 (0: 4 warps x 2 row-tiles, 5 120 CTAs at 640x512 / 4 src / D = 32), 16 as 4 x 4 (1, default:
+    // 47.6 -> 44.3 us, gpurun call r2c56), 16 as 8 x 2 (2: 48.0 us), 32 as 8 x 4 (3: 44.4-45.1 us)
+    const int pt = tune("PVW_TILE", 1);
+    const EpiPvw ep{logits, w->pvw_conv1, w->pvw_conv1_b, H3, W3};
+    if (pt == 1) IMVS_TRY((mma_conv<8, 16, 4, 4, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), ep, WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 16), N, 16, H3, W3, 1, st)));
+    else if (pt == 2) IMVS_TRY((mma_conv<8, 16, 2, 8, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), ep, WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 16), N, 16, H3, W3, 1, st)));
+    else if (pt == 3) IMVS_TRY((mma_conv<8, 16, 4, 8, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), ep, WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 32), N, 16, H3, W3, 1, st)));
+    else IMVS_TRY((mma_conv<8, 16, 2, 4, 1, true>("pvw.conv", in_nhwc(corr, H3, W3, 8), ep, WSets::single(w->pvw_conv0), conv_tables(3, 1, 1, 8), N, 16, H3, W3, 1, st)));
     IMVS_CUDA(launch_k(pvw_reduce_kernel, dim3(cdiv(B * S * P3, 128)), dim3(128), 0, st, (const float*)logits, vw3, B * S, D, P3));
     return launch_upsample2x_nhwc(vw3, vw2, B * S, H3, W3, 1, false, st);
 }

@@ -33,6 +33,7 @@ for name, val in SWEEPS:
         d = json.loads(r.stdout.strip().splitlines()[-1])
         st = d["stage_ms"]
         print(f"{label:24s} {d['value']:7.1f} refs/s  fnet {st['featurenet']:.4f} gru {st['gru']:.4f} head {st['head']:.4f} "
-              f"corrnet {st['corrnet']:.4f} hinit {st['hidden_init']:.4f}", flush=True)
+              f"corrnet {st['corrnet']:.4f} hinit {st['hidden_init']:.4f} pvw {st['pixel_view_weight']:.4f} ups {st['upsample']:.4f} "
+              f"single {d['single_stream']['value']:.1f} e2e {d['e2e']['value']:.1f}", flush=True)
     except Exception as e:
         print(label, "FAILED", e, r.stderr[-400:], flush=True)
