@@ -314,8 +314,13 @@ __global__ void init_expectation_kernel(const float* __restrict__ corr, size_t b
 
 template <int D>
 static int hinit_conv0(const imvs_weights* w, const float* corr, float* t, int B, int H3, int W3, cudaStream_t st) {
-    return mma_conv<D, 64, 2, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), EpiNHWC{t, nullptr, nullptr, H3, W3, 64, 64, 1},
-                                           WSets::single(w->hinit_conv0), conv_tables(3, 1, 1, 8), B, 64, H3, W3, 1, st);
+    // the 1/8-resolution map is small (80 x 64 at 640x512: 40 CTAs of 8 rows x 16 columns x 64 couts, each with 864 dependent MMAs per
+    // warp): IMVS_TUNE_HINIT_TILE=1: 4-row tiles (80 CTAs), 2: 4-row tiles x two 32-cout blocks (160 CTAs)
+    const EpiNHWC e{t, nullptr, nullptr, H3, W3, 64, 64, 1};
+    const int ht = tune("HINIT_TILE", 2);      // default 2: 29.6 -> 23.7 us (gpurun call r2c58)
+    if (ht == 1) return mma_conv<D, 64, 1, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), e, WSets::single(w->hinit_conv0), conv_tables(3, 1, 1, 4), B, 64, H3, W3, 1, st);
+    if (ht == 2) return mma_conv<D, 32, 1, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), e, WSets::single(w->hinit_conv0), conv_tables(3, 1, 1, 4), B, 64, H3, W3, 2, st);
+    return mma_conv<D, 64, 2, 4, 1, false>("hidden_init.conv0", in_nhwc(corr, H3, W3, D), e, WSets::single(w->hinit_conv0), conv_tables(3, 1, 1, 8), B, 64, H3, W3, 1, st);
 }
 
 }  // namespace imvs
@@ -509,8 +514,11 @@ extern "C" int imvs_hidden_init(const imvs_weights* w, const float* corr, float*
         case 64: IMVS_TRY(hinit_conv0<64>(w, corr, t, B, H3, W3, st)); break;
         default: return fail("hidden_init: D=%d not supported (8, 16, 32, 48 or 64 hypotheses)", D);
     }
-    IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("hidden_init.fc", in_nhwc(t, H3, W3, 64), EpiNHWC{u, w->hinit_fc_b, nullptr, H3, W3, 32, 32, 0},
-                                              WSets::single(w->hinit_fc), conv_tables(1, 1, 1, 8), B, 32, H3, W3, 1, st)));
+    const EpiNHWC efc{u, w->hinit_fc_b, nullptr, H3, W3, 32, 32, 0};
+    if (tune("HINIT_TILE", 2) >= 1)
+        IMVS_TRY((mma_conv<64, 32, 1, 4, 1, true>("hidden_init.fc", in_nhwc(t, H3, W3, 64), efc, WSets::single(w->hinit_fc), conv_tables(1, 1, 1, 4), B, 32, H3, W3, 1, st)));
+    else
+        IMVS_TRY((mma_conv<64, 32, 2, 4, 1, true>("hidden_init.fc", in_nhwc(t, H3, W3, 64), efc, WSets::single(w->hinit_fc), conv_tables(1, 1, 1, 8), B, 32, H3, W3, 1, st)));
     return launch_upsample2x_nhwc(u, hidden, B, H3, W3, 32, true, st);
 }
 

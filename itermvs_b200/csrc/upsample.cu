@@ -126,9 +126,19 @@ extern "C" int imvs_upsample_outputs(const imvs_weights* w, const float* ref_fea
     IMVS_REQUIRE(nd_pixel_stride >= 1, "upsample_outputs: nd_pixel_stride must be >= 1");
     ApiScope api_;
     cudaStream_t st = (cudaStream_t)stream;
-    IMVS_TRY((mma_conv<32, 64, 2, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride),
-                                               EpiNHWC{scratch, nullptr, nullptr, H2, W2, 64, 64, 1}, WSets::single(w->ups_conv0),
-                                               conv_tables(3, 1, 1, 8), B, 64, H2, W2, 1, st)));
+    // IMVS_TUNE_UPS_TILE: 0 = 8-row tiles x 64 couts (160 CTAs at 640x512, 864 dependent MMAs per warp), 1 = 4-row tiles (320 CTAs),
+    // 2 = 4-row tiles x two 32-cout blocks (640 CTAs)
+    const EpiNHWC e0{scratch, nullptr, nullptr, H2, W2, 64, 64, 1};
+    const int ut = tune("UPS_TILE", 2);          // default 2: stage 50.7 -> 46.6 us (gpurun call r2c58)
+    if (ut == 1)
+        IMVS_TRY((mma_conv<32, 64, 1, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride), e0, WSets::single(w->ups_conv0),
+                                                   conv_tables(3, 1, 1, 4), B, 64, H2, W2, 1, st)));
+    else if (ut == 2)
+        IMVS_TRY((mma_conv<32, 32, 1, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride), e0, WSets::single(w->ups_conv0),
+                                                   conv_tables(3, 1, 1, 4), B, 64, H2, W2, 2, st)));
+    else
+        IMVS_TRY((mma_conv<32, 64, 2, 4, 1, false>("upsample.conv0", in_nhwc(ref_fea2, H2, W2, 32, ref_batch_stride), e0, WSets::single(w->ups_conv0),
+                                                   conv_tables(3, 1, 1, 8), B, 64, H2, W2, 1, st)));
     UpsParams prm;
     prm.t = scratch; prm.fc = w->ups_fc; prm.nd = nd; prm.nd_bstride = nd_batch_stride; prm.nd_pstride = nd_pixel_stride;
     prm.depth_min = depth_min; prm.depth_max = depth_max; prm.depth_up = depth_up;

@@ -867,6 +867,50 @@ def test_launch_granularity_switches_are_bit_identical(dev, model, monkeypatch, 
             assert torch.equal(outs[0][k], outs[1][k]), (switch, value, k)
 
 
+@pytest.mark.parametrize("width,height,n_src,d", [(160, 128, 2, 8), (320, 256, 3, 48), (96, 64, 9, 32)])
+def test_padded_level3_entry_points(dev, width, height, n_src, d):
+    """imvs_pad_level3 + imvs_warpcorr_init_padded / imvs_warpcorr_iter_padded (the estimator's default since round 2: level 3 read
+    from a copy with 256 bytes per texel, include/itermvs_b200.h) against the 48-channel entry points on the same inputs: the padded
+    copy holds exactly the documented floats, the outputs agree to fp32 summation order."""
+    from itermvs_b200 import _lib, ops
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    V = n_src + 1
+    fea = [torch.randn(2, V, height // s_, width // s_, c, generator=g).to(dev) for s_, c in ((2, 16), (4, 32), (8, 48))]
+    smp = make_sample(width, height, n_src=n_src, batch=2, seed=3, scene="noise")
+    rts = [ops.compose_projections(smp["proj_matrices"][f"level_{l}"].float().to(dev)) for l in (1, 2, 3)]
+    H2, W2, H3, W3 = height // 4, width // 4, height // 8, width // 8
+    nd = torch.rand(2, H2 * W2, generator=g).to(dev)
+    vw = torch.rand(2, n_src, H2 * W2, generator=g).to(dev)
+    dmin, dmax = smp["depth_min"].float().to(dev), smp["depth_max"].float().to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    f3p = torch.full((2, V, H3, W3, 64), float("nan"), device=dev)
+    _lib.check(L.imvs_pad_level3(fea[2].data_ptr(), f3p.data_ptr(), 2, V, H3, W3, st), "pad_level3")
+    for grp in range(8):
+        assert torch.equal(f3p[..., 4 * grp:4 * grp + 4], fea[2][..., 6 * grp:6 * grp + 4])
+        assert torch.equal(f3p[..., 32 + 4 * grp:34 + 4 * grp], fea[2][..., 6 * grp + 4:6 * grp + 6])
+        assert float(f3p[..., 34 + 4 * grp:36 + 4 * grp].abs().max()) == 0.0
+    outs = []
+    for padded in (False, True):
+        f3 = f3p if padded else fea[2]
+        init_fn = L.imvs_warpcorr_init_padded if padded else L.imvs_warpcorr_init
+        iter_fn = L.imvs_warpcorr_iter_padded if padded else L.imvs_warpcorr_iter
+        corr = torch.full((2, n_src, d, H3 * W3, 8), float("nan"), device=dev)
+        agg = torch.full((2, 10, H2 * W2, 8), float("nan"), device=dev)
+        _lib.check(init_fn(f3.data_ptr(), rts[2].data_ptr(), dmin.data_ptr(), dmax.data_ptr(), None, corr.data_ptr(), 2, V, H3, W3, d, st),
+                   "warpcorr_init")
+        _lib.check(iter_fn(fea[0].data_ptr(), fea[1].data_ptr(), f3.data_ptr(), rts[0].data_ptr(), rts[1].data_ptr(), rts[2].data_ptr(),
+                           nd.data_ptr(), H2 * W2, 1, vw.data_ptr(), dmin.data_ptr(), dmax.data_ptr(), None, None, None, agg.data_ptr(),
+                           2, V, H2, W2, st), "warpcorr_iter")
+        torch.cuda.synchronize()
+        outs.append((corr, agg))
+    for a, b, name in ((outs[0][0], outs[1][0], "corr"), (outs[0][1], outs[1][1], "agg")):
+        assert torch.isfinite(b).all()
+        print(name, "padded vs 48-channel: max abs diff", maxerr(a, b), "of", float(a.abs().max()))
+        assert maxerr(a, b) < 2e-6 * max(1.0, float(a.abs().max()))
+    assert torch.equal(outs[0][1][:, :8], outs[1][1][:, :8])          # levels 1 and 2 run the same code: bit-identical
+
+
 def test_image_pyramid_and_prefetch_loader_on_device(dev, model, tmp_path):
     """f-4 on the GPU: (1) `imvs_image_pyramid_u8` -- raw 8-bit image -> 2 x / 255 - 1 -> cv2.resize(INTER_LINEAR) -> levels 1..3 --
     against OpenCV (1 ulp of the value: its SIMD / IPP paths may fuse a product); (2) `io.PrefetchLoader`: PNG files decoded on
